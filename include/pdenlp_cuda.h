@@ -1,0 +1,219 @@
+/*
+ * pdenlp_cuda.h — C ABI of libpdenlp_cuda.so
+ *
+ * B200-native (sm_100a, FP64) replacement for the derivative-evaluation hot
+ * path of PDENLPModels.jl: the NLPModels callbacks of a GridapPDENLPModel.
+ * Citations are relative to /root/reference (PDENLPModels.jl v0.3.5).
+ *
+ * The reference has no FFI for this path (it is pure Julia); every entry point
+ * below names the Julia method whose *body* it replaces.  The Julia wrapper
+ * (julia/PDENLPCuda.jl) keeps the method signatures, the
+ * @lencheck DimensionError checks and the Counters bookkeeping on its side and
+ * issues exactly one ccall per callback.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++/torch types cross the boundary.
+ *   - every function returns an int status: PDENLP_OK (0) or a negative
+ *     PDENLP_E* code; pdenlp_last_error() returns a thread-local message.
+ *   - all floating point is IEEE FP64; all dof ids are 1-based, signed int32
+ *     (negative id = Dirichlet dof, -id indexes the Dirichlet-value array —
+ *     Gridap's PosNegReindex, src/PDENLPModels.jl:27-43).
+ *   - x layout: x = [kappa (nparam) ; y free dofs (nfree_y) ; u free dofs (nfree_u)]
+ *     (src/GridapPDENLPModel.jl:249-251, src/util_functions.jl:9-17).
+ *   - vector arguments of the callbacks are DEVICE pointers unless the model was
+ *     created with PDENLP_MEM_HOST, in which case they are HOST pointers and the
+ *     library stages them (pinned bounce buffers, copies inside the call).
+ *   - a model handle owns the cells [0, ncells) of the arrays it was created
+ *     with.  Multi-GPU: one handle per GPU over a contiguous cell slab; the
+ *     COO value streams of the slabs concatenate to the global streams in rank
+ *     order, so jac_coord/hess_coord need no communication.
+ *   - callbacks on one handle are not re-entrant (same as the reference, whose
+ *     model owns its workspace: src/GridapPDENLPModel.jl:56-73).
+ *   - there is NO CPU fallback: every entry point fails with PDENLP_ECUDA when
+ *     no sm_100 device / driver is present.
+ */
+#ifndef PDENLP_CUDA_H
+#define PDENLP_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDENLP_ABI_VERSION 1
+
+/* status codes */
+#define PDENLP_OK 0
+#define PDENLP_EINVAL -1       /* bad argument / inconsistent description   */
+#define PDENLP_EUNSUPPORTED -2 /* (integrand, element) outside the closed set */
+#define PDENLP_ECUDA -3        /* CUDA runtime error (message has details)   */
+#define PDENLP_ENOMEM -4
+
+/* closed, named set of weak-form integrands (SURVEY §8a catalogue) */
+enum pdenlp_integrand {
+  /* f = 0.5(yd-y)^2 + 0.5*alpha*u^2 ; res = grad(v).grad(y) - v*u - v*h
+     README.md:58-98, src/GridapPDENLPModel.jl:164-204.  params[0]=alpha */
+  PDENLP_MEMBRANE = 1,
+  /* f as above ; res = grad(v).grad(y) + sinh(y)*v - u*v - v*h
+     docs/src/poisson-boltzman.md:30-67.  params[0]=alpha */
+  PDENLP_POISSON_BOLTZMANN = 2,
+  /* f as above ; res = -nu*grad(v).grad(y) + (grad(y).1)*v - v*u - v*h
+     test/problems/burger1d.jl:36-46, src/util_functions.jl:109-110.
+     params[0]=alpha, params[1]=nu */
+  PDENLP_BURGER_LIN = 3,
+  /* nparam=1: f = ... + 0.5*(k1-params[2])^2 ;
+     res = nu*grad(v).grad(y) - k1 + v*y*(grad(y).1) - v*u - v*h
+     test/problems/burger1d_param.jl:30-46.  params[0]=alpha, [1]=nu, [2]=0.08 */
+  PDENLP_BURGER_NL = 4,
+  /* nparam=2: f = 0.5(sol-y)^2 + 0.5(k1-1)^2 + 0.5(k2-1)^2 ;
+     res = k1*grad(v).grad(y) - v*f*k2 [- v*u when a control space is given]
+     test/problems/poissonmixed.jl:33-44 */
+  PDENLP_KAPPA_POISSON = 5
+};
+
+/* coefficient fields sampled at quadrature points, coef[k][cell][q] */
+#define PDENLP_COEF_TARGET 0 /* yd / sol */
+#define PDENLP_COEF_SOURCE 1 /* h / f    */
+#define PDENLP_MAX_PARAMS 8
+
+/* where the callback vectors live */
+#define PDENLP_MEM_DEVICE 0
+#define PDENLP_MEM_HOST 1
+
+/*
+ * Flattened model description — what the Julia layer extracts from Gridap once,
+ * right after the unchanged GridapPDENLPModel constructor
+ * (src/additional_constructors.jl:130-266).  All array pointers are HOST
+ * pointers; pdenlp_create copies them to the device.
+ */
+typedef struct pdenlp_desc {
+  int32_t abi_version;   /* PDENLP_ABI_VERSION */
+  int32_t integrand;     /* enum pdenlp_integrand */
+  int32_t dim;           /* 1, 2, 3 */
+  int32_t ny;            /* local dofs of the state space Ypde (= test space Xpde) */
+  int32_t nu;            /* local dofs of the control space Ycon, 0 if VoidFESpace */
+  int32_t nq;            /* quadrature points per cell */
+  int32_t nparam;        /* number of algebraic unknowns kappa */
+  int32_t memspace;      /* PDENLP_MEM_DEVICE | PDENLP_MEM_HOST */
+  int32_t device;        /* CUDA device ordinal, -1 = current device */
+  int32_t reserved0;
+
+  int64_t ncells;        /* cells owned by this handle (a contiguous slab) */
+  int64_t nfree_y;       /* num_free_dofs(Ypde) = ncon */
+  int64_t nfree_u;       /* num_free_dofs(Ycon) */
+  int64_t ndir_y;        /* Dirichlet dofs of Ypde */
+  int64_t ndir_u;        /* Dirichlet dofs of Ycon */
+
+  const int32_t* cell_dofs_y; /* [ncells][ny], get_cell_dof_ids(Ypde) */
+  const int32_t* cell_dofs_u; /* [ncells][nu], get_cell_dof_ids(Ycon) (no multi-field offset) */
+  const double* dir_y;        /* [ndir_y] Dirichlet values of the TRIAL space Ypde */
+  const double* dir_u;        /* [ndir_u] */
+
+  /* reference-FE tables at the quadrature points, physical gradients for the
+     uniform-Cartesian cell map (grad = diag(1/h) * reference gradient) */
+  const double* phi_y;   /* [nq][ny]      */
+  const double* grad_y;  /* [nq][ny][dim] */
+  const double* phi_u;   /* [nq][nu]      */
+  const double* wdet;    /* [nq] quadrature weight * det(J) */
+
+  int32_t ncoef;         /* number of coefficient fields (<= 2) */
+  int32_t reserved1;
+  const double* coef;    /* [ncoef][ncells][nq] */
+  double params[PDENLP_MAX_PARAMS];
+} pdenlp_desc;
+
+typedef struct pdenlp_model pdenlp_model; /* opaque */
+
+/* sizes derived at create time; mirrors NLPModelMeta/PDENLPMeta fields
+   (src/additional_constructors.jl:225-261) */
+typedef struct pdenlp_info {
+  int64_t nvar;       /* nparam + nfree_y + nfree_u */
+  int64_t ncon;       /* nfree_y */
+  int64_t nnzj;       /* LOCAL (this slab) Jacobian entries: k-block + y-block + u-block */
+  int64_t nnzj_k;     /* ncon*nparam (dense block, only on the handle with own_kblocks) */
+  int64_t nnzj_y;     /* y-block entries of this slab */
+  int64_t nnzj_u;     /* u-block entries of this slab */
+  int64_t nnzh;       /* LOCAL Hessian entries: obj k + obj FE + cons k + cons FE */
+  int64_t nnzh_obj;   /* obj k-block + obj FE block (pdemeta.nnzh_obj) */
+  int64_t nnzh_k_obj; /* get_nnz_hess_k, src/hessian_struct_nnzh_functions.jl:61-68 */
+  int64_t nnzh_fe;    /* entries of ONE FE block (obj and cons blocks are equal) */
+  int64_t nnzh_k_con; /* p(p+1)/2 + (n-p)p, src/GridapPDENLPModel.jl:362 */
+} pdenlp_info;
+
+const char* pdenlp_last_error(void);
+int pdenlp_abi_version(void);
+
+/* replaces nothing in the reference: new flattening hook run once after the
+   constructor. */
+int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out);
+int pdenlp_destroy(pdenlp_model* m);
+int pdenlp_get_info(const pdenlp_model* m, pdenlp_info* info);
+
+/* run the callbacks on this CUDA stream (a cudaStream_t cast to void*);
+   NULL = the legacy default stream */
+int pdenlp_set_stream(pdenlp_model* m, void* cuda_stream);
+int pdenlp_sync(pdenlp_model* m);
+
+/* device memory for callers without a CUDA binding (Julia without CUDA.jl) */
+int pdenlp_malloc(void** ptr, int64_t bytes);
+int pdenlp_free(void* ptr);
+int pdenlp_memcpy_h2d(void* dst, const void* src, int64_t bytes);
+int pdenlp_memcpy_d2h(void* dst, const void* src, int64_t bytes);
+
+/* obj(nlp, x)                          src/GridapPDENLPModel.jl:245-255
+   f is a HOST pointer to one double (partial sum of this slab). */
+int pdenlp_obj(pdenlp_model* m, const double* x, double* f);
+
+/* grad!(nlp, x, g)                     src/GridapPDENLPModel.jl:257-266
+   g[nvar] is zero-filled then accumulated (assemble_vector! semantics). */
+int pdenlp_grad(pdenlp_model* m, const double* x, double* g);
+
+/* cons_nln!(nlp, x, c)                 src/GridapPDENLPModel.jl:433-447,
+   _from_terms_to_residual!             src/jacobian_functions.jl:23-58 */
+int pdenlp_cons(pdenlp_model* m, const double* x, double* c);
+
+/* jac_nln_coord!(nlp, x, vals)         src/GridapPDENLPModel.jl:567-584,
+   _jac_coord!                          src/jacobian_functions.jl:122-206
+   vals[nnzj] in jac_nln_structure! order: [k-block | y-block | u-block]. */
+int pdenlp_jac_coord(pdenlp_model* m, const double* x, double* vals);
+
+/* hess_coord!(nlp, x, vals; obj_weight)     src/GridapPDENLPModel.jl:268-301
+   hess_coord!(nlp, x, lambda, vals; obj_weight)            ... :341-411
+   lambda == NULL selects the objective-only method (tail zero-filled, :295-297).
+   vals[nnzh] in hess_structure! order:
+   [obj k-block | obj FE | cons k-block | cons FE], lower triangle on global ids
+   (src/fill_matrix_hessian_functions.jl:50-94). */
+int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda,
+                      double obj_weight, double* vals);
+
+/* jprod_nln!(nlp, x, v, Jv)            src/GridapPDENLPModel.jl:473-487
+   jtprod_nln!(nlp, x, v, Jtv)          src/GridapPDENLPModel.jl:505-519
+   matrix-free: same result as coo_prod! on the jac_coord! values. */
+int pdenlp_jprod(pdenlp_model* m, const double* x, const double* v, double* Jv);
+int pdenlp_jtprod(pdenlp_model* m, const double* x, const double* v, double* Jtv);
+
+/* hprod!(nlp, x, v, Hv; obj_weight)         src/GridapPDENLPModel.jl:303-324
+   hprod!(nlp, x, lambda, v, Hv; obj_weight) src/GridapPDENLPModel.jl:413-431
+   lambda == NULL selects the objective-only method (zeros when obj_weight==0). */
+int pdenlp_hprod(pdenlp_model* m, const double* x, const double* lambda,
+                 double obj_weight, const double* v, double* Hv);
+
+/* jac_nln_structure!(nlp, rows, cols)  src/GridapPDENLPModel.jl:541-550
+   hess_structure!(nlp, rows, cols)     src/GridapPDENLPModel.jl:330-339
+   1-based Int64, same memory space as the callback vectors.  Under Julia the
+   arrays Gridap computed in the constructor stay authoritative; these are used
+   to cross-check them and, in this container, as the structure source. */
+int pdenlp_jac_structure(pdenlp_model* m, int64_t* rows, int64_t* cols);
+int pdenlp_hess_structure(pdenlp_model* m, int64_t* rows, int64_t* cols);
+
+/* bench support: number of kernel launches issued by this handle so far, and
+   the CUDA-event time (ms) of the most recent callback on the handle's stream */
+int pdenlp_launch_count(const pdenlp_model* m, int64_t* launches);
+int pdenlp_last_kernel_ms(pdenlp_model* m, float* ms);
+int pdenlp_set_timing(pdenlp_model* m, int32_t enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDENLP_CUDA_H */

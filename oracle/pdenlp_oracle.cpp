@@ -1,0 +1,643 @@
+// pdenlp_oracle.cpp — CPU ORACLE (test infrastructure, NOT product code).
+//
+// A CPU restatement of the algorithm PDENLPModels.jl v0.3.5 runs for the
+// NLPModels callbacks of a GridapPDENLPModel.  Only tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / --impl reference legs may load this library; the
+// product path (libpdenlp_cuda.so) never does.
+//
+// PARITY PINNING: the reference is pure Julia on top of Gridap 0.15.5 +
+// ForwardDiff, none of which exists in this image, so the oracle cannot be
+// checked against outputs of the reference itself.  It is pinned by (i) the
+// reference's own unit-test vectors for the dof numbering
+// (test/unit-test.jl:828,846,855-874), (ii) its known-answer tests
+// (test/problems/poissonparam.jl:54-63 etc.), (iii) its finite-difference /
+// coord-vs-product self-consistency checks re-expressed in tests/.  There are no
+// golden vectors for jac_coord!/hess_coord! values in the reference, so for
+// those values parity is "unpinned"  — see DESIGN.md.
+//
+// What is restated, and where it comes from (paths relative to /root/reference):
+//   * per-cell autodiff exactly as Gridap/ForwardDiff do it: the cell-local dof
+//     vector z_e = [y_e ; u_e] (Dirichlet entries included) is seeded with
+//     full-width duals (Chunk{length(x)}, src/test_autodiff.jl:8,26) and pushed
+//     through  sum_q w_q detJ integrand(x_q);  Hessians use nested duals
+//     (ForwardDiff.hessian = jacobian of gradient).
+//   * obj:   src/GridapPDENLPModel.jl:245-255, src/additional_obj_terms.jl:135-143,234-242
+//   * grad!: src/additional_obj_terms.jl:145-163,244-284 (assemble_vector!: zero-fill, add in cell order)
+//   * cons:  src/jacobian_functions.jl:23-58
+//   * jac:   src/jacobian_functions.jl:122-206 (segments [k | y-block | u-block];
+//            loop order of Gridap's fill_matrix_coo_numeric! = the loop of
+//            src/fill_matrix_hessian_functions.jl:50-67 without the <= filter)
+//   * hess:  src/GridapPDENLPModel.jl:268-301,341-411, src/fill_matrix_hessian_functions.jl:50-94
+//            (block order (1,1),(2,1),(1,2),(2,2); keep iff gidrow>0, gidcol>0, gidcol<=gidrow)
+//   * structure: src/hessian_struct_nnzh_functions.jl:10-130, src/jacobian_functions.jl:1-7,60-120,
+//            src/additional_constructors.jl:206-211,259-260
+//   * products: NLPModels coo_prod!/coo_sym_prod! as used at src/GridapPDENLPModel.jl:321,428,485,517
+//   * kappa blocks: the reference differentiates the whole assembly w.r.t. kappa
+//     (src/jacobian_functions.jl:136-142, src/GridapPDENLPModel.jl:361-380,
+//     src/additional_obj_terms.jl:286-314); here kappa is appended to the cell-local
+//     dual vector and the per-cell partials are summed in cell order — the same sums.
+//   * Gridap discretisation conventions (third party, not in /root/reference;
+//     Gridap = "0.15.5", Project.toml:17): SURVEY Appendix A.3.
+//
+// Build: see oracle/Makefile (g++ -O2 -fopenmp -shared -fPIC).
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+// ------------------------------------------------------------------ duals
+template <class T, int N>
+struct Dual {
+  T v;
+  T d[N];
+};
+
+template <class T> struct is_dual { static const bool value = false; };
+template <class T, int N> struct is_dual<Dual<T, N>> { static const bool value = true; };
+
+static inline double cst(double a, const double&) { return a; }
+template <class T, int N>
+static inline Dual<T, N> cst(double a, const Dual<T, N>& like) {
+  Dual<T, N> r;
+  r.v = cst(a, like.v);
+  for (int i = 0; i < N; ++i) r.d[i] = cst(0.0, like.v);
+  return r;
+}
+
+template <class T, int N> static inline Dual<T, N> operator+(const Dual<T, N>& a, const Dual<T, N>& b) {
+  Dual<T, N> r; r.v = a.v + b.v; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] + b.d[i]; return r; }
+template <class T, int N> static inline Dual<T, N> operator-(const Dual<T, N>& a, const Dual<T, N>& b) {
+  Dual<T, N> r; r.v = a.v - b.v; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] - b.d[i]; return r; }
+template <class T, int N> static inline Dual<T, N> operator-(const Dual<T, N>& a) {
+  Dual<T, N> r; r.v = -a.v; for (int i = 0; i < N; ++i) r.d[i] = -a.d[i]; return r; }
+template <class T, int N> static inline Dual<T, N> operator*(const Dual<T, N>& a, const Dual<T, N>& b) {
+  Dual<T, N> r; r.v = a.v * b.v; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] * b.v + a.v * b.d[i]; return r; }
+template <class T, int N> static inline Dual<T, N> operator*(double a, const Dual<T, N>& b) {
+  Dual<T, N> r; r.v = a * b.v; for (int i = 0; i < N; ++i) r.d[i] = a * b.d[i]; return r; }
+template <class T, int N> static inline Dual<T, N> operator*(const Dual<T, N>& b, double a) { return a * b; }
+template <class T, int N> static inline Dual<T, N> operator+(const Dual<T, N>& a, double b) {
+  Dual<T, N> r = a; r.v = a.v + b; return r; }
+template <class T, int N> static inline Dual<T, N> operator+(double b, const Dual<T, N>& a) { return a + b; }
+template <class T, int N> static inline Dual<T, N> operator-(const Dual<T, N>& a, double b) {
+  Dual<T, N> r = a; r.v = a.v - b; return r; }
+template <class T, int N> static inline Dual<T, N> operator-(double b, const Dual<T, N>& a) { return (-a) + b; }
+
+static inline double xsinh(double a) { return std::sinh(a); }
+static inline double xcosh(double a) { return std::cosh(a); }
+template <class T, int N> static inline Dual<T, N> xcosh(const Dual<T, N>& a);
+template <class T, int N> static inline Dual<T, N> xsinh(const Dual<T, N>& a) {
+  Dual<T, N> r; r.v = xsinh(a.v); T c = xcosh(a.v); for (int i = 0; i < N; ++i) r.d[i] = c * a.d[i]; return r; }
+template <class T, int N> static inline Dual<T, N> xcosh(const Dual<T, N>& a) {
+  Dual<T, N> r; r.v = xcosh(a.v); T s = xsinh(a.v); for (int i = 0; i < N; ++i) r.d[i] = s * a.d[i]; return r; }
+
+// ------------------------------------------------------------------ problem
+extern "C" {
+typedef struct oracle_problem {
+  int32_t integrand;  // same ids as include/pdenlp_cuda.h
+  int32_t dim;
+  int32_t order_y, order_u;  // order_u = 0 -> no control space (VoidFESpace)
+  int32_t degree;            // Measure(trian, degree)
+  int32_t nparam;
+  int32_t n[3];
+  int32_t nthreads;          // 0 = all OpenMP threads
+  double lo[3], hi[3];
+  int64_t ncells;            // cells of this slab
+  int64_t cell0;             // global index of the first cell (x-fastest numbering)
+  int64_t nfree_y, nfree_u;
+  const int32_t* cell_dofs_y;  // [ncells][ny]
+  const int32_t* cell_dofs_u;  // [ncells][nu]
+  const double* dir_y;
+  const double* dir_u;
+  double params[8];
+} oracle_problem;
+}
+
+enum { MEMBRANE = 1, PB = 2, BURGER_LIN = 3, BURGER_NL = 4, KAPPA_POISSON = 5 };
+
+static const double PI = 3.14159265358979323846;
+
+// coefficient functions, as written in the reference problem files
+static double coef_target(const oracle_problem& P, const double* x) {
+  switch (P.integrand) {
+    case MEMBRANE: return -x[0] * x[0];           // yd, README.md:82
+    case PB: {                                    // docs/src/poisson-boltzman.md:54
+      double m = std::fmin(std::fmin(x[0] - 0.25, 0.75 - x[0]), std::fmin(x[1] - 0.25, 0.75 - x[1]));
+      return m >= 0. ? 10. : 5.;
+    }
+    case BURGER_LIN:
+    case BURGER_NL: return -x[0] * x[0];          // test/problems/burger1d.jl:33
+    case KAPPA_POISSON: {                         // sol, test/problems/poissonmixed.jl:20
+      double s = std::sin(2 * PI * x[0]) * x[1];
+      return P.dim == 3 ? s * x[2] : s;
+    }
+  }
+  return 0.0;
+}
+static double coef_source(const oracle_problem& P, const double* x) {
+  switch (P.integrand) {
+    case MEMBRANE:
+    case PB: {                                    // h, README.md:90-91
+      double w = PI - 1.0 / 8.0;
+      return -std::sin(w * x[0]) * std::sin(w * x[1]);
+    }
+    case BURGER_LIN:
+    case BURGER_NL: return 2 * (P.params[1] + x[0] * x[0] * x[0]);  // burger1d.jl:24
+    case KAPPA_POISSON: {                         // f, poissonmixed.jl:31
+      double s = (2 * PI * PI) * std::sin(2 * PI * x[0]) * x[1];
+      return P.dim == 3 ? s * x[2] : s;
+    }
+  }
+  return 0.0;
+}
+
+// ------------------------------------------------------------------ reference FE
+// 1-D nodal Lagrange basis on [0,1]; node label 0: xi=0, 1: xi=1, 2: xi=1/2
+static void lag1d(int order, double xi, double* v, double* g) {
+  if (order == 1) {
+    v[0] = 1 - xi; v[1] = xi; g[0] = -1; g[1] = 1;
+  } else {
+    v[0] = (1 - xi) * (1 - 2 * xi); v[1] = xi * (2 * xi - 1); v[2] = 4 * xi * (1 - xi);
+    g[0] = 4 * xi - 3; g[1] = 4 * xi - 1; g[2] = 4 - 8 * xi;
+  }
+}
+// local dof -> per-direction node label, Gridap order: vertices, edges, interior
+static void node_label(int order, int dim, int a, int* lab) {
+  if (order == 1) { for (int d = 0; d < dim; ++d) lab[d] = (a >> d) & 1; return; }
+  if (dim == 1) { lab[0] = a; return; }
+  static const int L2[9][2] = {{0,0},{1,0},{0,1},{1,1},{2,0},{2,1},{0,2},{1,2},{2,2}};
+  lab[0] = L2[a][0]; lab[1] = L2[a][1];
+}
+static int nloc_of(int order, int dim) { int n = 1; for (int d = 0; d < dim; ++d) n *= (order + 1); return order == 0 ? 0 : n; }
+
+struct RefTables {
+  int nq = 0, ny = 0, nu = 0, dim = 0;
+  std::vector<double> xi, w;          // [nq][dim], [nq]
+  std::vector<double> phiy, dphiy;    // [nq][ny], [nq][ny][dim] (reference gradients)
+  std::vector<double> phiu;           // [nq][nu]
+};
+
+static void gauss01(int npd, double* x, double* w) {
+  // Gauss-Legendre on [0,1]
+  if (npd == 1) { x[0] = 0.5; w[0] = 1.0; }
+  else if (npd == 2) { double a = 0.5 / std::sqrt(3.0); x[0] = 0.5 - a; x[1] = 0.5 + a; w[0] = w[1] = 0.5; }
+  else { double a = 0.5 * std::sqrt(0.6); x[0] = 0.5 - a; x[1] = 0.5; x[2] = 0.5 + a; w[0] = w[2] = 5.0 / 18.0; w[1] = 8.0 / 18.0; }
+}
+
+static RefTables make_tables(const oracle_problem& P) {
+  RefTables T;
+  T.dim = P.dim;
+  int npd = (P.degree + 2) / 2;  // ceil((degree+1)/2)
+  if (npd > 3) npd = 3;
+  double x1[3], w1[3];
+  gauss01(npd, x1, w1);
+  T.nq = 1; for (int d = 0; d < P.dim; ++d) T.nq *= npd;
+  T.ny = nloc_of(P.order_y, P.dim);
+  T.nu = nloc_of(P.order_u, P.dim);
+  T.xi.resize(T.nq * P.dim); T.w.resize(T.nq);
+  T.phiy.resize(T.nq * T.ny); T.dphiy.resize(T.nq * T.ny * P.dim); T.phiu.resize(T.nq * (T.nu ? T.nu : 1));
+  for (int q = 0; q < T.nq; ++q) {
+    int r = q; double w = 1;
+    for (int d = 0; d < P.dim; ++d) { int k = r % npd; r /= npd; T.xi[q * P.dim + d] = x1[k]; w *= w1[k]; }
+    T.w[q] = w;
+    double v[3][3], g[3][3]; int lab[3];
+    for (int d = 0; d < P.dim; ++d) lag1d(P.order_y, T.xi[q * P.dim + d], v[d], g[d]);
+    for (int a = 0; a < T.ny; ++a) {
+      node_label(P.order_y, P.dim, a, lab);
+      double val = 1; for (int d = 0; d < P.dim; ++d) val *= v[d][lab[d]];
+      T.phiy[q * T.ny + a] = val;
+      for (int e = 0; e < P.dim; ++e) {
+        double gg = 1; for (int d = 0; d < P.dim; ++d) gg *= (d == e) ? g[d][lab[d]] : v[d][lab[d]];
+        T.dphiy[(q * T.ny + a) * P.dim + e] = gg;
+      }
+    }
+    if (T.nu) {
+      for (int d = 0; d < P.dim; ++d) lag1d(P.order_u, T.xi[q * P.dim + d], v[d], g[d]);
+      for (int b = 0; b < T.nu; ++b) {
+        node_label(P.order_u, P.dim, b, lab);
+        double val = 1; for (int d = 0; d < P.dim; ++d) val *= v[d][lab[d]];
+        T.phiu[q * T.nu + b] = val;
+      }
+    }
+  }
+  return T;
+}
+
+// ------------------------------------------------------------------ integrands
+// Pointwise data handed to the integrands: y, grad y, u at the quadrature point
+// (as scalars of type S), physical coordinates, the test function value/gradient.
+template <class S>
+struct Pt {
+  S y, gy[3], u;
+  S k[2];
+  double yd, h;   // coef_target, coef_source at x_q
+};
+
+// objective density f, exactly as written in the reference problem files
+template <class S>
+static S f_density(const oracle_problem& P, const Pt<S>& p) {
+  switch (P.integrand) {
+    case MEMBRANE: case PB: case BURGER_LIN: {
+      // 0.5 * (yd - y) * (yd - y) + 0.5 * alpha * u * u
+      S d = p.yd - p.y;
+      return 0.5 * d * d + (0.5 * P.params[0]) * p.u * p.u;
+    }
+    case BURGER_NL: {
+      S d = p.yd - p.y; S t = p.k[0] - P.params[2];
+      return 0.5 * d * d + (0.5 * P.params[0]) * p.u * p.u + 0.5 * t * t;
+    }
+    case KAPPA_POISSON: {
+      // 0.5*(sol-y)^2 + 0.5*(k1-1)^2 + 0.5*(k2-1)^2   (poissonmixed.jl:37-43)
+      S d = p.yd - p.y; S a = p.k[0] - 1.0; S b = p.k[1] - 1.0;
+      return 0.5 * d * d + 0.5 * a * a + 0.5 * b * b;
+    }
+  }
+  return cst(0.0, p.y);
+}
+
+// weak residual density for ONE test function (value v, physical gradient gv)
+template <class S>
+static S res_density(const oracle_problem& P, const Pt<S>& p, double v, const double* gv, bool has_u) {
+  S gg = cst(0.0, p.y);
+  for (int d = 0; d < P.dim; ++d) gg = gg + gv[d] * p.gy[d];   // grad(v) . grad(y)
+  S one_dot = cst(0.0, p.y);
+  for (int d = 0; d < P.dim; ++d) one_dot = one_dot + p.gy[d]; // grad(y) . one(grad(y))
+  switch (P.integrand) {
+    case MEMBRANE:   // grad(v).grad(y) - v*u - v*h
+      return gg - v * p.u - v * p.h;
+    case PB:         // grad(v).grad(y) + sinh(y)*v - u*v - v*h
+      return gg + xsinh(p.y) * v - p.u * v - v * p.h;
+    case BURGER_LIN: // -nu*(grad(v).grad(y)) + dt(y,v) - v*u - v*h ; dt(y,v) = (grad(y).1)*v
+      return (-P.params[1]) * gg + one_dot * v - v * p.u - v * p.h;
+    case BURGER_NL:  // nu*(grad(v).grad(y)) + k1 + c(y,v) - v*u - v*h ; k1(x) = -k[1] ; c = v*(y*(grad(y).1))
+      return P.params[1] * gg - p.k[0] + v * (one_dot * p.y) - v * p.u - v * p.h;
+    case KAPPA_POISSON: {  // k1*grad(v).grad(y) - v*f*k2 [- v*u]
+      S r = p.k[0] * gg - (v * p.h) * p.k[1];
+      if (has_u) r = r - v * p.u;
+      return r;
+    }
+  }
+  return cst(0.0, p.y);
+}
+
+// ------------------------------------------------------------------ cell evaluation
+struct CellGeom {
+  double x0[3];   // lower corner
+  double h[3];
+  double detJ;
+};
+static CellGeom cell_geom(const oracle_problem& P, int64_t c_local) {
+  CellGeom G; int64_t c = P.cell0 + c_local; G.detJ = 1;
+  for (int d = 0; d < 3; ++d) { G.x0[d] = 0; G.h[d] = 1; }
+  for (int d = 0; d < P.dim; ++d) {
+    int64_t i = c % P.n[d]; c /= P.n[d];
+    G.h[d] = (P.hi[d] - P.lo[d]) / P.n[d];
+    G.x0[d] = P.lo[d] + G.h[d] * (double)i;
+    G.detJ *= G.h[d];
+  }
+  return G;
+}
+
+// gather the cell-local values [kappa ; y_e ; u_e] (PosNegReindex semantics)
+template <int NP, int NY, int NU>
+static void gather_cell(const oracle_problem& P, const double* x, int64_t c, double* z) {
+  for (int k = 0; k < NP; ++k) z[k] = x[k];
+  const double* xy = x + NP;
+  const double* xu = x + NP + P.nfree_y;
+  for (int a = 0; a < NY; ++a) { int g = P.cell_dofs_y[c * NY + a]; z[NP + a] = g > 0 ? xy[g - 1] : P.dir_y[-g - 1]; }
+  for (int b = 0; b < NU; ++b) { int g = P.cell_dofs_u[c * NU + b]; z[NP + NY + b] = g > 0 ? xu[g - 1] : P.dir_u[-g - 1]; }
+}
+
+// build the pointwise data at quadrature point q from cell-local scalars zz
+template <class S, int NP, int NY, int NU>
+static Pt<S> point_data(const oracle_problem& P, const RefTables& T, const CellGeom& G, int q, const S* zz) {
+  Pt<S> p;
+  S zero = cst(0.0, zz[0]);
+  p.y = zero; p.u = zero; for (int d = 0; d < 3; ++d) p.gy[d] = zero;
+  p.k[0] = zero; p.k[1] = zero;
+  for (int k = 0; k < NP; ++k) p.k[k] = zz[k];
+  for (int a = 0; a < NY; ++a) {
+    p.y = p.y + T.phiy[q * NY + a] * zz[NP + a];
+    for (int d = 0; d < P.dim; ++d) p.gy[d] = p.gy[d] + (T.dphiy[(q * NY + a) * P.dim + d] / G.h[d]) * zz[NP + a];
+  }
+  for (int b = 0; b < NU; ++b) p.u = p.u + T.phiu[q * NU + b] * zz[NP + NY + b];
+  double xq[3] = {0, 0, 0};
+  for (int d = 0; d < P.dim; ++d) xq[d] = G.x0[d] + G.h[d] * T.xi[q * P.dim + d];
+  p.yd = coef_target(P, xq);
+  p.h = coef_source(P, xq);
+  return p;
+}
+
+// cell objective  F_e(z) = sum_q w_q detJ f(...)
+template <class S, int NP, int NY, int NU>
+static S cell_obj(const oracle_problem& P, const RefTables& T, const CellGeom& G, const S* zz) {
+  S acc = cst(0.0, zz[0]);
+  for (int q = 0; q < T.nq; ++q) {
+    Pt<S> p = point_data<S, NP, NY, NU>(P, T, G, q, zz);
+    acc = acc + (T.w[q] * G.detJ) * f_density(P, p);
+  }
+  return acc;
+}
+
+// cell residual vector  c_e[i](z) = sum_q w_q detJ res(..., v_i), i over the NY test functions
+template <class S, int NP, int NY, int NU>
+static void cell_res(const oracle_problem& P, const RefTables& T, const CellGeom& G, const S* zz, S* out) {
+  for (int i = 0; i < NY; ++i) out[i] = cst(0.0, zz[0]);
+  for (int q = 0; q < T.nq; ++q) {
+    Pt<S> p = point_data<S, NP, NY, NU>(P, T, G, q, zz);
+    for (int i = 0; i < NY; ++i) {
+      double gv[3];
+      for (int d = 0; d < P.dim; ++d) gv[d] = T.dphiy[(q * NY + i) * P.dim + d] / G.h[d];
+      out[i] = out[i] + (T.w[q] * G.detJ) * res_density(P, p, T.phiy[q * NY + i], gv, NU > 0);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ typed drivers
+template <int NP, int NY, int NU>
+struct Driver {
+  static const int N = NP + NY + NU;
+  typedef Dual<double, N> D1;
+  typedef Dual<D1, N> D2;
+
+  static void seed1(const double* z, D1* zz) {
+    for (int i = 0; i < N; ++i) { zz[i].v = z[i]; for (int j = 0; j < N; ++j) zz[i].d[j] = (i == j) ? 1.0 : 0.0; }
+  }
+  static void seed2(const double* z, D2* zz) {
+    for (int i = 0; i < N; ++i) {
+      zz[i].v.v = z[i];
+      for (int j = 0; j < N; ++j) zz[i].v.d[j] = (i == j) ? 1.0 : 0.0;
+      for (int k = 0; k < N; ++k) {
+        zz[i].d[k].v = (i == k) ? 1.0 : 0.0;
+        for (int j = 0; j < N; ++j) zz[i].d[k].d[j] = 0.0;
+      }
+    }
+  }
+
+  static double obj(const oracle_problem& P, const double* x) {
+    RefTables T = make_tables(P);
+    double total = 0.0;  // sum(::DomainContribution): cell order
+    for (int64_t c = 0; c < P.ncells; ++c) {
+      double z[N]; gather_cell<NP, NY, NU>(P, x, c, z);
+      CellGeom G = cell_geom(P, c);
+      total += cell_obj<double, NP, NY, NU>(P, T, G, z);
+    }
+    return total;
+  }
+
+  static void grad(const oracle_problem& P, const double* x, double* g) {
+    RefTables T = make_tables(P);
+    int64_t nvar = NP + P.nfree_y + P.nfree_u;
+    for (int64_t i = 0; i < nvar; ++i) g[i] = 0.0;
+    for (int64_t c = 0; c < P.ncells; ++c) {
+      double z[N]; gather_cell<NP, NY, NU>(P, x, c, z);
+      D1 zz[N]; seed1(z, zz);
+      CellGeom G = cell_geom(P, c);
+      D1 F = cell_obj<D1, NP, NY, NU>(P, T, G, zz);
+      for (int k = 0; k < NP; ++k) g[k] += F.d[k];
+      for (int a = 0; a < NY; ++a) { int gid = P.cell_dofs_y[c * NY + a]; if (gid > 0) g[NP + gid - 1] += F.d[NP + a]; }
+      for (int b = 0; b < NU; ++b) { int gid = P.cell_dofs_u[c * NU + b]; if (gid > 0) g[NP + P.nfree_y + gid - 1] += F.d[NP + NY + b]; }
+    }
+  }
+
+  static void cons(const oracle_problem& P, const double* x, double* cvec) {
+    RefTables T = make_tables(P);
+    for (int64_t i = 0; i < P.nfree_y; ++i) cvec[i] = 0.0;
+    for (int64_t c = 0; c < P.ncells; ++c) {
+      double z[N]; gather_cell<NP, NY, NU>(P, x, c, z);
+      CellGeom G = cell_geom(P, c);
+      double r[NY]; cell_res<double, NP, NY, NU>(P, T, G, z, r);
+      for (int i = 0; i < NY; ++i) { int gid = P.cell_dofs_y[c * NY + i]; if (gid > 0) cvec[gid - 1] += r[i]; }
+    }
+  }
+
+  // ---- per-cell counts (used for the segment offsets) -----------------------
+  static int count_jy(const oracle_problem& P, int64_t c) {
+    int n = 0;
+    for (int j = 0; j < NY; ++j) if (P.cell_dofs_y[c * NY + j] > 0)
+      for (int i = 0; i < NY; ++i) if (P.cell_dofs_y[c * NY + i] > 0) ++n;
+    return n;
+  }
+  static int count_ju(const oracle_problem& P, int64_t c) {
+    int n = 0;
+    for (int j = 0; j < NU; ++j) if (P.cell_dofs_u[c * NU + j] > 0)
+      for (int i = 0; i < NY; ++i) if (P.cell_dofs_y[c * NY + i] > 0) ++n;
+    return n;
+  }
+  // multi-field global ids of the cell: y ids as they are, u ids + nfree_y when positive
+  static void cell_gids(const oracle_problem& P, int64_t c, int64_t* gid) {
+    for (int a = 0; a < NY; ++a) gid[a] = P.cell_dofs_y[c * NY + a];
+    for (int b = 0; b < NU; ++b) { int64_t g = P.cell_dofs_u[c * NU + b]; gid[NY + b] = g > 0 ? g + P.nfree_y : g; }
+  }
+  // Visit the kept Hessian entries of one cell in the reference order.
+  // fn(local_row, local_col, gidrow, gidcol); local indices into [y_e ; u_e].
+  template <class F>
+  static void visit_hess_cell(const oracle_problem& P, int64_t c, F fn) {
+    int64_t gid[NY + NU + 1]; cell_gids(P, c, gid);
+    const int off[2] = {0, NY}, len[2] = {NY, NU};
+    const int nb = NU > 0 ? 2 : 1;
+    // eachblockid: column-major over field pairs -> (1,1),(2,1),(1,2),(2,2)
+    for (int bj = 0; bj < nb; ++bj)
+      for (int bi = 0; bi < nb; ++bi)
+        for (int j = 0; j < len[bj]; ++j) {
+          int64_t gc = gid[off[bj] + j];
+          if (gc > 0)
+            for (int i = 0; i < len[bi]; ++i) {
+              int64_t gr = gid[off[bi] + i];
+              if (gr > 0 && gc <= gr) fn(off[bi] + i, off[bj] + j, gr, gc);
+            }
+        }
+  }
+  static int count_h(const oracle_problem& P, int64_t c) {
+    int n = 0; visit_hess_cell(P, c, [&](int, int, int64_t, int64_t) { ++n; }); return n;
+  }
+
+  static void sizes(const oracle_problem& P, int64_t* out) {
+    // out: nnzj_k, nnzj_y, nnzj_u, nnzh_k_obj, nnzh_fe, nnzh_k_con
+    int64_t jy = 0, ju = 0, hf = 0;
+    for (int64_t c = 0; c < P.ncells; ++c) { jy += count_jy(P, c); ju += count_ju(P, c); hf += count_h(P, c); }
+    int64_t n = NP + P.nfree_y + P.nfree_u, p = NP;
+    out[0] = P.nfree_y * p; out[1] = jy; out[2] = ju;
+    bool inde = (P.integrand == KAPPA_POISSON);  // MixedEnergyFETerm(..., inde = true), poissonmixed.jl:44
+    out[3] = p == 0 ? 0 : (inde ? p * (p + 1) / 2 : p * (p + 1) / 2 + (n - p) * p);
+    out[4] = hf;
+    out[5] = p == 0 ? 0 : p * (p + 1) / 2 + (n - p) * p;
+  }
+
+  static void jac_structure(const oracle_problem& P, int64_t* rows, int64_t* cols) {
+    int64_t n = 0;
+    // jac_k_structure: ((i,j) for i = 1:ncon, j = 1:p), i fastest
+    for (int j = 1; j <= NP; ++j) for (int64_t i = 1; i <= P.nfree_y; ++i) { rows[n] = i; cols[n] = j; ++n; }
+    for (int64_t c = 0; c < P.ncells; ++c)
+      for (int j = 0; j < NY; ++j) { int gc = P.cell_dofs_y[c * NY + j]; if (gc > 0)
+        for (int i = 0; i < NY; ++i) { int gr = P.cell_dofs_y[c * NY + i]; if (gr > 0) { rows[n] = gr; cols[n] = gc + NP; ++n; } } }
+    for (int64_t c = 0; c < P.ncells; ++c)
+      for (int j = 0; j < NU; ++j) { int gc = P.cell_dofs_u[c * NU + j]; if (gc > 0)
+        for (int i = 0; i < NY; ++i) { int gr = P.cell_dofs_y[c * NY + i]; if (gr > 0) { rows[n] = gr; cols[n] = gc + P.nfree_y + NP; ++n; } } }
+  }
+
+  static void jac_coord(const oracle_problem& P, const double* x, double* vals) {
+    RefTables T = make_tables(P);
+    int64_t sz[6]; sizes(P, sz);
+    std::vector<int64_t> by(P.ncells + 1, 0), bu(P.ncells + 1, 0);
+    for (int64_t c = 0; c < P.ncells; ++c) { by[c + 1] = by[c] + count_jy(P, c); bu[c + 1] = bu[c] + count_ju(P, c); }
+    double* vk = vals; double* vy = vals + sz[0]; double* vu = vy + sz[1];
+    for (int64_t i = 0; i < sz[0]; ++i) vk[i] = 0.0;
+#pragma omp parallel for schedule(static) num_threads(P.nthreads > 0 ? P.nthreads : omp_get_max_threads())
+    for (int64_t c = 0; c < P.ncells; ++c) {
+      double z[N]; gather_cell<NP, NY, NU>(P, x, c, z);
+      D1 zz[N]; seed1(z, zz);
+      CellGeom G = cell_geom(P, c);
+      D1 r[NY]; cell_res<D1, NP, NY, NU>(P, T, G, zz, r);
+      int64_t n = by[c];
+      for (int j = 0; j < NY; ++j) if (P.cell_dofs_y[c * NY + j] > 0)
+        for (int i = 0; i < NY; ++i) if (P.cell_dofs_y[c * NY + i] > 0) vy[n++] = r[i].d[NP + j];
+      n = bu[c];
+      for (int j = 0; j < NU; ++j) if (P.cell_dofs_u[c * NU + j] > 0)
+        for (int i = 0; i < NY; ++i) if (P.cell_dofs_y[c * NY + i] > 0) vu[n++] = r[i].d[NP + NY + j];
+      if (NP > 0) {
+#pragma omp critical
+        for (int k = 0; k < NP; ++k)
+          for (int i = 0; i < NY; ++i) { int gr = P.cell_dofs_y[c * NY + i]; if (gr > 0) vk[(int64_t)k * P.nfree_y + gr - 1] += r[i].d[k]; }
+      }
+    }
+  }
+
+  static void hess_structure(const oracle_problem& P, int64_t* rows, int64_t* cols) {
+    int64_t sz[6]; sizes(P, sz);
+    int64_t n = 0, nvar = NP + P.nfree_y + P.nfree_u;
+    bool inde = (P.integrand == KAPPA_POISSON);
+    int64_t prows = inde ? NP : nvar;
+    // ((i, j) for i = 1:prows, j = 1:p if j <= i), i fastest
+    for (int j = 1; j <= NP; ++j) for (int64_t i = j; i <= prows; ++i) { rows[n] = i; cols[n] = j; ++n; }
+    for (int64_t c = 0; c < P.ncells; ++c)
+      visit_hess_cell(P, c, [&](int, int, int64_t gr, int64_t gc) { rows[n] = gr + NP; cols[n] = gc + NP; ++n; });
+    for (int j = 1; j <= NP; ++j) for (int64_t i = j; i <= nvar; ++i) { rows[n] = i; cols[n] = j; ++n; }
+    for (int64_t c = 0; c < P.ncells; ++c)
+      visit_hess_cell(P, c, [&](int, int, int64_t gr, int64_t gc) { rows[n] = gr + NP; cols[n] = gc + NP; ++n; });
+  }
+
+  // position of (global row i, kappa col j), 1-based, in the trapezoid "i fastest, j <= i" with prows rows
+  static int64_t trap_pos(int64_t i, int j, int64_t prows) {
+    int64_t pos = 0;
+    for (int jj = 1; jj < j; ++jj) pos += prows - jj + 1;
+    return pos + (i - j);
+  }
+
+  static void hess_coord(const oracle_problem& P, const double* x, const double* lambda, double obj_weight, double* vals) {
+    RefTables T = make_tables(P);
+    int64_t sz[6]; sizes(P, sz);
+    int64_t nvar = NP + P.nfree_y + P.nfree_u;
+    bool inde = (P.integrand == KAPPA_POISSON);
+    int64_t prows = inde ? NP : nvar;
+    std::vector<int64_t> bh(P.ncells + 1, 0);
+    for (int64_t c = 0; c < P.ncells; ++c) bh[c + 1] = bh[c] + count_h(P, c);
+    double* vko = vals; double* vfo = vko + sz[3]; double* vkc = vfo + sz[4]; double* vfc = vkc + sz[5];
+    int64_t nnzh = sz[3] + sz[4] + sz[5] + sz[4];
+    for (int64_t i = 0; i < nnzh; ++i) vals[i] = 0.0;
+#pragma omp parallel for schedule(static) num_threads(P.nthreads > 0 ? P.nthreads : omp_get_max_threads())
+    for (int64_t c = 0; c < P.ncells; ++c) {
+      double z[N]; gather_cell<NP, NY, NU>(P, x, c, z);
+      D2 zz[N]; seed2(z, zz);
+      CellGeom G = cell_geom(P, c);
+      int64_t gid[NY + NU + 1]; cell_gids(P, c, gid);
+      // objective part
+      D2 F = cell_obj<D2, NP, NY, NU>(P, T, G, zz);
+      int64_t n = bh[c];
+      visit_hess_cell(P, c, [&](int li, int lj, int64_t, int64_t) { vfo[n++] = F.d[NP + li].d[NP + lj]; });
+      if (NP > 0) {
+#pragma omp critical
+        for (int j = 0; j < NP; ++j) {
+          for (int i = j; i < NP; ++i) vko[trap_pos(i + 1, j + 1, prows)] += F.d[i].d[j];
+          if (!inde) for (int a = 0; a < NY + NU; ++a) { int64_t g = gid[a]; if (g > 0) vko[trap_pos(g + NP, j + 1, prows)] += F.d[NP + a].d[j]; }
+        }
+      }
+      if (lambda) {
+        // l_e(z) = sum_i lambda_e[i] c_e[i](z), lambda through the TEST space (Dirichlet entries = 0)
+        D2 r[NY]; cell_res<D2, NP, NY, NU>(P, T, G, zz, r);
+        D2 L = cst(0.0, zz[0]);
+        for (int i = 0; i < NY; ++i) { int g = P.cell_dofs_y[c * NY + i]; double li = g > 0 ? lambda[g - 1] : 0.0; L = L + li * r[i]; }
+        n = bh[c];
+        visit_hess_cell(P, c, [&](int li, int lj, int64_t, int64_t) { vfc[n++] = L.d[NP + li].d[NP + lj]; });
+        if (NP > 0) {
+#pragma omp critical
+          for (int j = 0; j < NP; ++j) {
+            for (int i = j; i < NP; ++i) vkc[trap_pos(i + 1, j + 1, nvar)] += L.d[i].d[j];
+            for (int a = 0; a < NY + NU; ++a) { int64_t g = gid[a]; if (g > 0) vkc[trap_pos(g + NP, j + 1, nvar)] += L.d[NP + a].d[j]; }
+          }
+        }
+      }
+    }
+    // vals .*= obj_weight on the objective part only (GridapPDENLPModel.jl:299 runs before the constraint part)
+    for (int64_t i = 0; i < sz[3] + sz[4]; ++i) vals[i] *= obj_weight;
+  }
+};
+
+// ------------------------------------------------------------------ dispatch
+#define DISPATCH(CALL)                                                             \
+  do {                                                                             \
+    int ny = nloc_of(P->order_y, P->dim), nu = nloc_of(P->order_u, P->dim);        \
+    int np = P->nparam;                                                            \
+    if (np == 0 && ny == 9 && nu == 4) { typedef Driver<0, 9, 4> D; CALL; }        \
+    else if (np == 0 && ny == 4 && nu == 4) { typedef Driver<0, 4, 4> D; CALL; }   \
+    else if (np == 0 && ny == 2 && nu == 2) { typedef Driver<0, 2, 2> D; CALL; }   \
+    else if (np == 1 && ny == 2 && nu == 2) { typedef Driver<1, 2, 2> D; CALL; }   \
+    else if (np == 2 && ny == 4 && nu == 0) { typedef Driver<2, 4, 0> D; CALL; }   \
+    else if (np == 2 && ny == 4 && nu == 4) { typedef Driver<2, 4, 4> D; CALL; }   \
+    else if (np == 2 && ny == 8 && nu == 8) { typedef Driver<2, 8, 8> D; CALL; }   \
+    else if (np == 2 && ny == 8 && nu == 0) { typedef Driver<2, 8, 0> D; CALL; }   \
+    else if (np == 0 && ny == 8 && nu == 8) { typedef Driver<0, 8, 8> D; CALL; }   \
+    else return -2;                                                                \
+  } while (0)
+
+extern "C" {
+
+int oracle_sizes(const oracle_problem* P, int64_t* out6) { DISPATCH(D::sizes(*P, out6)); return 0; }
+int oracle_obj(const oracle_problem* P, const double* x, double* f) { DISPATCH(*f = D::obj(*P, x)); return 0; }
+int oracle_grad(const oracle_problem* P, const double* x, double* g) { DISPATCH(D::grad(*P, x, g)); return 0; }
+int oracle_cons(const oracle_problem* P, const double* x, double* c) { DISPATCH(D::cons(*P, x, c)); return 0; }
+int oracle_jac_structure(const oracle_problem* P, int64_t* rows, int64_t* cols) { DISPATCH(D::jac_structure(*P, rows, cols)); return 0; }
+int oracle_jac_coord(const oracle_problem* P, const double* x, double* vals) { DISPATCH(D::jac_coord(*P, x, vals)); return 0; }
+int oracle_hess_structure(const oracle_problem* P, int64_t* rows, int64_t* cols) { DISPATCH(D::hess_structure(*P, rows, cols)); return 0; }
+int oracle_hess_coord(const oracle_problem* P, const double* x, const double* lambda, double obj_weight, double* vals) {
+  DISPATCH(D::hess_coord(*P, x, lambda, obj_weight, vals)); return 0;
+}
+
+// NLPModels coo_prod!(rows, cols, vals, v, Av): fill!(Av,0); Av[rows[k]] += vals[k]*v[cols[k]]
+void oracle_coo_prod(int64_t nnz, const int64_t* rows, const int64_t* cols, const double* vals,
+                     const double* v, int64_t nout, double* Av) {
+  for (int64_t i = 0; i < nout; ++i) Av[i] = 0.0;
+  for (int64_t k = 0; k < nnz; ++k) Av[rows[k] - 1] += vals[k] * v[cols[k] - 1];
+}
+// NLPModels coo_sym_prod!
+void oracle_coo_sym_prod(int64_t nnz, const int64_t* rows, const int64_t* cols, const double* vals,
+                         const double* v, int64_t nout, double* Av) {
+  for (int64_t i = 0; i < nout; ++i) Av[i] = 0.0;
+  for (int64_t k = 0; k < nnz; ++k) {
+    int64_t i = rows[k] - 1, j = cols[k] - 1;
+    Av[i] += vals[k] * v[j];
+    if (i != j) Av[j] += vals[k] * v[i];
+  }
+}
+
+// expose the oracle's own tables/coefs so the tests can cross-check the host flattening layer
+int oracle_tables(const oracle_problem* P, int32_t* nq, double* xi, double* w, double* phiy, double* dphiy, double* phiu) {
+  RefTables T = make_tables(*P);
+  *nq = T.nq;
+  if (xi) memcpy(xi, T.xi.data(), T.xi.size() * 8);
+  if (w) memcpy(w, T.w.data(), T.w.size() * 8);
+  if (phiy) memcpy(phiy, T.phiy.data(), T.phiy.size() * 8);
+  if (dphiy) memcpy(dphiy, T.dphiy.data(), T.dphiy.size() * 8);
+  if (phiu && T.nu) memcpy(phiu, T.phiu.data(), T.phiu.size() * 8);
+  return 0;
+}
+int oracle_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+}

@@ -1,0 +1,166 @@
+"""Flattening layer: FE objects -> the plain arrays of ``pdenlp_desc``.
+
+This is the Python stand-in for the Julia layer described in the north star
+("a Julia layer flattens these into device arrays: cell-to-dof maps,
+reference-FE shape-function and gradient tables at quadrature points, weights
+and Jacobians"); julia/PDENLPCuda.jl holds the Julia version that reads the
+same data from Gridap objects.  It also restates, vectorised, the COO structure
+the reference computes once in its constructor
+(/root/reference/src/additional_constructors.jl:206-211,259-260) so that the
+container has a structure source without Gridap.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+
+from .cartesian import gauss_legendre_01, lagrange_tables
+from .problems import ProblemSpec, KAPPA_POISSON
+
+
+@dataclass
+class FlatModel:
+    """Host arrays of one cell slab, laid out as pdenlp_desc expects."""
+    spec: ProblemSpec
+    cell0: int
+    ncells: int
+    dim: int
+    ny: int
+    nu: int
+    nq: int
+    nparam: int
+    nfree_y: int
+    nfree_u: int
+    cell_dofs_y: np.ndarray  # (ncells, ny) int32
+    cell_dofs_u: np.ndarray  # (ncells, nu) int32
+    dir_y: np.ndarray
+    dir_u: np.ndarray
+    phi_y: np.ndarray   # (nq, ny)
+    grad_y: np.ndarray  # (nq, ny, dim) physical gradients
+    phi_u: np.ndarray   # (nq, nu)
+    wdet: np.ndarray    # (nq,)
+    coef: np.ndarray    # (ncoef, ncells, nq)
+    params: np.ndarray  # (8,)
+
+    @property
+    def nvar(self) -> int:
+        return self.nparam + self.nfree_y + self.nfree_u
+
+    @property
+    def ncon(self) -> int:
+        return self.nfree_y
+
+
+def flatten(spec: ProblemSpec, cell_range: Optional[Tuple[int, int]] = None, with_coef: bool = True) -> FlatModel:
+    m = spec.model
+    c0, c1 = (0, m.ncells) if cell_range is None else cell_range
+    Y, U = spec.Ypde, spec.Ycon
+    ny = Y.nloc
+    nu = U.nloc if U is not None else 0
+    pts, wts = gauss_legendre_01(spec.degree, m.dim)
+    nq = pts.shape[0]
+    phi_y, dphi_y = lagrange_tables(Y.order, m.dim, pts)
+    grad_y = dphi_y / m.h  # physical gradient for the Cartesian map x = lo + h*(idx + xi)
+    if U is not None:
+        phi_u, _ = lagrange_tables(U.order, m.dim, pts)
+    else:
+        phi_u = np.zeros((nq, 0))
+    wdet = wts * float(np.prod(m.h))
+
+    ncells = c1 - c0
+    if with_coef:
+        idx = m.cell_multi_index(np.arange(c0, c1, dtype=np.int64))
+        coef = np.empty((2, ncells, nq))
+        for q in range(nq):
+            X = m.lo + (idx + pts[q]) * m.h
+            coef[0, :, q] = spec.target(X) if spec.target is not None else 0.0
+            coef[1, :, q] = spec.source(X) if spec.source is not None else 0.0
+    else:
+        coef = np.zeros((2, 0, nq))
+    params = np.zeros(8)
+    params[: len(spec.params)] = spec.params
+    return FlatModel(
+        spec=spec, cell0=c0, ncells=ncells, dim=m.dim, ny=ny, nu=nu, nq=nq, nparam=spec.nparam,
+        nfree_y=Y.nfree, nfree_u=(U.nfree if U is not None else 0),
+        cell_dofs_y=np.ascontiguousarray(Y.cell_dof_ids[c0:c1]),
+        cell_dofs_u=np.ascontiguousarray(U.cell_dof_ids[c0:c1]) if U is not None else np.zeros((ncells, 0), np.int32),
+        dir_y=np.ascontiguousarray(Y.dirichlet_vals, dtype=np.float64),
+        dir_u=np.ascontiguousarray(U.dirichlet_vals, dtype=np.float64) if U is not None else np.zeros(0),
+        phi_y=np.ascontiguousarray(phi_y), grad_y=np.ascontiguousarray(grad_y),
+        phi_u=np.ascontiguousarray(phi_u), wdet=np.ascontiguousarray(wdet),
+        coef=np.ascontiguousarray(coef), params=params,
+    )
+
+
+# --------------------------------------------------------------------------
+# COO structure, vectorised restatement of the reference constructor's output
+# --------------------------------------------------------------------------
+def _kept_pairs(row_ids: np.ndarray, col_ids: np.ndarray, lower: bool):
+    """Candidates of one block for all cells in the reference loop order
+    (col j outer, row i inner).  Returns (rows, cols, keep) shaped
+    (ncells, ncols*nrows)."""
+    nc, nr = row_ids.shape
+    ncol = col_ids.shape[1]
+    R = np.broadcast_to(row_ids[:, None, :], (nc, ncol, nr)).reshape(nc, -1)
+    C = np.broadcast_to(col_ids[:, :, None], (nc, ncol, nr)).reshape(nc, -1)
+    keep = (R > 0) & (C > 0)
+    if lower:
+        keep &= C <= R
+    return R, C, keep
+
+
+def jac_structure(fm: FlatModel):
+    """rows, cols (1-based int64) of jac_nln_structure! for this slab:
+    [k-block | y-block | u-block]; /root/reference/src/jacobian_functions.jl:1-7,
+    60-120, src/additional_constructors.jl:259-260."""
+    p = fm.nparam
+    gy = fm.cell_dofs_y.astype(np.int64)
+    rows = [np.tile(np.arange(1, fm.ncon + 1, dtype=np.int64), p)]
+    cols = [np.repeat(np.arange(1, p + 1, dtype=np.int64), fm.ncon)]
+    R, C, keep = _kept_pairs(gy, gy, lower=False)
+    rows.append(R[keep]); cols.append(C[keep] + p)
+    if fm.nu:
+        gu = fm.cell_dofs_u.astype(np.int64)
+        R, C, keep = _kept_pairs(gy, gu, lower=False)
+        rows.append(R[keep]); cols.append(C[keep] + fm.nfree_y + p)
+    return np.concatenate(rows), np.concatenate(cols)
+
+
+def _hess_fe_structure(fm: FlatModel):
+    gy = fm.cell_dofs_y.astype(np.int64)
+    if fm.nu:
+        gu = fm.cell_dofs_u.astype(np.int64)
+        gu = np.where(gu > 0, gu + fm.nfree_y, gu)  # MultiFieldFESpace, consecutive style
+        blocks = [(gy, gy), (gu, gy), (gy, gu), (gu, gu)]  # eachblockid: (1,1),(2,1),(1,2),(2,2) as (rows, cols)
+    else:
+        blocks = [(gy, gy)]
+    Rs, Cs, Ks = [], [], []
+    for rid, cid in blocks:
+        R, C, keep = _kept_pairs(rid, cid, lower=True)
+        Rs.append(R); Cs.append(C); Ks.append(keep)
+    R = np.concatenate(Rs, axis=1); C = np.concatenate(Cs, axis=1); K = np.concatenate(Ks, axis=1)
+    return R[K], C[K]
+
+
+def _trapezoid(prows: int, p: int):
+    rows = [np.arange(j, prows + 1, dtype=np.int64) for j in range(1, p + 1)]
+    cols = [np.full(prows - j + 1, j, dtype=np.int64) for j in range(1, p + 1)]
+    if not rows:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
+    return np.concatenate(rows), np.concatenate(cols)
+
+
+def hess_structure(fm: FlatModel):
+    """rows, cols of hess_structure!: [obj k | obj FE | cons k | cons FE];
+    /root/reference/src/hessian_struct_nnzh_functions.jl:10-130,
+    src/fill_matrix_hessian_functions.jl:96-209."""
+    p = fm.nparam
+    inde = fm.spec.integrand == KAPPA_POISSON
+    rk, ck = _trapezoid(p if inde else fm.nvar, p)
+    rf, cf = _hess_fe_structure(fm)
+    rkc, ckc = _trapezoid(fm.nvar, p)
+    rows = np.concatenate([rk, rf + p, rkc, rf + p])
+    cols = np.concatenate([ck, cf + p, ckc, cf + p])
+    return rows, cols, rk.size + rf.size

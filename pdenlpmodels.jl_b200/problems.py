@@ -1,0 +1,166 @@
+"""Problem catalogue: the closed, named set of weak-form integrands
+ and the BASELINE.json configurations built on them.
+
+Each ``ProblemSpec`` is what the user of the reference would have written with
+Gridap (mesh, spaces, quadrature degree, f, res) — here reduced to the named
+integrand id plus the coefficient functions, which the flattening layer samples
+at the quadrature points.  Formulas follow the reference files cited per
+problem; paths are relative to /root/reference.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+from .cartesian import CartesianDiscreteModel, LagrangianFESpace
+
+# integrand ids — keep in sync with include/pdenlp_cuda.h
+MEMBRANE = 1
+POISSON_BOLTZMANN = 2
+BURGER_LIN = 3
+BURGER_NL = 4
+KAPPA_POISSON = 5
+
+INTEGRAND_NAMES = {
+    MEMBRANE: "membrane",
+    POISSON_BOLTZMANN: "poisson_boltzmann",
+    BURGER_LIN: "burger_lin",
+    BURGER_NL: "burger_nl",
+    KAPPA_POISSON: "kappa_poisson",
+}
+
+
+@dataclass
+class ProblemSpec:
+    name: str
+    integrand: int
+    model: CartesianDiscreteModel
+    Ypde: LagrangianFESpace
+    Ycon: Optional[LagrangianFESpace]
+    degree: int
+    nparam: int = 0
+    params: Sequence[float] = ()
+    # coefficient fields: callables X (npts, dim) -> (npts,)
+    target: Optional[Callable] = None  # yd / sol
+    source: Optional[Callable] = None  # h / f
+
+    @property
+    def nvar(self) -> int:
+        return self.nparam + self.Ypde.nfree + (self.Ycon.nfree if self.Ycon is not None else 0)
+
+    @property
+    def ncon(self) -> int:
+        return self.Ypde.nfree
+
+
+_OMEGA = math.pi - 1.0 / 8.0
+
+
+def _h_membrane(X):
+    return -np.sin(_OMEGA * X[:, 0]) * np.sin(_OMEGA * X[:, 1])
+
+
+def controlelasticmembrane(n: int = 100) -> ProblemSpec:
+    """README 'Control elastic membrane' (README.md:58-98; docstring
+    src/GridapPDENLPModel.jl:164-204): Q2 state with Dirichlet boundary, Q1
+    control, degree 1, res-function (FEOperatorFromWeakForm) variant."""
+    model = CartesianDiscreteModel((-1, 1, -1, 1), (n, n))
+    Ypde = LagrangianFESpace(model, 2, "H1", "boundary", 0.0)
+    Ycon = LagrangianFESpace(model, 1, "H1")
+    return ProblemSpec(
+        name="Control elastic membrane",
+        integrand=MEMBRANE, model=model, Ypde=Ypde, Ycon=Ycon, degree=1,
+        params=(1e-2,),
+        target=lambda X: -X[:, 0] ** 2,
+        source=_h_membrane,
+    )
+
+
+def poissonboltzman2d(n: int = 100, control_conformity: str = "L2") -> ProblemSpec:
+    """docs/src/poisson-boltzman.md:30-67: Q1 state, Q1 control (L2 in the
+    doc), degree 1, sinh reaction term."""
+    model = CartesianDiscreteModel((-1, 1, -1, 1), (n, n))
+    Ypde = LagrangianFESpace(model, 1, "H1", "boundary", 0.0)
+    Ycon = LagrangianFESpace(model, 1, control_conformity)
+
+    def yd(X):
+        m = np.minimum(np.minimum(X[:, 0] - 0.25, 0.75 - X[:, 0]), np.minimum(X[:, 1] - 0.25, 0.75 - X[:, 1]))
+        return np.where(m >= 0.0, 10.0, 5.0)
+
+    return ProblemSpec(
+        name="poissonboltzman2d",
+        integrand=POISSON_BOLTZMANN, model=model, Ypde=Ypde, Ycon=Ycon, degree=1,
+        params=(1e-4,), target=yd, source=_h_membrane,
+    )
+
+
+def _burger_spaces(n):
+    model = CartesianDiscreteModel((0, 1), n)
+    # dirichlet_tags = ["diri0", "diri1"] = entities [1], [2]; values 0 and -1
+    Ypde = LagrangianFESpace(model, 1, "H1", [1, 2], {1: 0.0, 2: -1.0})
+    Ycon = LagrangianFESpace(model, 1, "H1")
+    return model, Ypde, Ycon
+
+
+def burger1d(n: int = 512) -> ProblemSpec:
+    """test/problems/burger1d.jl:1-52 (the test-suite variant: dt(y,v) = y' v
+    is linear, src/util_functions.jl:109-110)."""
+    model, Ypde, Ycon = _burger_spaces(n)
+    nu = 0.08
+    return ProblemSpec(
+        name="burger1d",
+        integrand=BURGER_LIN, model=model, Ypde=Ypde, Ycon=Ycon, degree=1,
+        params=(1e-2, nu),
+        target=lambda X: -X[:, 0] ** 2,
+        source=lambda X: 2 * (nu + X[:, 0] ** 3),
+    )
+
+
+def burger1d_param(n: int = 512) -> ProblemSpec:
+    """test/problems/burger1d_param.jl:1-54: nonlinear convection v*y*y',
+    one algebraic unknown."""
+    model, Ypde, Ycon = _burger_spaces(n)
+    nu = 0.08
+    return ProblemSpec(
+        name="burger1d_param",
+        integrand=BURGER_NL, model=model, Ypde=Ypde, Ycon=Ycon, degree=1,
+        nparam=1, params=(1e-2, nu, 0.08),
+        target=lambda X: -X[:, 0] ** 2,
+        source=lambda X: 2 * (nu + X[:, 0] ** 3),
+    )
+
+
+def poissonmixed(n: int = 3, dim: int = 2, control: bool = False) -> ProblemSpec:
+    """test/problems/poissonmixed.jl:14-48 (2 algebraic unknowns, degree 2);
+    ``dim=3, control=True`` is BASELINE config 5 (inverse Poisson with kappa +
+    3-D Q1 Poisson control)."""
+    dom = (0, 1) * dim
+    model = CartesianDiscreteModel(dom, (n,) * dim)
+    Ypde = LagrangianFESpace(model, 1, "H1", "boundary", 0.0)
+    Ycon = LagrangianFESpace(model, 1, "H1") if control else None
+
+    def sol(X):
+        s = np.sin(2 * np.pi * X[:, 0]) * X[:, 1]
+        return s * X[:, 2] if dim == 3 else s
+
+    def f(X):
+        s = (2 * np.pi ** 2) * np.sin(2 * np.pi * X[:, 0]) * X[:, 1]
+        return s * X[:, 2] if dim == 3 else s
+
+    return ProblemSpec(
+        name="poissonmixed" if not control else "inversePoissonproblem",
+        integrand=KAPPA_POISSON, model=model, Ypde=Ypde, Ycon=Ycon, degree=2,
+        nparam=2, params=(), target=sol, source=f,
+    )
+
+
+BASELINE_CONFIGS = {
+    "membrane_n100": lambda: controlelasticmembrane(100),
+    "membrane_n2048": lambda: controlelasticmembrane(2048),
+    "poissonboltzman2d_n1024": lambda: poissonboltzman2d(1024),
+    "burger1d_1M": lambda: burger1d_param(1_000_000),
+    "kappa_poisson3d_128": lambda: poissonmixed(128, dim=3, control=True),
+}
