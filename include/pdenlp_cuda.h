@@ -160,6 +160,10 @@ int pdenlp_malloc(void** ptr, int64_t bytes);
 int pdenlp_free(void* ptr);
 int pdenlp_memcpy_h2d(void* dst, const void* src, int64_t bytes);
 int pdenlp_memcpy_d2h(void* dst, const void* src, int64_t bytes);
+/* page-locked host memory: host vectors handed to a PDENLP_MEM_HOST model should
+   live here so the staging copies run at full PCIe speed */
+int pdenlp_host_alloc(void** ptr, int64_t bytes);
+int pdenlp_host_free(void* ptr);
 
 /* obj(nlp, x)                          src/GridapPDENLPModel.jl:245-255
    f is a HOST pointer to one double (partial sum of this slab). */

@@ -1,0 +1,205 @@
+"""ctypes binding of include/pdenlp_cuda.h (libpdenlp_cuda.so).
+
+This is the Python counterpart of the Julia ``ccall`` layer shown in
+INTEGRATION.md / julia/PDENLPCuda.jl: plain pointers and sizes only.
+There is no fallback: if the library is missing or no sm_100 device is
+present, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libpdenlp_cuda.so")
+
+ABI_VERSION = 1
+OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = 0, -1, -2, -3, -4
+MEM_DEVICE, MEM_HOST = 0, 1
+
+# every symbol include/pdenlp_cuda.h declares
+SYMBOLS = [
+    "pdenlp_last_error", "pdenlp_abi_version", "pdenlp_create", "pdenlp_destroy", "pdenlp_get_info",
+    "pdenlp_set_stream", "pdenlp_sync", "pdenlp_malloc", "pdenlp_free", "pdenlp_memcpy_h2d", "pdenlp_memcpy_d2h",
+    "pdenlp_host_alloc", "pdenlp_host_free",
+    "pdenlp_obj", "pdenlp_grad", "pdenlp_cons", "pdenlp_jac_coord", "pdenlp_hess_coord",
+    "pdenlp_jprod", "pdenlp_jtprod", "pdenlp_hprod", "pdenlp_jac_structure", "pdenlp_hess_structure",
+    "pdenlp_launch_count", "pdenlp_last_kernel_ms", "pdenlp_set_timing",
+]
+
+
+class Desc(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("integrand", C.c_int32), ("dim", C.c_int32), ("ny", C.c_int32),
+        ("nu", C.c_int32), ("nq", C.c_int32), ("nparam", C.c_int32), ("memspace", C.c_int32),
+        ("device", C.c_int32), ("reserved0", C.c_int32),
+        ("ncells", C.c_int64), ("nfree_y", C.c_int64), ("nfree_u", C.c_int64), ("ndir_y", C.c_int64), ("ndir_u", C.c_int64),
+        ("cell_dofs_y", C.c_void_p), ("cell_dofs_u", C.c_void_p), ("dir_y", C.c_void_p), ("dir_u", C.c_void_p),
+        ("phi_y", C.c_void_p), ("grad_y", C.c_void_p), ("phi_u", C.c_void_p), ("wdet", C.c_void_p),
+        ("ncoef", C.c_int32), ("reserved1", C.c_int32), ("coef", C.c_void_p),
+        ("params", C.c_double * 8),
+    ]
+
+
+class Info(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in (
+        "nvar", "ncon", "nnzj", "nnzj_k", "nnzj_y", "nnzj_u", "nnzh", "nnzh_obj", "nnzh_k_obj", "nnzh_fe", "nnzh_k_con")]
+
+
+class PdenlpError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libpdenlp_cuda error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load libpdenlp_cuda.so and check that it exports every declared symbol."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(
+            f"{LIB_PATH} is not built; run `python __graft_entry__.py` (nvcc, sm_100a). There is no fallback path.")
+    lib = C.CDLL(LIB_PATH)
+    missing = [s for s in SYMBOLS if not hasattr(lib, s)]
+    if missing:
+        raise ImportError(f"libpdenlp_cuda.so lacks symbols: {missing}")
+    lib.pdenlp_last_error.restype = C.c_char_p
+    vp, dbl, i64 = C.c_void_p, C.c_double, C.c_int64
+    lib.pdenlp_create.argtypes = [C.POINTER(Desc), C.POINTER(vp)]
+    lib.pdenlp_destroy.argtypes = [vp]
+    lib.pdenlp_get_info.argtypes = [vp, C.POINTER(Info)]
+    lib.pdenlp_set_stream.argtypes = [vp, vp]
+    lib.pdenlp_sync.argtypes = [vp]
+    lib.pdenlp_malloc.argtypes = [C.POINTER(vp), i64]
+    lib.pdenlp_free.argtypes = [vp]
+    lib.pdenlp_memcpy_h2d.argtypes = [vp, vp, i64]
+    lib.pdenlp_memcpy_d2h.argtypes = [vp, vp, i64]
+    lib.pdenlp_host_alloc.argtypes = [C.POINTER(vp), i64]
+    lib.pdenlp_host_free.argtypes = [vp]
+    lib.pdenlp_obj.argtypes = [vp, vp, C.POINTER(dbl)]
+    lib.pdenlp_grad.argtypes = [vp, vp, vp]
+    lib.pdenlp_cons.argtypes = [vp, vp, vp]
+    lib.pdenlp_jac_coord.argtypes = [vp, vp, vp]
+    lib.pdenlp_hess_coord.argtypes = [vp, vp, vp, dbl, vp]
+    lib.pdenlp_jprod.argtypes = [vp, vp, vp, vp]
+    lib.pdenlp_jtprod.argtypes = [vp, vp, vp, vp]
+    lib.pdenlp_hprod.argtypes = [vp, vp, vp, dbl, vp, vp]
+    lib.pdenlp_jac_structure.argtypes = [vp, vp, vp]
+    lib.pdenlp_hess_structure.argtypes = [vp, vp, vp]
+    lib.pdenlp_launch_count.argtypes = [vp, C.POINTER(i64)]
+    lib.pdenlp_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.pdenlp_set_timing.argtypes = [vp, C.c_int32]
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != OK:
+        raise PdenlpError(rc, load().pdenlp_last_error().decode())
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+
+
+class Handle:
+    """Owns one ``pdenlp_model*`` created from a FlatModel (one cell slab on one GPU)."""
+
+    def __init__(self, fm, device: int = -1, memspace: int = MEM_DEVICE, with_coef: bool = True):
+        lib = load()
+        d = Desc()
+        d.abi_version = ABI_VERSION
+        d.integrand = fm.spec.integrand
+        d.dim, d.ny, d.nu, d.nq, d.nparam = fm.dim, fm.ny, fm.nu, fm.nq, fm.nparam
+        d.memspace = memspace
+        d.device = device
+        d.ncells, d.nfree_y, d.nfree_u = fm.ncells, fm.nfree_y, fm.nfree_u
+        d.ndir_y, d.ndir_u = fm.dir_y.size, fm.dir_u.size
+        keep = [np.ascontiguousarray(fm.cell_dofs_y, np.int32), np.ascontiguousarray(fm.cell_dofs_u, np.int32),
+                fm.dir_y, fm.dir_u, fm.phi_y, fm.grad_y, fm.phi_u, fm.wdet, fm.coef]
+        d.cell_dofs_y, d.cell_dofs_u = _np_ptr(keep[0]), _np_ptr(keep[1])
+        d.dir_y, d.dir_u = _np_ptr(fm.dir_y), _np_ptr(fm.dir_u)
+        d.phi_y, d.grad_y, d.phi_u, d.wdet = _np_ptr(fm.phi_y), _np_ptr(fm.grad_y), _np_ptr(fm.phi_u), _np_ptr(fm.wdet)
+        if with_coef and fm.coef.shape[1] == fm.ncells:
+            d.ncoef, d.coef = 2, _np_ptr(fm.coef)
+        else:
+            d.ncoef, d.coef = 0, None
+        for i in range(8):
+            d.params[i] = fm.params[i]
+        h = C.c_void_p()
+        check(lib.pdenlp_create(C.byref(d), C.byref(h)))
+        del keep
+        self._h = h
+        self.memspace = memspace
+        info = Info()
+        check(lib.pdenlp_get_info(h, C.byref(info)))
+        self.info = info
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().pdenlp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # thin pass-throughs; pointers are ints (device or host addresses)
+    def set_stream(self, stream_ptr: int):
+        check(load().pdenlp_set_stream(self._h, C.c_void_p(stream_ptr)))
+
+    def sync(self):
+        check(load().pdenlp_sync(self._h))
+
+    def obj(self, x: int) -> float:
+        f = C.c_double()
+        check(load().pdenlp_obj(self._h, x, C.byref(f)))
+        return f.value
+
+    def grad(self, x, g):
+        check(load().pdenlp_grad(self._h, x, g))
+
+    def cons(self, x, c):
+        check(load().pdenlp_cons(self._h, x, c))
+
+    def jac_coord(self, x, vals):
+        check(load().pdenlp_jac_coord(self._h, x, vals))
+
+    def hess_coord(self, x, lam, obj_weight, vals):
+        check(load().pdenlp_hess_coord(self._h, x, lam, float(obj_weight), vals))
+
+    def jprod(self, x, v, out):
+        check(load().pdenlp_jprod(self._h, x, v, out))
+
+    def jtprod(self, x, v, out):
+        check(load().pdenlp_jtprod(self._h, x, v, out))
+
+    def hprod(self, x, lam, obj_weight, v, out):
+        check(load().pdenlp_hprod(self._h, x, lam, float(obj_weight), v, out))
+
+    def jac_structure(self, rows, cols):
+        check(load().pdenlp_jac_structure(self._h, rows, cols))
+
+    def hess_structure(self, rows, cols):
+        check(load().pdenlp_hess_structure(self._h, rows, cols))
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        check(load().pdenlp_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def set_timing(self, on: bool):
+        check(load().pdenlp_set_timing(self._h, 1 if on else 0))
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        check(load().pdenlp_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value

@@ -1,0 +1,112 @@
+// integrands.cuh — the closed, named set of weak-form integrands.
+//
+// Each integrand is written ONCE, generically over the scalar type T (double,
+// Jet1, Jet2), as a function of the pointwise fields
+//     s[SY] = y, s[SG+d] = d_d y, s[SU] = u, s[SK+k] = kappa_k
+// f(...)  : objective density
+// res(...) : weak residual density, linear in the test function (v, grad v):
+//            res = R[0]*v + sum_d R[1+d]*d_d v  (+ R[1+DIM]*1 when HAS_CONST:
+//            a term of the integrand that does not multiply v is added to every
+//            test component by Gridap's broadcasting — burger1d_param.jl:45).
+// Formulas follow the reference problem files cited in include/pdenlp_cuda.h.
+#pragma once
+#include "jet.cuh"
+
+namespace pdenlp {
+
+struct PointCtx {
+  double target;      // yd / sol at the quadrature point
+  double source;      // h / f at the quadrature point
+  const double* par;  // scalar parameters (alpha, nu, ...)
+};
+
+template <int DIM_, int NP_>
+struct FieldIdx {
+  static constexpr int DIM = DIM_, NP = NP_;
+  static constexpr int SY = 0, SG = 1, SU = 1 + DIM_, SK = 2 + DIM_;
+  static constexpr int M = 2 + DIM_ + NP_;
+};
+
+// 0.5*(yd - y)*(yd - y) + 0.5*alpha*u*u — shared by MEMBRANE / PB / BURGER
+template <class T, class I>
+PDENLP_HD T tracking_f(const PointCtx& c, const T* s) {
+  T d = c.target - s[I::SY];
+  return 0.5 * d * d + (0.5 * c.par[0]) * s[I::SU] * s[I::SU];
+}
+
+template <int DIM_>
+struct Membrane : FieldIdx<DIM_, 0> {
+  using I = FieldIdx<DIM_, 0>;
+  static constexpr bool HAS_CONST = false;
+  static constexpr bool NEEDS_COEF_DERIV = false;  // derivatives do not read coefficient fields
+  template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) { return tracking_f<T, I>(c, s); }
+  // grad(v).grad(y) - v*u - v*h
+  template <class T> PDENLP_HD static void res(const PointCtx& c, const T* s, T* R) {
+    R[0] = -s[I::SU] - c.source;
+#pragma unroll
+    for (int d = 0; d < DIM_; ++d) R[1 + d] = s[I::SG + d];
+  }
+};
+
+template <int DIM_>
+struct PoissonBoltzmann : FieldIdx<DIM_, 0> {
+  using I = FieldIdx<DIM_, 0>;
+  static constexpr bool HAS_CONST = false;
+  static constexpr bool NEEDS_COEF_DERIV = false;
+  template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) { return tracking_f<T, I>(c, s); }
+  // grad(v).grad(y) + sinh(y)*v - u*v - v*h
+  template <class T> PDENLP_HD static void res(const PointCtx& c, const T* s, T* R) {
+    R[0] = jsinh(s[I::SY]) - s[I::SU] - c.source;
+#pragma unroll
+    for (int d = 0; d < DIM_; ++d) R[1 + d] = s[I::SG + d];
+  }
+};
+
+struct BurgerLin : FieldIdx<1, 0> {
+  using I = FieldIdx<1, 0>;
+  static constexpr bool HAS_CONST = false;
+  static constexpr bool NEEDS_COEF_DERIV = false;
+  template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) { return tracking_f<T, I>(c, s); }
+  // -nu*grad(v).grad(y) + (grad(y).1)*v - v*u - v*h
+  template <class T> PDENLP_HD static void res(const PointCtx& c, const T* s, T* R) {
+    R[0] = s[I::SG] - s[I::SU] - c.source;
+    R[1] = (-c.par[1]) * s[I::SG];
+  }
+};
+
+struct BurgerNl : FieldIdx<1, 1> {
+  using I = FieldIdx<1, 1>;
+  static constexpr bool HAS_CONST = true;
+  static constexpr bool NEEDS_COEF_DERIV = false;
+  template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) {
+    T t = s[I::SK] - c.par[2];
+    return tracking_f<T, I>(c, s) + 0.5 * t * t;
+  }
+  // nu*grad(v).grad(y) - k1 + v*y*(grad(y).1) - v*u - v*h
+  template <class T> PDENLP_HD static void res(const PointCtx& c, const T* s, T* R) {
+    R[0] = s[I::SY] * s[I::SG] - s[I::SU] - c.source;
+    R[1] = c.par[1] * s[I::SG];
+    R[2] = -s[I::SK];
+  }
+};
+
+template <int DIM_, bool HAS_U>
+struct KappaPoisson : FieldIdx<DIM_, 2> {
+  using I = FieldIdx<DIM_, 2>;
+  static constexpr bool HAS_CONST = false;
+  static constexpr bool NEEDS_COEF_DERIV = true;  // d res / d k2 = -v*f
+  template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) {
+    T d = c.target - s[I::SY];
+    T a = s[I::SK] - 1.0, b = s[I::SK + 1] - 1.0;
+    return 0.5 * d * d + 0.5 * a * a + 0.5 * b * b;
+  }
+  // k1*grad(v).grad(y) - v*f*k2 [- v*u]
+  template <class T> PDENLP_HD static void res(const PointCtx& c, const T* s, T* R) {
+    R[0] = (-c.source) * s[I::SK + 1];
+    if (HAS_U) R[0] = R[0] - s[I::SU];
+#pragma unroll
+    for (int d = 0; d < DIM_; ++d) R[1 + d] = s[I::SK] * s[I::SG + d];
+  }
+};
+
+}  // namespace pdenlp

@@ -1,0 +1,844 @@
+// kernels.cuh — sm_100a FP64 kernels of the derivative-evaluation hot path.
+//
+// Data layout in HBM (owned by a pdenlp_model):
+//   dofs_y / dofs_u : int32, SoA [local dof][ldc]  (ldc = ncells rounded up to 32) so that a
+//                     warp (lane = cell) reads 128 B lines; signed, 1-based, <0 = Dirichlet
+//   dir_y / dir_u   : FP64 Dirichlet values, index -id-1
+//   coef            : FP64 [field][cell][q]
+//   base_jy/ju/h    : int64 exclusive scans of the per-tile (32 cells) COO entry counts
+//   tables          : passed BY VALUE as a __grid_constant__ kernel parameter => they live in
+//                     the constant bank and are consumed as immediate operands of DFMA
+//                     (zero load instructions; every lane reads the same entry)
+//
+// The coordinate kernels (jac_coord!, hess_coord!) are structured streaming writers:
+//   lane = cell, warp = tile of 32 consecutive cells = ONE contiguous run of each COO segment.
+//   Each lane evaluates its element derivatives in registers (forward-mode jets on the
+//   pointwise fields + contraction with the tables), ranks its kept entries with the
+//   reference's filter (gid>0, and gidcol<=gidrow for the Hessian — on GLOBAL ids), and
+//   writes them at (warp-scan offset + rank) into the warp's shared-memory staging buffer.
+//   One elected lane then streams the whole run to HBM with a single TMA bulk store
+//   (cp.async.bulk.global.shared::cta, SASS UBLKCP) — fully coalesced 16 B-aligned traffic,
+//   the SM's LSUs never touch the 10 GB output stream.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "integrands.cuh"
+
+namespace pdenlp {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kThreads = kWarpsPerCta * 32;
+
+// ------------------------------------------------------------------ element description
+template <class Integrand_, int NY_, int NU_, int NQ_>
+struct Elem {
+  using Integrand = Integrand_;
+  static constexpr int DIM = Integrand::DIM, NP = Integrand::NP, M = Integrand::M;
+  static constexpr int SY = Integrand::SY, SG = Integrand::SG, SU = Integrand::SU, SK = Integrand::SK;
+  static constexpr int NY = NY_, NU = NU_, NQ = NQ_;
+  static constexpr int NUS = NU_ > 0 ? NU_ : 1;
+  static constexpr int NB = 1 + DIM;                                  // (phi, grad phi)
+  static constexpr bool HAS_CONST = Integrand::HAS_CONST;
+  static constexpr int NR = 1 + DIM + (HAS_CONST ? 1 : 0);            // residual slots
+  static constexpr int RUN_JY = NY * NY, RUN_JU = NY * NU;
+  static constexpr int RUN_H = NY * (NY + 1) / 2 + NU * NY + NU * (NU + 1) / 2;  // distinct ids per cell
+  static constexpr int RUN_J = RUN_JY > RUN_JU ? RUN_JY : RUN_JU;
+};
+
+template <class E>
+struct Tables {
+  double wdet[E::NQ];
+  double By[E::NQ][E::NY][E::NB];
+  double Bu[E::NQ][E::NUS];
+  double par[8];
+};
+
+struct DevModel {
+  const int32_t* dofs_y;
+  const int32_t* dofs_u;
+  const double* dir_y;
+  const double* dir_u;
+  const double* coef;      // [2][ncells][nq]
+  const int64_t* base_jy;  // [ntiles+1]
+  const int64_t* base_ju;
+  const int64_t* base_h;
+  int64_t ncells, ldc;
+  int64_t nfree_y, nfree_u;
+  int32_t ntiles;
+  int32_t nparam;
+};
+
+// ------------------------------------------------------------------ small device helpers
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += t;
+  }
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// ------------------------------------------------------------------ per-lane cell data
+template <class E>
+struct Cell {
+  int gy[E::NY];
+  int gu[E::NUS];
+  double zy[E::NY];
+  double zu[E::NUS];
+};
+
+template <class E>
+__device__ __forceinline__ void load_ids(const DevModel& D, int64_t cell, bool valid, Cell<E>& c) {
+#pragma unroll
+  for (int a = 0; a < E::NY; ++a) c.gy[a] = valid ? __ldg(D.dofs_y + (int64_t)a * D.ldc + cell) : -1;
+#pragma unroll
+  for (int b = 0; b < E::NUS; ++b) c.gu[b] = (valid && E::NU > 0) ? __ldg(D.dofs_u + (int64_t)b * D.ldc + cell) : -1;
+}
+// PosNegReindex(free, dirichlet): /root/reference/src/PDENLPModels.jl:27-43
+template <class E>
+__device__ __forceinline__ void gather_state(const DevModel& D, const double* __restrict__ x, bool valid, Cell<E>& c) {
+  const double* xy = x + D.nparam;
+  const double* xu = xy + D.nfree_y;
+#pragma unroll
+  for (int a = 0; a < E::NY; ++a) {
+    const int g = c.gy[a];
+    c.zy[a] = !valid ? 0.0 : (g > 0 ? __ldg(xy + (g - 1)) : __ldg(D.dir_y + (-g - 1)));
+  }
+#pragma unroll
+  for (int b = 0; b < E::NUS; ++b) {
+    const int g = c.gu[b];
+    c.zu[b] = (!valid || E::NU == 0) ? 0.0 : (g > 0 ? __ldg(xu + (g - 1)) : __ldg(D.dir_u + (-g - 1)));
+  }
+}
+// values of a free-dof vector through a space whose Dirichlet values are zero
+// (lambda through the TEST space, /root/reference/src/GridapPDENLPModel.jl:383; directions v)
+template <int N>
+__device__ __forceinline__ void gather_free(const double* __restrict__ vec, const int* gid, double* out) {
+#pragma unroll
+  for (int a = 0; a < N; ++a) out[a] = gid[a] > 0 ? __ldg(vec + (gid[a] - 1)) : 0.0;
+}
+
+// pointwise fields at quadrature point q, seeded as jets (or plain doubles)
+template <class E, class T>
+__device__ __forceinline__ void point_state(const Tables<E>& tab, const Cell<E>& c, const double* __restrict__ x, int q, T* s) {
+  double val[E::M];
+#pragma unroll
+  for (int k = 0; k < E::M; ++k) val[k] = 0.0;
+#pragma unroll
+  for (int a = 0; a < E::NY; ++a)
+#pragma unroll
+    for (int k = 0; k < E::NB; ++k) val[k] = fma(tab.By[q][a][k], c.zy[a], val[k]);
+  if (E::NU > 0) {
+#pragma unroll
+    for (int b = 0; b < E::NU; ++b) val[E::SU] = fma(tab.Bu[q][b], c.zu[b], val[E::SU]);
+  }
+#pragma unroll
+  for (int k = 0; k < E::NP; ++k) val[E::SK + k] = __ldg(x + k);
+#pragma unroll
+  for (int k = 0; k < E::M; ++k) jet_seed(s[k], val[k], k);
+}
+
+template <class E>
+__device__ __forceinline__ PointCtx point_ctx(const DevModel& D, const Tables<E>& tab, int64_t cell, bool valid, int q, bool need) {
+  PointCtx pc;
+  pc.par = tab.par;
+  pc.target = 0.0;
+  pc.source = 0.0;
+  if (need && valid) {
+    pc.target = __ldg(D.coef + (cell * E::NQ + q));
+    pc.source = __ldg(D.coef + ((D.ncells + cell) * E::NQ + q));
+  }
+  return pc;
+}
+
+// test-function slot t of local test function i: (phi_i, grad phi_i, [1])
+template <class E>
+__device__ __forceinline__ double test_slot(const Tables<E>& tab, int q, int i, int t) {
+  return t < E::NB ? tab.By[q][i][t] : 1.0;
+}
+
+// ------------------------------------------------------------------ entry counts (reference filters)
+template <class E>
+__device__ __forceinline__ void count_entries(const Cell<E>& c, int& njy, int& nju, int& nh) {
+  int fy = 0, fu = 0;
+#pragma unroll
+  for (int a = 0; a < E::NY; ++a) fy += c.gy[a] > 0;
+#pragma unroll
+  for (int b = 0; b < E::NU; ++b) fu += c.gu[b] > 0;
+  njy = fy * fy;
+  nju = fy * fu;
+  int h = 0;
+#pragma unroll
+  for (int j = 0; j < E::NY; ++j)
+#pragma unroll
+    for (int i = 0; i < E::NY; ++i) h += (c.gy[j] > 0) & (c.gy[j] <= c.gy[i]);
+  h += fu * fy;  // block (2,1): u ids are offset by nfree_y, so gidcol <= gidrow always holds
+#pragma unroll
+  for (int j = 0; j < E::NU; ++j)
+#pragma unroll
+    for (int i = 0; i < E::NU; ++i) h += (c.gu[j] > 0) & (c.gu[j] <= c.gu[i]);
+  nh = h;
+}
+
+// per-tile counts, used once at create time to build the segment offsets
+template <class E>
+__global__ void __launch_bounds__(kThreads) k_count(DevModel D, int32_t* __restrict__ counts /*[ntiles][3]*/, int32_t* __restrict__ flag) {
+  const int lane = threadIdx.x & 31;
+  const int64_t tile = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (tile >= D.ntiles) return;
+  const int64_t cell = tile * 32 + lane;
+  const bool valid = cell < D.ncells;
+  Cell<E> c;
+  load_ids<E>(D, valid ? cell : 0, valid, c);
+  int njy, nju, nh;
+  count_entries<E>(c, njy, nju, nh);
+  if (nh > E::RUN_H) atomicExch(flag, 1);  // repeated dof ids inside one cell are not supported
+  for (int d = 16; d > 0; d >>= 1) {
+    njy += __shfl_xor_sync(0xffffffffu, njy, d);
+    nju += __shfl_xor_sync(0xffffffffu, nju, d);
+    nh += __shfl_xor_sync(0xffffffffu, nh, d);
+  }
+  if (lane == 0) { counts[tile * 3 + 0] = njy; counts[tile * 3 + 1] = nju; counts[tile * 3 + 2] = nh; }
+}
+
+// ------------------------------------------------------------------ staged segment writer
+// One per warp. The staging buffer holds the tile's run of one COO segment; `pad` keeps the
+// shared-memory image congruent (mod 16 B) with the global destination so the bulk copy is legal.
+template <class V>
+struct SegStage {
+  V* buf;
+  // make sure the previous bulk store has finished READING the buffer before refilling it
+  __device__ __forceinline__ void acquire(int lane) {
+    if (lane == 0) bulk_wait_read_all();
+    __syncwarp();
+  }
+  // all lanes have written their entries at buf[pad + excl ...]; stream [0,total) to gdst
+  __device__ __forceinline__ void release(V* gdst, int total, int pad, int lane) {
+    fence_proxy_async_smem();  // generic-proxy writes -> visible to the async proxy (TMA)
+    __syncwarp();
+    if (lane == 0 && total > 0) {
+      int done = 0;
+      if (pad) { gdst[0] = buf[1]; done = 1; }           // unaligned head element
+      const int nb = (total - done) & ~1;                 // 16 B granules
+      if (nb > 0) {
+        bulk_store_s2g(gdst + done, buf + 2 * pad, (uint32_t)nb * sizeof(V));
+        bulk_commit();
+      }
+      if ((total - done) & 1) gdst[total - 1] = buf[pad + total - 1];  // tail element
+    }
+  }
+};
+
+// ------------------------------------------------------------------ jac_coord!
+// vals layout (this slab): [k-block (ncon*p, filled elsewhere) | y-block | u-block]
+template <class E>
+__global__ void __launch_bounds__(kThreads, 1)
+k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const double* __restrict__ x,
+            double* __restrict__ vals_y, double* __restrict__ vals_u) {
+  using I = typename E::Integrand;
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  constexpr int STAGE = 32 * E::RUN_J + 2;
+  SegStage<double> st{smem + warp * STAGE};
+
+  for (int64_t tile = (int64_t)blockIdx.x * nwarps + warp; tile < D.ntiles; tile += (int64_t)gridDim.x * nwarps) {
+    const int64_t cell = tile * 32 + lane;
+    const bool valid = cell < D.ncells;
+    Cell<E> c;
+    load_ids<E>(D, valid ? cell : 0, valid, c);
+    gather_state<E>(D, x, valid, c);
+
+    int fy = 0, fu = 0;
+#pragma unroll
+    for (int a = 0; a < E::NY; ++a) fy += c.gy[a] > 0;
+#pragma unroll
+    for (int b = 0; b < E::NU; ++b) fu += c.gu[b] > 0;
+
+    // ---- y-block:  A_e[i][j] = sum_q w sum_t T_i[t] sum_k dR_t/ds_k By_j[k]
+    {
+      const int cnt = fy * fy;
+      const int incl = warp_incl_scan(cnt, lane);
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      double* gdst = vals_y + D.base_jy[tile];
+      const int pad = (int)((reinterpret_cast<uintptr_t>(gdst) >> 3) & 1);
+      st.acquire(lane);
+      double* const p0 = st.buf + pad + (incl - cnt);
+#pragma unroll 1
+      for (int q = 0; q < E::NQ; ++q) {
+        Jet1<E::M> s[E::M], R[E::NR];
+        point_state<E>(tab, c, x, q, s);
+        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        I::res(pc, s, R);
+        double* p = p0;
+#pragma unroll
+        for (int j = 0; j < E::NY; ++j) {
+          double Mj[E::NR];
+#pragma unroll
+          for (int t = 0; t < E::NR; ++t) {
+            double a = 0.0;
+#pragma unroll
+            for (int k = 0; k < E::NB; ++k) a = fma(R[t].g[k], tab.By[q][j][k], a);
+            Mj[t] = a * tab.wdet[q];
+          }
+          if (c.gy[j] > 0) {
+#pragma unroll
+            for (int i = 0; i < E::NY; ++i) {
+              double v = 0.0;
+#pragma unroll
+              for (int t = 0; t < E::NR; ++t) v = fma(test_slot<E>(tab, q, i, t), Mj[t], v);
+              if (c.gy[i] > 0) { if (q == 0) *p = v; else *p += v; ++p; }
+            }
+          }
+        }
+      }
+      st.release(gdst, total, pad, lane);
+    }
+    // ---- u-block:  B_e[i][b] = sum_q w sum_t T_i[t] dR_t/du psi_b
+    if (E::NU > 0) {
+      const int cnt = fy * fu;
+      const int incl = warp_incl_scan(cnt, lane);
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      double* gdst = vals_u + D.base_ju[tile];
+      const int pad = (int)((reinterpret_cast<uintptr_t>(gdst) >> 3) & 1);
+      st.acquire(lane);
+      double* const p0 = st.buf + pad + (incl - cnt);
+#pragma unroll 1
+      for (int q = 0; q < E::NQ; ++q) {
+        Jet1<E::M> s[E::M], R[E::NR];
+        point_state<E>(tab, c, x, q, s);
+        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        I::res(pc, s, R);
+        double* p = p0;
+#pragma unroll
+        for (int b = 0; b < E::NU; ++b) {
+          double Mb[E::NR];
+#pragma unroll
+          for (int t = 0; t < E::NR; ++t) Mb[t] = R[t].g[E::SU] * tab.Bu[q][b] * tab.wdet[q];
+          if (c.gu[b] > 0) {
+#pragma unroll
+            for (int i = 0; i < E::NY; ++i) {
+              double v = 0.0;
+#pragma unroll
+              for (int t = 0; t < E::NR; ++t) v = fma(test_slot<E>(tab, q, i, t), Mb[t], v);
+              if (c.gy[i] > 0) { if (q == 0) *p = v; else *p += v; ++p; }
+            }
+          }
+        }
+      }
+      st.release(gdst, total, pad, lane);
+    }
+  }
+  if (lane == 0) bulk_wait_all();
+}
+
+// ------------------------------------------------------------------ hess_coord!
+// Emit one FE Hessian block set of a cell from the pointwise second derivatives Dm (packed
+// symmetric M x M, already scaled by the quadrature weight), in the reference order:
+// block (1,1) [y,y], (2,1) [u rows, y cols], (1,2) [never kept], (2,2) [u,u]; within a block
+// columns outer, rows inner; keep iff gidcol>0 and gidcol<=gidrow (global ids).
+template <class E, bool ACC>
+__device__ __forceinline__ double* emit_hess(const Tables<E>& tab, int q, const Jet2<E::M>& L, double scale,
+                                             const Cell<E>& c, double* p) {
+  using J2 = Jet2<E::M>;
+  // (1,1)
+#pragma unroll
+  for (int j = 0; j < E::NY; ++j) {
+    double Nj[E::NB];
+#pragma unroll
+    for (int k = 0; k < E::NB; ++k) {
+      double a = 0.0;
+#pragma unroll
+      for (int l = 0; l < E::NB; ++l) a = fma(L.h[J2::idx(k, l)], tab.By[q][j][l], a);
+      Nj[k] = a * scale;
+    }
+    if (c.gy[j] > 0) {
+#pragma unroll
+      for (int i = 0; i < E::NY; ++i) {
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < E::NB; ++k) v = fma(tab.By[q][i][k], Nj[k], v);
+        if (c.gy[j] <= c.gy[i]) { if (ACC) *p += v; else *p = v; ++p; }
+      }
+    }
+  }
+  if (E::NU > 0) {
+    // (2,1): rows = control dofs, cols = state dofs
+#pragma unroll
+    for (int j = 0; j < E::NY; ++j) {
+      double a = 0.0;
+#pragma unroll
+      for (int l = 0; l < E::NB; ++l) a = fma(L.h[J2::idx(E::SU, l)], tab.By[q][j][l], a);
+      a *= scale;
+      if (c.gy[j] > 0) {
+#pragma unroll
+        for (int i = 0; i < E::NU; ++i) {
+          const double v = tab.Bu[q][i] * a;
+          if (c.gu[i] > 0) { if (ACC) *p += v; else *p = v; ++p; }
+        }
+      }
+    }
+    // (2,2)
+    const double duu = L.h[J2::idx(E::SU, E::SU)] * scale;
+#pragma unroll
+    for (int j = 0; j < E::NU; ++j) {
+      const double a = duu * tab.Bu[q][j];
+      if (c.gu[j] > 0) {
+#pragma unroll
+        for (int i = 0; i < E::NU; ++i) {
+          const double v = tab.Bu[q][i] * a;
+          if (c.gu[j] <= c.gu[i]) { if (ACC) *p += v; else *p = v; ++p; }
+        }
+      }
+    }
+  }
+  return p;
+}
+
+// lambda-weighted residual  l(s) = sum_t Lam_t R_t(s)  as a Jet2 (its Hessian is the pointwise
+// Lagrangian Hessian; its gradient the pointwise J^T lambda)
+template <class E, class T>
+__device__ __forceinline__ T weighted_res(const PointCtx& pc, const T* s, const double* Lam) {
+  using I = typename E::Integrand;
+  T R[E::NR];
+  I::res(pc, s, R);
+  T acc = Lam[0] * R[0];
+#pragma unroll
+  for (int t = 1; t < E::NR; ++t) acc = acc + Lam[t] * R[t];
+  return acc;
+}
+template <class E>
+__device__ __forceinline__ void lambda_slots(const Tables<E>& tab, int q, const double* lam_e, double* Lam) {
+#pragma unroll
+  for (int t = 0; t < E::NR; ++t) {
+    double a = 0.0;
+#pragma unroll
+    for (int i = 0; i < E::NY; ++i) a = fma(test_slot<E>(tab, q, i, t), lam_e[i], a);
+    Lam[t] = a;
+  }
+}
+
+// vals_obj / vals_con point at the FE blocks of this slab; either may be NULL (skipped).
+template <class E>
+__global__ void __launch_bounds__(kThreads, 1)
+k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const double* __restrict__ x,
+             const double* __restrict__ lambda, double obj_weight,
+             double* __restrict__ vals_obj, double* __restrict__ vals_con) {
+  using I = typename E::Integrand;
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  constexpr int STAGE = 32 * E::RUN_H + 2;
+  SegStage<double> st{smem + warp * STAGE};
+
+  for (int64_t tile = (int64_t)blockIdx.x * nwarps + warp; tile < D.ntiles; tile += (int64_t)gridDim.x * nwarps) {
+    const int64_t cell = tile * 32 + lane;
+    const bool valid = cell < D.ncells;
+    Cell<E> c;
+    load_ids<E>(D, valid ? cell : 0, valid, c);
+    gather_state<E>(D, x, valid, c);
+    int njy, nju, cnt;
+    count_entries<E>(c, njy, nju, cnt);
+    const int incl = warp_incl_scan(cnt, lane);
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int64_t tb = D.base_h[tile];
+
+    if (vals_obj != nullptr) {
+      double* gdst = vals_obj + tb;
+      const int pad = (int)((reinterpret_cast<uintptr_t>(gdst) >> 3) & 1);
+      st.acquire(lane);
+      double* const p0 = st.buf + pad + (incl - cnt);
+#pragma unroll 1
+      for (int q = 0; q < E::NQ; ++q) {
+        Jet2<E::M> s[E::M];
+        point_state<E>(tab, c, x, q, s);
+        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        const Jet2<E::M> F = I::f(pc, s);
+        if (q == 0) emit_hess<E, false>(tab, q, F, obj_weight * tab.wdet[q], c, p0);
+        else        emit_hess<E, true>(tab, q, F, obj_weight * tab.wdet[q], c, p0);
+      }
+      st.release(gdst, total, pad, lane);
+    }
+    if (vals_con != nullptr) {
+      double lam_e[E::NY];
+      gather_free<E::NY>(lambda, c.gy, lam_e);
+      double* gdst = vals_con + tb;
+      const int pad = (int)((reinterpret_cast<uintptr_t>(gdst) >> 3) & 1);
+      st.acquire(lane);
+      double* const p0 = st.buf + pad + (incl - cnt);
+#pragma unroll 1
+      for (int q = 0; q < E::NQ; ++q) {
+        Jet2<E::M> s[E::M];
+        point_state<E>(tab, c, x, q, s);
+        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        double Lam[E::NR];
+        lambda_slots<E>(tab, q, lam_e, Lam);
+        const Jet2<E::M> L = weighted_res<E>(pc, s, Lam);
+        if (q == 0) emit_hess<E, false>(tab, q, L, tab.wdet[q], c, p0);
+        else        emit_hess<E, true>(tab, q, L, tab.wdet[q], c, p0);
+      }
+      st.release(gdst, total, pad, lane);
+    }
+  }
+  if (lane == 0) bulk_wait_all();
+}
+
+// ------------------------------------------------------------------ structure (setup-time, not hot)
+// rows/cols of the FE blocks; kind 0 = Jacobian y-block, 1 = Jacobian u-block, 2 = Hessian FE block.
+// shift_r / shift_c are added to the 1-based ids (nparam and multi-field offsets).
+template <class E>
+__global__ void __launch_bounds__(kThreads)
+k_structure(const DevModel D, int kind, int64_t* __restrict__ rows, int64_t* __restrict__ cols, int64_t shift) {
+  const int lane = threadIdx.x & 31;
+  const int64_t tile = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (tile >= D.ntiles) return;
+  const int64_t cell = tile * 32 + lane;
+  const bool valid = cell < D.ncells;
+  Cell<E> c;
+  load_ids<E>(D, valid ? cell : 0, valid, c);
+  int njy, nju, nh;
+  count_entries<E>(c, njy, nju, nh);
+  const int cnt = kind == 0 ? njy : (kind == 1 ? nju : nh);
+  const int incl = warp_incl_scan(cnt, lane);
+  const int64_t base = (kind == 0 ? D.base_jy[tile] : (kind == 1 ? D.base_ju[tile] : D.base_h[tile])) + (incl - cnt);
+  int64_t n = base;
+  const int64_t offu = D.nfree_y;
+  if (kind == 0) {
+    for (int j = 0; j < E::NY; ++j) if (c.gy[j] > 0)
+      for (int i = 0; i < E::NY; ++i) if (c.gy[i] > 0) { rows[n] = c.gy[i]; cols[n] = c.gy[j] + shift; ++n; }
+  } else if (kind == 1) {
+    for (int j = 0; j < E::NU; ++j) if (c.gu[j] > 0)
+      for (int i = 0; i < E::NY; ++i) if (c.gy[i] > 0) { rows[n] = c.gy[i]; cols[n] = c.gu[j] + offu + shift; ++n; }
+  } else {
+    for (int j = 0; j < E::NY; ++j) if (c.gy[j] > 0)
+      for (int i = 0; i < E::NY; ++i) if (c.gy[j] <= c.gy[i]) { rows[n] = c.gy[i] + shift; cols[n] = c.gy[j] + shift; ++n; }
+    for (int j = 0; j < E::NY; ++j) if (c.gy[j] > 0)
+      for (int i = 0; i < E::NU; ++i) if (c.gu[i] > 0) { rows[n] = c.gu[i] + offu + shift; cols[n] = c.gy[j] + shift; ++n; }
+    for (int j = 0; j < E::NU; ++j) if (c.gu[j] > 0)
+      for (int i = 0; i < E::NU; ++i) if (c.gu[j] <= c.gu[i]) { rows[n] = c.gu[i] + offu + shift; cols[n] = c.gu[j] + offu + shift; ++n; }
+  }
+}
+
+// ------------------------------------------------------------------ vector-valued callbacks
+// (lane = cell; scatter with red.global.add.f64 — north star: "segmented atomics")
+enum VecOp { OP_OBJ = 0, OP_GRAD = 1, OP_CONS = 2, OP_JPROD = 3, OP_JTPROD = 4, OP_HPROD = 5 };
+
+template <class E>
+__device__ __forceinline__ void scatter_fields(const Tables<E>& tab, int q, const DevModel& D, const Cell<E>& c,
+                                               const double* gs /*[M], weighted*/, double* __restrict__ out) {
+  // out is an nvar-vector: d/dz_a = sum_k By_a[k] gs[k]; d/du_b = Bu_b gs[SU]; kappa handled by caller
+  double* oy = out + D.nparam;
+  double* ou = oy + D.nfree_y;
+#pragma unroll
+  for (int a = 0; a < E::NY; ++a) {
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < E::NB; ++k) v = fma(tab.By[q][a][k], gs[k], v);
+    if (c.gy[a] > 0) atomicAdd(oy + (c.gy[a] - 1), v);
+  }
+  if (E::NU > 0) {
+#pragma unroll
+    for (int b = 0; b < E::NU; ++b) {
+      const double v = tab.Bu[q][b] * gs[E::SU];
+      if (c.gu[b] > 0) atomicAdd(ou + (c.gu[b] - 1), v);
+    }
+  }
+}
+
+// direction of the pointwise fields induced by a free-dof direction v (Dirichlet entries = 0)
+template <class E>
+__device__ __forceinline__ void field_direction(const Tables<E>& tab, int q, const DevModel& D, const Cell<E>& c,
+                                                const double* __restrict__ v, double* ds) {
+  double vy[E::NY], vu[E::NUS];
+  gather_free<E::NY>(v + D.nparam, c.gy, vy);
+  if (E::NU > 0) gather_free<E::NUS>(v + D.nparam + D.nfree_y, c.gu, vu);
+#pragma unroll
+  for (int k = 0; k < E::M; ++k) ds[k] = 0.0;
+#pragma unroll
+  for (int a = 0; a < E::NY; ++a)
+#pragma unroll
+    for (int k = 0; k < E::NB; ++k) ds[k] = fma(tab.By[q][a][k], vy[a], ds[k]);
+  if (E::NU > 0) {
+#pragma unroll
+    for (int b = 0; b < E::NU; ++b) ds[E::SU] = fma(tab.Bu[q][b], vu[b], ds[E::SU]);
+  }
+#pragma unroll
+  for (int k = 0; k < E::NP; ++k) ds[E::SK + k] = __ldg(v + k);
+}
+
+template <class E, int OP>
+__global__ void __launch_bounds__(kThreads)
+k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* __restrict__ x,
+         const double* __restrict__ lambda, const double* __restrict__ v, double obj_weight,
+         double* __restrict__ out, double* __restrict__ partials) {
+  using I = typename E::Integrand;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double fsum = 0.0;
+  double ksum[E::NP > 0 ? E::NP : 1];
+#pragma unroll
+  for (int k = 0; k < (E::NP > 0 ? E::NP : 1); ++k) ksum[k] = 0.0;
+
+  for (int64_t tile = (int64_t)blockIdx.x * kWarpsPerCta + warp; tile < D.ntiles; tile += (int64_t)gridDim.x * kWarpsPerCta) {
+    const int64_t cell = tile * 32 + lane;
+    const bool valid = cell < D.ncells;
+    Cell<E> c;
+    load_ids<E>(D, valid ? cell : 0, valid, c);
+    gather_state<E>(D, x, valid, c);
+    if (!valid) continue;
+#pragma unroll 1
+    for (int q = 0; q < E::NQ; ++q) {
+      const double w = tab.wdet[q];
+      if (OP == OP_OBJ) {
+        double s[E::M];
+        point_state<E>(tab, c, x, q, s);
+        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, true);
+        fsum += w * I::f(pc, s);
+      } else if (OP == OP_GRAD) {
+        Jet1<E::M> s[E::M];
+        point_state<E>(tab, c, x, q, s);
+        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, true);
+        const Jet1<E::M> F = I::f(pc, s);
+        double gs[E::M];
+#pragma unroll
+        for (int k = 0; k < E::M; ++k) gs[k] = w * F.g[k];
+        scatter_fields<E>(tab, q, D, c, gs, out);
+#pragma unroll
+        for (int k = 0; k < E::NP; ++k) ksum[k] += gs[E::SK + k];
+      } else if (OP == OP_CONS) {
+        double s[E::M], R[E::NR];
+        point_state<E>(tab, c, x, q, s);
+        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, true);
+        I::res(pc, s, R);
+#pragma unroll
+        for (int i = 0; i < E::NY; ++i) {
+          double a = 0.0;
+#pragma unroll
+          for (int t = 0; t < E::NR; ++t) a = fma(test_slot<E>(tab, q, i, t), R[t], a);
+          if (c.gy[i] > 0) atomicAdd(out + (c.gy[i] - 1), w * a);
+        }
+      } else if (OP == OP_JPROD) {
+        Jet1<E::M> s[E::M], R[E::NR];
+        point_state<E>(tab, c, x, q, s);
+        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        I::res(pc, s, R);
+        double ds[E::M];
+        field_direction<E>(tab, q, D, c, v, ds);
+        double dR[E::NR];
+#pragma unroll
+        for (int t = 0; t < E::NR; ++t) {
+          double a = 0.0;
+#pragma unroll
+          for (int k = 0; k < E::M; ++k) a = fma(R[t].g[k], ds[k], a);
+          dR[t] = a * w;
+        }
+#pragma unroll
+        for (int i = 0; i < E::NY; ++i) {
+          double a = 0.0;
+#pragma unroll
+          for (int t = 0; t < E::NR; ++t) a = fma(test_slot<E>(tab, q, i, t), dR[t], a);
+          if (c.gy[i] > 0) atomicAdd(out + (c.gy[i] - 1), a);
+        }
+      } else if (OP == OP_JTPROD) {
+        Jet1<E::M> s[E::M];
+        point_state<E>(tab, c, x, q, s);
+        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        double w_e[E::NY], Lam[E::NR];
+        gather_free<E::NY>(v, c.gy, w_e);
+        lambda_slots<E>(tab, q, w_e, Lam);
+        const Jet1<E::M> L = weighted_res<E>(pc, s, Lam);
+        double gs[E::M];
+#pragma unroll
+        for (int k = 0; k < E::M; ++k) gs[k] = w * L.g[k];
+        scatter_fields<E>(tab, q, D, c, gs, out);
+#pragma unroll
+        for (int k = 0; k < E::NP; ++k) ksum[k] += gs[E::SK + k];
+      } else if (OP == OP_HPROD) {
+        Jet2<E::M> s[E::M];
+        point_state<E>(tab, c, x, q, s);
+        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        double ds[E::M];
+        field_direction<E>(tab, q, D, c, v, ds);
+        double gs[E::M];
+#pragma unroll
+        for (int k = 0; k < E::M; ++k) gs[k] = 0.0;
+        if (obj_weight != 0.0) {
+          const Jet2<E::M> F = I::f(pc, s);
+#pragma unroll
+          for (int k = 0; k < E::M; ++k) {
+            double a = 0.0;
+#pragma unroll
+            for (int l = 0; l < E::M; ++l) a = fma(F.h[Jet2<E::M>::idx(k, l)], ds[l], a);
+            gs[k] = (obj_weight * w) * a;
+          }
+        }
+        if (lambda != nullptr) {
+          double lam_e[E::NY], Lam[E::NR];
+          gather_free<E::NY>(lambda, c.gy, lam_e);
+          lambda_slots<E>(tab, q, lam_e, Lam);
+          const Jet2<E::M> L = weighted_res<E>(pc, s, Lam);
+#pragma unroll
+          for (int k = 0; k < E::M; ++k) {
+            double a = 0.0;
+#pragma unroll
+            for (int l = 0; l < E::M; ++l) a = fma(L.h[Jet2<E::M>::idx(k, l)], ds[l], a);
+            gs[k] = fma(w, a, gs[k]);
+          }
+        }
+        scatter_fields<E>(tab, q, D, c, gs, out);
+#pragma unroll
+        for (int k = 0; k < E::NP; ++k) ksum[k] += gs[E::SK + k];
+      }
+    }
+  }
+  // block-level reductions: objective partial sums (deterministic two-pass) and kappa entries
+  __shared__ double red[kWarpsPerCta];
+  if (OP == OP_OBJ) {
+    fsum = warp_sum(fsum);
+    if (lane == 0) red[warp] = fsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0.0;
+      for (int w = 0; w < kWarpsPerCta; ++w) a += red[w];
+      partials[blockIdx.x] = a;
+    }
+  } else if (E::NP > 0 && (OP == OP_GRAD || OP == OP_JTPROD || OP == OP_HPROD)) {
+#pragma unroll
+    for (int k = 0; k < E::NP; ++k) {
+      const double a = warp_sum(ksum[k]);
+      if (lane == 0) atomicAdd(out + k, a);
+    }
+  }
+}
+
+// fixed-order final sum of the per-CTA objective partials
+__global__ void k_sum_partials(const double* __restrict__ partials, int n, double* __restrict__ out) {
+  __shared__ double sh[256];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) a += partials[i];
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int d = 128; d > 0; d >>= 1) {
+    if (threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sh[0];
+}
+
+// ------------------------------------------------------------------ kappa blocks (dense, dof-indexed)
+// Jacobian k-block: Jk[i,k] = d c_i / d kappa_k, column-major ncon x p, accumulated with atomics
+// into a zero-filled block (/root/reference/src/jacobian_functions.jl:135-142).
+template <class E>
+__global__ void __launch_bounds__(kThreads)
+k_jac_kappa(const __grid_constant__ Tables<E> tab, const DevModel D, const double* __restrict__ x, double* __restrict__ vk) {
+  using I = typename E::Integrand;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t tile = (int64_t)blockIdx.x * kWarpsPerCta + warp; tile < D.ntiles; tile += (int64_t)gridDim.x * kWarpsPerCta) {
+    const int64_t cell = tile * 32 + lane;
+    const bool valid = cell < D.ncells;
+    if (!valid) continue;
+    Cell<E> c;
+    load_ids<E>(D, cell, valid, c);
+    gather_state<E>(D, x, valid, c);
+#pragma unroll 1
+    for (int q = 0; q < E::NQ; ++q) {
+      Jet1<E::M> s[E::M], R[E::NR];
+      point_state<E>(tab, c, x, q, s);
+      const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, true);
+      I::res(pc, s, R);
+#pragma unroll
+      for (int k = 0; k < E::NP; ++k)
+#pragma unroll
+        for (int i = 0; i < E::NY; ++i) {
+          double a = 0.0;
+#pragma unroll
+          for (int t = 0; t < E::NR; ++t) a = fma(test_slot<E>(tab, q, i, t), R[t].g[E::SK + k], a);
+          if (c.gy[i] > 0) atomicAdd(vk + ((int64_t)k * D.nfree_y + (c.gy[i] - 1)), tab.wdet[q] * a);
+        }
+    }
+  }
+}
+
+// Hessian k-trapezoid: entries (row i, kappa col j), j <= i, "i fastest"; prows = p (inde) or nvar.
+__device__ __forceinline__ int64_t trap_pos(int64_t i1, int j1, int64_t prows) {  // 1-based (i, j)
+  int64_t pos = 0;
+  for (int jj = 1; jj < j1; ++jj) pos += prows - jj + 1;
+  return pos + (i1 - j1);
+}
+// which: 0 = objective (scaled by obj_weight), 1 = constraints (lambda-weighted residual)
+template <class E>
+__global__ void __launch_bounds__(kThreads)
+k_hess_kappa(const __grid_constant__ Tables<E> tab, const DevModel D, const double* __restrict__ x,
+             const double* __restrict__ lambda, double obj_weight, int which, int64_t prows, double* __restrict__ vk) {
+  using I = typename E::Integrand;
+  using J2 = Jet2<E::M>;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NPS = E::NP > 0 ? E::NP : 1;
+  double kk[NPS][NPS];
+#pragma unroll
+  for (int a = 0; a < NPS; ++a)
+#pragma unroll
+    for (int b = 0; b < NPS; ++b) kk[a][b] = 0.0;
+  const bool cross = prows > E::NP;
+  for (int64_t tile = (int64_t)blockIdx.x * kWarpsPerCta + warp; tile < D.ntiles; tile += (int64_t)gridDim.x * kWarpsPerCta) {
+    const int64_t cell = tile * 32 + lane;
+    const bool valid = cell < D.ncells;
+    if (!valid) continue;
+    Cell<E> c;
+    load_ids<E>(D, cell, valid, c);
+    gather_state<E>(D, x, valid, c);
+#pragma unroll 1
+    for (int q = 0; q < E::NQ; ++q) {
+      Jet2<E::M> s[E::M];
+      point_state<E>(tab, c, x, q, s);
+      const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, true);
+      J2 L;
+      double scale = tab.wdet[q];
+      if (which == 0) { L = I::f(pc, s); scale *= obj_weight; }
+      else {
+        double lam_e[E::NY], Lam[E::NR];
+        gather_free<E::NY>(lambda, c.gy, lam_e);
+        lambda_slots<E>(tab, q, lam_e, Lam);
+        L = weighted_res<E>(pc, s, Lam);
+      }
+#pragma unroll
+      for (int j = 0; j < E::NP; ++j) {
+#pragma unroll
+        for (int i = j; i < E::NP; ++i) kk[i][j] += scale * L.h[J2::idx(E::SK + i, E::SK + j)];
+        if (cross) {
+#pragma unroll
+          for (int a = 0; a < E::NY; ++a) {
+            double v = 0.0;
+#pragma unroll
+            for (int k = 0; k < E::NB; ++k) v = fma(tab.By[q][a][k], L.h[J2::idx(k, E::SK + j)], v);
+            if (c.gy[a] > 0) atomicAdd(vk + trap_pos((int64_t)E::NP + c.gy[a], j + 1, prows), scale * v);
+          }
+#pragma unroll
+          for (int b = 0; b < E::NU; ++b) {
+            const double v = tab.Bu[q][b] * L.h[J2::idx(E::SU, E::SK + j)];
+            if (c.gu[b] > 0) atomicAdd(vk + trap_pos((int64_t)E::NP + D.nfree_y + c.gu[b], j + 1, prows), scale * v);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < E::NP; ++j)
+#pragma unroll
+    for (int i = j; i < E::NP; ++i) {
+      const double a = warp_sum(kk[i][j]);
+      if (lane == 0) atomicAdd(vk + trap_pos(i + 1, j + 1, prows), a);
+    }
+}
+
+}  // namespace pdenlp

@@ -1,0 +1,640 @@
+// pdenlp_cuda.cu — C ABI of libpdenlp_cuda.so (see include/pdenlp_cuda.h).
+//
+// Host side of the library: owns the device copy of the flattened model, picks the
+// template instantiation for the (integrand, element) pair, launches the kernels of
+// kernels.cuh on the caller's stream.  No CPU compute path exists: every entry point
+// needs an sm_100 device.
+#include "../../include/pdenlp_cuda.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace pdenlp;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(PDENLP_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));              \
+  } while (0)
+
+struct Launch {
+  cudaStream_t stream;
+  int sms;
+};
+
+// type-erased per-element operations
+struct Ops {
+  virtual ~Ops() {}
+  virtual int count(const DevModel& D, int32_t* counts, int32_t* flag, cudaStream_t s) = 0;
+  virtual int jac(const Launch& L, const DevModel& D, const double* x, double* vy, double* vu) = 0;
+  virtual int hess(const Launch& L, const DevModel& D, const double* x, const double* lam, double ow, double* vo, double* vc) = 0;
+  virtual int structure(const Launch& L, const DevModel& D, int kind, int64_t* r, int64_t* c, int64_t shift) = 0;
+  virtual int vec(const Launch& L, const DevModel& D, int op, const double* x, const double* lam, const double* v,
+                  double ow, double* out, double* partials, int* nblocks) = 0;
+  virtual int jac_kappa(const Launch& L, const DevModel& D, const double* x, double* vk) = 0;
+  virtual int hess_kappa(const Launch& L, const DevModel& D, const double* x, const double* lam, double ow, int which,
+                         int64_t prows, double* vk) = 0;
+  virtual int run_h() const = 0;
+};
+
+template <int RUN>
+constexpr int warps_for_run() {
+  // per-warp staging buffer of (32*RUN + 2) doubles; at most 8 warps, at most ~225 KB per CTA
+  return std::min(8, (225 * 1024) / ((32 * RUN + 2) * 8));
+}
+
+template <class E>
+struct OpsImpl : Ops {
+  Tables<E> tab;
+  bool attr_done = false;
+  static constexpr int WJ = warps_for_run<E::RUN_J>();
+  static constexpr int WH = warps_for_run<E::RUN_H>();
+  static constexpr size_t SMEM_J = (size_t)WJ * (32 * E::RUN_J + 2) * 8;
+  static constexpr size_t SMEM_H = (size_t)WH * (32 * E::RUN_H + 2) * 8;
+
+  int set_attrs() {
+    if (attr_done) return PDENLP_OK;
+    CU(cudaFuncSetAttribute(k_jac_coord<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_J));
+    CU(cudaFuncSetAttribute(k_hess_coord<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_H));
+    attr_done = true;
+    return PDENLP_OK;
+  }
+  int run_h() const override { return E::RUN_H; }
+  static int grid_for(int64_t ntiles, int warps, int cap) {
+    int64_t g = (ntiles + warps - 1) / warps;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(g, cap));
+  }
+  int count(const DevModel& D, int32_t* counts, int32_t* flag, cudaStream_t s) override {
+    k_count<E><<<grid_for(D.ntiles, kWarpsPerCta, 1 << 30), kThreads, 0, s>>>(D, counts, flag);
+    CU(cudaGetLastError());
+    return PDENLP_OK;
+  }
+  int jac(const Launch& L, const DevModel& D, const double* x, double* vy, double* vu) override {
+    if (int rc = set_attrs()) return rc;
+    k_jac_coord<E><<<grid_for(D.ntiles, WJ, L.sms), WJ * 32, SMEM_J, L.stream>>>(tab, D, x, vy, vu);
+    CU(cudaGetLastError());
+    return PDENLP_OK;
+  }
+  int hess(const Launch& L, const DevModel& D, const double* x, const double* lam, double ow, double* vo, double* vc) override {
+    if (int rc = set_attrs()) return rc;
+    k_hess_coord<E><<<grid_for(D.ntiles, WH, L.sms), WH * 32, SMEM_H, L.stream>>>(tab, D, x, lam, ow, vo, vc);
+    CU(cudaGetLastError());
+    return PDENLP_OK;
+  }
+  int structure(const Launch& L, const DevModel& D, int kind, int64_t* r, int64_t* c, int64_t shift) override {
+    k_structure<E><<<grid_for(D.ntiles, kWarpsPerCta, 1 << 30), kThreads, 0, L.stream>>>(D, kind, r, c, shift);
+    CU(cudaGetLastError());
+    return PDENLP_OK;
+  }
+  int vec(const Launch& L, const DevModel& D, int op, const double* x, const double* lam, const double* v, double ow,
+          double* out, double* partials, int* nblocks) override {
+    const int g = grid_for(D.ntiles, kWarpsPerCta, L.sms * 8);
+    *nblocks = g;
+    switch (op) {
+      case OP_OBJ: k_vector<E, OP_OBJ><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, v, ow, out, partials); break;
+      case OP_GRAD: k_vector<E, OP_GRAD><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, v, ow, out, partials); break;
+      case OP_CONS: k_vector<E, OP_CONS><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, v, ow, out, partials); break;
+      case OP_JPROD: k_vector<E, OP_JPROD><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, v, ow, out, partials); break;
+      case OP_JTPROD: k_vector<E, OP_JTPROD><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, v, ow, out, partials); break;
+      case OP_HPROD: k_vector<E, OP_HPROD><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, v, ow, out, partials); break;
+      default: return fail(PDENLP_EINVAL, "bad vector op");
+    }
+    CU(cudaGetLastError());
+    return PDENLP_OK;
+  }
+  int jac_kappa(const Launch& L, const DevModel& D, const double* x, double* vk) override {
+    if (E::NP == 0) return PDENLP_OK;
+    k_jac_kappa<E><<<grid_for(D.ntiles, kWarpsPerCta, L.sms * 8), kThreads, 0, L.stream>>>(tab, D, x, vk);
+    CU(cudaGetLastError());
+    return PDENLP_OK;
+  }
+  int hess_kappa(const Launch& L, const DevModel& D, const double* x, const double* lam, double ow, int which,
+                 int64_t prows, double* vk) override {
+    if (E::NP == 0) return PDENLP_OK;
+    k_hess_kappa<E><<<grid_for(D.ntiles, kWarpsPerCta, L.sms * 8), kThreads, 0, L.stream>>>(tab, D, x, lam, ow, which, prows, vk);
+    CU(cudaGetLastError());
+    return PDENLP_OK;
+  }
+};
+
+template <class E>
+Ops* make_ops(const pdenlp_desc& d) {
+  auto* o = new OpsImpl<E>();
+  for (int q = 0; q < E::NQ; ++q) {
+    o->tab.wdet[q] = d.wdet[q];
+    for (int a = 0; a < E::NY; ++a) {
+      o->tab.By[q][a][0] = d.phi_y[q * E::NY + a];
+      for (int k = 0; k < E::DIM; ++k) o->tab.By[q][a][1 + k] = d.grad_y[(q * E::NY + a) * E::DIM + k];
+    }
+    for (int b = 0; b < E::NUS; ++b) o->tab.Bu[q][b] = (E::NU > 0) ? d.phi_u[q * E::NU + b] : 0.0;
+  }
+  for (int i = 0; i < 8; ++i) o->tab.par[i] = d.params[i];
+  return o;
+}
+
+// the closed set of (integrand, dim, ny, nu, nq, nparam) instantiations
+Ops* select_ops(const pdenlp_desc& d) {
+  const int I = d.integrand, dim = d.dim, ny = d.ny, nu = d.nu, nq = d.nq, np = d.nparam;
+#define CASE(INT, DIMV, NYV, NUV, NQV, NPV, TYPE) \
+  if (I == INT && dim == DIMV && ny == NYV && nu == NUV && nq == NQV && np == NPV) return make_ops<Elem<TYPE, NYV, NUV, NQV>>(d);
+  CASE(PDENLP_MEMBRANE, 2, 9, 4, 1, 0, Membrane<2>)
+  CASE(PDENLP_MEMBRANE, 2, 4, 4, 1, 0, Membrane<2>)
+  CASE(PDENLP_POISSON_BOLTZMANN, 2, 4, 4, 1, 0, PoissonBoltzmann<2>)
+  CASE(PDENLP_BURGER_LIN, 1, 2, 2, 1, 0, BurgerLin)
+  CASE(PDENLP_BURGER_NL, 1, 2, 2, 1, 1, BurgerNl)
+  using KP2 = KappaPoisson<2, false>;
+  using KP2U = KappaPoisson<2, true>;
+  using KP3U = KappaPoisson<3, true>;
+  CASE(PDENLP_KAPPA_POISSON, 2, 4, 0, 4, 2, KP2)
+  CASE(PDENLP_KAPPA_POISSON, 2, 4, 4, 4, 2, KP2U)
+  CASE(PDENLP_KAPPA_POISSON, 3, 8, 8, 8, 2, KP3U)
+#undef CASE
+  return nullptr;
+}
+
+}  // namespace
+
+struct pdenlp_model {
+  pdenlp_desc d;  // scalar fields only are meaningful after create
+  pdenlp_info info;
+  Ops* ops = nullptr;
+  DevModel dm;
+  int device = 0;
+  int sms = 148;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+  bool inde = false;
+  // owned device memory
+  std::vector<void*> owned;
+  // scratch
+  double* partials = nullptr;
+  double* scalar = nullptr;
+  int32_t npartials = 0;
+  // host-memspace staging
+  double *sx = nullptr, *slam = nullptr, *sv = nullptr, *sout = nullptr;
+  int64_t sout_len = 0;
+  // timing
+  bool timing = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_valid = false;
+};
+
+namespace {
+
+template <class T>
+int dev_upload(pdenlp_model* m, const T* host, size_t n, T** out) {
+  *out = nullptr;
+  if (n == 0) { CU(cudaMalloc((void**)out, 16)); m->owned.push_back(*out); return PDENLP_OK; }
+  CU(cudaMalloc((void**)out, n * sizeof(T)));
+  m->owned.push_back(*out);
+  CU(cudaMemcpy(*out, host, n * sizeof(T), cudaMemcpyHostToDevice));
+  return PDENLP_OK;
+}
+
+int ensure_stage(pdenlp_model* m, double** p, int64_t n) {
+  if (*p == nullptr) {
+    CU(cudaMalloc((void**)p, std::max<int64_t>(n, 2) * 8));
+    m->owned.push_back(*p);
+  }
+  return PDENLP_OK;
+}
+int ensure_out(pdenlp_model* m, int64_t n) {
+  if (m->sout_len < n) {
+    if (m->sout) { cudaFree(m->sout); m->owned.erase(std::find(m->owned.begin(), m->owned.end(), (void*)m->sout)); }
+    m->sout = nullptr;
+    CU(cudaMalloc((void**)&m->sout, std::max<int64_t>(n, 2) * 8));
+    m->owned.push_back(m->sout);
+    m->sout_len = n;
+  }
+  return PDENLP_OK;
+}
+
+// resolve an input vector to a device pointer (staging it for PDENLP_MEM_HOST)
+int in_ptr(pdenlp_model* m, const double* user, int64_t n, double** stage, const double** dev) {
+  if (user == nullptr) { *dev = nullptr; return PDENLP_OK; }
+  if (m->d.memspace == PDENLP_MEM_DEVICE) { *dev = user; return PDENLP_OK; }
+  if (int rc = ensure_stage(m, stage, n)) return rc;
+  CU(cudaMemcpyAsync(*stage, user, n * 8, cudaMemcpyHostToDevice, m->stream));
+  *dev = *stage;
+  return PDENLP_OK;
+}
+int out_ptr(pdenlp_model* m, double* user, int64_t n, double** dev) {
+  if (m->d.memspace == PDENLP_MEM_DEVICE) { *dev = user; return PDENLP_OK; }
+  if (int rc = ensure_out(m, n)) return rc;
+  *dev = m->sout;
+  return PDENLP_OK;
+}
+int out_finish(pdenlp_model* m, double* user, int64_t n) {
+  if (m->d.memspace == PDENLP_MEM_DEVICE) return PDENLP_OK;
+  CU(cudaMemcpyAsync(user, m->sout, n * 8, cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  return PDENLP_OK;
+}
+
+struct Scope {  // device + timing bracket of one callback
+  pdenlp_model* m;
+  int prev = -1;
+  explicit Scope(pdenlp_model* mm) : m(mm) {
+    cudaGetDevice(&prev);
+    if (prev != m->device) cudaSetDevice(m->device);
+    if (m->timing) { cudaEventRecord(m->ev0, m->stream); }
+  }
+  ~Scope() {
+    if (m->timing) { cudaEventRecord(m->ev1, m->stream); m->ev_valid = true; }
+    if (prev != m->device && prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+const char* pdenlp_last_error(void) { return g_err.c_str(); }
+int pdenlp_abi_version(void) { return PDENLP_ABI_VERSION; }
+
+int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
+  if (!desc || !out) return fail(PDENLP_EINVAL, "null argument");
+  *out = nullptr;
+  if (desc->abi_version != PDENLP_ABI_VERSION) return fail(PDENLP_EINVAL, "abi_version mismatch");
+  if (desc->ncells <= 0 || desc->nfree_y <= 0) return fail(PDENLP_EINVAL, "empty model");
+  if (!desc->cell_dofs_y || !desc->phi_y || !desc->grad_y || !desc->wdet) return fail(PDENLP_EINVAL, "missing arrays");
+  if (desc->nu > 0 && (!desc->cell_dofs_u || !desc->phi_u)) return fail(PDENLP_EINVAL, "missing control arrays");
+  if (desc->ncells + 31 >= ((int64_t)1 << 36)) return fail(PDENLP_EINVAL, "too many cells");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (ndev == 0) return fail(PDENLP_ECUDA, "no CUDA device (libpdenlp_cuda has no CPU fallback)");
+  int dev = desc->device;
+  if (dev < 0) CU(cudaGetDevice(&dev));
+  if (dev >= ndev) return fail(PDENLP_EINVAL, "bad device ordinal");
+  int prev = 0;
+  CU(cudaGetDevice(&prev));
+  CU(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) { cudaSetDevice(prev); return fail(PDENLP_ECUDA, "libpdenlp_cuda is built for sm_100a only"); }
+
+  Ops* ops = select_ops(*desc);
+  if (!ops) { cudaSetDevice(prev); return fail(PDENLP_EUNSUPPORTED, "(integrand, dim, ny, nu, nq, nparam) is outside the closed set of instantiated kernels"); }
+
+  auto* m = new pdenlp_model();
+  m->d = *desc;
+  m->ops = ops;
+  m->device = dev;
+  m->sms = prop.multiProcessorCount;
+  m->inde = desc->integrand == PDENLP_KAPPA_POISSON;  // MixedEnergyFETerm(..., inde = true)
+  int rc = PDENLP_OK;
+  auto bail = [&](int code) { pdenlp_destroy(m); cudaSetDevice(prev); return code; };
+
+  const int64_t nc = desc->ncells, ldc = (nc + 31) / 32 * 32;
+  const int ny = desc->ny, nu = desc->nu;
+  // SoA transpose of the cell->dof maps
+  {
+    std::vector<int32_t> soa((size_t)ldc * ny, -1);
+    for (int64_t c = 0; c < nc; ++c)
+      for (int a = 0; a < ny; ++a) soa[(size_t)a * ldc + c] = desc->cell_dofs_y[c * ny + a];
+    int32_t* p;
+    if ((rc = dev_upload(m, soa.data(), soa.size(), &p))) return bail(rc);
+    m->dm.dofs_y = p;
+  }
+  {
+    std::vector<int32_t> soa((size_t)ldc * std::max(nu, 1), -1);
+    for (int64_t c = 0; c < nc; ++c)
+      for (int b = 0; b < nu; ++b) soa[(size_t)b * ldc + c] = desc->cell_dofs_u[c * nu + b];
+    int32_t* p;
+    if ((rc = dev_upload(m, soa.data(), soa.size(), &p))) return bail(rc);
+    m->dm.dofs_u = p;
+  }
+  // validate ids against the declared sizes (cheap, host side)
+  for (int64_t i = 0; i < nc * ny; ++i) {
+    const int32_t g = desc->cell_dofs_y[i];
+    if (g == 0 || g > desc->nfree_y || -g > desc->ndir_y) return bail(fail(PDENLP_EINVAL, "state dof id out of range"));
+  }
+  for (int64_t i = 0; i < nc * nu; ++i) {
+    const int32_t g = desc->cell_dofs_u[i];
+    if (g == 0 || g > desc->nfree_u || -g > desc->ndir_u) return bail(fail(PDENLP_EINVAL, "control dof id out of range"));
+  }
+  double* dp;
+  if ((rc = dev_upload(m, desc->dir_y, (size_t)desc->ndir_y, &dp))) return bail(rc);
+  m->dm.dir_y = dp;
+  if ((rc = dev_upload(m, desc->dir_u, (size_t)desc->ndir_u, &dp))) return bail(rc);
+  m->dm.dir_u = dp;
+  if (desc->ncoef > 0 && desc->coef) {
+    if (desc->ncoef != 2) return bail(fail(PDENLP_EINVAL, "ncoef must be 0 or 2"));
+    if ((rc = dev_upload(m, desc->coef, (size_t)2 * nc * desc->nq, &dp))) return bail(rc);
+    m->dm.coef = dp;
+  } else {
+    m->dm.coef = nullptr;
+  }
+  m->dm.ncells = nc;
+  m->dm.ldc = ldc;
+  m->dm.nfree_y = desc->nfree_y;
+  m->dm.nfree_u = desc->nfree_u;
+  m->dm.ntiles = (int32_t)(ldc / 32);
+  m->dm.nparam = desc->nparam;
+  m->dm.base_jy = m->dm.base_ju = m->dm.base_h = nullptr;
+
+  // per-tile entry counts -> exclusive scans (segment offsets)
+  {
+    const int64_t nt = m->dm.ntiles;
+    int32_t *dcounts = nullptr, *dflag = nullptr;
+    if (cudaMalloc((void**)&dcounts, nt * 3 * 4) != cudaSuccess || cudaMalloc((void**)&dflag, 4) != cudaSuccess)
+      return bail(fail(PDENLP_ENOMEM, "cudaMalloc failed"));
+    cudaMemset(dflag, 0, 4);
+    rc = ops->count(m->dm, dcounts, dflag, nullptr);
+    std::vector<int32_t> hc((size_t)nt * 3);
+    int32_t hflag = 0;
+    cudaError_t e1 = cudaMemcpy(hc.data(), dcounts, nt * 3 * 4, cudaMemcpyDeviceToHost);
+    cudaError_t e2 = cudaMemcpy(&hflag, dflag, 4, cudaMemcpyDeviceToHost);
+    cudaFree(dcounts);
+    cudaFree(dflag);
+    if (rc) return bail(rc);
+    if (e1 != cudaSuccess || e2 != cudaSuccess)
+      return bail(fail(PDENLP_ECUDA, std::string("count kernel: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)));
+    if (hflag) return bail(fail(PDENLP_EINVAL, "a cell repeats a dof id; not supported"));
+    std::vector<int64_t> b0(nt + 1), b1(nt + 1), b2(nt + 1);
+    b0[0] = b1[0] = b2[0] = 0;
+    for (int64_t t = 0; t < nt; ++t) {
+      b0[t + 1] = b0[t] + hc[t * 3 + 0];
+      b1[t + 1] = b1[t] + hc[t * 3 + 1];
+      b2[t + 1] = b2[t] + hc[t * 3 + 2];
+    }
+    int64_t* ip;
+    if ((rc = dev_upload(m, b0.data(), b0.size(), &ip))) return bail(rc);
+    m->dm.base_jy = ip;
+    if ((rc = dev_upload(m, b1.data(), b1.size(), &ip))) return bail(rc);
+    m->dm.base_ju = ip;
+    if ((rc = dev_upload(m, b2.data(), b2.size(), &ip))) return bail(rc);
+    m->dm.base_h = ip;
+    const int64_t p = desc->nparam, n = p + desc->nfree_y + desc->nfree_u;
+    pdenlp_info& I = m->info;
+    I.nvar = n;
+    I.ncon = desc->nfree_y;
+    I.nnzj_k = desc->nfree_y * p;
+    I.nnzj_y = b0[nt];
+    I.nnzj_u = b1[nt];
+    I.nnzj = I.nnzj_k + I.nnzj_y + I.nnzj_u;
+    I.nnzh_fe = b2[nt];
+    I.nnzh_k_obj = p == 0 ? 0 : (m->inde ? p * (p + 1) / 2 : p * (p + 1) / 2 + (n - p) * p);
+    I.nnzh_k_con = p == 0 ? 0 : p * (p + 1) / 2 + (n - p) * p;
+    I.nnzh_obj = I.nnzh_k_obj + I.nnzh_fe;
+    I.nnzh = I.nnzh_obj + I.nnzh_k_con + I.nnzh_fe;
+  }
+  m->npartials = m->sms * 8;
+  if (cudaMalloc((void**)&m->partials, (size_t)m->npartials * 8) != cudaSuccess || cudaMalloc((void**)&m->scalar, 16) != cudaSuccess)
+    return bail(fail(PDENLP_ENOMEM, "cudaMalloc failed"));
+  m->owned.push_back(m->partials);
+  m->owned.push_back(m->scalar);
+  if (cudaEventCreate(&m->ev0) != cudaSuccess || cudaEventCreate(&m->ev1) != cudaSuccess)
+    return bail(fail(PDENLP_ECUDA, "cudaEventCreate failed"));
+  // the host arrays of the description are not referenced after create
+  m->d.cell_dofs_y = m->d.cell_dofs_u = nullptr;
+  m->d.dir_y = m->d.dir_u = m->d.phi_y = m->d.grad_y = m->d.phi_u = m->d.wdet = m->d.coef = nullptr;
+  cudaSetDevice(prev);
+  *out = m;
+  return PDENLP_OK;
+}
+
+int pdenlp_destroy(pdenlp_model* m) {
+  if (!m) return PDENLP_OK;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(m->device);
+  for (void* p : m->owned) cudaFree(p);
+  if (m->ev0) cudaEventDestroy(m->ev0);
+  if (m->ev1) cudaEventDestroy(m->ev1);
+  delete m->ops;
+  delete m;
+  cudaSetDevice(prev);
+  return PDENLP_OK;
+}
+
+int pdenlp_get_info(const pdenlp_model* m, pdenlp_info* info) {
+  if (!m || !info) return fail(PDENLP_EINVAL, "null argument");
+  *info = m->info;
+  return PDENLP_OK;
+}
+int pdenlp_set_stream(pdenlp_model* m, void* s) {
+  if (!m) return fail(PDENLP_EINVAL, "null model");
+  m->stream = (cudaStream_t)s;
+  return PDENLP_OK;
+}
+int pdenlp_sync(pdenlp_model* m) {
+  if (!m) return fail(PDENLP_EINVAL, "null model");
+  CU(cudaStreamSynchronize(m->stream));
+  return PDENLP_OK;
+}
+int pdenlp_malloc(void** ptr, int64_t bytes) {
+  if (!ptr || bytes < 0) return fail(PDENLP_EINVAL, "bad argument");
+  CU(cudaMalloc(ptr, (size_t)std::max<int64_t>(bytes, 16)));
+  return PDENLP_OK;
+}
+int pdenlp_free(void* ptr) { CU(cudaFree(ptr)); return PDENLP_OK; }
+int pdenlp_memcpy_h2d(void* dst, const void* src, int64_t bytes) { CU(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyHostToDevice)); return PDENLP_OK; }
+int pdenlp_memcpy_d2h(void* dst, const void* src, int64_t bytes) { CU(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost)); return PDENLP_OK; }
+int pdenlp_host_alloc(void** ptr, int64_t bytes) {
+  if (!ptr || bytes < 0) return fail(PDENLP_EINVAL, "bad argument");
+  CU(cudaHostAlloc(ptr, (size_t)std::max<int64_t>(bytes, 16), cudaHostAllocDefault));
+  return PDENLP_OK;
+}
+int pdenlp_host_free(void* ptr) { CU(cudaFreeHost(ptr)); return PDENLP_OK; }
+
+int pdenlp_obj(pdenlp_model* m, const double* x, double* f) {
+  if (!m || !x || !f) return fail(PDENLP_EINVAL, "null argument");
+  if (!m->dm.coef) return fail(PDENLP_EINVAL, "obj needs the coefficient fields (desc.coef)");
+  Scope sc(m);
+  const double* dx;
+  if (int rc = in_ptr(m, x, m->info.nvar, &m->sx, &dx)) return rc;
+  Launch L{m->stream, m->sms};
+  int nb = 0;
+  if (int rc = m->ops->vec(L, m->dm, OP_OBJ, dx, nullptr, nullptr, 1.0, nullptr, m->partials, &nb)) return rc;
+  k_sum_partials<<<1, 256, 0, m->stream>>>(m->partials, nb, m->scalar);
+  CU(cudaGetLastError());
+  m->launches += 2;
+  CU(cudaMemcpyAsync(f, m->scalar, 8, cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  return PDENLP_OK;
+}
+
+static int vec_call(pdenlp_model* m, int op, const double* x, const double* lam, const double* v, int64_t nv, double ow,
+                    double* out, int64_t nout, bool need_coef) {
+  if (!m || !x || !out) return fail(PDENLP_EINVAL, "null argument");
+  if (need_coef && !m->dm.coef) return fail(PDENLP_EINVAL, "this callback needs the coefficient fields (desc.coef)");
+  Scope sc(m);
+  const double *dx, *dl, *dv;
+  double* dout;
+  if (int rc = in_ptr(m, x, m->info.nvar, &m->sx, &dx)) return rc;
+  if (int rc = in_ptr(m, lam, m->info.ncon, &m->slam, &dl)) return rc;
+  if (int rc = in_ptr(m, v, nv, &m->sv, &dv)) return rc;
+  if (int rc = out_ptr(m, out, nout, &dout)) return rc;
+  CU(cudaMemsetAsync(dout, 0, (size_t)nout * 8, m->stream));  // assemble_vector!/coo_prod! zero-fill first
+  Launch L{m->stream, m->sms};
+  int nb = 0;
+  if (int rc = m->ops->vec(L, m->dm, op, dx, dl, dv, ow, dout, m->partials, &nb)) return rc;
+  m->launches += 1;
+  return out_finish(m, out, nout);
+}
+
+int pdenlp_grad(pdenlp_model* m, const double* x, double* g) {
+  return vec_call(m, OP_GRAD, x, nullptr, nullptr, 0, 1.0, g, m ? m->info.nvar : 0, true);
+}
+int pdenlp_cons(pdenlp_model* m, const double* x, double* c) {
+  return vec_call(m, OP_CONS, x, nullptr, nullptr, 0, 1.0, c, m ? m->info.ncon : 0, true);
+}
+int pdenlp_jprod(pdenlp_model* m, const double* x, const double* v, double* Jv) {
+  if (!v) return fail(PDENLP_EINVAL, "null argument");
+  return vec_call(m, OP_JPROD, x, nullptr, v, m ? m->info.nvar : 0, 1.0, Jv, m ? m->info.ncon : 0, m && m->d.nparam > 0);
+}
+int pdenlp_jtprod(pdenlp_model* m, const double* x, const double* v, double* Jtv) {
+  if (!v) return fail(PDENLP_EINVAL, "null argument");
+  return vec_call(m, OP_JTPROD, x, nullptr, v, m ? m->info.ncon : 0, 1.0, Jtv, m ? m->info.nvar : 0, m && m->d.nparam > 0);
+}
+int pdenlp_hprod(pdenlp_model* m, const double* x, const double* lambda, double obj_weight, const double* v, double* Hv) {
+  if (!v) return fail(PDENLP_EINVAL, "null argument");
+  return vec_call(m, OP_HPROD, x, lambda, v, m ? m->info.nvar : 0, obj_weight, Hv, m ? m->info.nvar : 0, m && m->d.nparam > 0);
+}
+
+int pdenlp_jac_coord(pdenlp_model* m, const double* x, double* vals) {
+  if (!m || !x || !vals) return fail(PDENLP_EINVAL, "null argument");
+  Scope sc(m);
+  const double* dx;
+  double* dv;
+  if (int rc = in_ptr(m, x, m->info.nvar, &m->sx, &dx)) return rc;
+  if (int rc = out_ptr(m, vals, m->info.nnzj, &dv)) return rc;
+  Launch L{m->stream, m->sms};
+  if (m->info.nnzj_k > 0) {
+    if (!m->dm.coef) return fail(PDENLP_EINVAL, "the kappa block needs the coefficient fields (desc.coef)");
+    CU(cudaMemsetAsync(dv, 0, (size_t)m->info.nnzj_k * 8, m->stream));
+    if (int rc = m->ops->jac_kappa(L, m->dm, dx, dv)) return rc;
+    m->launches += 1;
+  }
+  double* vy = dv + m->info.nnzj_k;
+  double* vu = vy + m->info.nnzj_y;
+  if (int rc = m->ops->jac(L, m->dm, dx, vy, vu)) return rc;
+  m->launches += 1;
+  return out_finish(m, vals, m->info.nnzj);
+}
+
+int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda, double obj_weight, double* vals) {
+  if (!m || !x || !vals) return fail(PDENLP_EINVAL, "null argument");
+  Scope sc(m);
+  const double *dx, *dl;
+  double* dv;
+  if (int rc = in_ptr(m, x, m->info.nvar, &m->sx, &dx)) return rc;
+  if (int rc = in_ptr(m, lambda, m->info.ncon, &m->slam, &dl)) return rc;
+  if (int rc = out_ptr(m, vals, m->info.nnzh, &dv)) return rc;
+  Launch L{m->stream, m->sms};
+  const pdenlp_info& I = m->info;
+  double* vko = dv;
+  double* vfo = vko + I.nnzh_k_obj;
+  double* vkc = vfo + I.nnzh_fe;
+  double* vfc = vkc + I.nnzh_k_con;
+  if (I.nnzh_k_obj + I.nnzh_k_con > 0) {
+    if (!m->dm.coef) return fail(PDENLP_EINVAL, "the kappa blocks need the coefficient fields (desc.coef)");
+    CU(cudaMemsetAsync(vko, 0, (size_t)I.nnzh_k_obj * 8, m->stream));
+    CU(cudaMemsetAsync(vkc, 0, (size_t)I.nnzh_k_con * 8, m->stream));
+    if (int rc = m->ops->hess_kappa(L, m->dm, dx, nullptr, obj_weight, 0, m->inde ? m->d.nparam : I.nvar, vko)) return rc;
+    m->launches += 1;
+    if (dl) {
+      if (int rc = m->ops->hess_kappa(L, m->dm, dx, dl, 1.0, 1, I.nvar, vkc)) return rc;
+      m->launches += 1;
+    }
+  }
+  if (!dl) CU(cudaMemsetAsync(vfc, 0, (size_t)I.nnzh_fe * 8, m->stream));  // GridapPDENLPModel.jl:295-297
+  if (int rc = m->ops->hess(L, m->dm, dx, dl, obj_weight, vfo, dl ? vfc : nullptr)) return rc;
+  m->launches += 1;
+  return out_finish(m, vals, I.nnzh);
+}
+
+static int structure_call(pdenlp_model* m, bool hess, int64_t* rows, int64_t* cols) {
+  if (!m || !rows || !cols) return fail(PDENLP_EINVAL, "null argument");
+  Scope sc(m);
+  const pdenlp_info& I = m->info;
+  const int64_t nnz = hess ? I.nnzh : I.nnzj;
+  int64_t *dr = rows, *dc = cols;
+  const bool host = m->d.memspace == PDENLP_MEM_HOST;
+  if (host) {
+    CU(cudaMalloc((void**)&dr, std::max<int64_t>(nnz, 2) * 8));
+    CU(cudaMalloc((void**)&dc, std::max<int64_t>(nnz, 2) * 8));
+  }
+  Launch L{m->stream, m->sms};
+  const int64_t p = m->d.nparam, n = I.nvar;
+  int rc = PDENLP_OK;
+  // dense kappa blocks are tiny index patterns: build on the host and copy
+  auto put = [&](int64_t off, const std::vector<int64_t>& r, const std::vector<int64_t>& c) -> int {
+    if (r.empty()) return PDENLP_OK;
+    CU(cudaMemcpyAsync(dr + off, r.data(), r.size() * 8, cudaMemcpyHostToDevice, m->stream));
+    CU(cudaMemcpyAsync(dc + off, c.data(), c.size() * 8, cudaMemcpyHostToDevice, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    return PDENLP_OK;
+  };
+  auto trapezoid = [&](int64_t prows, std::vector<int64_t>& r, std::vector<int64_t>& c) {
+    for (int64_t j = 1; j <= p; ++j)
+      for (int64_t i = j; i <= prows; ++i) { r.push_back(i); c.push_back(j); }
+  };
+  if (!hess) {
+    std::vector<int64_t> r, c;
+    for (int64_t j = 1; j <= p; ++j)
+      for (int64_t i = 1; i <= I.ncon; ++i) { r.push_back(i); c.push_back(j); }
+    if (!rc) rc = put(0, r, c);
+    if (!rc) rc = m->ops->structure(L, m->dm, 0, dr + I.nnzj_k, dc + I.nnzj_k, p);
+    if (!rc && m->d.nu > 0) rc = m->ops->structure(L, m->dm, 1, dr + I.nnzj_k + I.nnzj_y, dc + I.nnzj_k + I.nnzj_y, p);
+    m->launches += 1 + (m->d.nu > 0);
+  } else {
+    std::vector<int64_t> r, c;
+    trapezoid(m->inde ? p : n, r, c);
+    if (!rc) rc = put(0, r, c);
+    r.clear(); c.clear();
+    trapezoid(n, r, c);
+    if (!rc) rc = put(I.nnzh_obj, r, c);
+    if (!rc) rc = m->ops->structure(L, m->dm, 2, dr + I.nnzh_k_obj, dc + I.nnzh_k_obj, p);
+    if (!rc) rc = m->ops->structure(L, m->dm, 2, dr + I.nnzh_obj + I.nnzh_k_con, dc + I.nnzh_obj + I.nnzh_k_con, p);
+    m->launches += 2;
+  }
+  if (host) {
+    if (!rc) {
+      cudaError_t e = cudaMemcpyAsync(rows, dr, nnz * 8, cudaMemcpyDeviceToHost, m->stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(cols, dc, nnz * 8, cudaMemcpyDeviceToHost, m->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+      if (e != cudaSuccess) rc = fail(PDENLP_ECUDA, cudaGetErrorString(e));
+    }
+    cudaFree(dr);
+    cudaFree(dc);
+  }
+  return rc;
+}
+int pdenlp_jac_structure(pdenlp_model* m, int64_t* rows, int64_t* cols) { return structure_call(m, false, rows, cols); }
+int pdenlp_hess_structure(pdenlp_model* m, int64_t* rows, int64_t* cols) { return structure_call(m, true, rows, cols); }
+
+int pdenlp_launch_count(const pdenlp_model* m, int64_t* launches) {
+  if (!m || !launches) return fail(PDENLP_EINVAL, "null argument");
+  *launches = m->launches;
+  return PDENLP_OK;
+}
+int pdenlp_set_timing(pdenlp_model* m, int32_t enabled) {
+  if (!m) return fail(PDENLP_EINVAL, "null model");
+  m->timing = enabled != 0;
+  m->ev_valid = false;
+  return PDENLP_OK;
+}
+int pdenlp_last_kernel_ms(pdenlp_model* m, float* ms) {
+  if (!m || !ms) return fail(PDENLP_EINVAL, "null argument");
+  if (!m->ev_valid) return fail(PDENLP_EINVAL, "no timed callback yet (pdenlp_set_timing)");
+  CU(cudaEventSynchronize(m->ev1));
+  CU(cudaEventElapsedTime(ms, m->ev0, m->ev1));
+  return PDENLP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,389 @@
+"""Host-side mirror of the reference interface for the hot path.
+
+``GridapPDENLPModel`` here exposes the NLPModels callbacks of the reference's
+``GridapPDENLPModel`` (/root/reference/src/GridapPDENLPModel.jl:219-661) with the
+same names, argument meaning, error behaviour (``DimensionError`` before any
+work — the reference's ``@lencheck``) and ``Counters`` bookkeeping
+(increment own counter; nested evaluations do not count:
+src/GridapPDENLPModel.jl:319-320,353-354,426-427,483-484,515-516).  Julia's
+``f!`` becomes ``f_`` (in-place, torch convention); ``f`` allocates.
+
+Every callback body is exactly one call into libpdenlp_cuda.so.  Vectors are
+torch CUDA float64 tensors (memspace "device") or numpy / torch CPU arrays
+(memspace "host": the library stages them, copies inside the call).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import capi
+from .flatten import FlatModel, flatten
+from .flatten import hess_structure as _host_hess_structure  # noqa: F401 (re-exported for tests)
+from .flatten import jac_structure as _host_jac_structure  # noqa: F401
+from .problems import ProblemSpec
+
+
+class DimensionError(Exception):
+    """NLPModels.DimensionError(name, dim_expected, dim_found)."""
+
+    def __init__(self, name, dim_expected, dim_found):
+        super().__init__(f"DimensionError: Input {name} should have length {dim_expected} not {dim_found}")
+        self.name, self.dim_expected, self.dim_found = name, dim_expected, dim_found
+
+
+_COUNTERS = (
+    "neval_obj", "neval_grad", "neval_cons", "neval_cons_lin", "neval_cons_nln", "neval_jcon", "neval_jgrad",
+    "neval_jac", "neval_jac_lin", "neval_jac_nln", "neval_jprod", "neval_jprod_lin", "neval_jprod_nln",
+    "neval_jtprod", "neval_jtprod_lin", "neval_jtprod_nln", "neval_hess", "neval_hprod", "neval_jhess", "neval_jhprod",
+)
+
+
+class Counters:
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        for c in _COUNTERS:
+            setattr(self, c, 0)
+
+    def as_dict(self):
+        return {c: getattr(self, c) for c in _COUNTERS}
+
+
+@dataclass
+class NLPModelMeta:
+    nvar: int
+    ncon: int
+    nnzj: int
+    nnzh: int
+    lin_nnzj: int = 0
+    nln_nnzj: int = 0
+    nlin: int = 0
+    nnln: int = 0
+    name: str = "Generic"
+    minimize: bool = True
+    x0: Optional[np.ndarray] = None
+    lvar: Optional[np.ndarray] = None
+    uvar: Optional[np.ndarray] = None
+    lcon: Optional[np.ndarray] = None
+    ucon: Optional[np.ndarray] = None
+    y0: Optional[np.ndarray] = None
+
+
+@dataclass
+class PDENLPMeta:
+    """The fields of the reference's PDENLPMeta that exist without Gridap
+    (src/GridapPDENLPModel.jl:24-49)."""
+    nvar_pde: int
+    nvar_con: int
+    nparam: int
+    nnzh_obj: int
+    nnzj_k: int
+    nnzj_y: int
+    nnzj_u: int
+    nnzh_fe: int
+    nnzh_k_obj: int
+    nnzh_k_con: int
+
+
+def _is_torch(a):
+    return isinstance(a, torch.Tensor)
+
+
+class GridapPDENLPModel:
+    """Drop-in mirror of the reference model for one cell slab on one GPU.
+
+    Parameters
+    ----------
+    spec : ProblemSpec — what the Gridap user code describes (mesh, spaces, f, res).
+    device : torch device string.
+    cell_range : (c0, c1) slab of cells owned by this handle (default: all).
+    memspace : "device" (vectors are CUDA tensors, used in place) or "host".
+    """
+
+    def __init__(self, spec: ProblemSpec, device: str = "cuda:0", cell_range=None, memspace: str = "device",
+                 with_coef: bool = True, flat: Optional[FlatModel] = None):
+        self.spec = spec
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("GridapPDENLPModel needs a CUDA device: the hot path has no CPU implementation")
+        self.memspace = memspace
+        fm = flat if flat is not None else flatten(spec, cell_range, with_coef=with_coef)
+        self.flat = fm
+        ms = capi.MEM_DEVICE if memspace == "device" else capi.MEM_HOST
+        self.handle = capi.Handle(fm, device=self.device.index if self.device.index is not None else 0,
+                                  memspace=ms, with_coef=with_coef)
+        I = self.handle.info
+        self.meta = NLPModelMeta(
+            nvar=I.nvar, ncon=I.ncon, nnzj=I.nnzj, nnzh=I.nnzh, lin_nnzj=0, nln_nnzj=I.nnzj, nlin=0, nnln=I.ncon,
+            name=spec.name, x0=np.zeros(I.nvar), lvar=np.full(I.nvar, -np.inf), uvar=np.full(I.nvar, np.inf),
+            lcon=np.zeros(I.ncon), ucon=np.zeros(I.ncon), y0=np.zeros(I.ncon),
+        )
+        self.pdemeta = PDENLPMeta(
+            nvar_pde=fm.nfree_y, nvar_con=fm.nfree_u, nparam=fm.nparam, nnzh_obj=I.nnzh_obj, nnzj_k=I.nnzj_k,
+            nnzj_y=I.nnzj_y, nnzj_u=I.nnzj_u, nnzh_fe=I.nnzh_fe, nnzh_k_obj=I.nnzh_k_obj, nnzh_k_con=I.nnzh_k_con,
+        )
+        self.counters = Counters()
+        self._use_current_stream()
+
+    # ------------------------------------------------------------------ plumbing
+    def _use_current_stream(self):
+        self.handle.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        self.handle.close()
+
+    def launch_count(self) -> int:
+        return self.handle.launch_count()
+
+    def _new(self, n, like=None, dtype=torch.float64):
+        if self.memspace == "device":
+            return torch.empty(n, dtype=dtype, device=self.device)
+        return np.empty(n, dtype=np.float64 if dtype == torch.float64 else np.int64)
+
+    def _lencheck(self, n, **vecs):
+        for name, v in vecs.items():
+            if v.shape[0] != n or v.ndim != 1:
+                raise DimensionError(name, n, v.shape[0] if v.ndim == 1 else tuple(v.shape))
+
+    def _in(self, v):
+        """Pointer of an input vector (contiguous float64 in the model's memory space)."""
+        if v is None:
+            return None, None
+        if self.memspace == "device":
+            if not _is_torch(v) or v.device != self.device:
+                v = torch.as_tensor(np.asarray(v.cpu() if _is_torch(v) else v), dtype=torch.float64).to(self.device)
+            if v.dtype != torch.float64 or not v.is_contiguous():
+                v = v.to(torch.float64).contiguous()  # views with stride != 1 are staged
+            return v.data_ptr(), v
+        a = v.detach().cpu().numpy() if _is_torch(v) else np.asarray(v)
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        return a.ctypes.data, a
+
+    def _out(self, v):
+        """(pointer, buffer, needs_copy_back) for an output vector."""
+        if self.memspace == "device":
+            if not _is_torch(v) or v.device != self.device or v.dtype != torch.float64:
+                raise TypeError("output must be a float64 CUDA tensor on the model's device")
+            if v.is_contiguous():
+                return v.data_ptr(), v, False
+            tmp = torch.empty(v.shape, dtype=v.dtype, device=v.device)
+            return tmp.data_ptr(), tmp, True
+        if _is_torch(v):
+            if v.is_contiguous() and v.dtype == torch.float64:
+                return v.data_ptr(), v, False
+            tmp = torch.empty(v.shape, dtype=torch.float64)
+            return tmp.data_ptr(), tmp, True
+        if v.flags.c_contiguous and v.dtype == np.float64:
+            return v.ctypes.data, v, False
+        tmp = np.empty(v.shape, dtype=np.float64)
+        return tmp.ctypes.data, tmp, True
+
+    @staticmethod
+    def _finish(user, buf, copy_back):
+        if copy_back:
+            if _is_torch(user):
+                user.copy_(buf if _is_torch(buf) else torch.from_numpy(buf))
+            else:
+                user[...] = buf
+        return user
+
+    # ------------------------------------------------------------------ obj / grad / cons
+    def obj(self, x) -> float:
+        self._lencheck(self.meta.nvar, x=x)
+        self.counters.neval_obj += 1
+        self._use_current_stream()
+        px, kx = self._in(x)
+        return self.handle.obj(px)
+
+    def grad_(self, x, g):
+        self._lencheck(self.meta.nvar, x=x, g=g)
+        self.counters.neval_grad += 1
+        self._use_current_stream()
+        px, kx = self._in(x)
+        pg, bg, cb = self._out(g)
+        self.handle.grad(px, pg)
+        return self._finish(g, bg, cb)
+
+    def grad(self, x):
+        return self.grad_(x, self._new(self.meta.nvar))
+
+    def cons_nln_(self, x, c):
+        self._lencheck(self.meta.nvar, x=x)
+        self._lencheck(self.meta.nnln, c=c)
+        self.counters.neval_cons_nln += 1
+        self._use_current_stream()
+        px, kx = self._in(x)
+        pc, bc, cb = self._out(c)
+        self.handle.cons(px, pc)
+        return self._finish(c, bc, cb)
+
+    def cons_(self, x, c):
+        """NLPModels generic cons!: nlin = 0 for FEOperatorFromWeakForm models
+        (src/additional_constructors.jl:213-223), so this is cons_nln! on the whole vector."""
+        self._lencheck(self.meta.nvar, x=x)
+        self._lencheck(self.meta.ncon, c=c)
+        self.counters.neval_cons += 1
+        return self.cons_nln_(x, c)
+
+    def cons(self, x):
+        return self.cons_(x, self._new(self.meta.ncon))
+
+    # ------------------------------------------------------------------ Jacobian
+    def jac_nln_coord_(self, x, vals):
+        self._lencheck(self.meta.nvar, x=x)
+        self._lencheck(self.meta.nln_nnzj, vals=vals)
+        self.counters.neval_jac_nln += 1
+        self._use_current_stream()
+        px, kx = self._in(x)
+        pv, bv, cb = self._out(vals)
+        self.handle.jac_coord(px, pv)
+        return self._finish(vals, bv, cb)
+
+    def jac_coord_(self, x, vals):
+        self._lencheck(self.meta.nvar, x=x)
+        self._lencheck(self.meta.nnzj, vals=vals)
+        self.counters.neval_jac += 1
+        return self.jac_nln_coord_(x, vals)
+
+    def jac_coord(self, x):
+        return self.jac_coord_(x, self._new(self.meta.nnzj))
+
+    def jac_nln_structure_(self, rows, cols):
+        self._lencheck(self.meta.nln_nnzj, rows=rows, cols=cols)
+        return self._structure(False, rows, cols)
+
+    jac_structure_ = jac_nln_structure_
+
+    def jac_structure(self):
+        return self.jac_structure_(self._new(self.meta.nnzj, dtype=torch.int64), self._new(self.meta.nnzj, dtype=torch.int64))
+
+    def _structure(self, hess, rows, cols):
+        self._use_current_stream()
+        ptrs = []
+        for v in (rows, cols):
+            if _is_torch(v):
+                if v.dtype != torch.int64 or not v.is_contiguous():
+                    raise TypeError("structure outputs must be contiguous int64")
+                ptrs.append(v.data_ptr())
+            else:
+                if v.dtype != np.int64 or not v.flags.c_contiguous:
+                    raise TypeError("structure outputs must be contiguous int64")
+                ptrs.append(v.ctypes.data)
+        (self.handle.hess_structure if hess else self.handle.jac_structure)(ptrs[0], ptrs[1])
+        return rows, cols
+
+    def jprod_nln_(self, x, v, Jv):
+        self._lencheck(self.meta.nvar, x=x, v=v)
+        self._lencheck(self.meta.nnln, Jv=Jv)
+        self.counters.neval_jprod_nln += 1
+        self._use_current_stream()
+        px, kx = self._in(x)
+        pv, kv = self._in(v)
+        po, bo, cb = self._out(Jv)
+        self.handle.jprod(px, pv, po)
+        return self._finish(Jv, bo, cb)
+
+    def jprod_(self, x, v, Jv):
+        self._lencheck(self.meta.nvar, x=x, v=v)
+        self._lencheck(self.meta.ncon, Jv=Jv)
+        self.counters.neval_jprod += 1
+        return self.jprod_nln_(x, v, Jv)
+
+    def jprod(self, x, v):
+        return self.jprod_(x, v, self._new(self.meta.ncon))
+
+    def jtprod_nln_(self, x, v, Jtv):
+        self._lencheck(self.meta.nvar, x=x, Jtv=Jtv)
+        self._lencheck(self.meta.nnln, v=v)
+        self.counters.neval_jtprod_nln += 1
+        self._use_current_stream()
+        px, kx = self._in(x)
+        pv, kv = self._in(v)
+        po, bo, cb = self._out(Jtv)
+        self.handle.jtprod(px, pv, po)
+        return self._finish(Jtv, bo, cb)
+
+    def jtprod_(self, x, v, Jtv):
+        self._lencheck(self.meta.nvar, x=x, Jtv=Jtv)
+        self._lencheck(self.meta.ncon, v=v)
+        self.counters.neval_jtprod += 1
+        return self.jtprod_nln_(x, v, Jtv)
+
+    def jtprod(self, x, v):
+        return self.jtprod_(x, v, self._new(self.meta.nvar))
+
+    # ------------------------------------------------------------------ Hessian
+    def hess_coord_(self, x, *args, obj_weight: float = 1.0):
+        """hess_coord!(nlp, x, vals; obj_weight) or hess_coord!(nlp, x, y, vals; obj_weight)."""
+        if len(args) == 1:
+            lam, vals = None, args[0]
+        elif len(args) == 2:
+            lam, vals = args
+        else:
+            raise TypeError("hess_coord_(x, vals) or hess_coord_(x, y, vals)")
+        self._lencheck(self.meta.nvar, x=x)
+        if lam is not None:
+            self._lencheck(self.meta.ncon, y=lam)
+        self._lencheck(self.meta.nnzh, vals=vals)
+        self.counters.neval_hess += 1
+        self._use_current_stream()
+        px, kx = self._in(x)
+        pl, kl = self._in(lam)
+        pv, bv, cb = self._out(vals)
+        self.handle.hess_coord(px, pl, obj_weight, pv)
+        return self._finish(vals, bv, cb)
+
+    def hess_coord(self, x, y=None, obj_weight: float = 1.0):
+        vals = self._new(self.meta.nnzh)
+        return self.hess_coord_(x, vals, obj_weight=obj_weight) if y is None else self.hess_coord_(x, y, vals, obj_weight=obj_weight)
+
+    def hess_structure_(self, rows, cols):
+        self._lencheck(self.meta.nnzh, rows=rows, cols=cols)
+        return self._structure(True, rows, cols)
+
+    def hess_structure(self):
+        return self.hess_structure_(self._new(self.meta.nnzh, dtype=torch.int64), self._new(self.meta.nnzh, dtype=torch.int64))
+
+    def hprod_(self, x, *args, obj_weight: float = 1.0):
+        """hprod!(nlp, x, v, Hv; obj_weight) or hprod!(nlp, x, y, v, Hv; obj_weight)."""
+        if len(args) == 2:
+            lam, (v, Hv) = None, args
+        elif len(args) == 3:
+            lam, v, Hv = args
+        else:
+            raise TypeError("hprod_(x, v, Hv) or hprod_(x, y, v, Hv)")
+        self._lencheck(self.meta.nvar, x=x, v=v, Hv=Hv)
+        if lam is not None:
+            self._lencheck(self.meta.ncon, y=lam)
+        self.counters.neval_hprod += 1
+        self._use_current_stream()
+        px, kx = self._in(x)
+        pl, kl = self._in(lam)
+        pv, kv = self._in(v)
+        po, bo, cb = self._out(Hv)
+        self.handle.hprod(px, pl, obj_weight, pv, po)
+        return self._finish(Hv, bo, cb)
+
+    def hprod(self, x, *args, obj_weight: float = 1.0):
+        Hv = self._new(self.meta.nvar)
+        return self.hprod_(x, *args, Hv, obj_weight=obj_weight)
+
+    # ------------------------------------------------------------------ operators (jac_op!/hess_op!)
+    def jac_op(self, x):
+        """Returns (prod, tprod) closures: v -> J(x) v and w -> J(x)^T w
+        (src/GridapPDENLPModel.jl:610-634; matrix-free here)."""
+        return (lambda v: self.jprod(x, v)), (lambda w: self.jtprod(x, w))
+
+    def hess_op(self, x, y=None, obj_weight: float = 1.0):
+        if y is None:
+            return lambda v: self.hprod(x, v, obj_weight=obj_weight)
+        return lambda v: self.hprod(x, y, v, obj_weight=obj_weight)
+
+    def reset_(self):
+        self.counters.reset()
+        return self

@@ -1,0 +1,137 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.
+
+Bar (BASELINE.json north_star): structure bit-exact; values within a relative
+tolerance of 1e-12 in FP64.  "Relative" is taken per COO segment / vector:
+|gpu - oracle| <= RTOL * max|oracle| (entries that are exactly zero in one
+evaluation order and round-off in the other cannot satisfy an entry-wise bound).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def _close(a, b, what):
+    a = np.asarray(a); b = np.asarray(b)
+    assert a.shape == b.shape, what
+    scale = max(np.abs(b).max() if b.size else 0.0, 1e-300)
+    err = np.abs(a - b).max() / scale if b.size else 0.0
+    assert err <= RTOL, f"{what}: max rel err {err:.3e}"
+
+
+def _cases(pkg):
+    return {
+        "membrane3": lambda: pkg.controlelasticmembrane(3),
+        "membrane8": lambda: pkg.controlelasticmembrane(8),
+        "membrane37": lambda: pkg.controlelasticmembrane(37),
+        "membrane100": lambda: pkg.controlelasticmembrane(100),
+        "pb_l2_9": lambda: pkg.poissonboltzman2d(9),
+        "pb_h1_33": lambda: pkg.poissonboltzman2d(33, "H1"),
+        "burger_lin_70": lambda: pkg.burger1d(70),
+        "burger_nl_70": lambda: pkg.burger1d_param(70),
+        "kappa2d_5": lambda: pkg.poissonmixed(5),
+        "kappa2d_u_6": lambda: pkg.poissonmixed(6, 2, True),
+        "kappa3d_u_4": lambda: pkg.poissonmixed(4, 3, True),
+    }
+
+
+CASE_NAMES = ["membrane3", "membrane8", "membrane37", "membrane100", "pb_l2_9", "pb_h1_33", "burger_lin_70",
+              "burger_nl_70", "kappa2d_5", "kappa2d_u_6", "kappa3d_u_4"]
+
+
+@pytest.fixture(scope="module", params=CASE_NAMES)
+def case(request, pkg, oracle_mod, cuda_lib):
+    from pdenlp_b200.model import GridapPDENLPModel
+    spec = _cases(pkg)[request.param]()
+    nlp = GridapPDENLPModel(spec, device="cuda:0")
+    orc = oracle_mod.Oracle(spec)
+    rng = np.random.default_rng(1998)
+    x = rng.uniform(-1, 1, nlp.meta.nvar)
+    if spec.nparam:
+        x[: spec.nparam] = 1 + 0.1 * rng.uniform(-1, 1, spec.nparam)
+    lam = np.random.default_rng(1999).uniform(-1, 1, nlp.meta.ncon)
+    v = np.random.default_rng(2000).uniform(-1, 1, nlp.meta.nvar)
+    yield dict(name=request.param, spec=spec, nlp=nlp, orc=orc, x=x, lam=lam, v=v)
+    nlp.close()
+
+
+def _d(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_sizes(case):
+    nlp, orc = case["nlp"], case["orc"]
+    assert (nlp.meta.nvar, nlp.meta.ncon, nlp.meta.nnzj, nlp.meta.nnzh) == (orc.nvar, orc.ncon, orc.nnzj, orc.nnzh)
+    assert nlp.pdemeta.nnzh_obj == orc.nnzh_obj
+
+
+def test_structure_bit_exact(case):
+    nlp, orc = case["nlp"], case["orc"]
+    r, c = nlp.jac_structure()
+    ro, co = orc.jac_structure()
+    assert np.array_equal(r.cpu().numpy(), ro) and np.array_equal(c.cpu().numpy(), co)
+    r, c = nlp.hess_structure()
+    ro, co = orc.hess_structure()
+    assert np.array_equal(r.cpu().numpy(), ro) and np.array_equal(c.cpu().numpy(), co)
+
+
+@pytest.mark.parametrize("xkind", ["rand", "zeros", "ones"])
+def test_jac_coord(case, xkind):
+    nlp, orc = case["nlp"], case["orc"]
+    x = {"rand": case["x"], "zeros": np.zeros_like(case["x"]), "ones": np.ones_like(case["x"])}[xkind]
+    _close(nlp.jac_coord(_d(x)).cpu().numpy(), orc.jac_coord(x), "jac_coord")
+
+
+@pytest.mark.parametrize("ow", [1.0, 0.0, 0.37])
+def test_hess_coord_lagrangian(case, ow):
+    nlp, orc, x, lam = case["nlp"], case["orc"], case["x"], case["lam"]
+    got = nlp.hess_coord(_d(x), _d(lam), obj_weight=ow).cpu().numpy()
+    ref = orc.hess_coord(x, lam, ow)
+    no = orc.nnzh_obj
+    _close(got[:no], ref[:no], "hess_coord obj part")
+    _close(got[no:], ref[no:], "hess_coord cons part")
+
+
+def test_hess_coord_objective_only(case):
+    nlp, orc, x = case["nlp"], case["orc"], case["x"]
+    got = nlp.hess_coord(_d(x), obj_weight=0.37).cpu().numpy()
+    ref = orc.hess_coord(x, None, 0.37)
+    _close(got, ref, "hess_coord(x)")
+    assert np.all(got[orc.nnzh_obj:] == 0.0)  # tail zero-filled, GridapPDENLPModel.jl:295-297
+
+
+def test_obj_grad_cons(case):
+    nlp, orc, x = case["nlp"], case["orc"], case["x"]
+    f, fo = nlp.obj(_d(x)), orc.obj(x)
+    assert abs(f - fo) <= RTOL * max(abs(fo), 1e-300)
+    _close(nlp.grad(_d(x)).cpu().numpy(), orc.grad(x), "grad")
+    _close(nlp.cons(_d(x)).cpu().numpy(), orc.cons(x), "cons")
+
+
+def test_products(case):
+    nlp, orc, x, lam, v = case["nlp"], case["orc"], case["x"], case["lam"], case["v"]
+    _close(nlp.jprod(_d(x), _d(v)).cpu().numpy(), orc.jprod(x, v), "jprod")
+    _close(nlp.jtprod(_d(x), _d(lam)).cpu().numpy(), orc.jtprod(x, lam), "jtprod")
+    _close(nlp.hprod(_d(x), _d(lam), _d(v), obj_weight=0.37).cpu().numpy(), orc.hprod(x, v, lam, 0.37), "hprod(x,y,v)")
+    _close(nlp.hprod(_d(x), _d(v), obj_weight=0.37).cpu().numpy(), orc.hprod(x, v, None, 0.37), "hprod(x,v)")
+    assert torch.all(nlp.hprod(_d(x), _d(v), obj_weight=0.0) == 0)  # GridapPDENLPModel.jl:313-316
+
+
+def test_host_memspace_matches_device(case, pkg):
+    """PDENLP_MEM_HOST: numpy in/out through the library's staging copies."""
+    from pdenlp_b200.model import GridapPDENLPModel
+    if case["name"] not in ("membrane8", "burger_nl_70"):
+        pytest.skip("one small case per family is enough")
+    nlp_h = GridapPDENLPModel(case["spec"], device="cuda:0", memspace="host")
+    x, lam = case["x"], case["lam"]
+    jd = case["nlp"].jac_coord(_d(x)).cpu().numpy()
+    hd = case["nlp"].hess_coord(_d(x), _d(lam), obj_weight=0.5).cpu().numpy()
+    assert np.array_equal(nlp_h.jac_coord(x), jd)
+    assert np.array_equal(nlp_h.hess_coord(x, lam, obj_weight=0.5), hd)
+    r, c = nlp_h.jac_structure()
+    ro, co = case["orc"].jac_structure()
+    assert np.array_equal(r, ro) and np.array_equal(c, co)
+    nlp_h.close()
