@@ -193,6 +193,18 @@ __device__ __forceinline__ void count_entries(const Cell<E>& c, int& njy, int& n
   nh = h;
 }
 
+// Closed-form counts, valid when the dof ids of a cell are pairwise distinct (checked once at
+// create time by k_count): among distinct ids exactly one of (i,j),(j,i) passes gidcol<=gidrow.
+template <class E>
+__device__ __forceinline__ void closed_counts(const Cell<E>& c, int& fy, int& fu, int& nh) {
+  fy = 0; fu = 0;
+#pragma unroll
+  for (int a = 0; a < E::NY; ++a) fy += c.gy[a] > 0;
+#pragma unroll
+  for (int b = 0; b < E::NU; ++b) fu += c.gu[b] > 0;
+  nh = fy * (fy + 1) / 2 + fu * fy + fu * (fu + 1) / 2;
+}
+
 // per-tile counts, used once at create time to build the segment offsets
 template <class E>
 __global__ void __launch_bounds__(kThreads) k_count(DevModel D, int32_t* __restrict__ counts /*[ntiles][3]*/, int32_t* __restrict__ flag) {
@@ -205,7 +217,9 @@ __global__ void __launch_bounds__(kThreads) k_count(DevModel D, int32_t* __restr
   load_ids<E>(D, valid ? cell : 0, valid, c);
   int njy, nju, nh;
   count_entries<E>(c, njy, nju, nh);
-  if (nh > E::RUN_H) atomicExch(flag, 1);  // repeated dof ids inside one cell are not supported
+  int fy, fu, nh_closed;
+  closed_counts<E>(c, fy, fu, nh_closed);
+  if (nh != nh_closed) atomicExch(flag, 1);  // repeated dof ids inside one cell are not supported
   for (int d = 16; d > 0; d >>= 1) {
     njy += __shfl_xor_sync(0xffffffffu, njy, d);
     nju += __shfl_xor_sync(0xffffffffu, nju, d);
@@ -254,12 +268,34 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
   constexpr int STAGE = 32 * E::RUN_J + 2;
   SegStage<double> st{smem + warp * STAGE};
 
-  for (int64_t tile = (int64_t)blockIdx.x * nwarps + warp; tile < D.ntiles; tile += (int64_t)gridDim.x * nwarps) {
+  const int64_t stride = (int64_t)gridDim.x * nwarps;
+  int64_t tile = (int64_t)blockIdx.x * nwarps + warp;
+  if (tile >= D.ntiles) return;
+  // Register software pipeline over tiles: while tile t is processed, the gathered values of
+  // tile t+stride and the dof ids of tile t+2*stride are already in flight (the id -> value
+  // gather is a two-level dependent load chain; without this it is ~30% of the warp's time).
+  Cell<E> c, n;
+  {
     const int64_t cell = tile * 32 + lane;
     const bool valid = cell < D.ncells;
-    Cell<E> c;
     load_ids<E>(D, valid ? cell : 0, valid, c);
     gather_state<E>(D, x, valid, c);
+    const int64_t ncell = (tile + stride) * 32 + lane;
+    const bool nvalid = (tile + stride) < D.ntiles && ncell < D.ncells;
+    load_ids<E>(D, nvalid ? ncell : 0, nvalid, n);
+  }
+  while (true) {
+    const int64_t cell = tile * 32 + lane;
+    const bool valid = cell < D.ncells;
+    const int64_t tnext = tile + stride;
+    const bool has_next = tnext < D.ntiles;
+    Cell<E> nn;
+    {
+      gather_state<E>(D, x, has_next && (tnext * 32 + lane) < D.ncells, n);
+      const int64_t c2 = (tnext + stride) * 32 + lane;
+      const bool v2 = (tnext + stride) < D.ntiles && c2 < D.ncells;
+      load_ids<E>(D, v2 ? c2 : 0, v2, nn);
+    }
 
     int fy = 0, fu = 0;
 #pragma unroll
@@ -340,6 +376,13 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
       }
       st.release(gdst, total, pad, lane);
     }
+    if (!has_next) break;
+    c = n;
+#pragma unroll
+    for (int a = 0; a < E::NY; ++a) n.gy[a] = nn.gy[a];
+#pragma unroll
+    for (int b = 0; b < E::NUS; ++b) n.gu[b] = nn.gu[b];
+    tile = tnext;
   }
   if (lane == 0) bulk_wait_all();
 }
@@ -442,14 +485,39 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
   constexpr int STAGE = 32 * E::RUN_H + 2;
   SegStage<double> st{smem + warp * STAGE};
 
-  for (int64_t tile = (int64_t)blockIdx.x * nwarps + warp; tile < D.ntiles; tile += (int64_t)gridDim.x * nwarps) {
+  const int64_t stride = (int64_t)gridDim.x * nwarps;
+  int64_t tile = (int64_t)blockIdx.x * nwarps + warp;
+  if (tile >= D.ntiles) return;
+  // Register software pipeline over tiles: while tile t is processed, the gathered values of
+  // tile t+stride and the dof ids of tile t+2*stride are already in flight (the id -> value
+  // gather is a two-level dependent load chain; without this it is ~30% of the warp's time).
+  Cell<E> c, n;
+  {
     const int64_t cell = tile * 32 + lane;
     const bool valid = cell < D.ncells;
-    Cell<E> c;
     load_ids<E>(D, valid ? cell : 0, valid, c);
     gather_state<E>(D, x, valid, c);
-    int njy, nju, cnt;
-    count_entries<E>(c, njy, nju, cnt);
+    const int64_t ncell = (tile + stride) * 32 + lane;
+    const bool nvalid = (tile + stride) < D.ntiles && ncell < D.ncells;
+    load_ids<E>(D, nvalid ? ncell : 0, nvalid, n);
+  }
+  double lam_e[E::NY], nlam[E::NY];
+  if (vals_con != nullptr) gather_free<E::NY>(lambda, c.gy, lam_e);
+  while (true) {
+    const int64_t cell = tile * 32 + lane;
+    const bool valid = cell < D.ncells;
+    const int64_t tnext = tile + stride;
+    const bool has_next = tnext < D.ntiles;
+    Cell<E> nn;
+    {
+      gather_state<E>(D, x, has_next && (tnext * 32 + lane) < D.ncells, n);
+      if (vals_con != nullptr) gather_free<E::NY>(lambda, n.gy, nlam);
+      const int64_t c2 = (tnext + stride) * 32 + lane;
+      const bool v2 = (tnext + stride) < D.ntiles && c2 < D.ncells;
+      load_ids<E>(D, v2 ? c2 : 0, v2, nn);
+    }
+    int fy, fu, cnt;
+    closed_counts<E>(c, fy, fu, cnt);
     const int incl = warp_incl_scan(cnt, lane);
     const int total = __shfl_sync(0xffffffffu, incl, 31);
     const int64_t tb = D.base_h[tile];
@@ -471,8 +539,6 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
       st.release(gdst, total, pad, lane);
     }
     if (vals_con != nullptr) {
-      double lam_e[E::NY];
-      gather_free<E::NY>(lambda, c.gy, lam_e);
       double* gdst = vals_con + tb;
       const int pad = (int)((reinterpret_cast<uintptr_t>(gdst) >> 3) & 1);
       st.acquire(lane);
@@ -490,6 +556,13 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
       }
       st.release(gdst, total, pad, lane);
     }
+    if (!has_next) break;
+    c = n;
+#pragma unroll
+    for (int a = 0; a < E::NY; ++a) { n.gy[a] = nn.gy[a]; lam_e[a] = nlam[a]; }
+#pragma unroll
+    for (int b = 0; b < E::NUS; ++b) n.gu[b] = nn.gu[b];
+    tile = tnext;
   }
   if (lane == 0) bulk_wait_all();
 }
