@@ -1,0 +1,174 @@
+"""Cell-slab sharding of one model over the GPUs of a box (one process per GPU).
+
+SURVEY §8(e): cells are independent units and are numbered x-fastest, so a
+contiguous cell range is a slab of mesh rows/planes.  Rank r owns cells
+[c_r, c_{r+1}) and therefore ONE contiguous sub-range of every COO segment:
+``jac_coord!`` / ``hess_coord!`` need no communication — each rank writes its own
+slice, the concatenation over ranks (segment by segment) is the global stream.
+
+The dof-indexed outputs (``obj``, ``grad!``, ``cons!``, ``jprod!``, ``jtprod!``,
+``hprod!``) are partial sums per slab; only the *interface* dofs (touched by more
+than one slab: one mesh row of state dofs + one row of control dofs per cut) and
+the kappa entries need a reduction: they are packed into one small buffer and
+all-reduced (NCCL over NVLink on the GPUs, gloo in the CPU tests).  After the
+reduction every rank holds the exact value of every dof its slab touches and
+zero elsewhere; ``allgather_owned`` assembles the replicated vector when a
+caller wants one.
+
+``local`` is any object with the GridapPDENLPModel callback interface: the CUDA
+model in production, an oracle-backed stand-in in the world_size-2 gloo tests.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def partition_cells(ncells: int, world: int, align: int = 32) -> List[Tuple[int, int]]:
+    """Contiguous slabs with boundaries aligned to the 32-cell tiles of the kernels."""
+    ntiles = (ncells + align - 1) // align
+    out = []
+    for r in range(world):
+        t0, t1 = ntiles * r // world, ntiles * (r + 1) // world
+        out.append((min(t0 * align, ncells), min(t1 * align, ncells)))
+    return out
+
+
+def _touched(ids: np.ndarray, nfree: int, ranges: Sequence[Tuple[int, int]]) -> np.ndarray:
+    """(world, nfree) boolean: dof touched by slab r."""
+    out = np.zeros((len(ranges), nfree), dtype=bool)
+    for r, (c0, c1) in enumerate(ranges):
+        g = ids[c0:c1].reshape(-1)
+        g = g[g > 0]
+        out[r, g - 1] = True
+    return out
+
+
+class SlabLayout:
+    """Index sets of the slab decomposition, in x-layout (0-based, kappa first)."""
+
+    def __init__(self, spec, world: int):
+        self.world = world
+        self.ranges = partition_cells(spec.model.ncells, world)
+        p = spec.nparam
+        ny = spec.Ypde.nfree
+        nu = spec.Ycon.nfree if spec.Ycon is not None else 0
+        ty = _touched(spec.Ypde.cell_dof_ids, ny, self.ranges)
+        self.touch_y = ty
+        iface_y = np.nonzero(ty.sum(axis=0) > 1)[0]
+        if nu:
+            tu = _touched(spec.Ycon.cell_dof_ids, nu, self.ranges)
+            iface_u = np.nonzero(tu.sum(axis=0) > 1)[0]
+        else:
+            tu = np.zeros((world, 0), dtype=bool)
+            iface_u = np.zeros(0, dtype=np.int64)
+        self.touch_u = tu
+        # interface entries of an nvar-vector (kappa entries are shared by every slab)
+        self.iface_var = np.concatenate([np.arange(p), p + iface_y, p + ny + iface_u]).astype(np.int64)
+        # interface entries of an ncon-vector (rows = free dofs of the test space Xpde = Ypde ids)
+        self.iface_con = iface_y.astype(np.int64)
+        # ownership for allgather_owned: the lowest rank touching a dof owns it
+        self.owner_y = np.argmax(ty, axis=0)
+        self.owner_u = np.argmax(tu, axis=0) if nu else np.zeros(0, dtype=np.int64)
+        self.p, self.ny, self.nu = p, ny, nu
+
+
+class ShardedModel:
+    def __init__(self, spec, local, layout: SlabLayout, rank: int, group=None):
+        self.spec, self.local, self.layout, self.rank, self.group = spec, local, layout, rank, group
+        self.world = layout.world
+        self._idx_cache = {}
+
+    # ---- helpers ---------------------------------------------------------
+    def _idx(self, which: str, like):
+        key = (which, like.device if isinstance(like, torch.Tensor) else "np")
+        if key not in self._idx_cache:
+            idx = self.layout.iface_var if which == "var" else self.layout.iface_con
+            t = torch.from_numpy(idx)
+            if isinstance(like, torch.Tensor):
+                t = t.to(like.device)
+            self._idx_cache[key] = t
+        return self._idx_cache[key]
+
+    def _reduce_interface(self, vec, which: str):
+        """Sum the interface entries of a slab-partial vector over the ranks."""
+        if self.world == 1:
+            return vec
+        t = vec if isinstance(vec, torch.Tensor) else torch.from_numpy(vec)
+        idx = self._idx(which, t)
+        if idx.numel():
+            buf = t.index_select(0, idx).contiguous()
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+            t.index_copy_(0, idx, buf)
+        return vec
+
+    # ---- scalar ----------------------------------------------------------
+    def obj(self, x) -> float:
+        f = self.local.obj(x)
+        if self.world == 1:
+            return f
+        dev = x.device if isinstance(x, torch.Tensor) else "cpu"
+        t = torch.tensor([f], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return float(t.item())
+
+    # ---- dof-indexed outputs --------------------------------------------
+    def grad_(self, x, g):
+        return self._reduce_interface(self.local.grad_(x, g), "var")
+
+    def cons_(self, x, c):
+        return self._reduce_interface(self.local.cons_(x, c), "con")
+
+    def jprod_(self, x, v, Jv):
+        return self._reduce_interface(self.local.jprod_(x, v, Jv), "con")
+
+    def jtprod_(self, x, v, Jtv):
+        return self._reduce_interface(self.local.jtprod_(x, v, Jtv), "var")
+
+    def hprod_(self, x, *args, obj_weight: float = 1.0):
+        return self._reduce_interface(self.local.hprod_(x, *args, obj_weight=obj_weight), "var")
+
+    # ---- COO streams: local slices, no communication ---------------------
+    def jac_coord_(self, x, vals):
+        return self.local.jac_coord_(x, vals)
+
+    def hess_coord_(self, x, *args, obj_weight: float = 1.0):
+        return self.local.hess_coord_(x, *args, obj_weight=obj_weight)
+
+    def segment_sizes(self) -> dict:
+        pm = self.local.pdemeta
+        return {"jy": pm.nnzj_y, "ju": pm.nnzj_u, "hfe": pm.nnzh_fe}
+
+    def global_segment_offsets(self) -> dict:
+        """Offset of this rank's slice inside each global FE segment (exclusive scan over ranks)."""
+        sizes = self.segment_sizes()
+        keys = sorted(sizes)
+        mine = torch.tensor([sizes[k] for k in keys], dtype=torch.int64)
+        if self.world == 1:
+            return {k: 0 for k in keys}
+        dev = self.local.device if hasattr(self.local, "device") and dist.get_backend(self.group) == "nccl" else "cpu"
+        mine = mine.to(dev)
+        allv = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(allv, mine, group=self.group)
+        allv = torch.stack(allv).cpu().numpy()
+        off = allv[: self.rank].sum(axis=0) if self.rank else np.zeros(len(keys), dtype=np.int64)
+        return {k: int(o) for k, o in zip(keys, off)}
+
+    def allgather_owned(self, vec, which: str = "var"):
+        """Replicated full vector from interface-reduced slab vectors: every dof is taken from
+        its owner (the lowest rank touching it).  Debug/verification helper, O(n) traffic."""
+        if self.world == 1:
+            return vec
+        L = self.layout
+        t = (vec if isinstance(vec, torch.Tensor) else torch.from_numpy(vec)).clone()
+        if which == "var":
+            own = np.concatenate([np.zeros(L.p, dtype=np.int64), L.owner_y, L.owner_u])
+        else:
+            own = L.owner_y
+        mask = torch.from_numpy(own == self.rank).to(t.device)
+        t = torch.where(mask, t, torch.zeros_like(t))
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t

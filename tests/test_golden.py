@@ -1,0 +1,62 @@
+"""Committed golden fixtures (tests/golden/*.npz, made by tests/golden/make_golden.py from the
+oracle — see its docstring for provenance): the oracle must reproduce them on CPU and the CUDA
+path must match them on the GPU.  Structure bit-exact; values within 1e-12 relative."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FILES = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
+RTOL = 1e-12
+
+
+def _spec(pkg, name):
+    import importlib.util
+    sp = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+    mod = importlib.util.module_from_spec(sp); sp.loader.exec_module(mod)
+    return mod.CASES[name](pkg)
+
+
+def _close(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    scale = max(np.abs(b).max() if b.size else 0.0, 1e-300)
+    return a.shape == b.shape and (np.abs(a - b).max() / scale if b.size else 0.0) <= RTOL
+
+
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-4] for f in FILES])
+def test_oracle_reproduces_golden(path, pkg, oracle_mod):
+    g = np.load(path)
+    o = oracle_mod.Oracle(_spec(pkg, os.path.basename(path)[:-4]), nthreads=1)
+    x, lam, v, ow = g["x"], g["lam"], g["v"], float(g["obj_weight"])
+    r, c = o.jac_structure(); assert np.array_equal(r, g["jac_rows"]) and np.array_equal(c, g["jac_cols"])
+    r, c = o.hess_structure(); assert np.array_equal(r, g["hess_rows"]) and np.array_equal(c, g["hess_cols"])
+    assert _close(o.obj(x), g["obj"]) and _close(o.grad(x), g["grad"]) and _close(o.cons(x), g["cons"])
+    assert _close(o.jac_coord(x), g["jac_vals"]) and _close(o.hess_coord(x, lam, ow), g["hess_vals"])
+    assert _close(o.hess_coord(x, None, ow), g["hess_obj_vals"])
+    assert _close(o.jprod(x, v), g["jprod"]) and _close(o.jtprod(x, lam), g["jtprod"]) and _close(o.hprod(x, v, lam, ow), g["hprod"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-4] for f in FILES])
+def test_cuda_matches_golden(path, pkg, cuda_lib):
+    import torch
+    from pdenlp_b200.model import GridapPDENLPModel
+    g = np.load(path)
+    nlp = GridapPDENLPModel(_spec(pkg, os.path.basename(path)[:-4]), device="cuda:0")
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    x, lam, v, ow = d(g["x"]), d(g["lam"]), d(g["v"]), float(g["obj_weight"])
+    r, c = nlp.jac_structure()
+    assert np.array_equal(r.cpu().numpy(), g["jac_rows"]) and np.array_equal(c.cpu().numpy(), g["jac_cols"])
+    r, c = nlp.hess_structure()
+    assert np.array_equal(r.cpu().numpy(), g["hess_rows"]) and np.array_equal(c.cpu().numpy(), g["hess_cols"])
+    assert nlp.pdemeta.nnzh_obj == int(g["nnzh_obj"])
+    assert _close(nlp.obj(x), g["obj"])
+    assert _close(nlp.grad(x).cpu().numpy(), g["grad"]) and _close(nlp.cons(x).cpu().numpy(), g["cons"])
+    assert _close(nlp.jac_coord(x).cpu().numpy(), g["jac_vals"])
+    assert _close(nlp.hess_coord(x, lam, obj_weight=ow).cpu().numpy(), g["hess_vals"])
+    assert _close(nlp.hess_coord(x, obj_weight=ow).cpu().numpy(), g["hess_obj_vals"])
+    assert _close(nlp.jprod(x, v).cpu().numpy(), g["jprod"]) and _close(nlp.jtprod(x, lam).cpu().numpy(), g["jtprod"])
+    assert _close(nlp.hprod(x, lam, v, obj_weight=ow).cpu().numpy(), g["hprod"])
+    nlp.close()

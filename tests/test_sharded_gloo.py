@@ -1,0 +1,116 @@
+"""N > 1 host logic on CPU: world_size-2 gloo.  The slab decomposition, interface-dof reduction
+and COO slice offsets of pdenlp_b200.sharded are exercised with an oracle-backed local model
+standing in for the CUDA model (tests may use the oracle; the product path never does)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleLocal:
+    """GridapPDENLPModel-shaped wrapper of the oracle for one slab (numpy vectors)."""
+
+    def __init__(self, orc):
+        self.o = orc
+        class PM: pass
+        self.pdemeta = PM()
+        self.pdemeta.nnzj_y, self.pdemeta.nnzj_u, self.pdemeta.nnzh_fe = orc.nnzj_y, orc.nnzj_u, orc.nnzh_fe
+
+    def obj(self, x): return self.o.obj(x)
+    def grad_(self, x, g): g[:] = self.o.grad(x); return g
+    def cons_(self, x, c): c[:] = self.o.cons(x); return c
+    def jprod_(self, x, v, o): o[:] = self.o.jprod(x, v); return o
+    def jtprod_(self, x, v, o): o[:] = self.o.jtprod(x, v); return o
+    def hprod_(self, x, *a, obj_weight=1.0):
+        if len(a) == 2: v, o = a; lam = None
+        else: lam, v, o = a
+        o[:] = self.o.hprod(x, v, lam, obj_weight); return o
+    def jac_coord_(self, x, vals): return self.o.jac_coord(x, vals)
+    def hess_coord_(self, x, *a, obj_weight=1.0):
+        if len(a) == 1: return self.o.hess_coord(x, None, obj_weight, a[0])
+        return self.o.hess_coord(x, a[0], obj_weight, a[1])
+
+
+def _worker(rank, world, port, case, q):
+    sys.path.insert(0, ROOT)
+    from __graft_entry__ import load_oracle, load_package
+    pkg = load_package(); O = load_oracle()
+    from pdenlp_b200.sharded import ShardedModel, SlabLayout
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        spec = {"membrane": lambda: pkg.controlelasticmembrane(8), "burger_nl": lambda: pkg.burger1d_param(100),
+                "pb": lambda: pkg.poissonboltzman2d(9)}[case]()
+        layout = SlabLayout(spec, world)
+        full = O.Oracle(spec, nthreads=1)
+        local = OracleLocal(O.Oracle(spec, layout.ranges[rank], nthreads=1))
+        sm = ShardedModel(spec, local, layout, rank)
+        rng = np.random.default_rng(5)
+        x = rng.uniform(-1, 1, full.nvar); lam = rng.uniform(-1, 1, full.ncon); v = rng.uniform(-1, 1, full.nvar)
+        res = {}
+        res["obj"] = abs(sm.obj(x) - full.obj(x)) <= 1e-13 * abs(full.obj(x))
+        ty = layout.touch_y[rank]; tu = layout.touch_u[rank]
+        tv = np.concatenate([np.ones(spec.nparam, bool), ty, tu])
+
+        def check(name, got, ref, touched):
+            ok = np.allclose(got[touched], ref[touched], rtol=1e-12, atol=1e-14) and np.all(got[~touched] == 0)
+            full_vec = sm.allgather_owned(got, "var" if touched.size == full.nvar else "con").numpy()
+            res[name] = bool(ok and np.allclose(full_vec, ref, rtol=1e-12, atol=1e-14))
+
+        check("grad", sm.grad_(x, np.zeros(full.nvar)), full.grad(x), tv)
+        check("cons", sm.cons_(x, np.zeros(full.ncon)), full.cons(x), ty)
+        check("jprod", sm.jprod_(x, v, np.zeros(full.ncon)), full.jprod(x, v), ty)
+        check("jtprod", sm.jtprod_(x, lam, np.zeros(full.nvar)), full.jtprod(x, lam), tv)
+        check("hprod", sm.hprod_(x, lam, v, np.zeros(full.nvar), obj_weight=0.3), full.hprod(x, v, lam, 0.3), tv)
+        # COO slices: local values land at the global offsets of this rank, no communication
+        off = sm.global_segment_offsets()
+        jl = sm.jac_coord_(x, np.empty(local.o.nnzj)); jf = full.jac_coord(x)
+        k = full.nnzj_k
+        ok = np.array_equal(jl[local.o.nnzj_k:][: local.o.nnzj_y], jf[k + off["jy"]: k + off["jy"] + local.o.nnzj_y])
+        ok &= np.array_equal(jl[local.o.nnzj_k + local.o.nnzj_y:], jf[k + full.nnzj_y + off["ju"]: k + full.nnzj_y + off["ju"] + local.o.nnzj_u])
+        res["jac_slices"] = bool(ok)
+        hl = sm.hess_coord_(x, lam, np.empty(local.o.nnzh), obj_weight=0.3); hf = full.hess_coord(x, lam, 0.3)
+        a = full.nnzh_k_obj + off["hfe"]
+        lo = local.o
+        ok = np.array_equal(hl[lo.nnzh_k_obj: lo.nnzh_k_obj + lo.nnzh_fe], hf[a: a + lo.nnzh_fe])
+        b = full.nnzh_obj + full.nnzh_k_con + off["hfe"]
+        ok &= np.array_equal(hl[lo.nnzh_obj + lo.nnzh_k_con:], hf[b: b + lo.nnzh_fe])
+        res["hess_slices"] = bool(ok)
+        res["iface_small"] = bool(layout.iface_var.size < 0.5 * full.nvar)
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+@pytest.mark.parametrize("case", ["membrane", "burger_nl", "pb"])
+def test_world2_gloo(case, oracle_mod):
+    oracle_mod.build()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, case, q)) for r in range(2)]
+    for p in procs: p.start()
+    out = [q.get(timeout=240) for _ in procs]
+    for p in procs: p.join(timeout=60)
+    assert all(p.exitcode == 0 for p in procs)
+    for rank, res in out:
+        assert all(res.values()), (rank, res)
+
+
+def test_partition_alignment(pkg):
+    from pdenlp_b200.sharded import partition_cells
+    for n, w in [(4194304, 8), (10000, 3), (1000000, 8), (37, 2)]:
+        r = partition_cells(n, w)
+        assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        assert all(c0 % 32 == 0 for c0, _ in r)
