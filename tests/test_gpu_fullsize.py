@@ -1,0 +1,136 @@
+"""BASELINE.json full sizes on the GPU, checked through size-independent properties and through
+oracle comparisons on slabs the oracle finishes in seconds."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+def _rel(a, b):
+    scale = max(float(np.abs(b).max()), 1e-300)
+    return float(np.abs(a - b).max()) / scale
+
+
+@pytest.fixture(scope="module")
+def membrane2048(pkg, cuda_lib):
+    from pdenlp_b200.model import GridapPDENLPModel
+    spec = pkg.controlelasticmembrane(2048)
+    nlp = GridapPDENLPModel(spec, device="cuda:0", with_coef=False)
+    yield spec, nlp
+    nlp.close()
+
+
+def test_membrane_n2048_sizes(membrane2048):
+    spec, nlp = membrane2048
+    assert nlp.meta.nvar == 16769025 + 4198401 and nlp.meta.ncon == 16769025
+    assert nlp.meta.nnzj == 490266740 and nlp.meta.nnzh == 762773640
+    assert nlp.pdemeta.nnzh_obj == 381386820
+
+
+def test_membrane_n2048_slabs_vs_oracle_and_properties(membrane2048, oracle_mod):
+    spec, nlp = membrane2048
+    nvar, ncon = nlp.meta.nvar, nlp.meta.ncon
+    x = torch.from_numpy(np.random.default_rng(1998).uniform(-1, 1, nvar)).cuda()
+    lam = torch.from_numpy(np.random.default_rng(1999).uniform(-1, 1, ncon)).cuda()
+    jv = nlp.jac_coord(x)
+    hv = nlp.hess_coord(x, lam, obj_weight=0.37)
+    assert torch.isfinite(jv).all() and torch.isfinite(hv).all()
+    pm = nlp.pdemeta
+    ncell = spec.model.ncells
+    nslab = 4096  # two mesh rows
+    xh, lh = x.cpu().numpy(), lam.cpu().numpy()
+    # first and last slabs: their slices sit at the head / tail of every segment
+    for c0, c1, head in ((0, nslab, True), (ncell - nslab, ncell, False)):
+        o = oracle_mod.Oracle(spec, (c0, c1))
+        jo = o.jac_coord(xh); ho = o.hess_coord(xh, lh, 0.37)
+        jy = jv[: o.nnzj_y] if head else jv[pm.nnzj_y - o.nnzj_y: pm.nnzj_y]
+        ju = jv[pm.nnzj_y: pm.nnzj_y + o.nnzj_u] if head else jv[pm.nnzj_y + pm.nnzj_u - o.nnzj_u:]
+        assert _rel(jy.cpu().numpy(), jo[: o.nnzj_y]) <= RTOL and _rel(ju.cpu().numpy(), jo[o.nnzj_y:]) <= RTOL
+        fo = hv[: o.nnzh_fe] if head else hv[pm.nnzh_fe - o.nnzh_fe: pm.nnzh_fe]
+        fc = hv[pm.nnzh_obj: pm.nnzh_obj + o.nnzh_fe] if head else hv[pm.nnzh_obj + pm.nnzh_fe - o.nnzh_fe:]
+        assert _rel(fo.cpu().numpy(), ho[: o.nnzh_fe]) <= RTOL
+        assert np.abs(fc.cpu().numpy() - ho[o.nnzh_fe:]).max() <= RTOL * max(np.abs(ho).max(), 1e-300)
+    # a middle slab through a slab-owning handle (the multi-GPU layout): bitwise equal to the oracle-checked path
+    from pdenlp_b200.model import GridapPDENLPModel
+    c0 = (ncell // 2 // 32) * 32
+    mid = GridapPDENLPModel(spec, device="cuda:0", cell_range=(c0, c0 + nslab), with_coef=False)
+    o = oracle_mod.Oracle(spec, (c0, c0 + nslab))
+    assert _rel(mid.jac_coord(x).cpu().numpy(), o.jac_coord(xh)) <= RTOL
+    assert _rel(mid.hess_coord(x, lam, obj_weight=0.37).cpu().numpy()[: o.nnzh_fe], o.hess_coord(xh, lh, 0.37)[: o.nnzh_fe]) <= RTOL
+    mid.close()
+    # properties of this integrand: derivatives do not depend on x or lambda,
+    # the residual is linear so the constraint Hessian block vanishes, obj part scales with obj_weight
+    x2 = torch.from_numpy(np.random.default_rng(7).uniform(-1, 1, nvar)).cuda()
+    assert torch.equal(nlp.jac_coord(x2), jv)
+    assert torch.all(hv[pm.nnzh_obj:] == 0)
+    h1 = nlp.hess_coord(x2, obj_weight=1.0)
+    assert torch.all(h1[pm.nnzh_obj:] == 0)
+    assert float((h1[: pm.nnzh_obj] * 0.37 - hv[: pm.nnzh_obj]).abs().max()) <= RTOL * float(h1.abs().max())
+    # checksum of checksums (Appendix B): per cell H^f_e = w at (bubble,bubble) + w*alpha/16 on the
+    # 4x4 control block, of which the lower triangle on global ids (10 entries) is stored
+    w = float(np.prod(spec.model.h))
+    expect = spec.model.ncells * w * (1.0 + 1e-2 * 10.0 / 16.0)
+    assert abs(float(h1[: pm.nnzh_obj].sum()) - expect) <= 1e-9 * expect
+
+
+def test_membrane_n2048_structure_properties(membrane2048):
+    spec, nlp = membrane2048
+    r, c = nlp.hess_structure()
+    assert bool((r >= c).all()) and int(r.max()) <= nlp.meta.nvar and int(c.min()) >= 1
+    no = nlp.pdemeta.nnzh_obj
+    assert torch.equal(r[:no], r[no:]) and torch.equal(c[:no], c[no:])  # obj and cons FE blocks share the pattern
+    del r, c
+    r, c = nlp.jac_structure()
+    assert int(r.max()) == nlp.meta.ncon and int(c.max()) == nlp.meta.nvar and int(r.min()) == 1
+    # every free state dof appears as a row; y-block columns are state dofs, u-block columns control dofs
+    ny = nlp.pdemeta.nnzj_y
+    assert int(c[:ny].max()) <= nlp.meta.ncon and int(c[ny:].min()) > nlp.meta.ncon
+
+
+def test_poissonboltzmann_n1024_lagrangian_hessian(pkg, cuda_lib, oracle_mod):
+    """config 3: hess_coord! of the Lagrangian with multipliers; linear in lambda, slab vs oracle."""
+    from pdenlp_b200.model import GridapPDENLPModel
+    spec = pkg.poissonboltzman2d(1024)
+    nlp = GridapPDENLPModel(spec, device="cuda:0", with_coef=False)
+    nvar, ncon = nlp.meta.nvar, nlp.meta.ncon
+    assert nlp.meta.nnzh == 75374664 and nlp.meta.nnzj == 33472564
+    x = torch.from_numpy(np.random.default_rng(1998).uniform(-1, 1, nvar)).cuda()
+    l1 = torch.from_numpy(np.random.default_rng(1999).uniform(-1, 1, ncon)).cuda()
+    l2 = torch.from_numpy(np.random.default_rng(2001).uniform(-1, 1, ncon)).cuda()
+    no = nlp.pdemeta.nnzh_obj
+    h1 = nlp.hess_coord(x, l1, obj_weight=0.0)
+    h2 = nlp.hess_coord(x, l2, obj_weight=0.0)
+    h12 = nlp.hess_coord(x, l1 + l2, obj_weight=0.0)
+    assert torch.all(h1[:no] == 0)
+    assert float((h1 + h2 - h12).abs().max()) <= 1e-12 * float(h12.abs().max())
+    assert float(h1[no:].abs().max()) > 0  # sinh reaction term: the constraint block is not trivial
+    o = oracle_mod.Oracle(spec, (0, 8192))
+    ho = o.hess_coord(x.cpu().numpy(), l1.cpu().numpy(), 0.0)
+    assert _rel(h1[no: no + o.nnzh_fe].cpu().numpy(), ho[o.nnzh_fe:]) <= RTOL
+    nlp.close()
+
+
+def test_burger1d_1M_operator_path(pkg, cuda_lib):
+    """config 4: jprod!/jtprod!/hprod! on 10^6 cells; adjoint and symmetry identities."""
+    from pdenlp_b200.model import GridapPDENLPModel
+    spec = pkg.burger1d_param(1_000_000)
+    nlp = GridapPDENLPModel(spec, device="cuda:0")
+    nvar, ncon = nlp.meta.nvar, nlp.meta.ncon
+    rng = np.random.default_rng(1998)
+    x = torch.from_numpy(rng.uniform(-1, 1, nvar)).cuda()
+    v = torch.from_numpy(rng.uniform(-1, 1, nvar)).cuda()
+    v2 = torch.from_numpy(rng.uniform(-1, 1, nvar)).cuda()
+    w = torch.from_numpy(rng.uniform(-1, 1, ncon)).cuda()
+    Jv = nlp.jprod(x, v); Jtw = nlp.jtprod(x, w)
+    a, b = float(torch.dot(w, Jv)), float(torch.dot(Jtw, v))
+    assert abs(a - b) <= 1e-11 * max(abs(a), abs(b), 1.0)  # <w, J v> = <J^T w, v>
+    Hv = nlp.hprod(x, w, v, obj_weight=0.5); Hv2 = nlp.hprod(x, w, v2, obj_weight=0.5)
+    a, b = float(torch.dot(v2, Hv)), float(torch.dot(v, Hv2))
+    assert abs(a - b) <= 1e-11 * max(abs(a), abs(b), 1.0)  # symmetry of the Lagrangian Hessian
+    # coord and operator forms agree: J v from the COO values
+    r, c = nlp.jac_structure(); vals = nlp.jac_coord(x)
+    Jv_coo = torch.zeros(ncon, dtype=torch.float64, device="cuda").index_add_(0, r - 1, vals * v[c - 1])
+    assert float((Jv_coo - Jv).abs().max()) <= 1e-12 * float(Jv.abs().max())
+    nlp.close()
