@@ -1,0 +1,206 @@
+# PDENLPCuda.jl — the reference-side binding of libpdenlp_cuda.so (include/pdenlp_cuda.h).
+#
+# NOT RUNNABLE IN THIS REPO'S CONTAINER (no Julia toolchain); it is the stub a PDENLPModels.jl
+# maintainer would add.  The GridapPDENLPModel constructor and the NLPModels API surface stay
+# unchanged: `attach_cuda!(nlp)` flattens the Gridap objects once, after the stock constructor
+# (src/additional_constructors.jl:130-266), and the callback *bodies* of
+# src/GridapPDENLPModel.jl:245-661 become one `ccall` each.  @lencheck and Counters stay in Julia.
+module PDENLPCuda
+
+using Gridap, NLPModels, PDENLPModels
+import NLPModels: obj, grad!, cons_nln!, jac_nln_coord!, hess_coord!, hprod!, jprod_nln!, jtprod_nln!,
+                  increment!, @lencheck
+
+const LIB = get(ENV, "PDENLP_CUDA_LIB", "libpdenlp_cuda.so")
+
+# integrand ids of include/pdenlp_cuda.h
+@enum Integrand MEMBRANE=1 POISSON_BOLTZMANN=2 BURGER_LIN=3 BURGER_NL=4 KAPPA_POISSON=5
+
+struct Desc   # mirrors struct pdenlp_desc field by field
+  abi_version::Int32; integrand::Int32; dim::Int32; ny::Int32; nu::Int32; nq::Int32; nparam::Int32
+  memspace::Int32; device::Int32; reserved0::Int32
+  ncells::Int64; nfree_y::Int64; nfree_u::Int64; ndir_y::Int64; ndir_u::Int64
+  cell_dofs_y::Ptr{Int32}; cell_dofs_u::Ptr{Int32}; dir_y::Ptr{Float64}; dir_u::Ptr{Float64}
+  phi_y::Ptr{Float64}; grad_y::Ptr{Float64}; phi_u::Ptr{Float64}; wdet::Ptr{Float64}
+  ncoef::Int32; reserved1::Int32; coef::Ptr{Float64}
+  params::NTuple{8, Float64}
+end
+
+struct Info
+  nvar::Int64; ncon::Int64; nnzj::Int64; nnzj_k::Int64; nnzj_y::Int64; nnzj_u::Int64
+  nnzh::Int64; nnzh_obj::Int64; nnzh_k_obj::Int64; nnzh_fe::Int64; nnzh_k_con::Int64
+end
+
+check(rc) = rc == 0 || error("libpdenlp_cuda ($rc): " * unsafe_string(ccall((:pdenlp_last_error, LIB), Cstring, ())))
+
+const HANDLES = IdDict{Any, Ptr{Cvoid}}()   # nlp => pdenlp_model*
+
+"""
+    attach_cuda!(nlp, integrand; params, target, source, memspace = 1)
+
+Flatten the Gridap side of `nlp` (cell→dof maps, Dirichlet values, reference-FE tables at the
+quadrature points, weights·detJ, coefficient fields sampled at the quadrature points) and create the
+device model.  `memspace = 1` (PDENLP_MEM_HOST): the callbacks take ordinary `Vector{Float64}`.
+"""
+function attach_cuda!(nlp::GridapPDENLPModel, integrand::Integrand; params = Float64[], target = x -> 0.0,
+                      source = x -> 0.0, degree::Int = 1, memspace::Integer = 1, device::Integer = -1)
+  Ypde, Ycon = nlp.pdemeta.Ypde, nlp.pdemeta.Ycon
+  trian = get_triangulation(Ypde)
+  dΩ = Measure(trian, degree)
+  quad = get_cell_quadrature(dΩ)   # Gridap.CellData.CellQuadrature
+  qpts = get_cell_points(quad)
+  ids_y = get_cell_dof_ids(Ypde)
+  nc = length(ids_y); ny = length(ids_y[1])
+  celly = Matrix{Int32}(undef, ny, nc)         # column-major ny×nc == C row-major [nc][ny]
+  for (c, v) in enumerate(ids_y); celly[:, c] .= v; end
+  has_u = !(Ycon isa PDENLPModels.VoidFESpace)
+  nu = has_u ? length(get_cell_dof_ids(Ycon)[1]) : 0
+  cellu = Matrix{Int32}(undef, max(nu, 0), nc)
+  has_u && for (c, v) in enumerate(get_cell_dof_ids(Ycon)); cellu[:, c] .= v; end
+  diry = collect(Float64, get_dirichlet_values(Ypde))
+  diru = has_u ? collect(Float64, get_dirichlet_values(Ycon)) : Float64[]
+  # tables on cell 1 (uniform Cartesian map: identical for every cell)
+  sfy = get_cell_shapefuns(Ypde)
+  φ = evaluate(sfy, qpts)[1]                    # nq × ny
+  ∇φ = evaluate(∇(sfy), qpts)[1]                # nq × ny of VectorValue (physical gradients)
+  nq, D = size(φ, 1), length(∇φ[1, 1])
+  phi_y = permutedims(Float64.(φ))              # ny × nq column-major == [nq][ny]
+  grad_y = [∇φ[q, a][d] for d in 1:D, a in 1:ny, q in 1:nq]   # [nq][ny][dim]
+  phi_u = has_u ? permutedims(Float64.(evaluate(get_cell_shapefuns(Ycon), qpts)[1])) : zeros(0, nq)
+  w = get_cell_weights(quad)[1]; cmap = get_cell_map(trian)
+  detJ = [abs(det(∇(cmap)[1](p))) for p in get_cell_coordinates(quad)[1]]
+  wdet = Float64.(w .* detJ)
+  xq = evaluate(cmap, get_cell_coordinates(quad))   # physical quadrature points per cell
+  coef = Array{Float64}(undef, nq, nc, 2)           # [2][nc][nq]
+  for c in 1:nc, q in 1:nq; coef[q, c, 1] = target(xq[c][q]); coef[q, c, 2] = source(xq[c][q]); end
+  par = ntuple(i -> i <= length(params) ? Float64(params[i]) : 0.0, 8)
+  GC.@preserve celly cellu diry diru phi_y grad_y phi_u wdet coef begin
+    d = Desc(1, Int32(integrand), D, ny, nu, nq, nlp.pdemeta.nparam, memspace, device, 0,
+             nc, num_free_dofs(Ypde), has_u ? num_free_dofs(Ycon) : 0, length(diry), length(diru),
+             pointer(celly), pointer(cellu), pointer(diry), pointer(diru),
+             pointer(phi_y), pointer(grad_y), pointer(phi_u), pointer(wdet), 2, 0, pointer(coef), par)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:pdenlp_create, LIB), Cint, (Ref{Desc}, Ref{Ptr{Cvoid}}), d, h))
+  end
+  info = Ref{Info}()
+  check(ccall((:pdenlp_get_info, LIB), Cint, (Ptr{Cvoid}, Ref{Info}), h[], info))
+  # Gridap's structure stays authoritative; the device structure only cross-checks it
+  @assert info[].nnzj == nlp.meta.nnzj && info[].nnzh == nlp.meta.nnzh && info[].nnzh_obj == nlp.pdemeta.nnzh_obj
+  rows = Vector{Int64}(undef, nlp.meta.nnzh); cols = similar(rows)
+  check(ccall((:pdenlp_hess_structure, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), h[], rows, cols))
+  @assert rows == nlp.pdemeta.Hrows && cols == nlp.pdemeta.Hcols "COO order differs from hess_structure!"
+  HANDLES[nlp] = h[]
+  finalizer(n -> (haskey(HANDLES, n) && ccall((:pdenlp_destroy, LIB), Cint, (Ptr{Cvoid},), pop!(HANDLES, n))), nlp)
+  return nlp
+end
+
+handle(nlp) = HANDLES[nlp]
+# callbacks arrive with contiguous whole-vector views (SURVEY §8b); anything else is staged
+dense(v::StridedVector{Float64}) = stride(v, 1) == 1 ? v : collect(v)
+dense(v) = collect(Float64, v)
+
+# ---- the callback bodies: @lencheck + Counters exactly as in the reference, then one ccall ----
+function obj(nlp::GridapPDENLPModel, x::AbstractVector)                       # src/GridapPDENLPModel.jl:245
+  @lencheck nlp.meta.nvar x
+  increment!(nlp, :neval_obj)
+  f = Ref{Float64}()
+  check(ccall((:pdenlp_obj, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}), handle(nlp), dense(x), f))
+  return f[]
+end
+
+function grad!(nlp::GridapPDENLPModel, x::AbstractVector, g::AbstractVector)   # :257
+  @lencheck nlp.meta.nvar x g
+  increment!(nlp, :neval_grad)
+  out = dense(g)
+  check(ccall((:pdenlp_grad, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), handle(nlp), dense(x), out))
+  out === g || copyto!(g, out)
+  return g
+end
+
+function cons_nln!(nlp::GridapPDENLPModel, x::AbstractVector, c::AbstractVector)   # :433
+  @lencheck nlp.meta.nvar x
+  @lencheck nlp.meta.nnln c
+  increment!(nlp, :neval_cons_nln)
+  out = dense(c)
+  check(ccall((:pdenlp_cons, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), handle(nlp), dense(x), out))
+  out === c || copyto!(c, out)
+  return c
+end
+
+function jac_nln_coord!(nlp::GridapPDENLPModel, x::AbstractVector, vals::AbstractVector)   # :567
+  @lencheck nlp.meta.nvar x
+  @lencheck nlp.meta.nln_nnzj vals
+  increment!(nlp, :neval_jac_nln)
+  out = dense(vals)
+  check(ccall((:pdenlp_jac_coord, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), handle(nlp), dense(x), out))
+  out === vals || copyto!(vals, out)
+  return vals
+end
+
+function hess_coord!(nlp::GridapPDENLPModel, x::AbstractVector{T}, vals::AbstractVector; obj_weight::Real = one(T)) where {T}   # :268
+  @lencheck nlp.meta.nvar x
+  @lencheck nlp.meta.nnzh vals
+  increment!(nlp, :neval_hess)
+  out = dense(vals)
+  check(ccall((:pdenlp_hess_coord, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cdouble, Ptr{Float64}),
+              handle(nlp), dense(x), C_NULL, obj_weight, out))
+  out === vals || copyto!(vals, out)
+  return vals
+end
+
+function hess_coord!(nlp::GridapPDENLPModel, x::AbstractVector{T}, λ::AbstractVector, vals::AbstractVector;
+                     obj_weight::Real = one(T)) where {T}   # :341
+  @lencheck nlp.meta.nvar x
+  @lencheck nlp.meta.ncon λ
+  @lencheck nlp.meta.nnzh vals
+  increment!(nlp, :neval_hess)
+  out = dense(vals)
+  check(ccall((:pdenlp_hess_coord, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cdouble, Ptr{Float64}),
+              handle(nlp), dense(x), dense(λ), obj_weight, out))
+  out === vals || copyto!(vals, out)
+  return vals
+end
+
+function jprod_nln!(nlp::GridapPDENLPModel, x::AbstractVector, v::AbstractVector, Jv::AbstractVector)   # :473
+  @lencheck nlp.meta.nvar x v
+  @lencheck nlp.meta.nnln Jv
+  increment!(nlp, :neval_jprod_nln)      # net effect of the reference's increment/decrement pair (:483-484)
+  out = dense(Jv)
+  check(ccall((:pdenlp_jprod, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), handle(nlp), dense(x), dense(v), out))
+  out === Jv || copyto!(Jv, out)
+  return Jv
+end
+
+function jtprod_nln!(nlp::GridapPDENLPModel, x::AbstractVector, v::AbstractVector, Jtv::AbstractVector)   # :505
+  @lencheck nlp.meta.nvar x Jtv
+  @lencheck nlp.meta.nnln v
+  increment!(nlp, :neval_jtprod_nln)
+  out = dense(Jtv)
+  check(ccall((:pdenlp_jtprod, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), handle(nlp), dense(x), dense(v), out))
+  out === Jtv || copyto!(Jtv, out)
+  return Jtv
+end
+
+function hprod!(nlp::GridapPDENLPModel, x::AbstractVector{T}, v::AbstractVector, Hv::AbstractVector; obj_weight::Real = one(T)) where {T}   # :303
+  @lencheck nlp.meta.nvar x v Hv
+  increment!(nlp, :neval_hprod)
+  out = dense(Hv)
+  check(ccall((:pdenlp_hprod, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cdouble, Ptr{Float64}, Ptr{Float64}),
+              handle(nlp), dense(x), C_NULL, obj_weight, dense(v), out))
+  out === Hv || copyto!(Hv, out)
+  return Hv
+end
+
+function hprod!(nlp::GridapPDENLPModel, x::AbstractVector{T}, λ::AbstractVector, v::AbstractVector, Hv::AbstractVector;
+                obj_weight::Real = one(T)) where {T}   # :413
+  @lencheck nlp.meta.nvar x v Hv
+  @lencheck nlp.meta.ncon λ
+  increment!(nlp, :neval_hprod)
+  out = dense(Hv)
+  check(ccall((:pdenlp_hprod, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cdouble, Ptr{Float64}, Ptr{Float64}),
+              handle(nlp), dense(x), dense(λ), obj_weight, dense(v), out))
+  out === Hv || copyto!(Hv, out)
+  return Hv
+end
+
+end # module
