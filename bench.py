@@ -42,6 +42,13 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -121,8 +128,8 @@ def run_reference(args, pkg):
     sample = min(ncell, args.cpu_sample_cells)
     c0 = (ncell // 2 // args.n) * args.n  # rows from the middle of the mesh (interior cells dominate)
     c0 = min(c0, ncell - sample)
-    orc = O.Oracle(spec, (c0, c0 + sample))
-    cores = O.max_threads()
+    cores = _host_cores()
+    orc = O.Oracle(spec, (c0, c0 + sample), nthreads=cores)  # torchrun exports OMP_NUM_THREADS=1: set it explicitly
     rng = np.random.default_rng(1998)
     x = rng.uniform(-1, 1, orc.nvar)
     lam = np.random.default_rng(1999).uniform(-1, 1, orc.ncon)
@@ -338,8 +345,8 @@ def cpu_baseline(args, spec):
     ncell = spec.model.ncells
     sample = min(ncell, args.cpu_sample_cells)
     c0 = min((ncell // 2 // args.n) * args.n, ncell - sample)
-    orc = O.Oracle(spec, (c0, c0 + sample))
-    cores = O.max_threads()
+    cores = _host_cores()
+    orc = O.Oracle(spec, (c0, c0 + sample), nthreads=cores)
     x = np.random.default_rng(1998).uniform(-1, 1, orc.nvar)
     lam = np.random.default_rng(1999).uniform(-1, 1, orc.ncon)
     jv = np.empty(orc.nnzj); hv = np.empty(orc.nnzh)
