@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libpdenlp_cuda.so")
+# PDENLP_CUDA_LIB selects an alternative build of the same library (A/B kernel experiments)
+LIB_PATH = os.environ.get("PDENLP_CUDA_LIB") or os.path.join(HERE, "csrc", "libpdenlp_cuda.so")
 
 ABI_VERSION = 1
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = 0, -1, -2, -3, -4
