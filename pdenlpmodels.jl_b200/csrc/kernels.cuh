@@ -393,10 +393,9 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
 // block (1,1) [y,y], (2,1) [u rows, y cols], (1,2) [never kept], (2,2) [u,u]; within a block
 // columns outer, rows inner; keep iff gidcol>0 and gidcol<=gidrow (global ids).
 template <class E, bool ACC>
-__device__ __forceinline__ double* emit_hess(const Tables<E>& tab, int q, const Jet2<E::M>& L, double scale,
-                                             const Cell<E>& c, double* p) {
+__device__ __forceinline__ double* emit_hess_yy(const Tables<E>& tab, int q, const Jet2<E::M>& L, double scale,
+                                                const Cell<E>& c, double* p) {
   using J2 = Jet2<E::M>;
-  // (1,1)
 #pragma unroll
   for (int j = 0; j < E::NY; ++j) {
     double Nj[E::NB];
@@ -417,8 +416,14 @@ __device__ __forceinline__ double* emit_hess(const Tables<E>& tab, int q, const 
       }
     }
   }
+  return p;
+}
+// blocks (2,1) [rows = control dofs, cols = state dofs] and (2,2)
+template <class E, bool ACC>
+__device__ __forceinline__ double* emit_hess_u(const Tables<E>& tab, int q, const Jet2<E::M>& L, double scale,
+                                               const Cell<E>& c, double* p) {
+  using J2 = Jet2<E::M>;
   if (E::NU > 0) {
-    // (2,1): rows = control dofs, cols = state dofs
 #pragma unroll
     for (int j = 0; j < E::NY; ++j) {
       double a = 0.0;
@@ -433,7 +438,6 @@ __device__ __forceinline__ double* emit_hess(const Tables<E>& tab, int q, const 
         }
       }
     }
-    // (2,2)
     const double duu = L.h[J2::idx(E::SU, E::SU)] * scale;
 #pragma unroll
     for (int j = 0; j < E::NU; ++j) {
@@ -448,6 +452,12 @@ __device__ __forceinline__ double* emit_hess(const Tables<E>& tab, int q, const 
     }
   }
   return p;
+}
+template <class E, bool ACC>
+__device__ __forceinline__ double* emit_hess(const Tables<E>& tab, int q, const Jet2<E::M>& L, double scale,
+                                             const Cell<E>& c, double* p) {
+  p = emit_hess_yy<E, ACC>(tab, q, L, scale, c, p);
+  return emit_hess_u<E, ACC>(tab, q, L, scale, c, p);
 }
 
 // lambda-weighted residual  l(s) = sum_t Lam_t R_t(s)  as a Jet2 (its Hessian is the pointwise
@@ -565,6 +575,86 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
     tile = tnext;
   }
   if (lane == 0) bulk_wait_all();
+}
+
+
+// ------------------------------------------------------------------ hess_coord!, warp-pair variant
+// Profiling showed the single-warp-per-tile kernel to be latency bound (time scales 1/warps, the
+// staging buffers cap a CTA at 8 warps).  Here TWO warps share one tile and one staging buffer:
+// warp A emits block (1,1), warp B blocks (2,1)+(2,2) at offset n11 = fy(fy+1)/2 of each cell's
+// run, so a CTA holds 16 warps with the same shared memory and every warp's instruction stream
+// per tile is roughly halved.  The pair synchronises with a named barrier (bar.sync id, 64).
+__device__ __forceinline__ void pair_bar(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+template <class E>
+__global__ void __launch_bounds__(512, 1)
+k_hess_coord_pair(const __grid_constant__ Tables<E> tab, const DevModel D, const double* __restrict__ x,
+                  const double* __restrict__ lambda, double obj_weight,
+                  double* __restrict__ vals_obj, double* __restrict__ vals_con) {
+  using I = typename E::Integrand;
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int pair = warp >> 1, role = warp & 1, npairs = blockDim.x >> 6;
+  constexpr int STAGE = 32 * E::RUN_H + 2;
+  double* const buf = smem + pair * STAGE;
+  const int bar_id = 1 + pair;
+  const bool issuer = role == 0 && lane == 0;
+
+  for (int64_t tile = (int64_t)blockIdx.x * npairs + pair; tile < D.ntiles; tile += (int64_t)gridDim.x * npairs) {
+    const int64_t cell = tile * 32 + lane;
+    const bool valid = cell < D.ncells;
+    Cell<E> c;
+    load_ids<E>(D, valid ? cell : 0, valid, c);
+    gather_state<E>(D, x, valid, c);
+    int fy, fu, cnt;
+    closed_counts<E>(c, fy, fu, cnt);
+    const int n11 = fy * (fy + 1) / 2;
+    const int incl = warp_incl_scan(cnt, lane);
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int64_t tb = D.base_h[tile];
+    const int my_off = (incl - cnt) + (role ? n11 : 0);
+
+#pragma unroll 1
+    for (int seg = 0; seg < 2; ++seg) {
+      double* vals = seg == 0 ? vals_obj : vals_con;
+      if (vals == nullptr) continue;  // uniform over the CTA
+      double* gdst = vals + tb;
+      const int pad = (int)((reinterpret_cast<uintptr_t>(gdst) >> 3) & 1);
+      double* const p0 = buf + pad + my_off;
+      double lam_e[E::NY];
+      if (seg == 1) gather_free<E::NY>(lambda, c.gy, lam_e);
+#pragma unroll 1
+      for (int q = 0; q < E::NQ; ++q) {
+        Jet2<E::M> s[E::M];
+        point_state<E>(tab, c, x, q, s);
+        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        Jet2<E::M> L;
+        double scale = tab.wdet[q];
+        if (seg == 0) { L = I::f(pc, s); scale *= obj_weight; }
+        else {
+          double Lam[E::NR];
+          lambda_slots<E>(tab, q, lam_e, Lam);
+          L = weighted_res<E>(pc, s, Lam);
+        }
+        if (q == 0) {  // the staging buffer must have been drained by the previous bulk store
+          if (issuer) bulk_wait_read_all();
+          pair_bar(bar_id);
+        }
+        if (role == 0) { if (q == 0) emit_hess_yy<E, false>(tab, q, L, scale, c, p0); else emit_hess_yy<E, true>(tab, q, L, scale, c, p0); }
+        else           { if (q == 0) emit_hess_u<E, false>(tab, q, L, scale, c, p0);  else emit_hess_u<E, true>(tab, q, L, scale, c, p0); }
+      }
+      fence_proxy_async_smem();
+      pair_bar(bar_id);
+      if (issuer && total > 0) {
+        int done = 0;
+        if (pad) { gdst[0] = buf[1]; done = 1; }
+        const int nb = (total - done) & ~1;
+        if (nb > 0) { bulk_store_s2g(gdst + done, buf + 2 * pad, (uint32_t)nb * 8u); bulk_commit(); }
+        if ((total - done) & 1) gdst[total - 1] = buf[pad + total - 1];
+      }
+    }
+  }
+  if (issuer) bulk_wait_all();
 }
 
 // ------------------------------------------------------------------ structure (setup-time, not hot)

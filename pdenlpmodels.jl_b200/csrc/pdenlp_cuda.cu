@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -69,6 +70,7 @@ struct OpsImpl : Ops {
     if (attr_done) return PDENLP_OK;
     CU(cudaFuncSetAttribute(k_jac_coord<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_J));
     CU(cudaFuncSetAttribute(k_hess_coord<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_H));
+    CU(cudaFuncSetAttribute(k_hess_coord_pair<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_H));
     attr_done = true;
     return PDENLP_OK;
   }
@@ -82,15 +84,35 @@ struct OpsImpl : Ops {
     CU(cudaGetLastError());
     return PDENLP_OK;
   }
+  // tuning knob (experiments only): PDENLP_WARPS_J / PDENLP_WARPS_H lower the warps per CTA
+  static int env_warps(const char* name, int maxw) {
+    const char* e = getenv(name);
+    if (!e) return maxw;
+    int w = atoi(e);
+    return w >= 1 && w <= maxw ? w : maxw;
+  }
   int jac(const Launch& L, const DevModel& D, const double* x, double* vy, double* vu) override {
     if (int rc = set_attrs()) return rc;
-    k_jac_coord<E><<<grid_for(D.ntiles, WJ, L.sms), WJ * 32, SMEM_J, L.stream>>>(tab, D, x, vy, vu);
+    static const int wj = env_warps("PDENLP_WARPS_J", WJ);
+    k_jac_coord<E><<<grid_for(D.ntiles, wj, L.sms), wj * 32, SMEM_J, L.stream>>>(tab, D, x, vy, vu);
     CU(cudaGetLastError());
     return PDENLP_OK;
   }
   int hess(const Launch& L, const DevModel& D, const double* x, const double* lam, double ow, double* vo, double* vc) override {
     if (int rc = set_attrs()) return rc;
-    k_hess_coord<E><<<grid_for(D.ntiles, WH, L.sms), WH * 32, SMEM_H, L.stream>>>(tab, D, x, lam, ow, vo, vc);
+    // experiment (PDENLP_HESS_PAIR=1): two warps per tile, 16 warps per CTA on the same shared memory.
+    // Measured slower than the pipelined single-warp kernel on B200 (1.27 vs 1.19 ms at config 2:
+    // both warps repeat the prologue and there is no register budget left for the prefetch pipeline),
+    // so it is off by default; profiles/r01_notes.md has the numbers.
+    static const bool use_pair = E::NU > 0 && E::RUN_H >= 64 && getenv("PDENLP_HESS_PAIR") && atoi(getenv("PDENLP_HESS_PAIR")) == 1;
+    if (use_pair) {
+      static const int np = env_warps("PDENLP_PAIRS_H", WH);
+      k_hess_coord_pair<E><<<grid_for(D.ntiles, np, L.sms), np * 64, SMEM_H, L.stream>>>(tab, D, x, lam, ow, vo, vc);
+      CU(cudaGetLastError());
+      return PDENLP_OK;
+    }
+    static const int wh = env_warps("PDENLP_WARPS_H", WH);
+    k_hess_coord<E><<<grid_for(D.ntiles, wh, L.sms), wh * 32, SMEM_H, L.stream>>>(tab, D, x, lam, ow, vo, vc);
     CU(cudaGetLastError());
     return PDENLP_OK;
   }
