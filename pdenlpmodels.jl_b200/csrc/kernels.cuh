@@ -229,32 +229,83 @@ __global__ void __launch_bounds__(kThreads) k_count(DevModel D, int32_t* __restr
 }
 
 // ------------------------------------------------------------------ staged segment writer
-// One per warp. The staging buffer holds the tile's run of one COO segment; `pad` keeps the
-// shared-memory image congruent (mod 16 B) with the global destination so the bulk copy is legal.
-template <class V>
+// One per warp.  The tile's run of one COO segment is staged in shared memory and streamed to HBM
+// with TMA bulk stores.  Lane l writes its k-th kept entry at (exclusive scan + k), i.e. lanes are
+// RUN doubles apart: with an even RUN that is a 2..16-way bank conflict on every STS.64 (measured:
+// 3.6e9 conflicts per launch for the 3-D Q1 element).  The image is therefore cut into P pieces of
+// CPP = 32/P consecutive cells; pieces are PSTRIDE (odd) doubles apart, which spreads the lanes
+// over the banks, and every piece is one contiguous global range streamed by its own bulk store,
+// issued by the piece's first lane.  `delta` keeps each piece congruent (mod 16 B) with its global
+// destination so the bulk copy is legal; unaligned head/tail elements go by plain 8 B stores.
+// RUN odd => P = 1: one piece, one bulk store per tile, no conflicts to begin with.
+template <int RUN>
+struct StageLayout {
+  // Pieces cost TMA efficiency (8 stores of 1.1 KB were measured 11% slower than one of 9.2 KB on the
+  // HBM-bound membrane u-block), so they are used only where the conflict is >= 8-way (RUN % 8 == 0).
+  static constexpr int P = (RUN % 8 == 0) ? 16 : 1;
+  static constexpr int CPP = 32 / P;                       // cells (lanes) per piece
+  static constexpr int PR = CPP * RUN + 2;                 // piece capacity incl. parity slack
+  static constexpr int PSTRIDE = (P == 1) ? PR : (PR | 1); // odd stride between pieces
+  static constexpr int WARP_DOUBLES = (P * PSTRIDE + 2) & ~1;  // even => 16 B aligned warp buffers
+};
+
+template <int RUN>
 struct SegStage {
-  V* buf;
-  // make sure the previous bulk store has finished READING the buffer before refilling it
+  using L = StageLayout<RUN>;
+  double* wbuf;    // this warp's staging buffer (16 B aligned)
+  double* piece;   // start of this lane's piece image (wbuf + piece*PSTRIDE + delta)
+  // make sure the previous bulk stores have finished READING the buffer before refilling it
+  // (lanes wait on their own bulk groups; the issuing lanes are the first lanes of the finest
+  // piece layout, 16 pieces = even lanes, which covers every coarser layout sharing the buffer)
   __device__ __forceinline__ void acquire(int lane) {
-    if (lane == 0) bulk_wait_read_all();
+    if ((lane & 1) == 0) bulk_wait_read_all();
     __syncwarp();
   }
-  // all lanes have written their entries at buf[pad + excl ...]; stream [0,total) to gdst
-  __device__ __forceinline__ void release(V* gdst, int total, int pad, int lane) {
+  // where this lane writes its first entry; gbase = global address of the tile's first entry
+  __device__ __forceinline__ double* begin(const double* gbase, int excl, int lane) {
+    if (L::P == 1) {
+      piece = wbuf + ((reinterpret_cast<uintptr_t>(gbase) >> 3) & 1);
+      return piece + excl;
+    }
+    const int l0 = lane & ~(L::CPP - 1);
+    const int pe = __shfl_sync(0xffffffffu, excl, l0);
+    double* region = wbuf + (lane / L::CPP) * L::PSTRIDE;
+    const unsigned gpar = (unsigned)(reinterpret_cast<uintptr_t>(gbase + pe) >> 3) & 1u;
+    const unsigned spar = (smem_u32(region) >> 3) & 1u;
+    piece = region + (gpar ^ spar);
+    return piece + (excl - pe);
+  }
+  // all lanes have written their entries; stream every piece to its global range
+  __device__ __forceinline__ void release(double* gbase, int excl, int incl, int lane) {
     fence_proxy_async_smem();  // generic-proxy writes -> visible to the async proxy (TMA)
     __syncwarp();
-    if (lane == 0 && total > 0) {
+    const int l0 = lane & ~(L::CPP - 1);
+    const int pe = L::P == 1 ? 0 : __shfl_sync(0xffffffffu, excl, l0);
+    const int pend = __shfl_sync(0xffffffffu, incl, l0 + L::CPP - 1);
+    if (lane == l0 && pend > pe) {
+      const int n = pend - pe;
+      double* g = gbase + pe;
       int done = 0;
-      if (pad) { gdst[0] = buf[1]; done = 1; }           // unaligned head element
-      const int nb = (total - done) & ~1;                 // 16 B granules
+      if ((reinterpret_cast<uintptr_t>(g) >> 3) & 1) { g[0] = piece[0]; done = 1; }  // unaligned head element
+      const int nb = (n - done) & ~1;                                                   // 16 B granules
       if (nb > 0) {
-        bulk_store_s2g(gdst + done, buf + 2 * pad, (uint32_t)nb * sizeof(V));
+        bulk_store_s2g(g + done, piece + done, (uint32_t)nb * 8u);
         bulk_commit();
       }
-      if ((total - done) & 1) gdst[total - 1] = buf[pad + total - 1];  // tail element
+      if ((n - done) & 1) g[n - 1] = piece[n - 1];  // tail element
     }
   }
+  __device__ __forceinline__ void drain(int lane) { if ((lane & 1) == 0) bulk_wait_all(); }
 };
+
+template <class E>
+__host__ __device__ constexpr int jac_stage_doubles() {
+  return StageLayout<E::RUN_JY>::WARP_DOUBLES > StageLayout<(E::NU > 0 ? E::RUN_JU : 1)>::WARP_DOUBLES
+             ? StageLayout<E::RUN_JY>::WARP_DOUBLES
+             : StageLayout<(E::NU > 0 ? E::RUN_JU : 1)>::WARP_DOUBLES;
+}
+template <class E>
+__host__ __device__ constexpr int hess_stage_doubles() { return StageLayout<E::RUN_H>::WARP_DOUBLES; }
 
 // ------------------------------------------------------------------ jac_coord!
 // vals layout (this slab): [k-block (ncon*p, filled elsewhere) | y-block | u-block]
@@ -265,8 +316,9 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
   using I = typename E::Integrand;
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  constexpr int STAGE = 32 * E::RUN_J + 2;
-  SegStage<double> st{smem + warp * STAGE};
+  constexpr int STAGE = jac_stage_doubles<E>();
+  SegStage<E::RUN_JY> sty{smem + warp * STAGE, nullptr};
+  SegStage<(E::NU > 0 ? E::RUN_JU : 1)> stu{smem + warp * STAGE, nullptr};
 
   const int64_t stride = (int64_t)gridDim.x * nwarps;
   int64_t tile = (int64_t)blockIdx.x * nwarps + warp;
@@ -307,11 +359,9 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
     {
       const int cnt = fy * fy;
       const int incl = warp_incl_scan(cnt, lane);
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
       double* gdst = vals_y + D.base_jy[tile];
-      const int pad = (int)((reinterpret_cast<uintptr_t>(gdst) >> 3) & 1);
-      st.acquire(lane);
-      double* const p0 = st.buf + pad + (incl - cnt);
+      sty.acquire(lane);
+      double* const p0 = sty.begin(gdst, incl - cnt, lane);
 #pragma unroll 1
       for (int q = 0; q < E::NQ; ++q) {
         Jet1<E::M> s[E::M], R[E::NR];
@@ -340,17 +390,15 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
           }
         }
       }
-      st.release(gdst, total, pad, lane);
+      sty.release(gdst, incl - cnt, incl, lane);
     }
     // ---- u-block:  B_e[i][b] = sum_q w sum_t T_i[t] dR_t/du psi_b
     if (E::NU > 0) {
       const int cnt = fy * fu;
       const int incl = warp_incl_scan(cnt, lane);
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
       double* gdst = vals_u + D.base_ju[tile];
-      const int pad = (int)((reinterpret_cast<uintptr_t>(gdst) >> 3) & 1);
-      st.acquire(lane);
-      double* const p0 = st.buf + pad + (incl - cnt);
+      stu.acquire(lane);
+      double* const p0 = stu.begin(gdst, incl - cnt, lane);
 #pragma unroll 1
       for (int q = 0; q < E::NQ; ++q) {
         Jet1<E::M> s[E::M], R[E::NR];
@@ -374,7 +422,7 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
           }
         }
       }
-      st.release(gdst, total, pad, lane);
+      stu.release(gdst, incl - cnt, incl, lane);
     }
     if (!has_next) break;
     c = n;
@@ -384,7 +432,7 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
     for (int b = 0; b < E::NUS; ++b) n.gu[b] = nn.gu[b];
     tile = tnext;
   }
-  if (lane == 0) bulk_wait_all();
+  sty.drain(lane);
 }
 
 // ------------------------------------------------------------------ hess_coord!
@@ -492,8 +540,8 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
   using I = typename E::Integrand;
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  constexpr int STAGE = 32 * E::RUN_H + 2;
-  SegStage<double> st{smem + warp * STAGE};
+  constexpr int STAGE = hess_stage_doubles<E>();
+  SegStage<E::RUN_H> st{smem + warp * STAGE, nullptr};
 
   const int64_t stride = (int64_t)gridDim.x * nwarps;
   int64_t tile = (int64_t)blockIdx.x * nwarps + warp;
@@ -529,14 +577,12 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
     int fy, fu, cnt;
     closed_counts<E>(c, fy, fu, cnt);
     const int incl = warp_incl_scan(cnt, lane);
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
     const int64_t tb = D.base_h[tile];
 
     if (vals_obj != nullptr) {
       double* gdst = vals_obj + tb;
-      const int pad = (int)((reinterpret_cast<uintptr_t>(gdst) >> 3) & 1);
       st.acquire(lane);
-      double* const p0 = st.buf + pad + (incl - cnt);
+      double* const p0 = st.begin(gdst, incl - cnt, lane);
 #pragma unroll 1
       for (int q = 0; q < E::NQ; ++q) {
         Jet2<E::M> s[E::M];
@@ -546,13 +592,12 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
         if (q == 0) emit_hess<E, false>(tab, q, F, obj_weight * tab.wdet[q], c, p0);
         else        emit_hess<E, true>(tab, q, F, obj_weight * tab.wdet[q], c, p0);
       }
-      st.release(gdst, total, pad, lane);
+      st.release(gdst, incl - cnt, incl, lane);
     }
     if (vals_con != nullptr) {
       double* gdst = vals_con + tb;
-      const int pad = (int)((reinterpret_cast<uintptr_t>(gdst) >> 3) & 1);
       st.acquire(lane);
-      double* const p0 = st.buf + pad + (incl - cnt);
+      double* const p0 = st.begin(gdst, incl - cnt, lane);
 #pragma unroll 1
       for (int q = 0; q < E::NQ; ++q) {
         Jet2<E::M> s[E::M];
@@ -564,7 +609,7 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
         if (q == 0) emit_hess<E, false>(tab, q, L, tab.wdet[q], c, p0);
         else        emit_hess<E, true>(tab, q, L, tab.wdet[q], c, p0);
       }
-      st.release(gdst, total, pad, lane);
+      st.release(gdst, incl - cnt, incl, lane);
     }
     if (!has_next) break;
     c = n;
@@ -574,88 +619,9 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
     for (int b = 0; b < E::NUS; ++b) n.gu[b] = nn.gu[b];
     tile = tnext;
   }
-  if (lane == 0) bulk_wait_all();
+  st.drain(lane);
 }
 
-
-// ------------------------------------------------------------------ hess_coord!, warp-pair variant
-// Profiling showed the single-warp-per-tile kernel to be latency bound (time scales 1/warps, the
-// staging buffers cap a CTA at 8 warps).  Here TWO warps share one tile and one staging buffer:
-// warp A emits block (1,1), warp B blocks (2,1)+(2,2) at offset n11 = fy(fy+1)/2 of each cell's
-// run, so a CTA holds 16 warps with the same shared memory and every warp's instruction stream
-// per tile is roughly halved.  The pair synchronises with a named barrier (bar.sync id, 64).
-__device__ __forceinline__ void pair_bar(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-
-template <class E>
-__global__ void __launch_bounds__(512, 1)
-k_hess_coord_pair(const __grid_constant__ Tables<E> tab, const DevModel D, const double* __restrict__ x,
-                  const double* __restrict__ lambda, double obj_weight,
-                  double* __restrict__ vals_obj, double* __restrict__ vals_con) {
-  using I = typename E::Integrand;
-  extern __shared__ __align__(16) double smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int pair = warp >> 1, role = warp & 1, npairs = blockDim.x >> 6;
-  constexpr int STAGE = 32 * E::RUN_H + 2;
-  double* const buf = smem + pair * STAGE;
-  const int bar_id = 1 + pair;
-  const bool issuer = role == 0 && lane == 0;
-
-  for (int64_t tile = (int64_t)blockIdx.x * npairs + pair; tile < D.ntiles; tile += (int64_t)gridDim.x * npairs) {
-    const int64_t cell = tile * 32 + lane;
-    const bool valid = cell < D.ncells;
-    Cell<E> c;
-    load_ids<E>(D, valid ? cell : 0, valid, c);
-    gather_state<E>(D, x, valid, c);
-    int fy, fu, cnt;
-    closed_counts<E>(c, fy, fu, cnt);
-    const int n11 = fy * (fy + 1) / 2;
-    const int incl = warp_incl_scan(cnt, lane);
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    const int64_t tb = D.base_h[tile];
-    const int my_off = (incl - cnt) + (role ? n11 : 0);
-
-#pragma unroll 1
-    for (int seg = 0; seg < 2; ++seg) {
-      double* vals = seg == 0 ? vals_obj : vals_con;
-      if (vals == nullptr) continue;  // uniform over the CTA
-      double* gdst = vals + tb;
-      const int pad = (int)((reinterpret_cast<uintptr_t>(gdst) >> 3) & 1);
-      double* const p0 = buf + pad + my_off;
-      double lam_e[E::NY];
-      if (seg == 1) gather_free<E::NY>(lambda, c.gy, lam_e);
-#pragma unroll 1
-      for (int q = 0; q < E::NQ; ++q) {
-        Jet2<E::M> s[E::M];
-        point_state<E>(tab, c, x, q, s);
-        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
-        Jet2<E::M> L;
-        double scale = tab.wdet[q];
-        if (seg == 0) { L = I::f(pc, s); scale *= obj_weight; }
-        else {
-          double Lam[E::NR];
-          lambda_slots<E>(tab, q, lam_e, Lam);
-          L = weighted_res<E>(pc, s, Lam);
-        }
-        if (q == 0) {  // the staging buffer must have been drained by the previous bulk store
-          if (issuer) bulk_wait_read_all();
-          pair_bar(bar_id);
-        }
-        if (role == 0) { if (q == 0) emit_hess_yy<E, false>(tab, q, L, scale, c, p0); else emit_hess_yy<E, true>(tab, q, L, scale, c, p0); }
-        else           { if (q == 0) emit_hess_u<E, false>(tab, q, L, scale, c, p0);  else emit_hess_u<E, true>(tab, q, L, scale, c, p0); }
-      }
-      fence_proxy_async_smem();
-      pair_bar(bar_id);
-      if (issuer && total > 0) {
-        int done = 0;
-        if (pad) { gdst[0] = buf[1]; done = 1; }
-        const int nb = (total - done) & ~1;
-        if (nb > 0) { bulk_store_s2g(gdst + done, buf + 2 * pad, (uint32_t)nb * 8u); bulk_commit(); }
-        if ((total - done) & 1) gdst[total - 1] = buf[pad + total - 1];
-      }
-    }
-  }
-  if (issuer) bulk_wait_all();
-}
 
 // ------------------------------------------------------------------ structure (setup-time, not hot)
 // rows/cols of the FE blocks; kind 0 = Jacobian y-block, 1 = Jacobian u-block, 2 = Hessian FE block.
@@ -913,6 +879,12 @@ k_jac_kappa(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
     Cell<E> c;
     load_ids<E>(D, cell, valid, c);
     gather_state<E>(D, x, valid, c);
+    constexpr int NPS = E::NP > 0 ? E::NP : 1;
+    double acc[NPS][E::NY];  // sum over quadrature points first: one atomic per (dof, kappa)
+#pragma unroll
+    for (int k = 0; k < NPS; ++k)
+#pragma unroll
+      for (int i = 0; i < E::NY; ++i) acc[k][i] = 0.0;
 #pragma unroll 1
     for (int q = 0; q < E::NQ; ++q) {
       Jet1<E::M> s[E::M], R[E::NR];
@@ -926,9 +898,14 @@ k_jac_kappa(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
           double a = 0.0;
 #pragma unroll
           for (int t = 0; t < E::NR; ++t) a = fma(test_slot<E>(tab, q, i, t), R[t].g[E::SK + k], a);
-          if (c.gy[i] > 0) atomicAdd(vk + ((int64_t)k * D.nfree_y + (c.gy[i] - 1)), tab.wdet[q] * a);
+          acc[k][i] = fma(tab.wdet[q], a, acc[k][i]);
         }
     }
+#pragma unroll
+    for (int k = 0; k < E::NP; ++k)
+#pragma unroll
+      for (int i = 0; i < E::NY; ++i)
+        if (c.gy[i] > 0) atomicAdd(vk + ((int64_t)k * D.nfree_y + (c.gy[i] - 1)), acc[k][i]);
   }
 }
 
@@ -960,6 +937,16 @@ k_hess_kappa(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
     Cell<E> c;
     load_ids<E>(D, cell, valid, c);
     gather_state<E>(D, x, valid, c);
+    double lam_e[E::NY];
+    if (which != 0) gather_free<E::NY>(lambda, c.gy, lam_e);
+    double accy[NPS][E::NY], accu[NPS][E::NUS];  // cross terms summed over quadrature points
+#pragma unroll
+    for (int j = 0; j < NPS; ++j) {
+#pragma unroll
+      for (int a = 0; a < E::NY; ++a) accy[j][a] = 0.0;
+#pragma unroll
+      for (int b = 0; b < E::NUS; ++b) accu[j][b] = 0.0;
+    }
 #pragma unroll 1
     for (int q = 0; q < E::NQ; ++q) {
       Jet2<E::M> s[E::M];
@@ -969,8 +956,7 @@ k_hess_kappa(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
       double scale = tab.wdet[q];
       if (which == 0) { L = I::f(pc, s); scale *= obj_weight; }
       else {
-        double lam_e[E::NY], Lam[E::NR];
-        gather_free<E::NY>(lambda, c.gy, lam_e);
+        double Lam[E::NR];
         lambda_slots<E>(tab, q, lam_e, Lam);
         L = weighted_res<E>(pc, s, Lam);
       }
@@ -984,14 +970,22 @@ k_hess_kappa(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
             double v = 0.0;
 #pragma unroll
             for (int k = 0; k < E::NB; ++k) v = fma(tab.By[q][a][k], L.h[J2::idx(k, E::SK + j)], v);
-            if (c.gy[a] > 0) atomicAdd(vk + trap_pos((int64_t)E::NP + c.gy[a], j + 1, prows), scale * v);
+            accy[j][a] = fma(scale, v, accy[j][a]);
           }
 #pragma unroll
-          for (int b = 0; b < E::NU; ++b) {
-            const double v = tab.Bu[q][b] * L.h[J2::idx(E::SU, E::SK + j)];
-            if (c.gu[b] > 0) atomicAdd(vk + trap_pos((int64_t)E::NP + D.nfree_y + c.gu[b], j + 1, prows), scale * v);
-          }
+          for (int b = 0; b < E::NU; ++b) accu[j][b] = fma(scale, tab.Bu[q][b] * L.h[J2::idx(E::SU, E::SK + j)], accu[j][b]);
         }
+      }
+    }
+    if (cross) {
+#pragma unroll
+      for (int j = 0; j < E::NP; ++j) {
+#pragma unroll
+        for (int a = 0; a < E::NY; ++a)
+          if (c.gy[a] > 0) atomicAdd(vk + trap_pos((int64_t)E::NP + c.gy[a], j + 1, prows), accy[j][a]);
+#pragma unroll
+        for (int b = 0; b < E::NU; ++b)
+          if (c.gu[b] > 0) atomicAdd(vk + trap_pos((int64_t)E::NP + D.nfree_y + c.gu[b], j + 1, prows), accu[j][b]);
       }
     }
   }

@@ -51,26 +51,24 @@ struct Ops {
   virtual int run_h() const = 0;
 };
 
-template <int RUN>
-constexpr int warps_for_run() {
-  // per-warp staging buffer of (32*RUN + 2) doubles; at most 8 warps, at most ~225 KB per CTA
-  return std::min(8, (225 * 1024) / ((32 * RUN + 2) * 8));
+constexpr int warps_for_stage(int stage_doubles) {
+  // per-warp staging buffer; at most 8 warps (launch bounds), at most ~225 KB per CTA
+  return std::min(8, (225 * 1024) / (stage_doubles * 8));
 }
 
 template <class E>
 struct OpsImpl : Ops {
   Tables<E> tab;
   bool attr_done = false;
-  static constexpr int WJ = warps_for_run<E::RUN_J>();
-  static constexpr int WH = warps_for_run<E::RUN_H>();
-  static constexpr size_t SMEM_J = (size_t)WJ * (32 * E::RUN_J + 2) * 8;
-  static constexpr size_t SMEM_H = (size_t)WH * (32 * E::RUN_H + 2) * 8;
+  static constexpr int WJ = warps_for_stage(jac_stage_doubles<E>());
+  static constexpr int WH = warps_for_stage(hess_stage_doubles<E>());
+  static constexpr size_t SMEM_J = (size_t)WJ * jac_stage_doubles<E>() * 8;
+  static constexpr size_t SMEM_H = (size_t)WH * hess_stage_doubles<E>() * 8;
 
   int set_attrs() {
     if (attr_done) return PDENLP_OK;
     CU(cudaFuncSetAttribute(k_jac_coord<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_J));
     CU(cudaFuncSetAttribute(k_hess_coord<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_H));
-    CU(cudaFuncSetAttribute(k_hess_coord_pair<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_H));
     attr_done = true;
     return PDENLP_OK;
   }
@@ -100,17 +98,6 @@ struct OpsImpl : Ops {
   }
   int hess(const Launch& L, const DevModel& D, const double* x, const double* lam, double ow, double* vo, double* vc) override {
     if (int rc = set_attrs()) return rc;
-    // experiment (PDENLP_HESS_PAIR=1): two warps per tile, 16 warps per CTA on the same shared memory.
-    // Measured slower than the pipelined single-warp kernel on B200 (1.27 vs 1.19 ms at config 2:
-    // both warps repeat the prologue and there is no register budget left for the prefetch pipeline),
-    // so it is off by default; profiles/r01_notes.md has the numbers.
-    static const bool use_pair = E::NU > 0 && E::RUN_H >= 64 && getenv("PDENLP_HESS_PAIR") && atoi(getenv("PDENLP_HESS_PAIR")) == 1;
-    if (use_pair) {
-      static const int np = env_warps("PDENLP_PAIRS_H", WH);
-      k_hess_coord_pair<E><<<grid_for(D.ntiles, np, L.sms), np * 64, SMEM_H, L.stream>>>(tab, D, x, lam, ow, vo, vc);
-      CU(cudaGetLastError());
-      return PDENLP_OK;
-    }
     static const int wh = env_warps("PDENLP_WARPS_H", WH);
     k_hess_coord<E><<<grid_for(D.ntiles, wh, L.sms), wh * 32, SMEM_H, L.stream>>>(tab, D, x, lam, ow, vo, vc);
     CU(cudaGetLastError());
