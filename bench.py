@@ -245,6 +245,8 @@ def main():
     # roofline of the dominant kernel (k_hess_coord: 61% of the bytes of a step) on THIS rank's slab
     peak, peak_src = _peaks()
     b_jac, b_hess = algorithmic_bytes(info, fm)
+    # (rank 0's slab bytes over the slowest rank's launch time: conservative for N > 1)
+    jac_ms, hess_ms = jac_ms_max, hess_ms_max
     ach_hess = b_hess / (hess_ms * 1e-3) / 1e9
     ach_jac = b_jac / (jac_ms * 1e-3) / 1e9
     ach_step = (b_jac + b_hess) / ((jac_ms + hess_ms) * 1e-3) / 1e9
