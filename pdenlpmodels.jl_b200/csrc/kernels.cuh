@@ -773,8 +773,10 @@ __device__ __forceinline__ void field_direction(const Tables<E>& tab, int q, con
   for (int k = 0; k < E::NP; ++k) ds[E::SK + k] = __ldg(v + k);
 }
 
+// These kernels are load-latency bound (ncu: long-scoreboard 8-14 stall cycles per issue at 16-24
+// resident warps), so the register budget is capped to keep 3-4 CTAs (24-32 warps) per SM.
 template <class E, int OP>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, (E::M >= 6 || OP == OP_HPROD) ? 2 : ((OP == OP_JPROD || OP == OP_JTPROD) ? 3 : 4))
 k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* __restrict__ x,
          const double* __restrict__ lambda, const double* __restrict__ v, double obj_weight,
          double* __restrict__ out, double* __restrict__ partials) {
@@ -785,11 +787,26 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
 #pragma unroll
   for (int k = 0; k < (E::NP > 0 ? E::NP : 1); ++k) ksum[k] = 0.0;
 
-  for (int64_t tile = (int64_t)blockIdx.x * kWarpsPerCta + warp; tile < D.ntiles; tile += (int64_t)gridDim.x * kWarpsPerCta) {
+  const int64_t vstride = (int64_t)gridDim.x * kWarpsPerCta;
+  Cell<E> c, nx;  // the dof ids of the next tile are loaded one iteration ahead
+  {
+    const int64_t t0 = (int64_t)blockIdx.x * kWarpsPerCta + warp;
+    const int64_t c0 = t0 * 32 + lane;
+    const bool v0 = t0 < D.ntiles && c0 < D.ncells;
+    load_ids<E>(D, v0 ? c0 : 0, v0, nx);
+  }
+  for (int64_t tile = (int64_t)blockIdx.x * kWarpsPerCta + warp; tile < D.ntiles; tile += vstride) {
     const int64_t cell = tile * 32 + lane;
     const bool valid = cell < D.ncells;
-    Cell<E> c;
-    load_ids<E>(D, valid ? cell : 0, valid, c);
+#pragma unroll
+    for (int a = 0; a < E::NY; ++a) c.gy[a] = nx.gy[a];
+#pragma unroll
+    for (int b = 0; b < E::NUS; ++b) c.gu[b] = nx.gu[b];
+    {
+      const int64_t c1 = (tile + vstride) * 32 + lane;
+      const bool v1 = (tile + vstride) < D.ntiles && c1 < D.ncells;
+      load_ids<E>(D, v1 ? c1 : 0, v1, nx);
+    }
     gather_state<E>(D, x, valid, c);
     if (!valid) continue;
 #pragma unroll 1
