@@ -49,6 +49,24 @@ def _host_cores() -> int:
         return os.cpu_count() or 1
 
 
+def _ncu_traffic(n, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of k_hess_coord per launch from the committed
+    `ncu --set full` capture (profiles/r01_v3_ncu_summary.json); only valid for the captured workload."""
+    if n != 2048 or world != 1:
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_v3_ncu_summary.json")) as fh:
+            d = json.load(fh)[0]
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            val, u = d[k].split()
+            tot += float(val) * unit[u]
+        return int(tot)
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -279,7 +297,7 @@ def main():
             "jac_ms": jac_ms_max, "hess_ms": hess_ms_max,
             "roofline": {
                 "bound": "hbm", "kernel": "k_hess_coord", "achieved": ach_hess, "peak": peak, "unit": "GB/s",
-                "frac": ach_hess / peak, "traffic": None, "peak_source": peak_src,
+                "frac": ach_hess / peak, "traffic": _ncu_traffic(args.n, world), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(b_hess), "launch_ms": hess_ms,
                 "jac_kernel": {"achieved": ach_jac, "frac": ach_jac / peak, "algorithmic_bytes_per_launch": int(b_jac), "launch_ms": jac_ms},
                 "step": {"achieved": ach_step, "frac": ach_step / peak},
