@@ -135,3 +135,24 @@ def test_host_memspace_matches_device(case, pkg):
     ro, co = case["orc"].jac_structure()
     assert np.array_equal(r, ro) and np.array_equal(c, co)
     nlp_h.close()
+
+
+def test_unaligned_guarded_outputs(case):
+    """Outputs that are only 8 B aligned (a view starting at an odd element) with sentinel guards on
+    both sides: exercises the head/tail handling of the 16 B-aligned bulk stores and catches any
+    out-of-bounds write (compute-sanitizer is closed on this pool)."""
+    nlp, x, lam = case["nlp"], case["x"], case["lam"]
+    xd, ld = _d(x), _d(lam)
+    jref = nlp.jac_coord(xd)
+    href = nlp.hess_coord(xd, ld, obj_weight=0.37)
+    for off in (1, 2, 3):
+        for ref, call in ((jref, lambda out: nlp.jac_coord_(xd, out)),
+                          (href, lambda out: nlp.hess_coord_(xd, ld, out, obj_weight=0.37))):
+            n = ref.numel()
+            big = torch.full((n + 16,), float("nan"), dtype=torch.float64, device="cuda")
+            view = big[off: off + n]
+            assert view.data_ptr() % 16 == (8 * off) % 16
+            call(view)
+            torch.cuda.synchronize()
+            assert torch.equal(view, ref)
+            assert torch.isnan(big[:off]).all() and torch.isnan(big[off + n:]).all()
