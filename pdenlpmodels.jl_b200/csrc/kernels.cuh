@@ -551,19 +551,24 @@ __device__ __forceinline__ double* emit_hess(const Tables<E>& tab, int q, const 
   return emit_hess_u<E, ACC>(tab, q, L, scale, c, p);
 }
 
-// True when every pointwise second derivative w.r.t. the FE fields (y, grad y, u) vanishes: then
-// the element block is exactly zero.  This is a data-dependent (not integrand-dependent) test; it
-// fires for the constraint block of every PDE that is linear in (y,u) — e.g. the membrane problem —
-// and for obj_weight == 0.
-template <class E>
-__device__ __forceinline__ bool fe_hess_is_zero(const Jet2<E::M>& L) {
+// Run-time structural zero tests on the pointwise second derivatives w.r.t. the FE fields.
+// UROW = false: the (y, grad y) x (y, grad y) part, which generates block (1,1);
+// UROW = true : the u row (u x (y, grad y, u)), which generates blocks (2,1) and (2,2).
+// These are data-dependent (not integrand-dependent) tests: both fire for the constraint block of
+// every PDE that is linear in (y,u) — e.g. the membrane problem.
+template <class E, bool UROW>
+__device__ __forceinline__ bool fe_hess_block_is_zero(const Jet2<E::M>& L) {
   using J2 = Jet2<E::M>;
-  constexpr int NF = E::NU > 0 ? E::SU + 1 : E::SU;  // fields 0..SU (SU unused without a control)
   bool z = true;
+  if (!UROW) {
 #pragma unroll
-  for (int k = 0; k < NF; ++k)
+    for (int k = 0; k < E::NB; ++k)
 #pragma unroll
-    for (int l = 0; l <= k; ++l) z = z && (L.h[J2::idx(k, l)] == 0.0);
+      for (int l = 0; l <= k; ++l) z = z && (L.h[J2::idx(k, l)] == 0.0);
+  } else if (E::NU > 0) {
+#pragma unroll
+    for (int l = 0; l <= E::SU; ++l) z = z && (L.h[J2::idx(E::SU, l)] == 0.0);
+  }
   return z;
 }
 
@@ -638,45 +643,59 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
     const int incl = warp_incl_scan(cnt, lane);
     const int64_t tb = D.base_h[tile];
 
-    if (vals_obj != nullptr) {
-      double* gdst = vals_obj + tb;
+    const int n11 = fy * (fy + 1) / 2;  // kept entries of block (1,1) (distinct ids)
+    // One staged FE block of the tile.  jet_at(q, scale) returns the pointwise Jet2 whose Hessian
+    // w.r.t. the FE fields generates the block.  Structural zeros are detected at run time, per
+    // sub-block and warp-uniformly (all quadrature points, all lanes): a vanishing (y,y) part and/or
+    // a vanishing u row skip their candidates; if both vanish the image is zero-filled.
+    auto segment = [&](double* gdst, auto&& jet_at) {
       st.acquire(lane);
       double* const p0 = st.begin(gdst, incl - cnt, lane);
+      bool zyy = true, zu = true;
+      Jet2<E::M> L;
+      double scale = 0.0;
 #pragma unroll 1
       for (int q = 0; q < E::NQ; ++q) {
+        L = jet_at(q, scale);
+        zyy = zyy && (scale == 0.0 || fe_hess_block_is_zero<E, false>(L));
+        zu = zu && (scale == 0.0 || fe_hess_block_is_zero<E, true>(L));
+      }
+      zyy = __all_sync(0xffffffffu, zyy || !valid);
+      zu = __all_sync(0xffffffffu, zu || !valid);
+      if (zyy && zu) {
+        st.zero_fill(__shfl_sync(0xffffffffu, incl, 31), lane);
+      } else {
+#pragma unroll 1
+        for (int q = 0; q < E::NQ; ++q) {
+          if (E::NQ > 1) L = jet_at(q, scale);  // NQ == 1: the jet of the test pass is reused
+          double* p = p0;
+          if (!zyy) p = (q == 0) ? emit_hess_yy<E, false>(tab, q, L, scale, c, p) : emit_hess_yy<E, true>(tab, q, L, scale, c, p);
+          else { if (q == 0) for (int k = 0; k < n11; ++k) p[k] = 0.0; p += n11; }
+          if (!zu) { if (q == 0) emit_hess_u<E, false>(tab, q, L, scale, c, p); else emit_hess_u<E, true>(tab, q, L, scale, c, p); }
+          else if (q == 0) for (int k = 0; k < cnt - n11; ++k) p[k] = 0.0;
+        }
+      }
+      st.release(gdst, incl - cnt, incl, lane);
+    };
+    if (vals_obj != nullptr) {
+      segment(vals_obj + tb, [&](int q, double& scale) {
         Jet2<E::M> s[E::M];
         point_state<E>(tab, c, x, q, s);
         const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
-        const Jet2<E::M> F = I::f(pc, s);
-        if (E::NQ == 1 && __all_sync(0xffffffffu, !valid || obj_weight == 0.0 || fe_hess_is_zero<E>(F))) {
-          st.zero_fill(__shfl_sync(0xffffffffu, incl, 31), lane);
-          continue;
-        }
-        if (q == 0) emit_hess<E, false>(tab, q, F, obj_weight * tab.wdet[q], c, p0);
-        else        emit_hess<E, true>(tab, q, F, obj_weight * tab.wdet[q], c, p0);
-      }
-      st.release(gdst, incl - cnt, incl, lane);
+        scale = obj_weight * tab.wdet[q];
+        return I::f(pc, s);
+      });
     }
     if (vals_con != nullptr) {
-      double* gdst = vals_con + tb;
-      st.acquire(lane);
-      double* const p0 = st.begin(gdst, incl - cnt, lane);
-#pragma unroll 1
-      for (int q = 0; q < E::NQ; ++q) {
+      segment(vals_con + tb, [&](int q, double& scale) {
         Jet2<E::M> s[E::M];
         point_state<E>(tab, c, x, q, s);
         const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
         double Lam[E::NR];
         lambda_slots<E>(tab, q, lam_e, Lam);
-        const Jet2<E::M> L = weighted_res<E>(pc, s, Lam);
-        if (E::NQ == 1 && __all_sync(0xffffffffu, !valid || fe_hess_is_zero<E>(L))) {
-          st.zero_fill(__shfl_sync(0xffffffffu, incl, 31), lane);
-          continue;
-        }
-        if (q == 0) emit_hess<E, false>(tab, q, L, tab.wdet[q], c, p0);
-        else        emit_hess<E, true>(tab, q, L, tab.wdet[q], c, p0);
-      }
-      st.release(gdst, incl - cnt, incl, lane);
+        scale = tab.wdet[q];
+        return weighted_res<E>(pc, s, Lam);
+      });
     }
     if (!has_next) break;
     c = n;
