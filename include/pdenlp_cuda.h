@@ -190,6 +190,9 @@ int pdenlp_jac_coord(pdenlp_model* m, const double* x, double* vals);
    (src/fill_matrix_hessian_functions.jl:50-94). */
 int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda,
                       double obj_weight, double* vals);
+/* objective part only, vals[nnzh_obj]: all there is for an AffineFEOperator model, whose
+   constraint-Hessian structure is empty (src/hessian_struct_nnzh_functions.jl:70-72) */
+int pdenlp_hess_coord_obj(pdenlp_model* m, const double* x, double obj_weight, double* vals);
 
 /* jprod_nln!(nlp, x, v, Jv)            src/GridapPDENLPModel.jl:473-487
    jtprod_nln!(nlp, x, v, Jtv)          src/GridapPDENLPModel.jl:505-519
@@ -210,6 +213,28 @@ int pdenlp_hprod(pdenlp_model* m, const double* x, const double* lambda,
    to cross-check them and, in this container, as the structure source. */
 int pdenlp_jac_structure(pdenlp_model* m, int64_t* rows, int64_t* cols);
 int pdenlp_hess_structure(pdenlp_model* m, int64_t* rows, int64_t* cols);
+
+/* ---- COO -> compressed sparse, duplicates summed -----------------------
+   What consumes the COO streams next: NLPModels jac()/hess() = sparse(rows, cols, vals), and the
+   linear API of an AffineFEOperator model, whose jac_lin_structure!/jac_lin_coord! return
+   findnz(get_matrix(op)) (src/jacobian_functions.jl:11-21, src/GridapPDENLPModel.jl:597-608): the
+   assembled matrix in CSC order, rows ascending inside a column.  The plan is built once from the
+   static structure (stable device sort); apply() is a deterministic gather-sum (no atomics), each
+   entry adding its contributions in COO (= cell) order. */
+#define PDENLP_ORDER_CSC 0
+#define PDENLP_ORDER_CSR 1
+typedef struct pdenlp_compaction pdenlp_compaction; /* opaque */
+/* rows/cols: 1-based Int64 COO structure (host pointers, or device pointers when
+   rows_cols_on_device != 0); the plan lives on the current CUDA device. */
+int pdenlp_compaction_create(int64_t nnz, const int64_t* rows, const int64_t* cols, int64_t nrows, int64_t ncols,
+                             int32_t order, int32_t rows_cols_on_device, pdenlp_compaction** out);
+int pdenlp_compaction_destroy(pdenlp_compaction* p);
+int pdenlp_compaction_nnz(const pdenlp_compaction* p, int64_t* nnz_out);
+/* compressed structure: rows/cols (1-based, nnz_out each) and/or the 1-based pointer array
+   (colptr for CSC: ncols+1 entries, rowptr for CSR: nrows+1); any of them may be NULL */
+int pdenlp_compaction_structure(pdenlp_compaction* p, int64_t* rows, int64_t* cols, int64_t* major_ptr, int32_t on_device);
+/* out_vals[e] = sum of the COO values mapped to compressed entry e (device pointers) */
+int pdenlp_compaction_apply(pdenlp_compaction* p, const double* coo_vals, double* out_vals, void* cuda_stream);
 
 /* bench support: number of kernel launches issued by this handle so far, and
    the CUDA-event time (ms) of the most recent callback on the handle's stream */

@@ -9,7 +9,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libpdenlp_cuda.so")
-SOURCES = ["pdenlp_cuda.cu"]
+SOURCES = ["pdenlp_cuda.cu", "compaction.cu"]
 HEADERS = ["kernels.cuh", "integrands.cuh", "jet.cuh", os.path.join("..", "..", "include", "pdenlp_cuda.h")]
 
 NVCC_FLAGS = [

@@ -25,10 +25,13 @@ SYMBOLS = [
     "pdenlp_last_error", "pdenlp_abi_version", "pdenlp_create", "pdenlp_destroy", "pdenlp_get_info",
     "pdenlp_set_stream", "pdenlp_sync", "pdenlp_malloc", "pdenlp_free", "pdenlp_memcpy_h2d", "pdenlp_memcpy_d2h",
     "pdenlp_host_alloc", "pdenlp_host_free",
-    "pdenlp_obj", "pdenlp_grad", "pdenlp_cons", "pdenlp_jac_coord", "pdenlp_hess_coord",
+    "pdenlp_obj", "pdenlp_grad", "pdenlp_cons", "pdenlp_jac_coord", "pdenlp_hess_coord", "pdenlp_hess_coord_obj",
     "pdenlp_jprod", "pdenlp_jtprod", "pdenlp_hprod", "pdenlp_jac_structure", "pdenlp_hess_structure",
     "pdenlp_launch_count", "pdenlp_last_kernel_ms", "pdenlp_set_timing",
+    "pdenlp_compaction_create", "pdenlp_compaction_destroy", "pdenlp_compaction_nnz",
+    "pdenlp_compaction_structure", "pdenlp_compaction_apply",
 ]
+ORDER_CSC, ORDER_CSR = 0, 1
 
 
 class Desc(C.Structure):
@@ -88,6 +91,7 @@ def load():
     lib.pdenlp_cons.argtypes = [vp, vp, vp]
     lib.pdenlp_jac_coord.argtypes = [vp, vp, vp]
     lib.pdenlp_hess_coord.argtypes = [vp, vp, vp, dbl, vp]
+    lib.pdenlp_hess_coord_obj.argtypes = [vp, vp, dbl, vp]
     lib.pdenlp_jprod.argtypes = [vp, vp, vp, vp]
     lib.pdenlp_jtprod.argtypes = [vp, vp, vp, vp]
     lib.pdenlp_hprod.argtypes = [vp, vp, vp, dbl, vp, vp]
@@ -96,6 +100,11 @@ def load():
     lib.pdenlp_launch_count.argtypes = [vp, C.POINTER(i64)]
     lib.pdenlp_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.pdenlp_set_timing.argtypes = [vp, C.c_int32]
+    lib.pdenlp_compaction_create.argtypes = [i64, vp, vp, i64, i64, C.c_int32, C.c_int32, C.POINTER(vp)]
+    lib.pdenlp_compaction_destroy.argtypes = [vp]
+    lib.pdenlp_compaction_nnz.argtypes = [vp, C.POINTER(i64)]
+    lib.pdenlp_compaction_structure.argtypes = [vp, vp, vp, vp, C.c_int32]
+    lib.pdenlp_compaction_apply.argtypes = [vp, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -177,6 +186,9 @@ class Handle:
     def hess_coord(self, x, lam, obj_weight, vals):
         check(load().pdenlp_hess_coord(self._h, x, lam, float(obj_weight), vals))
 
+    def hess_coord_obj(self, x, obj_weight, vals):
+        check(load().pdenlp_hess_coord_obj(self._h, x, float(obj_weight), vals))
+
     def jprod(self, x, v, out):
         check(load().pdenlp_jprod(self._h, x, v, out))
 
@@ -204,3 +216,39 @@ class Handle:
         ms = C.c_float()
         check(load().pdenlp_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value
+
+
+class Compaction:
+    """Owns one ``pdenlp_compaction*``: COO -> CSC/CSR plan with duplicates summed (device)."""
+
+    def __init__(self, rows, cols, nrows: int, ncols: int, order: int = ORDER_CSC):
+        """rows/cols: 1-based int64, numpy arrays (host) or CUDA torch tensors (device)."""
+        lib = load()
+        on_dev = int(hasattr(rows, "data_ptr"))
+        pr = rows.data_ptr() if on_dev else rows.ctypes.data
+        pc = cols.data_ptr() if on_dev else cols.ctypes.data
+        n = int(rows.numel() if on_dev else rows.size)
+        h = C.c_void_p()
+        check(lib.pdenlp_compaction_create(n, pr, pc, nrows, ncols, order, on_dev, C.byref(h)))
+        self._h = h
+        self.nrows, self.ncols, self.order, self.nnz_in = nrows, ncols, order, n
+        m = C.c_int64()
+        check(lib.pdenlp_compaction_nnz(h, C.byref(m)))
+        self.nnz = m.value
+
+    def structure(self, rows_ptr=None, cols_ptr=None, major_ptr=None, on_device: bool = False):
+        check(load().pdenlp_compaction_structure(self._h, rows_ptr, cols_ptr, major_ptr, int(on_device)))
+
+    def apply(self, coo_vals_ptr: int, out_ptr: int, stream_ptr: int = 0):
+        check(load().pdenlp_compaction_apply(self._h, coo_vals_ptr, out_ptr, C.c_void_p(stream_ptr)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().pdenlp_compaction_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

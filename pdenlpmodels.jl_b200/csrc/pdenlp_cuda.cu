@@ -16,12 +16,12 @@
 
 using namespace pdenlp;
 
+thread_local std::string pdenlp_g_err;  // shared with compaction.cu
+
 namespace {
 
-thread_local std::string g_err;
-
 int fail(int code, const std::string& msg) {
-  g_err = msg;
+  pdenlp_g_err = msg;
   return code;
 }
 #define CU(call)                                                                                   \
@@ -271,7 +271,7 @@ struct Scope {  // device + timing bracket of one callback
 
 extern "C" {
 
-const char* pdenlp_last_error(void) { return g_err.c_str(); }
+const char* pdenlp_last_error(void) { return pdenlp_g_err.c_str(); }
 int pdenlp_abi_version(void) { return PDENLP_ABI_VERSION; }
 
 int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
@@ -565,6 +565,28 @@ int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda, do
   if (int rc = m->ops->hess(L, m->dm, dx, dl, obj_weight, vfo, dl ? vfc : nullptr)) return rc;
   m->launches += 1;
   return out_finish(m, vals, I.nnzh);
+}
+
+// objective part only, vals[nnzh_obj]: the whole Hessian of a model whose operator is affine
+// (its constraint Hessian structure is empty, src/hessian_struct_nnzh_functions.jl:70-72)
+int pdenlp_hess_coord_obj(pdenlp_model* m, const double* x, double obj_weight, double* vals) {
+  if (!m || !x || !vals) return fail(PDENLP_EINVAL, "null argument");
+  Scope sc(m);
+  const double* dx;
+  double* dv;
+  const pdenlp_info& I = m->info;
+  if (int rc = in_ptr(m, x, I.nvar, &m->sx, &dx)) return rc;
+  if (int rc = out_ptr(m, vals, I.nnzh_obj, &dv)) return rc;
+  Launch L{m->stream, m->sms};
+  if (I.nnzh_k_obj > 0) {
+    if (!m->dm.coef) return fail(PDENLP_EINVAL, "the kappa blocks need the coefficient fields (desc.coef)");
+    CU(cudaMemsetAsync(dv, 0, (size_t)I.nnzh_k_obj * 8, m->stream));
+    if (int rc = m->ops->hess_kappa(L, m->dm, dx, nullptr, obj_weight, 0, m->inde ? m->d.nparam : I.nvar, dv)) return rc;
+    m->launches += 1;
+  }
+  if (int rc = m->ops->hess(L, m->dm, dx, nullptr, obj_weight, dv + I.nnzh_k_obj, nullptr)) return rc;
+  m->launches += 1;
+  return out_finish(m, vals, I.nnzh_obj);
 }
 
 static int structure_call(pdenlp_model* m, bool hess, int64_t* rows, int64_t* cols) {

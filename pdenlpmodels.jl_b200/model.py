@@ -118,8 +118,26 @@ class GridapPDENLPModel:
         self.handle = capi.Handle(fm, device=self.device.index if self.device.index is not None else 0,
                                   memspace=ms, with_coef=with_coef)
         I = self.handle.info
+        self.affine = bool(getattr(spec, "affine", False))
+        self._jac_plan = self._hess_plan = None
+        self._Alin_vals = None
+        if self.affine:
+            # AffineFEOperator: lin = 1:ncon, lin_nnzj = nnzj = nnz(A), nln_nnzj = 0
+            # (src/additional_constructors.jl:213-223); Jacobian structure = findnz(A)
+            # (src/jacobian_functions.jl:11-21); empty constraint-Hessian structure
+            # (src/hessian_struct_nnzh_functions.jl:70-72) => nnzh = nnzh_obj.
+            if spec.nparam:
+                raise NotImplementedError("AffineFEOperator with algebraic variables (the reference only warns)")
+            if memspace != "device":
+                raise NotImplementedError("the linear-API model keeps its vectors on the device")
+            self._jac_plan = self._make_plan(False, I.nnzj)
+            nnzj, nnzh = self._jac_plan.nnz, I.nnzh_obj
+            lin_nnzj, nln_nnzj, nlin, nnln = nnzj, 0, I.ncon, 0
+        else:
+            nnzj, nnzh = I.nnzj, I.nnzh
+            lin_nnzj, nln_nnzj, nlin, nnln = 0, I.nnzj, 0, I.ncon
         self.meta = NLPModelMeta(
-            nvar=I.nvar, ncon=I.ncon, nnzj=I.nnzj, nnzh=I.nnzh, lin_nnzj=0, nln_nnzj=I.nnzj, nlin=0, nnln=I.ncon,
+            nvar=I.nvar, ncon=I.ncon, nnzj=nnzj, nnzh=nnzh, lin_nnzj=lin_nnzj, nln_nnzj=nln_nnzj, nlin=nlin, nnln=nnln,
             name=spec.name, x0=np.zeros(I.nvar), lvar=np.full(I.nvar, -np.inf), uvar=np.full(I.nvar, np.inf),
             lcon=np.zeros(I.ncon), ucon=np.zeros(I.ncon), y0=np.zeros(I.ncon),
         )
@@ -192,6 +210,125 @@ class GridapPDENLPModel:
                 user[...] = buf
         return user
 
+    # ------------------------------------------------------------------ compaction plans (COO -> CSC)
+    def _make_plan(self, hess: bool, nnz: int):
+        """Device plan summing duplicates of the COO structure into CSC order (findnz order)."""
+        rows = torch.empty(nnz, dtype=torch.int64, device=self.device)
+        cols = torch.empty(nnz, dtype=torch.int64, device=self.device)
+        (self.handle.hess_structure if hess else self.handle.jac_structure)(rows.data_ptr(), cols.data_ptr())
+        I = self.handle.info
+        with torch.cuda.device(self.device):
+            plan = capi.Compaction(rows, cols, I.nvar if hess else I.ncon, I.nvar, capi.ORDER_CSC)
+        return plan
+
+    def _plan_structure(self, plan, with_ptr: bool = False):
+        rows = torch.empty(plan.nnz, dtype=torch.int64, device=self.device)
+        cols = torch.empty(plan.nnz, dtype=torch.int64, device=self.device)
+        ptr = torch.empty(plan.ncols + 1, dtype=torch.int64, device=self.device) if with_ptr else None
+        plan.structure(rows.data_ptr(), cols.data_ptr(), ptr.data_ptr() if with_ptr else None, on_device=True)
+        return (rows, cols, ptr) if with_ptr else (rows, cols)
+
+    def jac_csc(self, x):
+        """NLPModels ``jac(nlp, x)`` as (colptr, rowval, nzval), 1-based like SparseMatrixCSC:
+        sparse(rows, cols, vals, ncon, nvar) with duplicates summed on the device."""
+        if self.memspace != "device":
+            raise NotImplementedError("jac_csc needs a device-memspace model")
+        I = self.handle.info
+        if self._jac_plan is None:
+            self._jac_plan = self._make_plan(False, I.nnzj)
+        coo = torch.empty(I.nnzj, dtype=torch.float64, device=self.device)
+        self._use_current_stream()
+        px, kx = self._in(x)
+        self.handle.jac_coord(px, coo.data_ptr())
+        out = torch.empty(self._jac_plan.nnz, dtype=torch.float64, device=self.device)
+        self._jac_plan.apply(coo.data_ptr(), out.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+        rows, cols, ptr = self._plan_structure(self._jac_plan, with_ptr=True)
+        return ptr, rows, out
+
+    def hess_csc(self, x, y=None, obj_weight: float = 1.0):
+        """NLPModels ``hess(nlp, x[, y])``: lower triangle sparse(rows, cols, vals, nvar, nvar) with
+        the overlapping objective / constraint segments summed, as (colptr, rowval, nzval)."""
+        if self.memspace != "device" or self.affine:
+            raise NotImplementedError
+        I = self.handle.info
+        if self._hess_plan is None:
+            self._hess_plan = self._make_plan(True, I.nnzh)
+        coo = self.hess_coord(x, y, obj_weight=obj_weight)
+        out = torch.empty(self._hess_plan.nnz, dtype=torch.float64, device=self.device)
+        self._hess_plan.apply(coo.data_ptr(), out.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+        rows, cols, ptr = self._plan_structure(self._hess_plan, with_ptr=True)
+        return ptr, rows, out
+
+    # ------------------------------------------------------------------ linear API (AffineFEOperator)
+    def _require_affine(self):
+        if not self.affine:
+            raise TypeError("linear-API methods exist only for AffineFEOperator models")
+
+    def cons_lin_(self, x, c):
+        """cons_lin!: mul!(c, A, x); c -= b (src/GridapPDENLPModel.jl:460-471) — evaluated matrix-free
+        as the assembled residual of the same bilinear/linear forms."""
+        self._require_affine()
+        self._lencheck(self.meta.nvar, x=x)
+        self._lencheck(self.meta.nlin, c=c)
+        self.counters.neval_cons_lin += 1
+        self._use_current_stream()
+        px, kx = self._in(x)
+        pc, bc, cb = self._out(c)
+        self.handle.cons(px, pc)
+        return self._finish(c, bc, cb)
+
+    def _lin_vals(self):
+        if self._Alin_vals is None:  # A is constant: assemble its CSC values once
+            I = self.handle.info
+            coo = torch.empty(I.nnzj, dtype=torch.float64, device=self.device)
+            x0 = torch.zeros(I.nvar, dtype=torch.float64, device=self.device)
+            self.handle.jac_coord(x0.data_ptr(), coo.data_ptr())
+            out = torch.empty(self._jac_plan.nnz, dtype=torch.float64, device=self.device)
+            self._jac_plan.apply(coo.data_ptr(), out.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+            self._Alin_vals = out
+        return self._Alin_vals
+
+    def jac_lin_coord_(self, x, vals):
+        """jac_lin_coord!: vals .= findnz(get_matrix(op))[3] (src/GridapPDENLPModel.jl:597-608)."""
+        self._require_affine()
+        self._lencheck(self.meta.nvar, x=x)
+        self._lencheck(self.meta.lin_nnzj, vals=vals)
+        self.counters.neval_jac_lin += 1
+        self._use_current_stream()
+        vals.copy_(self._lin_vals())
+        return vals
+
+    def jac_lin_structure_(self, rows, cols):
+        self._require_affine()
+        self._lencheck(self.meta.lin_nnzj, rows=rows, cols=cols)
+        r, c = self._plan_structure(self._jac_plan)
+        rows.copy_(r); cols.copy_(c)
+        return rows, cols
+
+    def jprod_lin_(self, x, v, Jv):
+        self._require_affine()
+        self._lencheck(self.meta.nvar, x=x, v=v)
+        self._lencheck(self.meta.nlin, Jv=Jv)
+        self.counters.neval_jprod_lin += 1
+        self._use_current_stream()
+        px, kx = self._in(x)
+        pv, kv = self._in(v)
+        po, bo, cb = self._out(Jv)
+        self.handle.jprod(px, pv, po)
+        return self._finish(Jv, bo, cb)
+
+    def jtprod_lin_(self, x, v, Jtv):
+        self._require_affine()
+        self._lencheck(self.meta.nvar, x=x, Jtv=Jtv)
+        self._lencheck(self.meta.nlin, v=v)
+        self.counters.neval_jtprod_lin += 1
+        self._use_current_stream()
+        px, kx = self._in(x)
+        pv, kv = self._in(v)
+        po, bo, cb = self._out(Jtv)
+        self.handle.jtprod(px, pv, po)
+        return self._finish(Jtv, bo, cb)
+
     # ------------------------------------------------------------------ obj / grad / cons
     def obj(self, x) -> float:
         self._lencheck(self.meta.nvar, x=x)
@@ -228,7 +365,7 @@ class GridapPDENLPModel:
         self._lencheck(self.meta.nvar, x=x)
         self._lencheck(self.meta.ncon, c=c)
         self.counters.neval_cons += 1
-        return self.cons_nln_(x, c)
+        return self.cons_lin_(x, c) if self.meta.nlin > 0 else self.cons_nln_(x, c)
 
     def cons(self, x):
         return self.cons_(x, self._new(self.meta.ncon))
@@ -248,7 +385,7 @@ class GridapPDENLPModel:
         self._lencheck(self.meta.nvar, x=x)
         self._lencheck(self.meta.nnzj, vals=vals)
         self.counters.neval_jac += 1
-        return self.jac_nln_coord_(x, vals)
+        return self.jac_lin_coord_(x, vals) if self.meta.nlin > 0 else self.jac_nln_coord_(x, vals)
 
     def jac_coord(self, x):
         return self.jac_coord_(x, self._new(self.meta.nnzj))
@@ -257,7 +394,8 @@ class GridapPDENLPModel:
         self._lencheck(self.meta.nln_nnzj, rows=rows, cols=cols)
         return self._structure(False, rows, cols)
 
-    jac_structure_ = jac_nln_structure_
+    def jac_structure_(self, rows, cols):
+        return self.jac_lin_structure_(rows, cols) if self.meta.nlin > 0 else self.jac_nln_structure_(rows, cols)
 
     def jac_structure(self):
         return self.jac_structure_(self._new(self.meta.nnzj, dtype=torch.int64), self._new(self.meta.nnzj, dtype=torch.int64))
@@ -292,7 +430,7 @@ class GridapPDENLPModel:
         self._lencheck(self.meta.nvar, x=x, v=v)
         self._lencheck(self.meta.ncon, Jv=Jv)
         self.counters.neval_jprod += 1
-        return self.jprod_nln_(x, v, Jv)
+        return self.jprod_lin_(x, v, Jv) if self.meta.nlin > 0 else self.jprod_nln_(x, v, Jv)
 
     def jprod(self, x, v):
         return self.jprod_(x, v, self._new(self.meta.ncon))
@@ -312,7 +450,7 @@ class GridapPDENLPModel:
         self._lencheck(self.meta.nvar, x=x, Jtv=Jtv)
         self._lencheck(self.meta.ncon, v=v)
         self.counters.neval_jtprod += 1
-        return self.jtprod_nln_(x, v, Jtv)
+        return self.jtprod_lin_(x, v, Jtv) if self.meta.nlin > 0 else self.jtprod_nln_(x, v, Jtv)
 
     def jtprod(self, x, v):
         return self.jtprod_(x, v, self._new(self.meta.nvar))
@@ -335,7 +473,10 @@ class GridapPDENLPModel:
         px, kx = self._in(x)
         pl, kl = self._in(lam)
         pv, bv, cb = self._out(vals)
-        self.handle.hess_coord(px, pl, obj_weight, pv)
+        if self.affine:  # the constraint-Hessian structure of an affine operator is empty
+            self.handle.hess_coord_obj(px, obj_weight, pv)
+        else:
+            self.handle.hess_coord(px, pl, obj_weight, pv)
         return self._finish(vals, bv, cb)
 
     def hess_coord(self, x, y=None, obj_weight: float = 1.0):
@@ -344,6 +485,13 @@ class GridapPDENLPModel:
 
     def hess_structure_(self, rows, cols):
         self._lencheck(self.meta.nnzh, rows=rows, cols=cols)
+        if self.affine:  # objective segment only
+            n = self.handle.info.nnzh
+            r = torch.empty(n, dtype=torch.int64, device=self.device)
+            c = torch.empty(n, dtype=torch.int64, device=self.device)
+            self._structure(True, r, c)
+            rows.copy_(r[: self.meta.nnzh]); cols.copy_(c[: self.meta.nnzh])
+            return rows, cols
         return self._structure(True, rows, cols)
 
     def hess_structure(self):
@@ -366,7 +514,7 @@ class GridapPDENLPModel:
         pl, kl = self._in(lam)
         pv, kv = self._in(v)
         po, bo, cb = self._out(Hv)
-        self.handle.hprod(px, pl, obj_weight, pv, po)
+        self.handle.hprod(px, None if self.affine else pl, obj_weight, pv, po)
         return self._finish(Hv, bo, cb)
 
     def hprod(self, x, *args, obj_weight: float = 1.0):

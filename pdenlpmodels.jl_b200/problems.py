@@ -46,6 +46,9 @@ class ProblemSpec:
     # coefficient fields: callables X (npts, dim) -> (npts,)
     target: Optional[Callable] = None  # yd / sol
     source: Optional[Callable] = None  # h / f
+    # True: the constraint is an AffineFEOperator (linear API: cons_lin!, jac_lin_coord!, ...;
+    # Jacobian structure = findnz(A); empty constraint-Hessian structure)
+    affine: bool = False
 
     @property
     def nvar(self) -> int:
@@ -63,19 +66,22 @@ def _h_membrane(X):
     return -np.sin(_OMEGA * X[:, 0]) * np.sin(_OMEGA * X[:, 1])
 
 
-def controlelasticmembrane(n: int = 100) -> ProblemSpec:
+def controlelasticmembrane(n: int = 100, affine: bool = False) -> ProblemSpec:
     """README 'Control elastic membrane' (README.md:58-98; docstring
     src/GridapPDENLPModel.jl:164-204): Q2 state with Dirichlet boundary, Q1
-    control, degree 1, res-function (FEOperatorFromWeakForm) variant."""
+    control, degree 1, res-function (FEOperatorFromWeakForm) variant.
+    ``affine=True`` is the test-suite variant built on an AffineFEOperator
+    (test/problems/controlelasticmembrane.jl:48-53): same PDE, linear API."""
     model = CartesianDiscreteModel((-1, 1, -1, 1), (n, n))
     Ypde = LagrangianFESpace(model, 2, "H1", "boundary", 0.0)
     Ycon = LagrangianFESpace(model, 1, "H1")
     return ProblemSpec(
-        name="Control elastic membrane",
+        name="Control elastic membrane" if not affine else "controlelasticmembrane1",
         integrand=MEMBRANE, model=model, Ypde=Ypde, Ycon=Ycon, degree=1,
         params=(1e-2,),
         target=lambda X: -X[:, 0] ** 2,
         source=_h_membrane,
+        affine=affine,
     )
 
 
