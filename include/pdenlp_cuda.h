@@ -69,7 +69,13 @@ enum pdenlp_integrand {
   /* nparam=2: f = 0.5(sol-y)^2 + 0.5(k1-1)^2 + 0.5(k2-1)^2 ;
      res = k1*grad(v).grad(y) - v*f*k2 [- v*u when a control space is given]
      test/problems/poissonmixed.jl:33-44 */
-  PDENLP_KAPPA_POISSON = 5
+  PDENLP_KAPPA_POISSON = 5,
+  /* unconstrained (no res, ncon = 0): f = 0.5*grad(y).grad(y) - w*y, w = coef source
+     test/problems/penalizedpoisson.jl:31-38 */
+  PDENLP_PENALIZED_POISSON = 6,
+  /* unconstrained, two fields: f = 0.5*(ubis-u)^2 + 0.5*y^2, ubis = coef target
+     test/problems/basicunconstrained.jl:21-25 */
+  PDENLP_BASIC_UNCONSTRAINED = 7
 };
 
 /* coefficient fields sampled at quadrature points, coef[k][cell][q] */

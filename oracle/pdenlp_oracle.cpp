@@ -115,7 +115,7 @@ typedef struct oracle_problem {
 } oracle_problem;
 }
 
-enum { MEMBRANE = 1, PB = 2, BURGER_LIN = 3, BURGER_NL = 4, KAPPA_POISSON = 5 };
+enum { MEMBRANE = 1, PB = 2, BURGER_LIN = 3, BURGER_NL = 4, KAPPA_POISSON = 5, PENALIZED_POISSON = 6, BASIC_UNCONSTRAINED = 7 };
 
 static const double PI = 3.14159265358979323846;
 
@@ -133,6 +133,7 @@ static double coef_target(const oracle_problem& P, const double* x) {
       double s = std::sin(2 * PI * x[0]) * x[1];
       return P.dim == 3 ? s * x[2] : s;
     }
+    case BASIC_UNCONSTRAINED: return x[0] * x[0] + x[1] * x[1];  // ubis, basicunconstrained.jl:20
   }
   return 0.0;
 }
@@ -145,6 +146,7 @@ static double coef_source(const oracle_problem& P, const double* x) {
     }
     case BURGER_LIN:
     case BURGER_NL: return 2 * (P.params[1] + x[0] * x[0] * x[0]);  // burger1d.jl:24
+    case PENALIZED_POISSON: return 1.0;           // w, penalizedpoisson.jl:32
     case KAPPA_POISSON: {                         // f, poissonmixed.jl:31
       double s = (2 * PI * PI) * std::sin(2 * PI * x[0]) * x[1];
       return P.dim == 3 ? s * x[2] : s;
@@ -248,6 +250,17 @@ static S f_density(const oracle_problem& P, const Pt<S>& p) {
       S d = p.yd - p.y; S t = p.k[0] - P.params[2];
       return 0.5 * d * d + (0.5 * P.params[0]) * p.u * p.u + 0.5 * t * t;
     }
+    case PENALIZED_POISSON: {
+      // 0.5 * grad(y) . grad(y) - w * y   (penalizedpoisson.jl:33-35)
+      S gg = cst(0.0, p.y);
+      for (int d = 0; d < P.dim; ++d) gg = gg + p.gy[d] * p.gy[d];
+      return 0.5 * gg - p.h * p.y;
+    }
+    case BASIC_UNCONSTRAINED: {
+      // 0.5 * (ubis - u) * (ubis - u) + 0.5 * y * y   (basicunconstrained.jl:22-24)
+      S d = p.yd - p.u;
+      return 0.5 * d * d + 0.5 * p.y * p.y;
+    }
     case KAPPA_POISSON: {
       // 0.5*(sol-y)^2 + 0.5*(k1-1)^2 + 0.5*(k2-1)^2   (poissonmixed.jl:37-43)
       S d = p.yd - p.y; S a = p.k[0] - 1.0; S b = p.k[1] - 1.0;
@@ -265,6 +278,9 @@ static S res_density(const oracle_problem& P, const Pt<S>& p, double v, const do
   S one_dot = cst(0.0, p.y);
   for (int d = 0; d < P.dim; ++d) one_dot = one_dot + p.gy[d]; // grad(y) . one(grad(y))
   switch (P.integrand) {
+    case PENALIZED_POISSON:
+    case BASIC_UNCONSTRAINED:  // unconstrained problems have no residual
+      return cst(0.0, p.y);
     case MEMBRANE:   // grad(v).grad(y) - v*u - v*h
       return gg - v * p.u - v * p.h;
     case PB:         // grad(v).grad(y) + sinh(y)*v - u*v - v*h
@@ -582,6 +598,7 @@ struct Driver {
     int np = P->nparam;                                                            \
     if (np == 0 && ny == 9 && nu == 4) { typedef Driver<0, 9, 4> D; CALL; }        \
     else if (np == 0 && ny == 4 && nu == 4) { typedef Driver<0, 4, 4> D; CALL; }   \
+    else if (np == 0 && ny == 4 && nu == 0) { typedef Driver<0, 4, 0> D; CALL; }   \
     else if (np == 0 && ny == 2 && nu == 2) { typedef Driver<0, 2, 2> D; CALL; }   \
     else if (np == 1 && ny == 2 && nu == 2) { typedef Driver<1, 2, 2> D; CALL; }   \
     else if (np == 2 && ny == 4 && nu == 0) { typedef Driver<2, 4, 0> D; CALL; }   \

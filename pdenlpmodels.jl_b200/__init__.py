@@ -15,7 +15,8 @@ Layout (only what the hot path needs):
 """
 from . import cartesian, problems, flatten  # noqa: F401
 from .problems import (  # noqa: F401
-    controlelasticmembrane, poissonboltzman2d, burger1d, burger1d_param, poissonmixed, BASELINE_CONFIGS,
+    controlelasticmembrane, poissonboltzman2d, burger1d, burger1d_param, poissonmixed, penalizedpoisson,
+    basicunconstrained, BASELINE_CONFIGS,
 )
 
 __all__ = ["cartesian", "problems", "flatten"]

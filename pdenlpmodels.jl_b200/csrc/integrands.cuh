@@ -109,4 +109,40 @@ struct KappaPoisson : FieldIdx<DIM_, 2> {
   }
 };
 
+// ---- unconstrained problems: objective only, the residual is identically zero (ncon = 0 on the
+// host side; the constraint entry points are never called for these models)
+template <int DIM_>
+struct PenalizedPoisson : FieldIdx<DIM_, 0> {
+  using I = FieldIdx<DIM_, 0>;
+  static constexpr bool HAS_CONST = false;
+  static constexpr bool NEEDS_COEF_DERIV = false;
+  // 0.5 * grad(y).grad(y) - w * y
+  template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) {
+    T a = s[I::SG] * s[I::SG];
+#pragma unroll
+    for (int d = 1; d < DIM_; ++d) a = a + s[I::SG + d] * s[I::SG + d];
+    return 0.5 * a - c.source * s[I::SY];
+  }
+  template <class T> PDENLP_HD static void res(const PointCtx&, const T* s, T* R) {
+#pragma unroll
+    for (int t = 0; t < 1 + DIM_; ++t) R[t] = jet_const(0.0, s[0]);
+  }
+};
+
+template <int DIM_>
+struct BasicUnconstrained : FieldIdx<DIM_, 0> {
+  using I = FieldIdx<DIM_, 0>;
+  static constexpr bool HAS_CONST = false;
+  static constexpr bool NEEDS_COEF_DERIV = false;
+  // 0.5 * (ubis - u) * (ubis - u) + 0.5 * y * y
+  template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) {
+    T d = c.target - s[I::SU];
+    return 0.5 * d * d + 0.5 * s[I::SY] * s[I::SY];
+  }
+  template <class T> PDENLP_HD static void res(const PointCtx&, const T* s, T* R) {
+#pragma unroll
+    for (int t = 0; t < 1 + DIM_; ++t) R[t] = jet_const(0.0, s[0]);
+  }
+};
+
 }  // namespace pdenlp

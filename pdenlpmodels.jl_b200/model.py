@@ -136,10 +136,16 @@ class GridapPDENLPModel:
         else:
             nnzj, nnzh = I.nnzj, I.nnzh
             lin_nnzj, nln_nnzj, nlin, nnln = 0, I.nnzj, 0, I.ncon
+        self.unconstrained = bool(getattr(spec, "unconstrained", False))
+        ncon = I.ncon
+        if self.unconstrained:
+            # the reference's unconstrained constructor (src/additional_constructors.jl:1-66): no operator,
+            # ncon = 0, empty Jacobian, Hessian = objective segment only
+            ncon, nnzj, nnzh, lin_nnzj, nln_nnzj, nlin, nnln = 0, 0, I.nnzh_obj, 0, 0, 0, 0
         self.meta = NLPModelMeta(
-            nvar=I.nvar, ncon=I.ncon, nnzj=nnzj, nnzh=nnzh, lin_nnzj=lin_nnzj, nln_nnzj=nln_nnzj, nlin=nlin, nnln=nnln,
+            nvar=I.nvar, ncon=ncon, nnzj=nnzj, nnzh=nnzh, lin_nnzj=lin_nnzj, nln_nnzj=nln_nnzj, nlin=nlin, nnln=nnln,
             name=spec.name, x0=np.zeros(I.nvar), lvar=np.full(I.nvar, -np.inf), uvar=np.full(I.nvar, np.inf),
-            lcon=np.zeros(I.ncon), ucon=np.zeros(I.ncon), y0=np.zeros(I.ncon),
+            lcon=np.zeros(ncon), ucon=np.zeros(ncon), y0=np.zeros(ncon),
         )
         self.pdemeta = PDENLPMeta(
             nvar_pde=fm.nfree_y, nvar_con=fm.nfree_u, nparam=fm.nparam, nnzh_obj=I.nnzh_obj, nnzj_k=I.nnzj_k,
@@ -353,6 +359,8 @@ class GridapPDENLPModel:
         self._lencheck(self.meta.nvar, x=x)
         self._lencheck(self.meta.nnln, c=c)
         self.counters.neval_cons_nln += 1
+        if self.unconstrained:
+            return c
         self._use_current_stream()
         px, kx = self._in(x)
         pc, bc, cb = self._out(c)
@@ -375,6 +383,8 @@ class GridapPDENLPModel:
         self._lencheck(self.meta.nvar, x=x)
         self._lencheck(self.meta.nln_nnzj, vals=vals)
         self.counters.neval_jac_nln += 1
+        if self.unconstrained:
+            return vals
         self._use_current_stream()
         px, kx = self._in(x)
         pv, bv, cb = self._out(vals)
@@ -392,6 +402,8 @@ class GridapPDENLPModel:
 
     def jac_nln_structure_(self, rows, cols):
         self._lencheck(self.meta.nln_nnzj, rows=rows, cols=cols)
+        if self.unconstrained:
+            return rows, cols
         return self._structure(False, rows, cols)
 
     def jac_structure_(self, rows, cols):
@@ -419,6 +431,8 @@ class GridapPDENLPModel:
         self._lencheck(self.meta.nvar, x=x, v=v)
         self._lencheck(self.meta.nnln, Jv=Jv)
         self.counters.neval_jprod_nln += 1
+        if self.unconstrained:
+            return Jv
         self._use_current_stream()
         px, kx = self._in(x)
         pv, kv = self._in(v)
@@ -439,6 +453,9 @@ class GridapPDENLPModel:
         self._lencheck(self.meta.nvar, x=x, Jtv=Jtv)
         self._lencheck(self.meta.nnln, v=v)
         self.counters.neval_jtprod_nln += 1
+        if self.unconstrained:
+            Jtv[...] = 0.0
+            return Jtv
         self._use_current_stream()
         px, kx = self._in(x)
         pv, kv = self._in(v)
@@ -473,7 +490,7 @@ class GridapPDENLPModel:
         px, kx = self._in(x)
         pl, kl = self._in(lam)
         pv, bv, cb = self._out(vals)
-        if self.affine:  # the constraint-Hessian structure of an affine operator is empty
+        if self.affine or self.unconstrained:  # empty constraint-Hessian structure
             self.handle.hess_coord_obj(px, obj_weight, pv)
         else:
             self.handle.hess_coord(px, pl, obj_weight, pv)
@@ -485,7 +502,7 @@ class GridapPDENLPModel:
 
     def hess_structure_(self, rows, cols):
         self._lencheck(self.meta.nnzh, rows=rows, cols=cols)
-        if self.affine:  # objective segment only
+        if self.affine or self.unconstrained:  # objective segment only
             n = self.handle.info.nnzh
             r = torch.empty(n, dtype=torch.int64, device=self.device)
             c = torch.empty(n, dtype=torch.int64, device=self.device)
@@ -514,7 +531,7 @@ class GridapPDENLPModel:
         pl, kl = self._in(lam)
         pv, kv = self._in(v)
         po, bo, cb = self._out(Hv)
-        self.handle.hprod(px, None if self.affine else pl, obj_weight, pv, po)
+        self.handle.hprod(px, None if (self.affine or self.unconstrained) else pl, obj_weight, pv, po)
         return self._finish(Hv, bo, cb)
 
     def hprod(self, x, *args, obj_weight: float = 1.0):

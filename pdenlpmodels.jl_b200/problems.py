@@ -23,6 +23,8 @@ POISSON_BOLTZMANN = 2
 BURGER_LIN = 3
 BURGER_NL = 4
 KAPPA_POISSON = 5
+PENALIZED_POISSON = 6
+BASIC_UNCONSTRAINED = 7
 
 INTEGRAND_NAMES = {
     MEMBRANE: "membrane",
@@ -30,6 +32,8 @@ INTEGRAND_NAMES = {
     BURGER_LIN: "burger_lin",
     BURGER_NL: "burger_nl",
     KAPPA_POISSON: "kappa_poisson",
+    PENALIZED_POISSON: "penalized_poisson",
+    BASIC_UNCONSTRAINED: "basic_unconstrained",
 }
 
 
@@ -49,6 +53,9 @@ class ProblemSpec:
     # True: the constraint is an AffineFEOperator (linear API: cons_lin!, jac_lin_coord!, ...;
     # Jacobian structure = findnz(A); empty constraint-Hessian structure)
     affine: bool = False
+    # True: no constraint at all (the reference's unconstrained constructor,
+    # src/additional_constructors.jl:1-66): ncon = 0, nnzj = 0, nnzh = nnzh_obj
+    unconstrained: bool = False
 
     @property
     def nvar(self) -> int:
@@ -56,7 +63,7 @@ class ProblemSpec:
 
     @property
     def ncon(self) -> int:
-        return self.Ypde.nfree
+        return 0 if self.unconstrained else self.Ypde.nfree
 
 
 _OMEGA = math.pi - 1.0 / 8.0
@@ -160,6 +167,29 @@ def poissonmixed(n: int = 3, dim: int = 2, control: bool = False) -> ProblemSpec
         name="poissonmixed" if not control else "inversePoissonproblem",
         integrand=KAPPA_POISSON, model=model, Ypde=Ypde, Ycon=Ycon, degree=2,
         nparam=2, params=(), target=sol, source=f,
+    )
+
+
+def penalizedpoisson(n: int = 16) -> ProblemSpec:
+    """test/problems/penalizedpoisson.jl:14-42: min 0.5*int |grad y|^2 - w*y, y = 0 on the boundary
+    (Q1, degree 2, unconstrained; w = 1)."""
+    model = CartesianDiscreteModel((0, 1, 0, 1), (n, n))
+    Ypde = LagrangianFESpace(model, 1, "H1", "boundary", 0.0)
+    return ProblemSpec(
+        name="penalizedpoisson", integrand=PENALIZED_POISSON, model=model, Ypde=Ypde, Ycon=None, degree=2,
+        source=lambda X: np.ones(X.shape[0]), unconstrained=True,
+    )
+
+
+def basicunconstrained(n: int = 16) -> ProblemSpec:
+    """test/problems/basicunconstrained.jl:1-30: min 0.5*int (ubis-u)^2 + y^2 over the two fields
+    [y (Q1, Dirichlet 0), u (Q1)], degree 2, unconstrained."""
+    model = CartesianDiscreteModel((0, 1, 0, 1), (n, n))
+    Ypde = LagrangianFESpace(model, 1, "H1", "boundary", 0.0)
+    Ycon = LagrangianFESpace(model, 1, "H1")
+    return ProblemSpec(
+        name="basicunconstrained", integrand=BASIC_UNCONSTRAINED, model=model, Ypde=Ypde, Ycon=Ycon, degree=2,
+        target=lambda X: X[:, 0] ** 2 + X[:, 1] ** 2, unconstrained=True,
     )
 
 

@@ -22,6 +22,8 @@ CASES = {
     "burger1d_param_n6": lambda p: p.burger1d_param(6),
     "poissonmixed_n3": lambda p: p.poissonmixed(3),
     "inversepoisson3d_n2": lambda p: p.poissonmixed(2, 3, True),
+    "penalizedpoisson_n4": lambda p: p.penalizedpoisson(4),
+    "basicunconstrained_n3": lambda p: p.basicunconstrained(3),
 }
 
 
@@ -41,6 +43,16 @@ def main():
         o = O.Oracle(spec, nthreads=1)
         x, lam, v = inputs(o.nvar, o.ncon, spec.nparam)
         jr, jc = o.jac_structure(); hr, hc = o.hess_structure()
+        if spec.unconstrained:  # objective only: ncon = 0, no Jacobian, Hessian = objective segment
+            no = o.nnzh_obj
+            np.savez_compressed(
+                os.path.join(HERE, name + ".npz"),
+                x=x, v=v, obj_weight=0.37, obj=o.obj(x), grad=o.grad(x), unconstrained=True,
+                hess_rows=hr[:no], hess_cols=hc[:no], hess_obj_vals=o.hess_coord(x, None, 0.37)[:no],
+                hprod=o.hprod(x, v, None, 0.37), nnzh_obj=no,
+            )
+            print(name, "nvar", o.nvar, "unconstrained, nnzh", no)
+            continue
         np.savez_compressed(
             os.path.join(HERE, name + ".npz"),
             x=x, lam=lam, v=v, obj_weight=0.37, obj=o.obj(x), grad=o.grad(x), cons=o.cons(x),

@@ -29,6 +29,12 @@ def _close(a, b):
 def test_oracle_reproduces_golden(path, pkg, oracle_mod):
     g = np.load(path)
     o = oracle_mod.Oracle(_spec(pkg, os.path.basename(path)[:-4]), nthreads=1)
+    if "unconstrained" in g.files:
+        x, v, ow, no = g["x"], g["v"], float(g["obj_weight"]), int(g["nnzh_obj"])
+        r, c = o.hess_structure(); assert np.array_equal(r[:no], g["hess_rows"]) and np.array_equal(c[:no], g["hess_cols"])
+        assert _close(o.obj(x), g["obj"]) and _close(o.grad(x), g["grad"])
+        assert _close(o.hess_coord(x, None, ow)[:no], g["hess_obj_vals"]) and _close(o.hprod(x, v, None, ow), g["hprod"])
+        return
     x, lam, v, ow = g["x"], g["lam"], g["v"], float(g["obj_weight"])
     r, c = o.jac_structure(); assert np.array_equal(r, g["jac_rows"]) and np.array_equal(c, g["jac_cols"])
     r, c = o.hess_structure(); assert np.array_equal(r, g["hess_rows"]) and np.array_equal(c, g["hess_cols"])
@@ -46,6 +52,18 @@ def test_cuda_matches_golden(path, pkg, cuda_lib):
     g = np.load(path)
     nlp = GridapPDENLPModel(_spec(pkg, os.path.basename(path)[:-4]), device="cuda:0")
     d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    if "unconstrained" in g.files:
+        x, v, ow = d(g["x"]), d(g["v"]), float(g["obj_weight"])
+        assert (nlp.meta.ncon, nlp.meta.nnzj, nlp.meta.nnzh) == (0, 0, int(g["nnzh_obj"]))
+        r, c = nlp.hess_structure()
+        assert np.array_equal(r.cpu().numpy(), g["hess_rows"]) and np.array_equal(c.cpu().numpy(), g["hess_cols"])
+        assert _close(nlp.obj(x), g["obj"]) and _close(nlp.grad(x).cpu().numpy(), g["grad"])
+        assert _close(nlp.hess_coord(x, obj_weight=ow).cpu().numpy(), g["hess_obj_vals"])
+        assert _close(nlp.hprod(x, v, obj_weight=ow).cpu().numpy(), g["hprod"])
+        assert nlp.cons(x).numel() == 0 and nlp.jac_coord(x).numel() == 0
+        assert torch.all(nlp.jtprod(x, torch.empty(0, dtype=torch.float64, device="cuda")) == 0)
+        nlp.close()
+        return
     x, lam, v, ow = d(g["x"]), d(g["lam"]), d(g["v"]), float(g["obj_weight"])
     r, c = nlp.jac_structure()
     assert np.array_equal(r.cpu().numpy(), g["jac_rows"]) and np.array_equal(c.cpu().numpy(), g["jac_cols"])

@@ -156,3 +156,28 @@ def test_unaligned_guarded_outputs(case):
             torch.cuda.synchronize()
             assert torch.equal(view, ref)
             assert torch.isnan(big[:off]).all() and torch.isnan(big[off + n:]).all()
+
+
+@pytest.mark.parametrize("which", ["penalizedpoisson", "basicunconstrained"])
+def test_unconstrained_models(which, pkg, oracle_mod, cuda_lib):
+    """The reference's unconstrained constructor (src/additional_constructors.jl:1-66): ncon = 0,
+    empty Jacobian, Hessian = objective segment; values against the oracle."""
+    from pdenlp_b200.model import GridapPDENLPModel
+    spec = getattr(pkg, which)(24)
+    nlp = GridapPDENLPModel(spec, device="cuda:0")
+    orc = oracle_mod.Oracle(spec)
+    no = orc.nnzh_obj
+    assert (nlp.meta.nvar, nlp.meta.ncon, nlp.meta.nnzj, nlp.meta.nnzh) == (orc.nvar, 0, 0, no)
+    rng = np.random.default_rng(1998)
+    x = rng.uniform(-1, 1, orc.nvar); v = rng.uniform(-1, 1, orc.nvar)
+    f, fo = nlp.obj(_d(x)), orc.obj(x)
+    assert abs(f - fo) <= RTOL * abs(fo)
+    _close(nlp.grad(_d(x)).cpu().numpy(), orc.grad(x), "grad")
+    _close(nlp.hess_coord(_d(x), obj_weight=0.37).cpu().numpy(), orc.hess_coord(x, None, 0.37)[:no], "hess_coord")
+    _close(nlp.hprod(_d(x), _d(v), obj_weight=0.37).cpu().numpy(), orc.hprod(x, v, None, 0.37), "hprod")
+    r, c = nlp.hess_structure(); ro, co = orc.hess_structure()
+    assert np.array_equal(r.cpu().numpy(), ro[:no]) and np.array_equal(c.cpu().numpy(), co[:no])
+    empty = torch.empty(0, dtype=torch.float64, device="cuda")
+    assert nlp.cons(_d(x)).numel() == 0 and nlp.jac_coord(_d(x)).numel() == 0 and nlp.jprod(_d(x), _d(v)).numel() == 0
+    assert torch.all(nlp.jtprod(_d(x), empty) == 0)
+    nlp.close()

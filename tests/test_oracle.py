@@ -21,6 +21,8 @@ CASES = {
     "burger_nl_9": lambda p: p.burger1d_param(9),
     "kappa2d_3": lambda p: p.poissonmixed(3),
     "kappa3d_u_2": lambda p: p.poissonmixed(2, 3, True),
+    "penalizedpoisson_4": lambda p: p.penalizedpoisson(4),
+    "basicunconstrained_3": lambda p: p.basicunconstrained(3),
 }
 
 
@@ -161,3 +163,30 @@ def test_slab_concatenation(pkg, oracle_mod):
     assert np.array_equal(np.concatenate([ho, hc]), hf)
     assert np.allclose(sum(o.grad(x) for o in parts), full.grad(x), rtol=1e-14, atol=1e-16)
     assert np.isclose(sum(o.obj(x) for o in parts), full.obj(x), rtol=1e-14)
+
+
+def test_unconstrained_known_answers(pkg, oracle_mod):
+    """penalizedpoisson.jl:52-57 / basicunconstrained.jl:60-68: the Hessian is constant and
+    hprod == Symmetric(hess, :L) * v; basicunconstrained.jl:79-80: obj and grad are O(1/n) at the
+    interpolated solution (y = 0, u = ubis at the cell midpoints, last cell wins)."""
+    for mk in (pkg.penalizedpoisson, pkg.basicunconstrained):
+        spec = mk(6)
+        orc = oracle_mod.Oracle(spec)
+        rng = np.random.default_rng(0)
+        x1, x2, v = (rng.uniform(0, 1, orc.nvar) for _ in range(3))
+        no = orc.nnzh_obj
+        h1 = orc.hess_coord(x1, None, 1.0)[:no]; h2 = orc.hess_coord(x2, None, 1.0)[:no]
+        assert np.abs(h1 - h2).max() <= 1e-15
+        r, c = orc.hess_structure()
+        H = sp.coo_matrix((h1, (r[:no] - 1, c[:no] - 1)), shape=(orc.nvar, orc.nvar)).toarray()
+        H = H + np.tril(H, -1).T
+        assert np.allclose(orc.hprod(x1, v, None, 1.0), H @ v, rtol=1e-14, atol=1e-15)
+        assert np.all(orc.cons(x1) == 0.0)  # no residual
+    n = 10
+    spec = pkg.basicunconstrained(n)
+    orc = oracle_mod.Oracle(spec)
+    m = spec.model
+    mids = m.lo + (m.cell_multi_index() + 0.5) * m.h
+    solu = spec.Ycon.interpolate_cellwise_constant(mids[:, 0] ** 2 + mids[:, 1] ** 2)
+    sol = np.concatenate([np.zeros(spec.Ypde.nfree), solu])
+    assert orc.obj(sol) <= 1.0 / n and np.linalg.norm(orc.grad(sol)) <= 1.0 / n
