@@ -352,8 +352,14 @@ __host__ __device__ constexpr int hess_stage_doubles() { return StageLayout<E::R
 
 // ------------------------------------------------------------------ jac_coord!
 // vals layout (this slab): [k-block (ncon*p, filled elsewhere) | y-block | u-block]
+// Small elements (staging of a few KB per warp) leave most of the SM idle with one 8-warp CTA, so
+// their register budget is capped to let two CTAs share an SM; the host sizes the persistent grid
+// with the occupancy API.
 template <class E>
-__global__ void __launch_bounds__(kThreads, 1)
+constexpr int coord_min_blocks() { return E::RUN_H <= 48 ? 2 : 1; }
+
+template <class E>
+__global__ void __launch_bounds__(kThreads, coord_min_blocks<E>())
 k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const double* __restrict__ x,
             double* __restrict__ vals_y, double* __restrict__ vals_u) {
   using I = typename E::Integrand;
@@ -597,7 +603,7 @@ __device__ __forceinline__ void lambda_slots(const Tables<E>& tab, int q, const 
 
 // vals_obj / vals_con point at the FE blocks of this slab; either may be NULL (skipped).
 template <class E>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, coord_min_blocks<E>())
 k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const double* __restrict__ x,
              const double* __restrict__ lambda, double obj_weight,
              double* __restrict__ vals_obj, double* __restrict__ vals_con) {

@@ -65,10 +65,15 @@ struct OpsImpl : Ops {
   static constexpr size_t SMEM_J = (size_t)WJ * jac_stage_doubles<E>() * 8;
   static constexpr size_t SMEM_H = (size_t)WH * hess_stage_doubles<E>() * 8;
 
+  int occ_j = 1, occ_h = 1;  // resident CTAs per SM of the persistent coord kernels
   int set_attrs() {
     if (attr_done) return PDENLP_OK;
     CU(cudaFuncSetAttribute(k_jac_coord<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_J));
     CU(cudaFuncSetAttribute(k_hess_coord<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_H));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_j, k_jac_coord<E>, WJ * 32, SMEM_J));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_h, k_hess_coord<E>, WH * 32, SMEM_H));
+    occ_j = std::max(1, std::min(occ_j, 4));
+    occ_h = std::max(1, std::min(occ_h, 4));
     attr_done = true;
     return PDENLP_OK;
   }
@@ -92,14 +97,14 @@ struct OpsImpl : Ops {
   int jac(const Launch& L, const DevModel& D, const double* x, double* vy, double* vu) override {
     if (int rc = set_attrs()) return rc;
     static const int wj = env_warps("PDENLP_WARPS_J", WJ);
-    k_jac_coord<E><<<grid_for(D.ntiles, wj, L.sms), wj * 32, SMEM_J, L.stream>>>(tab, D, x, vy, vu);
+    k_jac_coord<E><<<grid_for(D.ntiles, wj, L.sms * occ_j), wj * 32, SMEM_J, L.stream>>>(tab, D, x, vy, vu);
     CU(cudaGetLastError());
     return PDENLP_OK;
   }
   int hess(const Launch& L, const DevModel& D, const double* x, const double* lam, double ow, double* vo, double* vc) override {
     if (int rc = set_attrs()) return rc;
     static const int wh = env_warps("PDENLP_WARPS_H", WH);
-    k_hess_coord<E><<<grid_for(D.ntiles, wh, L.sms), wh * 32, SMEM_H, L.stream>>>(tab, D, x, lam, ow, vo, vc);
+    k_hess_coord<E><<<grid_for(D.ntiles, wh, L.sms * occ_h), wh * 32, SMEM_H, L.stream>>>(tab, D, x, lam, ow, vo, vc);
     CU(cudaGetLastError());
     return PDENLP_OK;
   }

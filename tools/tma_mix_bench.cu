@@ -13,6 +13,32 @@ __global__ void __launch_bounds__(256, 1) k(double* out, size_t total_chunks, in
   double* b = smem + (size_t)warp * chunk_doubles;
   int acc = 0;
   const size_t stride = (size_t)gridDim.x * nw;
+  if (mode == 6 || mode == 7) {
+    // bursty reads: every G chunks the warp reads the ids of its next G chunks in one go
+    // (mode 6: G = 16, mode 7: G = 64), then streams G chunks without touching DRAM for reads
+    const int G = mode == 6 ? 16 : 64;
+    size_t c = (size_t)blockIdx.x * nw + warp;
+    while (c < total_chunks) {
+      for (int k = 0; k < G; ++k) {
+        const size_t cc = c + (size_t)k * stride;
+        if (cc < total_chunks) for (int a = 0; a < 13; ++a) acc += __ldg(ids + (cc * 13 + a) * 32 + lane);
+      }
+      for (int k = 0; k < G && c < total_chunks; ++k, c += stride) {
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        for (int i = lane; i < chunk_doubles / 2; i += 32) reinterpret_cast<double2*>(b)[i] = make_double2(1.0, (double)acc);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + c * chunk_doubles), "r"(s32(b)), "r"(chunk_doubles * 8) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (acc == 123456789) *sink = acc;
+    return;
+  }
   if (mode == 4 || mode == 5) {
     size_t c = (size_t)blockIdx.x * nw + warp;
     int g[13], gn[13]; double xv[13];
@@ -73,7 +99,7 @@ int main() {
   int* sink; cudaMalloc(&sink, 4);
   size_t smem = 8 * (size_t)cb;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  for (int mode = 0; mode < 6; ++mode) {
+  for (int mode = 0; mode < 8; ++mode) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     for (int i = 0; i < 2; ++i) k<<<148, 256, smem>>>(out, chunks, cb / 8, mode, ids, ldc, x, nx, sink);
     cudaEventRecord(a);
