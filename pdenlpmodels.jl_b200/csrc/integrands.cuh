@@ -39,6 +39,7 @@ struct Membrane : FieldIdx<DIM_, 0> {
   using I = FieldIdx<DIM_, 0>;
   static constexpr bool HAS_CONST = false;
   static constexpr bool NEEDS_COEF_DERIV = false;  // derivatives do not read coefficient fields
+  static constexpr bool FE_DERIVS_POINT_INDEPENDENT = true;  // d res/d(y,grad y,u) and the FE-field Hessians are the same at every point of a cell
   template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) { return tracking_f<T, I>(c, s); }
   // grad(v).grad(y) - v*u - v*h
   template <class T> PDENLP_HD static void res(const PointCtx& c, const T* s, T* R) {
@@ -53,6 +54,7 @@ struct PoissonBoltzmann : FieldIdx<DIM_, 0> {
   using I = FieldIdx<DIM_, 0>;
   static constexpr bool HAS_CONST = false;
   static constexpr bool NEEDS_COEF_DERIV = false;
+  static constexpr bool FE_DERIVS_POINT_INDEPENDENT = false;  // d res/d(y,grad y,u) and the FE-field Hessians are the same at every point of a cell
   template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) { return tracking_f<T, I>(c, s); }
   // grad(v).grad(y) + sinh(y)*v - u*v - v*h
   template <class T> PDENLP_HD static void res(const PointCtx& c, const T* s, T* R) {
@@ -66,6 +68,7 @@ struct BurgerLin : FieldIdx<1, 0> {
   using I = FieldIdx<1, 0>;
   static constexpr bool HAS_CONST = false;
   static constexpr bool NEEDS_COEF_DERIV = false;
+  static constexpr bool FE_DERIVS_POINT_INDEPENDENT = true;  // d res/d(y,grad y,u) and the FE-field Hessians are the same at every point of a cell
   template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) { return tracking_f<T, I>(c, s); }
   // -nu*grad(v).grad(y) + (grad(y).1)*v - v*u - v*h
   template <class T> PDENLP_HD static void res(const PointCtx& c, const T* s, T* R) {
@@ -78,6 +81,7 @@ struct BurgerNl : FieldIdx<1, 1> {
   using I = FieldIdx<1, 1>;
   static constexpr bool HAS_CONST = true;
   static constexpr bool NEEDS_COEF_DERIV = false;
+  static constexpr bool FE_DERIVS_POINT_INDEPENDENT = false;  // d res/d(y,grad y,u) and the FE-field Hessians are the same at every point of a cell
   template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) {
     T t = s[I::SK] - c.par[2];
     return tracking_f<T, I>(c, s) + 0.5 * t * t;
@@ -95,6 +99,7 @@ struct KappaPoisson : FieldIdx<DIM_, 2> {
   using I = FieldIdx<DIM_, 2>;
   static constexpr bool HAS_CONST = false;
   static constexpr bool NEEDS_COEF_DERIV = true;  // d res / d k2 = -v*f
+  static constexpr bool FE_DERIVS_POINT_INDEPENDENT = true;  // d res/d(y,grad y,u) and the FE-field Hessians are the same at every point of a cell
   template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) {
     T d = c.target - s[I::SY];
     T a = s[I::SK] - 1.0, b = s[I::SK + 1] - 1.0;
@@ -116,6 +121,7 @@ struct PenalizedPoisson : FieldIdx<DIM_, 0> {
   using I = FieldIdx<DIM_, 0>;
   static constexpr bool HAS_CONST = false;
   static constexpr bool NEEDS_COEF_DERIV = false;
+  static constexpr bool FE_DERIVS_POINT_INDEPENDENT = true;  // d res/d(y,grad y,u) and the FE-field Hessians are the same at every point of a cell
   // 0.5 * grad(y).grad(y) - w * y
   template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) {
     T a = s[I::SG] * s[I::SG];
@@ -134,6 +140,7 @@ struct BasicUnconstrained : FieldIdx<DIM_, 0> {
   using I = FieldIdx<DIM_, 0>;
   static constexpr bool HAS_CONST = false;
   static constexpr bool NEEDS_COEF_DERIV = false;
+  static constexpr bool FE_DERIVS_POINT_INDEPENDENT = true;  // d res/d(y,grad y,u) and the FE-field Hessians are the same at every point of a cell
   // 0.5 * (ubis - u) * (ubis - u) + 0.5 * y * y
   template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) {
     T d = c.target - s[I::SU];

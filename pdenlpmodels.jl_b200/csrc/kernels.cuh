@@ -53,6 +53,29 @@ struct Tables {
   double par[8];
 };
 
+// Pre-integrated reference tensors for elements with nq > 1 (uniform geometry):
+//   yy[k][l][j][i] = sum_q w_q By_i[k](q) By_j[l](q)   (Jacobian y-block with k = test slot; Hessian block (1,1))
+//   uy[l][j][i]    = sum_q w_q psi_i(q)  By_j[l](q)    (Hessian block (2,1): rows u_i, cols y_j)
+//   yu[t][b][i]    = sum_q w_q By_i[t](q) psi_b(q)     (Jacobian u-block: rows y_i, cols u_b)
+//   uu[j][i]       = sum_q w_q psi_i(q)  psi_j(q)      (Hessian block (2,2))
+// When the pointwise derivative data D of a cell is the same at all its quadrature points (bilinear /
+// constant-coefficient forms; detected at run time, warp-uniformly) the element blocks are
+// sum_{t,k} D[t][k] * K[t][k][.][.]: one pass, no per-quadrature-point read-modify-write in shared memory.
+template <class E>
+struct KTab {
+  static constexpr bool ENABLED = E::NQ > 1 && !E::HAS_CONST;
+  static constexpr int NB = E::NB, NY = E::NY, NU = E::NU;
+  static constexpr int OFF_YY = 0;
+  static constexpr int OFF_UY = NB * NB * NY * NY;
+  static constexpr int OFF_YU = OFF_UY + NB * NY * NU;
+  static constexpr int OFF_UU = OFF_YU + NB * NU * NY;
+  static constexpr int TOTAL = ENABLED ? ((OFF_UU + NU * NU + 1) & ~1) : 0;
+  __host__ __device__ static constexpr int yy(int k, int l, int j, int i) { return OFF_YY + ((k * NB + l) * NY + j) * NY + i; }
+  __host__ __device__ static constexpr int uy(int l, int j, int i) { return OFF_UY + (l * NY + j) * NU + i; }
+  __host__ __device__ static constexpr int yu(int t, int b, int i) { return OFF_YU + (t * NU + b) * NY + i; }
+  __host__ __device__ static constexpr int uu(int j, int i) { return OFF_UU + j * NU + i; }
+};
+
 struct DevModel {
   const int32_t* dofs_y;
   const int32_t* dofs_u;
@@ -62,6 +85,7 @@ struct DevModel {
   const int64_t* base_jy;  // [ntiles+1]
   const int64_t* base_ju;
   const int64_t* base_h;
+  const double* ktab;      // pre-integrated reference tensors (KTab layout), nq > 1 elements only
   int64_t ncells, ldc;
   int64_t nfree_y, nfree_u;
   int32_t ntiles;
@@ -341,6 +365,146 @@ struct SegStage {
   }
 };
 
+// ---- K-path emitters (see KTab).  D entries that are zero on every lane of the warp are skipped
+// through warp-uniform branches, so e.g. a Poisson-type form costs 3 of the 16 (t,k) terms.
+template <class E>
+__device__ __forceinline__ double* emit_jac_y_K(const double* __restrict__ Ks, const Jet1<E::M> (&R)[E::NR], const Cell<E>& c, double* p) {
+  using KT = KTab<E>;
+  unsigned nz = 0;
+#pragma unroll
+  for (int t = 0; t < E::NB; ++t)
+#pragma unroll
+    for (int k = 0; k < E::NB; ++k)
+      if (__any_sync(0xffffffffu, R[t].g[k] != 0.0)) nz |= 1u << (t * E::NB + k);
+#pragma unroll
+  for (int j = 0; j < E::NY; ++j) {
+    if (c.gy[j] > 0) {
+      double acc[E::NY];
+#pragma unroll
+      for (int i = 0; i < E::NY; ++i) acc[i] = 0.0;
+#pragma unroll
+      for (int t = 0; t < E::NB; ++t)
+#pragma unroll
+        for (int k = 0; k < E::NB; ++k)
+          if ((nz >> (t * E::NB + k)) & 1u) {
+            const double d = R[t].g[k];
+#pragma unroll
+            for (int i = 0; i < E::NY; ++i) acc[i] = fma(d, Ks[KT::yy(t, k, j, i)], acc[i]);
+          }
+#pragma unroll
+      for (int i = 0; i < E::NY; ++i)
+        if (c.gy[i] > 0) { *p = acc[i]; ++p; }
+    }
+  }
+  return p;
+}
+template <class E>
+__device__ __forceinline__ double* emit_jac_u_K(const double* __restrict__ Ks, const Jet1<E::M> (&R)[E::NR], const Cell<E>& c, double* p) {
+  using KT = KTab<E>;
+  unsigned nz = 0;
+#pragma unroll
+  for (int t = 0; t < E::NB; ++t)
+    if (__any_sync(0xffffffffu, R[t].g[E::SU] != 0.0)) nz |= 1u << t;
+#pragma unroll
+  for (int b = 0; b < E::NU; ++b) {
+    if (c.gu[b] > 0) {
+      double acc[E::NY];
+#pragma unroll
+      for (int i = 0; i < E::NY; ++i) acc[i] = 0.0;
+#pragma unroll
+      for (int t = 0; t < E::NB; ++t)
+        if ((nz >> t) & 1u) {
+          const double d = R[t].g[E::SU];
+#pragma unroll
+          for (int i = 0; i < E::NY; ++i) acc[i] = fma(d, Ks[KT::yu(t, b, i)], acc[i]);
+        }
+#pragma unroll
+      for (int i = 0; i < E::NY; ++i)
+        if (c.gy[i] > 0) { *p = acc[i]; ++p; }
+    }
+  }
+  return p;
+}
+template <class E>
+__device__ __forceinline__ double* emit_hess_yy_K(const double* __restrict__ Ks, const Jet2<E::M>& L, double sc, const Cell<E>& c, double* p) {
+  using KT = KTab<E>;
+  using J2 = Jet2<E::M>;
+  unsigned nz = 0;
+#pragma unroll
+  for (int k = 0; k < E::NB; ++k)
+#pragma unroll
+    for (int l = 0; l < E::NB; ++l)
+      if (__any_sync(0xffffffffu, L.h[J2::idx(k, l)] != 0.0)) nz |= 1u << (k * E::NB + l);
+#pragma unroll
+  for (int j = 0; j < E::NY; ++j) {
+    if (c.gy[j] > 0) {
+      double acc[E::NY];
+#pragma unroll
+      for (int i = 0; i < E::NY; ++i) acc[i] = 0.0;
+#pragma unroll
+      for (int k = 0; k < E::NB; ++k)
+#pragma unroll
+        for (int l = 0; l < E::NB; ++l)
+          if ((nz >> (k * E::NB + l)) & 1u) {
+            const double d = L.h[J2::idx(k, l)] * sc;
+#pragma unroll
+            for (int i = 0; i < E::NY; ++i) acc[i] = fma(d, Ks[KT::yy(k, l, j, i)], acc[i]);
+          }
+#pragma unroll
+      for (int i = 0; i < E::NY; ++i)
+        if (c.gy[j] <= c.gy[i]) { *p = acc[i]; ++p; }
+    }
+  }
+  return p;
+}
+template <class E>
+__device__ __forceinline__ double* emit_hess_u_K(const double* __restrict__ Ks, const Jet2<E::M>& L, double sc, const Cell<E>& c, double* p) {
+  using KT = KTab<E>;
+  using J2 = Jet2<E::M>;
+  if (E::NU > 0) {
+    unsigned nz = 0;
+#pragma unroll
+    for (int l = 0; l < E::NB; ++l)
+      if (__any_sync(0xffffffffu, L.h[J2::idx(E::SU, l)] != 0.0)) nz |= 1u << l;
+#pragma unroll
+    for (int j = 0; j < E::NY; ++j) {
+      if (c.gy[j] > 0) {
+        double acc[E::NUS];
+#pragma unroll
+        for (int i = 0; i < E::NUS; ++i) acc[i] = 0.0;
+#pragma unroll
+        for (int l = 0; l < E::NB; ++l)
+          if ((nz >> l) & 1u) {
+            const double d = L.h[J2::idx(E::SU, l)] * sc;
+#pragma unroll
+            for (int i = 0; i < E::NU; ++i) acc[i] = fma(d, Ks[KT::uy(l, j, i)], acc[i]);
+          }
+#pragma unroll
+        for (int i = 0; i < E::NU; ++i)
+          if (c.gu[i] > 0) { *p = acc[i]; ++p; }
+      }
+    }
+    const double duu = L.h[J2::idx(E::SU, E::SU)] * sc;
+#pragma unroll
+    for (int j = 0; j < E::NU; ++j) {
+      if (c.gu[j] > 0) {
+#pragma unroll
+        for (int i = 0; i < E::NU; ++i)
+          if (c.gu[j] <= c.gu[i]) { *p = duu * Ks[KT::uu(j, i)]; ++p; }
+      }
+    }
+  }
+  return p;
+}
+// the warp's CTA stages the tensors in shared memory once (after the staging buffers)
+template <class E>
+__device__ __forceinline__ const double* load_ktab(const DevModel& D, double* dst) {
+  if (!KTab<E>::ENABLED || D.ktab == nullptr) return nullptr;
+  for (int i = threadIdx.x; i < KTab<E>::TOTAL; i += blockDim.x) dst[i] = __ldg(D.ktab + i);
+  __syncthreads();
+  return dst;
+}
+
 template <class E>
 __host__ __device__ constexpr int jac_stage_doubles() {
   return StageLayout<E::RUN_JY>::WARP_DOUBLES > StageLayout<(E::NU > 0 ? E::RUN_JU : 1)>::WARP_DOUBLES
@@ -356,7 +520,7 @@ __host__ __device__ constexpr int hess_stage_doubles() { return StageLayout<E::R
 // their register budget is capped to let two CTAs share an SM; the host sizes the persistent grid
 // with the occupancy API.
 template <class E>
-constexpr int coord_min_blocks() { return E::RUN_H <= 48 ? 2 : 1; }
+constexpr int coord_min_blocks() { return (E::RUN_H <= 48 && E::NQ == 1) ? 2 : 1; }
 
 template <class E>
 __global__ void __launch_bounds__(kThreads, coord_min_blocks<E>())
@@ -368,6 +532,7 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
   constexpr int STAGE = jac_stage_doubles<E>();
   SegStage<E::RUN_JY> sty{smem + warp * STAGE, nullptr};
   SegStage<(E::NU > 0 ? E::RUN_JU : 1)> stu{smem + warp * STAGE, nullptr};
+  const double* const Ks = load_ktab<E>(D, smem + nwarps * STAGE);
 
   const int64_t stride = (int64_t)gridDim.x * nwarps;
   int64_t tile = (int64_t)blockIdx.x * nwarps + warp;
@@ -404,6 +569,32 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
 #pragma unroll
     for (int b = 0; b < E::NU; ++b) fu += c.gu[b] > 0;
 
+    // K-path test (nq > 1): is dR/d(y, grad y, u) the same at every quadrature point, on all lanes?
+    bool kpath = false;
+    Jet1<E::M> R0[E::NR];
+    if (KTab<E>::ENABLED && Ks != nullptr) {
+      bool uni = true;
+      // integrands that declare FE_DERIVS_POINT_INDEPENDENT are evaluated at the first point only
+      constexpr int NQT = I::FE_DERIVS_POINT_INDEPENDENT ? 1 : E::NQ;
+#pragma unroll 1
+      for (int q = 0; q < NQT; ++q) {
+        Jet1<E::M> s[E::M], R[E::NR];
+        point_state<E>(tab, c, x, q, s);
+        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        I::res(pc, s, R);
+        if (q == 0) {
+#pragma unroll
+          for (int t = 0; t < E::NR; ++t) R0[t] = R[t];
+        } else {
+#pragma unroll
+          for (int t = 0; t < E::NR; ++t)
+#pragma unroll
+            for (int k = 0; k <= E::SU; ++k) uni = uni && (R[t].g[k] == R0[t].g[k]);
+        }
+      }
+      kpath = __all_sync(0xffffffffu, uni || !valid);
+    }
+
     // ---- y-block:  A_e[i][j] = sum_q w sum_t T_i[t] sum_k dR_t/ds_k By_j[k]
     {
       const int cnt = fy * fy;
@@ -411,6 +602,8 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
       double* gdst = vals_y + D.base_jy[tile];
       sty.acquire(lane);
       double* const p0 = sty.begin(gdst, incl - cnt, lane);
+      if (kpath) emit_jac_y_K<E>(Ks, R0, c, p0);
+      else
 #pragma unroll 1
       for (int q = 0; q < E::NQ; ++q) {
         Jet1<E::M> s[E::M], R[E::NR];
@@ -448,6 +641,8 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
       double* gdst = vals_u + D.base_ju[tile];
       stu.acquire(lane);
       double* const p0 = stu.begin(gdst, incl - cnt, lane);
+      if (kpath) emit_jac_u_K<E>(Ks, R0, c, p0);
+      else
 #pragma unroll 1
       for (int q = 0; q < E::NQ; ++q) {
         Jet1<E::M> s[E::M], R[E::NR];
@@ -612,6 +807,7 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   constexpr int STAGE = hess_stage_doubles<E>();
   SegStage<E::RUN_H> st{smem + warp * STAGE, nullptr};
+  const double* const Ks = load_ktab<E>(D, smem + nwarps * STAGE);
 
   const int64_t stride = (int64_t)gridDim.x * nwarps;
   int64_t tile = (int64_t)blockIdx.x * nwarps + warp;
@@ -657,23 +853,41 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
     auto segment = [&](double* gdst, auto&& jet_at) {
       st.acquire(lane);
       double* const p0 = st.begin(gdst, incl - cnt, lane);
-      bool zyy = true, zu = true;
-      Jet2<E::M> L;
-      double scale = 0.0;
+      bool zyy = true, zu = true, quni = true;
+      Jet2<E::M> L, L0;
+      double sc = 0.0;  // quadrature-weight-free scale (obj_weight or 1)
+      constexpr int NQT = (KTab<E>::ENABLED && I::FE_DERIVS_POINT_INDEPENDENT) ? 1 : E::NQ;
 #pragma unroll 1
-      for (int q = 0; q < E::NQ; ++q) {
-        L = jet_at(q, scale);
-        zyy = zyy && (scale == 0.0 || fe_hess_block_is_zero<E, false>(L));
-        zu = zu && (scale == 0.0 || fe_hess_block_is_zero<E, true>(L));
+      for (int q = 0; q < NQT; ++q) {
+        L = jet_at(q, sc);
+        zyy = zyy && (sc == 0.0 || fe_hess_block_is_zero<E, false>(L));
+        zu = zu && (sc == 0.0 || fe_hess_block_is_zero<E, true>(L));
+        if (KTab<E>::ENABLED) {
+          if (q == 0) L0 = L;
+          else {
+#pragma unroll
+            for (int k = 0; k <= E::SU; ++k)
+#pragma unroll
+              for (int l = 0; l <= k; ++l) quni = quni && (L.h[Jet2<E::M>::idx(k, l)] == L0.h[Jet2<E::M>::idx(k, l)]);
+          }
+        }
       }
       zyy = __all_sync(0xffffffffu, zyy || !valid);
       zu = __all_sync(0xffffffffu, zu || !valid);
+      const bool kpath = KTab<E>::ENABLED && Ks != nullptr && __all_sync(0xffffffffu, quni || !valid);
       if (zyy && zu) {
         st.zero_fill(__shfl_sync(0xffffffffu, incl, 31), lane);
+      } else if (kpath) {  // q-independent second derivatives: pre-integrated tensors, one pass
+        double* p = p0;
+        if (!zyy) p = emit_hess_yy_K<E>(Ks, L0, sc, c, p);
+        else { for (int k = 0; k < n11; ++k) p[k] = 0.0; p += n11; }
+        if (!zu) emit_hess_u_K<E>(Ks, L0, sc, c, p);
+        else for (int k = 0; k < cnt - n11; ++k) p[k] = 0.0;
       } else {
 #pragma unroll 1
         for (int q = 0; q < E::NQ; ++q) {
-          if (E::NQ > 1) L = jet_at(q, scale);  // NQ == 1: the jet of the test pass is reused
+          if (E::NQ > 1) L = jet_at(q, sc);  // NQ == 1: the jet of the test pass is reused
+          const double scale = sc * tab.wdet[q];
           double* p = p0;
           if (!zyy) p = (q == 0) ? emit_hess_yy<E, false>(tab, q, L, scale, c, p) : emit_hess_yy<E, true>(tab, q, L, scale, c, p);
           else { if (q == 0) for (int k = 0; k < n11; ++k) p[k] = 0.0; p += n11; }
@@ -688,7 +902,7 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
         Jet2<E::M> s[E::M];
         point_state<E>(tab, c, x, q, s);
         const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
-        scale = obj_weight * tab.wdet[q];
+        scale = obj_weight;
         return I::f(pc, s);
       });
     }
@@ -699,7 +913,7 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
         const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
         double Lam[E::NR];
         lambda_slots<E>(tab, q, lam_e, Lam);
-        scale = tab.wdet[q];
+        scale = 1.0;
         return weighted_res<E>(pc, s, Lam);
       });
     }
@@ -755,25 +969,35 @@ k_structure(const DevModel D, int kind, int64_t* __restrict__ rows, int64_t* __r
 // (lane = cell; scatter with red.global.add.f64 — north star: "segmented atomics")
 enum VecOp { OP_OBJ = 0, OP_GRAD = 1, OP_CONS = 2, OP_JPROD = 3, OP_JTPROD = 4, OP_HPROD = 5 };
 
+// element vector d/dz_a += sum_k By_a[k] gs[k], d/du_b += Bu_b gs[SU]: accumulated over the quadrature points in
+// registers, scattered once per cell (one red.global.add.f64 per local dof, not per dof and point)
 template <class E>
-__device__ __forceinline__ void scatter_fields(const Tables<E>& tab, int q, const DevModel& D, const Cell<E>& c,
-                                               const double* gs /*[M], weighted*/, double* __restrict__ out) {
-  // out is an nvar-vector: d/dz_a = sum_k By_a[k] gs[k]; d/du_b = Bu_b gs[SU]; kappa handled by caller
-  double* oy = out + D.nparam;
-  double* ou = oy + D.nfree_y;
+__device__ __forceinline__ void accumulate_fields(const Tables<E>& tab, int q, const double* gs /*[M], weighted*/,
+                                                  double* ey, double* eu) {
 #pragma unroll
   for (int a = 0; a < E::NY; ++a) {
-    double v = 0.0;
+    double v = ey[a];
 #pragma unroll
     for (int k = 0; k < E::NB; ++k) v = fma(tab.By[q][a][k], gs[k], v);
-    if (c.gy[a] > 0) atomicAdd(oy + (c.gy[a] - 1), v);
+    ey[a] = v;
   }
   if (E::NU > 0) {
 #pragma unroll
-    for (int b = 0; b < E::NU; ++b) {
-      const double v = tab.Bu[q][b] * gs[E::SU];
-      if (c.gu[b] > 0) atomicAdd(ou + (c.gu[b] - 1), v);
-    }
+    for (int b = 0; b < E::NU; ++b) eu[b] = fma(tab.Bu[q][b], gs[E::SU], eu[b]);
+  }
+}
+template <class E>
+__device__ __forceinline__ void scatter_element(const DevModel& D, const Cell<E>& c, const double* ey, const double* eu,
+                                                double* __restrict__ out /* nvar-vector */) {
+  double* oy = out + D.nparam;
+  double* ou = oy + D.nfree_y;
+#pragma unroll
+  for (int a = 0; a < E::NY; ++a)
+    if (c.gy[a] > 0) atomicAdd(oy + (c.gy[a] - 1), ey[a]);
+  if (E::NU > 0) {
+#pragma unroll
+    for (int b = 0; b < E::NU; ++b)
+      if (c.gu[b] > 0) atomicAdd(ou + (c.gu[b] - 1), eu[b]);
   }
 }
 
@@ -834,6 +1058,11 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
     }
     gather_state<E>(D, x, valid, c);
     if (!valid) continue;
+    double ey[E::NY], eu[E::NUS];  // element vector, summed over the quadrature points
+#pragma unroll
+    for (int a = 0; a < E::NY; ++a) ey[a] = 0.0;
+#pragma unroll
+    for (int b = 0; b < E::NUS; ++b) eu[b] = 0.0;
 #pragma unroll 1
     for (int q = 0; q < E::NQ; ++q) {
       const double w = tab.wdet[q];
@@ -850,7 +1079,7 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
         double gs[E::M];
 #pragma unroll
         for (int k = 0; k < E::M; ++k) gs[k] = w * F.g[k];
-        scatter_fields<E>(tab, q, D, c, gs, out);
+        accumulate_fields<E>(tab, q, gs, ey, eu);
 #pragma unroll
         for (int k = 0; k < E::NP; ++k) ksum[k] += gs[E::SK + k];
       } else if (OP == OP_CONS) {
@@ -863,7 +1092,7 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
           double a = 0.0;
 #pragma unroll
           for (int t = 0; t < E::NR; ++t) a = fma(test_slot<E>(tab, q, i, t), R[t], a);
-          if (c.gy[i] > 0) atomicAdd(out + (c.gy[i] - 1), w * a);
+          ey[i] = fma(w, a, ey[i]);
         }
       } else if (OP == OP_JPROD) {
         Jet1<E::M> s[E::M], R[E::NR];
@@ -885,7 +1114,7 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
           double a = 0.0;
 #pragma unroll
           for (int t = 0; t < E::NR; ++t) a = fma(test_slot<E>(tab, q, i, t), dR[t], a);
-          if (c.gy[i] > 0) atomicAdd(out + (c.gy[i] - 1), a);
+          ey[i] += a;
         }
       } else if (OP == OP_JTPROD) {
         Jet1<E::M> s[E::M];
@@ -898,7 +1127,7 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
         double gs[E::M];
 #pragma unroll
         for (int k = 0; k < E::M; ++k) gs[k] = w * L.g[k];
-        scatter_fields<E>(tab, q, D, c, gs, out);
+        accumulate_fields<E>(tab, q, gs, ey, eu);
 #pragma unroll
         for (int k = 0; k < E::NP; ++k) ksum[k] += gs[E::SK + k];
       } else if (OP == OP_HPROD) {
@@ -933,10 +1162,16 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
             gs[k] = fma(w, a, gs[k]);
           }
         }
-        scatter_fields<E>(tab, q, D, c, gs, out);
+        accumulate_fields<E>(tab, q, gs, ey, eu);
 #pragma unroll
         for (int k = 0; k < E::NP; ++k) ksum[k] += gs[E::SK + k];
       }
+    }
+    if (OP == OP_GRAD || OP == OP_JTPROD || OP == OP_HPROD) scatter_element<E>(D, c, ey, eu, out);
+    if (OP == OP_CONS || OP == OP_JPROD) {  // rows = free dofs of the test space
+#pragma unroll
+      for (int i = 0; i < E::NY; ++i)
+        if (c.gy[i] > 0) atomicAdd(out + (c.gy[i] - 1), ey[i]);
     }
   }
   // block-level reductions: objective partial sums (deterministic two-pass) and kappa entries

@@ -49,21 +49,24 @@ struct Ops {
   virtual int hess_kappa(const Launch& L, const DevModel& D, const double* x, const double* lam, double ow, int which,
                          int64_t prows, double* vk) = 0;
   virtual int run_h() const = 0;
+  virtual const std::vector<double>& ktab() const = 0;  // pre-integrated reference tensors (may be empty)
 };
 
-constexpr int warps_for_stage(int stage_doubles) {
+constexpr int warps_for_stage(int stage_doubles, int reserved_doubles) {
   // per-warp staging buffer; at most 8 warps (launch bounds), at most ~225 KB per CTA
-  return std::min(8, (225 * 1024) / (stage_doubles * 8));
+  return std::min(8, (225 * 1024 - reserved_doubles * 8) / (stage_doubles * 8));
 }
 
 template <class E>
 struct OpsImpl : Ops {
   Tables<E> tab;
   bool attr_done = false;
-  static constexpr int WJ = warps_for_stage(jac_stage_doubles<E>());
-  static constexpr int WH = warps_for_stage(hess_stage_doubles<E>());
-  static constexpr size_t SMEM_J = (size_t)WJ * jac_stage_doubles<E>() * 8;
-  static constexpr size_t SMEM_H = (size_t)WH * hess_stage_doubles<E>() * 8;
+  std::vector<double> ktab_;
+  const std::vector<double>& ktab() const override { return ktab_; }
+  static constexpr int WJ = warps_for_stage(jac_stage_doubles<E>(), KTab<E>::TOTAL);
+  static constexpr int WH = warps_for_stage(hess_stage_doubles<E>(), KTab<E>::TOTAL);
+  static constexpr size_t SMEM_J = ((size_t)WJ * jac_stage_doubles<E>() + KTab<E>::TOTAL) * 8;
+  static constexpr size_t SMEM_H = ((size_t)WH * hess_stage_doubles<E>() + KTab<E>::TOTAL) * 8;
 
   int occ_j = 1, occ_h = 1;  // resident CTAs per SM of the persistent coord kernels
   int set_attrs() {
@@ -156,6 +159,26 @@ Ops* make_ops(const pdenlp_desc& d) {
     for (int b = 0; b < E::NUS; ++b) o->tab.Bu[q][b] = (E::NU > 0) ? d.phi_u[q * E::NU + b] : 0.0;
   }
   for (int i = 0; i < 8; ++i) o->tab.par[i] = d.params[i];
+  if (KTab<E>::ENABLED) {  // pre-integrated reference tensors (see KTab in kernels.cuh)
+    using KT = KTab<E>;
+    o->ktab_.assign(KT::TOTAL, 0.0);
+    const auto& T = o->tab;
+    for (int q = 0; q < E::NQ; ++q) {
+      const double w = T.wdet[q];
+      for (int j = 0; j < E::NY; ++j)
+        for (int i = 0; i < E::NY; ++i)
+          for (int k = 0; k < E::NB; ++k)
+            for (int l = 0; l < E::NB; ++l) o->ktab_[KT::yy(k, l, j, i)] += w * T.By[q][i][k] * T.By[q][j][l];
+      for (int j = 0; j < E::NY; ++j)
+        for (int i = 0; i < E::NU; ++i)
+          for (int l = 0; l < E::NB; ++l) {
+            o->ktab_[KT::uy(l, j, i)] += w * T.Bu[q][i] * T.By[q][j][l];
+            o->ktab_[KT::yu(l, i, j)] += w * T.By[q][j][l] * T.Bu[q][i];
+          }
+      for (int j = 0; j < E::NU; ++j)
+        for (int i = 0; i < E::NU; ++i) o->ktab_[KT::uu(j, i)] += w * T.Bu[q][i] * T.Bu[q][j];
+    }
+  }
   return o;
 }
 
@@ -361,6 +384,11 @@ int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
   m->dm.ntiles = (int32_t)(ldc / 32);
   m->dm.nparam = desc->nparam;
   m->dm.base_jy = m->dm.base_ju = m->dm.base_h = nullptr;
+  m->dm.ktab = nullptr;
+  if (!ops->ktab().empty()) {
+    if ((rc = dev_upload(m, ops->ktab().data(), ops->ktab().size(), &dp))) return bail(rc);
+    m->dm.ktab = dp;
+  }
 
   // per-tile entry counts -> exclusive scans (segment offsets)
   {
