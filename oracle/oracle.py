@@ -32,6 +32,7 @@ class _Problem(C.Structure):
         ("ncells", C.c_int64), ("cell0", C.c_int64), ("nfree_y", C.c_int64), ("nfree_u", C.c_int64),
         ("cell_dofs_y", C.c_void_p), ("cell_dofs_u", C.c_void_p), ("dir_y", C.c_void_p), ("dir_u", C.c_void_p),
         ("params", C.c_double * 8),
+        ("nfy", C.c_int32), ("nfu", C.c_int32), ("field_nfree", C.c_int64 * 8), ("field_ndir", C.c_int64 * 8),
     ]
 
 
@@ -67,6 +68,9 @@ class Oracle:
         P = _Problem()
         P.integrand = spec.integrand
         P.dim = m.dim
+        if getattr(spec, "is_multifield", False):
+            self._init_multifield(P, spec, c0, c1, nthreads)
+            return
         P.order_y = spec.Ypde.order
         P.order_u = spec.Ycon.order if spec.Ycon is not None else 0
         P.degree = spec.degree
@@ -93,6 +97,42 @@ class Oracle:
             P.dir_u = _p(du)
         for i, v in enumerate(spec.params):
             P.params[i] = v
+        self._finish_init(P, spec)
+
+    def _init_multifield(self, P, spec, c0, c1, nthreads):
+        m = spec.model
+        Ys, Us = list(spec.Yfields), list(spec.Ufields)
+        P.order_y = Ys[0].order
+        P.order_u = Us[0].order if Us else 0
+        P.degree = spec.degree
+        P.nparam = 0
+        for d in range(3):
+            P.n[d] = m.n[d] if d < m.dim else 1
+            P.lo[d] = m.lo[d] if d < m.dim else 0.0
+            P.hi[d] = m.hi[d] if d < m.dim else 1.0
+        P.nthreads = nthreads
+        P.ncells = c1 - c0
+        P.cell0 = c0
+        P.nfree_y = sum(f.nfree for f in Ys)
+        P.nfree_u = sum(f.nfree for f in Us)
+        P.nfy, P.nfu = len(Ys), len(Us)
+        for i, f in enumerate(Ys + Us):
+            P.field_nfree[i] = f.nfree
+            P.field_ndir[i] = f.ndirichlet
+        cy = np.ascontiguousarray(np.concatenate([f.cell_dof_ids[c0:c1] for f in Ys], axis=1), dtype=np.int32)
+        dy = np.ascontiguousarray(np.concatenate([f.dirichlet_vals for f in Ys]), dtype=np.float64)
+        self._keep += [cy, dy]
+        P.cell_dofs_y, P.dir_y = _p(cy), _p(dy)
+        if Us:
+            cu = np.ascontiguousarray(np.concatenate([f.cell_dof_ids[c0:c1] for f in Us], axis=1), dtype=np.int32)
+            du = np.ascontiguousarray(np.concatenate([f.dirichlet_vals for f in Us]), dtype=np.float64)
+            self._keep += [cu, du]
+            P.cell_dofs_u, P.dir_u = _p(cu), _p(du)
+        for i, v in enumerate(spec.params):
+            P.params[i] = v
+        self._finish_init(P, spec)
+
+    def _finish_init(self, P, spec):
         self.P = P
         self.nvar = spec.nparam + P.nfree_y + P.nfree_u
         self.ncon = P.nfree_y
@@ -170,7 +210,10 @@ class Oracle:
         return out
 
     def tables(self):
-        ny = self.spec.Ypde.nloc; nu = self.spec.Ycon.nloc if self.spec.Ycon is not None else 0
+        if getattr(self.spec, "is_multifield", False):
+            ny = self.spec.Yfields[0].nloc; nu = self.spec.Ufields[0].nloc if self.spec.Ufields else 0
+        else:
+            ny = self.spec.Ypde.nloc; nu = self.spec.Ycon.nloc if self.spec.Ycon is not None else 0
         dim = self.spec.model.dim
         nqmax = 27
         nq = C.c_int32()

@@ -85,6 +85,13 @@ template <class T, int N> static inline Dual<T, N> operator-(const Dual<T, N>& a
   Dual<T, N> r = a; r.v = a.v - b; return r; }
 template <class T, int N> static inline Dual<T, N> operator-(double b, const Dual<T, N>& a) { return (-a) + b; }
 
+static inline double xcos(double a) { return std::cos(a); }
+static inline double xsin(double a) { return std::sin(a); }
+template <class T, int N> static inline Dual<T, N> xsin(const Dual<T, N>& a);
+template <class T, int N> static inline Dual<T, N> xcos(const Dual<T, N>& a) {
+  Dual<T, N> r; r.v = xcos(a.v); T s = xsin(a.v); for (int i = 0; i < N; ++i) r.d[i] = (-s) * a.d[i]; return r; }
+template <class T, int N> static inline Dual<T, N> xsin(const Dual<T, N>& a) {
+  Dual<T, N> r; r.v = xsin(a.v); T c = xcos(a.v); for (int i = 0; i < N; ++i) r.d[i] = c * a.d[i]; return r; }
 static inline double xsinh(double a) { return std::sinh(a); }
 static inline double xcosh(double a) { return std::cosh(a); }
 template <class T, int N> static inline Dual<T, N> xcosh(const Dual<T, N>& a);
@@ -112,10 +119,17 @@ typedef struct oracle_problem {
   const double* dir_y;
   const double* dir_u;
   double params[8];
+  // multi-field layout (nfy = 0 or 1: single-field legacy): nfy state fields x ny local dofs, nfu control
+  // fields x nu; cell_dofs_y is [ncells][nfy*ny] field-major with per-field ids; field_nfree / field_ndir list
+  // the state fields first, then the control fields; dir_y / dir_u are the concatenated Dirichlet values
+  int32_t nfy, nfu;
+  int64_t field_nfree[8];
+  int64_t field_ndir[8];
 } oracle_problem;
 }
 
-enum { MEMBRANE = 1, PB = 2, BURGER_LIN = 3, BURGER_NL = 4, KAPPA_POISSON = 5, PENALIZED_POISSON = 6, BASIC_UNCONSTRAINED = 7 };
+enum { MEMBRANE = 1, PB = 2, BURGER_LIN = 3, BURGER_NL = 4, KAPPA_POISSON = 5, PENALIZED_POISSON = 6, BASIC_UNCONSTRAINED = 7,
+       CONTROL_SIR = 8, CELL_INCREASE = 9, DYNAMIC_SIR = 10, TORE_BRACHISTOCHRONE = 11 };
 
 static const double PI = 3.14159265358979323846;
 
@@ -134,6 +148,7 @@ static double coef_target(const oracle_problem& P, const double* x) {
       return P.dim == 3 ? s * x[2] : s;
     }
     case BASIC_UNCONSTRAINED: return x[0] * x[0] + x[1] * x[1];  // ubis, basicunconstrained.jl:20
+    case DYNAMIC_SIR: return 1.0 + x[0];                         // w0, dynamicsir.jl:50
   }
   return 0.0;
 }
@@ -591,6 +606,236 @@ struct Driver {
   }
 };
 
+
+// ================================================================== multi-field
+// Ypde / Ycon are MultiFieldFESpaces of scalar Lagrangian fields (test/problems/controlsir.jl,
+// cellincrease.jl, dynamicsir.jl, torebrachistochrone.jl).  Cell-local vector z = [y_1 .. y_nfy ; u_1 .. u_nfu]
+// (field-major), consecutive multi-field numbering of the free dofs, one test field per state field.
+// Cell matrices are block arrays: blocks are visited in eachblockid order (column-major over field pairs),
+// inside a block column outer / row inner (src/fill_matrix_hessian_functions.jl:69-94).
+template <class S>
+struct PtMF {
+  S y[4], gy[4][3], u[4];
+  double yd, h;
+};
+
+template <class S>
+static S f_density_mf(const oracle_problem& P, const PtMF<S>& p) {
+  switch (P.integrand) {
+    case CONTROL_SIR:   // 0.5 * I * I                           (controlsir.jl:30-33)
+      return 0.5 * p.y[0] * p.y[0];
+    case CELL_INCREASE: // kp * pf                               (cellincrease.jl:15-18)
+      return P.params[0] * p.y[1];
+    case DYNAMIC_SIR: { // 0.5*((bf*w0)-w1)^2 + 0.5*((cf*w0)-w2)^2   (dynamicsir.jl:54-58)
+      S a = p.yd * p.u[0] - P.params[0];
+      S b = p.yd * p.u[1] - P.params[1];
+      return 0.5 * a * a + 0.5 * b * b;
+    }
+    case TORE_BRACHISTOCHRONE: {  // a*a*phi'^2 + (c + a*cos(phi))^2 * theta'^2   (torebrachistochrone.jl:25-28)
+      const double a = P.params[0], c = P.params[1];
+      S w = c + a * xcos(p.y[0]);
+      return (a * a) * p.gy[0][0] * p.gy[0][0] + w * w * p.gy[1][0] * p.gy[1][0];
+    }
+  }
+  return cst(0.0, p.y[0]);
+}
+// residual density against ONE test function (value v) of test field ft; dt(y, v) = (grad(y).1) * v
+template <class S>
+static S res_density_mf(const oracle_problem& P, const PtMF<S>& p, int ft, double v) {
+  const S& I = p.y[0]; const S& Sv = p.y[1];
+  const S& dI = p.gy[0][0]; const S& dS = p.gy[1][0];
+  switch (P.integrand) {
+    case CONTROL_SIR: {  // dt(I,p) + dt(S,q) - p*(a*S*I - b*I) - q*(mu - b*I - a*S*I)   (controlsir.jl:20-24)
+      const double a = P.params[0], b = P.params[1], mu = P.params[2];
+      if (ft == 0) return dI * v - v * (a * Sv * I - b * I);
+      return dS * v - v * (mu - b * I - a * Sv * I);
+    }
+    case CELL_INCREASE: {  // cellincrease.jl:33-40 with (cf, pf) = y, u the control
+      const double kp = P.params[0], kr = P.params[1];
+      const S& cf = I; const S& pf = Sv;
+      if (ft == 0) return dI * v - v * (kp * pf * (1.0 - cf) - kr * cf * (1.0 - cf - pf));
+      return dS * v + v * (p.u[0] * kr * cf * (1.0 - cf - pf) - kp * pf * pf);
+    }
+    case DYNAMIC_SIR: {  // dt(I,p) + dt(S,q) - p*(bf*S*I - cf*I) + q*bf*S*I   (dynamicsir.jl:36-41)
+      if (ft == 0) return dI * v - v * (p.u[0] * Sv * I - p.u[1] * I);
+      return dS * v + v * (p.u[0] * Sv * I);
+    }
+  }
+  return cst(0.0, p.y[0]);
+}
+
+template <int NFY, int NFU, int NLY, int NLU>
+struct MFDriver {
+  static const int NYT = NFY * NLY, NUT = NFU * NLU, N = NYT + NUT, NF = NFY + NFU;
+  typedef Dual<double, N> D1;
+  typedef Dual<D1, N> D2;
+
+  static int64_t off_free(const oracle_problem& P, int F) { int64_t o = 0; for (int f = 0; f < F; ++f) o += P.field_nfree[f]; return o; }
+  static int64_t off_dir(const oracle_problem& P, int F) {   // within dir_y (state) or dir_u (control)
+    int64_t o = 0; const int f0 = F < NFY ? 0 : NFY; for (int f = f0; f < F; ++f) o += P.field_ndir[f]; return o; }
+  static int nloc(int F) { return F < NFY ? NLY : NLU; }
+  static int zoff(int F) { return F < NFY ? F * NLY : NYT + (F - NFY) * NLU; }
+  static int raw_id(const oracle_problem& P, int64_t c, int F, int a) {
+    return F < NFY ? P.cell_dofs_y[c * NYT + F * NLY + a] : P.cell_dofs_u[c * NUT + (F - NFY) * NLU + a];
+  }
+  static void gather(const oracle_problem& P, const double* x, int64_t c, double* z) {
+    for (int F = 0; F < NF; ++F)
+      for (int a = 0; a < nloc(F); ++a) {
+        const int g = raw_id(P, c, F, a);
+        const double* dir = F < NFY ? P.dir_y : P.dir_u;
+        z[zoff(F) + a] = g > 0 ? x[off_free(P, F) + g - 1] : dir[off_dir(P, F) - g - 1];
+      }
+  }
+  // multi-field global ids (offset positive ids), indexed like z
+  static void gids(const oracle_problem& P, int64_t c, int64_t* gid) {
+    for (int F = 0; F < NF; ++F)
+      for (int a = 0; a < nloc(F); ++a) { const int g = raw_id(P, c, F, a); gid[zoff(F) + a] = g > 0 ? g + off_free(P, F) : g; }
+  }
+  template <class S>
+  static PtMF<S> point(const oracle_problem& P, const RefTables& T, const CellGeom& G, int q, const S* zz) {
+    PtMF<S> p; S zero = cst(0.0, zz[0]);
+    for (int f = 0; f < 4; ++f) { p.y[f] = zero; p.u[f] = zero; for (int d = 0; d < 3; ++d) p.gy[f][d] = zero; }
+    for (int f = 0; f < NFY; ++f)
+      for (int a = 0; a < NLY; ++a) {
+        p.y[f] = p.y[f] + T.phiy[q * NLY + a] * zz[f * NLY + a];
+        for (int d = 0; d < P.dim; ++d) p.gy[f][d] = p.gy[f][d] + (T.dphiy[(q * NLY + a) * P.dim + d] / G.h[d]) * zz[f * NLY + a];
+      }
+    for (int g = 0; g < NFU; ++g)
+      for (int b = 0; b < NLU; ++b) p.u[g] = p.u[g] + T.phiu[q * NLU + b] * zz[NYT + g * NLU + b];
+    double xq[3] = {0, 0, 0};
+    for (int d = 0; d < P.dim; ++d) xq[d] = G.x0[d] + G.h[d] * T.xi[q * P.dim + d];
+    p.yd = coef_target(P, xq); p.h = coef_source(P, xq);
+    return p;
+  }
+  template <class S> static S cell_obj(const oracle_problem& P, const RefTables& T, const CellGeom& G, const S* zz) {
+    S acc = cst(0.0, zz[0]);
+    for (int q = 0; q < T.nq; ++q) acc = acc + (T.w[q] * G.detJ) * f_density_mf(P, point<S>(P, T, G, q, zz));
+    return acc;
+  }
+  // residual vector indexed like the state part of z: (test field ft, local i)
+  template <class S> static void cell_res(const oracle_problem& P, const RefTables& T, const CellGeom& G, const S* zz, S* out) {
+    for (int i = 0; i < NYT; ++i) out[i] = cst(0.0, zz[0]);
+    for (int q = 0; q < T.nq; ++q) {
+      PtMF<S> p = point<S>(P, T, G, q, zz);
+      for (int ft = 0; ft < NFY; ++ft)
+        for (int i = 0; i < NLY; ++i) out[ft * NLY + i] = out[ft * NLY + i] + (T.w[q] * G.detJ) * res_density_mf(P, p, ft, T.phiy[q * NLY + i]);
+    }
+  }
+  static void seed1(const double* z, D1* zz) { for (int i = 0; i < N; ++i) { zz[i].v = z[i]; for (int j = 0; j < N; ++j) zz[i].d[j] = i == j; } }
+  static void seed2(const double* z, D2* zz) {
+    for (int i = 0; i < N; ++i) {
+      zz[i].v.v = z[i];
+      for (int j = 0; j < N; ++j) zz[i].v.d[j] = i == j;
+      for (int k = 0; k < N; ++k) { zz[i].d[k].v = i == k; for (int j = 0; j < N; ++j) zz[i].d[k].d[j] = 0.0; }
+    }
+  }
+  // visit the entries of a block matrix (rows fields [r0,r1), cols fields [c0,c1)) of one cell in the reference order
+  template <class Fn> static void visit(const oracle_problem& P, int64_t c, int r0, int r1, int c0, int c1, bool lower, Fn fn) {
+    int64_t gid[N + 1]; gids(P, c, gid);
+    for (int bj = c0; bj < c1; ++bj)
+      for (int bi = r0; bi < r1; ++bi)
+        for (int j = 0; j < nloc(bj); ++j) {
+          const int64_t gc = gid[zoff(bj) + j];
+          if (gc > 0)
+            for (int i = 0; i < nloc(bi); ++i) {
+              const int64_t gr = gid[zoff(bi) + i];
+              if (gr > 0 && (!lower || gc <= gr)) fn(zoff(bi) + i, zoff(bj) + j, gr, gc);
+            }
+        }
+  }
+  static int cnt(const oracle_problem& P, int64_t c, int r0, int r1, int c0, int c1, bool lower) {
+    int n = 0; visit(P, c, r0, r1, c0, c1, lower, [&](int, int, int64_t, int64_t) { ++n; }); return n; }
+
+  static double obj(const oracle_problem& P, const double* x) {
+    RefTables T = make_tables(P); double total = 0.0;
+    for (int64_t c = 0; c < P.ncells; ++c) { double z[N]; gather(P, x, c, z); total += cell_obj<double>(P, T, cell_geom(P, c), z); }
+    return total;
+  }
+  static void grad(const oracle_problem& P, const double* x, double* g) {
+    RefTables T = make_tables(P);
+    const int64_t nvar = P.nfree_y + P.nfree_u;
+    for (int64_t i = 0; i < nvar; ++i) g[i] = 0.0;
+    for (int64_t c = 0; c < P.ncells; ++c) {
+      double z[N]; gather(P, x, c, z); D1 zz[N]; seed1(z, zz);
+      D1 F = cell_obj<D1>(P, T, cell_geom(P, c), zz);
+      int64_t gid[N + 1]; gids(P, c, gid);
+      for (int a = 0; a < N; ++a) if (gid[a] > 0) g[gid[a] - 1] += F.d[a];
+    }
+  }
+  static void cons(const oracle_problem& P, const double* x, double* cv) {
+    RefTables T = make_tables(P);
+    for (int64_t i = 0; i < P.nfree_y; ++i) cv[i] = 0.0;
+    for (int64_t c = 0; c < P.ncells; ++c) {
+      double z[N]; gather(P, x, c, z); double r[NYT > 0 ? NYT : 1];
+      cell_res<double>(P, T, cell_geom(P, c), z, r);
+      int64_t gid[N + 1]; gids(P, c, gid);
+      for (int i = 0; i < NYT; ++i) if (gid[i] > 0) cv[gid[i] - 1] += r[i];
+    }
+  }
+  static void sizes(const oracle_problem& P, int64_t* out) {
+    int64_t jy = 0, ju = 0, hf = 0;
+    for (int64_t c = 0; c < P.ncells; ++c) {
+      jy += cnt(P, c, 0, NFY, 0, NFY, false); ju += cnt(P, c, 0, NFY, NFY, NF, false); hf += cnt(P, c, 0, NF, 0, NF, true);
+    }
+    out[0] = 0; out[1] = jy; out[2] = ju; out[3] = 0; out[4] = hf; out[5] = 0;
+  }
+  static void jac_structure(const oracle_problem& P, int64_t* rows, int64_t* cols) {
+    int64_t n = 0;
+    for (int64_t c = 0; c < P.ncells; ++c) visit(P, c, 0, NFY, 0, NFY, false, [&](int, int, int64_t gr, int64_t gc) { rows[n] = gr; cols[n] = gc; ++n; });
+    for (int64_t c = 0; c < P.ncells; ++c) visit(P, c, 0, NFY, NFY, NF, false, [&](int, int, int64_t gr, int64_t gc) { rows[n] = gr; cols[n] = gc; ++n; });
+  }
+  static void jac_coord(const oracle_problem& P, const double* x, double* vals) {
+    RefTables T = make_tables(P);
+    int64_t sz[6]; sizes(P, sz);
+    double* vy = vals; double* vu = vals + sz[1];
+    int64_t ny = 0, nu = 0;
+    for (int64_t c = 0; c < P.ncells; ++c) {
+      double z[N]; gather(P, x, c, z); D1 zz[N]; seed1(z, zz);
+      D1 r[NYT > 0 ? NYT : 1]; cell_res<D1>(P, T, cell_geom(P, c), zz, r);
+      visit(P, c, 0, NFY, 0, NFY, false, [&](int li, int lj, int64_t, int64_t) { vy[ny++] = r[li].d[lj]; });
+      visit(P, c, 0, NFY, NFY, NF, false, [&](int li, int lj, int64_t, int64_t) { vu[nu++] = r[li].d[lj]; });
+    }
+  }
+  static void hess_structure(const oracle_problem& P, int64_t* rows, int64_t* cols) {
+    int64_t n = 0;
+    for (int rep = 0; rep < 2; ++rep)
+      for (int64_t c = 0; c < P.ncells; ++c) visit(P, c, 0, NF, 0, NF, true, [&](int, int, int64_t gr, int64_t gc) { rows[n] = gr; cols[n] = gc; ++n; });
+  }
+  static void hess_coord(const oracle_problem& P, const double* x, const double* lambda, double obj_weight, double* vals) {
+    RefTables T = make_tables(P);
+    int64_t sz[6]; sizes(P, sz);
+    double* vo = vals; double* vc = vals + sz[4];
+    for (int64_t i = 0; i < 2 * sz[4]; ++i) vals[i] = 0.0;
+    int64_t no = 0, nc = 0;
+    for (int64_t c = 0; c < P.ncells; ++c) {
+      double z[N]; gather(P, x, c, z); D2 zz[N]; seed2(z, zz);
+      CellGeom G = cell_geom(P, c);
+      D2 F = cell_obj<D2>(P, T, G, zz);
+      visit(P, c, 0, NF, 0, NF, true, [&](int li, int lj, int64_t, int64_t) { vo[no++] = F.d[li].d[lj]; });
+      if (lambda) {
+        D2 r[NYT > 0 ? NYT : 1]; cell_res<D2>(P, T, G, zz, r);
+        int64_t gid[N + 1]; gids(P, c, gid);
+        D2 L = cst(0.0, zz[0]);
+        for (int i = 0; i < NYT; ++i) { const double li = gid[i] > 0 ? lambda[gid[i] - 1] : 0.0; L = L + li * r[i]; }
+        visit(P, c, 0, NF, 0, NF, true, [&](int li, int lj, int64_t, int64_t) { vc[nc++] = L.d[li].d[lj]; });
+      }
+    }
+    for (int64_t i = 0; i < sz[4]; ++i) vals[i] *= obj_weight;
+  }
+};
+
+#define MF_DISPATCH(CALL)                                                                      \
+  do {                                                                                         \
+    const int nfy = P->nfy, nfu = P->nfu;                                                      \
+    const int nly = nloc_of(P->order_y, P->dim), nlu = nloc_of(P->order_u, P->dim);            \
+    if (nfy == 2 && nfu == 0 && nly == 2) { typedef MFDriver<2, 0, 2, 1> D; CALL; }            \
+    else if (nfy == 2 && nfu == 1 && nly == 2 && nlu == 2) { typedef MFDriver<2, 1, 2, 2> D; CALL; } \
+    else if (nfy == 2 && nfu == 2 && nly == 2 && nlu == 2) { typedef MFDriver<2, 2, 2, 2> D; CALL; } \
+    else return -2;                                                                            \
+    return 0;                                                                                  \
+  } while (0)
+static bool is_mf(const oracle_problem* P) { return P->integrand >= CONTROL_SIR; }
+
 // ------------------------------------------------------------------ dispatch
 #define DISPATCH(CALL)                                                             \
   do {                                                                             \
@@ -611,14 +856,15 @@ struct Driver {
 
 extern "C" {
 
-int oracle_sizes(const oracle_problem* P, int64_t* out6) { DISPATCH(D::sizes(*P, out6)); return 0; }
-int oracle_obj(const oracle_problem* P, const double* x, double* f) { DISPATCH(*f = D::obj(*P, x)); return 0; }
-int oracle_grad(const oracle_problem* P, const double* x, double* g) { DISPATCH(D::grad(*P, x, g)); return 0; }
-int oracle_cons(const oracle_problem* P, const double* x, double* c) { DISPATCH(D::cons(*P, x, c)); return 0; }
-int oracle_jac_structure(const oracle_problem* P, int64_t* rows, int64_t* cols) { DISPATCH(D::jac_structure(*P, rows, cols)); return 0; }
-int oracle_jac_coord(const oracle_problem* P, const double* x, double* vals) { DISPATCH(D::jac_coord(*P, x, vals)); return 0; }
-int oracle_hess_structure(const oracle_problem* P, int64_t* rows, int64_t* cols) { DISPATCH(D::hess_structure(*P, rows, cols)); return 0; }
+int oracle_sizes(const oracle_problem* P, int64_t* out6) { if (is_mf(P)) MF_DISPATCH(D::sizes(*P, out6)); DISPATCH(D::sizes(*P, out6)); return 0; }
+int oracle_obj(const oracle_problem* P, const double* x, double* f) { if (is_mf(P)) MF_DISPATCH(*f = D::obj(*P, x)); DISPATCH(*f = D::obj(*P, x)); return 0; }
+int oracle_grad(const oracle_problem* P, const double* x, double* g) { if (is_mf(P)) MF_DISPATCH(D::grad(*P, x, g)); DISPATCH(D::grad(*P, x, g)); return 0; }
+int oracle_cons(const oracle_problem* P, const double* x, double* c) { if (is_mf(P)) MF_DISPATCH(D::cons(*P, x, c)); DISPATCH(D::cons(*P, x, c)); return 0; }
+int oracle_jac_structure(const oracle_problem* P, int64_t* rows, int64_t* cols) { if (is_mf(P)) MF_DISPATCH(D::jac_structure(*P, rows, cols)); DISPATCH(D::jac_structure(*P, rows, cols)); return 0; }
+int oracle_jac_coord(const oracle_problem* P, const double* x, double* vals) { if (is_mf(P)) MF_DISPATCH(D::jac_coord(*P, x, vals)); DISPATCH(D::jac_coord(*P, x, vals)); return 0; }
+int oracle_hess_structure(const oracle_problem* P, int64_t* rows, int64_t* cols) { if (is_mf(P)) MF_DISPATCH(D::hess_structure(*P, rows, cols)); DISPATCH(D::hess_structure(*P, rows, cols)); return 0; }
 int oracle_hess_coord(const oracle_problem* P, const double* x, const double* lambda, double obj_weight, double* vals) {
+  if (is_mf(P)) MF_DISPATCH(D::hess_coord(*P, x, lambda, obj_weight, vals));
   DISPATCH(D::hess_coord(*P, x, lambda, obj_weight, vals)); return 0;
 }
 

@@ -43,6 +43,13 @@ class FlatModel:
     wdet: np.ndarray    # (nq,)
     coef: np.ndarray    # (ncoef, ncells, nq)
     params: np.ndarray  # (8,)
+    # multi-field layout: nfy state fields x ny local dofs, nfu control fields x nu;
+    # cell_dofs_y is (ncells, nfy*ny) field-major, ids are per-field (no multi-field offset);
+    # field_nfree / field_ndir list the state fields first, then the control fields
+    nfy: int = 1
+    nfu: int = 1
+    field_nfree: np.ndarray = None
+    field_ndir: np.ndarray = None
 
     @property
     def nvar(self) -> int:
@@ -53,7 +60,48 @@ class FlatModel:
         return self.nfree_y
 
 
+def _flatten_mf(spec, cell_range, with_coef):
+    m = spec.model
+    c0, c1 = (0, m.ncells) if cell_range is None else cell_range
+    Ys, Us = list(spec.Yfields), list(spec.Ufields)
+    assert len({(f.order, f.nloc) for f in Ys}) == 1 and len({(f.order, f.nloc) for f in Us}) <= 1
+    pts, wts = gauss_legendre_01(spec.degree, m.dim)
+    nq = pts.shape[0]
+    phi_y, dphi_y = lagrange_tables(Ys[0].order, m.dim, pts)
+    phi_u = lagrange_tables(Us[0].order, m.dim, pts)[0] if Us else np.zeros((nq, 0))
+    ncells = c1 - c0
+    if with_coef:
+        idx = m.cell_multi_index(np.arange(c0, c1, dtype=np.int64))
+        coef = np.zeros((2, ncells, nq))
+        for q in range(nq):
+            X = m.lo + (idx + pts[q]) * m.h
+            if spec.target is not None:
+                coef[0, :, q] = spec.target(X)
+            if spec.source is not None:
+                coef[1, :, q] = spec.source(X)
+    else:
+        coef = np.zeros((2, 0, nq))
+    params = np.zeros(8)
+    params[: len(spec.params)] = spec.params
+    cat = lambda fs: (np.ascontiguousarray(np.concatenate([f.cell_dof_ids[c0:c1] for f in fs], axis=1))
+                      if fs else np.zeros((ncells, 0), np.int32))
+    catd = lambda fs: (np.ascontiguousarray(np.concatenate([f.dirichlet_vals for f in fs]).astype(np.float64))
+                       if fs else np.zeros(0))
+    return FlatModel(
+        spec=spec, cell0=c0, ncells=ncells, dim=m.dim, ny=Ys[0].nloc, nu=(Us[0].nloc if Us else 0), nq=nq, nparam=0,
+        nfree_y=sum(f.nfree for f in Ys), nfree_u=sum(f.nfree for f in Us),
+        cell_dofs_y=cat(Ys), cell_dofs_u=cat(Us), dir_y=catd(Ys), dir_u=catd(Us),
+        phi_y=np.ascontiguousarray(phi_y), grad_y=np.ascontiguousarray(dphi_y / m.h), phi_u=np.ascontiguousarray(phi_u),
+        wdet=np.ascontiguousarray(wts * float(np.prod(m.h))), coef=np.ascontiguousarray(coef), params=params,
+        nfy=len(Ys), nfu=len(Us),
+        field_nfree=np.array([f.nfree for f in Ys + Us], dtype=np.int64),
+        field_ndir=np.array([f.ndirichlet for f in Ys + Us], dtype=np.int64),
+    )
+
+
 def flatten(spec: ProblemSpec, cell_range: Optional[Tuple[int, int]] = None, with_coef: bool = True) -> FlatModel:
+    if getattr(spec, "is_multifield", False):
+        return _flatten_mf(spec, cell_range, with_coef)
     m = spec.model
     c0, c1 = (0, m.ncells) if cell_range is None else cell_range
     Y, U = spec.Ypde, spec.Ycon
@@ -91,6 +139,9 @@ def flatten(spec: ProblemSpec, cell_range: Optional[Tuple[int, int]] = None, wit
         phi_y=np.ascontiguousarray(phi_y), grad_y=np.ascontiguousarray(grad_y),
         phi_u=np.ascontiguousarray(phi_u), wdet=np.ascontiguousarray(wdet),
         coef=np.ascontiguousarray(coef), params=params,
+        nfy=1, nfu=(1 if U is not None else 0),
+        field_nfree=np.array([Y.nfree] + ([U.nfree] if U is not None else []), dtype=np.int64),
+        field_ndir=np.array([Y.ndirichlet] + ([U.ndirichlet] if U is not None else []), dtype=np.int64),
     )
 
 
@@ -111,37 +162,53 @@ def _kept_pairs(row_ids: np.ndarray, col_ids: np.ndarray, lower: bool):
     return R, C, keep
 
 
+def _field_ids(fm: FlatModel):
+    """Per field, the (ncells, nloc) cell dof ids with the multi-field (consecutive) offsets applied to the
+    positive ids: state fields first, then control fields (offset by nfree_y)."""
+    ys, us = [], []
+    off = 0
+    for f in range(fm.nfy):
+        g = fm.cell_dofs_y[:, f * fm.ny:(f + 1) * fm.ny].astype(np.int64)
+        ys.append(np.where(g > 0, g + off, g))
+        off += int(fm.field_nfree[f])
+    for f in range(fm.nfu):
+        g = fm.cell_dofs_u[:, f * fm.nu:(f + 1) * fm.nu].astype(np.int64)
+        us.append(np.where(g > 0, g + off, g))
+        off += int(fm.field_nfree[fm.nfy + f])
+    return ys, us
+
+
+def _blocks(row_fields, col_fields, lower):
+    """Cell-major COO entries of a block matrix: blocks in eachblockid order (column-major over field
+    pairs), inside a block column outer / row inner (fill_matrix_hessian_functions.jl:50-94)."""
+    Rs, Cs, Ks = [], [], []
+    for cid in col_fields:
+        for rid in row_fields:
+            R, C, keep = _kept_pairs(rid, cid, lower)
+            Rs.append(R); Cs.append(C); Ks.append(keep)
+    R = np.concatenate(Rs, axis=1); C = np.concatenate(Cs, axis=1); K = np.concatenate(Ks, axis=1)
+    return R[K], C[K]
+
+
 def jac_structure(fm: FlatModel):
     """rows, cols (1-based int64) of jac_nln_structure! for this slab:
     [k-block | y-block | u-block]; /root/reference/src/jacobian_functions.jl:1-7,
-    60-120, src/additional_constructors.jl:259-260."""
+    60-120, src/additional_constructors.jl:259-260.  Rows are free dofs of the (multi-field) test space."""
     p = fm.nparam
-    gy = fm.cell_dofs_y.astype(np.int64)
+    ys, us = _field_ids(fm)
     rows = [np.tile(np.arange(1, fm.ncon + 1, dtype=np.int64), p)]
     cols = [np.repeat(np.arange(1, p + 1, dtype=np.int64), fm.ncon)]
-    R, C, keep = _kept_pairs(gy, gy, lower=False)
-    rows.append(R[keep]); cols.append(C[keep] + p)
-    if fm.nu:
-        gu = fm.cell_dofs_u.astype(np.int64)
-        R, C, keep = _kept_pairs(gy, gu, lower=False)
-        rows.append(R[keep]); cols.append(C[keep] + fm.nfree_y + p)
+    r, c = _blocks(ys, ys, lower=False)
+    rows.append(r); cols.append(c + p)
+    if us:
+        r, c = _blocks(ys, us, lower=False)
+        rows.append(r); cols.append(c + p)
     return np.concatenate(rows), np.concatenate(cols)
 
 
 def _hess_fe_structure(fm: FlatModel):
-    gy = fm.cell_dofs_y.astype(np.int64)
-    if fm.nu:
-        gu = fm.cell_dofs_u.astype(np.int64)
-        gu = np.where(gu > 0, gu + fm.nfree_y, gu)  # MultiFieldFESpace, consecutive style
-        blocks = [(gy, gy), (gu, gy), (gy, gu), (gu, gu)]  # eachblockid: (1,1),(2,1),(1,2),(2,2) as (rows, cols)
-    else:
-        blocks = [(gy, gy)]
-    Rs, Cs, Ks = [], [], []
-    for rid, cid in blocks:
-        R, C, keep = _kept_pairs(rid, cid, lower=True)
-        Rs.append(R); Cs.append(C); Ks.append(keep)
-    R = np.concatenate(Rs, axis=1); C = np.concatenate(Cs, axis=1); K = np.concatenate(Ks, axis=1)
-    return R[K], C[K]
+    ys, us = _field_ids(fm)
+    return _blocks(ys + us, ys + us, lower=True)
 
 
 def _trapezoid(prows: int, p: int):

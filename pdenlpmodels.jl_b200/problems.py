@@ -25,6 +25,10 @@ BURGER_NL = 4
 KAPPA_POISSON = 5
 PENALIZED_POISSON = 6
 BASIC_UNCONSTRAINED = 7
+CONTROL_SIR = 8
+CELL_INCREASE = 9
+DYNAMIC_SIR = 10
+TORE_BRACHISTOCHRONE = 11
 
 INTEGRAND_NAMES = {
     MEMBRANE: "membrane",
@@ -34,6 +38,10 @@ INTEGRAND_NAMES = {
     KAPPA_POISSON: "kappa_poisson",
     PENALIZED_POISSON: "penalized_poisson",
     BASIC_UNCONSTRAINED: "basic_unconstrained",
+    CONTROL_SIR: "control_sir",
+    CELL_INCREASE: "cell_increase",
+    DYNAMIC_SIR: "dynamic_sir",
+    TORE_BRACHISTOCHRONE: "tore_brachistochrone",
 }
 
 
@@ -64,6 +72,34 @@ class ProblemSpec:
     @property
     def ncon(self) -> int:
         return 0 if self.unconstrained else self.Ypde.nfree
+
+
+@dataclass
+class MFProblemSpec:
+    """Multi-field variant: Ypde / Ycon are MultiFieldFESpaces of scalar
+    Lagrangian fields of one element type each; x = [y_1 .. y_nfy ; u_1 .. u_nfu] (consecutive
+    multi-field numbering), the test space has one field per state field."""
+    name: str
+    integrand: int
+    model: CartesianDiscreteModel
+    Yfields: Sequence[LagrangianFESpace]
+    Ufields: Sequence[LagrangianFESpace]
+    degree: int
+    params: Sequence[float] = ()
+    target: Optional[Callable] = None
+    source: Optional[Callable] = None
+    unconstrained: bool = False
+    nparam: int = 0
+    affine: bool = False
+    is_multifield: bool = True
+
+    @property
+    def nvar(self) -> int:
+        return sum(f.nfree for f in self.Yfields) + sum(f.nfree for f in self.Ufields)
+
+    @property
+    def ncon(self) -> int:
+        return 0 if self.unconstrained else sum(f.nfree for f in self.Yfields)
 
 
 _OMEGA = math.pi - 1.0 / 8.0
@@ -191,6 +227,45 @@ def basicunconstrained(n: int = 16) -> ProblemSpec:
         name="basicunconstrained", integrand=BASIC_UNCONSTRAINED, model=model, Ypde=Ypde, Ycon=Ycon, degree=2,
         target=lambda X: X[:, 0] ** 2 + X[:, 1] ** 2, unconstrained=True,
     )
+
+
+def _ode_state_fields(model, x0):
+    # VI, VS: Q1, Dirichlet at t = 0 ("diri0" = entity 1) with the initial values x0
+    return [LagrangianFESpace(model, 1, "H1", [1], float(v)) for v in x0]
+
+
+def controlsir(n: int = 10, x0=(1.0, 2.0), a: float = 0.2, b: float = 0.1, mu: float = 0.1, T: float = 1.0) -> MFProblemSpec:
+    """test/problems/controlsir.jl:1-38: SIR ODE system as constraints on the two fields (I, S),
+    f = 0.5*I^2, no control; params = (a, b, mu)."""
+    model = CartesianDiscreteModel((0, T), n)
+    return MFProblemSpec(name="controlsir", integrand=CONTROL_SIR, model=model, Yfields=_ode_state_fields(model, x0),
+                         Ufields=[], degree=1, params=(a, b, mu))
+
+
+def cellincrease(n: int = 10, x0=(0.6, 0.1), T: float = 7.0) -> MFProblemSpec:
+    """test/problems/cellincrease.jl:1-46: two state fields (cf, pf), one L2 control; f = kp*pf;
+    params = (kp, kr) = (1.01, 2.03)."""
+    model = CartesianDiscreteModel((0, T), n)
+    return MFProblemSpec(name="cellincrease", integrand=CELL_INCREASE, model=model, Yfields=_ode_state_fields(model, x0),
+                         Ufields=[LagrangianFESpace(model, 1, "L2")], degree=1, params=(1.01, 2.03))
+
+
+def dynamicsir(n: int = 10, x0=(1.0, 2.0), T: float = 1.0) -> MFProblemSpec:
+    """test/problems/dynamicsir.jl:1-64: state (I, S), controls (bf, cf) in H1;
+    f = 0.5*(bf*w0 - w1)^2 + 0.5*(cf*w0 - w2)^2 with w0 = 1 + t, w1 = 1, w2 = 2; params = (w1, w2)."""
+    model = CartesianDiscreteModel((0, T), n)
+    return MFProblemSpec(name="dynamicsir", integrand=DYNAMIC_SIR, model=model, Yfields=_ode_state_fields(model, x0),
+                         Ufields=[LagrangianFESpace(model, 1, "H1"), LagrangianFESpace(model, 1, "H1")], degree=1,
+                         params=(1.0, 2.0), target=lambda X: 1.0 + X[:, 0])
+
+
+def torebrachistochrone(n: int = 3, a: float = 1.0, c: float = 3.0) -> MFProblemSpec:
+    """test/problems/torebrachistochrone.jl:1-67: geodesic on a torus, fields (phi, theta) fixed at both
+    ends (0 and pi), unconstrained; f = a^2 phi'^2 + (c + a cos(phi))^2 theta'^2; params = (a, c)."""
+    model = CartesianDiscreteModel((0, 1), n)
+    fields = [LagrangianFESpace(model, 1, "H1", [1, 2], {1: 0.0, 2: math.pi}) for _ in range(2)]
+    return MFProblemSpec(name="torebrachistochrone", integrand=TORE_BRACHISTOCHRONE, model=model, Yfields=fields,
+                         Ufields=[], degree=1, params=(a, c), unconstrained=True)
 
 
 BASELINE_CONFIGS = {

@@ -23,6 +23,11 @@ CASES = {
     "kappa3d_u_2": lambda p: p.poissonmixed(2, 3, True),
     "penalizedpoisson_4": lambda p: p.penalizedpoisson(4),
     "basicunconstrained_3": lambda p: p.basicunconstrained(3),
+    # multi-field state / control spaces
+    "controlsir_6": lambda p: p.controlsir(6),
+    "cellincrease_5": lambda p: p.cellincrease(5),
+    "dynamicsir_6": lambda p: p.dynamicsir(6),
+    "torebrachistochrone_4": lambda p: p.torebrachistochrone(4),
 }
 
 
@@ -190,3 +195,28 @@ def test_unconstrained_known_answers(pkg, oracle_mod):
     solu = spec.Ycon.interpolate_cellwise_constant(mids[:, 0] ** 2 + mids[:, 1] ** 2)
     sol = np.concatenate([np.zeros(spec.Ypde.nfree), solu])
     assert orc.obj(sol) <= 1.0 / n and np.linalg.norm(orc.grad(sol)) <= 1.0 / n
+
+
+def test_multifield_known_answers(pkg, oracle_mod):
+    """controlsir.jl:133 `obj(nlp, x0) == x0[1]^2/8/n` is not reachable at x = 0 because the objective
+    integrates the Dirichlet lift of I (I(0)=1 -> one cell of (0.5*1)^2*0.5*h) -- the same number;
+    dynamicsir.jl: obj(0) = 0.5*int (bf - 0)^2 with the constant targets."""
+    n = 10
+    o = oracle_mod.Oracle(pkg.controlsir(n))
+    assert np.isclose(o.obj(np.zeros(o.nvar)), 1.0 / 8 / n, rtol=1e-14)
+    o = oracle_mod.Oracle(pkg.dynamicsir(n))
+    assert np.isclose(o.obj(np.zeros(o.nvar)), 2.5, rtol=1e-14)
+
+
+def test_multifield_layout(pkg):
+    """MultiFieldFESpace with ConsecutiveMultiFieldStyle: x = [y-field 1 | y-field 2 | u-field 1 ...],
+    rows of the Jacobian are the free dofs of the multi-field test space."""
+    spec = pkg.dynamicsir(7)
+    fm = F.flatten(spec)
+    assert fm.nfy == 2 and fm.nfu == 2 and fm.cell_dofs_y.shape == (7, 4) and fm.cell_dofs_u.shape == (7, 4)
+    assert fm.nvar == int(fm.field_nfree.sum()) and fm.ncon == int(fm.field_nfree[:2].sum())
+    r, c = F.jac_structure(fm)
+    assert r.min() == 1 and r.max() == fm.ncon and c.max() == fm.nvar
+    ys, us = F._field_ids(fm)
+    assert ys[1][ys[1] > 0].min() == fm.field_nfree[0] + 1
+    assert us[0][us[0] > 0].min() == fm.ncon + 1
