@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define PDENLP_ABI_VERSION 1
+#define PDENLP_ABI_VERSION 2
 
 /* status codes */
 #define PDENLP_OK 0
@@ -75,7 +75,23 @@ enum pdenlp_integrand {
   PDENLP_PENALIZED_POISSON = 6,
   /* unconstrained, two fields: f = 0.5*(ubis-u)^2 + 0.5*y^2, ubis = coef target
      test/problems/basicunconstrained.jl:21-25 */
-  PDENLP_BASIC_UNCONSTRAINED = 7
+  PDENLP_BASIC_UNCONSTRAINED = 7,
+  /* ---- multi-field state / control spaces (MultiFieldFESpace); 1-D, dt(y,v) = (grad(y).1)*v ----
+     state (I,S), no control: f = 0.5*I*I ;
+     res = dt(I,p) + dt(S,q) - p*(a*S*I - b*I) - q*(mu - b*I - a*S*I)
+     test/problems/controlsir.jl:20-33.  params = (a, b, mu) */
+  PDENLP_CONTROL_SIR = 8,
+  /* state (cf,pf), control u: f = kp*pf ;
+     res = dt(cf,p) + dt(pf,q) - p*(kp*pf*(1-cf) - kr*cf*(1-cf-pf)) + q*(u*kr*cf*(1-cf-pf) - kp*pf*pf)
+     test/problems/cellincrease.jl:15-40.  params = (kp, kr) */
+  PDENLP_CELL_INCREASE = 9,
+  /* state (I,S), controls (bf,cf): f = 0.5*(bf*w0 - w1)^2 + 0.5*(cf*w0 - w2)^2, w0 = coef target ;
+     res = dt(I,p) + dt(S,q) - p*(bf*S*I - cf*I) + q*bf*S*I
+     test/problems/dynamicsir.jl:36-58.  params = (w1, w2) */
+  PDENLP_DYNAMIC_SIR = 10,
+  /* unconstrained, state (phi,theta): f = a^2*phi'^2 + (c + a*cos(phi))^2 * theta'^2
+     test/problems/torebrachistochrone.jl:25-28.  params = (a, c) */
+  PDENLP_TORE_BRACHISTOCHRONE = 11
 };
 
 /* coefficient fields sampled at quadrature points, coef[k][cell][q] */
@@ -97,13 +113,13 @@ typedef struct pdenlp_desc {
   int32_t abi_version;   /* PDENLP_ABI_VERSION */
   int32_t integrand;     /* enum pdenlp_integrand */
   int32_t dim;           /* 1, 2, 3 */
-  int32_t ny;            /* local dofs of the state space Ypde (= test space Xpde) */
-  int32_t nu;            /* local dofs of the control space Ycon, 0 if VoidFESpace */
+  int32_t ny;            /* local dofs of ONE field of the state space Ypde (= test space Xpde) */
+  int32_t nu;            /* local dofs of ONE field of the control space Ycon, 0 if VoidFESpace */
   int32_t nq;            /* quadrature points per cell */
   int32_t nparam;        /* number of algebraic unknowns kappa */
   int32_t memspace;      /* PDENLP_MEM_DEVICE | PDENLP_MEM_HOST */
   int32_t device;        /* CUDA device ordinal, -1 = current device */
-  int32_t reserved0;
+  int32_t nfields_y;     /* fields of a MultiFieldFESpace Ypde; 0 or 1 = single field */
 
   int64_t ncells;        /* cells owned by this handle (a contiguous slab) */
   int64_t nfree_y;       /* num_free_dofs(Ypde) = ncon */
@@ -111,8 +127,8 @@ typedef struct pdenlp_desc {
   int64_t ndir_y;        /* Dirichlet dofs of Ypde */
   int64_t ndir_u;        /* Dirichlet dofs of Ycon */
 
-  const int32_t* cell_dofs_y; /* [ncells][ny], get_cell_dof_ids(Ypde) */
-  const int32_t* cell_dofs_u; /* [ncells][nu], get_cell_dof_ids(Ycon) (no multi-field offset) */
+  const int32_t* cell_dofs_y; /* [ncells][nfields_y*ny], get_cell_dof_ids(Ypde) */
+  const int32_t* cell_dofs_u; /* [ncells][nfields_u*nu], get_cell_dof_ids(Ycon) (no multi-field offset) */
   const double* dir_y;        /* [ndir_y] Dirichlet values of the TRIAL space Ypde */
   const double* dir_u;        /* [ndir_u] */
 
@@ -124,9 +140,19 @@ typedef struct pdenlp_desc {
   const double* wdet;    /* [nq] quadrature weight * det(J) */
 
   int32_t ncoef;         /* number of coefficient fields (<= 2) */
-  int32_t reserved1;
+  int32_t nfields_u;     /* fields of a MultiFieldFESpace Ycon; 0 or 1 = single field */
   const double* coef;    /* [ncoef][ncells][nq] */
   double params[PDENLP_MAX_PARAMS];
+
+  /* multi-field spaces only (nfields_y > 1 or nfields_u > 1), else may be NULL:
+     [nfields_y + nfields_u] free / Dirichlet dof counts per field, state fields first.  All fields
+     of a space share the reference element (ny / nu local dofs); cell_dofs_y is then
+     [ncells][nfields_y*ny] field-major with each field's OWN ids (get_cell_dof_ids of the single
+     field spaces), dir_y the per-field Dirichlet values concatenated, nfree_y / ndir_y the sums;
+     likewise for the control space.  x = [kappa | y fields | u fields]
+     (ConsecutiveMultiFieldStyle, src/additional_constructors.jl:236-242). */
+  const int64_t* field_nfree;
+  const int64_t* field_ndir;
 } pdenlp_desc;
 
 typedef struct pdenlp_model pdenlp_model; /* opaque */

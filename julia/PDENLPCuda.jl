@@ -18,12 +18,13 @@ const LIB = get(ENV, "PDENLP_CUDA_LIB", "libpdenlp_cuda.so")
 
 struct Desc   # mirrors struct pdenlp_desc field by field
   abi_version::Int32; integrand::Int32; dim::Int32; ny::Int32; nu::Int32; nq::Int32; nparam::Int32
-  memspace::Int32; device::Int32; reserved0::Int32
+  memspace::Int32; device::Int32; nfields_y::Int32
   ncells::Int64; nfree_y::Int64; nfree_u::Int64; ndir_y::Int64; ndir_u::Int64
   cell_dofs_y::Ptr{Int32}; cell_dofs_u::Ptr{Int32}; dir_y::Ptr{Float64}; dir_u::Ptr{Float64}
   phi_y::Ptr{Float64}; grad_y::Ptr{Float64}; phi_u::Ptr{Float64}; wdet::Ptr{Float64}
-  ncoef::Int32; reserved1::Int32; coef::Ptr{Float64}
+  ncoef::Int32; nfields_u::Int32; coef::Ptr{Float64}
   params::NTuple{8, Float64}
+  field_nfree::Ptr{Int64}; field_ndir::Ptr{Int64}   # multi-field spaces only, else C_NULL
 end
 
 struct Info
@@ -75,10 +76,11 @@ function attach_cuda!(nlp::GridapPDENLPModel, integrand::Integrand; params = Flo
   for c in 1:nc, q in 1:nq; coef[q, c, 1] = target(xq[c][q]); coef[q, c, 2] = source(xq[c][q]); end
   par = ntuple(i -> i <= length(params) ? Float64(params[i]) : 0.0, 8)
   GC.@preserve celly cellu diry diru phi_y grad_y phi_u wdet coef begin
-    d = Desc(1, Int32(integrand), D, ny, nu, nq, nlp.pdemeta.nparam, memspace, device, 0,
+    d = Desc(2, Int32(integrand), D, ny, nu, nq, nlp.pdemeta.nparam, memspace, device, 1,
              nc, num_free_dofs(Ypde), has_u ? num_free_dofs(Ycon) : 0, length(diry), length(diru),
              pointer(celly), pointer(cellu), pointer(diry), pointer(diru),
-             pointer(phi_y), pointer(grad_y), pointer(phi_u), pointer(wdet), 2, 0, pointer(coef), par)
+             pointer(phi_y), pointer(grad_y), pointer(phi_u), pointer(wdet), 2, has_u ? 1 : 0, pointer(coef), par,
+             Ptr{Int64}(C_NULL), Ptr{Int64}(C_NULL))  # single-field spaces; see include/pdenlp_cuda.h for MultiFieldFESpace
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:pdenlp_create, LIB), Cint, (Ref{Desc}, Ref{Ptr{Cvoid}}), d, h))
   end

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # PDENLP_CUDA_LIB selects an alternative build of the same library (A/B kernel experiments)
 LIB_PATH = os.environ.get("PDENLP_CUDA_LIB") or os.path.join(HERE, "csrc", "libpdenlp_cuda.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = 0, -1, -2, -3, -4
 MEM_DEVICE, MEM_HOST = 0, 1
 
@@ -38,12 +38,13 @@ class Desc(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32), ("integrand", C.c_int32), ("dim", C.c_int32), ("ny", C.c_int32),
         ("nu", C.c_int32), ("nq", C.c_int32), ("nparam", C.c_int32), ("memspace", C.c_int32),
-        ("device", C.c_int32), ("reserved0", C.c_int32),
+        ("device", C.c_int32), ("nfields_y", C.c_int32),
         ("ncells", C.c_int64), ("nfree_y", C.c_int64), ("nfree_u", C.c_int64), ("ndir_y", C.c_int64), ("ndir_u", C.c_int64),
         ("cell_dofs_y", C.c_void_p), ("cell_dofs_u", C.c_void_p), ("dir_y", C.c_void_p), ("dir_u", C.c_void_p),
         ("phi_y", C.c_void_p), ("grad_y", C.c_void_p), ("phi_u", C.c_void_p), ("wdet", C.c_void_p),
-        ("ncoef", C.c_int32), ("reserved1", C.c_int32), ("coef", C.c_void_p),
+        ("ncoef", C.c_int32), ("nfields_u", C.c_int32), ("coef", C.c_void_p),
         ("params", C.c_double * 8),
+        ("field_nfree", C.c_void_p), ("field_ndir", C.c_void_p),
     ]
 
 
@@ -142,6 +143,9 @@ class Handle:
             d.ncoef, d.coef = 0, None
         for i in range(8):
             d.params[i] = fm.params[i]
+        d.nfields_y, d.nfields_u = fm.nfy, fm.nfu
+        keep += [np.ascontiguousarray(fm.field_nfree, np.int64), np.ascontiguousarray(fm.field_ndir, np.int64)]
+        d.field_nfree, d.field_ndir = _np_ptr(keep[-2]), _np_ptr(keep[-1])
         h = C.c_void_p()
         check(lib.pdenlp_create(C.byref(d), C.byref(h)))
         del keep

@@ -3,6 +3,7 @@
 // Each integrand is written ONCE, generically over the scalar type T (double,
 // Jet1, Jet2), as a function of the pointwise fields
 //     s[SY] = y, s[SG+d] = d_d y, s[SU] = u, s[SK+k] = kappa_k
+// (several state / control fields: see MFIdx at the end of the file)
 // f(...)  : objective density
 // res(...) : weak residual density, linear in the test function (v, grad v):
 //            res = R[0]*v + sum_d R[1+d]*d_d v  (+ R[1+DIM]*1 when HAS_CONST:
@@ -23,6 +24,7 @@ struct PointCtx {
 template <int DIM_, int NP_>
 struct FieldIdx {
   static constexpr int DIM = DIM_, NP = NP_;
+  static constexpr int NFY = 1, NFU = 1;  // one state field, (at most) one control field
   static constexpr int SY = 0, SG = 1, SU = 1 + DIM_, SK = 2 + DIM_;
   static constexpr int M = 2 + DIM_ + NP_;
 };
@@ -150,6 +152,90 @@ struct BasicUnconstrained : FieldIdx<DIM_, 0> {
 #pragma unroll
     for (int t = 0; t < 1 + DIM_; ++t) R[t] = jet_const(0.0, s[0]);
   }
+};
+
+// ---- multi-field state / control spaces (MultiFieldFESpace).
+// Pointwise fields: state field f occupies slots f*NB .. f*NB+DIM (value, gradient), NB = 1 + DIM;
+// control field g occupies slot SU + g.  Residual slots are laid out the same way over the TEST
+// fields: R[f*NB] multiplies v_f, R[f*NB+1+d] multiplies d_d v_f.
+template <int DIM_, int NFY_, int NFU_>
+struct MFIdx {
+  static constexpr int DIM = DIM_, NP = 0, NFY = NFY_, NFU = NFU_;
+  static constexpr int NB = 1 + DIM_;
+  static constexpr int SY = 0, SG = 1, SU = NFY_ * NB, SK = SU + (NFU_ > 0 ? NFU_ : 1);
+  static constexpr int M = SK;
+  static constexpr bool HAS_CONST = false;
+  static constexpr bool FE_DERIVS_POINT_INDEPENDENT = false;
+  PDENLP_HD static constexpr int Y(int f) { return f * NB; }
+  PDENLP_HD static constexpr int G(int f, int d = 0) { return f * NB + 1 + d; }
+  PDENLP_HD static constexpr int U(int g) { return SU + g; }
+  template <class T> PDENLP_HD static void zero_res(const T* s, T* R) {
+#pragma unroll
+    for (int t = 0; t < NFY_ * NB; ++t) R[t] = jet_const(0.0, s[0]);
+  }
+};
+
+// test/problems/controlsir.jl:20-33: fields (I, S); par = (a, b, mu)
+struct ControlSir : MFIdx<1, 2, 0> {
+  static constexpr bool NEEDS_COEF_DERIV = false;
+  using X = MFIdx<1, 2, 0>;
+  template <class T> PDENLP_HD static T f(const PointCtx&, const T* s) { return 0.5 * s[X::Y(0)] * s[X::Y(0)]; }
+  // dt(I,p) + dt(S,q) - p*(a*S*I - b*I) - q*(mu - b*I - a*S*I)
+  template <class T> PDENLP_HD static void res(const PointCtx& c, const T* s, T* R) {
+    const double a = c.par[0], b = c.par[1], mu = c.par[2];
+    const T& I = s[X::Y(0)]; const T& S = s[X::Y(1)];
+    X::zero_res(s, R);
+    const T aSI = a * S * I;
+    R[X::Y(0)] = s[X::G(0)] - (aSI - b * I);
+    R[X::Y(1)] = s[X::G(1)] - (mu - b * I - aSI);
+  }
+};
+
+// test/problems/cellincrease.jl:15-40: fields (cf, pf), control u in L2; par = (kp, kr)
+struct CellIncrease : MFIdx<1, 2, 1> {
+  static constexpr bool NEEDS_COEF_DERIV = false;
+  using X = MFIdx<1, 2, 1>;
+  template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) { return c.par[0] * s[X::Y(1)]; }
+  // dt(cf,p) + dt(pf,q) - p*(kp*pf*(1-cf) - kr*cf*(1-cf-pf)) + q*(u*kr*cf*(1-cf-pf) - kp*pf*pf)
+  template <class T> PDENLP_HD static void res(const PointCtx& c, const T* s, T* R) {
+    const double kp = c.par[0], kr = c.par[1];
+    const T& cf = s[X::Y(0)]; const T& pf = s[X::Y(1)]; const T& u = s[X::U(0)];
+    X::zero_res(s, R);
+    const T g = kr * cf * (1.0 - cf - pf);
+    R[X::Y(0)] = s[X::G(0)] - (kp * pf * (1.0 - cf) - g);
+    R[X::Y(1)] = s[X::G(1)] + (u * g - kp * pf * pf);
+  }
+};
+
+// test/problems/dynamicsir.jl:36-58: fields (I, S), controls (bf, cf) in H1; target = w0(t), par = (w1, w2)
+struct DynamicSir : MFIdx<1, 2, 2> {
+  static constexpr bool NEEDS_COEF_DERIV = true;  // d f / d(bf, cf) reads w0 = coef target
+  using X = MFIdx<1, 2, 2>;
+  template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) {
+    T a = c.target * s[X::U(0)] - c.par[0];
+    T b = c.target * s[X::U(1)] - c.par[1];
+    return 0.5 * a * a + 0.5 * b * b;
+  }
+  // dt(I,p) + dt(S,q) - p*(bf*S*I - cf*I) + q*bf*S*I
+  template <class T> PDENLP_HD static void res(const PointCtx&, const T* s, T* R) {
+    const T& I = s[X::Y(0)]; const T& S = s[X::Y(1)];
+    X::zero_res(s, R);
+    const T bSI = s[X::U(0)] * S * I;
+    R[X::Y(0)] = s[X::G(0)] - (bSI - s[X::U(1)] * I);
+    R[X::Y(1)] = s[X::G(1)] + bSI;
+  }
+};
+
+// test/problems/torebrachistochrone.jl:25-28: fields (phi, theta), unconstrained; par = (a, c)
+struct ToreBrachistochrone : MFIdx<1, 2, 0> {
+  static constexpr bool NEEDS_COEF_DERIV = false;
+  using X = MFIdx<1, 2, 0>;
+  template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) {
+    const double a = c.par[0];
+    T w = c.par[1] + a * jcos(s[X::Y(0)]);
+    return (a * a) * s[X::G(0)] * s[X::G(0)] + w * w * s[X::G(1)] * s[X::G(1)];
+  }
+  template <class T> PDENLP_HD static void res(const PointCtx&, const T* s, T* R) { X::zero_res(s, R); }
 };
 
 }  // namespace pdenlp

@@ -82,6 +82,12 @@ template <int M> PDENLP_HD Jet1<M> jsinh(const Jet1<M>& a) {
   for (int k = 0; k < M; ++k) r.g[k] = c * a.g[k];
   return r;
 }
+template <int M> PDENLP_HD Jet1<M> jcos(const Jet1<M>& a) {
+  Jet1<M> r; r.v = cos(a.v); const double ms = -sin(a.v);
+#pragma unroll
+  for (int k = 0; k < M; ++k) r.g[k] = ms * a.g[k];
+  return r;
+}
 
 // ---------------------------------------------------------------- Jet2
 template <int M>
@@ -169,10 +175,22 @@ template <int M> PDENLP_HD Jet2<M> jsinh(const Jet2<M>& a) {
       r.h[k * (k + 1) / 2 + l] = c * a.h[k * (k + 1) / 2 + l] + s * (a.g[k] * a.g[l]);
   return r;
 }
+template <int M> PDENLP_HD Jet2<M> jcos(const Jet2<M>& a) {
+  Jet2<M> r; const double c = cos(a.v), ms = -sin(a.v); r.v = c;
+#pragma unroll
+  for (int k = 0; k < M; ++k) r.g[k] = ms * a.g[k];
+#pragma unroll
+  for (int k = 0; k < M; ++k)
+#pragma unroll
+    for (int l = 0; l <= k; ++l)
+      r.h[k * (k + 1) / 2 + l] = ms * a.h[k * (k + 1) / 2 + l] - c * (a.g[k] * a.g[l]);
+  return r;
+}
 
 // plain doubles take part in the same generic integrand code
 PDENLP_HD double jet_const(double a, const double&) { return a; }
 PDENLP_HD double jsinh(double a) { return sinh(a); }
+PDENLP_HD double jcos(double a) { return cos(a); }
 PDENLP_HD void jet_seed(double& r, double val, int) { r = val; }
 
 }  // namespace pdenlp

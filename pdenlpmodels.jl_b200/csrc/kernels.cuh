@@ -30,16 +30,23 @@ constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
 
 // ------------------------------------------------------------------ element description
-template <class Integrand_, int NY_, int NU_, int NQ_>
+// NLY_/NLU_ are the local dofs of ONE state / control field; a multi-field space (NFY state fields,
+// NFU control fields, all fields of a kind sharing one reference element) is handled as one element
+// with NY = NFY*NLY state dofs, field-major, whose dof ids were renumbered at create time to the
+// concatenated (ConsecutiveMultiFieldStyle) ids of the whole state / control space.
+template <class Integrand_, int NLY_, int NLU_, int NQ_>
 struct Elem {
   using Integrand = Integrand_;
   static constexpr int DIM = Integrand::DIM, NP = Integrand::NP, M = Integrand::M;
   static constexpr int SY = Integrand::SY, SG = Integrand::SG, SU = Integrand::SU, SK = Integrand::SK;
-  static constexpr int NY = NY_, NU = NU_, NQ = NQ_;
-  static constexpr int NUS = NU_ > 0 ? NU_ : 1;
+  static constexpr int NFY = Integrand::NFY, NFU = NLU_ > 0 ? Integrand::NFU : 0;
+  static constexpr int NLY = NLY_, NLU = NLU_, NLUS = NLU_ > 0 ? NLU_ : 1;
+  static constexpr bool MULTI = NFY > 1 || NFU > 1;
+  static constexpr int NY = NFY * NLY_, NU = NFU * NLU_, NQ = NQ_;
+  static constexpr int NUS = NU > 0 ? NU : 1;
   static constexpr int NB = 1 + DIM;                                  // (phi, grad phi)
   static constexpr bool HAS_CONST = Integrand::HAS_CONST;
-  static constexpr int NR = 1 + DIM + (HAS_CONST ? 1 : 0);            // residual slots
+  static constexpr int NR = NFY * NB + (HAS_CONST ? 1 : 0);           // residual slots
   static constexpr int RUN_JY = NY * NY, RUN_JU = NY * NU;
   static constexpr int RUN_H = NY * (NY + 1) / 2 + NU * NY + NU * (NU + 1) / 2;  // distinct ids per cell
   static constexpr int RUN_J = RUN_JY > RUN_JU ? RUN_JY : RUN_JU;
@@ -48,8 +55,8 @@ struct Elem {
 template <class E>
 struct Tables {
   double wdet[E::NQ];
-  double By[E::NQ][E::NY][E::NB];
-  double Bu[E::NQ][E::NUS];
+  double By[E::NQ][E::NLY][E::NB];
+  double Bu[E::NQ][E::NLUS];
   double par[8];
 };
 
@@ -63,7 +70,7 @@ struct Tables {
 // sum_{t,k} D[t][k] * K[t][k][.][.]: one pass, no per-quadrature-point read-modify-write in shared memory.
 template <class E>
 struct KTab {
-  static constexpr bool ENABLED = E::NQ > 1 && !E::HAS_CONST;
+  static constexpr bool ENABLED = E::NQ > 1 && !E::HAS_CONST && !E::MULTI;
   static constexpr int NB = E::NB, NY = E::NY, NU = E::NU;
   static constexpr int OFF_YY = 0;
   static constexpr int OFF_UY = NB * NB * NY * NY;
@@ -162,13 +169,15 @@ __device__ __forceinline__ void point_state(const Tables<E>& tab, const Cell<E>&
 #pragma unroll
   for (int k = 0; k < E::M; ++k) val[k] = 0.0;
 #pragma unroll
-  for (int a = 0; a < E::NY; ++a)
+  for (int f = 0; f < E::NFY; ++f)
 #pragma unroll
-    for (int k = 0; k < E::NB; ++k) val[k] = fma(tab.By[q][a][k], c.zy[a], val[k]);
-  if (E::NU > 0) {
+    for (int a = 0; a < E::NLY; ++a)
 #pragma unroll
-    for (int b = 0; b < E::NU; ++b) val[E::SU] = fma(tab.Bu[q][b], c.zu[b], val[E::SU]);
-  }
+      for (int k = 0; k < E::NB; ++k) val[f * E::NB + k] = fma(tab.By[q][a][k], c.zy[f * E::NLY + a], val[f * E::NB + k]);
+#pragma unroll
+  for (int f = 0; f < E::NFU; ++f)
+#pragma unroll
+    for (int b = 0; b < E::NLU; ++b) val[E::SU + f] = fma(tab.Bu[q][b], c.zu[f * E::NLU + b], val[E::SU + f]);
 #pragma unroll
   for (int k = 0; k < E::NP; ++k) val[E::SK + k] = __ldg(x + k);
 #pragma unroll
@@ -188,10 +197,21 @@ __device__ __forceinline__ PointCtx point_ctx(const DevModel& D, const Tables<E>
   return pc;
 }
 
-// test-function slot t of local test function i: (phi_i, grad phi_i, [1])
+// test-function slot t of local test function i: (phi_i, grad phi_i, [1])  (single-field elements)
 template <class E>
 __device__ __forceinline__ double test_slot(const Tables<E>& tab, int q, int i, int t) {
+  static_assert(!E::MULTI, "single-field helper");
   return t < E::NB ? tab.By[q][i][t] : 1.0;
+}
+// sum_t T_i[t] * vec[t] for local test function i of test field f; vec is laid out like the residual
+// slots: [f*NB + (value, gradient)] per test field, then the constant slot
+template <class E>
+__device__ __forceinline__ double test_contract(const Tables<E>& tab, int q, int f, int i, const double* vec) {
+  double a = 0.0;
+#pragma unroll
+  for (int t = 0; t < E::NB; ++t) a = fma(tab.By[q][i][t], vec[f * E::NB + t], a);
+  if (E::HAS_CONST) a += vec[E::NFY * E::NB];
+  return a;
 }
 
 // ------------------------------------------------------------------ entry counts (reference filters)
@@ -788,11 +808,19 @@ __device__ __forceinline__ T weighted_res(const PointCtx& pc, const T* s, const 
 template <class E>
 __device__ __forceinline__ void lambda_slots(const Tables<E>& tab, int q, const double* lam_e, double* Lam) {
 #pragma unroll
-  for (int t = 0; t < E::NR; ++t) {
+  for (int f = 0; f < E::NFY; ++f)
+#pragma unroll
+    for (int t = 0; t < E::NB; ++t) {
+      double a = 0.0;
+#pragma unroll
+      for (int i = 0; i < E::NLY; ++i) a = fma(tab.By[q][i][t], lam_e[f * E::NLY + i], a);
+      Lam[f * E::NB + t] = a;
+    }
+  if (E::HAS_CONST) {
     double a = 0.0;
 #pragma unroll
-    for (int i = 0; i < E::NY; ++i) a = fma(test_slot<E>(tab, q, i, t), lam_e[i], a);
-    Lam[t] = a;
+    for (int i = 0; i < E::NY; ++i) a += lam_e[i];
+    Lam[E::NFY * E::NB] = a;
   }
 }
 
@@ -929,6 +957,255 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
 }
 
 
+// ------------------------------------------------------------------ multi-field coordinate kernels
+// Several state / control fields (MultiFieldFESpace): the same lane = cell, warp = tile streaming
+// writer, with the entries of a cell emitted block by block (column field outer, row field inner —
+// fill_matrix_hessian_functions.jl:50-94), and inside a block column dof outer / row dof inner.  The
+// per-tile segment offsets are those of the single-field kernels (counts do not depend on the order).
+// These are the ODE-type problems of the reference (1-D, one quadrature point); they take the plain
+// per-tile loop without the register pipeline and reference-tensor paths of the kernels above.
+template <class E, bool ACC>
+__device__ __forceinline__ double* emit_jac_y_mf(const Tables<E>& tab, int q, const Jet1<E::M> (&R)[E::NR], const Cell<E>& c, double* p) {
+  const double w = tab.wdet[q];
+#pragma unroll
+  for (int cf = 0; cf < E::NFY; ++cf)
+#pragma unroll
+    for (int rf = 0; rf < E::NFY; ++rf)
+#pragma unroll
+      for (int j = 0; j < E::NLY; ++j) {
+        double Mj[E::NB];
+#pragma unroll
+        for (int t = 0; t < E::NB; ++t) {
+          double a = 0.0;
+#pragma unroll
+          for (int k = 0; k < E::NB; ++k) a = fma(R[rf * E::NB + t].g[cf * E::NB + k], tab.By[q][j][k], a);
+          Mj[t] = a * w;
+        }
+        if (c.gy[cf * E::NLY + j] > 0) {
+#pragma unroll
+          for (int i = 0; i < E::NLY; ++i) {
+            double v = 0.0;
+#pragma unroll
+            for (int t = 0; t < E::NB; ++t) v = fma(tab.By[q][i][t], Mj[t], v);
+            if (c.gy[rf * E::NLY + i] > 0) { if (ACC) *p += v; else *p = v; ++p; }
+          }
+        }
+      }
+  return p;
+}
+template <class E, bool ACC>
+__device__ __forceinline__ double* emit_jac_u_mf(const Tables<E>& tab, int q, const Jet1<E::M> (&R)[E::NR], const Cell<E>& c, double* p) {
+  const double w = tab.wdet[q];
+#pragma unroll
+  for (int cf = 0; cf < E::NFU; ++cf)
+#pragma unroll
+    for (int rf = 0; rf < E::NFY; ++rf)
+#pragma unroll
+      for (int b = 0; b < E::NLU; ++b) {
+        double Mb[E::NB];
+#pragma unroll
+        for (int t = 0; t < E::NB; ++t) Mb[t] = R[rf * E::NB + t].g[E::SU + cf] * tab.Bu[q][b] * w;
+        if (c.gu[cf * E::NLU + b] > 0) {
+#pragma unroll
+          for (int i = 0; i < E::NLY; ++i) {
+            double v = 0.0;
+#pragma unroll
+            for (int t = 0; t < E::NB; ++t) v = fma(tab.By[q][i][t], Mb[t], v);
+            if (c.gy[rf * E::NLY + i] > 0) { if (ACC) *p += v; else *p = v; ++p; }
+          }
+        }
+      }
+  return p;
+}
+
+template <class E>
+__global__ void __launch_bounds__(kThreads)
+k_jac_coord_mf(const __grid_constant__ Tables<E> tab, const DevModel D, const double* __restrict__ x,
+               double* __restrict__ vals_y, double* __restrict__ vals_u) {
+  using I = typename E::Integrand;
+  static_assert(!E::HAS_CONST, "multi-field integrands have no constant residual slot");
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  constexpr int STAGE = jac_stage_doubles<E>();
+  SegStage<E::RUN_JY> sty{smem + warp * STAGE, nullptr};
+  SegStage<(E::NU > 0 ? E::RUN_JU : 1)> stu{smem + warp * STAGE, nullptr};
+  const int64_t stride = (int64_t)gridDim.x * nwarps;
+  for (int64_t tile = (int64_t)blockIdx.x * nwarps + warp; tile < D.ntiles; tile += stride) {
+    const int64_t cell = tile * 32 + lane;
+    const bool valid = cell < D.ncells;
+    Cell<E> c;
+    load_ids<E>(D, valid ? cell : 0, valid, c);
+    gather_state<E>(D, x, valid, c);
+    int fy = 0, fu = 0;
+#pragma unroll
+    for (int a = 0; a < E::NY; ++a) fy += c.gy[a] > 0;
+#pragma unroll
+    for (int b = 0; b < E::NU; ++b) fu += c.gu[b] > 0;
+    {
+      const int cnt = fy * fy;
+      const int incl = warp_incl_scan(cnt, lane);
+      double* gdst = vals_y + D.base_jy[tile];
+      sty.acquire(lane);
+      double* const p0 = sty.begin(gdst, incl - cnt, lane);
+#pragma unroll 1
+      for (int q = 0; q < E::NQ; ++q) {
+        Jet1<E::M> s[E::M], R[E::NR];
+        point_state<E>(tab, c, x, q, s);
+        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        I::res(pc, s, R);
+        if (q == 0) emit_jac_y_mf<E, false>(tab, q, R, c, p0); else emit_jac_y_mf<E, true>(tab, q, R, c, p0);
+      }
+      sty.release(gdst, incl - cnt, incl, lane);
+    }
+    if (E::NU > 0) {
+      const int cnt = fy * fu;
+      const int incl = warp_incl_scan(cnt, lane);
+      double* gdst = vals_u + D.base_ju[tile];
+      stu.acquire(lane);
+      double* const p0 = stu.begin(gdst, incl - cnt, lane);
+#pragma unroll 1
+      for (int q = 0; q < E::NQ; ++q) {
+        Jet1<E::M> s[E::M], R[E::NR];
+        point_state<E>(tab, c, x, q, s);
+        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        I::res(pc, s, R);
+        if (q == 0) emit_jac_u_mf<E, false>(tab, q, R, c, p0); else emit_jac_u_mf<E, true>(tab, q, R, c, p0);
+      }
+      stu.release(gdst, incl - cnt, incl, lane);
+    }
+  }
+  sty.drain(lane);
+}
+
+// One FE Hessian block set of a cell over the fields F = (state fields, control fields): blocks with
+// row field < column field hold no lower-triangle entry (multi-field ids grow with the field), the
+// diagonal blocks keep gidcol <= gidrow, the blocks below keep every free pair.
+template <class E, bool ACC>
+__device__ __forceinline__ double* emit_hess_mf(const Tables<E>& tab, int q, const Jet2<E::M>& L, double scale,
+                                                const Cell<E>& c, double* p) {
+  using J2 = Jet2<E::M>;
+  constexpr int NF = E::NFY + E::NFU;
+#pragma unroll
+  for (int cf = 0; cf < NF; ++cf)
+#pragma unroll
+    for (int rf = cf; rf < NF; ++rf) {
+      if (cf < E::NFY) {
+#pragma unroll
+        for (int j = 0; j < E::NLY; ++j) {
+          const int gc = c.gy[cf * E::NLY + j];
+          if (rf < E::NFY) {  // state rows, state columns
+            double Nj[E::NB];
+#pragma unroll
+            for (int k = 0; k < E::NB; ++k) {
+              double a = 0.0;
+#pragma unroll
+              for (int l = 0; l < E::NB; ++l) a = fma(L.h[J2::idx(rf * E::NB + k, cf * E::NB + l)], tab.By[q][j][l], a);
+              Nj[k] = a * scale;
+            }
+            if (gc > 0) {
+#pragma unroll
+              for (int i = 0; i < E::NLY; ++i) {
+                double v = 0.0;
+#pragma unroll
+                for (int k = 0; k < E::NB; ++k) v = fma(tab.By[q][i][k], Nj[k], v);
+                const int gr = c.gy[rf * E::NLY + i];
+                if (rf == cf ? gc <= gr : gr > 0) { if (ACC) *p += v; else *p = v; ++p; }
+              }
+            }
+          } else {            // control rows, state columns
+            const int ru = rf - E::NFY;
+            double a = 0.0;
+#pragma unroll
+            for (int l = 0; l < E::NB; ++l) a = fma(L.h[J2::idx(E::SU + ru, cf * E::NB + l)], tab.By[q][j][l], a);
+            a *= scale;
+            if (gc > 0) {
+#pragma unroll
+              for (int i = 0; i < E::NLU; ++i) {
+                const double v = tab.Bu[q][i] * a;
+                if (c.gu[ru * E::NLU + i] > 0) { if (ACC) *p += v; else *p = v; ++p; }
+              }
+            }
+          }
+        }
+      } else {                // control rows, control columns
+        const int cu = cf - E::NFY, ru = rf - E::NFY;
+        const double duu = L.h[J2::idx(E::SU + ru, E::SU + cu)] * scale;
+#pragma unroll
+        for (int j = 0; j < E::NLU; ++j) {
+          const double a = duu * tab.Bu[q][j];
+          const int gc = c.gu[cu * E::NLU + j];
+          if (gc > 0) {
+#pragma unroll
+            for (int i = 0; i < E::NLU; ++i) {
+              const double v = tab.Bu[q][i] * a;
+              const int gr = c.gu[ru * E::NLU + i];
+              if (ru == cu ? gc <= gr : gr > 0) { if (ACC) *p += v; else *p = v; ++p; }
+            }
+          }
+        }
+      }
+    }
+  return p;
+}
+
+template <class E>
+__global__ void __launch_bounds__(kThreads)
+k_hess_coord_mf(const __grid_constant__ Tables<E> tab, const DevModel D, const double* __restrict__ x,
+                const double* __restrict__ lambda, double obj_weight,
+                double* __restrict__ vals_obj, double* __restrict__ vals_con) {
+  using I = typename E::Integrand;
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  constexpr int STAGE = hess_stage_doubles<E>();
+  SegStage<E::RUN_H> st{smem + warp * STAGE, nullptr};
+  const int64_t stride = (int64_t)gridDim.x * nwarps;
+  for (int64_t tile = (int64_t)blockIdx.x * nwarps + warp; tile < D.ntiles; tile += stride) {
+    const int64_t cell = tile * 32 + lane;
+    const bool valid = cell < D.ncells;
+    Cell<E> c;
+    load_ids<E>(D, valid ? cell : 0, valid, c);
+    gather_state<E>(D, x, valid, c);
+    int fy, fu, cnt;
+    closed_counts<E>(c, fy, fu, cnt);
+    const int incl = warp_incl_scan(cnt, lane);
+    const int64_t tb = D.base_h[tile];
+    if (vals_obj != nullptr) {
+      double* gdst = vals_obj + tb;
+      st.acquire(lane);
+      double* const p0 = st.begin(gdst, incl - cnt, lane);
+#pragma unroll 1
+      for (int q = 0; q < E::NQ; ++q) {
+        Jet2<E::M> s[E::M];
+        point_state<E>(tab, c, x, q, s);
+        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        const Jet2<E::M> L = I::f(pc, s);
+        const double scale = obj_weight * tab.wdet[q];
+        if (q == 0) emit_hess_mf<E, false>(tab, q, L, scale, c, p0); else emit_hess_mf<E, true>(tab, q, L, scale, c, p0);
+      }
+      st.release(gdst, incl - cnt, incl, lane);
+    }
+    if (vals_con != nullptr) {
+      double lam_e[E::NY];
+      gather_free<E::NY>(lambda, c.gy, lam_e);
+      double* gdst = vals_con + tb;
+      st.acquire(lane);
+      double* const p0 = st.begin(gdst, incl - cnt, lane);
+#pragma unroll 1
+      for (int q = 0; q < E::NQ; ++q) {
+        Jet2<E::M> s[E::M];
+        point_state<E>(tab, c, x, q, s);
+        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        double Lam[E::NR];
+        lambda_slots<E>(tab, q, lam_e, Lam);
+        const Jet2<E::M> L = weighted_res<E>(pc, s, Lam);
+        if (q == 0) emit_hess_mf<E, false>(tab, q, L, tab.wdet[q], c, p0); else emit_hess_mf<E, true>(tab, q, L, tab.wdet[q], c, p0);
+      }
+      st.release(gdst, incl - cnt, incl, lane);
+    }
+  }
+  st.drain(lane);
+}
+
 // ------------------------------------------------------------------ structure (setup-time, not hot)
 // rows/cols of the FE blocks; kind 0 = Jacobian y-block, 1 = Jacobian u-block, 2 = Hessian FE block.
 // shift_r / shift_c are added to the 1-based ids (nparam and multi-field offsets).
@@ -949,20 +1226,28 @@ k_structure(const DevModel D, int kind, int64_t* __restrict__ rows, int64_t* __r
   const int64_t base = (kind == 0 ? D.base_jy[tile] : (kind == 1 ? D.base_ju[tile] : D.base_h[tile])) + (incl - cnt);
   int64_t n = base;
   const int64_t offu = D.nfree_y;
-  if (kind == 0) {
-    for (int j = 0; j < E::NY; ++j) if (c.gy[j] > 0)
-      for (int i = 0; i < E::NY; ++i) if (c.gy[i] > 0) { rows[n] = c.gy[i]; cols[n] = c.gy[j] + shift; ++n; }
-  } else if (kind == 1) {
-    for (int j = 0; j < E::NU; ++j) if (c.gu[j] > 0)
-      for (int i = 0; i < E::NY; ++i) if (c.gy[i] > 0) { rows[n] = c.gy[i]; cols[n] = c.gu[j] + offu + shift; ++n; }
-  } else {
-    for (int j = 0; j < E::NY; ++j) if (c.gy[j] > 0)
-      for (int i = 0; i < E::NY; ++i) if (c.gy[j] <= c.gy[i]) { rows[n] = c.gy[i] + shift; cols[n] = c.gy[j] + shift; ++n; }
-    for (int j = 0; j < E::NY; ++j) if (c.gy[j] > 0)
-      for (int i = 0; i < E::NU; ++i) if (c.gu[i] > 0) { rows[n] = c.gu[i] + offu + shift; cols[n] = c.gy[j] + shift; ++n; }
-    for (int j = 0; j < E::NU; ++j) if (c.gu[j] > 0)
-      for (int i = 0; i < E::NU; ++i) if (c.gu[j] <= c.gu[i]) { rows[n] = c.gu[i] + offu + shift; cols[n] = c.gu[j] + offu + shift; ++n; }
-  }
+  // blocks in eachblockid order (column field outer, row field inner), inside a block column dof
+  // outer / row dof inner; with one field per space this is the plain (j, i) order
+  constexpr int NF = E::NFY + E::NFU;
+  auto gid = [&](int F, int a) -> int64_t {  // multi-field global id of local dof a of field F (<= 0: not free)
+    if (F < E::NFY) return c.gy[F * E::NLY + a];
+    const int g = c.gu[(F - E::NFY) * E::NLU + a];
+    return g > 0 ? g + offu : g;
+  };
+  auto nloc = [&](int F) { return F < E::NFY ? E::NLY : E::NLU; };
+  const int c0 = kind == 1 ? E::NFY : 0, c1 = kind == 0 ? E::NFY : NF;
+  const int r1 = kind == 2 ? NF : E::NFY;
+  const int64_t shift_r = kind == 2 ? shift : 0;
+  for (int cf = c0; cf < c1; ++cf)
+    for (int rf = 0; rf < r1; ++rf)
+      for (int j = 0; j < nloc(cf); ++j) {
+        const int64_t gc = gid(cf, j);
+        if (gc <= 0) continue;
+        for (int i = 0; i < nloc(rf); ++i) {
+          const int64_t gr = gid(rf, i);
+          if (gr > 0 && (kind != 2 || gc <= gr)) { rows[n] = gr + shift_r; cols[n] = gc + shift; ++n; }
+        }
+      }
 }
 
 // ------------------------------------------------------------------ vector-valued callbacks
@@ -975,16 +1260,18 @@ template <class E>
 __device__ __forceinline__ void accumulate_fields(const Tables<E>& tab, int q, const double* gs /*[M], weighted*/,
                                                   double* ey, double* eu) {
 #pragma unroll
-  for (int a = 0; a < E::NY; ++a) {
-    double v = ey[a];
+  for (int f = 0; f < E::NFY; ++f)
 #pragma unroll
-    for (int k = 0; k < E::NB; ++k) v = fma(tab.By[q][a][k], gs[k], v);
-    ey[a] = v;
-  }
-  if (E::NU > 0) {
+    for (int a = 0; a < E::NLY; ++a) {
+      double v = ey[f * E::NLY + a];
 #pragma unroll
-    for (int b = 0; b < E::NU; ++b) eu[b] = fma(tab.Bu[q][b], gs[E::SU], eu[b]);
-  }
+      for (int k = 0; k < E::NB; ++k) v = fma(tab.By[q][a][k], gs[f * E::NB + k], v);
+      ey[f * E::NLY + a] = v;
+    }
+#pragma unroll
+  for (int f = 0; f < E::NFU; ++f)
+#pragma unroll
+    for (int b = 0; b < E::NLU; ++b) eu[f * E::NLU + b] = fma(tab.Bu[q][b], gs[E::SU + f], eu[f * E::NLU + b]);
 }
 template <class E>
 __device__ __forceinline__ void scatter_element(const DevModel& D, const Cell<E>& c, const double* ey, const double* eu,
@@ -1011,13 +1298,15 @@ __device__ __forceinline__ void field_direction(const Tables<E>& tab, int q, con
 #pragma unroll
   for (int k = 0; k < E::M; ++k) ds[k] = 0.0;
 #pragma unroll
-  for (int a = 0; a < E::NY; ++a)
+  for (int f = 0; f < E::NFY; ++f)
 #pragma unroll
-    for (int k = 0; k < E::NB; ++k) ds[k] = fma(tab.By[q][a][k], vy[a], ds[k]);
-  if (E::NU > 0) {
+    for (int a = 0; a < E::NLY; ++a)
 #pragma unroll
-    for (int b = 0; b < E::NU; ++b) ds[E::SU] = fma(tab.Bu[q][b], vu[b], ds[E::SU]);
-  }
+      for (int k = 0; k < E::NB; ++k) ds[f * E::NB + k] = fma(tab.By[q][a][k], vy[f * E::NLY + a], ds[f * E::NB + k]);
+#pragma unroll
+  for (int f = 0; f < E::NFU; ++f)
+#pragma unroll
+    for (int b = 0; b < E::NLU; ++b) ds[E::SU + f] = fma(tab.Bu[q][b], vu[f * E::NLU + b], ds[E::SU + f]);
 #pragma unroll
   for (int k = 0; k < E::NP; ++k) ds[E::SK + k] = __ldg(v + k);
 }
@@ -1088,12 +1377,9 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
         const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, true);
         I::res(pc, s, R);
 #pragma unroll
-        for (int i = 0; i < E::NY; ++i) {
-          double a = 0.0;
+        for (int f = 0; f < E::NFY; ++f)
 #pragma unroll
-          for (int t = 0; t < E::NR; ++t) a = fma(test_slot<E>(tab, q, i, t), R[t], a);
-          ey[i] = fma(w, a, ey[i]);
-        }
+          for (int i = 0; i < E::NLY; ++i) ey[f * E::NLY + i] = fma(w, test_contract<E>(tab, q, f, i, R), ey[f * E::NLY + i]);
       } else if (OP == OP_JPROD) {
         Jet1<E::M> s[E::M], R[E::NR];
         point_state<E>(tab, c, x, q, s);
@@ -1110,12 +1396,9 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
           dR[t] = a * w;
         }
 #pragma unroll
-        for (int i = 0; i < E::NY; ++i) {
-          double a = 0.0;
+        for (int f = 0; f < E::NFY; ++f)
 #pragma unroll
-          for (int t = 0; t < E::NR; ++t) a = fma(test_slot<E>(tab, q, i, t), dR[t], a);
-          ey[i] += a;
-        }
+          for (int i = 0; i < E::NLY; ++i) ey[f * E::NLY + i] += test_contract<E>(tab, q, f, i, dR);
       } else if (OP == OP_JTPROD) {
         Jet1<E::M> s[E::M];
         point_state<E>(tab, c, x, q, s);

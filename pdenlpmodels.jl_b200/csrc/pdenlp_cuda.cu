@@ -49,6 +49,7 @@ struct Ops {
   virtual int hess_kappa(const Launch& L, const DevModel& D, const double* x, const double* lam, double ow, int which,
                          int64_t prows, double* vk) = 0;
   virtual int run_h() const = 0;
+  virtual bool needs_coef_deriv() const = 0;  // derivative callbacks read the coefficient fields
   virtual const std::vector<double>& ktab() const = 0;  // pre-integrated reference tensors (may be empty)
 };
 
@@ -68,19 +69,29 @@ struct OpsImpl : Ops {
   static constexpr size_t SMEM_J = ((size_t)WJ * jac_stage_doubles<E>() + KTab<E>::TOTAL) * 8;
   static constexpr size_t SMEM_H = ((size_t)WH * hess_stage_doubles<E>() + KTab<E>::TOTAL) * 8;
 
+  // multi-field elements run the block-ordered kernels
+  using JacKernel = void (*)(const Tables<E>, const DevModel, const double*, double*, double*);
+  using HessKernel = void (*)(const Tables<E>, const DevModel, const double*, const double*, double, double*, double*);
+  static JacKernel jac_kernel() {
+    if constexpr (E::MULTI) return k_jac_coord_mf<E>; else return k_jac_coord<E>;
+  }
+  static HessKernel hess_kernel() {
+    if constexpr (E::MULTI) return k_hess_coord_mf<E>; else return k_hess_coord<E>;
+  }
   int occ_j = 1, occ_h = 1;  // resident CTAs per SM of the persistent coord kernels
   int set_attrs() {
     if (attr_done) return PDENLP_OK;
-    CU(cudaFuncSetAttribute(k_jac_coord<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_J));
-    CU(cudaFuncSetAttribute(k_hess_coord<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_H));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_j, k_jac_coord<E>, WJ * 32, SMEM_J));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_h, k_hess_coord<E>, WH * 32, SMEM_H));
+    CU(cudaFuncSetAttribute(jac_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_J));
+    CU(cudaFuncSetAttribute(hess_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_H));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_j, jac_kernel(), WJ * 32, SMEM_J));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_h, hess_kernel(), WH * 32, SMEM_H));
     occ_j = std::max(1, std::min(occ_j, 4));
     occ_h = std::max(1, std::min(occ_h, 4));
     attr_done = true;
     return PDENLP_OK;
   }
   int run_h() const override { return E::RUN_H; }
+  bool needs_coef_deriv() const override { return E::Integrand::NEEDS_COEF_DERIV; }
   static int grid_for(int64_t ntiles, int warps, int cap) {
     int64_t g = (ntiles + warps - 1) / warps;
     return (int)std::max<int64_t>(1, std::min<int64_t>(g, cap));
@@ -100,14 +111,14 @@ struct OpsImpl : Ops {
   int jac(const Launch& L, const DevModel& D, const double* x, double* vy, double* vu) override {
     if (int rc = set_attrs()) return rc;
     static const int wj = env_warps("PDENLP_WARPS_J", WJ);
-    k_jac_coord<E><<<grid_for(D.ntiles, wj, L.sms * occ_j), wj * 32, SMEM_J, L.stream>>>(tab, D, x, vy, vu);
+    jac_kernel()<<<grid_for(D.ntiles, wj, L.sms * occ_j), wj * 32, SMEM_J, L.stream>>>(tab, D, x, vy, vu);
     CU(cudaGetLastError());
     return PDENLP_OK;
   }
   int hess(const Launch& L, const DevModel& D, const double* x, const double* lam, double ow, double* vo, double* vc) override {
     if (int rc = set_attrs()) return rc;
     static const int wh = env_warps("PDENLP_WARPS_H", WH);
-    k_hess_coord<E><<<grid_for(D.ntiles, wh, L.sms * occ_h), wh * 32, SMEM_H, L.stream>>>(tab, D, x, lam, ow, vo, vc);
+    hess_kernel()<<<grid_for(D.ntiles, wh, L.sms * occ_h), wh * 32, SMEM_H, L.stream>>>(tab, D, x, lam, ow, vo, vc);
     CU(cudaGetLastError());
     return PDENLP_OK;
   }
@@ -133,14 +144,14 @@ struct OpsImpl : Ops {
     return PDENLP_OK;
   }
   int jac_kappa(const Launch& L, const DevModel& D, const double* x, double* vk) override {
-    if (E::NP == 0) return PDENLP_OK;
+    if constexpr (E::NP > 0)
     k_jac_kappa<E><<<grid_for(D.ntiles, kWarpsPerCta, L.sms * 8), kThreads, 0, L.stream>>>(tab, D, x, vk);
     CU(cudaGetLastError());
     return PDENLP_OK;
   }
   int hess_kappa(const Launch& L, const DevModel& D, const double* x, const double* lam, double ow, int which,
                  int64_t prows, double* vk) override {
-    if (E::NP == 0) return PDENLP_OK;
+    if constexpr (E::NP > 0)
     k_hess_kappa<E><<<grid_for(D.ntiles, kWarpsPerCta, L.sms * 8), kThreads, 0, L.stream>>>(tab, D, x, lam, ow, which, prows, vk);
     CU(cudaGetLastError());
     return PDENLP_OK;
@@ -152,14 +163,14 @@ Ops* make_ops(const pdenlp_desc& d) {
   auto* o = new OpsImpl<E>();
   for (int q = 0; q < E::NQ; ++q) {
     o->tab.wdet[q] = d.wdet[q];
-    for (int a = 0; a < E::NY; ++a) {
-      o->tab.By[q][a][0] = d.phi_y[q * E::NY + a];
-      for (int k = 0; k < E::DIM; ++k) o->tab.By[q][a][1 + k] = d.grad_y[(q * E::NY + a) * E::DIM + k];
+    for (int a = 0; a < E::NLY; ++a) {
+      o->tab.By[q][a][0] = d.phi_y[q * E::NLY + a];
+      for (int k = 0; k < E::DIM; ++k) o->tab.By[q][a][1 + k] = d.grad_y[(q * E::NLY + a) * E::DIM + k];
     }
-    for (int b = 0; b < E::NUS; ++b) o->tab.Bu[q][b] = (E::NU > 0) ? d.phi_u[q * E::NU + b] : 0.0;
+    for (int b = 0; b < E::NLUS; ++b) o->tab.Bu[q][b] = (E::NLU > 0) ? d.phi_u[q * E::NLU + b] : 0.0;
   }
   for (int i = 0; i < 8; ++i) o->tab.par[i] = d.params[i];
-  if (KTab<E>::ENABLED) {  // pre-integrated reference tensors (see KTab in kernels.cuh)
+  if constexpr (KTab<E>::ENABLED) {  // pre-integrated reference tensors (see KTab in kernels.cuh)
     using KT = KTab<E>;
     o->ktab_.assign(KT::TOTAL, 0.0);
     const auto& T = o->tab;
@@ -182,11 +193,19 @@ Ops* make_ops(const pdenlp_desc& d) {
   return o;
 }
 
-// the closed set of (integrand, dim, ny, nu, nq, nparam) instantiations
+// number of state / control fields of the description (0 = the single-field default)
+int desc_nfy(const pdenlp_desc& d) { return d.nfields_y > 0 ? d.nfields_y : 1; }
+int desc_nfu(const pdenlp_desc& d) { return d.nu == 0 ? 0 : (d.nfields_u > 0 ? d.nfields_u : 1); }
+
+// the closed set of (integrand, dim, ny, nu, nq, nparam, fields) instantiations
 Ops* select_ops(const pdenlp_desc& d) {
   const int I = d.integrand, dim = d.dim, ny = d.ny, nu = d.nu, nq = d.nq, np = d.nparam;
-#define CASE(INT, DIMV, NYV, NUV, NQV, NPV, TYPE) \
-  if (I == INT && dim == DIMV && ny == NYV && nu == NUV && nq == NQV && np == NPV) return make_ops<Elem<TYPE, NYV, NUV, NQV>>(d);
+  const int nfy = desc_nfy(d), nfu = desc_nfu(d);
+#define CASE(INT, DIMV, NYV, NUV, NQV, NPV, TYPE)                                                       \
+  if (I == INT && dim == DIMV && ny == NYV && nu == NUV && nq == NQV && np == NPV) {                   \
+    using EL = Elem<TYPE, NYV, NUV, NQV>;                                                               \
+    if (nfy == EL::NFY && nfu == EL::NFU) return make_ops<EL>(d);                                       \
+  }
   CASE(PDENLP_MEMBRANE, 2, 9, 4, 1, 0, Membrane<2>)
   CASE(PDENLP_MEMBRANE, 2, 4, 4, 1, 0, Membrane<2>)
   CASE(PDENLP_POISSON_BOLTZMANN, 2, 4, 4, 1, 0, PoissonBoltzmann<2>)
@@ -200,6 +219,11 @@ Ops* select_ops(const pdenlp_desc& d) {
   CASE(PDENLP_KAPPA_POISSON, 3, 8, 8, 8, 2, KP3U)
   CASE(PDENLP_PENALIZED_POISSON, 2, 4, 0, 4, 0, PenalizedPoisson<2>)
   CASE(PDENLP_BASIC_UNCONSTRAINED, 2, 4, 4, 4, 0, BasicUnconstrained<2>)
+  // multi-field ODE problems: 1-D, P1 state fields, one quadrature point
+  CASE(PDENLP_CONTROL_SIR, 1, 2, 0, 1, 0, ControlSir)
+  CASE(PDENLP_CELL_INCREASE, 1, 2, 2, 1, 0, CellIncrease)
+  CASE(PDENLP_DYNAMIC_SIR, 1, 2, 2, 1, 0, DynamicSir)
+  CASE(PDENLP_TORE_BRACHISTOCHRONE, 1, 2, 0, 1, 0, ToreBrachistochrone)
 #undef CASE
   return nullptr;
 }
@@ -338,33 +362,44 @@ int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
   auto bail = [&](int code) { pdenlp_destroy(m); cudaSetDevice(prev); return code; };
 
   const int64_t nc = desc->ncells, ldc = (nc + 31) / 32 * 32;
-  const int ny = desc->ny, nu = desc->nu;
-  // SoA transpose of the cell->dof maps
-  {
-    std::vector<int32_t> soa((size_t)ldc * ny, -1);
-    for (int64_t c = 0; c < nc; ++c)
-      for (int a = 0; a < ny; ++a) soa[(size_t)a * ldc + c] = desc->cell_dofs_y[c * ny + a];
-    int32_t* p;
-    if ((rc = dev_upload(m, soa.data(), soa.size(), &p))) return bail(rc);
-    m->dm.dofs_y = p;
+  const int nfy = desc_nfy(*desc), nfu = desc_nfu(*desc);
+  const int ny = nfy * desc->ny, nu = nfu * desc->nu;  // local dofs of the whole state / control space
+  // per-field sizes -> offsets of the concatenated (ConsecutiveMultiFieldStyle) numbering of each space
+  std::vector<int64_t> fnf(nfy + nfu), fnd(nfy + nfu), offf(nfy + nfu), offd(nfy + nfu);
+  if (nfy > 1 || nfu > 1) {
+    if (!desc->field_nfree || !desc->field_ndir) return bail(fail(PDENLP_EINVAL, "multi-field description without field_nfree/field_ndir"));
+    for (int f = 0; f < nfy + nfu; ++f) { fnf[f] = desc->field_nfree[f]; fnd[f] = desc->field_ndir[f]; }
+  } else {
+    fnf[0] = desc->nfree_y; fnd[0] = desc->ndir_y;
+    if (nfu) { fnf[1] = desc->nfree_u; fnd[1] = desc->ndir_u; }
   }
   {
-    std::vector<int32_t> soa((size_t)ldc * std::max(nu, 1), -1);
+    int64_t sf = 0, sd = 0;
+    for (int f = 0; f < nfy; ++f) { offf[f] = sf; offd[f] = sd; sf += fnf[f]; sd += fnd[f]; }
+    if (sf != desc->nfree_y || sd != desc->ndir_y) return bail(fail(PDENLP_EINVAL, "state field sizes do not add up to nfree_y/ndir_y"));
+    sf = sd = 0;
+    for (int f = nfy; f < nfy + nfu; ++f) { offf[f] = sf; offd[f] = sd; sf += fnf[f]; sd += fnd[f]; }
+    if (nfu && (sf != desc->nfree_u || sd != desc->ndir_u)) return bail(fail(PDENLP_EINVAL, "control field sizes do not add up to nfree_u/ndir_u"));
+  }
+  // SoA transpose of the cell->dof maps, validating the per-field ids against the declared sizes and
+  // renumbering them to the concatenated ids of the space
+  auto upload_ids = [&](const int32_t* ids, int nloc_total, int nloc_field, int f0, const char* what, const int32_t** out_ptr) -> int {
+    std::vector<int32_t> soa((size_t)ldc * std::max(nloc_total, 1), -1);
     for (int64_t c = 0; c < nc; ++c)
-      for (int b = 0; b < nu; ++b) soa[(size_t)b * ldc + c] = desc->cell_dofs_u[c * nu + b];
+      for (int a = 0; a < nloc_total; ++a) {
+        const int f = f0 + a / nloc_field;
+        const int64_t g = ids[c * nloc_total + a];
+        if (g == 0 || g > fnf[f] || -g > fnd[f]) return fail(PDENLP_EINVAL, std::string(what) + " dof id out of range");
+        soa[(size_t)a * ldc + c] = (int32_t)(g > 0 ? g + offf[f] : g - offd[f]);
+      }
     int32_t* p;
-    if ((rc = dev_upload(m, soa.data(), soa.size(), &p))) return bail(rc);
-    m->dm.dofs_u = p;
-  }
-  // validate ids against the declared sizes (cheap, host side)
-  for (int64_t i = 0; i < nc * ny; ++i) {
-    const int32_t g = desc->cell_dofs_y[i];
-    if (g == 0 || g > desc->nfree_y || -g > desc->ndir_y) return bail(fail(PDENLP_EINVAL, "state dof id out of range"));
-  }
-  for (int64_t i = 0; i < nc * nu; ++i) {
-    const int32_t g = desc->cell_dofs_u[i];
-    if (g == 0 || g > desc->nfree_u || -g > desc->ndir_u) return bail(fail(PDENLP_EINVAL, "control dof id out of range"));
-  }
+    if (int r = dev_upload(m, soa.data(), soa.size(), &p)) return r;
+    *out_ptr = p;
+    return PDENLP_OK;
+  };
+  if (desc->nfree_y >= ((int64_t)1 << 31) || desc->nfree_u >= ((int64_t)1 << 31)) return bail(fail(PDENLP_EINVAL, "too many dofs for int32 ids"));
+  if ((rc = upload_ids(desc->cell_dofs_y, ny, desc->ny, 0, "state", &m->dm.dofs_y))) return bail(rc);
+  if ((rc = upload_ids(desc->cell_dofs_u, nu, std::max(desc->nu, 1), nfy, "control", &m->dm.dofs_u))) return bail(rc);
   double* dp;
   if ((rc = dev_upload(m, desc->dir_y, (size_t)desc->ndir_y, &dp))) return bail(rc);
   m->dm.dir_y = dp;
@@ -539,15 +574,15 @@ int pdenlp_cons(pdenlp_model* m, const double* x, double* c) {
 }
 int pdenlp_jprod(pdenlp_model* m, const double* x, const double* v, double* Jv) {
   if (!v) return fail(PDENLP_EINVAL, "null argument");
-  return vec_call(m, OP_JPROD, x, nullptr, v, m ? m->info.nvar : 0, 1.0, Jv, m ? m->info.ncon : 0, m && m->d.nparam > 0);
+  return vec_call(m, OP_JPROD, x, nullptr, v, m ? m->info.nvar : 0, 1.0, Jv, m ? m->info.ncon : 0, m && m->ops->needs_coef_deriv());
 }
 int pdenlp_jtprod(pdenlp_model* m, const double* x, const double* v, double* Jtv) {
   if (!v) return fail(PDENLP_EINVAL, "null argument");
-  return vec_call(m, OP_JTPROD, x, nullptr, v, m ? m->info.ncon : 0, 1.0, Jtv, m ? m->info.nvar : 0, m && m->d.nparam > 0);
+  return vec_call(m, OP_JTPROD, x, nullptr, v, m ? m->info.ncon : 0, 1.0, Jtv, m ? m->info.nvar : 0, m && m->ops->needs_coef_deriv());
 }
 int pdenlp_hprod(pdenlp_model* m, const double* x, const double* lambda, double obj_weight, const double* v, double* Hv) {
   if (!v) return fail(PDENLP_EINVAL, "null argument");
-  return vec_call(m, OP_HPROD, x, lambda, v, m ? m->info.nvar : 0, obj_weight, Hv, m ? m->info.nvar : 0, m && m->d.nparam > 0);
+  return vec_call(m, OP_HPROD, x, lambda, v, m ? m->info.nvar : 0, obj_weight, Hv, m ? m->info.nvar : 0, m && m->ops->needs_coef_deriv());
 }
 
 int pdenlp_jac_coord(pdenlp_model* m, const double* x, double* vals) {
@@ -557,6 +592,7 @@ int pdenlp_jac_coord(pdenlp_model* m, const double* x, double* vals) {
   double* dv;
   if (int rc = in_ptr(m, x, m->info.nvar, &m->sx, &dx)) return rc;
   if (int rc = out_ptr(m, vals, m->info.nnzj, &dv)) return rc;
+  if (m->ops->needs_coef_deriv() && !m->dm.coef) return fail(PDENLP_EINVAL, "this integrand's derivatives need the coefficient fields (desc.coef)");
   Launch L{m->stream, m->sms};
   if (m->info.nnzj_k > 0) {
     if (!m->dm.coef) return fail(PDENLP_EINVAL, "the kappa block needs the coefficient fields (desc.coef)");
@@ -579,6 +615,7 @@ int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda, do
   if (int rc = in_ptr(m, x, m->info.nvar, &m->sx, &dx)) return rc;
   if (int rc = in_ptr(m, lambda, m->info.ncon, &m->slam, &dl)) return rc;
   if (int rc = out_ptr(m, vals, m->info.nnzh, &dv)) return rc;
+  if (m->ops->needs_coef_deriv() && !m->dm.coef) return fail(PDENLP_EINVAL, "this integrand's derivatives need the coefficient fields (desc.coef)");
   Launch L{m->stream, m->sms};
   const pdenlp_info& I = m->info;
   double* vko = dv;
@@ -612,6 +649,7 @@ int pdenlp_hess_coord_obj(pdenlp_model* m, const double* x, double obj_weight, d
   const pdenlp_info& I = m->info;
   if (int rc = in_ptr(m, x, I.nvar, &m->sx, &dx)) return rc;
   if (int rc = out_ptr(m, vals, I.nnzh_obj, &dv)) return rc;
+  if (m->ops->needs_coef_deriv() && !m->dm.coef) return fail(PDENLP_EINVAL, "this integrand's derivatives need the coefficient fields (desc.coef)");
   Launch L{m->stream, m->sms};
   if (I.nnzh_k_obj > 0) {
     if (!m->dm.coef) return fail(PDENLP_EINVAL, "the kappa blocks need the coefficient fields (desc.coef)");

@@ -47,6 +47,16 @@ def _touched(ids: np.ndarray, nfree: int, ranges: Sequence[Tuple[int, int]]) -> 
     return out
 
 
+def _space_ids(fields) -> Tuple[np.ndarray, int]:
+    """Cell dof ids of a (multi-field) space with the positive ids offset to the concatenated numbering."""
+    cols, off = [], 0
+    for f in fields:
+        g = f.cell_dof_ids.astype(np.int64)
+        cols.append(np.where(g > 0, g + off, g))
+        off += f.nfree
+    return (np.concatenate(cols, axis=1) if cols else np.zeros((0, 0), np.int64)), off
+
+
 class SlabLayout:
     """Index sets of the slab decomposition, in x-layout (0-based, kappa first)."""
 
@@ -54,13 +64,17 @@ class SlabLayout:
         self.world = world
         self.ranges = partition_cells(spec.model.ncells, world)
         p = spec.nparam
-        ny = spec.Ypde.nfree
-        nu = spec.Ycon.nfree if spec.Ycon is not None else 0
-        ty = _touched(spec.Ypde.cell_dof_ids, ny, self.ranges)
+        if getattr(spec, "is_multifield", False):
+            yfields, ufields = list(spec.Yfields), list(spec.Ufields)
+        else:
+            yfields, ufields = [spec.Ypde], ([spec.Ycon] if spec.Ycon is not None else [])
+        ids_y, ny = _space_ids(yfields)
+        ids_u, nu = _space_ids(ufields)
+        ty = _touched(ids_y, ny, self.ranges)
         self.touch_y = ty
         iface_y = np.nonzero(ty.sum(axis=0) > 1)[0]
         if nu:
-            tu = _touched(spec.Ycon.cell_dof_ids, nu, self.ranges)
+            tu = _touched(ids_u, nu, self.ranges)
             iface_u = np.nonzero(tu.sum(axis=0) > 1)[0]
         else:
             tu = np.zeros((world, 0), dtype=bool)

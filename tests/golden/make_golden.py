@@ -4,7 +4,7 @@ PROVENANCE: the Julia reference (PDENLPModels.jl on Gridap 0.15.5) cannot run in
 these vectors come from the CPU oracle (oracle/pdenlp_oracle.cpp), NOT from the reference itself.
 They freeze the oracle's output (regression pin for both the oracle and the CUDA path); true
 reference vectors can replace them out of band with julia/export_golden.jl, which writes the
-same keys.  Run:  python tests/golden/make_golden.py
+same keys.  Run:  python tests/golden/make_golden.py [case names; default = all]
 """
 import os
 import sys
@@ -24,6 +24,11 @@ CASES = {
     "inversepoisson3d_n2": lambda p: p.poissonmixed(2, 3, True),
     "penalizedpoisson_n4": lambda p: p.penalizedpoisson(4),
     "basicunconstrained_n3": lambda p: p.basicunconstrained(3),
+    # multi-field spaces
+    "controlsir_n6": lambda p: p.controlsir(6),
+    "cellincrease_n5": lambda p: p.cellincrease(5),
+    "dynamicsir_n6": lambda p: p.dynamicsir(6),
+    "torebrachistochrone_n4": lambda p: p.torebrachistochrone(4),
 }
 
 
@@ -38,7 +43,10 @@ def inputs(nvar, ncon, nparam):
 
 def main():
     pkg = load_package(); O = load_oracle()
+    only = sys.argv[1:]
     for name, mk in CASES.items():
+        if only and name not in only:
+            continue
         spec = mk(pkg)
         o = O.Oracle(spec, nthreads=1)
         x, lam, v = inputs(o.nvar, o.ncon, spec.nparam)

@@ -36,9 +36,10 @@ def test_ctypes_mirrors_match_c_layout(cuda_lib):
 #include <stddef.h>
 #include "pdenlp_cuda.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(pdenlp_desc), offsetof(pdenlp_desc, ncells),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(pdenlp_desc), offsetof(pdenlp_desc, ncells),
          offsetof(pdenlp_desc, cell_dofs_y), offsetof(pdenlp_desc, wdet), offsetof(pdenlp_desc, coef),
-         offsetof(pdenlp_desc, params), sizeof(pdenlp_info));
+         offsetof(pdenlp_desc, params), sizeof(pdenlp_info), offsetof(pdenlp_desc, nfields_y),
+         offsetof(pdenlp_desc, nfields_u), offsetof(pdenlp_desc, field_ndir));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as td:
@@ -48,7 +49,7 @@ int main(void) {
         vals = [int(v) for v in subprocess.check_output([exe]).split()]
     D = capi.Desc
     assert vals == [C.sizeof(D), D.ncells.offset, D.cell_dofs_y.offset, D.wdet.offset, D.coef.offset,
-                    D.params.offset, C.sizeof(capi.Info)]
+                    D.params.offset, C.sizeof(capi.Info), D.nfields_y.offset, D.nfields_u.offset, D.field_ndir.offset]
 
 
 def test_header_enum_matches_python_catalogue():

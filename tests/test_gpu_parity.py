@@ -35,11 +35,17 @@ def _cases(pkg):
         "kappa2d_5": lambda: pkg.poissonmixed(5),
         "kappa2d_u_6": lambda: pkg.poissonmixed(6, 2, True),
         "kappa3d_u_4": lambda: pkg.poissonmixed(4, 3, True),
+        # multi-field state / control spaces (block-ordered COO)
+        "controlsir_70": lambda: pkg.controlsir(70),
+        "cellincrease_45": lambda: pkg.cellincrease(45),
+        "dynamicsir_100": lambda: pkg.dynamicsir(100),
+        "dynamicsir_5": lambda: pkg.dynamicsir(5),
     }
 
 
 CASE_NAMES = ["membrane3", "membrane8", "membrane37", "membrane100", "pb_l2_9", "pb_h1_33", "burger_lin_70",
-              "burger_nl_70", "kappa2d_5", "kappa2d_u_6", "kappa3d_u_4"]
+              "burger_nl_70", "kappa2d_5", "kappa2d_u_6", "kappa3d_u_4",
+              "controlsir_70", "cellincrease_45", "dynamicsir_100", "dynamicsir_5"]
 
 
 @pytest.fixture(scope="module", params=CASE_NAMES)
@@ -123,7 +129,7 @@ def test_products(case):
 def test_host_memspace_matches_device(case, pkg):
     """PDENLP_MEM_HOST: numpy in/out through the library's staging copies."""
     from pdenlp_b200.model import GridapPDENLPModel
-    if case["name"] not in ("membrane8", "burger_nl_70"):
+    if case["name"] not in ("membrane8", "burger_nl_70", "dynamicsir_100"):
         pytest.skip("one small case per family is enough")
     nlp_h = GridapPDENLPModel(case["spec"], device="cuda:0", memspace="host")
     x, lam = case["x"], case["lam"]
@@ -158,7 +164,7 @@ def test_unaligned_guarded_outputs(case):
             assert torch.isnan(big[:off]).all() and torch.isnan(big[off + n:]).all()
 
 
-@pytest.mark.parametrize("which", ["penalizedpoisson", "basicunconstrained"])
+@pytest.mark.parametrize("which", ["penalizedpoisson", "basicunconstrained", "torebrachistochrone"])
 def test_unconstrained_models(which, pkg, oracle_mod, cuda_lib):
     """The reference's unconstrained constructor (src/additional_constructors.jl:1-66): ncon = 0,
     empty Jacobian, Hessian = objective segment; values against the oracle."""

@@ -47,7 +47,7 @@ def _worker(rank, world, port, case, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         spec = {"membrane": lambda: pkg.controlelasticmembrane(8), "burger_nl": lambda: pkg.burger1d_param(100),
-                "pb": lambda: pkg.poissonboltzman2d(9)}[case]()
+                "pb": lambda: pkg.poissonboltzman2d(9), "dynamicsir": lambda: pkg.dynamicsir(100)}[case]()
         layout = SlabLayout(spec, world)
         full = O.Oracle(spec, nthreads=1)
         local = OracleLocal(O.Oracle(spec, layout.ranges[rank], nthreads=1))
@@ -93,7 +93,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-@pytest.mark.parametrize("case", ["membrane", "burger_nl", "pb"])
+@pytest.mark.parametrize("case", ["membrane", "burger_nl", "pb", "dynamicsir"])
 def test_world2_gloo(case, oracle_mod):
     oracle_mod.build()
     ctx = mp.get_context("spawn")
