@@ -42,6 +42,7 @@ struct Membrane : FieldIdx<DIM_, 0> {
   static constexpr bool HAS_CONST = false;
   static constexpr bool NEEDS_COEF_DERIV = false;  // derivatives do not read coefficient fields
   static constexpr bool FE_DERIVS_POINT_INDEPENDENT = true;  // d res/d(y,grad y,u) and the FE-field Hessians are the same at every point of a cell
+  static constexpr bool RES_FE_HESSIAN_ZERO = true;  // res is affine in (y, grad y, u): the constraint FE Hessian block is identically zero
   template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) { return tracking_f<T, I>(c, s); }
   // grad(v).grad(y) - v*u - v*h
   template <class T> PDENLP_HD static void res(const PointCtx& c, const T* s, T* R) {
@@ -57,6 +58,7 @@ struct PoissonBoltzmann : FieldIdx<DIM_, 0> {
   static constexpr bool HAS_CONST = false;
   static constexpr bool NEEDS_COEF_DERIV = false;
   static constexpr bool FE_DERIVS_POINT_INDEPENDENT = false;  // d res/d(y,grad y,u) and the FE-field Hessians are the same at every point of a cell
+  static constexpr bool RES_FE_HESSIAN_ZERO = false;  // res is affine in (y, grad y, u): the constraint FE Hessian block is identically zero
   template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) { return tracking_f<T, I>(c, s); }
   // grad(v).grad(y) + sinh(y)*v - u*v - v*h
   template <class T> PDENLP_HD static void res(const PointCtx& c, const T* s, T* R) {
@@ -71,6 +73,7 @@ struct BurgerLin : FieldIdx<1, 0> {
   static constexpr bool HAS_CONST = false;
   static constexpr bool NEEDS_COEF_DERIV = false;
   static constexpr bool FE_DERIVS_POINT_INDEPENDENT = true;  // d res/d(y,grad y,u) and the FE-field Hessians are the same at every point of a cell
+  static constexpr bool RES_FE_HESSIAN_ZERO = true;  // res is affine in (y, grad y, u): the constraint FE Hessian block is identically zero
   template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) { return tracking_f<T, I>(c, s); }
   // -nu*grad(v).grad(y) + (grad(y).1)*v - v*u - v*h
   template <class T> PDENLP_HD static void res(const PointCtx& c, const T* s, T* R) {
@@ -84,6 +87,7 @@ struct BurgerNl : FieldIdx<1, 1> {
   static constexpr bool HAS_CONST = true;
   static constexpr bool NEEDS_COEF_DERIV = false;
   static constexpr bool FE_DERIVS_POINT_INDEPENDENT = false;  // d res/d(y,grad y,u) and the FE-field Hessians are the same at every point of a cell
+  static constexpr bool RES_FE_HESSIAN_ZERO = false;  // res is affine in (y, grad y, u): the constraint FE Hessian block is identically zero
   template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) {
     T t = s[I::SK] - c.par[2];
     return tracking_f<T, I>(c, s) + 0.5 * t * t;
@@ -102,6 +106,7 @@ struct KappaPoisson : FieldIdx<DIM_, 2> {
   static constexpr bool HAS_CONST = false;
   static constexpr bool NEEDS_COEF_DERIV = true;  // d res / d k2 = -v*f
   static constexpr bool FE_DERIVS_POINT_INDEPENDENT = true;  // d res/d(y,grad y,u) and the FE-field Hessians are the same at every point of a cell
+  static constexpr bool RES_FE_HESSIAN_ZERO = true;  // res is affine in (y, grad y, u): the constraint FE Hessian block is identically zero
   template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) {
     T d = c.target - s[I::SY];
     T a = s[I::SK] - 1.0, b = s[I::SK + 1] - 1.0;
@@ -124,6 +129,7 @@ struct PenalizedPoisson : FieldIdx<DIM_, 0> {
   static constexpr bool HAS_CONST = false;
   static constexpr bool NEEDS_COEF_DERIV = false;
   static constexpr bool FE_DERIVS_POINT_INDEPENDENT = true;  // d res/d(y,grad y,u) and the FE-field Hessians are the same at every point of a cell
+  static constexpr bool RES_FE_HESSIAN_ZERO = true;  // res is affine in (y, grad y, u): the constraint FE Hessian block is identically zero
   // 0.5 * grad(y).grad(y) - w * y
   template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) {
     T a = s[I::SG] * s[I::SG];
@@ -143,6 +149,7 @@ struct BasicUnconstrained : FieldIdx<DIM_, 0> {
   static constexpr bool HAS_CONST = false;
   static constexpr bool NEEDS_COEF_DERIV = false;
   static constexpr bool FE_DERIVS_POINT_INDEPENDENT = true;  // d res/d(y,grad y,u) and the FE-field Hessians are the same at every point of a cell
+  static constexpr bool RES_FE_HESSIAN_ZERO = true;  // res is affine in (y, grad y, u): the constraint FE Hessian block is identically zero
   // 0.5 * (ubis - u) * (ubis - u) + 0.5 * y * y
   template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) {
     T d = c.target - s[I::SU];
@@ -178,6 +185,7 @@ struct MFIdx {
 // test/problems/controlsir.jl:20-33: fields (I, S); par = (a, b, mu)
 struct ControlSir : MFIdx<1, 2, 0> {
   static constexpr bool NEEDS_COEF_DERIV = false;
+  static constexpr bool RES_FE_HESSIAN_ZERO = false;
   using X = MFIdx<1, 2, 0>;
   template <class T> PDENLP_HD static T f(const PointCtx&, const T* s) { return 0.5 * s[X::Y(0)] * s[X::Y(0)]; }
   // dt(I,p) + dt(S,q) - p*(a*S*I - b*I) - q*(mu - b*I - a*S*I)
@@ -194,6 +202,7 @@ struct ControlSir : MFIdx<1, 2, 0> {
 // test/problems/cellincrease.jl:15-40: fields (cf, pf), control u in L2; par = (kp, kr)
 struct CellIncrease : MFIdx<1, 2, 1> {
   static constexpr bool NEEDS_COEF_DERIV = false;
+  static constexpr bool RES_FE_HESSIAN_ZERO = false;
   using X = MFIdx<1, 2, 1>;
   template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) { return c.par[0] * s[X::Y(1)]; }
   // dt(cf,p) + dt(pf,q) - p*(kp*pf*(1-cf) - kr*cf*(1-cf-pf)) + q*(u*kr*cf*(1-cf-pf) - kp*pf*pf)
@@ -210,6 +219,7 @@ struct CellIncrease : MFIdx<1, 2, 1> {
 // test/problems/dynamicsir.jl:36-58: fields (I, S), controls (bf, cf) in H1; target = w0(t), par = (w1, w2)
 struct DynamicSir : MFIdx<1, 2, 2> {
   static constexpr bool NEEDS_COEF_DERIV = true;  // d f / d(bf, cf) reads w0 = coef target
+  static constexpr bool RES_FE_HESSIAN_ZERO = false;
   using X = MFIdx<1, 2, 2>;
   template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) {
     T a = c.target * s[X::U(0)] - c.par[0];
@@ -229,6 +239,7 @@ struct DynamicSir : MFIdx<1, 2, 2> {
 // test/problems/torebrachistochrone.jl:25-28: fields (phi, theta), unconstrained; par = (a, c)
 struct ToreBrachistochrone : MFIdx<1, 2, 0> {
   static constexpr bool NEEDS_COEF_DERIV = false;
+  static constexpr bool RES_FE_HESSIAN_ZERO = true;
   using X = MFIdx<1, 2, 0>;
   template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) {
     const double a = c.par[0];

@@ -1477,6 +1477,30 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
   }
 }
 
+// Zero fill of a COO segment that is structurally zero (constraint FE Hessian block of an affine
+// residual, or hess_coord! without multipliers): pure streaming 16 B stores, 4 per thread per step.
+__global__ void __launch_bounds__(256) k_zero_fill(double* __restrict__ p, int64_t n) {
+  const int64_t head = (n > 0 && ((reinterpret_cast<uintptr_t>(p) >> 3) & 1)) ? 1 : 0;  // 8 B-aligned start
+  const int64_t n2 = (n - head) >> 1;
+  double2* q = reinterpret_cast<double2*>(p + head);
+  const double2 z = make_double2(0.0, 0.0);
+  // each CTA owns contiguous 16 KB chunks (4 x 256 x 16 B)
+  const int64_t nchunks = (n2 + 1023) >> 10;
+  for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const int64_t i0 = (c << 10) + threadIdx.x;
+    if (i0 + 768 < n2) {
+      q[i0] = z; q[i0 + 256] = z; q[i0 + 512] = z; q[i0 + 768] = z;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (i0 + k * 256 < n2) q[i0 + k * 256] = z;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (head) p[0] = 0.0;
+    if ((n - head) & 1) p[n - 1] = 0.0;
+  }
+}
+
 // fixed-order final sum of the per-CTA objective partials
 __global__ void k_sum_partials(const double* __restrict__ partials, int n, double* __restrict__ out) {
   __shared__ double sh[256];
