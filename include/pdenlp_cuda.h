@@ -91,7 +91,15 @@ enum pdenlp_integrand {
   PDENLP_DYNAMIC_SIR = 10,
   /* unconstrained, state (phi,theta): f = a^2*phi'^2 + (c + a*cos(phi))^2 * theta'^2
      test/problems/torebrachistochrone.jl:25-28.  params = (a, c) */
-  PDENLP_TORE_BRACHISTOCHRONE = 11
+  PDENLP_TORE_BRACHISTOCHRONE = 11,
+  /* ---- NoFETerm objectives: obj = fk(kappa), no integral (src/additional_obj_terms.jl:59-106); the
+     objective Hessian has no FE block, its kappa-block is the p x p lower triangle ----
+     nparam=1: fk = 0.5*dot(k .- 1, k .- 1) ; res = k1*grad(v).grad(y) - v*f
+     test/problems/poissonparam.jl:35-44 */
+  PDENLP_POISSON_PARAM = 12,
+  /* state (I,S), NoFETerm() = 0: res = dt(I,p) + dt(S,q) - p*(a*S*I - b*I) - q*(b*I - a*S*I)
+     test/problems/sis.jl:21-34.  params = (a, b) */
+  PDENLP_SIS = 13
 };
 
 /* coefficient fields sampled at quadrature points, coef[k][cell][q] */
@@ -169,8 +177,11 @@ typedef struct pdenlp_info {
   int64_t nnzh;       /* LOCAL Hessian entries: obj k + obj FE + cons k + cons FE */
   int64_t nnzh_obj;   /* obj k-block + obj FE block (pdemeta.nnzh_obj) */
   int64_t nnzh_k_obj; /* get_nnz_hess_k, src/hessian_struct_nnzh_functions.jl:61-68 */
-  int64_t nnzh_fe;    /* entries of ONE FE block (obj and cons blocks are equal) */
+  int64_t nnzh_fe;    /* entries of ONE FE block (the constraint block; the objective block is equal or absent) */
   int64_t nnzh_k_con; /* p(p+1)/2 + (n-p)p, src/GridapPDENLPModel.jl:362 */
+  int64_t nnzh_fe_obj;/* entries of the OBJECTIVE FE block: nnzh_fe, or 0 for a NoFETerm objective
+                         (src/hessian_struct_nnzh_functions.jl:41-43); nnzh_obj = nnzh_k_obj + nnzh_fe_obj,
+                         nnzh = nnzh_obj + nnzh_k_con + nnzh_fe */
 } pdenlp_info;
 
 const char* pdenlp_last_error(void);

@@ -29,7 +29,7 @@ end
 
 struct Info
   nvar::Int64; ncon::Int64; nnzj::Int64; nnzj_k::Int64; nnzj_y::Int64; nnzj_u::Int64
-  nnzh::Int64; nnzh_obj::Int64; nnzh_k_obj::Int64; nnzh_fe::Int64; nnzh_k_con::Int64
+  nnzh::Int64; nnzh_obj::Int64; nnzh_k_obj::Int64; nnzh_fe::Int64; nnzh_k_con::Int64; nnzh_fe_obj::Int64
 end
 
 check(rc) = rc == 0 || error("libpdenlp_cuda ($rc): " * unsafe_string(ccall((:pdenlp_last_error, LIB), Cstring, ())))

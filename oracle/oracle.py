@@ -136,11 +136,12 @@ class Oracle:
         self.P = P
         self.nvar = spec.nparam + P.nfree_y + P.nfree_u
         self.ncon = P.nfree_y
-        sz = np.zeros(6, dtype=np.int64)
+        sz = np.zeros(7, dtype=np.int64)
         self._check(lib().oracle_sizes(C.byref(P), _p(sz)))
-        self.nnzj_k, self.nnzj_y, self.nnzj_u, self.nnzh_k_obj, self.nnzh_fe, self.nnzh_k_con = (int(v) for v in sz)
+        (self.nnzj_k, self.nnzj_y, self.nnzj_u, self.nnzh_k_obj, self.nnzh_fe, self.nnzh_k_con,
+         self.nnzh_fe_obj) = (int(v) for v in sz)  # nnzh_fe_obj = 0 for NoFETerm objectives, else nnzh_fe
         self.nnzj = self.nnzj_k + self.nnzj_y + self.nnzj_u
-        self.nnzh_obj = self.nnzh_k_obj + self.nnzh_fe
+        self.nnzh_obj = self.nnzh_k_obj + self.nnzh_fe_obj
         self.nnzh = self.nnzh_obj + self.nnzh_k_con + self.nnzh_fe
 
     @staticmethod

@@ -129,7 +129,18 @@ typedef struct oracle_problem {
 }
 
 enum { MEMBRANE = 1, PB = 2, BURGER_LIN = 3, BURGER_NL = 4, KAPPA_POISSON = 5, PENALIZED_POISSON = 6, BASIC_UNCONSTRAINED = 7,
-       CONTROL_SIR = 8, CELL_INCREASE = 9, DYNAMIC_SIR = 10, TORE_BRACHISTOCHRONE = 11 };
+       CONTROL_SIR = 8, CELL_INCREASE = 9, DYNAMIC_SIR = 10, TORE_BRACHISTOCHRONE = 11, POISSON_PARAM = 12, SIS = 13 };
+
+// NoFETerm objectives (src/additional_obj_terms.jl:59-106): f(kappa) without any integral; the objective has no
+// FE Hessian block (hessian_struct_nnzh_functions.jl:41-43) and its kappa-block is the p x p lower triangle
+static bool is_nofe(const oracle_problem& P) { return P.integrand == POISSON_PARAM || P.integrand == SIS; }
+// fk(k) = 0.5 * dot(k .- 1, k .- 1) (poissonparam.jl:43-44); SIS: NoFETerm() = 0
+template <class S>
+static S nofe_obj(const oracle_problem& P, const S* k, int np) {
+  S a = cst(0.0, k[0]);
+  if (P.integrand == POISSON_PARAM) for (int i = 0; i < np; ++i) { S d = k[i] - 1.0; a = a + 0.5 * d * d; }
+  return a;
+}
 
 static const double PI = 3.14159265358979323846;
 
@@ -162,6 +173,7 @@ static double coef_source(const oracle_problem& P, const double* x) {
     case BURGER_LIN:
     case BURGER_NL: return 2 * (P.params[1] + x[0] * x[0] * x[0]);  // burger1d.jl:24
     case PENALIZED_POISSON: return 1.0;           // w, penalizedpoisson.jl:32
+    case POISSON_PARAM:                           // f, poissonparam.jl:33
     case KAPPA_POISSON: {                         // f, poissonmixed.jl:31
       double s = (2 * PI * PI) * std::sin(2 * PI * x[0]) * x[1];
       return P.dim == 3 ? s * x[2] : s;
@@ -304,6 +316,8 @@ static S res_density(const oracle_problem& P, const Pt<S>& p, double v, const do
       return (-P.params[1]) * gg + one_dot * v - v * p.u - v * p.h;
     case BURGER_NL:  // nu*(grad(v).grad(y)) + k1 + c(y,v) - v*u - v*h ; k1(x) = -k[1] ; c = v*(y*(grad(y).1))
       return P.params[1] * gg - p.k[0] + v * (one_dot * p.y) - v * p.u - v * p.h;
+    case POISSON_PARAM:    // k1*grad(v).grad(y) - v*f   (poissonparam.jl:35-38)
+      return p.k[0] * gg - v * p.h;
     case KAPPA_POISSON: {  // k1*grad(v).grad(y) - v*f*k2 [- v*u]
       S r = p.k[0] * gg - (v * p.h) * p.k[1];
       if (has_u) r = r - v * p.u;
@@ -408,6 +422,7 @@ struct Driver {
   }
 
   static double obj(const oracle_problem& P, const double* x) {
+    if (is_nofe(P)) return nofe_obj<double>(P, x, NP);  // _obj_integral(::NoFETerm, k, x) = f(k)
     RefTables T = make_tables(P);
     double total = 0.0;  // sum(::DomainContribution): cell order
     for (int64_t c = 0; c < P.ncells; ++c) {
@@ -422,6 +437,14 @@ struct Driver {
     RefTables T = make_tables(P);
     int64_t nvar = NP + P.nfree_y + P.nfree_u;
     for (int64_t i = 0; i < nvar; ++i) g[i] = 0.0;
+    if (is_nofe(P)) {  // g[p+1:] = 0, g[1:p] = ForwardDiff.gradient(f, k)   (additional_obj_terms.jl:69-95)
+      typedef Dual<double, (NP > 0 ? NP : 1)> DK;
+      DK k[NP > 0 ? NP : 1];
+      for (int i = 0; i < NP; ++i) { k[i].v = x[i]; for (int j = 0; j < NP; ++j) k[i].d[j] = i == j; }
+      DK F = nofe_obj<DK>(P, k, NP);
+      for (int i = 0; i < NP; ++i) g[i] = F.d[i];
+      return;
+    }
     for (int64_t c = 0; c < P.ncells; ++c) {
       double z[N]; gather_cell<NP, NY, NU>(P, x, c, z);
       D1 zz[N]; seed1(z, zz);
@@ -491,10 +514,11 @@ struct Driver {
     for (int64_t c = 0; c < P.ncells; ++c) { jy += count_jy(P, c); ju += count_ju(P, c); hf += count_h(P, c); }
     int64_t n = NP + P.nfree_y + P.nfree_u, p = NP;
     out[0] = P.nfree_y * p; out[1] = jy; out[2] = ju;
-    bool inde = (P.integrand == KAPPA_POISSON);  // MixedEnergyFETerm(..., inde = true), poissonmixed.jl:44
+    bool inde = (P.integrand == KAPPA_POISSON) || is_nofe(P);  // MixedEnergyFETerm(..., inde = true), poissonmixed.jl:44
     out[3] = p == 0 ? 0 : (inde ? p * (p + 1) / 2 : p * (p + 1) / 2 + (n - p) * p);
     out[4] = hf;
     out[5] = p == 0 ? 0 : p * (p + 1) / 2 + (n - p) * p;
+    out[6] = is_nofe(P) ? 0 : hf;  // objective FE block
   }
 
   static void jac_structure(const oracle_problem& P, int64_t* rows, int64_t* cols) {
@@ -511,7 +535,7 @@ struct Driver {
 
   static void jac_coord(const oracle_problem& P, const double* x, double* vals) {
     RefTables T = make_tables(P);
-    int64_t sz[6]; sizes(P, sz);
+    int64_t sz[7]; sizes(P, sz);
     std::vector<int64_t> by(P.ncells + 1, 0), bu(P.ncells + 1, 0);
     for (int64_t c = 0; c < P.ncells; ++c) { by[c + 1] = by[c] + count_jy(P, c); bu[c + 1] = bu[c] + count_ju(P, c); }
     double* vk = vals; double* vy = vals + sz[0]; double* vu = vy + sz[1];
@@ -537,12 +561,13 @@ struct Driver {
   }
 
   static void hess_structure(const oracle_problem& P, int64_t* rows, int64_t* cols) {
-    int64_t sz[6]; sizes(P, sz);
+    int64_t sz[7]; sizes(P, sz);
     int64_t n = 0, nvar = NP + P.nfree_y + P.nfree_u;
-    bool inde = (P.integrand == KAPPA_POISSON);
+    bool inde = (P.integrand == KAPPA_POISSON) || is_nofe(P);
     int64_t prows = inde ? NP : nvar;
     // ((i, j) for i = 1:prows, j = 1:p if j <= i), i fastest
     for (int j = 1; j <= NP; ++j) for (int64_t i = j; i <= prows; ++i) { rows[n] = i; cols[n] = j; ++n; }
+    if (!is_nofe(P))
     for (int64_t c = 0; c < P.ncells; ++c)
       visit_hess_cell(P, c, [&](int, int, int64_t gr, int64_t gc) { rows[n] = gr + NP; cols[n] = gc + NP; ++n; });
     for (int j = 1; j <= NP; ++j) for (int64_t i = j; i <= nvar; ++i) { rows[n] = i; cols[n] = j; ++n; }
@@ -559,15 +584,26 @@ struct Driver {
 
   static void hess_coord(const oracle_problem& P, const double* x, const double* lambda, double obj_weight, double* vals) {
     RefTables T = make_tables(P);
-    int64_t sz[6]; sizes(P, sz);
+    int64_t sz[7]; sizes(P, sz);
     int64_t nvar = NP + P.nfree_y + P.nfree_u;
-    bool inde = (P.integrand == KAPPA_POISSON);
+    const bool nofe = is_nofe(P);
+    bool inde = (P.integrand == KAPPA_POISSON) || nofe;
     int64_t prows = inde ? NP : nvar;
     std::vector<int64_t> bh(P.ncells + 1, 0);
     for (int64_t c = 0; c < P.ncells; ++c) bh[c + 1] = bh[c] + count_h(P, c);
-    double* vko = vals; double* vfo = vko + sz[3]; double* vkc = vfo + sz[4]; double* vfc = vkc + sz[5];
-    int64_t nnzh = sz[3] + sz[4] + sz[5] + sz[4];
+    double* vko = vals; double* vfo = vko + sz[3]; double* vkc = vfo + sz[6]; double* vfc = vkc + sz[5];
+    int64_t nnzh = sz[3] + sz[6] + sz[5] + sz[4];
     for (int64_t i = 0; i < nnzh; ++i) vals[i] = 0.0;
+    if (nofe && NP > 0) {  // vals[1:nnz_hess_k] = LowerTriangular(ForwardDiff.hessian(f, k))   (additional_obj_terms.jl:97-106)
+      typedef Dual<double, (NP > 0 ? NP : 1)> DK1; typedef Dual<DK1, (NP > 0 ? NP : 1)> DK2;
+      DK2 k[NP > 0 ? NP : 1];
+      for (int i = 0; i < NP; ++i) {
+        k[i].v.v = x[i];
+        for (int j = 0; j < NP; ++j) { k[i].v.d[j] = i == j; k[i].d[j].v = i == j; for (int l = 0; l < NP; ++l) k[i].d[j].d[l] = 0.0; }
+      }
+      DK2 F = nofe_obj<DK2>(P, k, NP);
+      for (int j = 0; j < NP; ++j) for (int i = j; i < NP; ++i) vko[trap_pos(i + 1, j + 1, prows)] = F.d[i].d[j];
+    }
 #pragma omp parallel for schedule(static) num_threads(P.nthreads > 0 ? P.nthreads : omp_get_max_threads())
     for (int64_t c = 0; c < P.ncells; ++c) {
       double z[N]; gather_cell<NP, NY, NU>(P, x, c, z);
@@ -575,10 +611,13 @@ struct Driver {
       CellGeom G = cell_geom(P, c);
       int64_t gid[NY + NU + 1]; cell_gids(P, c, gid);
       // objective part
-      D2 F = cell_obj<D2, NP, NY, NU>(P, T, G, zz);
       int64_t n = bh[c];
-      visit_hess_cell(P, c, [&](int li, int lj, int64_t, int64_t) { vfo[n++] = F.d[NP + li].d[NP + lj]; });
-      if (NP > 0) {
+      D2 F = cst(0.0, zz[0]);
+      if (!nofe) {
+        F = cell_obj<D2, NP, NY, NU>(P, T, G, zz);
+        visit_hess_cell(P, c, [&](int li, int lj, int64_t, int64_t) { vfo[n++] = F.d[NP + li].d[NP + lj]; });
+      }
+      if (NP > 0 && !nofe) {
 #pragma omp critical
         for (int j = 0; j < NP; ++j) {
           for (int i = j; i < NP; ++i) vko[trap_pos(i + 1, j + 1, prows)] += F.d[i].d[j];
@@ -602,7 +641,7 @@ struct Driver {
       }
     }
     // vals .*= obj_weight on the objective part only (GridapPDENLPModel.jl:299 runs before the constraint part)
-    for (int64_t i = 0; i < sz[3] + sz[4]; ++i) vals[i] *= obj_weight;
+    for (int64_t i = 0; i < sz[3] + sz[6]; ++i) vals[i] *= obj_weight;
   }
 };
 
@@ -655,6 +694,11 @@ static S res_density_mf(const oracle_problem& P, const PtMF<S>& p, int ft, doubl
       const S& cf = I; const S& pf = Sv;
       if (ft == 0) return dI * v - v * (kp * pf * (1.0 - cf) - kr * cf * (1.0 - cf - pf));
       return dS * v + v * (p.u[0] * kr * cf * (1.0 - cf - pf) - kp * pf * pf);
+    }
+    case SIS: {  // dt(I,p) + dt(S,q) - p*(a*S*I - b*I) - q*(b*I - a*S*I)   (sis.jl:21-25)
+      const double a = P.params[0], b = P.params[1];
+      if (ft == 0) return dI * v - v * (a * Sv * I - b * I);
+      return dS * v - v * (b * I - a * Sv * I);
     }
     case DYNAMIC_SIR: {  // dt(I,p) + dt(S,q) - p*(bf*S*I - cf*I) + q*bf*S*I   (dynamicsir.jl:36-41)
       if (ft == 0) return dI * v - v * (p.u[0] * Sv * I - p.u[1] * I);
@@ -777,7 +821,7 @@ struct MFDriver {
     for (int64_t c = 0; c < P.ncells; ++c) {
       jy += cnt(P, c, 0, NFY, 0, NFY, false); ju += cnt(P, c, 0, NFY, NFY, NF, false); hf += cnt(P, c, 0, NF, 0, NF, true);
     }
-    out[0] = 0; out[1] = jy; out[2] = ju; out[3] = 0; out[4] = hf; out[5] = 0;
+    out[0] = 0; out[1] = jy; out[2] = ju; out[3] = 0; out[4] = hf; out[5] = 0; out[6] = is_nofe(P) ? 0 : hf;
   }
   static void jac_structure(const oracle_problem& P, int64_t* rows, int64_t* cols) {
     int64_t n = 0;
@@ -786,7 +830,7 @@ struct MFDriver {
   }
   static void jac_coord(const oracle_problem& P, const double* x, double* vals) {
     RefTables T = make_tables(P);
-    int64_t sz[6]; sizes(P, sz);
+    int64_t sz[7]; sizes(P, sz);
     double* vy = vals; double* vu = vals + sz[1];
     int64_t ny = 0, nu = 0;
     for (int64_t c = 0; c < P.ncells; ++c) {
@@ -798,20 +842,23 @@ struct MFDriver {
   }
   static void hess_structure(const oracle_problem& P, int64_t* rows, int64_t* cols) {
     int64_t n = 0;
-    for (int rep = 0; rep < 2; ++rep)
+    for (int rep = is_nofe(P) ? 1 : 0; rep < 2; ++rep)
       for (int64_t c = 0; c < P.ncells; ++c) visit(P, c, 0, NF, 0, NF, true, [&](int, int, int64_t gr, int64_t gc) { rows[n] = gr; cols[n] = gc; ++n; });
   }
   static void hess_coord(const oracle_problem& P, const double* x, const double* lambda, double obj_weight, double* vals) {
     RefTables T = make_tables(P);
-    int64_t sz[6]; sizes(P, sz);
-    double* vo = vals; double* vc = vals + sz[4];
-    for (int64_t i = 0; i < 2 * sz[4]; ++i) vals[i] = 0.0;
+    int64_t sz[7]; sizes(P, sz);
+    const bool nofe = is_nofe(P);
+    double* vo = vals; double* vc = vals + sz[6];
+    for (int64_t i = 0; i < sz[6] + sz[4]; ++i) vals[i] = 0.0;
     int64_t no = 0, nc = 0;
     for (int64_t c = 0; c < P.ncells; ++c) {
       double z[N]; gather(P, x, c, z); D2 zz[N]; seed2(z, zz);
       CellGeom G = cell_geom(P, c);
-      D2 F = cell_obj<D2>(P, T, G, zz);
-      visit(P, c, 0, NF, 0, NF, true, [&](int li, int lj, int64_t, int64_t) { vo[no++] = F.d[li].d[lj]; });
+      if (!nofe) {
+        D2 F = cell_obj<D2>(P, T, G, zz);
+        visit(P, c, 0, NF, 0, NF, true, [&](int li, int lj, int64_t, int64_t) { vo[no++] = F.d[li].d[lj]; });
+      }
       if (lambda) {
         D2 r[NYT > 0 ? NYT : 1]; cell_res<D2>(P, T, G, zz, r);
         int64_t gid[N + 1]; gids(P, c, gid);
@@ -820,7 +867,7 @@ struct MFDriver {
         visit(P, c, 0, NF, 0, NF, true, [&](int li, int lj, int64_t, int64_t) { vc[nc++] = L.d[li].d[lj]; });
       }
     }
-    for (int64_t i = 0; i < sz[4]; ++i) vals[i] *= obj_weight;
+    for (int64_t i = 0; i < sz[6]; ++i) vals[i] *= obj_weight;
   }
 };
 
@@ -834,7 +881,7 @@ struct MFDriver {
     else return -2;                                                                            \
     return 0;                                                                                  \
   } while (0)
-static bool is_mf(const oracle_problem* P) { return P->integrand >= CONTROL_SIR; }
+static bool is_mf(const oracle_problem* P) { return (P->integrand >= CONTROL_SIR && P->integrand <= TORE_BRACHISTOCHRONE) || P->integrand == SIS; }
 
 // ------------------------------------------------------------------ dispatch
 #define DISPATCH(CALL)                                                             \
@@ -851,12 +898,14 @@ static bool is_mf(const oracle_problem* P) { return P->integrand >= CONTROL_SIR;
     else if (np == 2 && ny == 8 && nu == 8) { typedef Driver<2, 8, 8> D; CALL; }   \
     else if (np == 2 && ny == 8 && nu == 0) { typedef Driver<2, 8, 0> D; CALL; }   \
     else if (np == 0 && ny == 8 && nu == 8) { typedef Driver<0, 8, 8> D; CALL; }   \
+    else if (np == 1 && ny == 4 && nu == 0) { typedef Driver<1, 4, 0> D; CALL; }   \
     else return -2;                                                                \
   } while (0)
 
 extern "C" {
 
-int oracle_sizes(const oracle_problem* P, int64_t* out6) { if (is_mf(P)) MF_DISPATCH(D::sizes(*P, out6)); DISPATCH(D::sizes(*P, out6)); return 0; }
+// out7: nnzj_k, nnzj_y, nnzj_u, nnzh_k_obj, nnzh_fe (constraint FE block), nnzh_k_con, nnzh_fe_obj (objective FE block)
+int oracle_sizes(const oracle_problem* P, int64_t* out7) { if (is_mf(P)) MF_DISPATCH(D::sizes(*P, out7)); DISPATCH(D::sizes(*P, out7)); return 0; }
 int oracle_obj(const oracle_problem* P, const double* x, double* f) { if (is_mf(P)) MF_DISPATCH(*f = D::obj(*P, x)); DISPATCH(*f = D::obj(*P, x)); return 0; }
 int oracle_grad(const oracle_problem* P, const double* x, double* g) { if (is_mf(P)) MF_DISPATCH(D::grad(*P, x, g)); DISPATCH(D::grad(*P, x, g)); return 0; }
 int oracle_cons(const oracle_problem* P, const double* x, double* c) { if (is_mf(P)) MF_DISPATCH(D::cons(*P, x, c)); DISPATCH(D::cons(*P, x, c)); return 0; }

@@ -16,7 +16,7 @@ Layout (only what the hot path needs):
 from . import cartesian, problems, flatten  # noqa: F401
 from .problems import (  # noqa: F401
     controlelasticmembrane, poissonboltzman2d, burger1d, burger1d_param, poissonmixed, penalizedpoisson,
-    basicunconstrained, controlsir, cellincrease, dynamicsir, torebrachistochrone, BASELINE_CONFIGS,
+    basicunconstrained, controlsir, cellincrease, dynamicsir, torebrachistochrone, poissonparam, sis, BASELINE_CONFIGS,
 )
 
 __all__ = ["cartesian", "problems", "flatten"]

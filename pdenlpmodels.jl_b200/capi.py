@@ -50,7 +50,8 @@ class Desc(C.Structure):
 
 class Info(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
-        "nvar", "ncon", "nnzj", "nnzj_k", "nnzj_y", "nnzj_u", "nnzh", "nnzh_obj", "nnzh_k_obj", "nnzh_fe", "nnzh_k_con")]
+        "nvar", "ncon", "nnzj", "nnzj_k", "nnzj_y", "nnzj_u", "nnzh", "nnzh_obj", "nnzh_k_obj", "nnzh_fe", "nnzh_k_con",
+        "nnzh_fe_obj")]
 
 
 class PdenlpError(RuntimeError):

@@ -25,6 +25,7 @@ template <int DIM_, int NP_>
 struct FieldIdx {
   static constexpr int DIM = DIM_, NP = NP_;
   static constexpr int NFY = 1, NFU = 1;  // one state field, (at most) one control field
+  static constexpr bool NO_FE_OBJ = false;  // true: NoFETerm objective fk(kappa), no integral (see PoissonParam)
   static constexpr int SY = 0, SG = 1, SU = 1 + DIM_, SK = 2 + DIM_;
   static constexpr int M = 2 + DIM_ + NP_;
 };
@@ -121,6 +122,30 @@ struct KappaPoisson : FieldIdx<DIM_, 2> {
   }
 };
 
+// NoFETerm objective (src/additional_obj_terms.jl:59-106): obj = fk(kappa), not an integral.  The density f is
+// identically zero (so the FE parts of grad!/hprod! vanish), the objective Hessian has NO FE block and its
+// kappa-block is the p x p lower triangle; fk is differentiated by a one-thread kernel (k_nofe).
+// test/problems/poissonparam.jl:35-44: fk = 0.5*dot(k .- 1, k .- 1), res = k1*grad(v).grad(y) - v*f
+template <int DIM_>
+struct PoissonParam : FieldIdx<DIM_, 1> {
+  using I = FieldIdx<DIM_, 1>;
+  static constexpr bool HAS_CONST = false;
+  static constexpr bool NEEDS_COEF_DERIV = false;
+  static constexpr bool FE_DERIVS_POINT_INDEPENDENT = true;
+  static constexpr bool RES_FE_HESSIAN_ZERO = true;
+  static constexpr bool NO_FE_OBJ = true;
+  template <class T> PDENLP_HD static T f(const PointCtx&, const T* s) { return jet_const(0.0, s[0]); }
+  template <class T> PDENLP_HD static T fk(const double*, const T* k) {
+    T d = k[0] - 1.0;
+    return 0.5 * d * d;
+  }
+  template <class T> PDENLP_HD static void res(const PointCtx& c, const T* s, T* R) {
+    R[0] = jet_const(-c.source, s[0]);
+#pragma unroll
+    for (int d = 0; d < DIM_; ++d) R[1 + d] = s[I::SK] * s[I::SG + d];
+  }
+};
+
 // ---- unconstrained problems: objective only, the residual is identically zero (ncon = 0 on the
 // host side; the constraint entry points are never called for these models)
 template <int DIM_>
@@ -173,6 +198,7 @@ struct MFIdx {
   static constexpr int M = SK;
   static constexpr bool HAS_CONST = false;
   static constexpr bool FE_DERIVS_POINT_INDEPENDENT = false;
+  static constexpr bool NO_FE_OBJ = false;
   PDENLP_HD static constexpr int Y(int f) { return f * NB; }
   PDENLP_HD static constexpr int G(int f, int d = 0) { return f * NB + 1 + d; }
   PDENLP_HD static constexpr int U(int g) { return SU + g; }
@@ -247,6 +273,25 @@ struct ToreBrachistochrone : MFIdx<1, 2, 0> {
     return (a * a) * s[X::G(0)] * s[X::G(0)] + w * w * s[X::G(1)] * s[X::G(1)];
   }
   template <class T> PDENLP_HD static void res(const PointCtx&, const T* s, T* R) { X::zero_res(s, R); }
+};
+
+// test/problems/sis.jl:21-34: fields (I, S), objective NoFETerm() = 0; par = (a, b)
+struct Sis : MFIdx<1, 2, 0> {
+  static constexpr bool NEEDS_COEF_DERIV = false;
+  static constexpr bool RES_FE_HESSIAN_ZERO = false;
+  static constexpr bool NO_FE_OBJ = true;
+  using X = MFIdx<1, 2, 0>;
+  template <class T> PDENLP_HD static T f(const PointCtx&, const T* s) { return jet_const(0.0, s[0]); }
+  template <class T> PDENLP_HD static T fk(const double*, const T* k) { return jet_const(0.0, k[0]); }
+  // dt(I,p) + dt(S,q) - p*(a*S*I - b*I) - q*(b*I - a*S*I)
+  template <class T> PDENLP_HD static void res(const PointCtx& c, const T* s, T* R) {
+    const double a = c.par[0], b = c.par[1];
+    const T& I = s[X::Y(0)]; const T& S = s[X::Y(1)];
+    X::zero_res(s, R);
+    const T t = a * S * I - b * I;
+    R[X::Y(0)] = s[X::G(0)] - t;
+    R[X::Y(1)] = s[X::G(1)] + t;
+  }
 };
 
 }  // namespace pdenlp

@@ -1566,6 +1566,35 @@ __device__ __forceinline__ int64_t trap_pos(int64_t i1, int j1, int64_t prows) {
   for (int jj = 1; jj < j1; ++jj) pos += prows - jj + 1;
   return pos + (i1 - j1);
 }
+
+// NoFETerm objective fk(kappa): a p-variable scalar function, differentiated by ONE thread with a
+// Jet2<p> (the reference runs ForwardDiff.gradient / hessian on it, additional_obj_terms.jl:88-106).
+enum NoFeMode { NOFE_OBJ = 0, NOFE_GRAD = 1, NOFE_HESS = 2, NOFE_HPROD = 3 };
+template <class E>
+__global__ void k_nofe(const __grid_constant__ Tables<E> tab, const double* __restrict__ x, int mode, double obj_weight,
+                       const double* __restrict__ v, double* __restrict__ out) {
+  constexpr int NP = E::NP > 0 ? E::NP : 1;
+  using J2 = Jet2<NP>;
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  J2 k[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) jet_seed(k[i], x[i], i);
+  const J2 F = E::Integrand::fk(tab.par, k);
+  if (mode == NOFE_OBJ) {
+    out[0] = F.v;
+  } else if (mode == NOFE_GRAD) {        // out = g (zero-filled by the caller)
+    for (int i = 0; i < E::NP; ++i) out[i] += F.g[i];
+  } else if (mode == NOFE_HESS) {        // out = the p x p lower triangle, i fastest
+    for (int j = 0; j < E::NP; ++j)
+      for (int i = j; i < E::NP; ++i) out[trap_pos(i + 1, j + 1, E::NP)] = obj_weight * F.h[J2::idx(i, j)];
+  } else {                               // out = Hv (kappa rows), v = direction
+    for (int i = 0; i < E::NP; ++i) {
+      double a = 0.0;
+      for (int l = 0; l < E::NP; ++l) a = fma(F.h[J2::idx(i, l)], v[l], a);
+      out[i] += obj_weight * a;
+    }
+  }
+}
 // which: 0 = objective (scaled by obj_weight), 1 = constraints (lambda-weighted residual)
 template <class E>
 __global__ void __launch_bounds__(kThreads)

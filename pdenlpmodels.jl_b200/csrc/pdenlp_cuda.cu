@@ -51,6 +51,8 @@ struct Ops {
   virtual int run_h() const = 0;
   virtual bool needs_coef_deriv() const = 0;  // derivative callbacks read the coefficient fields
   virtual bool res_fe_hessian_zero() const = 0;  // constraint FE Hessian block is structurally zero
+  virtual bool no_fe_obj() const = 0;            // NoFETerm objective fk(kappa)
+  virtual int nofe(const Launch& L, int mode, const double* x, double ow, const double* v, double* out) = 0;
   virtual const std::vector<double>& ktab() const = 0;  // pre-integrated reference tensors (may be empty)
 };
 
@@ -94,6 +96,14 @@ struct OpsImpl : Ops {
   int run_h() const override { return E::RUN_H; }
   bool needs_coef_deriv() const override { return E::Integrand::NEEDS_COEF_DERIV; }
   bool res_fe_hessian_zero() const override { return E::Integrand::RES_FE_HESSIAN_ZERO; }
+  bool no_fe_obj() const override { return E::Integrand::NO_FE_OBJ; }
+  int nofe(const Launch& L, int mode, const double* x, double ow, const double* v, double* out) override {
+    if constexpr (E::Integrand::NO_FE_OBJ) {
+      k_nofe<E><<<1, 32, 0, L.stream>>>(tab, x, mode, ow, v, out);
+      CU(cudaGetLastError());
+    }
+    return PDENLP_OK;
+  }
   static int grid_for(int64_t ntiles, int warps, int cap) {
     int64_t g = (ntiles + warps - 1) / warps;
     return (int)std::max<int64_t>(1, std::min<int64_t>(g, cap));
@@ -226,6 +236,9 @@ Ops* select_ops(const pdenlp_desc& d) {
   CASE(PDENLP_CELL_INCREASE, 1, 2, 2, 1, 0, CellIncrease)
   CASE(PDENLP_DYNAMIC_SIR, 1, 2, 2, 1, 0, DynamicSir)
   CASE(PDENLP_TORE_BRACHISTOCHRONE, 1, 2, 0, 1, 0, ToreBrachistochrone)
+  // NoFETerm objectives
+  CASE(PDENLP_POISSON_PARAM, 2, 4, 0, 4, 1, PoissonParam<2>)
+  CASE(PDENLP_SIS, 1, 2, 0, 1, 0, Sis)
 #undef CASE
   return nullptr;
 }
@@ -242,6 +255,7 @@ struct pdenlp_model {
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
   bool inde = false;
+  bool nofe = false;  // NoFETerm objective
   // owned device memory
   std::vector<void*> owned;
   // scratch
@@ -378,7 +392,9 @@ int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
   m->ops = ops;
   m->device = dev;
   m->sms = prop.multiProcessorCount;
-  m->inde = desc->integrand == PDENLP_KAPPA_POISSON;  // MixedEnergyFETerm(..., inde = true)
+  m->nofe = ops->no_fe_obj();
+  // MixedEnergyFETerm(..., inde = true) and NoFETerm: objective kappa-block = p x p lower triangle
+  m->inde = desc->integrand == PDENLP_KAPPA_POISSON || m->nofe;
   int rc = PDENLP_OK;
   auto bail = [&](int code) { pdenlp_destroy(m); cudaSetDevice(prev); return code; };
 
@@ -489,7 +505,8 @@ int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
     I.nnzh_fe = b2[nt];
     I.nnzh_k_obj = p == 0 ? 0 : (m->inde ? p * (p + 1) / 2 : p * (p + 1) / 2 + (n - p) * p);
     I.nnzh_k_con = p == 0 ? 0 : p * (p + 1) / 2 + (n - p) * p;
-    I.nnzh_obj = I.nnzh_k_obj + I.nnzh_fe;
+    I.nnzh_fe_obj = m->nofe ? 0 : I.nnzh_fe;
+    I.nnzh_obj = I.nnzh_k_obj + I.nnzh_fe_obj;
     I.nnzh = I.nnzh_obj + I.nnzh_k_con + I.nnzh_fe;
   }
   m->npartials = m->sms * 8;
@@ -553,16 +570,21 @@ int pdenlp_host_free(void* ptr) { CU(cudaFreeHost(ptr)); return PDENLP_OK; }
 
 int pdenlp_obj(pdenlp_model* m, const double* x, double* f) {
   if (!m || !x || !f) return fail(PDENLP_EINVAL, "null argument");
-  if (!m->dm.coef) return fail(PDENLP_EINVAL, "obj needs the coefficient fields (desc.coef)");
+  if (!m->nofe && !m->dm.coef) return fail(PDENLP_EINVAL, "obj needs the coefficient fields (desc.coef)");
   Scope sc(m);
   const double* dx;
   if (int rc = in_ptr(m, x, m->info.nvar, &m->sx, &dx)) return rc;
   Launch L{m->stream, m->sms};
-  int nb = 0;
-  if (int rc = m->ops->vec(L, m->dm, OP_OBJ, dx, nullptr, nullptr, 1.0, nullptr, m->partials, &nb)) return rc;
-  k_sum_partials<<<1, 256, 0, m->stream>>>(m->partials, nb, m->scalar);
-  CU(cudaGetLastError());
-  m->launches += 2;
+  if (m->nofe) {  // _obj_integral(::NoFETerm, kappa, x) = f(kappa)
+    if (int rc = m->ops->nofe(L, NOFE_OBJ, dx, 1.0, nullptr, m->scalar)) return rc;
+    m->launches += 1;
+  } else {
+    int nb = 0;
+    if (int rc = m->ops->vec(L, m->dm, OP_OBJ, dx, nullptr, nullptr, 1.0, nullptr, m->partials, &nb)) return rc;
+    k_sum_partials<<<1, 256, 0, m->stream>>>(m->partials, nb, m->scalar);
+    CU(cudaGetLastError());
+    m->launches += 2;
+  }
   CU(cudaMemcpyAsync(f, m->scalar, 8, cudaMemcpyDeviceToHost, m->stream));
   CU(cudaStreamSynchronize(m->stream));
   return PDENLP_OK;
@@ -582,13 +604,21 @@ static int vec_call(pdenlp_model* m, int op, const double* x, const double* lam,
   CU(cudaMemsetAsync(dout, 0, (size_t)nout * 8, m->stream));  // assemble_vector!/coo_prod! zero-fill first
   Launch L{m->stream, m->sms};
   int nb = 0;
-  if (int rc = m->ops->vec(L, m->dm, op, dx, dl, dv, ow, dout, m->partials, &nb)) return rc;
-  m->launches += 1;
+  // NoFETerm objective: the FE part of grad! is zero (additional_obj_terms.jl:82), hprod! keeps its constraint part
+  const bool skip_fe = m->nofe && (op == OP_GRAD || (op == OP_HPROD && dl == nullptr));
+  if (!skip_fe) {
+    if (int rc = m->ops->vec(L, m->dm, op, dx, dl, dv, ow, dout, m->partials, &nb)) return rc;
+    m->launches += 1;
+  }
+  if (m->nofe && m->d.nparam > 0 && (op == OP_GRAD || op == OP_HPROD)) {
+    if (int rc = m->ops->nofe(L, op == OP_GRAD ? NOFE_GRAD : NOFE_HPROD, dx, ow, dv, dout)) return rc;
+    m->launches += 1;
+  }
   return out_finish(m, out, nout);
 }
 
 int pdenlp_grad(pdenlp_model* m, const double* x, double* g) {
-  return vec_call(m, OP_GRAD, x, nullptr, nullptr, 0, 1.0, g, m ? m->info.nvar : 0, true);
+  return vec_call(m, OP_GRAD, x, nullptr, nullptr, 0, 1.0, g, m ? m->info.nvar : 0, m && !m->nofe);
 }
 int pdenlp_cons(pdenlp_model* m, const double* x, double* c) {
   return vec_call(m, OP_CONS, x, nullptr, nullptr, 0, 1.0, c, m ? m->info.ncon : 0, true);
@@ -641,13 +671,17 @@ int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda, do
   const pdenlp_info& I = m->info;
   double* vko = dv;
   double* vfo = vko + I.nnzh_k_obj;
-  double* vkc = vfo + I.nnzh_fe;
+  double* vkc = vfo + I.nnzh_fe_obj;
   double* vfc = vkc + I.nnzh_k_con;
   if (I.nnzh_k_obj + I.nnzh_k_con > 0) {
     if (!m->dm.coef) return fail(PDENLP_EINVAL, "the kappa blocks need the coefficient fields (desc.coef)");
     CU(cudaMemsetAsync(vko, 0, (size_t)I.nnzh_k_obj * 8, m->stream));
     CU(cudaMemsetAsync(vkc, 0, (size_t)I.nnzh_k_con * 8, m->stream));
-    if (int rc = m->ops->hess_kappa(L, m->dm, dx, nullptr, obj_weight, 0, m->inde ? m->d.nparam : I.nvar, vko)) return rc;
+    if (m->nofe) {
+      if (int rc = m->ops->nofe(L, NOFE_HESS, dx, obj_weight, nullptr, vko)) return rc;
+    } else {
+      if (int rc = m->ops->hess_kappa(L, m->dm, dx, nullptr, obj_weight, 0, m->inde ? m->d.nparam : I.nvar, vko)) return rc;
+    }
     m->launches += 1;
     if (dl) {
       if (int rc = m->ops->hess_kappa(L, m->dm, dx, dl, 1.0, 1, I.nvar, vkc)) return rc;
@@ -662,8 +696,12 @@ int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda, do
   if (cons_zero) {
     if (int rc = zero_fill(m, vfc, I.nnzh_fe)) return rc;
   }
-  if (int rc = m->ops->hess(L, m->dm, dx, dl, obj_weight, vfo, cons_zero ? nullptr : vfc)) return rc;
-  m->launches += 1;
+  double* vo = m->nofe ? nullptr : vfo;  // NoFETerm: the objective has no FE block
+  double* vc = cons_zero ? nullptr : vfc;
+  if (vo || vc) {
+    if (int rc = m->ops->hess(L, m->dm, dx, dl, obj_weight, vo, vc)) return rc;
+    m->launches += 1;
+  }
   return out_finish(m, vals, I.nnzh);
 }
 
@@ -682,11 +720,17 @@ int pdenlp_hess_coord_obj(pdenlp_model* m, const double* x, double obj_weight, d
   if (I.nnzh_k_obj > 0) {
     if (!m->dm.coef) return fail(PDENLP_EINVAL, "the kappa blocks need the coefficient fields (desc.coef)");
     CU(cudaMemsetAsync(dv, 0, (size_t)I.nnzh_k_obj * 8, m->stream));
-    if (int rc = m->ops->hess_kappa(L, m->dm, dx, nullptr, obj_weight, 0, m->inde ? m->d.nparam : I.nvar, dv)) return rc;
+    if (m->nofe) {
+      if (int rc = m->ops->nofe(L, NOFE_HESS, dx, obj_weight, nullptr, dv)) return rc;
+    } else {
+      if (int rc = m->ops->hess_kappa(L, m->dm, dx, nullptr, obj_weight, 0, m->inde ? m->d.nparam : I.nvar, dv)) return rc;
+    }
     m->launches += 1;
   }
-  if (int rc = m->ops->hess(L, m->dm, dx, nullptr, obj_weight, dv + I.nnzh_k_obj, nullptr)) return rc;
-  m->launches += 1;
+  if (!m->nofe) {
+    if (int rc = m->ops->hess(L, m->dm, dx, nullptr, obj_weight, dv + I.nnzh_k_obj, nullptr)) return rc;
+    m->launches += 1;
+  }
   return out_finish(m, vals, I.nnzh_obj);
 }
 
@@ -731,9 +775,9 @@ static int structure_call(pdenlp_model* m, bool hess, int64_t* rows, int64_t* co
     r.clear(); c.clear();
     trapezoid(n, r, c);
     if (!rc) rc = put(I.nnzh_obj, r, c);
-    if (!rc) rc = m->ops->structure(L, m->dm, 2, dr + I.nnzh_k_obj, dc + I.nnzh_k_obj, p);
+    if (!rc && !m->nofe) rc = m->ops->structure(L, m->dm, 2, dr + I.nnzh_k_obj, dc + I.nnzh_k_obj, p);
     if (!rc) rc = m->ops->structure(L, m->dm, 2, dr + I.nnzh_obj + I.nnzh_k_con, dc + I.nnzh_obj + I.nnzh_k_con, p);
-    m->launches += 2;
+    m->launches += m->nofe ? 1 : 2;
   }
   if (host) {
     if (!rc) {

@@ -224,10 +224,13 @@ def hess_structure(fm: FlatModel):
     /root/reference/src/hessian_struct_nnzh_functions.jl:10-130,
     src/fill_matrix_hessian_functions.jl:96-209."""
     p = fm.nparam
-    inde = fm.spec.integrand == KAPPA_POISSON
+    nofe = getattr(fm.spec, "no_fe_obj", False)  # NoFETerm: no objective FE block (hessian_struct_nnzh_functions.jl:41-43)
+    inde = fm.spec.integrand == KAPPA_POISSON or nofe
     rk, ck = _trapezoid(p if inde else fm.nvar, p)
     rf, cf = _hess_fe_structure(fm)
     rkc, ckc = _trapezoid(fm.nvar, p)
+    if nofe:
+        return np.concatenate([rk, rkc, rf + p]), np.concatenate([ck, ckc, cf + p]), rk.size
     rows = np.concatenate([rk, rf + p, rkc, rf + p])
     cols = np.concatenate([ck, cf + p, ckc, cf + p])
     return rows, cols, rk.size + rf.size

@@ -29,6 +29,8 @@ CONTROL_SIR = 8
 CELL_INCREASE = 9
 DYNAMIC_SIR = 10
 TORE_BRACHISTOCHRONE = 11
+POISSON_PARAM = 12
+SIS = 13
 
 INTEGRAND_NAMES = {
     MEMBRANE: "membrane",
@@ -42,6 +44,8 @@ INTEGRAND_NAMES = {
     CELL_INCREASE: "cell_increase",
     DYNAMIC_SIR: "dynamic_sir",
     TORE_BRACHISTOCHRONE: "tore_brachistochrone",
+    POISSON_PARAM: "poisson_param",
+    SIS: "sis",
 }
 
 
@@ -64,6 +68,9 @@ class ProblemSpec:
     # True: no constraint at all (the reference's unconstrained constructor,
     # src/additional_constructors.jl:1-66): ncon = 0, nnzj = 0, nnzh = nnzh_obj
     unconstrained: bool = False
+    # True: the objective is a NoFETerm, f(kappa) without any integral (src/additional_obj_terms.jl:59-106):
+    # no FE block in the objective Hessian, kappa-block p x p lower triangle, zero FE gradient
+    no_fe_obj: bool = False
 
     @property
     def nvar(self) -> int:
@@ -91,6 +98,7 @@ class MFProblemSpec:
     unconstrained: bool = False
     nparam: int = 0
     affine: bool = False
+    no_fe_obj: bool = False
     is_multifield: bool = True
 
     @property
@@ -206,6 +214,18 @@ def poissonmixed(n: int = 3, dim: int = 2, control: bool = False) -> ProblemSpec
     )
 
 
+def poissonparam(n: int = 3) -> ProblemSpec:
+    """test/problems/poissonparam.jl:14-46: one algebraic unknown, objective NoFETerm(0.5*|k - 1|^2),
+    res = k1*grad(v).grad(y) - v*f, Dirichlet data = the manufactured solution (Q1, degree 2)."""
+    model = CartesianDiscreteModel((0, 1, 0, 1), (n, n))
+    sol = lambda X: np.sin(2 * np.pi * X[:, 0]) * X[:, 1]
+    Ypde = LagrangianFESpace(model, 1, "H1", "boundary", sol)
+    return ProblemSpec(
+        name="poissonparam", integrand=POISSON_PARAM, model=model, Ypde=Ypde, Ycon=None, degree=2, nparam=1,
+        source=lambda X: (2 * np.pi ** 2) * np.sin(2 * np.pi * X[:, 0]) * X[:, 1], no_fe_obj=True,
+    )
+
+
 def penalizedpoisson(n: int = 16) -> ProblemSpec:
     """test/problems/penalizedpoisson.jl:14-42: min 0.5*int |grad y|^2 - w*y, y = 0 on the boundary
     (Q1, degree 2, unconstrained; w = 1)."""
@@ -240,6 +260,14 @@ def controlsir(n: int = 10, x0=(1.0, 2.0), a: float = 0.2, b: float = 0.1, mu: f
     model = CartesianDiscreteModel((0, T), n)
     return MFProblemSpec(name="controlsir", integrand=CONTROL_SIR, model=model, Yfields=_ode_state_fields(model, x0),
                          Ufields=[], degree=1, params=(a, b, mu))
+
+
+def sis(n: int = 10, x0=(1.0, 2.0), a: float = 0.2, b: float = 0.7, T: float = 1.0) -> MFProblemSpec:
+    """test/problems/sis.jl:1-35: SIS ODE system on the two fields (I, S), objective NoFETerm() = 0, no control;
+    params = (a, b)."""
+    model = CartesianDiscreteModel((0, T), n)
+    return MFProblemSpec(name="sis", integrand=SIS, model=model, Yfields=_ode_state_fields(model, x0),
+                         Ufields=[], degree=1, params=(a, b), no_fe_obj=True)
 
 
 def cellincrease(n: int = 10, x0=(0.6, 0.1), T: float = 7.0) -> MFProblemSpec:

@@ -40,12 +40,15 @@ def _cases(pkg):
         "cellincrease_45": lambda: pkg.cellincrease(45),
         "dynamicsir_100": lambda: pkg.dynamicsir(100),
         "dynamicsir_5": lambda: pkg.dynamicsir(5),
+        # NoFETerm objectives: no objective FE block in the Hessian
+        "poissonparam_24": lambda: pkg.poissonparam(24),
+        "sis_80": lambda: pkg.sis(80),
     }
 
 
 CASE_NAMES = ["membrane3", "membrane8", "membrane37", "membrane100", "pb_l2_9", "pb_h1_33", "burger_lin_70",
               "burger_nl_70", "kappa2d_5", "kappa2d_u_6", "kappa3d_u_4",
-              "controlsir_70", "cellincrease_45", "dynamicsir_100", "dynamicsir_5"]
+              "controlsir_70", "cellincrease_45", "dynamicsir_100", "dynamicsir_5", "poissonparam_24", "sis_80"]
 
 
 @pytest.fixture(scope="module", params=CASE_NAMES)
@@ -160,7 +163,10 @@ def test_unaligned_guarded_outputs(case):
             assert view.data_ptr() % 16 == (8 * off) % 16
             call(view)
             torch.cuda.synchronize()
-            assert torch.equal(view, ref)
+            if case["spec"].nparam == 0:
+                assert torch.equal(view, ref)
+            else:  # the dense kappa blocks are accumulated with atomics: equal up to summation order
+                assert torch.allclose(view, ref, rtol=1e-12, atol=1e-13 * float(ref.abs().max()))
             assert torch.isnan(big[:off]).all() and torch.isnan(big[off + n:]).all()
 
 

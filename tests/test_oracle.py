@@ -28,6 +28,9 @@ CASES = {
     "cellincrease_5": lambda p: p.cellincrease(5),
     "dynamicsir_6": lambda p: p.dynamicsir(6),
     "torebrachistochrone_4": lambda p: p.torebrachistochrone(4),
+    # NoFETerm objectives
+    "poissonparam_3": lambda p: p.poissonparam(3),
+    "sis_6": lambda p: p.sis(6),
 }
 
 
@@ -220,3 +223,41 @@ def test_multifield_layout(pkg):
     ys, us = F._field_ids(fm)
     assert ys[1][ys[1] > 0].min() == fm.field_nfree[0] + 1
     assert us[0][us[0] > 0].min() == fm.ncon + 1
+
+
+def test_poissonparam_known_answers(pkg, oracle_mod):
+    """poissonparam_test (test/problems/poissonparam.jl:48-83): obj(x0) == 0.5, obj(x1) == 0,
+    grad(x0) == [-1, 0...], hess == LowerTriangular([1 0; 0 0]) at both points, nnzh_obj = 1."""
+    spec = pkg.poissonparam(5)
+    o = oracle_mod.Oracle(spec)
+    n = spec.Ypde.nfree
+    assert spec.nparam == 1 and o.nvar == n + 1 and o.ncon == n and o.nnzh_obj == 1
+    x0 = np.zeros(n + 1); x1 = np.concatenate([[1.0], np.random.default_rng(0).uniform(0, 1, n)])
+    assert o.obj(x0) == 0.5 and o.obj(x1) == 0.0
+    assert np.array_equal(o.grad(x0), np.concatenate([[-1.0], np.zeros(n)])) and np.all(o.grad(x1) == 0.0)
+    r, c = o.hess_structure()
+    assert (r[0], c[0]) == (1, 1)
+    for x in (x0, x1):
+        h = o.hess_coord(x, None, 1.0)
+        assert h[0] == 1.0 and np.all(h[1:] == 0.0)
+    assert np.all(o.hprod(x1, np.zeros(n + 1), None, 1.0) == 0.0)
+    vr = np.random.default_rng(1).uniform(0, 1, n + 1)
+    assert np.array_equal(o.hprod(x1, vr, None, 1.0), np.concatenate([[vr[0]], np.zeros(n)]))
+
+
+def test_sis_residual_against_hand_discretisation(pkg, oracle_mod):
+    """sis_test (test/problems/sis.jl:37-50): with P1 elements and the midpoint rule the residual of the
+    (I, S) system is the hand-written c(x) = A x + A0 - F(x) integrated with the hat functions; here the
+    cheap invariants: obj == 0, grad == 0, and rows of I and S sum to zero reaction terms (S + I conserved)."""
+    n, a, b = 10, 0.2, 0.7
+    spec = pkg.sis(n, a=a, b=b)
+    o = oracle_mod.Oracle(spec)
+    x = np.random.default_rng(3).uniform(0.5, 1.5, o.nvar)
+    assert o.obj(x) == 0.0 and np.all(o.grad(x) == 0.0) and o.nnzh_obj == 0
+    c = o.cons(x)
+    # adding the I-equation and the S-equation of one node cancels the reaction term: what is left is
+    # the weak time derivative of (I + S), which vanishes for a constant total population
+    xc = np.concatenate([np.full(n, 1.0), np.full(n, 2.0)])  # I = x0[1], S = x0[2] everywhere
+    cc = o.cons(xc)
+    assert np.allclose(cc[:n] + cc[n:], 0.0, atol=1e-15)
+    assert c.shape == (2 * n,)
