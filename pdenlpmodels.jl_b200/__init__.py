@@ -11,15 +11,17 @@ Layout (only what the hot path needs):
   cartesian.py  stand-in for Gridap's host-side setup (mesh, spaces, numbering)
   flatten.py    flattening layer: FE objects -> pdenlp_desc arrays + COO structure
   problems.py   the closed set of named integrands / BASELINE configs
+  bounds.py     bounds_functions_to_vectors (lvar / uvar from functions or vectors)
   sharded.py    cell-slab partition over one process per GPU
 """
-from . import cartesian, problems, flatten  # noqa: F401
+from . import cartesian, problems, flatten, bounds  # noqa: F401
+from .bounds import bounds_functions_to_vectors  # noqa: F401
 from .problems import (  # noqa: F401
     controlelasticmembrane, poissonboltzman2d, burger1d, burger1d_param, poissonmixed, penalizedpoisson,
     basicunconstrained, controlsir, cellincrease, dynamicsir, torebrachistochrone, poissonparam, sis, BASELINE_CONFIGS,
 )
 
-__all__ = ["cartesian", "problems", "flatten"]
+__all__ = ["cartesian", "problems", "flatten", "bounds"]
 
 
 def __getattr__(name):

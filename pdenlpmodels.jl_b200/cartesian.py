@@ -388,13 +388,12 @@ class LagrangianFESpace:
 
     def interpolate_cellwise_constant(self, cell_values: np.ndarray) -> np.ndarray:
         """Free values of ``interpolate(cell_l, V)`` for a cell-wise constant
-        field: the last cell touching a dof wins (used only by the numbering
-        pins, /root/reference/src/bounds_function.jl:196-201)."""
+        field: the last cell touching a dof wins (bounds.py and the numbering
+        pins; /root/reference/src/bounds_function.jl:196-201)."""
         out = np.zeros(self.nfree)
         ids = self.cell_dof_ids
-        for c in range(ids.shape[0]):
-            for a in range(ids.shape[1]):
-                g = ids[c, a]
-                if g > 0:
-                    out[g - 1] = cell_values[c]
+        vals = np.broadcast_to(np.asarray(cell_values, dtype=np.float64)[:, None], ids.shape)
+        free = ids > 0
+        # cell-major order; for a repeated index NumPy keeps the LAST assigned value = the last cell
+        out[ids[free] - 1] = vals[free]
         return out

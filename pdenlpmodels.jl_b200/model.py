@@ -27,12 +27,7 @@ from .flatten import jac_structure as _host_jac_structure  # noqa: F401
 from .problems import ProblemSpec
 
 
-class DimensionError(Exception):
-    """NLPModels.DimensionError(name, dim_expected, dim_found)."""
-
-    def __init__(self, name, dim_expected, dim_found):
-        super().__init__(f"DimensionError: Input {name} should have length {dim_expected} not {dim_found}")
-        self.name, self.dim_expected, self.dim_found = name, dim_expected, dim_found
+from .model_errors import DimensionError  # noqa: E402,F401  (NLPModels.DimensionError)
 
 
 _COUNTERS = (
@@ -106,7 +101,8 @@ class GridapPDENLPModel:
     """
 
     def __init__(self, spec: ProblemSpec, device: str = "cuda:0", cell_range=None, memspace: str = "device",
-                 with_coef: bool = True, flat: Optional[FlatModel] = None):
+                 with_coef: bool = True, flat: Optional[FlatModel] = None, x0=None, lvar=None, uvar=None,
+                 lvary=None, uvary=None, lvaru=None, uvaru=None, lvark=None, uvark=None):
         self.spec = spec
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -142,9 +138,13 @@ class GridapPDENLPModel:
             # the reference's unconstrained constructor (src/additional_constructors.jl:1-66): no operator,
             # ncon = 0, empty Jacobian, Hessian = objective segment only
             ncon, nnzj, nnzh, lin_nnzj, nln_nnzj, nlin, nnln = 0, 0, I.nnzh_obj, 0, 0, 0, 0
+        lvar, uvar = self._bounds(spec, fm, I.nvar, lvar, uvar, lvary, uvary, lvaru, uvaru, lvark, uvark)
+        x0 = np.zeros(I.nvar) if x0 is None else np.asarray(x0, dtype=np.float64)
+        if x0.shape != (I.nvar,):
+            raise DimensionError("x0", I.nvar, x0.shape[0] if x0.ndim == 1 else tuple(x0.shape))
         self.meta = NLPModelMeta(
             nvar=I.nvar, ncon=ncon, nnzj=nnzj, nnzh=nnzh, lin_nnzj=lin_nnzj, nln_nnzj=nln_nnzj, nlin=nlin, nnln=nnln,
-            name=spec.name, x0=np.zeros(I.nvar), lvar=np.full(I.nvar, -np.inf), uvar=np.full(I.nvar, np.inf),
+            name=spec.name, x0=x0, lvar=lvar, uvar=uvar,
             lcon=np.zeros(ncon), ucon=np.zeros(ncon), y0=np.zeros(ncon),
         )
         self.pdemeta = PDENLPMeta(
@@ -153,6 +153,39 @@ class GridapPDENLPModel:
         )
         self.counters = Counters()
         self._use_current_stream()
+
+    @staticmethod
+    def _bounds(spec, fm, nvar, lvar, uvar, lvary, uvary, lvaru, uvaru, lvark, uvark):
+        """lvar / uvar as the constrained constructor builds them (src/additional_constructors.jl:178-204):
+        whole vectors, or [kappa bounds ; bounds_functions_to_vectors(y and u bounds as functions or vectors)];
+        the default is unbounded."""
+        p = fm.nparam
+        if lvar is not None or uvar is not None:
+            lvar = np.full(nvar, -np.inf) if lvar is None else np.asarray(lvar, dtype=np.float64)
+            uvar = np.full(nvar, np.inf) if uvar is None else np.asarray(uvar, dtype=np.float64)
+            for name, v in (("lvar", lvar), ("uvar", uvar)):
+                if v.shape != (nvar,):
+                    raise DimensionError(name, nvar, v.shape[0] if v.ndim == 1 else tuple(v.shape))
+            return lvar, uvar
+        if all(b is None for b in (lvary, uvary, lvaru, uvaru, lvark, uvark)):
+            return np.full(nvar, -np.inf), np.full(nvar, np.inf)
+        from .bounds import bounds_functions_to_vectors
+        if getattr(spec, "is_multifield", False):
+            Ypde, Ycon = list(spec.Yfields), (list(spec.Ufields) or None)
+        else:
+            Ypde, Ycon = spec.Ypde, spec.Ycon
+        ny, nu = fm.nfree_y, fm.nfree_u
+        lvary = np.full(ny, -np.inf) if lvary is None else lvary
+        uvary = np.full(ny, np.inf) if uvary is None else uvary
+        lvaru = np.full(nu, -np.inf) if lvaru is None else lvaru
+        uvaru = np.full(nu, np.inf) if uvaru is None else uvaru
+        lyu, uyu = bounds_functions_to_vectors(Ycon, Ypde, spec.model, lvary, uvary, lvaru, uvaru)
+        lk = np.full(p, -np.inf) if lvark is None else np.asarray(lvark, dtype=np.float64)
+        uk = np.full(p, np.inf) if uvark is None else np.asarray(uvark, dtype=np.float64)
+        for name, v in (("lvark", lk), ("uvark", uk)):
+            if v.shape != (p,):
+                raise DimensionError(name, p, v.shape[0] if v.ndim == 1 else tuple(v.shape))
+        return np.concatenate([lk, lyu]), np.concatenate([uk, uyu])
 
     # ------------------------------------------------------------------ plumbing
     def _use_current_stream(self):

@@ -107,3 +107,26 @@ def test_views_are_accepted(nlp):
     assert nlp.handle.calls[-1][0] == "grad"
     t = torch.zeros(82, dtype=torch.float64)[::2]
     nlp.grad_(t, torch.zeros(41, dtype=torch.float64))
+
+
+def test_constructor_bounds_and_x0(monkeypatch, pkg):
+    """src/additional_constructors.jl:178-204: bounds on y / u as functions or vectors, kappa bounds in front."""
+    monkeypatch.setattr(capi, "Handle", FakeHandle)
+    monkeypatch.setattr(M.GridapPDENLPModel, "_use_current_stream", lambda self: None)
+    spec = pkg.controlelasticmembrane(3)
+    umin = lambda X: X[:, 0] + X[:, 1]
+    umax = lambda X: X[:, 0] ** 2 + X[:, 1] ** 2 + 10.0
+    nlp = M.GridapPDENLPModel(spec, device="cuda:0", memspace="host", lvaru=umin, uvaru=umax, x0=np.ones(41))
+    ny = spec.Ypde.nfree
+    assert np.all(np.isinf(nlp.meta.lvar[:ny])) and np.all(np.isinf(nlp.meta.uvar[:ny]))
+    assert np.all(np.isfinite(nlp.meta.lvar[ny:])) and np.all(nlp.meta.lvar[ny:] <= nlp.meta.uvar[ny:])
+    assert np.array_equal(nlp.meta.x0, np.ones(41))
+    nlp2 = M.GridapPDENLPModel(spec, device="cuda:0", memspace="host", lvar=-np.ones(41), uvar=np.ones(41))
+    assert np.array_equal(nlp2.meta.lvar, -np.ones(41)) and np.array_equal(nlp2.meta.uvar, np.ones(41))
+    with pytest.raises(M.DimensionError):
+        M.GridapPDENLPModel(spec, device="cuda:0", memspace="host", lvar=np.zeros(40))
+    with pytest.raises(M.DimensionError):
+        M.GridapPDENLPModel(spec, device="cuda:0", memspace="host", x0=np.zeros(40))
+    spec_k = pkg.burger1d_param(5)
+    nlp3 = M.GridapPDENLPModel(spec_k, device="cuda:0", memspace="host", lvark=[0.0], uvark=[2.0])
+    assert nlp3.meta.lvar[0] == 0.0 and nlp3.meta.uvar[0] == 2.0 and np.isinf(nlp3.meta.lvar[1:]).all()

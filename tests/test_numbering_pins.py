@@ -6,6 +6,7 @@ Q2 Dirichlet-boundary state space and a Q1 control space and checks
 free-dof order.  They hold for our host-side generator.
 """
 import numpy as np
+import pytest
 
 from pdenlp_b200.cartesian import CartesianDiscreteModel, LagrangianFESpace
 from pdenlp_b200 import flatten as F
@@ -97,3 +98,48 @@ def test_l2_control_numbering(pkg):
     spec = pkg.poissonboltzman2d(3)
     assert spec.Ycon.nfree == 9 * 4
     assert spec.Ycon.cell_dof_ids[2].tolist() == [9, 10, 11, 12]
+
+
+def test_bounds_functions_to_vectors_reference_vectors(pkg):
+    """test/unit-test.jl:755-879 "Functions used to create bounds in constructors": the reference's own
+    expected lvar / uvar (cell-midpoint sampling + last-cell-wins interpolation on the Gridap numbering)."""
+    from pdenlp_b200.bounds import bounds_functions_to_vectors
+    from pdenlp_b200.cartesian import CartesianDiscreteModel, LagrangianFESpace
+    from pdenlp_b200.model_errors import DimensionError
+    model = CartesianDiscreteModel((-1, 1, -1, 1), (2, 2))
+    Ypde = LagrangianFESpace(model, 2, "H1", "boundary", 0.0)
+    Ycon = LagrangianFESpace(model, 1, "H1")
+    assert Ypde.nfree == 9 and Ycon.nfree == 9
+    inf9 = np.full(9, np.inf)
+    umin = lambda X: X[:, 0] + X[:, 1]
+    umax = lambda X: X[:, 0] ** 2 + X[:, 1] ** 2
+    exp_y = np.array([1.0, 0.0, 0.0, 1.0, 1.0, -1.0, 0.0, 0.0, 1.0])
+    exp_u = np.array([-1.0, 0.0, 0.0, 0.0, 1.0, 1.0, 0.0, 1.0, 1.0])
+    for T in (np.float16, np.float32, np.float64):
+        # Example 0 / 0bis: vectors
+        l, u = bounds_functions_to_vectors(Ycon, Ypde, model, -inf9, inf9, -inf9, inf9, dtype=T)
+        assert np.array_equal(l, -np.inf * np.ones(18)) and np.array_equal(u, np.inf * np.ones(18)) and l.dtype == T
+        l, u = bounds_functions_to_vectors(None, Ypde, model, -inf9, inf9, [], [], dtype=T)
+        assert np.array_equal(l, -inf9) and np.array_equal(u, inf9) and u.dtype == T
+        # Example 1: state bounds as vectors, control bounds as functions
+        l, u = bounds_functions_to_vectors(Ycon, Ypde, model, -inf9, inf9, umin, umax, dtype=T)
+        assert np.array_equal(l, np.concatenate([-inf9, exp_u])) and np.array_equal(u, np.concatenate([inf9, 0.5 * np.ones(9)]))
+        # Example 1bis: VoidFESpace control, state bounds as functions
+        l, u = bounds_functions_to_vectors(None, Ypde, model, umin, umax, None, None, dtype=T)
+        assert np.array_equal(l, exp_y) and np.array_equal(u, 0.5 * np.ones(9)) and l.dtype == T
+        # Example 2: everything as (vector-valued) functions
+        vmin = lambda X: umin(X)[:, None]
+        vmax = lambda X: umax(X)[:, None]
+        l, u = bounds_functions_to_vectors(Ycon, Ypde, model, vmin, vmax, vmin, vmax, dtype=T)
+        assert np.array_equal(l, np.concatenate([exp_y, exp_u])) and np.array_equal(u, 0.5 * np.ones(18))
+    with pytest.raises(DimensionError):
+        bounds_functions_to_vectors(Ycon, Ypde, model, -np.ones(8), inf9, -inf9, inf9)
+    # multi-field spaces: one column per field
+    m1 = CartesianDiscreteModel((0, 1), 4)
+    fields = [LagrangianFESpace(m1, 1, "H1", [1], 1.0), LagrangianFESpace(m1, 1, "H1", [1], 2.0)]
+    lo = lambda X: np.stack([X[:, 0], -X[:, 0]], axis=1)
+    hi = lambda X: np.stack([X[:, 0] + 1, 1 - X[:, 0]], axis=1)
+    l, u = bounds_functions_to_vectors(None, fields, m1, lo, hi)
+    mids = np.array([0.125, 0.375, 0.625, 0.875])  # free dofs = nodes 2..5, last cell wins
+    assert np.allclose(l, np.concatenate([mids[[1, 2, 3, 3]], -mids[[1, 2, 3, 3]]]))
+    assert np.allclose(u, np.concatenate([mids[[1, 2, 3, 3]] + 1, 1 - mids[[1, 2, 3, 3]]]))
