@@ -134,3 +134,53 @@ def test_burger1d_1M_operator_path(pkg, cuda_lib):
     Jv_coo = torch.zeros(ncon, dtype=torch.float64, device="cuda").index_add_(0, r - 1, vals * v[c - 1])
     assert float((Jv_coo - Jv).abs().max()) <= 1e-12 * float(Jv.abs().max())
     nlp.close()
+
+
+def test_kappa_poisson3d_128_slabs_and_identities(pkg, cuda_lib, oracle_mod):
+    """config 5 (kappa + 3-D Q1 control, 128^3 cells, nq = 8): FE segments of a cell slab against the
+    oracle, kappa blocks through linearity in lambda / adjoint identities, sizes from the closed forms."""
+    from pdenlp_b200.model import GridapPDENLPModel
+    n = 128
+    spec = pkg.poissonmixed(n, dim=3, control=True)
+    nlp = GridapPDENLPModel(spec, device="cuda:0")
+    nvar, ncon, p = nlp.meta.nvar, nlp.meta.ncon, 2
+    assert ncon == (n - 1) ** 3 and nvar == p + (n - 1) ** 3 + (n + 1) ** 3
+    assert nlp.pdemeta.nnzj_k == ncon * p and nlp.pdemeta.nnzh_k_obj == 3 and nlp.pdemeta.nnzh_k_con == 3 + (nvar - p) * p
+    rng = np.random.default_rng(1998)
+    xh = rng.uniform(-1, 1, nvar); xh[:p] = 1 + 0.1 * rng.uniform(-1, 1, p)
+    lh = rng.uniform(-1, 1, ncon)
+    x, lam = torch.from_numpy(xh).cuda(), torch.from_numpy(lh).cuda()
+    jv = nlp.jac_coord(x); hv = nlp.hess_coord(x, lam, obj_weight=0.37)
+    # a slab of 2 mesh planes from the middle against the oracle (FE segments are cell-major)
+    c0 = (n // 2) * n * n; c1 = c0 + 2 * n * n
+    o = oracle_mod.Oracle(spec, (c0, c1))
+    full = nlp.handle  # noqa: F841  (offsets of the slab inside the global segments come from a second handle)
+    head = GridapPDENLPModel(spec, device="cuda:0", cell_range=(0, c0), with_coef=False)
+    oy, ou, oh = head.pdemeta.nnzj_y, head.pdemeta.nnzj_u, head.pdemeta.nnzh_fe
+    head.close()
+    jo = o.jac_coord(xh); ho = o.hess_coord(xh, lh, 0.37)
+    pm = nlp.pdemeta
+    a = pm.nnzj_k + oy
+    assert _rel(jv[a: a + o.nnzj_y].cpu().numpy(), jo[o.nnzj_k: o.nnzj_k + o.nnzj_y]) <= RTOL
+    a = pm.nnzj_k + pm.nnzj_y + ou
+    assert _rel(jv[a: a + o.nnzj_u].cpu().numpy(), jo[o.nnzj_k + o.nnzj_y:]) <= RTOL
+    a = pm.nnzh_k_obj + oh
+    assert _rel(hv[a: a + o.nnzh_fe].cpu().numpy(), ho[o.nnzh_k_obj: o.nnzh_k_obj + o.nnzh_fe]) <= RTOL
+    a = pm.nnzh_obj + pm.nnzh_k_con + oh
+    assert torch.all(hv[a: a + o.nnzh_fe] == 0)  # k1*grad(v).grad(y) - v*f*k2 - v*u: affine in (y, u)
+    assert np.all(ho[o.nnzh_obj + o.nnzh_k_con:] == 0)
+    # kappa blocks: <w, J v> = <J^T w, v> with v exciting the kappa columns, symmetry of H
+    v = torch.from_numpy(rng.uniform(-1, 1, nvar)).cuda(); v2 = torch.from_numpy(rng.uniform(-1, 1, nvar)).cuda()
+    w = torch.from_numpy(rng.uniform(-1, 1, ncon)).cuda()
+    a_, b_ = float(torch.dot(w, nlp.jprod(x, v))), float(torch.dot(nlp.jtprod(x, w), v))
+    assert abs(a_ - b_) <= 1e-11 * max(abs(a_), abs(b_), 1.0)
+    Hv = nlp.hprod(x, lam, v, obj_weight=0.37); Hv2 = nlp.hprod(x, lam, v2, obj_weight=0.37)
+    a_, b_ = float(torch.dot(v2, Hv)), float(torch.dot(v, Hv2))
+    assert abs(a_ - b_) <= 1e-11 * max(abs(a_), abs(b_), 1.0)
+    # coord form == operator form, kappa blocks included
+    r, c = nlp.hess_structure()
+    d = r != c
+    Hv_coo = torch.zeros(nvar, dtype=torch.float64, device="cuda").index_add_(0, r - 1, hv * v[c - 1])
+    Hv_coo.index_add_(0, c[d] - 1, hv[d] * v[r[d] - 1])
+    assert float((Hv_coo - Hv).abs().max()) <= 1e-11 * float(Hv.abs().max())
+    nlp.close()
