@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace pdenlp;
@@ -319,6 +320,27 @@ int out_ptr(pdenlp_model* m, double* user, int64_t n, double** dev) {
 int out_finish(pdenlp_model* m, double* user, int64_t n) {
   if (m->d.memspace == PDENLP_MEM_DEVICE) return PDENLP_OK;
   CU(cudaMemcpyAsync(user, m->sout, n * 8, cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  return PDENLP_OK;
+}
+// PDENLP_MEM_HOST: a structurally zero tail of the output is not sent over PCIe; host threads fill it
+// while the DMA engine copies the computed part [0, ncopy)
+void host_zero_parallel(double* p, int64_t n) {
+  if (n <= 0) return;
+  static const unsigned env_t = getenv("PDENLP_HOST_THREADS") ? (unsigned)atoi(getenv("PDENLP_HOST_THREADS")) : 0u;
+  unsigned T = env_t ? env_t : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+  if (n < (int64_t)1 << 20) T = 1;
+  std::vector<std::thread> th;
+  for (unsigned t = 1; t < T; ++t) {
+    const int64_t a = n * t / T, b = n * (t + 1) / T;
+    th.emplace_back([=] { memset(p + a, 0, (size_t)(b - a) * 8); });
+  }
+  memset(p, 0, (size_t)(n / T) * 8);
+  for (auto& t : th) t.join();
+}
+int out_finish_zero_tail(pdenlp_model* m, double* user, int64_t ncopy, int64_t nzero) {
+  CU(cudaMemcpyAsync(user, m->sout, ncopy * 8, cudaMemcpyDeviceToHost, m->stream));
+  host_zero_parallel(user + ncopy, nzero);
   CU(cudaStreamSynchronize(m->stream));
   return PDENLP_OK;
 }
@@ -693,7 +715,9 @@ int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda, do
   // memset streams at the pure-write rate, without the read/write mix of the emitting kernel.
   static const bool no_zero_trait = getenv("PDENLP_NO_ZERO_TRAIT") != nullptr;  // experiments only
   const bool cons_zero = !dl || (m->ops->res_fe_hessian_zero() && !no_zero_trait);
-  if (cons_zero) {
+  // (host memory space: that block is the tail of vals; it is zero-filled on the host, not transferred)
+  const bool host_tail = cons_zero && m->d.memspace == PDENLP_MEM_HOST;
+  if (cons_zero && !host_tail) {
     if (int rc = zero_fill(m, vfc, I.nnzh_fe)) return rc;
   }
   double* vo = m->nofe ? nullptr : vfo;  // NoFETerm: the objective has no FE block
@@ -702,6 +726,7 @@ int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda, do
     if (int rc = m->ops->hess(L, m->dm, dx, dl, obj_weight, vo, vc)) return rc;
     m->launches += 1;
   }
+  if (host_tail) return out_finish_zero_tail(m, vals, I.nnzh - I.nnzh_fe, I.nnzh_fe);
   return out_finish(m, vals, I.nnzh);
 }
 
