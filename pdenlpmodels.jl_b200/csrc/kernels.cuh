@@ -1313,8 +1313,18 @@ __device__ __forceinline__ void field_direction(const Tables<E>& tab, int q, con
 
 // These kernels are load-latency bound (ncu: long-scoreboard 8-14 stall cycles per issue at 16-24
 // resident warps), so the register budget is capped to keep 3-4 CTAs (24-32 warps) per SM.
+// hprod! over >= 6 pointwise fields (Jet2<7>: 28 second derivatives per jet) spills at 128 registers; with the
+// whole register file (1 CTA/SM) config 5 runs in 0.50 ms instead of 0.93 ms.
+#ifndef PDENLP_VEC_MINB_BIG_HPROD
+#define PDENLP_VEC_MINB_BIG_HPROD 1
+#endif
 template <class E, int OP>
-__global__ void __launch_bounds__(kThreads, (E::M >= 6 || OP == OP_HPROD) ? 2 : ((OP == OP_JPROD || OP == OP_JTPROD) ? 3 : 4))
+constexpr int vec_min_blocks() {
+  if (E::M >= 6 && OP == OP_HPROD) return PDENLP_VEC_MINB_BIG_HPROD;
+  return (E::M >= 6 || OP == OP_HPROD) ? 2 : ((OP == OP_JPROD || OP == OP_JTPROD) ? 3 : 4);
+}
+template <class E, int OP>
+__global__ void __launch_bounds__(kThreads, vec_min_blocks<E, OP>())
 k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* __restrict__ x,
          const double* __restrict__ lambda, const double* __restrict__ v, double obj_weight,
          double* __restrict__ out, double* __restrict__ partials) {
