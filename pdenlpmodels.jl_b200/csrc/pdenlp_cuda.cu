@@ -164,6 +164,13 @@ struct OpsImpl : Ops {
   }
   int hess_kappa(const Launch& L, const DevModel& D, const double* x, const double* lam, double ow, int which,
                  int64_t prows, double* vk) override {
+    if constexpr (E::NP > 0) {
+      if (which == 0 && prows == E::NP) {  // objective, kappa-kappa triangle only
+        k_hess_kappa_kk<E><<<grid_for(D.ntiles, kWarpsPerCta, L.sms * 8), kThreads, 0, L.stream>>>(tab, D, x, ow, vk);
+        CU(cudaGetLastError());
+        return PDENLP_OK;
+      }
+    }
     if constexpr (E::NP > 0)
     k_hess_kappa<E><<<grid_for(D.ntiles, kWarpsPerCta, L.sms * 8), kThreads, 0, L.stream>>>(tab, D, x, lam, ow, which, prows, vk);
     CU(cudaGetLastError());
