@@ -387,15 +387,20 @@ struct SegStage {
 
 // ---- K-path emitters (see KTab).  D entries that are zero on every lane of the warp are skipped
 // through warp-uniform branches, so e.g. a Poisson-type form costs 3 of the 16 (t,k) terms.
-template <class E>
-__device__ __forceinline__ double* emit_jac_y_K(const double* __restrict__ Ks, const Jet1<E::M> (&R)[E::NR], const Cell<E>& c, double* p) {
+// Common sparsity patterns of the NB x NB pointwise derivative data, as bit masks over (t*NB + k): the
+// emitters are instantiated for them with the pattern as a compile-time constant (straight-line code, no
+// per-column uniform tests); any other pattern takes the generic instance (CMASK = 0) with run-time tests.
+template <class E> __host__ __device__ constexpr unsigned kmask_mass() { return 1u; }                    // (0,0): reaction / L2 terms
+template <class E> __host__ __device__ constexpr unsigned kmask_diag_grad() {                            // (d,d), d >= 1: Laplace-type terms
+  unsigned m = 0;
+  for (int d = 1; d < E::NB; ++d) m |= 1u << (d * E::NB + d);
+  return m;
+}
+
+template <class E, unsigned CMASK>
+__device__ __forceinline__ double* emit_jac_y_K_impl(const double* __restrict__ Ks, const Jet1<E::M> (&R)[E::NR], const Cell<E>& c,
+                                                     double* p, unsigned nz) {
   using KT = KTab<E>;
-  unsigned nz = 0;
-#pragma unroll
-  for (int t = 0; t < E::NB; ++t)
-#pragma unroll
-    for (int k = 0; k < E::NB; ++k)
-      if (__any_sync(0xffffffffu, R[t].g[k] != 0.0)) nz |= 1u << (t * E::NB + k);
 #pragma unroll
   for (int j = 0; j < E::NY; ++j) {
     if (c.gy[j] > 0) {
@@ -406,7 +411,7 @@ __device__ __forceinline__ double* emit_jac_y_K(const double* __restrict__ Ks, c
       for (int t = 0; t < E::NB; ++t)
 #pragma unroll
         for (int k = 0; k < E::NB; ++k)
-          if ((nz >> (t * E::NB + k)) & 1u) {
+          if (((CMASK ? CMASK : nz) >> (t * E::NB + k)) & 1u) {
             const double d = R[t].g[k];
 #pragma unroll
             for (int i = 0; i < E::NY; ++i) acc[i] = fma(d, Ks[KT::yy(t, k, j, i)], acc[i]);
@@ -417,6 +422,18 @@ __device__ __forceinline__ double* emit_jac_y_K(const double* __restrict__ Ks, c
     }
   }
   return p;
+}
+template <class E>
+__device__ __forceinline__ double* emit_jac_y_K(const double* __restrict__ Ks, const Jet1<E::M> (&R)[E::NR], const Cell<E>& c, double* p) {
+  unsigned nz = 0;
+#pragma unroll
+  for (int t = 0; t < E::NB; ++t)
+#pragma unroll
+    for (int k = 0; k < E::NB; ++k)
+      if (__any_sync(0xffffffffu, R[t].g[k] != 0.0)) nz |= 1u << (t * E::NB + k);
+  constexpr unsigned DG = kmask_diag_grad<E>();
+  if (nz == DG) return emit_jac_y_K_impl<E, DG>(Ks, R, c, p, nz);
+  return emit_jac_y_K_impl<E, 0u>(Ks, R, c, p, nz);
 }
 template <class E>
 __device__ __forceinline__ double* emit_jac_u_K(const double* __restrict__ Ks, const Jet1<E::M> (&R)[E::NR], const Cell<E>& c, double* p) {
@@ -445,16 +462,11 @@ __device__ __forceinline__ double* emit_jac_u_K(const double* __restrict__ Ks, c
   }
   return p;
 }
-template <class E>
-__device__ __forceinline__ double* emit_hess_yy_K(const double* __restrict__ Ks, const Jet2<E::M>& L, double sc, const Cell<E>& c, double* p) {
+template <class E, unsigned CMASK>
+__device__ __forceinline__ double* emit_hess_yy_K_impl(const double* __restrict__ Ks, const Jet2<E::M>& L, double sc, const Cell<E>& c,
+                                                       double* p, unsigned nz) {
   using KT = KTab<E>;
   using J2 = Jet2<E::M>;
-  unsigned nz = 0;
-#pragma unroll
-  for (int k = 0; k < E::NB; ++k)
-#pragma unroll
-    for (int l = 0; l < E::NB; ++l)
-      if (__any_sync(0xffffffffu, L.h[J2::idx(k, l)] != 0.0)) nz |= 1u << (k * E::NB + l);
 #pragma unroll
   for (int j = 0; j < E::NY; ++j) {
     if (c.gy[j] > 0) {
@@ -465,7 +477,7 @@ __device__ __forceinline__ double* emit_hess_yy_K(const double* __restrict__ Ks,
       for (int k = 0; k < E::NB; ++k)
 #pragma unroll
         for (int l = 0; l < E::NB; ++l)
-          if ((nz >> (k * E::NB + l)) & 1u) {
+          if (((CMASK ? CMASK : nz) >> (k * E::NB + l)) & 1u) {
             const double d = L.h[J2::idx(k, l)] * sc;
 #pragma unroll
             for (int i = 0; i < E::NY; ++i) acc[i] = fma(d, Ks[KT::yy(k, l, j, i)], acc[i]);
@@ -476,6 +488,20 @@ __device__ __forceinline__ double* emit_hess_yy_K(const double* __restrict__ Ks,
     }
   }
   return p;
+}
+template <class E>
+__device__ __forceinline__ double* emit_hess_yy_K(const double* __restrict__ Ks, const Jet2<E::M>& L, double sc, const Cell<E>& c, double* p) {
+  using J2 = Jet2<E::M>;
+  unsigned nz = 0;
+#pragma unroll
+  for (int k = 0; k < E::NB; ++k)
+#pragma unroll
+    for (int l = 0; l < E::NB; ++l)
+      if (__any_sync(0xffffffffu, L.h[J2::idx(k, l)] != 0.0)) nz |= 1u << (k * E::NB + l);
+  constexpr unsigned MS = kmask_mass<E>(), DG = kmask_diag_grad<E>();
+  if (nz == MS) return emit_hess_yy_K_impl<E, MS>(Ks, L, sc, c, p, nz);
+  if (nz == DG) return emit_hess_yy_K_impl<E, DG>(Ks, L, sc, c, p, nz);
+  return emit_hess_yy_K_impl<E, 0u>(Ks, L, sc, c, p, nz);
 }
 template <class E>
 __device__ __forceinline__ double* emit_hess_u_K(const double* __restrict__ Ks, const Jet2<E::M>& L, double sc, const Cell<E>& c, double* p) {
