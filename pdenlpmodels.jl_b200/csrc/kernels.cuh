@@ -861,6 +861,9 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   constexpr int STAGE = hess_stage_doubles<E>();
   SegStage<E::RUN_H> st{smem + warp * STAGE, nullptr};
+  // a kernel launched behind this one with programmatic stream serialization (the zero fill of the other,
+  // disjoint, FE block) may start right away; a no-op otherwise
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const double* const Ks = load_ktab<E>(D, smem + nwarps * STAGE);
 
   const int64_t stride = (int64_t)gridDim.x * nwarps;

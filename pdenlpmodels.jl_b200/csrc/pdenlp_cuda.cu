@@ -53,6 +53,7 @@ struct Ops {
   virtual bool needs_coef_deriv() const = 0;  // derivative callbacks read the coefficient fields
   virtual bool res_fe_hessian_zero() const = 0;  // constraint FE Hessian block is structurally zero
   virtual bool no_fe_obj() const = 0;            // NoFETerm objective fk(kappa)
+  virtual bool is_multi() const = 0;             // multi-field element (block-ordered kernels)
   virtual int nofe(const Launch& L, int mode, const double* x, double ow, const double* v, double* out) = 0;
   virtual const std::vector<double>& ktab() const = 0;  // pre-integrated reference tensors (may be empty)
 };
@@ -98,6 +99,7 @@ struct OpsImpl : Ops {
   bool needs_coef_deriv() const override { return E::Integrand::NEEDS_COEF_DERIV; }
   bool res_fe_hessian_zero() const override { return E::Integrand::RES_FE_HESSIAN_ZERO; }
   bool no_fe_obj() const override { return E::Integrand::NO_FE_OBJ; }
+  bool is_multi() const override { return E::MULTI; }
   int nofe(const Launch& L, int mode, const double* x, double ow, const double* v, double* out) override {
     if constexpr (E::Integrand::NO_FE_OBJ) {
       k_nofe<E><<<1, 32, 0, L.stream>>>(tab, x, mode, ow, v, out);
@@ -353,7 +355,7 @@ int out_finish_zero_tail(pdenlp_model* m, double* user, int64_t ncopy, int64_t n
 }
 
 // zero fill of a (large) COO segment on the model's stream
-int zero_fill(pdenlp_model* m, double* p, int64_t n) {
+int zero_fill(pdenlp_model* m, double* p, int64_t n, bool overlap_previous = false) {
   static const bool use_memset = getenv("PDENLP_ZERO_MEMSET") != nullptr;  // experiments only
   if (n <= 0) return PDENLP_OK;
   if (use_memset || n < 4096) {
@@ -365,8 +367,20 @@ int zero_fill(pdenlp_model* m, double* p, int64_t n) {
   // 0.56/0.50/0.47 ms; cudaMemsetAsync 0.41 ms); PDENLP_FILL_CTAS = CTAs per SM of a persistent grid (experiments)
   static const int per_sm = getenv("PDENLP_FILL_CTAS") ? atoi(getenv("PDENLP_FILL_CTAS")) : 0;
   const int grid = (int)std::max<int64_t>(1, per_sm > 0 ? std::min<int64_t>(want, (int64_t)m->sms * per_sm) : std::min<int64_t>(want, 0x7fffffff));
-  k_zero_fill<<<grid, 256, 0, m->stream>>>(p, n);
-  CU(cudaGetLastError());
+  if (overlap_previous) {
+    // programmatic dependent launch: the previous kernel on the stream (k_hess_coord, which writes a disjoint
+    // block and has signalled launch_dependents) need not have finished
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = m->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CU(cudaLaunchKernelEx(&cfg, k_zero_fill, p, n));
+  } else {
+    k_zero_fill<<<grid, 256, 0, m->stream>>>(p, n);
+    CU(cudaGetLastError());
+  }
   m->launches += 1;
   return PDENLP_OK;
 }
@@ -724,7 +738,11 @@ int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda, do
   const bool cons_zero = !dl || (m->ops->res_fe_hessian_zero() && !no_zero_trait);
   // (host memory space: that block is the tail of vals; it is zero-filled on the host, not transferred)
   const bool host_tail = cons_zero && m->d.memspace == PDENLP_MEM_HOST;
-  if (cons_zero && !host_tail) {
+  // The fill is launched BEHIND the emitting kernel with programmatic stream serialization, so it starts while
+  // that kernel is still running (disjoint outputs): hides one launch ramp/tail per callback (config 2: -7 us at
+  // N = 1, ~5 % of hess_coord! on a 1/8 slab).  PDENLP_NO_PDL=1 restores the plain order fill -> kernel.
+  static const bool pdl = getenv("PDENLP_NO_PDL") == nullptr;
+  if (cons_zero && !host_tail && !pdl) {
     if (int rc = zero_fill(m, vfc, I.nnzh_fe)) return rc;
   }
   double* vo = m->nofe ? nullptr : vfo;  // NoFETerm: the objective has no FE block
@@ -732,6 +750,9 @@ int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda, do
   if (vo || vc) {
     if (int rc = m->ops->hess(L, m->dm, dx, dl, obj_weight, vo, vc)) return rc;
     m->launches += 1;
+  }
+  if (cons_zero && !host_tail && pdl) {
+    if (int rc = zero_fill(m, vfc, I.nnzh_fe, (vo || vc) && !m->ops->is_multi())) return rc;
   }
   if (host_tail) return out_finish_zero_tail(m, vals, I.nnzh - I.nnzh_fe, I.nnzh_fe);
   return out_finish(m, vals, I.nnzh);
