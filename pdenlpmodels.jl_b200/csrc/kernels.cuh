@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(kThreads) k_count(DevModel D, int32_t* __restr
 // with TMA bulk stores.  Lane l writes its k-th kept entry at (exclusive scan + k), i.e. lanes are
 // RUN doubles apart: with an even RUN that is a 2..16-way bank conflict on every STS.64 (measured:
 // 3.6e9 conflicts per launch for the 3-D Q1 element).  The image is therefore cut into P pieces of
-// CPP = 32/P consecutive cells; pieces are PSTRIDE (odd) doubles apart, which spreads the lanes
+// CPP = 32/P consecutive cells; pieces are PSTRIDE doubles apart (see below), which spreads the lanes
 // over the banks, and every piece is one contiguous global range streamed by its own bulk store,
 // issued by the piece's first lane.  `delta` keeps each piece congruent (mod 16 B) with its global
 // destination so the bulk copy is legal; unaligned head/tail elements go by plain 8 B stores.
@@ -289,7 +289,17 @@ struct StageLayout {
   static constexpr int P = (RUN % 8 == 0) ? 16 : 1;
   static constexpr int CPP = 32 / P;                       // cells (lanes) per piece
   static constexpr int PR = CPP * RUN + 2;                 // piece capacity incl. parity slack
+#ifdef PDENLP_EXP_ODD_PSTRIDE
   static constexpr int PSTRIDE = (P == 1) ? PR : (PR | 1); // odd stride between pieces
+#else
+  // Every piece image starts at a double offset congruent (mod 2) with its global range, and the ranges of one tile
+  // almost always share their parity (even entry counts), so the piece starts can only spread over the 8 even (or
+  // odd) bank pairs: the stride must make p*PSTRIDE/2 run through all residues mod 8 for the 8 pieces of a half-warp,
+  // i.e. PSTRIDE = 2 (mod 4).  PR = CPP*RUN + 2 with RUN % 8 == 0 already is.  (An odd stride looks conflict-free on
+  // paper but the parity shift folds pieces p and p+5 onto the same banks: 8 wavefronts per STS.64 measured, 4 now.)
+  static constexpr int PSTRIDE = PR;
+  static_assert(P == 1 || PR % 4 == 2, "piece stride must be 2 mod 4");
+#endif
   static constexpr int WARP_DOUBLES = (P * PSTRIDE + 2) & ~1;  // even => 16 B aligned warp buffers
 };
 
