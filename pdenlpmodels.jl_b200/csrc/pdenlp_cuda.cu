@@ -562,6 +562,7 @@ int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
   // the host arrays of the description are not referenced after create
   m->d.cell_dofs_y = m->d.cell_dofs_u = nullptr;
   m->d.dir_y = m->d.dir_u = m->d.phi_y = m->d.grad_y = m->d.phi_u = m->d.wdet = m->d.coef = nullptr;
+  m->d.field_nfree = m->d.field_ndir = nullptr;
   cudaSetDevice(prev);
   *out = m;
   return PDENLP_OK;
