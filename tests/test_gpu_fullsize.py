@@ -29,6 +29,32 @@ def test_membrane_n2048_sizes(membrane2048):
     assert nlp.pdemeta.nnzh_obj == 381386820
 
 
+def test_membrane_n2048_stream_order_after_overlapped_fill(membrane2048):
+    """hess_coord! launches its zero fill behind the emitting kernel with programmatic stream serialization (the
+    fill may run concurrently and finishes first).  Work enqueued on the stream right after the callback must
+    still see the COMPLETE result: poison the output, call, snapshot with a stream-ordered copy."""
+    spec, nlp = membrane2048
+    x = torch.from_numpy(np.random.default_rng(1).uniform(-1, 1, nlp.meta.nvar)).cuda()
+    lam = torch.from_numpy(np.random.default_rng(2).uniform(-1, 1, nlp.meta.ncon)).cuda()
+    hv = torch.empty(nlp.meta.nnzh, dtype=torch.float64, device="cuda")
+    jv = torch.empty(nlp.meta.nnzj, dtype=torch.float64, device="cuda")
+    ref = None
+    for rep in range(4):
+        hv.fill_(float("nan")); jv.fill_(float("nan"))
+        nlp.hess_coord_(x, lam, hv, obj_weight=1.0)
+        snap = hv.clone()                    # enqueued immediately behind the callback
+        nlp.jac_coord_(x, jv)                # the next callback, then another immediate consumer
+        jsum = jv.sum()
+        torch.cuda.synchronize()
+        assert not torch.isnan(snap).any() and torch.equal(snap, hv)
+        assert torch.isfinite(jsum)
+        if ref is None:
+            ref = snap
+        else:
+            assert torch.equal(snap, ref)    # FE blocks are written without atomics: bitwise reproducible
+    del snap, ref, hv, jv
+
+
 def test_membrane_n2048_slabs_vs_oracle_and_properties(membrane2048, oracle_mod):
     spec, nlp = membrane2048
     nvar, ncon = nlp.meta.nvar, nlp.meta.ncon
