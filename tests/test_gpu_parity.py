@@ -193,3 +193,25 @@ def test_unconstrained_models(which, pkg, oracle_mod, cuda_lib):
     assert nlp.cons(_d(x)).numel() == 0 and nlp.jac_coord(_d(x)).numel() == 0 and nlp.jprod(_d(x), _d(v)).numel() == 0
     assert torch.all(nlp.jtprod(_d(x), empty) == 0)
     nlp.close()
+
+
+def test_callbacks_follow_the_current_torch_stream(pkg, cuda_lib):
+    """pdenlp_set_stream: every callback runs on torch's current stream, so producer / consumer kernels
+    enqueued on a side stream are ordered with it without host synchronisation."""
+    from pdenlp_b200.model import GridapPDENLPModel
+    spec = pkg.controlelasticmembrane(64)
+    nlp = GridapPDENLPModel(spec, device="cuda:0")
+    rng = np.random.default_rng(3)
+    x0 = _d(rng.uniform(-1, 1, nlp.meta.nvar)); lam = _d(rng.uniform(-1, 1, nlp.meta.ncon))
+    ref_j = nlp.jac_coord(2.0 * x0); ref_h = nlp.hess_coord(2.0 * x0, lam, obj_weight=0.5); ref_g = nlp.grad(2.0 * x0)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        x = x0 * 2.0                         # producer on the side stream
+        j = nlp.jac_coord(x); h = nlp.hess_coord(x, lam, obj_weight=0.5); g = nlp.grad(x)
+        js = j.clone(); hs = h.clone()       # consumers on the side stream
+    side.synchronize()
+    assert torch.equal(js, ref_j) and torch.equal(hs, ref_h)
+    assert torch.allclose(g, ref_g, rtol=1e-13, atol=1e-15)
+    nlp.close()
