@@ -159,7 +159,11 @@ __device__ __forceinline__ void gather_state(const DevModel& D, const double* __
 template <int N>
 __device__ __forceinline__ void gather_free(const double* __restrict__ vec, const int* gid, double* out) {
 #pragma unroll
-  for (int a = 0; a < N; ++a) out[a] = gid[a] > 0 ? __ldg(vec + (gid[a] - 1)) : 0.0;
+  for (int a = 0; a < N; ++a) {  // unconditional load (entry 0 for a non-free dof), then select: no branch
+    const int g = gid[a];
+    const double v = __ldg(vec + (g > 0 ? g - 1 : 0));
+    out[a] = g > 0 ? v : 0.0;
+  }
 }
 
 // pointwise fields at quadrature point q, seeded as jets (or plain doubles)

@@ -286,7 +286,7 @@ namespace {
 template <class T>
 int dev_upload(pdenlp_model* m, const T* host, size_t n, T** out) {
   *out = nullptr;
-  if (n == 0) { CU(cudaMalloc((void**)out, 16)); m->owned.push_back(*out); return PDENLP_OK; }
+  if (n == 0) { CU(cudaMalloc((void**)out, 16)); m->owned.push_back(*out); CU(cudaMemset(*out, 0, 16)); return PDENLP_OK; }
   CU(cudaMalloc((void**)out, n * sizeof(T)));
   m->owned.push_back(*out);
   CU(cudaMemcpy(*out, host, n * sizeof(T), cudaMemcpyHostToDevice));
