@@ -1364,7 +1364,10 @@ __device__ __forceinline__ void field_direction(const Tables<E>& tab, int q, con
 template <class E, int OP>
 constexpr int vec_min_blocks() {
   if (E::M >= 6 && OP == OP_HPROD) return PDENLP_VEC_MINB_BIG_HPROD;
-  return (E::M >= 6 || OP == OP_HPROD) ? 2 : ((OP == OP_JPROD || OP == OP_JTPROD) ? 3 : 4);
+#ifndef PDENLP_VEC_MINB_SMALL
+#define PDENLP_VEC_MINB_SMALL 4
+#endif
+  return (E::M >= 6 || OP == OP_HPROD) ? 2 : ((OP == OP_JPROD || OP == OP_JTPROD) ? 3 : (OP == OP_OBJ ? 4 : PDENLP_VEC_MINB_SMALL));
 }
 template <class E, int OP>
 __global__ void __launch_bounds__(kThreads, vec_min_blocks<E, OP>())
