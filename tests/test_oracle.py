@@ -261,3 +261,68 @@ def test_sis_residual_against_hand_discretisation(pkg, oracle_mod):
     cc = o.cons(xc)
     assert np.allclose(cc[:n] + cc[n:], 0.0, atol=1e-15)
     assert c.shape == (2 * n,)
+
+
+def _dense(o, vals, rows, cols, shape):
+    return sp.coo_matrix((vals, (rows - 1, cols - 1)), shape=shape).toarray()  # duplicates are summed
+
+
+def test_textbook_stencils_pin_jacobian_and_hessian_values(pkg, oracle_mod):
+    """Value-level known answers that do not come from this repository: the assembled COO streams must
+    reproduce the classic uniform-grid finite-element stencils.
+      * Q1 Laplacian on a uniform 2-D grid (any h): 8/3 on the diagonal, -1/3 for the 8 neighbours;
+      * Q1 mass matrix: h^2/36 * [1 4 1; 4 16 4; 1 4 1];
+      * 1-D P1: stiffness (1/h)[-1 2 -1], midpoint-rule convection (1/2)[-1 0 1], midpoint-rule mass (h/4)[1 2 1]."""
+    # --- poissonparam: c = k1 * K y - F  ->  dc/dy = k1 * K, dc/dk = K y_total (incl. Dirichlet lift)
+    n = 6
+    spec = pkg.poissonparam(n)
+    o = oracle_mod.Oracle(spec)
+    ny = spec.Ypde.nfree
+    x = np.concatenate([[1.7], np.random.default_rng(0).uniform(-1, 1, ny)])
+    r, c = o.jac_structure()
+    J = _dense(o, o.jac_coord(x), r, c, (o.ncon, o.nvar))
+    K = J[:, 1:] / 1.7
+    m = n - 1  # interior nodes per direction, x-fastest numbering
+    idx = lambda i, j: j * m + i
+    for (i, j) in ((2, 2), (1, 3), (0, 0), (4, 2)):
+        row = K[idx(i, j)]
+        assert np.isclose(row[idx(i, j)], 8.0 / 3.0, rtol=1e-13)
+        nb = [(i + di, j + dj) for di in (-1, 0, 1) for dj in (-1, 0, 1) if (di or dj) and 0 <= i + di < m and 0 <= j + dj < m]
+        assert np.allclose([row[idx(a, b)] for a, b in nb], -1.0 / 3.0, rtol=1e-13)
+        assert np.count_nonzero(np.abs(row) > 1e-14) == 1 + len(nb)
+    assert np.allclose(K, K.T, atol=1e-14)
+    # --- poissonmixed: objective 0.5*int (sol - y)^2  ->  FE Hessian block = Q1 mass matrix
+    spec = pkg.poissonmixed(n)
+    o = oracle_mod.Oracle(spec)
+    xk = np.concatenate([[1.0, 1.0], np.random.default_rng(1).uniform(-1, 1, spec.Ypde.nfree)])
+    r, c = o.hess_structure()
+    no = o.nnzh_obj
+    H = _dense(o, o.hess_coord(xk, None, 1.0)[:no], r[:no], c[:no], (o.nvar, o.nvar))
+    H = H + np.tril(H, -1).T
+    M = H[2:, 2:]
+    h = 1.0 / n
+    st = {(0, 0): 16.0, (1, 0): 4.0, (0, 1): 4.0, (1, 1): 1.0}
+    for (i, j) in ((2, 2), (0, 3), (4, 4)):
+        for di in (-1, 0, 1):
+            for dj in (-1, 0, 1):
+                if 0 <= i + di < m and 0 <= j + dj < m:
+                    assert np.isclose(M[idx(i, j), idx(i + di, j + dj)], h * h / 36.0 * st[(abs(di), abs(dj))], rtol=1e-12)
+    assert np.allclose(np.diag(H)[:2], 1.0, rtol=1e-13)  # 0.5*(k-1)^2 integrated over |Omega| = 1
+    # --- burger1d (linear): c = -nu*K y + C y - Mu u - F with the midpoint rule (degree 1)
+    n1 = 8
+    spec = pkg.burger1d(n1)
+    o = oracle_mod.Oracle(spec)
+    h = 1.0 / n1
+    nu_ = spec.params[1]
+    x = np.random.default_rng(2).uniform(-1, 1, o.nvar)
+    r, c = o.jac_structure()
+    J = _dense(o, o.jac_coord(x), r, c, (o.ncon, o.nvar))
+    ny = spec.Ypde.nfree
+    Jy, Ju = J[:, :ny], J[:, ny:]
+    i = 3
+    assert np.isclose(Jy[i, i], -nu_ * 2.0 / h, rtol=1e-13)
+    assert np.isclose(Jy[i, i + 1], -nu_ * (-1.0 / h) + 0.5, rtol=1e-13)
+    assert np.isclose(Jy[i, i - 1], -nu_ * (-1.0 / h) - 0.5, rtol=1e-13)
+    # state node i (free dof i, interior node i+1 of the mesh) meets control nodes i, i+1, i+2 (all control dofs are free)
+    assert np.allclose(Ju[i, i:i + 3], [-h / 4.0, -h / 2.0, -h / 4.0], rtol=1e-13)
+    assert np.count_nonzero(np.abs(Ju[i]) > 1e-15) == 3
