@@ -174,3 +174,16 @@ def test_view_subarray(prob):
         assert torch.allclose(nlp.jtprod(xv, yv), nlp.jtprod(x, y), **tol)
         assert torch.allclose(nlp.hess_coord(xv, yv, obj_weight=0.5), nlp.hess_coord(x, y, obj_weight=0.5), **tol)
         assert torch.allclose(nlp.hprod(xv, yv, vv, obj_weight=0.5), nlp.hprod(x, y, v, obj_weight=0.5), **tol)
+
+
+def test_sis_residual_at_exact_solution_on_the_gpu(pkg, cuda_lib):
+    """sis_test (test/problems/sis.jl:78-93) through the CUDA path: the weak residual of the exact ODE solution
+    is below 1e-15 at n = 1e5 (the reference accepts the first n = 10^k, k <= 6, that gets there)."""
+    from pdenlp_b200.model import GridapPDENLPModel
+    from test_oracle import _sis_exact
+    n = 10 ** 5
+    nlp = GridapPDENLPModel(pkg.sis(n), device="cuda:0")
+    x = _d(_sis_exact(n))
+    assert float(nlp.cons(x).abs().max()) <= 1e-15
+    assert nlp.obj(x) == 0.0 and float(nlp.grad(x).abs().max()) == 0.0
+    nlp.close()

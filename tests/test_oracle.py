@@ -326,3 +326,67 @@ def test_textbook_stencils_pin_jacobian_and_hessian_values(pkg, oracle_mod):
     # state node i (free dof i, interior node i+1 of the mesh) meets control nodes i, i+1, i+2 (all control dofs are free)
     assert np.allclose(Ju[i, i:i + 3], [-h / 4.0, -h / 2.0, -h / 4.0], rtol=1e-13)
     assert np.count_nonzero(np.abs(Ju[i]) > 1e-15) == 3
+
+
+def _sis_exact(n, x0=(1.0, 2.0), a=0.2, b=0.7, T=1.0):
+    """Exact solution of the SIS system sampled at the free nodes (test/problems/sis.jl:52-66)."""
+    N = sum(x0)
+    t = np.arange(1, n + 1) * (T / n)
+    rho = a * N - b + a * x0[0] * (np.exp((a * N - b) * t) - 1)
+    I = (a * N - b) * x0[0] * np.exp((a * N - b) * t) / rho
+    return np.concatenate([I, N - I])
+
+
+def test_sis_residual_vanishes_at_the_exact_ode_solution(pkg, oracle_mod):
+    """sis_test (test/problems/sis.jl:78-93): ||cons(nlp, exact solution)||_inf drops below 1e-15 for some
+    n = 10^k, k <= 6.  Here: third-order decay and <= 1e-15 from n = 1e5 on."""
+    res = []
+    for k in range(1, 6):
+        n = 10 ** k
+        o = oracle_mod.Oracle(pkg.sis(n))
+        res.append(np.abs(o.cons(_sis_exact(n))).max())
+    assert res[-1] <= 1e-15
+    assert all(r1 < r0 / 500 for r0, r1 in zip(res[:3], res[1:4]))  # O(h^3) while above round-off
+
+
+def test_controlsir_residual_at_the_reference_solution(pkg, oracle_mod):
+    """controlsir_test (test/problems/controlsir.jl:84-128): ||cons(nlp, closed-form solution)||_inf <= 1e-7 is
+    reached at n = 10^k for some k <= 6 ("beyond is tough"): first-order decay, 1.0e-7 exactly at n = 1e6."""
+    x0, a, b, mu, T = (1.0, 2.0), 0.2, 0.1, 0.1, 1.0
+    C = x0[0] + x0[1] - 1
+    lam = a - b + a * C
+
+    def sol(n):
+        t = np.arange(1, n + 1) * (T / n)
+        rho = a + lam * (lam - x0[0] * a) / (lam * x0[0] * np.exp(a * C / b)) * np.exp(-lam * t + a * C / b)
+        I = lam / rho
+        return np.concatenate([I, 1 + C * (1 - b * t) - I])
+
+    res = {k: np.abs(oracle_mod.Oracle(pkg.controlsir(10 ** k)).cons(sol(10 ** k))).max() for k in (2, 4, 6)}
+    assert res[6] <= 1e-7 < res[4]
+    assert np.isclose(res[2] / res[4], 100.0, rtol=1e-2) and np.isclose(res[4] / res[6], 100.0, rtol=1e-2)
+
+
+def test_dynamicsir_at_the_exact_solution(pkg, oracle_mod):
+    """dynamicsir_test (test/problems/dynamicsir.jl:66-130): with b(t) = 1/(t+1), c(t) = 2/(t+1) and the exact
+    (I, S) of Bohner-Streipert-Torres, `res <= 1e-5 && val <= 1e-10` must be reached for some n = 10^k, k <= 6
+    ("beyond is tough"): here first-order decay of the residual, reached exactly at k = 6, objective O(h^4)."""
+    x0, T = (1.0, 2.0), 1.0
+
+    def sol(n):
+        h = T / n
+        t = np.arange(1, n + 1) * h
+        kap = x0[0] / x0[1]
+        I = x0[0] * (kap + 1 + t) / ((kap + 1) * (t + 1) ** 2)
+        S = x0[1] * (kap + 1 + t) / ((kap + 1) * (t + 1))
+        tt = np.arange(0, n + 1) * h
+        return np.concatenate([I, S, 1 / (tt + 1), 2 / (tt + 1)])
+
+    out = {}
+    for k in (2, 3, 5, 6):
+        o = oracle_mod.Oracle(pkg.dynamicsir(10 ** k))
+        s = sol(10 ** k)
+        out[k] = (np.abs(o.cons(s)).max(), o.obj(s))
+    assert out[6][0] <= 1e-5 < out[5][0] and out[6][1] <= 1e-10
+    assert np.isclose(out[5][0] / out[6][0], 10.0, rtol=1e-3)
+    assert np.isclose(out[2][1] / out[3][1], 1e4, rtol=1e-2)  # objective: fourth order
