@@ -14,7 +14,7 @@ import NLPModels: obj, grad!, cons_nln!, jac_nln_coord!, hess_coord!, hprod!, jp
 const LIB = get(ENV, "PDENLP_CUDA_LIB", "libpdenlp_cuda.so")
 
 # integrand ids of include/pdenlp_cuda.h
-@enum Integrand MEMBRANE=1 POISSON_BOLTZMANN=2 BURGER_LIN=3 BURGER_NL=4 KAPPA_POISSON=5
+@enum Integrand MEMBRANE=1 POISSON_BOLTZMANN=2 BURGER_LIN=3 BURGER_NL=4 KAPPA_POISSON=5 PENALIZED_POISSON=6 BASIC_UNCONSTRAINED=7 CONTROL_SIR=8 CELL_INCREASE=9 DYNAMIC_SIR=10 TORE_BRACHISTOCHRONE=11 POISSON_PARAM=12 SIS=13
 
 struct Desc   # mirrors struct pdenlp_desc field by field
   abi_version::Int32; integrand::Int32; dim::Int32; ny::Int32; nu::Int32; nq::Int32; nparam::Int32
@@ -50,24 +50,32 @@ function attach_cuda!(nlp::GridapPDENLPModel, integrand::Integrand; params = Flo
   dΩ = Measure(trian, degree)
   quad = get_cell_quadrature(dΩ)   # Gridap.CellData.CellQuadrature
   qpts = get_cell_points(quad)
-  ids_y = get_cell_dof_ids(Ypde)
-  nc = length(ids_y); ny = length(ids_y[1])
-  celly = Matrix{Int32}(undef, ny, nc)         # column-major ny×nc == C row-major [nc][ny]
-  for (c, v) in enumerate(ids_y); celly[:, c] .= v; end
+  # single-field spaces of Ypde / Ycon (a MultiFieldFESpace contributes its fields, each with its OWN dof ids:
+  # the library applies the consecutive multi-field offsets itself, see include/pdenlp_cuda.h)
+  fields(sp) = sp isa MultiFieldFESpace ? collect(sp.spaces) : [sp]
+  function flat(fs)   # -> cell ids [nfields*nloc] x nc (field-major), Dirichlet values, per-field sizes, nloc
+    ids = [get_cell_dof_ids(f) for f in fs]
+    ncl = length(ids[1]); nl = length(ids[1][1])
+    cell = Matrix{Int32}(undef, nl * length(fs), ncl)   # column-major == C row-major [nc][nfields*nloc]
+    for (k, idk) in enumerate(ids), (c, v) in enumerate(idk); cell[((k - 1) * nl + 1):(k * nl), c] .= v; end
+    dir = reduce(vcat, [collect(Float64, get_dirichlet_values(f)) for f in fs])
+    return cell, dir, Int64[num_free_dofs(f) for f in fs], Int64[length(get_dirichlet_values(f)) for f in fs], nl
+  end
+  yf = fields(Ypde)
+  celly, diry, nfree_yf, ndir_yf, ny = flat(yf)
+  nc = size(celly, 2)
   has_u = !(Ycon isa PDENLPModels.VoidFESpace)
-  nu = has_u ? length(get_cell_dof_ids(Ycon)[1]) : 0
-  cellu = Matrix{Int32}(undef, max(nu, 0), nc)
-  has_u && for (c, v) in enumerate(get_cell_dof_ids(Ycon)); cellu[:, c] .= v; end
-  diry = collect(Float64, get_dirichlet_values(Ypde))
-  diru = has_u ? collect(Float64, get_dirichlet_values(Ycon)) : Float64[]
-  # tables on cell 1 (uniform Cartesian map: identical for every cell)
-  sfy = get_cell_shapefuns(Ypde)
+  uf = has_u ? fields(Ycon) : []
+  cellu, diru, nfree_uf, ndir_uf, nu = has_u ? flat(uf) : (Matrix{Int32}(undef, 0, nc), Float64[], Int64[], Int64[], 0)
+  field_nfree = vcat(nfree_yf, nfree_uf); field_ndir = vcat(ndir_yf, ndir_uf)
+  # tables on cell 1 (uniform Cartesian map: identical for every cell; all fields of a space share the element)
+  sfy = get_cell_shapefuns(yf[1])
   φ = evaluate(sfy, qpts)[1]                    # nq × ny
   ∇φ = evaluate(∇(sfy), qpts)[1]                # nq × ny of VectorValue (physical gradients)
   nq, D = size(φ, 1), length(∇φ[1, 1])
   phi_y = permutedims(Float64.(φ))              # ny × nq column-major == [nq][ny]
   grad_y = [∇φ[q, a][d] for d in 1:D, a in 1:ny, q in 1:nq]   # [nq][ny][dim]
-  phi_u = has_u ? permutedims(Float64.(evaluate(get_cell_shapefuns(Ycon), qpts)[1])) : zeros(0, nq)
+  phi_u = has_u ? permutedims(Float64.(evaluate(get_cell_shapefuns(uf[1]), qpts)[1])) : zeros(0, nq)
   w = get_cell_weights(quad)[1]; cmap = get_cell_map(trian)
   detJ = [abs(det(∇(cmap)[1](p))) for p in get_cell_coordinates(quad)[1]]
   wdet = Float64.(w .* detJ)
@@ -75,12 +83,12 @@ function attach_cuda!(nlp::GridapPDENLPModel, integrand::Integrand; params = Flo
   coef = Array{Float64}(undef, nq, nc, 2)           # [2][nc][nq]
   for c in 1:nc, q in 1:nq; coef[q, c, 1] = target(xq[c][q]); coef[q, c, 2] = source(xq[c][q]); end
   par = ntuple(i -> i <= length(params) ? Float64(params[i]) : 0.0, 8)
-  GC.@preserve celly cellu diry diru phi_y grad_y phi_u wdet coef begin
-    d = Desc(2, Int32(integrand), D, ny, nu, nq, nlp.pdemeta.nparam, memspace, device, 1,
+  GC.@preserve celly cellu diry diru phi_y grad_y phi_u wdet coef field_nfree field_ndir begin
+    d = Desc(2, Int32(integrand), D, ny, nu, nq, nlp.pdemeta.nparam, memspace, device, length(yf),
              nc, num_free_dofs(Ypde), has_u ? num_free_dofs(Ycon) : 0, length(diry), length(diru),
              pointer(celly), pointer(cellu), pointer(diry), pointer(diru),
-             pointer(phi_y), pointer(grad_y), pointer(phi_u), pointer(wdet), 2, has_u ? 1 : 0, pointer(coef), par,
-             Ptr{Int64}(C_NULL), Ptr{Int64}(C_NULL))  # single-field spaces; see include/pdenlp_cuda.h for MultiFieldFESpace
+             pointer(phi_y), pointer(grad_y), pointer(phi_u), pointer(wdet), 2, length(uf), pointer(coef), par,
+             pointer(field_nfree), pointer(field_ndir))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:pdenlp_create, LIB), Cint, (Ref{Desc}, Ref{Ptr{Cvoid}}), d, h))
   end
