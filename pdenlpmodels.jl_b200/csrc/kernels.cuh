@@ -415,6 +415,13 @@ template <class E, unsigned CMASK>
 __device__ __forceinline__ double* emit_jac_y_K_impl(const double* __restrict__ Ks, const Jet1<E::M> (&R)[E::NR], const Cell<E>& c,
                                                      double* p, unsigned nz) {
   using KT = KTab<E>;
+  // every column keeps the same rows (the free ones): one pointer per row, advanced by the number of kept
+  // rows per kept column — independent address chains instead of one pointer bumped after every store
+  double* rp[E::NY];
+  int fy = 0;
+#pragma unroll
+  for (int i = 0; i < E::NY; ++i) { rp[i] = p + fy; fy += c.gy[i] > 0; }
+  int ncol = 0;
 #pragma unroll
   for (int j = 0; j < E::NY; ++j) {
     if (c.gy[j] > 0) {
@@ -431,11 +438,14 @@ __device__ __forceinline__ double* emit_jac_y_K_impl(const double* __restrict__ 
             for (int i = 0; i < E::NY; ++i) acc[i] = fma(d, Ks[KT::yy(t, k, j, i)], acc[i]);
           }
 #pragma unroll
-      for (int i = 0; i < E::NY; ++i)
-        if (c.gy[i] > 0) { *p = acc[i]; ++p; }
+      for (int i = 0; i < E::NY; ++i) {
+        if (c.gy[i] > 0) *rp[i] = acc[i];
+        rp[i] += fy;
+      }
+      ++ncol;
     }
   }
-  return p;
+  return p + ncol * fy;
 }
 template <class E>
 __device__ __forceinline__ double* emit_jac_y_K(const double* __restrict__ Ks, const Jet1<E::M> (&R)[E::NR], const Cell<E>& c, double* p) {
@@ -456,6 +466,11 @@ __device__ __forceinline__ double* emit_jac_u_K(const double* __restrict__ Ks, c
 #pragma unroll
   for (int t = 0; t < E::NB; ++t)
     if (__any_sync(0xffffffffu, R[t].g[E::SU] != 0.0)) nz |= 1u << t;
+  double* rp[E::NY];
+  int fy = 0;
+#pragma unroll
+  for (int i = 0; i < E::NY; ++i) { rp[i] = p + fy; fy += c.gy[i] > 0; }
+  int ncol = 0;
 #pragma unroll
   for (int b = 0; b < E::NU; ++b) {
     if (c.gu[b] > 0) {
@@ -470,11 +485,14 @@ __device__ __forceinline__ double* emit_jac_u_K(const double* __restrict__ Ks, c
           for (int i = 0; i < E::NY; ++i) acc[i] = fma(d, Ks[KT::yu(t, b, i)], acc[i]);
         }
 #pragma unroll
-      for (int i = 0; i < E::NY; ++i)
-        if (c.gy[i] > 0) { *p = acc[i]; ++p; }
+      for (int i = 0; i < E::NY; ++i) {
+        if (c.gy[i] > 0) *rp[i] = acc[i];
+        rp[i] += fy;
+      }
+      ++ncol;
     }
   }
-  return p;
+  return p + ncol * fy;
 }
 template <class E, unsigned CMASK>
 __device__ __forceinline__ double* emit_hess_yy_K_impl(const double* __restrict__ Ks, const Jet2<E::M>& L, double sc, const Cell<E>& c,
