@@ -233,6 +233,12 @@ Ops* select_ops(const pdenlp_desc& d) {
   CASE(PDENLP_POISSON_BOLTZMANN, 2, 4, 4, 1, 0, PoissonBoltzmann<2>)
   CASE(PDENLP_BURGER_LIN, 1, 2, 2, 1, 0, BurgerLin)
   CASE(PDENLP_BURGER_NL, 1, 2, 2, 1, 1, BurgerNl)
+  // the same problems with the user's quadrature degree raised to 2 or 3 (2 Gauss points per direction)
+  CASE(PDENLP_MEMBRANE, 2, 9, 4, 4, 0, Membrane<2>)
+  CASE(PDENLP_MEMBRANE, 2, 4, 4, 4, 0, Membrane<2>)
+  CASE(PDENLP_POISSON_BOLTZMANN, 2, 4, 4, 4, 0, PoissonBoltzmann<2>)
+  CASE(PDENLP_BURGER_LIN, 1, 2, 2, 2, 0, BurgerLin)
+  CASE(PDENLP_BURGER_NL, 1, 2, 2, 2, 1, BurgerNl)
   using KP2 = KappaPoisson<2, false>;
   using KP2U = KappaPoisson<2, true>;
   using KP3U = KappaPoisson<3, true>;

@@ -117,18 +117,20 @@ def _h_membrane(X):
     return -np.sin(_OMEGA * X[:, 0]) * np.sin(_OMEGA * X[:, 1])
 
 
-def controlelasticmembrane(n: int = 100, affine: bool = False) -> ProblemSpec:
+def controlelasticmembrane(n: int = 100, affine: bool = False, degree: int = 1, state_order: int = 2) -> ProblemSpec:
     """README 'Control elastic membrane' (README.md:58-98; docstring
     src/GridapPDENLPModel.jl:164-204): Q2 state with Dirichlet boundary, Q1
     control, degree 1, res-function (FEOperatorFromWeakForm) variant.
     ``affine=True`` is the test-suite variant built on an AffineFEOperator
-    (test/problems/controlelasticmembrane.jl:48-53): same PDE, linear API."""
+    (test/problems/controlelasticmembrane.jl:48-53): same PDE, linear API.
+    ``degree`` is the user's `Measure(trian, degree)` (1 in the README; 2 or 3 give 2x2 Gauss points),
+    ``state_order`` the order of the state element (2 in the README)."""
     model = CartesianDiscreteModel((-1, 1, -1, 1), (n, n))
-    Ypde = LagrangianFESpace(model, 2, "H1", "boundary", 0.0)
+    Ypde = LagrangianFESpace(model, state_order, "H1", "boundary", 0.0)
     Ycon = LagrangianFESpace(model, 1, "H1")
     return ProblemSpec(
         name="Control elastic membrane" if not affine else "controlelasticmembrane1",
-        integrand=MEMBRANE, model=model, Ypde=Ypde, Ycon=Ycon, degree=1,
+        integrand=MEMBRANE, model=model, Ypde=Ypde, Ycon=Ycon, degree=degree,
         params=(1e-2,),
         target=lambda X: -X[:, 0] ** 2,
         source=_h_membrane,
@@ -136,7 +138,7 @@ def controlelasticmembrane(n: int = 100, affine: bool = False) -> ProblemSpec:
     )
 
 
-def poissonboltzman2d(n: int = 100, control_conformity: str = "L2") -> ProblemSpec:
+def poissonboltzman2d(n: int = 100, control_conformity: str = "L2", degree: int = 1) -> ProblemSpec:
     """docs/src/poisson-boltzman.md:30-67: Q1 state, Q1 control (L2 in the
     doc), degree 1, sinh reaction term."""
     model = CartesianDiscreteModel((-1, 1, -1, 1), (n, n))
@@ -149,7 +151,7 @@ def poissonboltzman2d(n: int = 100, control_conformity: str = "L2") -> ProblemSp
 
     return ProblemSpec(
         name="poissonboltzman2d",
-        integrand=POISSON_BOLTZMANN, model=model, Ypde=Ypde, Ycon=Ycon, degree=1,
+        integrand=POISSON_BOLTZMANN, model=model, Ypde=Ypde, Ycon=Ycon, degree=degree,
         params=(1e-4,), target=yd, source=_h_membrane,
     )
 
@@ -162,28 +164,28 @@ def _burger_spaces(n):
     return model, Ypde, Ycon
 
 
-def burger1d(n: int = 512) -> ProblemSpec:
+def burger1d(n: int = 512, degree: int = 1) -> ProblemSpec:
     """test/problems/burger1d.jl:1-52 (the test-suite variant: dt(y,v) = y' v
     is linear, src/util_functions.jl:109-110)."""
     model, Ypde, Ycon = _burger_spaces(n)
     nu = 0.08
     return ProblemSpec(
         name="burger1d",
-        integrand=BURGER_LIN, model=model, Ypde=Ypde, Ycon=Ycon, degree=1,
+        integrand=BURGER_LIN, model=model, Ypde=Ypde, Ycon=Ycon, degree=degree,
         params=(1e-2, nu),
         target=lambda X: -X[:, 0] ** 2,
         source=lambda X: 2 * (nu + X[:, 0] ** 3),
     )
 
 
-def burger1d_param(n: int = 512) -> ProblemSpec:
+def burger1d_param(n: int = 512, degree: int = 1) -> ProblemSpec:
     """test/problems/burger1d_param.jl:1-54: nonlinear convection v*y*y',
     one algebraic unknown."""
     model, Ypde, Ycon = _burger_spaces(n)
     nu = 0.08
     return ProblemSpec(
         name="burger1d_param",
-        integrand=BURGER_NL, model=model, Ypde=Ypde, Ycon=Ycon, degree=1,
+        integrand=BURGER_NL, model=model, Ypde=Ypde, Ycon=Ycon, degree=degree,
         nparam=1, params=(1e-2, nu, 0.08),
         target=lambda X: -X[:, 0] ** 2,
         source=lambda X: 2 * (nu + X[:, 0] ** 3),

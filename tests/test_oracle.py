@@ -28,6 +28,11 @@ CASES = {
     "cellincrease_5": lambda p: p.cellincrease(5),
     "dynamicsir_6": lambda p: p.dynamicsir(6),
     "torebrachistochrone_4": lambda p: p.torebrachistochrone(4),
+    # the user's quadrature degree raised to 2 (2 Gauss points per direction)
+    "membrane3_deg2": lambda p: p.controlelasticmembrane(3, degree=2),
+    "membrane_q1_4_deg3": lambda p: p.controlelasticmembrane(4, degree=3, state_order=1),
+    "pb_l2_3_deg2": lambda p: p.poissonboltzman2d(3, degree=2),
+    "burger_nl_7_deg2": lambda p: p.burger1d_param(7, degree=2),
     # NoFETerm objectives
     "poissonparam_3": lambda p: p.poissonparam(3),
     "sis_6": lambda p: p.sis(6),
