@@ -99,7 +99,11 @@ enum pdenlp_integrand {
   PDENLP_POISSON_PARAM = 12,
   /* state (I,S), NoFETerm() = 0: res = dt(I,p) + dt(S,q) - p*(a*S*I - b*I) - q*(b*I - a*S*I)
      test/problems/sis.jl:21-34.  params = (a, b) */
-  PDENLP_SIS = 13
+  PDENLP_SIS = 13,
+  /* nparam=2, plain MixedEnergyFETerm (inde = false: objective kappa-block with cross rows):
+     f = k1*(sol-y)^2 + 0.5*(k2-1)^2 ; res = k1*grad(v).grad(y) - v*f*k2
+     test/problems/poissonmixed2.jl:35-44 */
+  PDENLP_KAPPA_POISSON2 = 14
 };
 
 /* coefficient fields sampled at quadrature points, coef[k][cell][q] */

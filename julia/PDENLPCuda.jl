@@ -14,7 +14,7 @@ import NLPModels: obj, grad!, cons_nln!, jac_nln_coord!, hess_coord!, hprod!, jp
 const LIB = get(ENV, "PDENLP_CUDA_LIB", "libpdenlp_cuda.so")
 
 # integrand ids of include/pdenlp_cuda.h
-@enum Integrand MEMBRANE=1 POISSON_BOLTZMANN=2 BURGER_LIN=3 BURGER_NL=4 KAPPA_POISSON=5 PENALIZED_POISSON=6 BASIC_UNCONSTRAINED=7 CONTROL_SIR=8 CELL_INCREASE=9 DYNAMIC_SIR=10 TORE_BRACHISTOCHRONE=11 POISSON_PARAM=12 SIS=13
+@enum Integrand MEMBRANE=1 POISSON_BOLTZMANN=2 BURGER_LIN=3 BURGER_NL=4 KAPPA_POISSON=5 PENALIZED_POISSON=6 BASIC_UNCONSTRAINED=7 CONTROL_SIR=8 CELL_INCREASE=9 DYNAMIC_SIR=10 TORE_BRACHISTOCHRONE=11 POISSON_PARAM=12 SIS=13 KAPPA_POISSON2=14
 
 struct Desc   # mirrors struct pdenlp_desc field by field
   abi_version::Int32; integrand::Int32; dim::Int32; ny::Int32; nu::Int32; nq::Int32; nparam::Int32

@@ -129,7 +129,7 @@ typedef struct oracle_problem {
 }
 
 enum { MEMBRANE = 1, PB = 2, BURGER_LIN = 3, BURGER_NL = 4, KAPPA_POISSON = 5, PENALIZED_POISSON = 6, BASIC_UNCONSTRAINED = 7,
-       CONTROL_SIR = 8, CELL_INCREASE = 9, DYNAMIC_SIR = 10, TORE_BRACHISTOCHRONE = 11, POISSON_PARAM = 12, SIS = 13 };
+       CONTROL_SIR = 8, CELL_INCREASE = 9, DYNAMIC_SIR = 10, TORE_BRACHISTOCHRONE = 11, POISSON_PARAM = 12, SIS = 13, KAPPA_POISSON2 = 14 };
 
 // NoFETerm objectives (src/additional_obj_terms.jl:59-106): f(kappa) without any integral; the objective has no
 // FE Hessian block (hessian_struct_nnzh_functions.jl:41-43) and its kappa-block is the p x p lower triangle
@@ -154,6 +154,7 @@ static double coef_target(const oracle_problem& P, const double* x) {
     }
     case BURGER_LIN:
     case BURGER_NL: return -x[0] * x[0];          // test/problems/burger1d.jl:33
+    case KAPPA_POISSON2:
     case KAPPA_POISSON: {                         // sol, test/problems/poissonmixed.jl:20
       double s = std::sin(2 * PI * x[0]) * x[1];
       return P.dim == 3 ? s * x[2] : s;
@@ -173,6 +174,7 @@ static double coef_source(const oracle_problem& P, const double* x) {
     case BURGER_LIN:
     case BURGER_NL: return 2 * (P.params[1] + x[0] * x[0] * x[0]);  // burger1d.jl:24
     case PENALIZED_POISSON: return 1.0;           // w, penalizedpoisson.jl:32
+    case KAPPA_POISSON2:
     case POISSON_PARAM:                           // f, poissonparam.jl:33
     case KAPPA_POISSON: {                         // f, poissonmixed.jl:31
       double s = (2 * PI * PI) * std::sin(2 * PI * x[0]) * x[1];
@@ -288,6 +290,11 @@ static S f_density(const oracle_problem& P, const Pt<S>& p) {
       S d = p.yd - p.u;
       return 0.5 * d * d + 0.5 * p.y * p.y;
     }
+    case KAPPA_POISSON2: {
+      // k1*(sol-y)*(sol-y) + 0.5*(k2-1)^2   (poissonmixed2.jl:39-42)
+      S d = p.yd - p.y; S b = p.k[1] - 1.0;
+      return p.k[0] * d * d + 0.5 * b * b;
+    }
     case KAPPA_POISSON: {
       // 0.5*(sol-y)^2 + 0.5*(k1-1)^2 + 0.5*(k2-1)^2   (poissonmixed.jl:37-43)
       S d = p.yd - p.y; S a = p.k[0] - 1.0; S b = p.k[1] - 1.0;
@@ -318,6 +325,7 @@ static S res_density(const oracle_problem& P, const Pt<S>& p, double v, const do
       return P.params[1] * gg - p.k[0] + v * (one_dot * p.y) - v * p.u - v * p.h;
     case POISSON_PARAM:    // k1*grad(v).grad(y) - v*f   (poissonparam.jl:35-38)
       return p.k[0] * gg - v * p.h;
+    case KAPPA_POISSON2:
     case KAPPA_POISSON: {  // k1*grad(v).grad(y) - v*f*k2 [- v*u]
       S r = p.k[0] * gg - (v * p.h) * p.k[1];
       if (has_u) r = r - v * p.u;

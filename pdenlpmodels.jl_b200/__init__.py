@@ -18,7 +18,7 @@ from . import cartesian, problems, flatten, bounds  # noqa: F401
 from .bounds import bounds_functions_to_vectors  # noqa: F401
 from .problems import (  # noqa: F401
     controlelasticmembrane, poissonboltzman2d, burger1d, burger1d_param, poissonmixed, penalizedpoisson,
-    basicunconstrained, controlsir, cellincrease, dynamicsir, torebrachistochrone, poissonparam, sis, BASELINE_CONFIGS,
+    basicunconstrained, controlsir, cellincrease, dynamicsir, torebrachistochrone, poissonparam, sis, poissonmixed2, BASELINE_CONFIGS,
 )
 
 __all__ = ["cartesian", "problems", "flatten", "bounds"]

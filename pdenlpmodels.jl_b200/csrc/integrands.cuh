@@ -146,6 +146,26 @@ struct PoissonParam : FieldIdx<DIM_, 1> {
   }
 };
 
+// test/problems/poissonmixed2.jl:35-43: f = k1*(sol - y)^2 + 0.5*(k2 - 1)^2 (inde = false), res as KappaPoisson
+template <int DIM_>
+struct KappaPoisson2 : FieldIdx<DIM_, 2> {
+  using I = FieldIdx<DIM_, 2>;
+  static constexpr bool HAS_CONST = false;
+  static constexpr bool NEEDS_COEF_DERIV = true;
+  static constexpr bool FE_DERIVS_POINT_INDEPENDENT = false;  // d2f/dy2 = 2*k1 is, but the kappa-y cross terms are not
+  static constexpr bool RES_FE_HESSIAN_ZERO = true;
+  template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) {
+    T d = c.target - s[I::SY];
+    T b = s[I::SK + 1] - 1.0;
+    return s[I::SK] * d * d + 0.5 * b * b;
+  }
+  template <class T> PDENLP_HD static void res(const PointCtx& c, const T* s, T* R) {
+    R[0] = (-c.source) * s[I::SK + 1];
+#pragma unroll
+    for (int d = 0; d < DIM_; ++d) R[1 + d] = s[I::SK] * s[I::SG + d];
+  }
+};
+
 // ---- unconstrained problems: objective only, the residual is identically zero (ncon = 0 on the
 // host side; the constraint entry points are never called for these models)
 template <int DIM_>

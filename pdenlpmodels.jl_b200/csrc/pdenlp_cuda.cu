@@ -245,6 +245,7 @@ Ops* select_ops(const pdenlp_desc& d) {
   CASE(PDENLP_KAPPA_POISSON, 2, 4, 0, 4, 2, KP2)
   CASE(PDENLP_KAPPA_POISSON, 2, 4, 4, 4, 2, KP2U)
   CASE(PDENLP_KAPPA_POISSON, 3, 8, 8, 8, 2, KP3U)
+  CASE(PDENLP_KAPPA_POISSON2, 2, 4, 0, 4, 2, KappaPoisson2<2>)
   CASE(PDENLP_PENALIZED_POISSON, 2, 4, 0, 4, 0, PenalizedPoisson<2>)
   CASE(PDENLP_BASIC_UNCONSTRAINED, 2, 4, 4, 4, 0, BasicUnconstrained<2>)
   // multi-field ODE problems: 1-D, P1 state fields, one quadrature point

@@ -31,6 +31,7 @@ DYNAMIC_SIR = 10
 TORE_BRACHISTOCHRONE = 11
 POISSON_PARAM = 12
 SIS = 13
+KAPPA_POISSON2 = 14
 
 INTEGRAND_NAMES = {
     MEMBRANE: "membrane",
@@ -46,6 +47,7 @@ INTEGRAND_NAMES = {
     TORE_BRACHISTOCHRONE: "tore_brachistochrone",
     POISSON_PARAM: "poisson_param",
     SIS: "sis",
+    KAPPA_POISSON2: "kappa_poisson2",
 }
 
 
@@ -225,6 +227,20 @@ def poissonparam(n: int = 3) -> ProblemSpec:
     return ProblemSpec(
         name="poissonparam", integrand=POISSON_PARAM, model=model, Ypde=Ypde, Ycon=None, degree=2, nparam=1,
         source=lambda X: (2 * np.pi ** 2) * np.sin(2 * np.pi * X[:, 0]) * X[:, 1], no_fe_obj=True,
+    )
+
+
+def poissonmixed2(n: int = 3) -> ProblemSpec:
+    """test/problems/poissonmixed2.jl:14-49 as evidently intended: f = k1*(sol - y)^2 + 0.5*(k2 - 1)^2 with a plain
+    MixedEnergyFETerm (inde = false: the objective kappa-block has cross rows with y), res as poissonmixed.
+    (The file passes the test space V0 in the Ycon slot of MixedEnergyFETerm; it is on the reference's
+    local-only list.)"""
+    model = CartesianDiscreteModel((0, 1, 0, 1), (n, n))
+    Ypde = LagrangianFESpace(model, 1, "H1", "boundary", lambda X: np.sin(2 * np.pi * X[:, 0]) * X[:, 1])
+    return ProblemSpec(
+        name="poissonmixed2", integrand=KAPPA_POISSON2, model=model, Ypde=Ypde, Ycon=None, degree=2, nparam=2,
+        target=lambda X: np.sin(2 * np.pi * X[:, 0]) * X[:, 1],
+        source=lambda X: (2 * np.pi ** 2) * np.sin(2 * np.pi * X[:, 0]) * X[:, 1],
     )
 
 

@@ -29,6 +29,7 @@ CASES = {
     "cellincrease_n5": lambda p: p.cellincrease(5),
     "dynamicsir_n6": lambda p: p.dynamicsir(6),
     "torebrachistochrone_n4": lambda p: p.torebrachistochrone(4),
+    "poissonmixed2_n3": lambda p: p.poissonmixed2(3),
     # NoFETerm objectives
     "poissonparam_n3": lambda p: p.poissonparam(3),
     "sis_n6": lambda p: p.sis(6),

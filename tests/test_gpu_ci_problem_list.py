@@ -31,6 +31,7 @@ PROBLEMS = {
     "SIS": lambda p: p.sis(N),
     "DYNAMICSIR": lambda p: p.dynamicsir(N),
     "BASICUNCONSTRAINED": lambda p: p.basicunconstrained(N),
+    "POISSONMIXED2": lambda p: p.poissonmixed2(N),
 }
 
 

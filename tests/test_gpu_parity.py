@@ -47,6 +47,7 @@ def _cases(pkg):
         "pb_l2_21_deg2": lambda: pkg.poissonboltzman2d(21, degree=2),
         "burger_lin_90_deg2": lambda: pkg.burger1d(90, degree=2),
         "burger_nl_90_deg3": lambda: pkg.burger1d_param(90, degree=3),
+        "poissonmixed2_17": lambda: pkg.poissonmixed2(17),   # inde = false: kappa-y cross rows in the objective block
         # NoFETerm objectives: no objective FE block in the Hessian
         "poissonparam_24": lambda: pkg.poissonparam(24),
         "sis_80": lambda: pkg.sis(80),
@@ -56,7 +57,8 @@ def _cases(pkg):
 CASE_NAMES = ["membrane3", "membrane8", "membrane37", "membrane100", "pb_l2_9", "pb_h1_33", "burger_lin_70",
               "burger_nl_70", "kappa2d_5", "kappa2d_u_6", "kappa3d_u_4",
               "controlsir_70", "cellincrease_45", "dynamicsir_100", "dynamicsir_5", "poissonparam_24", "sis_80",
-              "membrane20_deg2", "membrane_q1_33_deg3", "pb_l2_21_deg2", "burger_lin_90_deg2", "burger_nl_90_deg3"]
+              "membrane20_deg2", "membrane_q1_33_deg3", "pb_l2_21_deg2", "burger_lin_90_deg2", "burger_nl_90_deg3",
+              "poissonmixed2_17"]
 
 
 @pytest.fixture(scope="module", params=CASE_NAMES)

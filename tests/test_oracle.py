@@ -33,6 +33,7 @@ CASES = {
     "membrane_q1_4_deg3": lambda p: p.controlelasticmembrane(4, degree=3, state_order=1),
     "pb_l2_3_deg2": lambda p: p.poissonboltzman2d(3, degree=2),
     "burger_nl_7_deg2": lambda p: p.burger1d_param(7, degree=2),
+    "poissonmixed2_3": lambda p: p.poissonmixed2(3),
     # NoFETerm objectives
     "poissonparam_3": lambda p: p.poissonparam(3),
     "sis_6": lambda p: p.sis(6),
