@@ -120,6 +120,8 @@ __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uin
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int N>  // at most N of this thread's most recent bulk groups may still be reading shared memory
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ------------------------------------------------------------------ per-lane cell data
@@ -316,12 +318,15 @@ struct SegStage {
 #ifdef PDENLP_COPYOUT_STG
   // Experiment (-DPDENLP_COPYOUT_STG): copy-out with posted vector stores instead of TMA.  Measured
   // 33% slower on B200 (step 2.54 vs 1.91 ms at config 2), so TMA bulk stores are the default.
-  __device__ __forceinline__ void acquire(int) {}
+  template <int NBUF = 1> __device__ __forceinline__ void acquire(int) {}
 #else
   // (lanes wait on their own bulk groups; the issuing lanes are the first lanes of the finest
   // piece layout, 16 pieces = even lanes, which covers every coarser layout sharing the buffer)
+  // NBUF > 1: the warp rotates over NBUF staging buffers (small elements), so only the store issued NBUF
+  // uses ago must have left shared memory
+  template <int NBUF = 1>
   __device__ __forceinline__ void acquire(int lane) {
-    if ((lane & 1) == 0) bulk_wait_read_all();
+    if ((lane & 1) == 0) bulk_wait_read<NBUF - 1>();
     __syncwarp();
   }
 #endif
@@ -591,6 +596,14 @@ __host__ __device__ constexpr int jac_stage_doubles() {
 }
 template <class E>
 __host__ __device__ constexpr int hess_stage_doubles() { return StageLayout<E::RUN_H>::WARP_DOUBLES; }
+// Staging buffers per warp: elements whose tile image is small rotate over up to 4 buffers so that a warp does
+// not wait for the bulk store of its previous tile to drain shared memory before staging the next one.
+#ifndef PDENLP_NBUF_BYTES
+#define PDENLP_NBUF_BYTES 8192
+#endif
+__host__ __device__ constexpr int coord_nbuf(int stage_doubles) {
+  return stage_doubles * 8 * 2 > PDENLP_NBUF_BYTES ? 1 : (PDENLP_NBUF_BYTES / (stage_doubles * 8) > 4 ? 4 : PDENLP_NBUF_BYTES / (stage_doubles * 8));
+}
 
 // ------------------------------------------------------------------ jac_coord!
 // vals layout (this slab): [k-block (ncon*p, filled elsewhere) | y-block | u-block]
@@ -607,10 +620,12 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
   using I = typename E::Integrand;
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  constexpr int STAGE = jac_stage_doubles<E>();
-  SegStage<E::RUN_JY> sty{smem + warp * STAGE, nullptr};
-  SegStage<(E::NU > 0 ? E::RUN_JU : 1)> stu{smem + warp * STAGE, nullptr};
-  const double* const Ks = load_ktab<E>(D, smem + nwarps * STAGE);
+  constexpr int STAGE = jac_stage_doubles<E>(), NBUF = coord_nbuf(STAGE);
+  double* const wbase = smem + warp * STAGE * NBUF;
+  int slot = 0;
+  SegStage<E::RUN_JY> sty{wbase, nullptr};
+  SegStage<(E::NU > 0 ? E::RUN_JU : 1)> stu{wbase, nullptr};
+  const double* const Ks = load_ktab<E>(D, smem + nwarps * STAGE * NBUF);
 
   const int64_t stride = (int64_t)gridDim.x * nwarps;
   int64_t tile = (int64_t)blockIdx.x * nwarps + warp;
@@ -678,7 +693,8 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
       const int cnt = fy * fy;
       const int incl = warp_incl_scan(cnt, lane);
       double* gdst = vals_y + D.base_jy[tile];
-      sty.acquire(lane);
+      if (NBUF > 1) { sty.wbuf = wbase + slot * STAGE; slot = slot + 1 == NBUF ? 0 : slot + 1; }
+      sty.template acquire<NBUF>(lane);
       double* const p0 = sty.begin(gdst, incl - cnt, lane);
       if (kpath) emit_jac_y_K<E>(Ks, R0, c, p0);
       else
@@ -717,7 +733,8 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
       const int cnt = fy * fu;
       const int incl = warp_incl_scan(cnt, lane);
       double* gdst = vals_u + D.base_ju[tile];
-      stu.acquire(lane);
+      if (NBUF > 1) { stu.wbuf = wbase + slot * STAGE; slot = slot + 1 == NBUF ? 0 : slot + 1; }
+      stu.template acquire<NBUF>(lane);
       double* const p0 = stu.begin(gdst, incl - cnt, lane);
       if (kpath) emit_jac_u_K<E>(Ks, R0, c, p0);
       else
@@ -891,12 +908,14 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
   using I = typename E::Integrand;
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  constexpr int STAGE = hess_stage_doubles<E>();
-  SegStage<E::RUN_H> st{smem + warp * STAGE, nullptr};
+  constexpr int STAGE = hess_stage_doubles<E>(), NBUF = coord_nbuf(STAGE);
+  double* const wbase = smem + warp * STAGE * NBUF;
+  int slot = 0;
+  SegStage<E::RUN_H> st{wbase, nullptr};
   // a kernel launched behind this one with programmatic stream serialization (the zero fill of the other,
   // disjoint, FE block) may start right away; a no-op otherwise
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  const double* const Ks = load_ktab<E>(D, smem + nwarps * STAGE);
+  const double* const Ks = load_ktab<E>(D, smem + nwarps * STAGE * NBUF);
 
   const int64_t stride = (int64_t)gridDim.x * nwarps;
   int64_t tile = (int64_t)blockIdx.x * nwarps + warp;
@@ -940,7 +959,8 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
     // sub-block and warp-uniformly (all quadrature points, all lanes): a vanishing (y,y) part and/or
     // a vanishing u row skip their candidates; if both vanish the image is zero-filled.
     auto segment = [&](double* gdst, auto&& jet_at) {
-      st.acquire(lane);
+      if (NBUF > 1) { st.wbuf = wbase + slot * STAGE; slot = slot + 1 == NBUF ? 0 : slot + 1; }
+      st.template acquire<NBUF>(lane);
       double* const p0 = st.begin(gdst, incl - cnt, lane);
       bool zyy = true, zu = true, quni = true;
       Jet2<E::M> L, L0;
@@ -1087,9 +1107,11 @@ k_jac_coord_mf(const __grid_constant__ Tables<E> tab, const DevModel D, const do
   static_assert(!E::HAS_CONST, "multi-field integrands have no constant residual slot");
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  constexpr int STAGE = jac_stage_doubles<E>();
-  SegStage<E::RUN_JY> sty{smem + warp * STAGE, nullptr};
-  SegStage<(E::NU > 0 ? E::RUN_JU : 1)> stu{smem + warp * STAGE, nullptr};
+  constexpr int STAGE = jac_stage_doubles<E>(), NBUF = coord_nbuf(STAGE);
+  double* const wbase = smem + warp * STAGE * NBUF;
+  int slot = 0;
+  SegStage<E::RUN_JY> sty{wbase, nullptr};
+  SegStage<(E::NU > 0 ? E::RUN_JU : 1)> stu{wbase, nullptr};
   const int64_t stride = (int64_t)gridDim.x * nwarps;
   for (int64_t tile = (int64_t)blockIdx.x * nwarps + warp; tile < D.ntiles; tile += stride) {
     const int64_t cell = tile * 32 + lane;
@@ -1106,7 +1128,8 @@ k_jac_coord_mf(const __grid_constant__ Tables<E> tab, const DevModel D, const do
       const int cnt = fy * fy;
       const int incl = warp_incl_scan(cnt, lane);
       double* gdst = vals_y + D.base_jy[tile];
-      sty.acquire(lane);
+      if (NBUF > 1) { sty.wbuf = wbase + slot * STAGE; slot = slot + 1 == NBUF ? 0 : slot + 1; }
+      sty.template acquire<NBUF>(lane);
       double* const p0 = sty.begin(gdst, incl - cnt, lane);
 #pragma unroll 1
       for (int q = 0; q < E::NQ; ++q) {
@@ -1122,7 +1145,8 @@ k_jac_coord_mf(const __grid_constant__ Tables<E> tab, const DevModel D, const do
       const int cnt = fy * fu;
       const int incl = warp_incl_scan(cnt, lane);
       double* gdst = vals_u + D.base_ju[tile];
-      stu.acquire(lane);
+      if (NBUF > 1) { stu.wbuf = wbase + slot * STAGE; slot = slot + 1 == NBUF ? 0 : slot + 1; }
+      stu.template acquire<NBUF>(lane);
       double* const p0 = stu.begin(gdst, incl - cnt, lane);
 #pragma unroll 1
       for (int q = 0; q < E::NQ; ++q) {
@@ -1217,8 +1241,10 @@ k_hess_coord_mf(const __grid_constant__ Tables<E> tab, const DevModel D, const d
   using I = typename E::Integrand;
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  constexpr int STAGE = hess_stage_doubles<E>();
-  SegStage<E::RUN_H> st{smem + warp * STAGE, nullptr};
+  constexpr int STAGE = hess_stage_doubles<E>(), NBUF = coord_nbuf(STAGE);
+  double* const wbase = smem + warp * STAGE * NBUF;
+  int slot = 0;
+  SegStage<E::RUN_H> st{wbase, nullptr};
   const int64_t stride = (int64_t)gridDim.x * nwarps;
   for (int64_t tile = (int64_t)blockIdx.x * nwarps + warp; tile < D.ntiles; tile += stride) {
     const int64_t cell = tile * 32 + lane;
@@ -1232,7 +1258,8 @@ k_hess_coord_mf(const __grid_constant__ Tables<E> tab, const DevModel D, const d
     const int64_t tb = D.base_h[tile];
     if (vals_obj != nullptr) {
       double* gdst = vals_obj + tb;
-      st.acquire(lane);
+      if (NBUF > 1) { st.wbuf = wbase + slot * STAGE; slot = slot + 1 == NBUF ? 0 : slot + 1; }
+      st.template acquire<NBUF>(lane);
       double* const p0 = st.begin(gdst, incl - cnt, lane);
 #pragma unroll 1
       for (int q = 0; q < E::NQ; ++q) {
@@ -1249,7 +1276,8 @@ k_hess_coord_mf(const __grid_constant__ Tables<E> tab, const DevModel D, const d
       double lam_e[E::NY];
       gather_free<E::NY>(lambda, c.gy, lam_e);
       double* gdst = vals_con + tb;
-      st.acquire(lane);
+      if (NBUF > 1) { st.wbuf = wbase + slot * STAGE; slot = slot + 1 == NBUF ? 0 : slot + 1; }
+      st.template acquire<NBUF>(lane);
       double* const p0 = st.begin(gdst, incl - cnt, lane);
 #pragma unroll 1
       for (int q = 0; q < E::NQ; ++q) {
@@ -1309,6 +1337,21 @@ k_structure(const DevModel D, int kind, int64_t* __restrict__ rows, int64_t* __r
           if (gr > 0 && (kind != 2 || gc <= gr)) { rows[n] = gr + shift_r; cols[n] = gc + shift; ++n; }
         }
       }
+}
+
+// Sum of one value per thread over the CTA, added to *dst by ONE atomic (thread 0).  The kappa entries are
+// single addresses: one atomic per warp (~9500 same-address atomics per launch) serialised in L2 and cost
+// 30-40 us per kernel at 10^6 cells.  Must be called by all threads of the CTA.
+__device__ __forceinline__ void cta_sum_atomic(double v, double* dst, double* red /* [kWarpsPerCta] shared */) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += red[w];
+    atomicAdd(dst, a);
+  }
+  __syncthreads();
 }
 
 // ------------------------------------------------------------------ vector-valued callbacks
@@ -1543,10 +1586,15 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
       partials[blockIdx.x] = a;
     }
   } else if (E::NP > 0 && (OP == OP_GRAD || OP == OP_JTPROD || OP == OP_HPROD)) {
+    if (E::M >= 6 && OP == OP_HPROD) {  // register-bound instance (Jet2<7>): keep the plain per-warp atomics
 #pragma unroll
-    for (int k = 0; k < E::NP; ++k) {
-      const double a = warp_sum(ksum[k]);
-      if (lane == 0) atomicAdd(out + k, a);
+      for (int k = 0; k < E::NP; ++k) {
+        const double a = warp_sum(ksum[k]);
+        if (lane == 0) atomicAdd(out + k, a);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < E::NP; ++k) cta_sum_atomic(ksum[k], out + k, red);
     }
   }
 }
@@ -1711,13 +1759,11 @@ k_hess_kappa_kk(const __grid_constant__ Tables<E> tab, const DevModel D, const d
         for (int i = j; i < E::NP; ++i) kk[i][j] += scale * F.h[JK::idx(i, j)];
     }
   }
+  __shared__ double red[kWarpsPerCta];
 #pragma unroll
   for (int j = 0; j < E::NP; ++j)
 #pragma unroll
-    for (int i = j; i < E::NP; ++i) {
-      const double a = warp_sum(kk[i][j]);
-      if (lane == 0) atomicAdd(vk + trap_pos(i + 1, j + 1, E::NP), a);
-    }
+    for (int i = j; i < E::NP; ++i) cta_sum_atomic(kk[i][j], vk + trap_pos(i + 1, j + 1, E::NP), red);
 }
 
 // which: 0 = objective (scaled by obj_weight), 1 = constraints (lambda-weighted residual)
@@ -1794,13 +1840,11 @@ k_hess_kappa(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
       }
     }
   }
+  __shared__ double red[kWarpsPerCta];
 #pragma unroll
   for (int j = 0; j < E::NP; ++j)
 #pragma unroll
-    for (int i = j; i < E::NP; ++i) {
-      const double a = warp_sum(kk[i][j]);
-      if (lane == 0) atomicAdd(vk + trap_pos(i + 1, j + 1, prows), a);
-    }
+    for (int i = j; i < E::NP; ++i) cta_sum_atomic(kk[i][j], vk + trap_pos(i + 1, j + 1, prows), red);
 }
 
 }  // namespace pdenlp

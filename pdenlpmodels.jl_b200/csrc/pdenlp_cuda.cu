@@ -69,10 +69,13 @@ struct OpsImpl : Ops {
   bool attr_done = false;
   std::vector<double> ktab_;
   const std::vector<double>& ktab() const override { return ktab_; }
-  static constexpr int WJ = warps_for_stage(jac_stage_doubles<E>(), KTab<E>::TOTAL);
-  static constexpr int WH = warps_for_stage(hess_stage_doubles<E>(), KTab<E>::TOTAL);
-  static constexpr size_t SMEM_J = ((size_t)WJ * jac_stage_doubles<E>() + KTab<E>::TOTAL) * 8;
-  static constexpr size_t SMEM_H = ((size_t)WH * hess_stage_doubles<E>() + KTab<E>::TOTAL) * 8;
+  // per-warp staging = (buffer size) x (number of rotating buffers, > 1 only for small elements)
+  static constexpr int STJ = jac_stage_doubles<E>() * coord_nbuf(jac_stage_doubles<E>());
+  static constexpr int STH = hess_stage_doubles<E>() * coord_nbuf(hess_stage_doubles<E>());
+  static constexpr int WJ = warps_for_stage(STJ, KTab<E>::TOTAL);
+  static constexpr int WH = warps_for_stage(STH, KTab<E>::TOTAL);
+  static constexpr size_t SMEM_J = ((size_t)WJ * STJ + KTab<E>::TOTAL) * 8;
+  static constexpr size_t SMEM_H = ((size_t)WH * STH + KTab<E>::TOTAL) * 8;
 
   // multi-field elements run the block-ordered kernels
   using JacKernel = void (*)(const Tables<E>, const DevModel, const double*, double*, double*);
