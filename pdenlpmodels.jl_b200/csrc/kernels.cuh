@@ -612,6 +612,21 @@ __host__ __device__ constexpr int coord_nbuf(int stage_doubles) {
 // with the occupancy API.
 template <class E>
 constexpr int coord_min_blocks() { return (E::RUN_H <= 48 && E::NQ == 1) ? 2 : 1; }
+// Small elements also prefetch the next tile's segment offsets (a dependent global load per segment that is a
+// visible part of their short per-tile time); for the large elements the extra live registers cost more than the
+// load latency (measured on config 2: jac 0.67 -> 0.73 ms), so they load the offsets at the point of use.
+// Measured: config 3 (Q1/Q1 2-D, RUN_H = 36) jac 0.081 -> 0.064 ms but hess 0.124 -> 0.136 ms (its Hessian kernel sits at
+// the 128-register cap of two CTAs per SM); config 4 (P1/P1 1-D, RUN_H = 10) jac 0.046 -> 0.040, hess 0.105 -> 0.101 ms.
+#ifndef PDENLP_PREFETCH_BASE_RUN_J
+#define PDENLP_PREFETCH_BASE_RUN_J 48
+#endif
+#ifndef PDENLP_PREFETCH_BASE_RUN_H
+#define PDENLP_PREFETCH_BASE_RUN_H 16
+#endif
+template <class E, bool HESS>
+__host__ __device__ constexpr bool coord_prefetch_base() {
+  return E::RUN_H <= (HESS ? PDENLP_PREFETCH_BASE_RUN_H : PDENLP_PREFETCH_BASE_RUN_J);
+}
 
 template <class E>
 __global__ void __launch_bounds__(kThreads, coord_min_blocks<E>())
@@ -643,17 +658,21 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
     const bool nvalid = (tile + stride) < D.ntiles && ncell < D.ncells;
     load_ids<E>(D, nvalid ? ncell : 0, nvalid, n);
   }
+  constexpr bool PFB = coord_prefetch_base<E, false>();
+  int64_t b_jy = PFB ? D.base_jy[tile] : 0, b_ju = (PFB && E::NU > 0) ? D.base_ju[tile] : 0;
   while (true) {
     const int64_t cell = tile * 32 + lane;
     const bool valid = cell < D.ncells;
     const int64_t tnext = tile + stride;
     const bool has_next = tnext < D.ntiles;
     Cell<E> nn;
+    int64_t nb_jy = 0, nb_ju = 0;
     {
       gather_state<E>(D, x, has_next && (tnext * 32 + lane) < D.ncells, n);
       const int64_t c2 = (tnext + stride) * 32 + lane;
       const bool v2 = (tnext + stride) < D.ntiles && c2 < D.ncells;
       load_ids<E>(D, v2 ? c2 : 0, v2, nn);
+      if (PFB && has_next) { nb_jy = D.base_jy[tnext]; if (E::NU > 0) nb_ju = D.base_ju[tnext]; }
     }
 
     int fy = 0, fu = 0;
@@ -692,7 +711,7 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
     {
       const int cnt = fy * fy;
       const int incl = warp_incl_scan(cnt, lane);
-      double* gdst = vals_y + D.base_jy[tile];
+      double* gdst = vals_y + (PFB ? b_jy : D.base_jy[tile]);
       if (NBUF > 1) { sty.wbuf = wbase + slot * STAGE; slot = slot + 1 == NBUF ? 0 : slot + 1; }
       sty.template acquire<NBUF>(lane);
       double* const p0 = sty.begin(gdst, incl - cnt, lane);
@@ -732,7 +751,7 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
     if (E::NU > 0) {
       const int cnt = fy * fu;
       const int incl = warp_incl_scan(cnt, lane);
-      double* gdst = vals_u + D.base_ju[tile];
+      double* gdst = vals_u + (PFB ? b_ju : D.base_ju[tile]);
       if (NBUF > 1) { stu.wbuf = wbase + slot * STAGE; slot = slot + 1 == NBUF ? 0 : slot + 1; }
       stu.template acquire<NBUF>(lane);
       double* const p0 = stu.begin(gdst, incl - cnt, lane);
@@ -769,6 +788,7 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
     for (int a = 0; a < E::NY; ++a) n.gy[a] = nn.gy[a];
 #pragma unroll
     for (int b = 0; b < E::NUS; ++b) n.gu[b] = nn.gu[b];
+    b_jy = nb_jy; b_ju = nb_ju;
     tile = tnext;
   }
   sty.drain(lane);
@@ -935,23 +955,27 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
   }
   double lam_e[E::NY], nlam[E::NY];
   if (vals_con != nullptr) gather_free<E::NY>(lambda, c.gy, lam_e);
+  constexpr bool PFB = coord_prefetch_base<E, true>();
+  int64_t b_h = PFB ? D.base_h[tile] : 0;
   while (true) {
     const int64_t cell = tile * 32 + lane;
     const bool valid = cell < D.ncells;
     const int64_t tnext = tile + stride;
     const bool has_next = tnext < D.ntiles;
     Cell<E> nn;
+    int64_t nb_h = 0;
     {
       gather_state<E>(D, x, has_next && (tnext * 32 + lane) < D.ncells, n);
       if (vals_con != nullptr) gather_free<E::NY>(lambda, n.gy, nlam);
       const int64_t c2 = (tnext + stride) * 32 + lane;
       const bool v2 = (tnext + stride) < D.ntiles && c2 < D.ncells;
       load_ids<E>(D, v2 ? c2 : 0, v2, nn);
+      if (PFB && has_next) nb_h = D.base_h[tnext];
     }
     int fy, fu, cnt;
     closed_counts<E>(c, fy, fu, cnt);
     const int incl = warp_incl_scan(cnt, lane);
-    const int64_t tb = D.base_h[tile];
+    const int64_t tb = PFB ? b_h : D.base_h[tile];
 
     const int n11 = fy * (fy + 1) / 2;  // kept entries of block (1,1) (distinct ids)
     // One staged FE block of the tile.  jet_at(q, scale) returns the pointwise Jet2 whose Hessian
@@ -1032,6 +1056,7 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
     for (int a = 0; a < E::NY; ++a) { n.gy[a] = nn.gy[a]; lam_e[a] = nlam[a]; }
 #pragma unroll
     for (int b = 0; b < E::NUS; ++b) n.gu[b] = nn.gu[b];
+    b_h = nb_h;
     tile = tnext;
   }
   st.drain(lane);
