@@ -51,11 +51,11 @@ def _host_cores() -> int:
 
 def _ncu_traffic(n, world, kernel="k_jac_coord"):
     """dram__bytes_read.sum + dram__bytes_write.sum of one kernel per launch from the committed
-    `ncu --set full` capture (profiles/r01_v5_ncu_summary.json); only valid for the captured workload."""
+    `ncu --set full` capture (profiles/r01_final_ncu_summary.json); only valid for the captured workload."""
     if n != 2048 or world != 1:
         return None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_v5_ncu_summary.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r01_final_ncu_summary.json")) as fh:
             d = [e for e in json.load(fh) if kernel + "<" in e.get("Kernel Name", "")][0]
         unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         tot = 0.0
