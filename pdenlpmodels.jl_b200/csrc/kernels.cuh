@@ -1138,12 +1138,35 @@ k_jac_coord_mf(const __grid_constant__ Tables<E> tab, const DevModel D, const do
   SegStage<E::RUN_JY> sty{wbase, nullptr};
   SegStage<(E::NU > 0 ? E::RUN_JU : 1)> stu{wbase, nullptr};
   const int64_t stride = (int64_t)gridDim.x * nwarps;
-  for (int64_t tile = (int64_t)blockIdx.x * nwarps + warp; tile < D.ntiles; tile += stride) {
+  int64_t tile = (int64_t)blockIdx.x * nwarps + warp;
+  if (tile >= D.ntiles) return;
+  // the same register pipeline as k_jac_coord: state of tile t+stride, ids of tile t+2*stride and the segment
+  // offsets of tile t+stride are in flight while tile t is processed
+  Cell<E> c, n;
+  {
     const int64_t cell = tile * 32 + lane;
     const bool valid = cell < D.ncells;
-    Cell<E> c;
     load_ids<E>(D, valid ? cell : 0, valid, c);
     gather_state<E>(D, x, valid, c);
+    const int64_t ncell = (tile + stride) * 32 + lane;
+    const bool nvalid = (tile + stride) < D.ntiles && ncell < D.ncells;
+    load_ids<E>(D, nvalid ? ncell : 0, nvalid, n);
+  }
+  int64_t b_jy = D.base_jy[tile], b_ju = E::NU > 0 ? D.base_ju[tile] : 0;
+  while (true) {
+    const int64_t cell = tile * 32 + lane;
+    const bool valid = cell < D.ncells;
+    const int64_t tnext = tile + stride;
+    const bool has_next = tnext < D.ntiles;
+    Cell<E> nn;
+    int64_t nb_jy = 0, nb_ju = 0;
+    {
+      gather_state<E>(D, x, has_next && (tnext * 32 + lane) < D.ncells, n);
+      const int64_t c2 = (tnext + stride) * 32 + lane;
+      const bool v2 = (tnext + stride) < D.ntiles && c2 < D.ncells;
+      load_ids<E>(D, v2 ? c2 : 0, v2, nn);
+      if (has_next) { nb_jy = D.base_jy[tnext]; if (E::NU > 0) nb_ju = D.base_ju[tnext]; }
+    }
     int fy = 0, fu = 0;
 #pragma unroll
     for (int a = 0; a < E::NY; ++a) fy += c.gy[a] > 0;
@@ -1152,7 +1175,7 @@ k_jac_coord_mf(const __grid_constant__ Tables<E> tab, const DevModel D, const do
     {
       const int cnt = fy * fy;
       const int incl = warp_incl_scan(cnt, lane);
-      double* gdst = vals_y + D.base_jy[tile];
+      double* gdst = vals_y + b_jy;
       if (NBUF > 1) { sty.wbuf = wbase + slot * STAGE; slot = slot + 1 == NBUF ? 0 : slot + 1; }
       sty.template acquire<NBUF>(lane);
       double* const p0 = sty.begin(gdst, incl - cnt, lane);
@@ -1169,7 +1192,7 @@ k_jac_coord_mf(const __grid_constant__ Tables<E> tab, const DevModel D, const do
     if (E::NU > 0) {
       const int cnt = fy * fu;
       const int incl = warp_incl_scan(cnt, lane);
-      double* gdst = vals_u + D.base_ju[tile];
+      double* gdst = vals_u + b_ju;
       if (NBUF > 1) { stu.wbuf = wbase + slot * STAGE; slot = slot + 1 == NBUF ? 0 : slot + 1; }
       stu.template acquire<NBUF>(lane);
       double* const p0 = stu.begin(gdst, incl - cnt, lane);
@@ -1183,6 +1206,14 @@ k_jac_coord_mf(const __grid_constant__ Tables<E> tab, const DevModel D, const do
       }
       stu.release(gdst, incl - cnt, incl, lane);
     }
+    if (!has_next) break;
+    c = n;
+#pragma unroll
+    for (int a = 0; a < E::NY; ++a) n.gy[a] = nn.gy[a];
+#pragma unroll
+    for (int b = 0; b < E::NUS; ++b) n.gu[b] = nn.gu[b];
+    b_jy = nb_jy; b_ju = nb_ju;
+    tile = tnext;
   }
   sty.drain(lane);
 }
@@ -1271,16 +1302,37 @@ k_hess_coord_mf(const __grid_constant__ Tables<E> tab, const DevModel D, const d
   int slot = 0;
   SegStage<E::RUN_H> st{wbase, nullptr};
   const int64_t stride = (int64_t)gridDim.x * nwarps;
-  for (int64_t tile = (int64_t)blockIdx.x * nwarps + warp; tile < D.ntiles; tile += stride) {
+  int64_t tile = (int64_t)blockIdx.x * nwarps + warp;
+  if (tile >= D.ntiles) return;
+  Cell<E> c, n;  // register pipeline over tiles, as in k_hess_coord
+  {
     const int64_t cell = tile * 32 + lane;
     const bool valid = cell < D.ncells;
-    Cell<E> c;
     load_ids<E>(D, valid ? cell : 0, valid, c);
     gather_state<E>(D, x, valid, c);
+    const int64_t ncell = (tile + stride) * 32 + lane;
+    const bool nvalid = (tile + stride) < D.ntiles && ncell < D.ncells;
+    load_ids<E>(D, nvalid ? ncell : 0, nvalid, n);
+  }
+  int64_t b_h = D.base_h[tile];
+  while (true) {
+    const int64_t cell = tile * 32 + lane;
+    const bool valid = cell < D.ncells;
+    const int64_t tnext = tile + stride;
+    const bool has_next = tnext < D.ntiles;
+    Cell<E> nn;
+    int64_t nb_h = 0;
+    {
+      gather_state<E>(D, x, has_next && (tnext * 32 + lane) < D.ncells, n);
+      const int64_t c2 = (tnext + stride) * 32 + lane;
+      const bool v2 = (tnext + stride) < D.ntiles && c2 < D.ncells;
+      load_ids<E>(D, v2 ? c2 : 0, v2, nn);
+      if (has_next) nb_h = D.base_h[tnext];
+    }
     int fy, fu, cnt;
     closed_counts<E>(c, fy, fu, cnt);
     const int incl = warp_incl_scan(cnt, lane);
-    const int64_t tb = D.base_h[tile];
+    const int64_t tb = b_h;
     if (vals_obj != nullptr) {
       double* gdst = vals_obj + tb;
       if (NBUF > 1) { st.wbuf = wbase + slot * STAGE; slot = slot + 1 == NBUF ? 0 : slot + 1; }
@@ -1316,6 +1368,14 @@ k_hess_coord_mf(const __grid_constant__ Tables<E> tab, const DevModel D, const d
       }
       st.release(gdst, incl - cnt, incl, lane);
     }
+    if (!has_next) break;
+    c = n;
+#pragma unroll
+    for (int a = 0; a < E::NY; ++a) n.gy[a] = nn.gy[a];
+#pragma unroll
+    for (int b = 0; b < E::NUS; ++b) n.gu[b] = nn.gu[b];
+    b_h = nb_h;
+    tile = tnext;
   }
   st.drain(lane);
 }
