@@ -612,6 +612,15 @@ __host__ __device__ constexpr int coord_nbuf(int stage_doubles) {
 // with the occupancy API.
 template <class E>
 constexpr int coord_min_blocks() { return (E::RUN_H <= 48 && E::NQ == 1) ? 2 : 1; }
+// Several quadrature points without the reference-tensor path (a residual / objective that is not affine in the
+// fields, e.g. the sinh term with degree 2): small elements sum their element blocks over the points in registers
+// and stage them once, instead of a shared-memory read-modify-write per entry and point.
+// (Integrands that declare FE_DERIVS_POINT_INDEPENDENT take the reference-tensor path instead.)
+template <class E>
+__host__ __device__ constexpr bool coord_reg_accumulate() {
+  return E::NQ > 1 && E::NY <= 4 && E::NU <= 4 && !E::MULTI &&
+         !(KTab<E>::ENABLED && E::Integrand::FE_DERIVS_POINT_INDEPENDENT);
+}
 // Small elements also prefetch the next tile's segment offsets (a dependent global load per segment that is a
 // visible part of their short per-tile time); for the large elements the extra live registers cost more than the
 // load latency (measured on config 2: jac 0.67 -> 0.73 ms), so they load the offsets at the point of use.
@@ -684,7 +693,51 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
     // K-path test (nq > 1): is dR/d(y, grad y, u) the same at every quadrature point, on all lanes?
     bool kpath = false;
     Jet1<E::M> R0[E::NR];
-    if (KTab<E>::ENABLED && Ks != nullptr) {
+    constexpr bool RA = coord_reg_accumulate<E>();
+    double A[E::NY][E::NY], B[E::NUS][E::NY];  // element blocks summed over the points (RA elements only)
+    if (RA) {  // one pass over the quadrature points for both blocks
+#pragma unroll
+      for (int j = 0; j < E::NY; ++j)
+#pragma unroll
+        for (int i = 0; i < E::NY; ++i) A[j][i] = 0.0;
+#pragma unroll
+      for (int b = 0; b < E::NUS; ++b)
+#pragma unroll
+        for (int i = 0; i < E::NY; ++i) B[b][i] = 0.0;
+#pragma unroll 1
+      for (int q = 0; q < E::NQ; ++q) {
+        Jet1<E::M> s[E::M], R[E::NR];
+        point_state<E>(tab, c, x, q, s);
+        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        I::res(pc, s, R);
+#pragma unroll
+        for (int j = 0; j < E::NY; ++j) {
+          double Mj[E::NR];
+#pragma unroll
+          for (int t = 0; t < E::NR; ++t) {
+            double a = 0.0;
+#pragma unroll
+            for (int k = 0; k < E::NB; ++k) a = fma(R[t].g[k], tab.By[q][j][k], a);
+            Mj[t] = a * tab.wdet[q];
+          }
+#pragma unroll
+          for (int i = 0; i < E::NY; ++i)
+#pragma unroll
+            for (int t = 0; t < E::NR; ++t) A[j][i] = fma(test_slot<E>(tab, q, i, t), Mj[t], A[j][i]);
+        }
+#pragma unroll
+        for (int b = 0; b < E::NU; ++b) {
+          double Mb[E::NR];
+#pragma unroll
+          for (int t = 0; t < E::NR; ++t) Mb[t] = R[t].g[E::SU] * tab.Bu[q][b] * tab.wdet[q];
+#pragma unroll
+          for (int i = 0; i < E::NY; ++i)
+#pragma unroll
+            for (int t = 0; t < E::NR; ++t) B[b][i] = fma(test_slot<E>(tab, q, i, t), Mb[t], B[b][i]);
+        }
+      }
+    }
+    if (KTab<E>::ENABLED && Ks != nullptr && !RA) {
       bool uni = true;
       // integrands that declare FE_DERIVS_POINT_INDEPENDENT are evaluated at the first point only
       constexpr int NQT = I::FE_DERIVS_POINT_INDEPENDENT ? 1 : E::NQ;
@@ -716,7 +769,16 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
       sty.template acquire<NBUF>(lane);
       double* const p0 = sty.begin(gdst, incl - cnt, lane);
       if (kpath) emit_jac_y_K<E>(Ks, R0, c, p0);
-      else
+      else if (RA) {
+        double* p = p0;
+#pragma unroll
+        for (int j = 0; j < E::NY; ++j)
+          if (c.gy[j] > 0) {
+#pragma unroll
+            for (int i = 0; i < E::NY; ++i)
+              if (c.gy[i] > 0) { *p = A[j][i]; ++p; }
+          }
+      } else
 #pragma unroll 1
       for (int q = 0; q < E::NQ; ++q) {
         Jet1<E::M> s[E::M], R[E::NR];
@@ -756,7 +818,16 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
       stu.template acquire<NBUF>(lane);
       double* const p0 = stu.begin(gdst, incl - cnt, lane);
       if (kpath) emit_jac_u_K<E>(Ks, R0, c, p0);
-      else
+      else if (RA) {
+        double* p = p0;
+#pragma unroll
+        for (int b = 0; b < E::NU; ++b)
+          if (c.gu[b] > 0) {
+#pragma unroll
+            for (int i = 0; i < E::NY; ++i)
+              if (c.gy[i] > 0) { *p = B[b][i]; ++p; }
+          }
+      } else
 #pragma unroll 1
       for (int q = 0; q < E::NQ; ++q) {
         Jet1<E::M> s[E::M], R[E::NR];
@@ -986,10 +1057,12 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
       if (NBUF > 1) { st.wbuf = wbase + slot * STAGE; slot = slot + 1 == NBUF ? 0 : slot + 1; }
       st.template acquire<NBUF>(lane);
       double* const p0 = st.begin(gdst, incl - cnt, lane);
-      bool zyy = true, zu = true, quni = true;
+      // (elements that sum their blocks over the points in registers skip the test pass: no zero / uniformity tests)
+      constexpr bool RA = coord_reg_accumulate<E>();
+      bool zyy = !RA, zu = !RA, quni = true;
       Jet2<E::M> L, L0;
       double sc = 0.0;  // quadrature-weight-free scale (obj_weight or 1)
-      constexpr int NQT = (KTab<E>::ENABLED && I::FE_DERIVS_POINT_INDEPENDENT) ? 1 : E::NQ;
+      constexpr int NQT = RA ? 0 : ((KTab<E>::ENABLED && I::FE_DERIVS_POINT_INDEPENDENT) ? 1 : E::NQ);
 #pragma unroll 1
       for (int q = 0; q < NQT; ++q) {
         L = jet_at(q, sc);
@@ -1007,7 +1080,7 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
       }
       zyy = __all_sync(0xffffffffu, zyy || !valid);
       zu = __all_sync(0xffffffffu, zu || !valid);
-      const bool kpath = KTab<E>::ENABLED && Ks != nullptr && __all_sync(0xffffffffu, quni || !valid);
+      const bool kpath = !RA && KTab<E>::ENABLED && Ks != nullptr && __all_sync(0xffffffffu, quni || !valid);
       if (zyy && zu) {
         st.zero_fill(__shfl_sync(0xffffffffu, incl, 31), lane);
       } else if (kpath) {  // q-independent second derivatives: pre-integrated tensors, one pass
@@ -1016,6 +1089,79 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
         else { for (int k = 0; k < n11; ++k) p[k] = 0.0; p += n11; }
         if (!zu) emit_hess_u_K<E>(Ks, L0, sc, c, p);
         else for (int k = 0; k < cnt - n11; ++k) p[k] = 0.0;
+      } else if (RA) {  // sum the element blocks over the points in registers, stage once
+        using J2 = Jet2<E::M>;
+        double Hyy[E::NY][E::NY], Huy[E::NY][E::NUS], Huu[E::NUS][E::NUS];
+#pragma unroll
+        for (int j = 0; j < E::NY; ++j) {
+#pragma unroll
+          for (int i = 0; i < E::NY; ++i) Hyy[j][i] = 0.0;
+#pragma unroll
+          for (int i = 0; i < E::NUS; ++i) Huy[j][i] = 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < E::NUS; ++j)
+#pragma unroll
+          for (int i = 0; i < E::NUS; ++i) Huu[j][i] = 0.0;
+#pragma unroll 1
+        for (int q = 0; q < E::NQ; ++q) {
+          L = jet_at(q, sc);
+          const double scale = sc * tab.wdet[q];
+#pragma unroll
+          for (int j = 0; j < E::NY; ++j) {
+            double Nj[E::NB];
+#pragma unroll
+            for (int k = 0; k < E::NB; ++k) {
+              double a = 0.0;
+#pragma unroll
+              for (int l = 0; l < E::NB; ++l) a = fma(L.h[J2::idx(k, l)], tab.By[q][j][l], a);
+              Nj[k] = a * scale;
+            }
+#pragma unroll
+            for (int i = 0; i < E::NY; ++i)
+#pragma unroll
+              for (int k = 0; k < E::NB; ++k) Hyy[j][i] = fma(tab.By[q][i][k], Nj[k], Hyy[j][i]);
+            if (E::NU > 0) {
+              double a = 0.0;
+#pragma unroll
+              for (int l = 0; l < E::NB; ++l) a = fma(L.h[J2::idx(E::SU, l)], tab.By[q][j][l], a);
+              a *= scale;
+#pragma unroll
+              for (int i = 0; i < E::NU; ++i) Huy[j][i] = fma(tab.Bu[q][i], a, Huy[j][i]);
+            }
+          }
+          if (E::NU > 0) {
+            const double duu = L.h[J2::idx(E::SU, E::SU)] * scale;
+#pragma unroll
+            for (int j = 0; j < E::NU; ++j)
+#pragma unroll
+              for (int i = 0; i < E::NU; ++i) Huu[j][i] = fma(tab.Bu[q][i] * tab.Bu[q][j], duu, Huu[j][i]);
+          }
+        }
+        double* p = p0;
+#pragma unroll
+        for (int j = 0; j < E::NY; ++j)
+          if (c.gy[j] > 0) {
+#pragma unroll
+            for (int i = 0; i < E::NY; ++i)
+              if (c.gy[j] <= c.gy[i]) { *p = Hyy[j][i]; ++p; }
+          }
+        if (E::NU > 0) {
+#pragma unroll
+          for (int j = 0; j < E::NY; ++j)
+            if (c.gy[j] > 0) {
+#pragma unroll
+              for (int i = 0; i < E::NU; ++i)
+                if (c.gu[i] > 0) { *p = Huy[j][i]; ++p; }
+            }
+#pragma unroll
+          for (int j = 0; j < E::NU; ++j)
+            if (c.gu[j] > 0) {
+#pragma unroll
+              for (int i = 0; i < E::NU; ++i)
+                if (c.gu[j] <= c.gu[i]) { *p = Huu[j][i]; ++p; }
+            }
+        }
       } else {
 #pragma unroll 1
         for (int q = 0; q < E::NQ; ++q) {
