@@ -1832,7 +1832,7 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
 
 // Zero fill of a COO segment that is structurally zero (constraint FE Hessian block of an affine
 // residual, or hess_coord! without multipliers): pure streaming 16 B stores, 4 per thread per step.
-__global__ void __launch_bounds__(256) k_zero_fill(double* __restrict__ p, int64_t n) {
+static __global__ void __launch_bounds__(256) k_zero_fill(double* __restrict__ p, int64_t n) {
   const int64_t head = (n > 0 && ((reinterpret_cast<uintptr_t>(p) >> 3) & 1)) ? 1 : 0;  // 8 B-aligned start
   const int64_t n2 = (n - head) >> 1;
   double2* q = reinterpret_cast<double2*>(p + head);
@@ -1855,7 +1855,7 @@ __global__ void __launch_bounds__(256) k_zero_fill(double* __restrict__ p, int64
 }
 
 // fixed-order final sum of the per-CTA objective partials
-__global__ void k_sum_partials(const double* __restrict__ partials, int n, double* __restrict__ out) {
+static __global__ void k_sum_partials(const double* __restrict__ partials, int n, double* __restrict__ out) {
   __shared__ double sh[256];
   double a = 0.0;
   for (int i = threadIdx.x; i < n; i += 256) a += partials[i];

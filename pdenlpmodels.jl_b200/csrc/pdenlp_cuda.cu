@@ -4,8 +4,7 @@
 // template instantiation for the (integrand, element) pair, launches the kernels of
 // kernels.cuh on the caller's stream.  No CPU compute path exists: every entry point
 // needs an sm_100 device.
-#include "../../include/pdenlp_cuda.h"
-#include "kernels.cuh"
+#include "ops.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -17,250 +16,18 @@
 
 using namespace pdenlp;
 
-thread_local std::string pdenlp_g_err;  // shared with compaction.cu
+thread_local std::string pdenlp_g_err;  // shared with compaction.cu and the ops_*.cu units
+
+using namespace pdenlp::host;
 
 namespace {
 
-int fail(int code, const std::string& msg) {
-  pdenlp_g_err = msg;
-  return code;
-}
-#define CU(call)                                                                                   \
-  do {                                                                                             \
-    cudaError_t e__ = (call);                                                                      \
-    if (e__ != cudaSuccess)                                                                        \
-      return fail(PDENLP_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));              \
-  } while (0)
-
-struct Launch {
-  cudaStream_t stream;
-  int sms;
-};
-
-// type-erased per-element operations
-struct Ops {
-  virtual ~Ops() {}
-  virtual int count(const DevModel& D, int32_t* counts, int32_t* flag, cudaStream_t s) = 0;
-  virtual int jac(const Launch& L, const DevModel& D, const double* x, double* vy, double* vu) = 0;
-  virtual int hess(const Launch& L, const DevModel& D, const double* x, const double* lam, double ow, double* vo, double* vc) = 0;
-  virtual int structure(const Launch& L, const DevModel& D, int kind, int64_t* r, int64_t* c, int64_t shift) = 0;
-  virtual int vec(const Launch& L, const DevModel& D, int op, const double* x, const double* lam, const double* v,
-                  double ow, double* out, double* partials, int* nblocks) = 0;
-  virtual int jac_kappa(const Launch& L, const DevModel& D, const double* x, double* vk) = 0;
-  virtual int hess_kappa(const Launch& L, const DevModel& D, const double* x, const double* lam, double ow, int which,
-                         int64_t prows, double* vk) = 0;
-  virtual int run_h() const = 0;
-  virtual bool needs_coef_deriv() const = 0;  // derivative callbacks read the coefficient fields
-  virtual bool res_fe_hessian_zero() const = 0;  // constraint FE Hessian block is structurally zero
-  virtual bool no_fe_obj() const = 0;            // NoFETerm objective fk(kappa)
-  virtual bool is_multi() const = 0;             // multi-field element (block-ordered kernels)
-  virtual int nofe(const Launch& L, int mode, const double* x, double ow, const double* v, double* out) = 0;
-  virtual const std::vector<double>& ktab() const = 0;  // pre-integrated reference tensors (may be empty)
-};
-
-constexpr int warps_for_stage(int stage_doubles, int reserved_doubles) {
-  // per-warp staging buffer; at most 8 warps (launch bounds), at most ~225 KB per CTA
-  return std::min(8, (225 * 1024 - reserved_doubles * 8) / (stage_doubles * 8));
-}
-
-template <class E>
-struct OpsImpl : Ops {
-  Tables<E> tab;
-  bool attr_done = false;
-  std::vector<double> ktab_;
-  const std::vector<double>& ktab() const override { return ktab_; }
-  // per-warp staging = (buffer size) x (number of rotating buffers, > 1 only for small elements)
-  static constexpr int STJ = jac_stage_doubles<E>() * coord_nbuf(jac_stage_doubles<E>());
-  static constexpr int STH = hess_stage_doubles<E>() * coord_nbuf(hess_stage_doubles<E>());
-  static constexpr int WJ = warps_for_stage(STJ, KTab<E>::TOTAL);
-  static constexpr int WH = warps_for_stage(STH, KTab<E>::TOTAL);
-  static constexpr size_t SMEM_J = ((size_t)WJ * STJ + KTab<E>::TOTAL) * 8;
-  static constexpr size_t SMEM_H = ((size_t)WH * STH + KTab<E>::TOTAL) * 8;
-
-  // multi-field elements run the block-ordered kernels
-  using JacKernel = void (*)(const Tables<E>, const DevModel, const double*, double*, double*);
-  using HessKernel = void (*)(const Tables<E>, const DevModel, const double*, const double*, double, double*, double*);
-  static JacKernel jac_kernel() {
-    if constexpr (E::MULTI) return k_jac_coord_mf<E>; else return k_jac_coord<E>;
-  }
-  static HessKernel hess_kernel() {
-    if constexpr (E::MULTI) return k_hess_coord_mf<E>; else return k_hess_coord<E>;
-  }
-  int occ_j = 1, occ_h = 1;  // resident CTAs per SM of the persistent coord kernels
-  int set_attrs() {
-    if (attr_done) return PDENLP_OK;
-    CU(cudaFuncSetAttribute(jac_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_J));
-    CU(cudaFuncSetAttribute(hess_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_H));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_j, jac_kernel(), WJ * 32, SMEM_J));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_h, hess_kernel(), WH * 32, SMEM_H));
-    occ_j = std::max(1, std::min(occ_j, 4));
-    occ_h = std::max(1, std::min(occ_h, 4));
-    attr_done = true;
-    return PDENLP_OK;
-  }
-  int run_h() const override { return E::RUN_H; }
-  bool needs_coef_deriv() const override { return E::Integrand::NEEDS_COEF_DERIV; }
-  bool res_fe_hessian_zero() const override { return E::Integrand::RES_FE_HESSIAN_ZERO; }
-  bool no_fe_obj() const override { return E::Integrand::NO_FE_OBJ; }
-  bool is_multi() const override { return E::MULTI; }
-  int nofe(const Launch& L, int mode, const double* x, double ow, const double* v, double* out) override {
-    if constexpr (E::Integrand::NO_FE_OBJ) {
-      k_nofe<E><<<1, 32, 0, L.stream>>>(tab, x, mode, ow, v, out);
-      CU(cudaGetLastError());
-    }
-    return PDENLP_OK;
-  }
-  static int grid_for(int64_t ntiles, int warps, int cap) {
-    int64_t g = (ntiles + warps - 1) / warps;
-    return (int)std::max<int64_t>(1, std::min<int64_t>(g, cap));
-  }
-  int count(const DevModel& D, int32_t* counts, int32_t* flag, cudaStream_t s) override {
-    k_count<E><<<grid_for(D.ntiles, kWarpsPerCta, 1 << 30), kThreads, 0, s>>>(D, counts, flag);
-    CU(cudaGetLastError());
-    return PDENLP_OK;
-  }
-  // tuning knob (experiments only): PDENLP_WARPS_J / PDENLP_WARPS_H lower the warps per CTA
-  static int env_warps(const char* name, int maxw) {
-    const char* e = getenv(name);
-    if (!e) return maxw;
-    int w = atoi(e);
-    return w >= 1 && w <= maxw ? w : maxw;
-  }
-  int jac(const Launch& L, const DevModel& D, const double* x, double* vy, double* vu) override {
-    if (int rc = set_attrs()) return rc;
-    static const int wj = env_warps("PDENLP_WARPS_J", WJ);
-    jac_kernel()<<<grid_for(D.ntiles, wj, L.sms * occ_j), wj * 32, SMEM_J, L.stream>>>(tab, D, x, vy, vu);
-    CU(cudaGetLastError());
-    return PDENLP_OK;
-  }
-  int hess(const Launch& L, const DevModel& D, const double* x, const double* lam, double ow, double* vo, double* vc) override {
-    if (int rc = set_attrs()) return rc;
-    static const int wh = env_warps("PDENLP_WARPS_H", WH);
-    hess_kernel()<<<grid_for(D.ntiles, wh, L.sms * occ_h), wh * 32, SMEM_H, L.stream>>>(tab, D, x, lam, ow, vo, vc);
-    CU(cudaGetLastError());
-    return PDENLP_OK;
-  }
-  int structure(const Launch& L, const DevModel& D, int kind, int64_t* r, int64_t* c, int64_t shift) override {
-    k_structure<E><<<grid_for(D.ntiles, kWarpsPerCta, 1 << 30), kThreads, 0, L.stream>>>(D, kind, r, c, shift);
-    CU(cudaGetLastError());
-    return PDENLP_OK;
-  }
-  int vec(const Launch& L, const DevModel& D, int op, const double* x, const double* lam, const double* v, double ow,
-          double* out, double* partials, int* nblocks) override {
-    const int g = grid_for(D.ntiles, kWarpsPerCta, L.sms * 8);
-    *nblocks = g;
-    switch (op) {
-      case OP_OBJ: k_vector<E, OP_OBJ><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, v, ow, out, partials); break;
-      case OP_GRAD: k_vector<E, OP_GRAD><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, v, ow, out, partials); break;
-      case OP_CONS: k_vector<E, OP_CONS><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, v, ow, out, partials); break;
-      case OP_JPROD: k_vector<E, OP_JPROD><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, v, ow, out, partials); break;
-      case OP_JTPROD: k_vector<E, OP_JTPROD><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, v, ow, out, partials); break;
-      case OP_HPROD: k_vector<E, OP_HPROD><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, v, ow, out, partials); break;
-      default: return fail(PDENLP_EINVAL, "bad vector op");
-    }
-    CU(cudaGetLastError());
-    return PDENLP_OK;
-  }
-  int jac_kappa(const Launch& L, const DevModel& D, const double* x, double* vk) override {
-    if constexpr (E::NP > 0)
-    k_jac_kappa<E><<<grid_for(D.ntiles, kWarpsPerCta, L.sms * 8), kThreads, 0, L.stream>>>(tab, D, x, vk);
-    CU(cudaGetLastError());
-    return PDENLP_OK;
-  }
-  int hess_kappa(const Launch& L, const DevModel& D, const double* x, const double* lam, double ow, int which,
-                 int64_t prows, double* vk) override {
-    if constexpr (E::NP > 0) {
-      if (which == 0 && prows == E::NP) {  // objective, kappa-kappa triangle only
-        k_hess_kappa_kk<E><<<grid_for(D.ntiles, kWarpsPerCta, L.sms * 8), kThreads, 0, L.stream>>>(tab, D, x, ow, vk);
-        CU(cudaGetLastError());
-        return PDENLP_OK;
-      }
-    }
-    if constexpr (E::NP > 0)
-    k_hess_kappa<E><<<grid_for(D.ntiles, kWarpsPerCta, L.sms * 8), kThreads, 0, L.stream>>>(tab, D, x, lam, ow, which, prows, vk);
-    CU(cudaGetLastError());
-    return PDENLP_OK;
-  }
-};
-
-template <class E>
-Ops* make_ops(const pdenlp_desc& d) {
-  auto* o = new OpsImpl<E>();
-  for (int q = 0; q < E::NQ; ++q) {
-    o->tab.wdet[q] = d.wdet[q];
-    for (int a = 0; a < E::NLY; ++a) {
-      o->tab.By[q][a][0] = d.phi_y[q * E::NLY + a];
-      for (int k = 0; k < E::DIM; ++k) o->tab.By[q][a][1 + k] = d.grad_y[(q * E::NLY + a) * E::DIM + k];
-    }
-    for (int b = 0; b < E::NLUS; ++b) o->tab.Bu[q][b] = (E::NLU > 0) ? d.phi_u[q * E::NLU + b] : 0.0;
-  }
-  for (int i = 0; i < 8; ++i) o->tab.par[i] = d.params[i];
-  if constexpr (KTab<E>::ENABLED) {  // pre-integrated reference tensors (see KTab in kernels.cuh)
-    using KT = KTab<E>;
-    o->ktab_.assign(KT::TOTAL, 0.0);
-    const auto& T = o->tab;
-    for (int q = 0; q < E::NQ; ++q) {
-      const double w = T.wdet[q];
-      for (int j = 0; j < E::NY; ++j)
-        for (int i = 0; i < E::NY; ++i)
-          for (int k = 0; k < E::NB; ++k)
-            for (int l = 0; l < E::NB; ++l) o->ktab_[KT::yy(k, l, j, i)] += w * T.By[q][i][k] * T.By[q][j][l];
-      for (int j = 0; j < E::NY; ++j)
-        for (int i = 0; i < E::NU; ++i)
-          for (int l = 0; l < E::NB; ++l) {
-            o->ktab_[KT::uy(l, j, i)] += w * T.Bu[q][i] * T.By[q][j][l];
-            o->ktab_[KT::yu(l, i, j)] += w * T.By[q][j][l] * T.Bu[q][i];
-          }
-      for (int j = 0; j < E::NU; ++j)
-        for (int i = 0; i < E::NU; ++i) o->ktab_[KT::uu(j, i)] += w * T.Bu[q][i] * T.Bu[q][j];
-    }
-  }
-  return o;
-}
-
-// number of state / control fields of the description (0 = the single-field default)
-int desc_nfy(const pdenlp_desc& d) { return d.nfields_y > 0 ? d.nfields_y : 1; }
-int desc_nfu(const pdenlp_desc& d) { return d.nu == 0 ? 0 : (d.nfields_u > 0 ? d.nfields_u : 1); }
-
-// the closed set of (integrand, dim, ny, nu, nq, nparam, fields) instantiations
+// the closed set of (integrand, dim, ny, nu, nq, nparam, fields) instantiations lives in the ops_*.cu units
 Ops* select_ops(const pdenlp_desc& d) {
-  const int I = d.integrand, dim = d.dim, ny = d.ny, nu = d.nu, nq = d.nq, np = d.nparam;
-  const int nfy = desc_nfy(d), nfu = desc_nfu(d);
-#define CASE(INT, DIMV, NYV, NUV, NQV, NPV, TYPE)                                                       \
-  if (I == INT && dim == DIMV && ny == NYV && nu == NUV && nq == NQV && np == NPV) {                   \
-    using EL = Elem<TYPE, NYV, NUV, NQV>;                                                               \
-    if (nfy == EL::NFY && nfu == EL::NFU) return make_ops<EL>(d);                                       \
-  }
-  CASE(PDENLP_MEMBRANE, 2, 9, 4, 1, 0, Membrane<2>)
-  CASE(PDENLP_MEMBRANE, 2, 4, 4, 1, 0, Membrane<2>)
-  CASE(PDENLP_POISSON_BOLTZMANN, 2, 4, 4, 1, 0, PoissonBoltzmann<2>)
-  CASE(PDENLP_BURGER_LIN, 1, 2, 2, 1, 0, BurgerLin)
-  CASE(PDENLP_BURGER_NL, 1, 2, 2, 1, 1, BurgerNl)
-  // the same problems with the user's quadrature degree raised to 2 or 3 (2 Gauss points per direction)
-  CASE(PDENLP_MEMBRANE, 2, 9, 4, 4, 0, Membrane<2>)
-  CASE(PDENLP_MEMBRANE, 2, 4, 4, 4, 0, Membrane<2>)
-  CASE(PDENLP_POISSON_BOLTZMANN, 2, 4, 4, 4, 0, PoissonBoltzmann<2>)
-  CASE(PDENLP_BURGER_LIN, 1, 2, 2, 2, 0, BurgerLin)
-  CASE(PDENLP_BURGER_NL, 1, 2, 2, 2, 1, BurgerNl)
-  using KP2 = KappaPoisson<2, false>;
-  using KP2U = KappaPoisson<2, true>;
-  using KP3U = KappaPoisson<3, true>;
-  CASE(PDENLP_KAPPA_POISSON, 2, 4, 0, 4, 2, KP2)
-  CASE(PDENLP_KAPPA_POISSON, 2, 4, 4, 4, 2, KP2U)
-  CASE(PDENLP_KAPPA_POISSON, 3, 8, 8, 8, 2, KP3U)
-  CASE(PDENLP_KAPPA_POISSON2, 2, 4, 0, 4, 2, KappaPoisson2<2>)
-  CASE(PDENLP_PENALIZED_POISSON, 2, 4, 0, 4, 0, PenalizedPoisson<2>)
-  CASE(PDENLP_BASIC_UNCONSTRAINED, 2, 4, 4, 4, 0, BasicUnconstrained<2>)
-  // multi-field ODE problems: 1-D, P1 state fields, one quadrature point
-  CASE(PDENLP_CONTROL_SIR, 1, 2, 0, 1, 0, ControlSir)
-  CASE(PDENLP_CELL_INCREASE, 1, 2, 2, 1, 0, CellIncrease)
-  CASE(PDENLP_DYNAMIC_SIR, 1, 2, 2, 1, 0, DynamicSir)
-  CASE(PDENLP_TORE_BRACHISTOCHRONE, 1, 2, 0, 1, 0, ToreBrachistochrone)
-  // NoFETerm objectives
-  CASE(PDENLP_POISSON_PARAM, 2, 4, 0, 4, 1, PoissonParam<2>)
-  CASE(PDENLP_SIS, 1, 2, 0, 1, 0, Sis)
-#undef CASE
-  return nullptr;
+  if (Ops* o = select_ops_part0(d)) return o;
+  if (Ops* o = select_ops_part1(d)) return o;
+  if (Ops* o = select_ops_part2(d)) return o;
+  return select_ops_part3(d);
 }
 
 }  // namespace
