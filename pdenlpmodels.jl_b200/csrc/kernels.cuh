@@ -19,6 +19,20 @@
 //   One elected lane then streams the whole run to HBM with a single TMA bulk store
 //   (cp.async.bulk.global.shared::cta, SASS UBLKCP) — fully coalesced 16 B-aligned traffic,
 //   the SM's LSUs never touch the 10 GB output stream.
+//
+// Map of the file:
+//   Elem / Tables / KTab / DevModel            element description, constant tables, reference tensors, device model
+//   load_ids, gather_state, point_state, ...    per-lane cell data and pointwise fields (single- and multi-field)
+//   StageLayout / SegStage                     the staged segment writer (pieces, parity, bulk stores)
+//   emit_*_K, load_ktab                        reference-tensor emitters for nq > 1 with point-independent derivatives
+//   k_jac_coord, k_hess_coord                  the two streaming writers (register pipeline over tiles; nq > 1 elements
+//                                              take the reference-tensor path, the register-accumulate path for small
+//                                              nonlinear elements, or per-point accumulation in shared memory)
+//   k_jac_coord_mf, k_hess_coord_mf            the same writers for multi-field spaces (block-ordered emission)
+//   k_structure, k_count                       setup: rows / cols and per-tile entry counts
+//   k_vector<OP>                               obj, grad!, cons!, jprod!, jtprod!, hprod! (matrix-free, atomics)
+//   k_zero_fill, k_sum_partials, k_nofe        zero fill of structurally zero blocks, objective reduction, NoFETerm
+//   k_jac_kappa, k_hess_kappa(_kk)             dense kappa blocks
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
