@@ -27,7 +27,8 @@ Ops* select_ops(const pdenlp_desc& d) {
   if (Ops* o = select_ops_part0(d)) return o;
   if (Ops* o = select_ops_part1(d)) return o;
   if (Ops* o = select_ops_part2(d)) return o;
-  return select_ops_part3(d);
+  if (Ops* o = select_ops_part3(d)) return o;
+  return select_ops_part4(d);
 }
 
 }  // namespace

@@ -119,15 +119,16 @@ def _h_membrane(X):
     return -np.sin(_OMEGA * X[:, 0]) * np.sin(_OMEGA * X[:, 1])
 
 
-def controlelasticmembrane(n: int = 100, affine: bool = False, degree: int = 1, state_order: int = 2) -> ProblemSpec:
+def controlelasticmembrane(n: int = 100, affine: bool = False, degree: int = 1, state_order: int = 2, dim: int = 2) -> ProblemSpec:
     """README 'Control elastic membrane' (README.md:58-98; docstring
     src/GridapPDENLPModel.jl:164-204): Q2 state with Dirichlet boundary, Q1
     control, degree 1, res-function (FEOperatorFromWeakForm) variant.
     ``affine=True`` is the test-suite variant built on an AffineFEOperator
     (test/problems/controlelasticmembrane.jl:48-53): same PDE, linear API.
     ``degree`` is the user's `Measure(trian, degree)` (1 in the README; 2 or 3 give 2x2 Gauss points),
-    ``state_order`` the order of the state element (2 in the README)."""
-    model = CartesianDiscreteModel((-1, 1, -1, 1), (n, n))
+    ``state_order`` the order of the state element (2 in the README); ``dim = 3`` is the same problem on (-1,1)^3
+    (yd and h keep depending on x1, x2 only)."""
+    model = CartesianDiscreteModel((-1, 1) * dim, (n,) * dim)
     Ypde = LagrangianFESpace(model, state_order, "H1", "boundary", 0.0)
     Ycon = LagrangianFESpace(model, 1, "H1")
     return ProblemSpec(
@@ -140,10 +141,10 @@ def controlelasticmembrane(n: int = 100, affine: bool = False, degree: int = 1, 
     )
 
 
-def poissonboltzman2d(n: int = 100, control_conformity: str = "L2", degree: int = 1) -> ProblemSpec:
+def poissonboltzman2d(n: int = 100, control_conformity: str = "L2", degree: int = 1, dim: int = 2) -> ProblemSpec:
     """docs/src/poisson-boltzman.md:30-67: Q1 state, Q1 control (L2 in the
-    doc), degree 1, sinh reaction term."""
-    model = CartesianDiscreteModel((-1, 1, -1, 1), (n, n))
+    doc), degree 1, sinh reaction term (``dim = 3``: the same on (-1,1)^3)."""
+    model = CartesianDiscreteModel((-1, 1) * dim, (n,) * dim)
     Ypde = LagrangianFESpace(model, 1, "H1", "boundary", 0.0)
     Ycon = LagrangianFESpace(model, 1, control_conformity)
 

@@ -48,6 +48,10 @@ def _cases(pkg):
         "burger_lin_90_deg2": lambda: pkg.burger1d(90, degree=2),
         "burger_nl_90_deg3": lambda: pkg.burger1d_param(90, degree=3),
         "poissonmixed2_17": lambda: pkg.poissonmixed2(17),   # inde = false: kappa-y cross rows in the objective block
+        # 3-D Q1/Q1
+        "membrane3d_6": lambda: pkg.controlelasticmembrane(6, state_order=1, dim=3),
+        "membrane3d_5_deg2": lambda: pkg.controlelasticmembrane(5, state_order=1, dim=3, degree=2),
+        "pb3d_l2_6": lambda: pkg.poissonboltzman2d(6, dim=3),
         # NoFETerm objectives: no objective FE block in the Hessian
         "poissonparam_24": lambda: pkg.poissonparam(24),
         "sis_80": lambda: pkg.sis(80),
@@ -58,7 +62,7 @@ CASE_NAMES = ["membrane3", "membrane8", "membrane37", "membrane100", "pb_l2_9", 
               "burger_nl_70", "kappa2d_5", "kappa2d_u_6", "kappa3d_u_4",
               "controlsir_70", "cellincrease_45", "dynamicsir_100", "dynamicsir_5", "poissonparam_24", "sis_80",
               "membrane20_deg2", "membrane_q1_33_deg3", "pb_l2_21_deg2", "burger_lin_90_deg2", "burger_nl_90_deg3",
-              "poissonmixed2_17"]
+              "poissonmixed2_17", "membrane3d_6", "membrane3d_5_deg2", "pb3d_l2_6"]
 
 
 @pytest.fixture(scope="module", params=CASE_NAMES)

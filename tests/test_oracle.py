@@ -34,6 +34,8 @@ CASES = {
     "pb_l2_3_deg2": lambda p: p.poissonboltzman2d(3, degree=2),
     "burger_nl_7_deg2": lambda p: p.burger1d_param(7, degree=2),
     "poissonmixed2_3": lambda p: p.poissonmixed2(3),
+    "membrane3d_2": lambda p: p.controlelasticmembrane(2, state_order=1, dim=3),
+    "pb3d_2": lambda p: p.poissonboltzman2d(2, "H1", dim=3),
     # NoFETerm objectives
     "poissonparam_3": lambda p: p.poissonparam(3),
     "sis_6": lambda p: p.sis(6),
