@@ -233,7 +233,7 @@ inline int desc_nfu(const pdenlp_desc& d) { return d.nu == 0 ? 0 : (d.nfields_u 
 
 // the translation units of the closed set (each returns nullptr when the case is not one of its own)
 Ops* select_ops_part0(const pdenlp_desc& d);   // ops_membrane.cu : membrane and Poisson-Boltzmann, 1 point (+ PB with 4)
-Ops* select_ops_part1(const pdenlp_desc& d);   // ops_membrane4.cu: membrane with 4 points
+Ops* select_ops_part1(const pdenlp_desc& d);   // ops_membrane4.cu: membrane with 4 points, Poisson-Boltzmann with a Q2 state
 Ops* select_ops_part2(const pdenlp_desc& d);   // ops_kappa.cu    : kappa-Poisson 2-D / 3-D
 Ops* select_ops_part3(const pdenlp_desc& d);   // ops_misc.cu     : the remaining 2-D problems, Burgers, the ODE systems
 Ops* select_ops_part4(const pdenlp_desc& d);   // ops_3d.cu       : membrane / Poisson-Boltzmann on 3-D Q1 meshes

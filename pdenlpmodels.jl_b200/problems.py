@@ -141,11 +141,12 @@ def controlelasticmembrane(n: int = 100, affine: bool = False, degree: int = 1, 
     )
 
 
-def poissonboltzman2d(n: int = 100, control_conformity: str = "L2", degree: int = 1, dim: int = 2) -> ProblemSpec:
+def poissonboltzman2d(n: int = 100, control_conformity: str = "L2", degree: int = 1, dim: int = 2,
+                      state_order: int = 1) -> ProblemSpec:
     """docs/src/poisson-boltzman.md:30-67: Q1 state, Q1 control (L2 in the
     doc), degree 1, sinh reaction term (``dim = 3``: the same on (-1,1)^3)."""
     model = CartesianDiscreteModel((-1, 1) * dim, (n,) * dim)
-    Ypde = LagrangianFESpace(model, 1, "H1", "boundary", 0.0)
+    Ypde = LagrangianFESpace(model, state_order, "H1", "boundary", 0.0)
     Ycon = LagrangianFESpace(model, 1, control_conformity)
 
     def yd(X):

@@ -52,6 +52,8 @@ def _cases(pkg):
         "membrane3d_6": lambda: pkg.controlelasticmembrane(6, state_order=1, dim=3),
         "membrane3d_5_deg2": lambda: pkg.controlelasticmembrane(5, state_order=1, dim=3, degree=2),
         "pb3d_l2_6": lambda: pkg.poissonboltzman2d(6, dim=3),
+        "pb_q2_19": lambda: pkg.poissonboltzman2d(19, "H1", state_order=2),
+        "pb_q2_11_deg2": lambda: pkg.poissonboltzman2d(11, state_order=2, degree=2),   # per-point accumulation in shared memory
         # NoFETerm objectives: no objective FE block in the Hessian
         "poissonparam_24": lambda: pkg.poissonparam(24),
         "sis_80": lambda: pkg.sis(80),
@@ -62,7 +64,8 @@ CASE_NAMES = ["membrane3", "membrane8", "membrane37", "membrane100", "pb_l2_9", 
               "burger_nl_70", "kappa2d_5", "kappa2d_u_6", "kappa3d_u_4",
               "controlsir_70", "cellincrease_45", "dynamicsir_100", "dynamicsir_5", "poissonparam_24", "sis_80",
               "membrane20_deg2", "membrane_q1_33_deg3", "pb_l2_21_deg2", "burger_lin_90_deg2", "burger_nl_90_deg3",
-              "poissonmixed2_17", "membrane3d_6", "membrane3d_5_deg2", "pb3d_l2_6"]
+              "poissonmixed2_17", "membrane3d_6", "membrane3d_5_deg2", "pb3d_l2_6",
+              "pb_q2_19", "pb_q2_11_deg2"]
 
 
 @pytest.fixture(scope="module", params=CASE_NAMES)

@@ -36,6 +36,7 @@ CASES = {
     "poissonmixed2_3": lambda p: p.poissonmixed2(3),
     "membrane3d_2": lambda p: p.controlelasticmembrane(2, state_order=1, dim=3),
     "pb3d_2": lambda p: p.poissonboltzman2d(2, "H1", dim=3),
+    "pb_q2_3_deg2": lambda p: p.poissonboltzman2d(3, state_order=2, degree=2),
     # NoFETerm objectives
     "poissonparam_3": lambda p: p.poissonparam(3),
     "sis_6": lambda p: p.sis(6),
