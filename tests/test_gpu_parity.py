@@ -232,3 +232,34 @@ def test_callbacks_follow_the_current_torch_stream(pkg, cuda_lib):
     assert torch.equal(js, ref_j) and torch.equal(hs, ref_h)
     assert torch.allclose(g, ref_g, rtol=1e-13, atol=1e-15)
     nlp.close()
+
+
+def test_callbacks_can_be_captured_in_a_cuda_graph(pkg, cuda_lib):
+    """Device-memspace coordinate / vector callbacks enqueue kernels only (no host synchronisation, no host
+    copies), so a solver can capture an iteration in a CUDA graph and replay it with new x / lambda contents."""
+    from pdenlp_b200.model import GridapPDENLPModel
+    spec = pkg.controlelasticmembrane(48)
+    nlp = GridapPDENLPModel(spec, device="cuda:0")
+    rng = np.random.default_rng(4)
+    x = _d(rng.uniform(-1, 1, nlp.meta.nvar)); lam = _d(rng.uniform(-1, 1, nlp.meta.ncon))
+    jv = torch.empty(nlp.meta.nnzj, dtype=torch.float64, device="cuda")
+    hv = torch.empty(nlp.meta.nnzh, dtype=torch.float64, device="cuda")
+    g = torch.empty(nlp.meta.nvar, dtype=torch.float64, device="cuda")
+    c = torch.empty(nlp.meta.ncon, dtype=torch.float64, device="cuda")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):   # warm-up outside the capture (function attributes, occupancy queries)
+        nlp.jac_coord_(x, jv); nlp.hess_coord_(x, lam, hv, obj_weight=0.5); nlp.grad_(x, g); nlp.cons_(x, c)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        nlp.jac_coord_(x, jv); nlp.hess_coord_(x, lam, hv, obj_weight=0.5); nlp.grad_(x, g); nlp.cons_(x, c)
+    x2 = _d(rng.uniform(-1, 1, nlp.meta.nvar)); lam2 = _d(rng.uniform(-1, 1, nlp.meta.ncon))
+    x.copy_(x2); lam.copy_(lam2)
+    jv.fill_(float("nan")); hv.fill_(float("nan"))
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(jv, nlp.jac_coord(x2)) and torch.equal(hv, nlp.hess_coord(x2, lam2, obj_weight=0.5))
+    assert torch.allclose(g, nlp.grad(x2), rtol=1e-13, atol=1e-15) and torch.allclose(c, nlp.cons(x2), rtol=1e-13, atol=1e-15)
+    nlp.close()
