@@ -252,9 +252,13 @@ class GridapPDENLPModel:
     # ------------------------------------------------------------------ compaction plans (COO -> CSC)
     def _make_plan(self, hess: bool, nnz: int):
         """Device plan summing duplicates of the COO structure into CSC order (findnz order)."""
-        rows = torch.empty(nnz, dtype=torch.int64, device=self.device)
-        cols = torch.empty(nnz, dtype=torch.int64, device=self.device)
-        (self.handle.hess_structure if hess else self.handle.jac_structure)(rows.data_ptr(), cols.data_ptr())
+        if hess:  # the model-level structure (objective segment only for unconstrained models)
+            rows, cols = self.hess_structure()
+            rows, cols = rows.contiguous(), cols.contiguous()
+        else:
+            rows = torch.empty(nnz, dtype=torch.int64, device=self.device)
+            cols = torch.empty(nnz, dtype=torch.int64, device=self.device)
+            self.handle.jac_structure(rows.data_ptr(), cols.data_ptr())
         I = self.handle.info
         with torch.cuda.device(self.device):
             plan = capi.Compaction(rows, cols, I.nvar if hess else I.ncon, I.nvar, capi.ORDER_CSC)
@@ -289,9 +293,8 @@ class GridapPDENLPModel:
         the overlapping objective / constraint segments summed, as (colptr, rowval, nzval)."""
         if self.memspace != "device" or self.affine:
             raise NotImplementedError
-        I = self.handle.info
         if self._hess_plan is None:
-            self._hess_plan = self._make_plan(True, I.nnzh)
+            self._hess_plan = self._make_plan(True, self.meta.nnzh)
         coo = self.hess_coord(x, y, obj_weight=obj_weight)
         out = torch.empty(self._hess_plan.nnz, dtype=torch.float64, device=self.device)
         self._hess_plan.apply(coo.data_ptr(), out.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
@@ -570,6 +573,30 @@ class GridapPDENLPModel:
     def hprod(self, x, *args, obj_weight: float = 1.0):
         Hv = self._new(self.meta.nvar)
         return self.hprod_(x, *args, Hv, obj_weight=obj_weight)
+
+    # ------------------------------------------------------------------ NLPModels generic wrappers
+    # (the reference inherits these from NLPModels; they compose the callbacks above)
+    def objgrad_(self, x, g):
+        """objgrad!(nlp, x, g) = (obj(nlp, x), grad!(nlp, x, g))."""
+        return self.obj(x), self.grad_(x, g)
+
+    def objgrad(self, x):
+        return self.objgrad_(x, self._new(self.meta.nvar, like=x))
+
+    def objcons_(self, x, c):
+        """objcons!(nlp, x, c) = (obj(nlp, x), cons!(nlp, x, c))."""
+        return self.obj(x), (self.cons_(x, c) if self.meta.ncon > 0 else c)
+
+    def objcons(self, x):
+        return self.objcons_(x, self._new(self.meta.ncon, like=x))
+
+    def jac(self, x):
+        """jac(nlp, x): the Jacobian as (colptr, rowval, nzval) of a SparseMatrixCSC (see jac_csc)."""
+        return self.jac_csc(x)
+
+    def hess(self, x, y=None, obj_weight: float = 1.0):
+        """hess(nlp, x[, y]; obj_weight): lower triangle as (colptr, rowval, nzval) (see hess_csc)."""
+        return self.hess_csc(x, y, obj_weight=obj_weight)
 
     # ------------------------------------------------------------------ operators (jac_op!/hess_op!)
     def jac_op(self, x):

@@ -188,3 +188,28 @@ def test_sis_residual_at_exact_solution_on_the_gpu(pkg, cuda_lib):
     assert float(nlp.cons(x).abs().max()) <= 1e-15
     assert nlp.obj(x) == 0.0 and float(nlp.grad(x).abs().max()) == 0.0
     nlp.close()
+
+
+def test_generic_wrappers(prob):
+    """objgrad, objcons, jac, hess: the NLPModels compositions of the callbacks (Appendix A.1)."""
+    name, spec, nlp = prob
+    n, m = nlp.meta.nvar, nlp.meta.ncon
+    x = _d(_points(n)[2]); y = _d(np.random.default_rng(13).uniform(-1, 1, m))
+    f, g = nlp.objgrad(x)
+    assert f == nlp.obj(x) and torch.allclose(g, nlp.grad(x), rtol=1e-13, atol=1e-15)
+    f2, c = nlp.objcons(x)
+    assert f2 == f and c.numel() == m and (m == 0 or torch.allclose(c, nlp.cons(x), rtol=1e-13, atol=1e-15))
+    if getattr(spec, "affine", False):
+        return
+    colptr, rowval, nzval = nlp.hess(x, y if m else None, obj_weight=0.7)
+    H = sp.csc_matrix((_h(nzval), _h(rowval) - 1, _h(colptr) - 1), shape=(n, n)).toarray()
+    r, c_ = nlp.hess_structure()
+    vals = nlp.hess_coord(x, y, obj_weight=0.7) if m else nlp.hess_coord(x, obj_weight=0.7)
+    Href = sp.coo_matrix((_h(vals), (_h(r) - 1, _h(c_) - 1)), shape=(n, n)).toarray()
+    assert np.allclose(H, Href, rtol=1e-13, atol=1e-15) and np.all(np.triu(H, 1) == 0)
+    if m:
+        colptr, rowval, nzval = nlp.jac(x)
+        J = sp.csc_matrix((_h(nzval), _h(rowval) - 1, _h(colptr) - 1), shape=(m, n)).toarray()
+        r, c_ = nlp.jac_structure()
+        Jref = sp.coo_matrix((_h(nlp.jac_coord(x)), (_h(r) - 1, _h(c_) - 1)), shape=(m, n)).toarray()
+        assert np.allclose(J, Jref, rtol=1e-13, atol=1e-15)
