@@ -540,10 +540,13 @@ class GridapPDENLPModel:
         self._lencheck(self.meta.nnzh, rows=rows, cols=cols)
         if self.affine or self.unconstrained:  # objective segment only
             n = self.handle.info.nnzh
-            r = torch.empty(n, dtype=torch.int64, device=self.device)
-            c = torch.empty(n, dtype=torch.int64, device=self.device)
+            r = self._new(n, dtype=torch.int64)
+            c = self._new(n, dtype=torch.int64)
             self._structure(True, r, c)
-            rows.copy_(r[: self.meta.nnzh]); cols.copy_(c[: self.meta.nnzh])
+            if _is_torch(rows):
+                rows.copy_(r[: self.meta.nnzh]); cols.copy_(c[: self.meta.nnzh])
+            else:
+                rows[:] = r[: self.meta.nnzh]; cols[:] = c[: self.meta.nnzh]
             return rows, cols
         return self._structure(True, rows, cols)
 

@@ -213,3 +213,33 @@ def test_generic_wrappers(prob):
         r, c_ = nlp.jac_structure()
         Jref = sp.coo_matrix((_h(nlp.jac_coord(x)), (_h(r) - 1, _h(c_) - 1)), shape=(m, n)).toarray()
         assert np.allclose(J, Jref, rtol=1e-13, atol=1e-15)
+
+
+def test_host_memspace_on_every_problem(prob):
+    """PDENLP_MEM_HOST (numpy in / out, library-side staging, host zero fill of structurally zero blocks) gives the
+    device-memspace results on every problem."""
+    from pdenlp_b200.model import GridapPDENLPModel
+    name, spec, nlp = prob
+    if getattr(spec, "affine", False):
+        pytest.skip("the linear-API model keeps its vectors on the device")
+    nh = GridapPDENLPModel(spec, device="cuda:0", memspace="host")
+    n, m = nlp.meta.nvar, nlp.meta.ncon
+    rng = np.random.default_rng(21)
+    x = rng.uniform(-1, 1, n); y = rng.uniform(-1, 1, m); v = rng.uniform(-1, 1, n)
+    tol = dict(rtol=1e-12, atol=1e-14)
+    assert np.isclose(nh.obj(x), nlp.obj(_d(x)), rtol=1e-13, atol=1e-15)
+    assert np.allclose(nh.grad(x), _h(nlp.grad(_d(x))), **tol)
+    assert np.allclose(nh.hess_coord(x, obj_weight=0.3), _h(nlp.hess_coord(_d(x), obj_weight=0.3)), **tol)
+    assert np.allclose(nh.hprod(x, v, obj_weight=0.3), _h(nlp.hprod(_d(x), _d(v), obj_weight=0.3)), **tol)
+    r, c = nh.hess_structure(); rd, cd = nlp.hess_structure()
+    assert np.array_equal(r, _h(rd)) and np.array_equal(c, _h(cd))
+    if m:
+        assert np.allclose(nh.cons(x), _h(nlp.cons(_d(x))), **tol)
+        assert np.allclose(nh.jac_coord(x), _h(nlp.jac_coord(_d(x))), **tol)
+        assert np.allclose(nh.hess_coord(x, y, obj_weight=0.3), _h(nlp.hess_coord(_d(x), _d(y), obj_weight=0.3)), **tol)
+        assert np.allclose(nh.jprod(x, v), _h(nlp.jprod(_d(x), _d(v))), **tol)
+        assert np.allclose(nh.jtprod(x, y), _h(nlp.jtprod(_d(x), _d(y))), **tol)
+        assert np.allclose(nh.hprod(x, y, v, obj_weight=0.3), _h(nlp.hprod(_d(x), _d(y), _d(v), obj_weight=0.3)), **tol)
+        r, c = nh.jac_structure(); rd, cd = nlp.jac_structure()
+        assert np.array_equal(r, _h(rd)) and np.array_equal(c, _h(cd))
+    nh.close()
