@@ -95,6 +95,9 @@ class ShardedModel:
         self.spec, self.local, self.layout, self.rank, self.group = spec, local, layout, rank, group
         self.world = layout.world
         self._idx_cache = {}
+        # NoFETerm objective fk(kappa): not a sum over cells, so only ONE slab (rank 0) may contribute it to the
+        # reduced outputs (every slab's model evaluates the whole of it)
+        self.nofe = bool(getattr(spec, "no_fe_obj", False))
 
     # ---- helpers ---------------------------------------------------------
     def _idx(self, which: str, like):
@@ -122,7 +125,7 @@ class ShardedModel:
     # ---- scalar ----------------------------------------------------------
     def obj(self, x) -> float:
         f = self.local.obj(x)
-        if self.world == 1:
+        if self.world == 1 or self.nofe:
             return f
         dev = x.device if isinstance(x, torch.Tensor) else "cpu"
         t = torch.tensor([f], dtype=torch.float64, device=dev)
@@ -131,7 +134,10 @@ class ShardedModel:
 
     # ---- dof-indexed outputs --------------------------------------------
     def grad_(self, x, g):
-        return self._reduce_interface(self.local.grad_(x, g), "var")
+        g = self.local.grad_(x, g)
+        if self.nofe and self.rank != 0:
+            g[: self.layout.p] = 0.0
+        return self._reduce_interface(g, "var")
 
     def cons_(self, x, c):
         return self._reduce_interface(self.local.cons_(x, c), "con")
@@ -142,15 +148,19 @@ class ShardedModel:
     def jtprod_(self, x, v, Jtv):
         return self._reduce_interface(self.local.jtprod_(x, v, Jtv), "var")
 
+    def _ow(self, obj_weight):
+        return 0.0 if (self.nofe and self.rank != 0) else obj_weight
+
     def hprod_(self, x, *args, obj_weight: float = 1.0):
-        return self._reduce_interface(self.local.hprod_(x, *args, obj_weight=obj_weight), "var")
+        return self._reduce_interface(self.local.hprod_(x, *args, obj_weight=self._ow(obj_weight)), "var")
 
     # ---- COO streams: local slices, no communication ---------------------
     def jac_coord_(self, x, vals):
         return self.local.jac_coord_(x, vals)
 
     def hess_coord_(self, x, *args, obj_weight: float = 1.0):
-        return self.local.hess_coord_(x, *args, obj_weight=obj_weight)
+        """Local slices of the FE segments; the dense kappa blocks are slab partials (to be summed over the ranks)."""
+        return self.local.hess_coord_(x, *args, obj_weight=self._ow(obj_weight))
 
     def segment_sizes(self) -> dict:
         pm = self.local.pdemeta

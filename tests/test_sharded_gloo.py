@@ -47,7 +47,8 @@ def _worker(rank, world, port, case, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         spec = {"membrane": lambda: pkg.controlelasticmembrane(8), "burger_nl": lambda: pkg.burger1d_param(100),
-                "pb": lambda: pkg.poissonboltzman2d(9), "dynamicsir": lambda: pkg.dynamicsir(100)}[case]()
+                "pb": lambda: pkg.poissonboltzman2d(9), "dynamicsir": lambda: pkg.dynamicsir(100),
+                "poissonparam": lambda: pkg.poissonparam(9)}[case]()
         layout = SlabLayout(spec, world)
         full = O.Oracle(spec, nthreads=1)
         local = OracleLocal(O.Oracle(spec, layout.ranges[rank], nthreads=1))
@@ -77,11 +78,20 @@ def _worker(rank, world, port, case, q):
         ok &= np.array_equal(jl[local.o.nnzj_k + local.o.nnzj_y:], jf[k + full.nnzj_y + off["ju"]: k + full.nnzj_y + off["ju"] + local.o.nnzj_u])
         res["jac_slices"] = bool(ok)
         hl = sm.hess_coord_(x, lam, np.empty(local.o.nnzh), obj_weight=0.3); hf = full.hess_coord(x, lam, 0.3)
-        a = full.nnzh_k_obj + off["hfe"]
         lo = local.o
-        ok = np.array_equal(hl[lo.nnzh_k_obj: lo.nnzh_k_obj + lo.nnzh_fe], hf[a: a + lo.nnzh_fe])
-        b = full.nnzh_obj + full.nnzh_k_con + off["hfe"]
-        ok &= np.array_equal(hl[lo.nnzh_obj + lo.nnzh_k_con:], hf[b: b + lo.nnzh_fe])
+        if getattr(spec, "no_fe_obj", False):
+            # NoFETerm: [obj kappa triangle | cons kappa trapezoid | cons FE]; fk(kappa) comes from rank 0 only and
+            # the dense kappa blocks are slab partials that sum to the global ones
+            kb = torch.from_numpy(hl[: lo.nnzh_obj + lo.nnzh_k_con].copy())
+            dist.all_reduce(kb, op=dist.ReduceOp.SUM)
+            ok = np.allclose(kb.numpy(), hf[: full.nnzh_obj + full.nnzh_k_con], rtol=1e-12, atol=1e-14)
+            b = full.nnzh_obj + full.nnzh_k_con + off["hfe"]
+            ok &= np.array_equal(hl[lo.nnzh_obj + lo.nnzh_k_con:], hf[b: b + lo.nnzh_fe])
+        else:
+            a = full.nnzh_k_obj + off["hfe"]
+            ok = np.array_equal(hl[lo.nnzh_k_obj: lo.nnzh_k_obj + lo.nnzh_fe], hf[a: a + lo.nnzh_fe])
+            b = full.nnzh_obj + full.nnzh_k_con + off["hfe"]
+            ok &= np.array_equal(hl[lo.nnzh_obj + lo.nnzh_k_con:], hf[b: b + lo.nnzh_fe])
         res["hess_slices"] = bool(ok)
         res["iface_small"] = bool(layout.iface_var.size < 0.5 * full.nvar)
         q.put((rank, res))
@@ -93,7 +103,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-@pytest.mark.parametrize("case", ["membrane", "burger_nl", "pb", "dynamicsir"])
+@pytest.mark.parametrize("case", ["membrane", "burger_nl", "pb", "dynamicsir", "poissonparam"])
 def test_world2_gloo(case, oracle_mod):
     oracle_mod.build()
     ctx = mp.get_context("spawn")
