@@ -234,7 +234,10 @@ int pdenlp_jac_coord(pdenlp_model* m, const double* x, double* vals);
    lambda == NULL selects the objective-only method (tail zero-filled, :295-297).
    vals[nnzh] in hess_structure! order:
    [obj k-block | obj FE | cons k-block | cons FE], lower triangle on global ids
-   (src/fill_matrix_hessian_functions.jl:50-94). */
+   (src/fill_matrix_hessian_functions.jl:50-94); the obj FE block is absent for a NoFETerm
+   objective (pdenlp_info.nnzh_fe_obj == 0).  A cons FE block that is structurally zero (no
+   lambda, or a residual that is affine in the FE fields) is zero-filled without being computed;
+   with PDENLP_MEM_HOST it is filled in the caller's buffer by host threads and not transferred. */
 int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda,
                       double obj_weight, double* vals);
 /* objective part only, vals[nnzh_obj]: all there is for an AffineFEOperator model, whose
