@@ -210,3 +210,40 @@ def test_kappa_poisson3d_128_slabs_and_identities(pkg, cuda_lib, oracle_mod):
     Hv_coo.index_add_(0, c[d] - 1, hv[d] * v[r[d] - 1])
     assert float((Hv_coo - Hv).abs().max()) <= 1e-11 * float(Hv.abs().max())
     nlp.close()
+
+
+def test_burger1d_1M_coord_slabs_vs_oracle(pkg, cuda_lib, oracle_mod):
+    """config 4: jac_coord!/hess_coord! on 10^6 cells; a slab from the middle (FE segments are cell-major, so the
+    slab's runs sit at the offsets given by a head model) and the kappa blocks against the oracle of the full mesh."""
+    from pdenlp_b200.model import GridapPDENLPModel
+    n = 1_000_000
+    spec = pkg.burger1d_param(n)
+    nlp = GridapPDENLPModel(spec, device="cuda:0")
+    rng = np.random.default_rng(1998)
+    xh = rng.uniform(-1, 1, nlp.meta.nvar); xh[0] = 1.05
+    lh = rng.uniform(-1, 1, nlp.meta.ncon)
+    x, lam = torch.from_numpy(xh).cuda(), torch.from_numpy(lh).cuda()
+    jv = nlp.jac_coord(x); hv = nlp.hess_coord(x, lam, obj_weight=0.37)
+    c0, c1 = 400_000, 465_536
+    head = GridapPDENLPModel(spec, device="cuda:0", cell_range=(0, c0), with_coef=False)
+    oy, ou, oh = head.pdemeta.nnzj_y, head.pdemeta.nnzj_u, head.pdemeta.nnzh_fe
+    head.close()
+    o = oracle_mod.Oracle(spec, (c0, c1))
+    jo = o.jac_coord(xh); ho = o.hess_coord(xh, lh, 0.37)
+    pm = nlp.pdemeta
+    a = pm.nnzj_k + oy
+    assert _rel(jv[a: a + o.nnzj_y].cpu().numpy(), jo[o.nnzj_k: o.nnzj_k + o.nnzj_y]) <= RTOL
+    a = pm.nnzj_k + pm.nnzj_y + ou
+    assert _rel(jv[a: a + o.nnzj_u].cpu().numpy(), jo[o.nnzj_k + o.nnzj_y:]) <= RTOL
+    a = pm.nnzh_k_obj + oh
+    assert _rel(hv[a: a + o.nnzh_fe].cpu().numpy(), ho[o.nnzh_k_obj: o.nnzh_k_obj + o.nnzh_fe]) <= RTOL
+    a = pm.nnzh_obj + pm.nnzh_k_con + oh
+    assert _rel(hv[a: a + o.nnzh_fe].cpu().numpy(), ho[o.nnzh_obj + o.nnzh_k_con:]) <= RTOL
+    # dense kappa blocks (atomics over all cells) against the full-mesh oracle
+    of = oracle_mod.Oracle(spec)
+    jf = of.jac_coord(xh); hf = of.hess_coord(xh, lh, 0.37)
+    assert _rel(jv[: pm.nnzj_k].cpu().numpy(), jf[: of.nnzj_k]) <= 1e-11
+    assert _rel(hv[: pm.nnzh_k_obj].cpu().numpy(), hf[: of.nnzh_k_obj]) <= 1e-11
+    b = pm.nnzh_obj
+    assert _rel(hv[b: b + pm.nnzh_k_con].cpu().numpy(), hf[of.nnzh_obj: of.nnzh_obj + of.nnzh_k_con]) <= 1e-11
+    nlp.close()
