@@ -134,6 +134,13 @@ __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uin
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// Programmatic dependent launch (all no-ops when the kernel was not launched with the stream-serialization attribute):
+// wait = every earlier kernel of the stream has completed and its writes are visible; launch_dependents = the next
+// kernel of the stream may start its prologue.  Protocol of the coord kernels: read model-owned data (dof ids,
+// reference tensors) -> wait -> launch_dependents -> touch the caller's vectors.  A kernel therefore never reads or
+// writes caller memory before its predecessors are done, and its completion implies theirs.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 template <int N>  // at most N of this thread's most recent bulk groups may still be reading shared memory
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -676,10 +683,12 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
     const int64_t cell = tile * 32 + lane;
     const bool valid = cell < D.ncells;
     load_ids<E>(D, valid ? cell : 0, valid, c);
-    gather_state<E>(D, x, valid, c);
     const int64_t ncell = (tile + stride) * 32 + lane;
     const bool nvalid = (tile + stride) < D.ntiles && ncell < D.ncells;
     load_ids<E>(D, nvalid ? ncell : 0, nvalid, n);
+    griddep_wait();               // from here on the caller's vectors are touched
+    griddep_launch_dependents();
+    gather_state<E>(D, x, valid, c);
   }
   constexpr bool PFB = coord_prefetch_base<E, false>();
   int64_t b_jy = PFB ? D.base_jy[tile] : 0, b_ju = (PFB && E::NU > 0) ? D.base_ju[tile] : 0;
@@ -1017,9 +1026,6 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
   double* const wbase = smem + warp * STAGE * NBUF;
   int slot = 0;
   SegStage<E::RUN_H> st{wbase, nullptr};
-  // a kernel launched behind this one with programmatic stream serialization (the zero fill of the other,
-  // disjoint, FE block) may start right away; a no-op otherwise
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const double* const Ks = load_ktab<E>(D, smem + nwarps * STAGE * NBUF);
 
   const int64_t stride = (int64_t)gridDim.x * nwarps;
@@ -1033,10 +1039,12 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
     const int64_t cell = tile * 32 + lane;
     const bool valid = cell < D.ncells;
     load_ids<E>(D, valid ? cell : 0, valid, c);
-    gather_state<E>(D, x, valid, c);
     const int64_t ncell = (tile + stride) * 32 + lane;
     const bool nvalid = (tile + stride) < D.ntiles && ncell < D.ncells;
     load_ids<E>(D, nvalid ? ncell : 0, nvalid, n);
+    griddep_wait();               // from here on the caller's vectors are touched
+    griddep_launch_dependents();  // e.g. the zero fill of the other (disjoint) FE block starts right away
+    gather_state<E>(D, x, valid, c);
   }
   double lam_e[E::NY], nlam[E::NY];
   if (vals_con != nullptr) gather_free<E::NY>(lambda, c.gy, lam_e);
@@ -1847,6 +1855,10 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
 // Zero fill of a COO segment that is structurally zero (constraint FE Hessian block of an affine
 // residual, or hess_coord! without multipliers): pure streaming 16 B stores, 4 per thread per step.
 static __global__ void __launch_bounds__(256) k_zero_fill(double* __restrict__ p, int64_t n) {
+  // Launched behind the emitting kernel of the same callback (disjoint block): it runs concurrently with it, lets the
+  // next kernel start its prologue, and ONE thread waits for the predecessor at the end so that the completion of this grid
+  // implies theirs (all threads waiting would park the early CTAs on the SMs until the emitting kernel is done).
+  griddep_launch_dependents();
   const int64_t head = (n > 0 && ((reinterpret_cast<uintptr_t>(p) >> 3) & 1)) ? 1 : 0;  // 8 B-aligned start
   const int64_t n2 = (n - head) >> 1;
   double2* q = reinterpret_cast<double2*>(p + head);
@@ -1865,6 +1877,7 @@ static __global__ void __launch_bounds__(256) k_zero_fill(double* __restrict__ p
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     if (head) p[0] = 0.0;
     if ((n - head) & 1) p[n - 1] = 0.0;
+    griddep_wait();  // one thread is enough: the grid is not complete before it returns
   }
 }
 

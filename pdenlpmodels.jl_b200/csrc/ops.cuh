@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 extern thread_local std::string pdenlp_g_err;  // defined in pdenlp_cuda.cu
@@ -33,6 +34,24 @@ struct Launch {
   cudaStream_t stream;
   int sms;
 };
+
+// Kernel launch with the programmatic-stream-serialization attribute (see griddep_wait in kernels.cuh): the kernel may
+// be scheduled while its predecessor on the stream drains; it synchronises itself with griddepcontrol.wait.
+// PDENLP_PDL_CHAIN=1 (experiment) turns it on for the coord kernels; the fill behind k_hess_coord always uses it.
+inline bool pdl_chain() {
+  static const bool on = getenv("PDENLP_PDL_CHAIN") != nullptr;
+  return on;
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_kernel(void (*k)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k, std::forward<Args>(args)...);
+}
 
 // type-erased per-element operations
 struct Ops {
@@ -126,15 +145,15 @@ struct OpsImpl : Ops {
   int jac(const Launch& L, const DevModel& D, const double* x, double* vy, double* vu) override {
     if (int rc = set_attrs()) return rc;
     static const int wj = env_warps("PDENLP_WARPS_J", WJ);
-    jac_kernel()<<<grid_for(D.ntiles, wj, L.sms * occ_j), wj * 32, SMEM_J, L.stream>>>(tab, D, x, vy, vu);
-    CU(cudaGetLastError());
+    CU(launch_kernel(jac_kernel(), grid_for(D.ntiles, wj, L.sms * occ_j), wj * 32, SMEM_J, L.stream, pdl_chain() && !E::MULTI,
+                     tab, D, x, vy, vu));
     return PDENLP_OK;
   }
   int hess(const Launch& L, const DevModel& D, const double* x, const double* lam, double ow, double* vo, double* vc) override {
     if (int rc = set_attrs()) return rc;
     static const int wh = env_warps("PDENLP_WARPS_H", WH);
-    hess_kernel()<<<grid_for(D.ntiles, wh, L.sms * occ_h), wh * 32, SMEM_H, L.stream>>>(tab, D, x, lam, ow, vo, vc);
-    CU(cudaGetLastError());
+    CU(launch_kernel(hess_kernel(), grid_for(D.ntiles, wh, L.sms * occ_h), wh * 32, SMEM_H, L.stream, pdl_chain() && !E::MULTI,
+                     tab, D, x, lam, ow, vo, vc));
     return PDENLP_OK;
   }
   int structure(const Launch& L, const DevModel& D, int kind, int64_t* r, int64_t* c, int64_t shift) override {
