@@ -526,6 +526,10 @@ int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda, do
   }
   double* vo = m->nofe ? nullptr : vfo;  // NoFETerm: the objective has no FE block
   double* vc = cons_zero ? nullptr : vfc;
+  if (vo && obj_weight == 0.0) {  // vals .*= obj_weight (GridapPDENLPModel.jl:299): the objective block is a zero fill too
+    if (int rc = zero_fill(m, vfo, I.nnzh_fe_obj)) return rc;
+    vo = nullptr;
+  }
   if (vo || vc) {
     if (int rc = m->ops->hess(L, m->dm, dx, dl, obj_weight, vo, vc)) return rc;
     m->launches += 1;
