@@ -220,6 +220,10 @@ int pdenlp_obj(pdenlp_model* m, const double* x, double* f);
    g[nvar] is zero-filled then accumulated (assemble_vector! semantics). */
 int pdenlp_grad(pdenlp_model* m, const double* x, double* g);
 
+/* objgrad!(nlp, x, g): NLPModels composes it from obj and grad! (the reference does not override it);
+   here one sweep over the cells yields both.  f: HOST pointer to one double. */
+int pdenlp_objgrad(pdenlp_model* m, const double* x, double* f, double* g);
+
 /* cons_nln!(nlp, x, c)                 src/GridapPDENLPModel.jl:433-447,
    _from_terms_to_residual!             src/jacobian_functions.jl:23-58 */
 int pdenlp_cons(pdenlp_model* m, const double* x, double* c);

@@ -1609,7 +1609,8 @@ __device__ __forceinline__ void cta_sum_atomic(double v, double* dst, double* re
 
 // ------------------------------------------------------------------ vector-valued callbacks
 // (lane = cell; scatter with red.global.add.f64 — north star: "segmented atomics")
-enum VecOp { OP_OBJ = 0, OP_GRAD = 1, OP_CONS = 2, OP_JPROD = 3, OP_JTPROD = 4, OP_HPROD = 5 };
+enum VecOp { OP_OBJ = 0, OP_GRAD = 1, OP_CONS = 2, OP_JPROD = 3, OP_JTPROD = 4, OP_HPROD = 5,
+             OP_OBJGRAD = 6 /* objgrad!: objective and gradient from one sweep (one gather, one jet evaluation) */ };
 
 // element vector d/dz_a += sum_k By_a[k] gs[k], d/du_b += Bu_b gs[SU]: accumulated over the quadrature points in
 // registers, scattered once per cell (one red.global.add.f64 per local dof, not per dof and point)
@@ -1730,11 +1731,12 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
         point_state<E>(tab, c, x, q, s);
         const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, true);
         fsum += w * I::f(pc, s);
-      } else if (OP == OP_GRAD) {
+      } else if (OP == OP_GRAD || OP == OP_OBJGRAD) {
         Jet1<E::M> s[E::M];
         point_state<E>(tab, c, x, q, s);
         const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, true);
         const Jet1<E::M> F = I::f(pc, s);
+        if (OP == OP_OBJGRAD) fsum += w * F.v;
         double gs[E::M];
 #pragma unroll
         for (int k = 0; k < E::M; ++k) gs[k] = w * F.g[k];
@@ -1820,7 +1822,7 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
         for (int k = 0; k < E::NP; ++k) ksum[k] += gs[E::SK + k];
       }
     }
-    if (OP == OP_GRAD || OP == OP_JTPROD || OP == OP_HPROD) scatter_element<E>(D, c, ey, eu, out);
+    if (OP == OP_GRAD || OP == OP_OBJGRAD || OP == OP_JTPROD || OP == OP_HPROD) scatter_element<E>(D, c, ey, eu, out);
     if (OP == OP_CONS || OP == OP_JPROD) {  // rows = free dofs of the test space
 #pragma unroll
       for (int i = 0; i < E::NY; ++i)
@@ -1829,7 +1831,7 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
   }
   // block-level reductions: objective partial sums (deterministic two-pass) and kappa entries
   __shared__ double red[kWarpsPerCta];
-  if (OP == OP_OBJ) {
+  if (OP == OP_OBJ || OP == OP_OBJGRAD) {
     fsum = warp_sum(fsum);
     if (lane == 0) red[warp] = fsum;
     __syncthreads();
@@ -1838,7 +1840,9 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
       for (int w = 0; w < kWarpsPerCta; ++w) a += red[w];
       partials[blockIdx.x] = a;
     }
-  } else if (E::NP > 0 && (OP == OP_GRAD || OP == OP_JTPROD || OP == OP_HPROD)) {
+    __syncthreads();
+  }
+  if (E::NP > 0 && (OP == OP_GRAD || OP == OP_OBJGRAD || OP == OP_JTPROD || OP == OP_HPROD)) {
     if (E::M >= 6 && OP == OP_HPROD) {  // register-bound instance (Jet2<7>): keep the plain per-warp atomics
 #pragma unroll
       for (int k = 0; k < E::NP; ++k) {

@@ -580,8 +580,16 @@ class GridapPDENLPModel:
     # ------------------------------------------------------------------ NLPModels generic wrappers
     # (the reference inherits these from NLPModels; they compose the callbacks above)
     def objgrad_(self, x, g):
-        """objgrad!(nlp, x, g) = (obj(nlp, x), grad!(nlp, x, g))."""
-        return self.obj(x), self.grad_(x, g)
+        """objgrad!(nlp, x, g) = (obj(nlp, x), grad!(nlp, x, g)); both from one sweep over the cells
+        (pdenlp_objgrad), counted as one obj and one grad evaluation like the NLPModels default."""
+        self._lencheck(self.meta.nvar, x=x, g=g)
+        self.counters.neval_obj += 1
+        self.counters.neval_grad += 1
+        self._use_current_stream()
+        px, kx = self._in(x)
+        pg, bg, cb = self._out(g)
+        f = self.handle.objgrad(px, pg)
+        return f, self._finish(g, bg, cb)
 
     def objgrad(self, x):
         return self.objgrad_(x, self._new(self.meta.nvar, like=x))
