@@ -223,6 +223,8 @@ int pdenlp_grad(pdenlp_model* m, const double* x, double* g);
 /* objgrad!(nlp, x, g): NLPModels composes it from obj and grad! (the reference does not override it);
    here one sweep over the cells yields both.  f: HOST pointer to one double. */
 int pdenlp_objgrad(pdenlp_model* m, const double* x, double* f, double* g);
+/* objcons!(nlp, x, c): likewise the objective and the residual from one sweep */
+int pdenlp_objcons(pdenlp_model* m, const double* x, double* f, double* c);
 
 /* cons_nln!(nlp, x, c)                 src/GridapPDENLPModel.jl:433-447,
    _from_terms_to_residual!             src/jacobian_functions.jl:23-58 */

@@ -25,7 +25,7 @@ SYMBOLS = [
     "pdenlp_last_error", "pdenlp_abi_version", "pdenlp_create", "pdenlp_destroy", "pdenlp_get_info",
     "pdenlp_set_stream", "pdenlp_sync", "pdenlp_malloc", "pdenlp_free", "pdenlp_memcpy_h2d", "pdenlp_memcpy_d2h",
     "pdenlp_host_alloc", "pdenlp_host_free",
-    "pdenlp_obj", "pdenlp_objgrad", "pdenlp_grad", "pdenlp_cons", "pdenlp_jac_coord", "pdenlp_hess_coord", "pdenlp_hess_coord_obj",
+    "pdenlp_obj", "pdenlp_objgrad", "pdenlp_objcons", "pdenlp_grad", "pdenlp_cons", "pdenlp_jac_coord", "pdenlp_hess_coord", "pdenlp_hess_coord_obj",
     "pdenlp_jprod", "pdenlp_jtprod", "pdenlp_hprod", "pdenlp_jac_structure", "pdenlp_hess_structure",
     "pdenlp_launch_count", "pdenlp_last_kernel_ms", "pdenlp_set_timing",
     "pdenlp_compaction_create", "pdenlp_compaction_destroy", "pdenlp_compaction_nnz",
@@ -91,6 +91,7 @@ def load():
     lib.pdenlp_obj.argtypes = [vp, vp, C.POINTER(dbl)]
     lib.pdenlp_grad.argtypes = [vp, vp, vp]
     lib.pdenlp_objgrad.argtypes = [vp, vp, C.POINTER(dbl), vp]
+    lib.pdenlp_objcons.argtypes = [vp, vp, C.POINTER(dbl), vp]
     lib.pdenlp_cons.argtypes = [vp, vp, vp]
     lib.pdenlp_jac_coord.argtypes = [vp, vp, vp]
     lib.pdenlp_hess_coord.argtypes = [vp, vp, vp, dbl, vp]
@@ -186,6 +187,11 @@ class Handle:
     def objgrad(self, x, g) -> float:
         f = C.c_double()
         check(load().pdenlp_objgrad(self._h, x, C.byref(f), g))
+        return f.value
+
+    def objcons(self, x, c) -> float:
+        f = C.c_double()
+        check(load().pdenlp_objcons(self._h, x, C.byref(f), c))
         return f.value
 
     def cons(self, x, c):

@@ -1610,7 +1610,8 @@ __device__ __forceinline__ void cta_sum_atomic(double v, double* dst, double* re
 // ------------------------------------------------------------------ vector-valued callbacks
 // (lane = cell; scatter with red.global.add.f64 — north star: "segmented atomics")
 enum VecOp { OP_OBJ = 0, OP_GRAD = 1, OP_CONS = 2, OP_JPROD = 3, OP_JTPROD = 4, OP_HPROD = 5,
-             OP_OBJGRAD = 6 /* objgrad!: objective and gradient from one sweep (one gather, one jet evaluation) */ };
+             OP_OBJGRAD = 6 /* objgrad!: objective and gradient from one sweep (one gather, one jet evaluation) */,
+             OP_OBJCONS = 7 /* objcons!: objective and residual from one sweep */ };
 
 // element vector d/dz_a += sum_k By_a[k] gs[k], d/du_b += Bu_b gs[SU]: accumulated over the quadrature points in
 // registers, scattered once per cell (one red.global.add.f64 per local dof, not per dof and point)
@@ -1743,10 +1744,11 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
         accumulate_fields<E>(tab, q, gs, ey, eu);
 #pragma unroll
         for (int k = 0; k < E::NP; ++k) ksum[k] += gs[E::SK + k];
-      } else if (OP == OP_CONS) {
+      } else if (OP == OP_CONS || OP == OP_OBJCONS) {
         double s[E::M], R[E::NR];
         point_state<E>(tab, c, x, q, s);
         const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, true);
+        if (OP == OP_OBJCONS) fsum += w * I::f(pc, s);
         I::res(pc, s, R);
 #pragma unroll
         for (int f = 0; f < E::NFY; ++f)
@@ -1823,7 +1825,7 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
       }
     }
     if (OP == OP_GRAD || OP == OP_OBJGRAD || OP == OP_JTPROD || OP == OP_HPROD) scatter_element<E>(D, c, ey, eu, out);
-    if (OP == OP_CONS || OP == OP_JPROD) {  // rows = free dofs of the test space
+    if (OP == OP_CONS || OP == OP_OBJCONS || OP == OP_JPROD) {  // rows = free dofs of the test space
 #pragma unroll
       for (int i = 0; i < E::NY; ++i)
         if (c.gy[i] > 0) atomicAdd(out + (c.gy[i] - 1), ey[i]);
@@ -1831,7 +1833,7 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
   }
   // block-level reductions: objective partial sums (deterministic two-pass) and kappa entries
   __shared__ double red[kWarpsPerCta];
-  if (OP == OP_OBJ || OP == OP_OBJGRAD) {
+  if (OP == OP_OBJ || OP == OP_OBJGRAD || OP == OP_OBJCONS) {
     fsum = warp_sum(fsum);
     if (lane == 0) red[warp] = fsum;
     __syncthreads();

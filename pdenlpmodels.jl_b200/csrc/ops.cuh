@@ -173,6 +173,7 @@ struct OpsImpl : Ops {
       case OP_JTPROD: k_vector<E, OP_JTPROD><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, v, ow, out, partials); break;
       case OP_HPROD: k_vector<E, OP_HPROD><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, v, ow, out, partials); break;
       case OP_OBJGRAD: k_vector<E, OP_OBJGRAD><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, v, ow, out, partials); break;
+      case OP_OBJCONS: k_vector<E, OP_OBJCONS><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, v, ow, out, partials); break;
       default: return fail(PDENLP_EINVAL, "bad vector op");
     }
     CU(cudaGetLastError());

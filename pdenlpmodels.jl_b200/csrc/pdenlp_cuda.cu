@@ -439,31 +439,37 @@ static int vec_call(pdenlp_model* m, int op, const double* x, const double* lam,
   return out_finish(m, out, nout);
 }
 
-// objgrad!(nlp, x, g): objective and gradient from ONE sweep over the cells
-int pdenlp_objgrad(pdenlp_model* m, const double* x, double* f, double* g) {
-  if (!m || !x || !f || !g) return fail(PDENLP_EINVAL, "null argument");
-  if (m->nofe) {  // NoFETerm: both come from the one-thread kernel
+// objgrad!(nlp, x, g) / objcons!(nlp, x, c): the objective and the gradient (resp. the residual) from ONE sweep
+static int obj_and_vector(pdenlp_model* m, int op, const double* x, double* f, double* out, int64_t n,
+                          int (*vector_only)(pdenlp_model*, const double*, double*)) {
+  if (!m || !x || !f || !out) return fail(PDENLP_EINVAL, "null argument");
+  if (m->nofe) {  // NoFETerm: the objective comes from the one-thread kernel
     if (int rc = pdenlp_obj(m, x, f)) return rc;
-    return pdenlp_grad(m, x, g);
+    return vector_only(m, x, out);
   }
   if (!m->dm.coef) return fail(PDENLP_EINVAL, "this callback needs the coefficient fields (desc.coef)");
   Scope sc(m);
   const double* dx;
   double* dout;
-  const int64_t n = m->info.nvar;
-  if (int rc = in_ptr(m, x, n, &m->sx, &dx)) return rc;
-  if (int rc = out_ptr(m, g, n, &dout)) return rc;
+  if (int rc = in_ptr(m, x, m->info.nvar, &m->sx, &dx)) return rc;
+  if (int rc = out_ptr(m, out, n, &dout)) return rc;
   CU(cudaMemsetAsync(dout, 0, (size_t)n * 8, m->stream));
   Launch L{m->stream, m->sms};
   int nb = 0;
-  if (int rc = m->ops->vec(L, m->dm, OP_OBJGRAD, dx, nullptr, nullptr, 1.0, dout, m->partials, &nb)) return rc;
+  if (int rc = m->ops->vec(L, m->dm, op, dx, nullptr, nullptr, 1.0, dout, m->partials, &nb)) return rc;
   k_sum_partials<<<1, 256, 0, m->stream>>>(m->partials, nb, m->scalar);
   CU(cudaGetLastError());
   m->launches += 2;
   CU(cudaMemcpyAsync(f, m->scalar, 8, cudaMemcpyDeviceToHost, m->stream));
-  if (m->d.memspace == PDENLP_MEM_HOST) return out_finish(m, g, n);
+  if (m->d.memspace == PDENLP_MEM_HOST) return out_finish(m, out, n);
   CU(cudaStreamSynchronize(m->stream));
   return PDENLP_OK;
+}
+int pdenlp_objgrad(pdenlp_model* m, const double* x, double* f, double* g) {
+  return obj_and_vector(m, OP_OBJGRAD, x, f, g, m ? m->info.nvar : 0, pdenlp_grad);
+}
+int pdenlp_objcons(pdenlp_model* m, const double* x, double* f, double* c) {
+  return obj_and_vector(m, OP_OBJCONS, x, f, c, m ? m->info.ncon : 0, pdenlp_cons);
 }
 
 int pdenlp_grad(pdenlp_model* m, const double* x, double* g) {

@@ -595,8 +595,20 @@ class GridapPDENLPModel:
         return self.objgrad_(x, self._new(self.meta.nvar, like=x))
 
     def objcons_(self, x, c):
-        """objcons!(nlp, x, c) = (obj(nlp, x), cons!(nlp, x, c))."""
-        return self.obj(x), (self.cons_(x, c) if self.meta.ncon > 0 else c)
+        """objcons!(nlp, x, c) = (obj(nlp, x), cons!(nlp, x, c)); for a plain FEOperatorFromWeakForm model both
+        come from one sweep over the cells (pdenlp_objcons), counted like the NLPModels default."""
+        if self.meta.ncon == 0 or self.meta.nlin > 0:
+            return self.obj(x), (self.cons_(x, c) if self.meta.ncon > 0 else c)
+        self._lencheck(self.meta.nvar, x=x)
+        self._lencheck(self.meta.ncon, c=c)
+        self.counters.neval_obj += 1
+        self.counters.neval_cons += 1
+        self.counters.neval_cons_nln += 1
+        self._use_current_stream()
+        px, kx = self._in(x)
+        pc, bc, cb = self._out(c)
+        f = self.handle.objcons(px, pc)
+        return f, self._finish(c, bc, cb)
 
     def objcons(self, x):
         return self.objcons_(x, self._new(self.meta.ncon, like=x))

@@ -23,6 +23,7 @@ class FakeHandle:
     def obj(self, x): self.calls.append(("obj", x)); return 1.5
     def grad(self, x, g): self.calls.append(("grad", x, g))
     def objgrad(self, x, g): self.calls.append(("objgrad", x, g)); return 1.5
+    def objcons(self, x, c): self.calls.append(("objcons", x, c)); return 1.5
     def cons(self, x, c): self.calls.append(("cons", x, c))
     def jac_coord(self, x, v): self.calls.append(("jac_coord", x, v))
     def hess_coord(self, x, lam, ow, v): self.calls.append(("hess_coord", x, lam, ow, v))
