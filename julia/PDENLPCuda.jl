@@ -127,6 +127,16 @@ function grad!(nlp::GridapPDENLPModel, x::AbstractVector, g::AbstractVector)   #
   return g
 end
 
+# optional override of the NLPModels default (obj then grad!): one sweep over the cells for both
+function objgrad!(nlp::GridapPDENLPModel, x::AbstractVector, g::AbstractVector)
+  @lencheck nlp.meta.nvar x g
+  increment!(nlp, :neval_obj); increment!(nlp, :neval_grad)
+  out = dense(g); f = Ref{Float64}(0.0)
+  check(ccall((:pdenlp_objgrad, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}), handle(nlp), dense(x), f, out))
+  out === g || copyto!(g, out)
+  return f[], g
+end
+
 function cons_nln!(nlp::GridapPDENLPModel, x::AbstractVector, c::AbstractVector)   # :433
   @lencheck nlp.meta.nvar x
   @lencheck nlp.meta.nnln c
