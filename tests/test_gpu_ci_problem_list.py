@@ -229,6 +229,10 @@ def test_host_memspace_on_every_problem(prob):
     tol = dict(rtol=1e-12, atol=1e-14)
     assert np.isclose(nh.obj(x), nlp.obj(_d(x)), rtol=1e-13, atol=1e-15)
     assert np.allclose(nh.grad(x), _h(nlp.grad(_d(x))), **tol)
+    fh, gh = nh.objgrad(x)
+    assert np.isclose(fh, nlp.obj(_d(x)), rtol=1e-13, atol=1e-15) and np.allclose(gh, _h(nlp.grad(_d(x))), **tol)
+    fh, ch = nh.objcons(x)
+    assert np.isclose(fh, nlp.obj(_d(x)), rtol=1e-13, atol=1e-15) and (m == 0 or np.allclose(ch, _h(nlp.cons(_d(x))), **tol))
     assert np.allclose(nh.hess_coord(x, obj_weight=0.3), _h(nlp.hess_coord(_d(x), obj_weight=0.3)), **tol)
     assert np.allclose(nh.hprod(x, v, obj_weight=0.3), _h(nlp.hprod(_d(x), _d(v), obj_weight=0.3)), **tol)
     r, c = nh.hess_structure(); rd, cd = nlp.hess_structure()
