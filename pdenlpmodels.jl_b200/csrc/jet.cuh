@@ -139,6 +139,17 @@ template <int M> PDENLP_HD Jet2<M> operator-(const Jet2<M>& a) {
   for (int k = 0; k < Jet2<M>::NH; ++k) r.h[k] = -a.h[k];
   return r;
 }
+// h * v with a structurally zero second derivative: the seeds (and everything affine in them) carry the literal
+// constant 0.0 in h after inlining, but IEEE arithmetic forbids folding 0.0 * v, which would keep the VALUE of the
+// other factor alive — and with it the gather of x — in kernels that only consume second derivatives (the Hessian
+// of a quadratic objective or of a bilinear residual does not depend on x at all).  The explicit test folds at
+// compile time for such operands and is a select otherwise.
+#ifdef PDENLP_NO_ZMUL  // A/B switch for measurements
+PDENLP_HD double zmul(double h, double v) { return h * v; }
+#else
+PDENLP_HD double zmul(double h, double v) { return h == 0.0 ? 0.0 : h * v; }
+#endif
+
 template <int M> PDENLP_HD Jet2<M> operator*(const Jet2<M>& a, const Jet2<M>& b) {
   Jet2<M> r; r.v = a.v * b.v;
 #pragma unroll
@@ -147,7 +158,7 @@ template <int M> PDENLP_HD Jet2<M> operator*(const Jet2<M>& a, const Jet2<M>& b)
   for (int k = 0; k < M; ++k)
 #pragma unroll
     for (int l = 0; l <= k; ++l)
-      r.h[k * (k + 1) / 2 + l] = a.h[k * (k + 1) / 2 + l] * b.v + a.v * b.h[k * (k + 1) / 2 + l] +
+      r.h[k * (k + 1) / 2 + l] = zmul(a.h[k * (k + 1) / 2 + l], b.v) + zmul(b.h[k * (k + 1) / 2 + l], a.v) +
                                  a.g[k] * b.g[l] + a.g[l] * b.g[k];
   return r;
 }
