@@ -33,6 +33,7 @@ class _Problem(C.Structure):
         ("cell_dofs_y", C.c_void_p), ("cell_dofs_u", C.c_void_p), ("dir_y", C.c_void_p), ("dir_u", C.c_void_p),
         ("params", C.c_double * 8),
         ("nfy", C.c_int32), ("nfu", C.c_int32), ("field_nfree", C.c_int64 * 8), ("field_ndir", C.c_int64 * 8),
+        ("compat_shifted_x", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -60,13 +61,14 @@ class Oracle:
     tables, quadrature and coefficient fields are restated inside the C++.
     """
 
-    def __init__(self, spec, cell_range=None, nthreads: int = 0):
+    def __init__(self, spec, cell_range=None, nthreads: int = 0, compat_shifted_x: bool = False):
         m = spec.model
         c0, c1 = (0, m.ncells) if cell_range is None else cell_range
         self.spec = spec
         self._keep = []
         P = _Problem()
         P.integrand = spec.integrand
+        P.compat_shifted_x = int(bool(compat_shifted_x))
         P.dim = m.dim
         if getattr(spec, "is_multifield", False):
             self._init_multifield(P, spec, c0, c1, nthreads)

@@ -125,6 +125,11 @@ typedef struct oracle_problem {
   int32_t nfy, nfu;
   int64_t field_nfree[8];
   int64_t field_ndir[8];
+  // 1: reproduce the reference's hess_coord!(x, lambda) literally: its FE constraint block is evaluated at
+  // FEFunction(Y, x) with the UN-shifted x (src/GridapPDENLPModel.jl:384), i.e. the y dofs are read from
+  // x[1:nfree_y] and the u dofs from x[nfree_y+1:...] although kappa occupies x[1:nparam]
+  int32_t compat_shifted_x;
+  int32_t reserved;
 } oracle_problem;
 }
 
@@ -355,10 +360,10 @@ static CellGeom cell_geom(const oracle_problem& P, int64_t c_local) {
 
 // gather the cell-local values [kappa ; y_e ; u_e] (PosNegReindex semantics)
 template <int NP, int NY, int NU>
-static void gather_cell(const oracle_problem& P, const double* x, int64_t c, double* z) {
+static void gather_cell(const oracle_problem& P, const double* x, int64_t c, double* z, bool unshifted = false) {
   for (int k = 0; k < NP; ++k) z[k] = x[k];
-  const double* xy = x + NP;
-  const double* xu = x + NP + P.nfree_y;
+  const double* xy = x + (unshifted ? 0 : NP);
+  const double* xu = xy + P.nfree_y;
   for (int a = 0; a < NY; ++a) { int g = P.cell_dofs_y[c * NY + a]; z[NP + a] = g > 0 ? xy[g - 1] : P.dir_y[-g - 1]; }
   for (int b = 0; b < NU; ++b) { int g = P.cell_dofs_u[c * NU + b]; z[NP + NY + b] = g > 0 ? xu[g - 1] : P.dir_u[-g - 1]; }
 }
@@ -634,7 +639,9 @@ struct Driver {
       }
       if (lambda) {
         // l_e(z) = sum_i lambda_e[i] c_e[i](z), lambda through the TEST space (Dirichlet entries = 0)
-        D2 r[NY]; cell_res<D2, NP, NY, NU>(P, T, G, zz, r);
+        D2 zc[N];
+        if (NP > 0 && P.compat_shifted_x) { double z2[N]; gather_cell<NP, NY, NU>(P, x, c, z2, true); seed2(z2, zc); }
+        D2 r[NY]; cell_res<D2, NP, NY, NU>(P, T, G, (NP > 0 && P.compat_shifted_x) ? zc : zz, r);
         D2 L = cst(0.0, zz[0]);
         for (int i = 0; i < NY; ++i) { int g = P.cell_dofs_y[c * NY + i]; double li = g > 0 ? lambda[g - 1] : 0.0; L = L + li * r[i]; }
         n = bh[c];

@@ -399,3 +399,19 @@ def test_dynamicsir_at_the_exact_solution(pkg, oracle_mod):
     assert out[6][0] <= 1e-5 < out[5][0] and out[6][1] <= 1e-10
     assert np.isclose(out[5][0] / out[6][0], 10.0, rtol=1e-3)
     assert np.isclose(out[2][1] / out[3][1], 1e4, rtol=1e-2)  # objective: fourth order
+
+
+def test_unshifted_x_quirk_has_no_effect_on_the_reference_problems(pkg, oracle_mod):
+    """The reference builds the FE constraint block of hess_coord!(x, lambda) at FEFunction(Y, x) with the
+    un-shifted x (src/GridapPDENLPModel.jl:384) although kappa occupies x[1:nparam].  The oracle can reproduce that
+    literally (compat_shifted_x); for every problem of the reference with nparam > 0 the residual is at most quadratic
+    in the fields, so its second derivatives do not depend on the evaluation point and both variants coincide bit for
+    bit — the CUDA path (correct shift) therefore agrees with the reference as it is."""
+    rng = np.random.default_rng(0)
+    for mk in (lambda: pkg.burger1d_param(9), lambda: pkg.poissonmixed(4), lambda: pkg.poissonmixed(3, 2, True),
+               lambda: pkg.poissonmixed2(4), lambda: pkg.poissonparam(4), lambda: pkg.poissonmixed(2, 3, True)):
+        spec = mk()
+        o = oracle_mod.Oracle(spec); oc = oracle_mod.Oracle(spec, compat_shifted_x=True)
+        x = rng.uniform(-1, 1, o.nvar); lam = rng.uniform(-1, 1, o.ncon)
+        assert np.array_equal(o.hess_coord(x, lam, 0.5), oc.hess_coord(x, lam, 0.5)), spec.name
+        assert np.array_equal(o.hprod(x, rng.uniform(-1, 1, o.nvar), lam, 0.5).shape, (o.nvar,))
