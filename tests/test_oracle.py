@@ -413,5 +413,7 @@ def test_unshifted_x_quirk_has_no_effect_on_the_reference_problems(pkg, oracle_m
         spec = mk()
         o = oracle_mod.Oracle(spec); oc = oracle_mod.Oracle(spec, compat_shifted_x=True)
         x = rng.uniform(-1, 1, o.nvar); lam = rng.uniform(-1, 1, o.ncon)
-        assert np.array_equal(o.hess_coord(x, lam, 0.5), oc.hess_coord(x, lam, 0.5)), spec.name
-        assert np.array_equal(o.hprod(x, rng.uniform(-1, 1, o.nvar), lam, 0.5).shape, (o.nvar,))
+        h, hc = o.hess_coord(x, lam, 0.5), oc.hess_coord(x, lam, 0.5)
+        k = o.nnzh_obj + o.nnzh_k_con          # the FE constraint block is the only part the quirk touches
+        assert np.array_equal(h[k:], hc[k:]), spec.name
+        assert np.allclose(h[:k], hc[:k], rtol=1e-14, atol=1e-16)  # dense kappa blocks: OpenMP summation order
