@@ -190,6 +190,10 @@ typedef struct pdenlp_info {
 
 const char* pdenlp_last_error(void);
 int pdenlp_abi_version(void);
+/* build provenance: 16 hex digits of the sha256 over the library's sources and headers, baked in at compile time
+   (pdenlpmodels.jl_b200/build.py: source_hash).  The host layer recomputes it from the tree and refuses a library
+   built from other sources. */
+const char* pdenlp_build_id(void);
 
 /* replaces nothing in the reference: new flattening hook run once after the
    constructor. */

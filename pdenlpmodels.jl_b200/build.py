@@ -22,6 +22,39 @@ NVCC_FLAGS = [
 ]
 
 
+def source_hash() -> str:
+    """Build id: sha256 over every source and header of the library (names + contents, fixed order).  It is
+    baked into the binary at compile time (-DPDENLP_BUILD_ID, returned by pdenlp_build_id()); capi.load()
+    recomputes it from the tree and refuses a library built from other sources."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(SOURCES) + sorted(HEADERS):
+        path = os.path.normpath(os.path.join(CSRC, f))
+        h.update(os.path.basename(path).encode() + b"\0")
+        with open(path, "rb") as fh:
+            h.update(fh.read())
+        h.update(b"\0")
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()[:16]
+
+
+def built_id(path: str = None) -> str:
+    """The build id baked into an existing library ('' if none).  Read from the file's bytes (marker string
+    "PDENLP_BUILD_ID=<id>;"), not through dlopen: a library already mapped in this process would answer for
+    the file it was loaded from, not for the file on disk now."""
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        return ""
+    import mmap
+    marker = b"PDENLP_BUILD_ID="
+    with open(path, "rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+        i = mm.find(marker)
+        if i < 0:
+            return ""
+        j = mm.find(b";", i)
+        return mm[i + len(marker): j].decode(errors="replace") if 0 < j - i < 64 else ""
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -30,11 +63,8 @@ def _nvcc() -> str:
 
 
 def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
-        return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
-    return any(os.path.getmtime(d) > t for d in deps)
+    """True when the library is missing or was built from other sources (content hash, not mtimes)."""
+    return built_id() != source_hash()
 
 
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
@@ -45,9 +75,12 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     objdir = os.path.join(CSRC, "build")
     os.makedirs(objdir, exist_ok=True)
 
+    bid = source_hash()
+
     def compile_one(src):
         obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        extra = [f'-DPDENLP_BUILD_ID="{bid}"'] if src == "pdenlp_cuda.cu" else []
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         return src, obj, cmd, subprocess.run(cmd, capture_output=True, text=True)
 
     with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
@@ -65,6 +98,8 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
         fh.write(" ".join(link) + "\n" + res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc link failed:\n" + res.stdout[-4000:] + res.stderr[-8000:])
+    if built_id() != bid:
+        raise RuntimeError("the freshly built library does not report the build id of the sources")
     if verbose:
-        print("nvcc ok ->", LIB_PATH, "(ptxas -v log in", log + ")")
+        print("nvcc ok ->", LIB_PATH, "build id", bid, "(ptxas -v log in", log + ")")
     return LIB_PATH

@@ -22,7 +22,7 @@ MEM_DEVICE, MEM_HOST = 0, 1
 
 # every symbol include/pdenlp_cuda.h declares
 SYMBOLS = [
-    "pdenlp_last_error", "pdenlp_abi_version", "pdenlp_create", "pdenlp_destroy", "pdenlp_get_info",
+    "pdenlp_last_error", "pdenlp_abi_version", "pdenlp_build_id", "pdenlp_create", "pdenlp_destroy", "pdenlp_get_info",
     "pdenlp_set_stream", "pdenlp_sync", "pdenlp_malloc", "pdenlp_free", "pdenlp_memcpy_h2d", "pdenlp_memcpy_d2h",
     "pdenlp_host_alloc", "pdenlp_host_free",
     "pdenlp_obj", "pdenlp_objgrad", "pdenlp_objcons", "pdenlp_grad", "pdenlp_cons", "pdenlp_jac_coord", "pdenlp_hess_coord", "pdenlp_hess_coord_obj",
@@ -76,6 +76,15 @@ def load():
     if missing:
         raise ImportError(f"libpdenlp_cuda.so lacks symbols: {missing}")
     lib.pdenlp_last_error.restype = C.c_char_p
+    lib.pdenlp_build_id.restype = C.c_char_p
+    # build provenance: the binary must have been built from the sources of this tree (PDENLP_CUDA_LIB selects an
+    # experimental build on purpose and is exempt)
+    if not os.environ.get("PDENLP_CUDA_LIB"):
+        from .build import source_hash
+        have, want = lib.pdenlp_build_id().decode(), source_hash()
+        if have != want:
+            raise ImportError(f"{LIB_PATH} is stale: built from sources {have}, the tree is {want}; "
+                              "run `python __graft_entry__.py` to rebuild (there is no fallback path)")
     vp, dbl, i64 = C.c_void_p, C.c_double, C.c_int64
     lib.pdenlp_create.argtypes = [C.POINTER(Desc), C.POINTER(vp)]
     lib.pdenlp_destroy.argtypes = [vp]
@@ -111,6 +120,10 @@ def load():
     lib.pdenlp_compaction_apply.argtypes = [vp, vp, vp, vp]
     _lib = lib
     return lib
+
+
+def build_id() -> str:
+    return load().pdenlp_build_id().decode()
 
 
 def check(rc):

@@ -126,6 +126,9 @@ int pdenlp_compaction_create(int64_t nnz, const int64_t* rows, const int64_t* co
     }                                                                                 \
   } while (0)
   if (rows_cols_on_device) {
+    // the caller may have produced rows/cols on a non-blocking stream (pdenlp_*_structure on the model's stream), which
+    // is not ordered with the legacy default stream used below: wait for the device once (setup-time only)
+    TRY(cudaDeviceSynchronize());
     drows = const_cast<int64_t*>(rows);
     dcols = const_cast<int64_t*>(cols);
   } else {
@@ -201,6 +204,9 @@ int pdenlp_compaction_structure(pdenlp_compaction* P, int64_t* rows, int64_t* co
       if (e != cudaSuccess) return cfail(PDENLP_ECUDA, cudaGetErrorString(e));
     }
   }
+  // device outputs were written on the legacy default stream; a consumer on a non-blocking stream is not ordered
+  // with it, so the call returns only when they are complete
+  if (on_device) CCU(cudaDeviceSynchronize());
   return PDENLP_OK;
 }
 

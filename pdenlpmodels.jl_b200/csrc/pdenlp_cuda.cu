@@ -51,7 +51,10 @@ struct pdenlp_model {
   double* scalar = nullptr;
   int32_t npartials = 0;
   // host-memspace staging
-  double *sx = nullptr, *slam = nullptr, *sv = nullptr, *sout = nullptr;
+  // (each staging buffer remembers its capacity: sv serves directions of length nvar (jprod!, hprod!) and ncon (jtprod!))
+  struct Stage { double* p = nullptr; int64_t len = 0; };
+  Stage sx, slam, sv;
+  double* sout = nullptr;
   int64_t sout_len = 0;
   // timing
   bool timing = false;
@@ -71,10 +74,17 @@ int dev_upload(pdenlp_model* m, const T* host, size_t n, T** out) {
   return PDENLP_OK;
 }
 
-int ensure_stage(pdenlp_model* m, double** p, int64_t n) {
-  if (*p == nullptr) {
-    CU(cudaMalloc((void**)p, std::max<int64_t>(n, 2) * 8));
-    m->owned.push_back(*p);
+int ensure_stage(pdenlp_model* m, pdenlp_model::Stage* st, int64_t n) {
+  if (st->p == nullptr || st->len < n) {  // grow: the same buffer may be asked for a longer vector later
+    if (st->p) {
+      CU(cudaStreamSynchronize(m->stream));  // an earlier callback may still read it
+      cudaFree(st->p);
+      m->owned.erase(std::find(m->owned.begin(), m->owned.end(), (void*)st->p));
+      st->p = nullptr; st->len = 0;
+    }
+    CU(cudaMalloc((void**)&st->p, std::max<int64_t>(n, 2) * 8));
+    m->owned.push_back(st->p);
+    st->len = n;
   }
   return PDENLP_OK;
 }
@@ -90,12 +100,12 @@ int ensure_out(pdenlp_model* m, int64_t n) {
 }
 
 // resolve an input vector to a device pointer (staging it for PDENLP_MEM_HOST)
-int in_ptr(pdenlp_model* m, const double* user, int64_t n, double** stage, const double** dev) {
+int in_ptr(pdenlp_model* m, const double* user, int64_t n, pdenlp_model::Stage* stage, const double** dev) {
   if (user == nullptr) { *dev = nullptr; return PDENLP_OK; }
   if (m->d.memspace == PDENLP_MEM_DEVICE) { *dev = user; return PDENLP_OK; }
   if (int rc = ensure_stage(m, stage, n)) return rc;
-  CU(cudaMemcpyAsync(*stage, user, n * 8, cudaMemcpyHostToDevice, m->stream));
-  *dev = *stage;
+  CU(cudaMemcpyAsync(stage->p, user, n * 8, cudaMemcpyHostToDevice, m->stream));
+  *dev = stage->p;
   return PDENLP_OK;
 }
 int out_ptr(pdenlp_model* m, double* user, int64_t n, double** dev) {
@@ -183,6 +193,15 @@ extern "C" {
 
 const char* pdenlp_last_error(void) { return pdenlp_g_err.c_str(); }
 int pdenlp_abi_version(void) { return PDENLP_ABI_VERSION; }
+#ifndef PDENLP_BUILD_ID
+#define PDENLP_BUILD_ID "unknown"
+#endif
+// (the marker prefix lets build.py read the id from the file without loading it)
+__attribute__((used, visibility("default"))) extern const char pdenlp_build_marker[] = "PDENLP_BUILD_ID=" PDENLP_BUILD_ID ";";
+const char* pdenlp_build_id(void) {
+  static const std::string id(pdenlp_build_marker + 16, sizeof(pdenlp_build_marker) - 16 - 2);
+  return id.c_str();
+}
 
 int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
   if (!desc || !out) return fail(PDENLP_EINVAL, "null argument");

@@ -89,6 +89,30 @@ class SlabLayout:
         self.owner_u = np.argmax(tu, axis=0) if nu else np.zeros(0, dtype=np.int64)
         self.p, self.ny, self.nu = p, ny, nu
 
+    # ---- dense kappa blocks (dof-indexed like the vector outputs: only interface rows need a reduction) ----------
+    def trap_offsets(self, prows: int) -> np.ndarray:
+        """Start of column j (0-based) of a lower trapezoid with `prows` rows and p columns, "i fastest", j <= i
+        (src/additional_obj_terms.jl:311, src/GridapPDENLPModel.jl:362)."""
+        j = np.arange(self.p + 1, dtype=np.int64)
+        return j * prows - j * (j - 1) // 2
+
+    def jac_kblock_index(self, rows: np.ndarray) -> np.ndarray:
+        """Positions of the given constraint rows (0-based) in the column-major ncon x p Jacobian kappa-block."""
+        return (np.arange(self.p, dtype=np.int64)[:, None] * self.ny + rows[None, :]).reshape(-1)
+
+    def trap_index(self, prows: int, var_rows: np.ndarray) -> np.ndarray:
+        """Positions of the given x-layout rows (0-based, kappa rows included) in a Hessian kappa trapezoid."""
+        off = self.trap_offsets(prows)
+        out = []
+        for j in range(self.p):
+            r = var_rows[(var_rows >= j) & (var_rows < prows)]
+            out.append(off[j] + (r - j))
+        return np.concatenate(out) if out else np.zeros(0, dtype=np.int64)
+
+    def var_owner(self) -> np.ndarray:
+        """Owning rank of every x-layout entry (kappa entries: rank 0)."""
+        return np.concatenate([np.zeros(self.p, dtype=np.int64), self.owner_y, self.owner_u]).astype(np.int64)
+
 
 class ShardedModel:
     def __init__(self, spec, local, layout: SlabLayout, rank: int, group=None):
@@ -154,13 +178,93 @@ class ShardedModel:
     def hprod_(self, x, *args, obj_weight: float = 1.0):
         return self._reduce_interface(self.local.hprod_(x, *args, obj_weight=self._ow(obj_weight)), "var")
 
-    # ---- COO streams: local slices, no communication ---------------------
+    # ---- COO streams: local slices of the FE segments, no communication.  The dense kappa blocks are dof-indexed
+    #      (not cell-indexed) sums over cells, i.e. slab partials exactly like grad!/cons!: their INTERFACE rows (and
+    #      the p x p kappa-kappa corner) are packed and all-reduced; afterwards every rank holds the exact value of
+    #      every row its slab touches and zero elsewhere ------------------------------------------------------------
+    def _reduce_packed(self, vals, base: int, idx: np.ndarray, key):
+        """Sum the entries base + idx of a COO value vector over the ranks (one packed all-reduce)."""
+        if self.world == 1 or idx.size == 0:
+            return vals
+        t = vals if isinstance(vals, torch.Tensor) else torch.from_numpy(vals)
+        ck = (key, t.device)
+        if ck not in self._idx_cache:
+            self._idx_cache[ck] = torch.from_numpy(idx + base).to(t.device)
+        ix = self._idx_cache[ck]
+        buf = t.index_select(0, ix).contiguous()
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+        t.index_copy_(0, ix, buf)
+        return vals
+
+    def _prows_obj(self) -> int:
+        pm = self.local.pdemeta
+        p = self.layout.p
+        return p if pm.nnzh_k_obj == p * (p + 1) // 2 else p + self.layout.ny + self.layout.nu
+
     def jac_coord_(self, x, vals):
-        return self.local.jac_coord_(x, vals)
+        """[k-block (ncon x p) | this slab's y-block | this slab's u-block]; interface rows of the kappa-block reduced
+        (src/jacobian_functions.jl:135-142)."""
+        vals = self.local.jac_coord_(x, vals)
+        if self.layout.p == 0:
+            return vals
+        return self._reduce_packed(vals, 0, self.layout.jac_kblock_index(self.layout.iface_con), "jk")
 
     def hess_coord_(self, x, *args, obj_weight: float = 1.0):
-        """Local slices of the FE segments; the dense kappa blocks are slab partials (to be summed over the ranks)."""
-        return self.local.hess_coord_(x, *args, obj_weight=self._ow(obj_weight))
+        """[obj k-block | this slab's obj FE | cons k-block | this slab's cons FE]; interface rows of both kappa
+        trapezoids reduced (src/GridapPDENLPModel.jl:361-380, src/additional_obj_terms.jl:286-314)."""
+        vals = self.local.hess_coord_(x, *args, obj_weight=self._ow(obj_weight))
+        L, pm = self.layout, self.local.pdemeta
+        if L.p == 0:
+            return vals
+        nvar = L.p + L.ny + L.nu
+        vals = self._reduce_packed(vals, 0, L.trap_index(self._prows_obj(), L.iface_var), "hko")
+        return self._reduce_packed(vals, pm.nnzh_obj, L.trap_index(nvar, L.iface_var), "hkc")
+
+    def assemble_global_coo(self, vals, which: str):
+        """The GLOBAL COO value stream (replicated on every rank) from the per-rank streams: every dense kappa-block
+        row from its owner, then each FE segment as the concatenation of the slab slices in rank order.
+        Verification helper (O(nnz) traffic); which = "jac" | "hess"."""
+        pm, L = self.local.pdemeta, self.layout
+        nvar = L.p + L.ny + L.nu
+        t = (vals if isinstance(vals, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(vals))).clone()
+        own_var = np.nonzero(L.var_owner() == self.rank)[0]
+        own_con = np.nonzero(L.owner_y == self.rank)[0]
+        if which == "jac":
+            dense = [((0, pm.nnzj_k), L.jac_kblock_index(own_con))]
+            fe = [(pm.nnzj_k, pm.nnzj_k + pm.nnzj_y), (pm.nnzj_k + pm.nnzj_y, pm.nnzj_k + pm.nnzj_y + pm.nnzj_u)]
+            order = [("d", 0), ("f", 0), ("f", 1)]
+        else:
+            nfo = pm.nnzh_obj - pm.nnzh_k_obj
+            dense = [((0, pm.nnzh_k_obj), L.trap_index(self._prows_obj(), own_var)),
+                     ((pm.nnzh_obj, pm.nnzh_obj + pm.nnzh_k_con), L.trap_index(nvar, own_var))]
+            fe = [(pm.nnzh_k_obj, pm.nnzh_k_obj + nfo),
+                  (pm.nnzh_obj + pm.nnzh_k_con, pm.nnzh_obj + pm.nnzh_k_con + pm.nnzh_fe)]
+            order = [("d", 0), ("f", 0), ("d", 1), ("f", 1)]
+        dense_out = []
+        for (a, b), own in dense:
+            blk = t[a:b].clone()
+            if self.world > 1 and b > a:
+                keep = torch.zeros(b - a, dtype=torch.bool, device=blk.device)
+                keep[torch.from_numpy(own).to(blk.device)] = True
+                blk = torch.where(keep, blk, torch.zeros_like(blk))
+                dist.all_reduce(blk, op=dist.ReduceOp.SUM, group=self.group)
+            dense_out.append(blk)
+        gathered = []
+        for a, b in fe:
+            mine = t[a:b].contiguous()
+            if self.world == 1:
+                gathered.append(mine)
+                continue
+            n = torch.tensor([mine.numel()], dtype=torch.int64, device=mine.device)
+            sizes = [torch.zeros_like(n) for _ in range(self.world)]
+            dist.all_gather(sizes, n, group=self.group)
+            sizes = [int(v.item()) for v in sizes]
+            pad = torch.zeros(max(sizes + [1]), dtype=mine.dtype, device=mine.device)
+            pad[: mine.numel()] = mine
+            parts = [torch.zeros_like(pad) for _ in range(self.world)]
+            dist.all_gather(parts, pad, group=self.group)
+            gathered.append(torch.cat([q[:k] for q, k in zip(parts, sizes)]))
+        return torch.cat([dense_out[i] if kind == "d" else gathered[i] for kind, i in order])
 
     def segment_sizes(self) -> dict:
         pm = self.local.pdemeta

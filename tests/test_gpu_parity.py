@@ -152,7 +152,18 @@ def test_host_memspace_matches_device(case, pkg):
     if case["name"] not in ("membrane8", "burger_nl_70", "dynamicsir_100"):
         pytest.skip("one small case per family is enough")
     nlp_h = GridapPDENLPModel(case["spec"], device="cuda:0", memspace="host")
-    x, lam = case["x"], case["lam"]
+    x, lam, v = case["x"], case["lam"], case["v"]
+    # jtprod! FIRST: its direction has length ncon < nvar, and the staging buffer of the directions is shared with
+    # jprod!/hprod! (length nvar) — it must grow (round-1 bug: sized by first use, later overflowed)
+    nlp_d = case["nlp"]
+    assert nlp_h.meta.nvar > nlp_h.meta.ncon
+    big = 1e3 * np.ones_like(v)  # a direction whose overflowing tail would be visible in neighbouring arrays
+    tol = dict(rtol=1e-12, atol=1e-13)
+    assert np.allclose(nlp_h.jtprod(x, lam), nlp_d.jtprod(_d(x), _d(lam)).cpu().numpy(), **tol)
+    assert np.allclose(nlp_h.jprod(x, big), nlp_d.jprod(_d(x), _d(big)).cpu().numpy(), rtol=1e-12, atol=1e-9)
+    assert np.allclose(nlp_h.hprod(x, lam, v, obj_weight=0.37), nlp_d.hprod(_d(x), _d(lam), _d(v), obj_weight=0.37).cpu().numpy(), **tol)
+    assert np.allclose(nlp_h.jtprod(x, lam), nlp_d.jtprod(_d(x), _d(lam)).cpu().numpy(), **tol)
+    assert np.allclose(nlp_h.grad(x), nlp_d.grad(_d(x)).cpu().numpy(), **tol)
     jd = case["nlp"].jac_coord(_d(x)).cpu().numpy()
     hd = case["nlp"].hess_coord(_d(x), _d(lam), obj_weight=0.5).cpu().numpy()
     assert np.array_equal(nlp_h.jac_coord(x), jd)

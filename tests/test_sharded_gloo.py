@@ -21,7 +21,8 @@ class OracleLocal:
         self.o = orc
         class PM: pass
         self.pdemeta = PM()
-        self.pdemeta.nnzj_y, self.pdemeta.nnzj_u, self.pdemeta.nnzh_fe = orc.nnzj_y, orc.nnzj_u, orc.nnzh_fe
+        for k in ("nnzj_k", "nnzj_y", "nnzj_u", "nnzh_fe", "nnzh_obj", "nnzh_k_obj", "nnzh_k_con"):
+            setattr(self.pdemeta, k, getattr(orc, k))
 
     def obj(self, x): return self.o.obj(x)
     def grad_(self, x, g): g[:] = self.o.grad(x); return g
@@ -48,7 +49,9 @@ def _worker(rank, world, port, case, q):
     try:
         spec = {"membrane": lambda: pkg.controlelasticmembrane(8), "burger_nl": lambda: pkg.burger1d_param(100),
                 "pb": lambda: pkg.poissonboltzman2d(9), "dynamicsir": lambda: pkg.dynamicsir(100),
-                "poissonparam": lambda: pkg.poissonparam(9)}[case]()
+                "poissonparam": lambda: pkg.poissonparam(9), "poissonmixed": lambda: pkg.poissonmixed(7),
+                "poissonmixed2": lambda: pkg.poissonmixed2(7),
+                "kappa3d_u": lambda: pkg.poissonmixed(4, 3, True)}[case]()  # BASELINE configs[4] family
         layout = SlabLayout(spec, world)
         full = O.Oracle(spec, nthreads=1)
         local = OracleLocal(O.Oracle(spec, layout.ranges[rank], nthreads=1))
@@ -79,20 +82,24 @@ def _worker(rank, world, port, case, q):
         res["jac_slices"] = bool(ok)
         hl = sm.hess_coord_(x, lam, np.empty(local.o.nnzh), obj_weight=0.3); hf = full.hess_coord(x, lam, 0.3)
         lo = local.o
-        if getattr(spec, "no_fe_obj", False):
-            # NoFETerm: [obj kappa triangle | cons kappa trapezoid | cons FE]; fk(kappa) comes from rank 0 only and
-            # the dense kappa blocks are slab partials that sum to the global ones
-            kb = torch.from_numpy(hl[: lo.nnzh_obj + lo.nnzh_k_con].copy())
-            dist.all_reduce(kb, op=dist.ReduceOp.SUM)
-            ok = np.allclose(kb.numpy(), hf[: full.nnzh_obj + full.nnzh_k_con], rtol=1e-12, atol=1e-14)
-            b = full.nnzh_obj + full.nnzh_k_con + off["hfe"]
-            ok &= np.array_equal(hl[lo.nnzh_obj + lo.nnzh_k_con:], hf[b: b + lo.nnzh_fe])
-        else:
-            a = full.nnzh_k_obj + off["hfe"]
-            ok = np.array_equal(hl[lo.nnzh_k_obj: lo.nnzh_k_obj + lo.nnzh_fe], hf[a: a + lo.nnzh_fe])
-            b = full.nnzh_obj + full.nnzh_k_con + off["hfe"]
-            ok &= np.array_equal(hl[lo.nnzh_obj + lo.nnzh_k_con:], hf[b: b + lo.nnzh_fe])
+        # (the dense kappa blocks: interface rows reduced inside hess_coord_, checked through the global assembly below;
+        # fk(kappa) of a NoFETerm objective comes from rank 0 only)
+        ok = True
+        nfo = lo.nnzh_obj - lo.nnzh_k_obj  # objective FE block: nnzh_fe, or 0 for a NoFETerm objective
+        a = full.nnzh_k_obj + (off["hfe"] if nfo else 0)
+        ok &= np.array_equal(hl[lo.nnzh_k_obj: lo.nnzh_obj], hf[a: a + nfo])
+        b = full.nnzh_obj + full.nnzh_k_con + off["hfe"]
+        ok &= np.array_equal(hl[lo.nnzh_obj + lo.nnzh_k_con:], hf[b: b + lo.nnzh_fe])
         res["hess_slices"] = bool(ok)
+        # Jacobian kappa-block (ncon x p): every row this slab touches is exact after the interface reduction, the rest 0
+        if full.nnzj_k:
+            jk, jkf = jl[: lo.nnzj_k].reshape(spec.nparam, -1), jf[: full.nnzj_k].reshape(spec.nparam, -1)
+            res["jac_kblock"] = bool(np.allclose(jk[:, ty], jkf[:, ty], rtol=1e-12, atol=1e-14) and np.all(jk[:, ~ty] == 0))
+        # and the per-rank streams assemble to the single-rank GLOBAL streams
+        gj = sm.assemble_global_coo(jl, "jac").numpy(); gh = sm.assemble_global_coo(hl, "hess").numpy()
+        res["global_jac"] = bool(gj.shape == jf.shape and np.allclose(gj, jf, rtol=1e-12, atol=1e-14)
+                                 and np.array_equal(gj[full.nnzj_k:], jf[full.nnzj_k:]))
+        res["global_hess"] = bool(gh.shape == hf.shape and np.allclose(gh, hf, rtol=1e-12, atol=1e-14))
         res["iface_small"] = bool(layout.iface_var.size < 0.5 * full.nvar)
         q.put((rank, res))
     finally:
@@ -103,7 +110,8 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-@pytest.mark.parametrize("case", ["membrane", "burger_nl", "pb", "dynamicsir", "poissonparam"])
+@pytest.mark.parametrize("case", ["membrane", "burger_nl", "pb", "dynamicsir", "poissonparam", "poissonmixed",
+                                  "poissonmixed2", "kappa3d_u"])
 def test_world2_gloo(case, oracle_mod):
     oracle_mod.build()
     ctx = mp.get_context("spawn")
