@@ -100,6 +100,34 @@ template <class T, int N> static inline Dual<T, N> xsinh(const Dual<T, N>& a) {
 template <class T, int N> static inline Dual<T, N> xcosh(const Dual<T, N>& a) {
   Dual<T, N> r; r.v = xcosh(a.v); T s = xsinh(a.v); for (int i = 0; i < N; ++i) r.d[i] = s * a.d[i]; return r; }
 
+// ------------------------------------------------------------------ long scalar sums
+// The reference's scalar reductions over ALL cells are `sum(::DomainContribution)` (src/additional_obj_terms.jl:135-143,
+// 234-242: obj, and through ForwardDiff the kappa entries of grad! and the kappa-kappa entries of the objective
+// Hessian, :275-314).  That is Julia's generic `sum` over an indexable array: PAIRWISE summation — Base
+// `mapreduce_impl(f, op, A, ifirst, ilast, blksize = 1024)` (third party: Julia Base reduce.jl, not in /root/reference):
+// ranges shorter than 1024 are added left to right, longer ones are halved recursively.  Restated here on the per-cell
+// values in cell order; its error grows like log(n)*eps, whereas a plain left-to-right loop over 10^6 same-sign cell
+// values drifts by ~1e-12 relative — more than the parity tolerance.  (Inside a block Julia's loop is @simd, so even
+// the reference's bits depend on the SIMD width; any summation of pairwise accuracy agrees with it to ~1e-15.)
+static double pairwise_sum(const double* a, int64_t ifirst, int64_t ilast /* inclusive */) {
+  if (ilast < ifirst) return 0.0;
+  if (ifirst == ilast) return a[ifirst];
+  if (ilast - ifirst < 1024) {
+    double v = a[ifirst] + a[ifirst + 1];
+    for (int64_t i = ifirst + 2; i <= ilast; ++i) v += a[i];
+    return v;
+  }
+  const int64_t imid = ifirst + ((ilast - ifirst) >> 1);
+  return pairwise_sum(a, ifirst, imid) + pairwise_sum(a, imid + 1, ilast);
+}
+// per-cell values of `ncomp` scalar quantities, summed pairwise over the cells
+struct CellSums {
+  int ncomp; int64_t ncells; std::vector<double> v;  // [comp][cell]
+  CellSums(int nc, int64_t n) : ncomp(nc), ncells(n), v((size_t)(nc > 0 ? nc : 1) * (size_t)n, 0.0) {}
+  double& at(int comp, int64_t cell) { return v[(size_t)comp * ncells + cell]; }
+  double sum(int comp) const { return pairwise_sum(v.data() + (size_t)comp * ncells, 0, ncells - 1); }
+};
+
 // ------------------------------------------------------------------ problem
 extern "C" {
 typedef struct oracle_problem {
@@ -437,13 +465,13 @@ struct Driver {
   static double obj(const oracle_problem& P, const double* x) {
     if (is_nofe(P)) return nofe_obj<double>(P, x, NP);  // _obj_integral(::NoFETerm, k, x) = f(k)
     RefTables T = make_tables(P);
-    double total = 0.0;  // sum(::DomainContribution): cell order
+    CellSums S(1, P.ncells);  // sum(::DomainContribution): pairwise over the cells (see pairwise_sum)
     for (int64_t c = 0; c < P.ncells; ++c) {
       double z[N]; gather_cell<NP, NY, NU>(P, x, c, z);
       CellGeom G = cell_geom(P, c);
-      total += cell_obj<double, NP, NY, NU>(P, T, G, z);
+      S.at(0, c) = cell_obj<double, NP, NY, NU>(P, T, G, z);
     }
-    return total;
+    return S.sum(0);
   }
 
   static void grad(const oracle_problem& P, const double* x, double* g) {
@@ -458,15 +486,17 @@ struct Driver {
       for (int i = 0; i < NP; ++i) g[i] = F.d[i];
       return;
     }
+    CellSums S(NP, P.ncells);  // g[1:p] = d(sum over cells)/dkappa: the same pairwise `sum`, on duals
     for (int64_t c = 0; c < P.ncells; ++c) {
       double z[N]; gather_cell<NP, NY, NU>(P, x, c, z);
       D1 zz[N]; seed1(z, zz);
       CellGeom G = cell_geom(P, c);
       D1 F = cell_obj<D1, NP, NY, NU>(P, T, G, zz);
-      for (int k = 0; k < NP; ++k) g[k] += F.d[k];
+      for (int k = 0; k < NP; ++k) S.at(k, c) = F.d[k];
       for (int a = 0; a < NY; ++a) { int gid = P.cell_dofs_y[c * NY + a]; if (gid > 0) g[NP + gid - 1] += F.d[NP + a]; }
       for (int b = 0; b < NU; ++b) { int gid = P.cell_dofs_u[c * NU + b]; if (gid > 0) g[NP + P.nfree_y + gid - 1] += F.d[NP + NY + b]; }
     }
+    for (int k = 0; k < NP; ++k) g[k] = S.sum(k);
   }
 
   static void cons(const oracle_problem& P, const double* x, double* cvec) {
@@ -617,6 +647,10 @@ struct Driver {
       DK2 F = nofe_obj<DK2>(P, k, NP);
       for (int j = 0; j < NP; ++j) for (int i = j; i < NP; ++i) vko[trap_pos(i + 1, j + 1, prows)] = F.d[i].d[j];
     }
+    // kappa-kappa corner entries are sums over ALL cells: per-cell values, summed pairwise afterwards (deterministic,
+    // independent of the thread count); the cross rows (a dof is touched by a handful of cells) are added in place
+    constexpr int NKK = NP * (NP + 1) / 2;
+    CellSums Sko(NP > 0 ? NKK : 0, NP > 0 ? P.ncells : 0), Skc(NP > 0 ? NKK : 0, NP > 0 ? P.ncells : 0);
 #pragma omp parallel for schedule(static) num_threads(P.nthreads > 0 ? P.nthreads : omp_get_max_threads())
     for (int64_t c = 0; c < P.ncells; ++c) {
       double z[N]; gather_cell<NP, NY, NU>(P, x, c, z);
@@ -631,9 +665,10 @@ struct Driver {
         visit_hess_cell(P, c, [&](int li, int lj, int64_t, int64_t) { vfo[n++] = F.d[NP + li].d[NP + lj]; });
       }
       if (NP > 0 && !nofe) {
+        for (int j = 0, e = 0; j < NP; ++j)
+          for (int i = j; i < NP; ++i, ++e) Sko.at(e, c) = F.d[i].d[j];
 #pragma omp critical
         for (int j = 0; j < NP; ++j) {
-          for (int i = j; i < NP; ++i) vko[trap_pos(i + 1, j + 1, prows)] += F.d[i].d[j];
           if (!inde) for (int a = 0; a < NY + NU; ++a) { int64_t g = gid[a]; if (g > 0) vko[trap_pos(g + NP, j + 1, prows)] += F.d[NP + a].d[j]; }
         }
       }
@@ -647,13 +682,21 @@ struct Driver {
         n = bh[c];
         visit_hess_cell(P, c, [&](int li, int lj, int64_t, int64_t) { vfc[n++] = L.d[NP + li].d[NP + lj]; });
         if (NP > 0) {
+          for (int j = 0, e = 0; j < NP; ++j)
+            for (int i = j; i < NP; ++i, ++e) Skc.at(e, c) = L.d[i].d[j];
 #pragma omp critical
           for (int j = 0; j < NP; ++j) {
-            for (int i = j; i < NP; ++i) vkc[trap_pos(i + 1, j + 1, nvar)] += L.d[i].d[j];
             for (int a = 0; a < NY + NU; ++a) { int64_t g = gid[a]; if (g > 0) vkc[trap_pos(g + NP, j + 1, nvar)] += L.d[NP + a].d[j]; }
           }
         }
       }
+    }
+    if (NP > 0) {
+      for (int j = 0, e = 0; j < NP; ++j)
+        for (int i = j; i < NP; ++i, ++e) {
+          if (!nofe) vko[trap_pos(i + 1, j + 1, prows)] = Sko.sum(e);
+          if (lambda) vkc[trap_pos(i + 1, j + 1, nvar)] = Skc.sum(e);
+        }
     }
     // vals .*= obj_weight on the objective part only (GridapPDENLPModel.jl:299 runs before the constraint part)
     for (int64_t i = 0; i < sz[3] + sz[6]; ++i) vals[i] *= obj_weight;
@@ -806,9 +849,9 @@ struct MFDriver {
     int n = 0; visit(P, c, r0, r1, c0, c1, lower, [&](int, int, int64_t, int64_t) { ++n; }); return n; }
 
   static double obj(const oracle_problem& P, const double* x) {
-    RefTables T = make_tables(P); double total = 0.0;
-    for (int64_t c = 0; c < P.ncells; ++c) { double z[N]; gather(P, x, c, z); total += cell_obj<double>(P, T, cell_geom(P, c), z); }
-    return total;
+    RefTables T = make_tables(P); CellSums S(1, P.ncells);  // pairwise over the cells (see pairwise_sum)
+    for (int64_t c = 0; c < P.ncells; ++c) { double z[N]; gather(P, x, c, z); S.at(0, c) = cell_obj<double>(P, T, cell_geom(P, c), z); }
+    return S.sum(0);
   }
   static void grad(const oracle_problem& P, const double* x, double* g) {
     RefTables T = make_tables(P);

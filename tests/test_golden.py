@@ -19,10 +19,7 @@ def _spec(pkg, name):
     return mod.CASES[name](pkg)
 
 
-def _close(a, b):
-    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
-    scale = max(np.abs(b).max() if b.size else 0.0, 1e-300)
-    return a.shape == b.shape and (np.abs(a - b).max() / scale if b.size else 0.0) <= RTOL
+from parity import is_close as _close  # noqa: E402  (element-wise + segment-relative 1e-12, tests/parity.py)
 
 
 @pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-4] for f in FILES])

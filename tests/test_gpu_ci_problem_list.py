@@ -109,9 +109,7 @@ def test_values_against_oracle(prob, oracle_mod):
     x = _points(n)[2]; xd = _d(x)
     y = np.random.default_rng(12).uniform(-1, 1, m)
 
-    def close(a, b):
-        b = np.asarray(b); scale = max(np.abs(b).max() if b.size else 0.0, 1e-300)
-        return a.shape == b.shape and (np.abs(a - b).max() / scale if b.size else 0.0) <= 1e-12
+    from parity import is_close as close  # element-wise + segment-relative 1e-12 (tests/parity.py)
 
     assert abs(nlp.obj(xd) - orc.obj(x)) <= 1e-12 * max(abs(orc.obj(x)), 1e-300)
     assert close(_h(nlp.grad(xd)), orc.grad(x))
