@@ -103,7 +103,10 @@ enum pdenlp_integrand {
   /* nparam=2, plain MixedEnergyFETerm (inde = false: objective kappa-block with cross rows):
      f = k1*(sol-y)^2 + 0.5*(k2-1)^2 ; res = k1*grad(v).grad(y) - v*f*k2
      test/problems/poissonmixed2.jl:35-44 */
-  PDENLP_KAPPA_POISSON2 = 14
+  PDENLP_KAPPA_POISSON2 = 14,
+  /* TEST ONLY: PDENLP_POISSON_BOLTZMANN with its shortcut traits deliberately mis-declared; pdenlp_create must
+     reject it with PDENLP_EINVAL (create-time self-check, see pdenlp_selfcheck_error) */
+  PDENLP_SELFTEST_WRONG_TRAIT = 1000
 };
 
 /* coefficient fields sampled at quadrature points, coef[k][cell][q] */
@@ -200,6 +203,13 @@ const char* pdenlp_build_id(void);
 int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out);
 int pdenlp_destroy(pdenlp_model* m);
 int pdenlp_get_info(const pdenlp_model* m, pdenlp_info* info);
+
+/* Create-time self-check.  Integrand traits select shortcuts (a constraint FE Hessian block that is structurally zero
+   is zero-filled instead of computed; integrands whose FE-field derivatives are the same at every quadrature point of
+   a cell use pre-integrated reference tensors).  pdenlp_create runs the shortcut and the generic per-point kernels
+   on a sample of the model's own cells with pseudo-random x, lambda, v and fails with PDENLP_EINVAL if they differ by
+   more than 1e-12 (relative); this returns the worst relative difference it saw (0 when no shortcut applies). */
+int pdenlp_selfcheck_error(const pdenlp_model* m, double* max_rel_err);
 
 /* run the callbacks on this CUDA stream (a cudaStream_t cast to void*);
    NULL = the legacy default stream */

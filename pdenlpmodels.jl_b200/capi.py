@@ -27,7 +27,7 @@ SYMBOLS = [
     "pdenlp_host_alloc", "pdenlp_host_free",
     "pdenlp_obj", "pdenlp_objgrad", "pdenlp_objcons", "pdenlp_grad", "pdenlp_cons", "pdenlp_jac_coord", "pdenlp_hess_coord", "pdenlp_hess_coord_obj",
     "pdenlp_jprod", "pdenlp_jtprod", "pdenlp_hprod", "pdenlp_jac_structure", "pdenlp_hess_structure",
-    "pdenlp_launch_count", "pdenlp_last_kernel_ms", "pdenlp_set_timing",
+    "pdenlp_selfcheck_error", "pdenlp_launch_count", "pdenlp_last_kernel_ms", "pdenlp_set_timing",
     "pdenlp_compaction_create", "pdenlp_compaction_destroy", "pdenlp_compaction_nnz",
     "pdenlp_compaction_structure", "pdenlp_compaction_apply",
 ]
@@ -110,6 +110,7 @@ def load():
     lib.pdenlp_hprod.argtypes = [vp, vp, vp, dbl, vp, vp]
     lib.pdenlp_jac_structure.argtypes = [vp, vp, vp]
     lib.pdenlp_hess_structure.argtypes = [vp, vp, vp]
+    lib.pdenlp_selfcheck_error.argtypes = [vp, C.POINTER(dbl)]
     lib.pdenlp_launch_count.argtypes = [vp, C.POINTER(i64)]
     lib.pdenlp_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.pdenlp_set_timing.argtypes = [vp, C.c_int32]
@@ -238,6 +239,11 @@ class Handle:
         n = C.c_int64()
         check(load().pdenlp_launch_count(self._h, C.byref(n)))
         return n.value
+
+    def selfcheck_error(self) -> float:
+        e = C.c_double()
+        check(load().pdenlp_selfcheck_error(self._h, C.byref(e)))
+        return e.value
 
     def set_timing(self, on: bool):
         check(load().pdenlp_set_timing(self._h, 1 if on else 0))

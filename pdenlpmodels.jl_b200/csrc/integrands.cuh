@@ -69,6 +69,15 @@ struct PoissonBoltzmann : FieldIdx<DIM_, 0> {
   }
 };
 
+// TEST ONLY (PDENLP_SELFTEST_WRONG_TRAIT): the Poisson-Boltzmann integrand with both shortcut traits WRONGLY set — the
+// sinh term makes the residual non-affine, so its constraint FE Hessian block is not zero and its derivatives differ
+// from point to point.  pdenlp_create must refuse it (create-time self-check), tests/test_gpu_error_paths.py.
+template <int DIM_>
+struct WrongTraitPB : PoissonBoltzmann<DIM_> {
+  static constexpr bool FE_DERIVS_POINT_INDEPENDENT = true;
+  static constexpr bool RES_FE_HESSIAN_ZERO = true;
+};
+
 struct BurgerLin : FieldIdx<1, 0> {
   using I = FieldIdx<1, 0>;
   static constexpr bool HAS_CONST = false;

@@ -90,7 +90,16 @@ struct KTab {
   static constexpr int OFF_UY = NB * NB * NY * NY;
   static constexpr int OFF_YU = OFF_UY + NB * NY * NU;
   static constexpr int OFF_UU = OFF_YU + NB * NU * NY;
-  static constexpr int TOTAL = ENABLED ? ((OFF_UU + NU * NU + 1) & ~1) : 0;
+  // used by the K-path vector kernels (kvector.cuh): lap[j][i] = sum_{d>=1} yy[d][d][j][i] (Laplace-type forms),
+  // first-order tensors y1[k][j] = sum_q w_q By_j[k](q), u1[b] = sum_q w_q psi_b(q), and vol = sum_q w_q
+  static constexpr int OFF_LAP = (OFF_UU + NU * NU + 1) & ~1;
+  static constexpr int OFF_Y1 = OFF_LAP + NY * NY;
+  static constexpr int OFF_U1 = OFF_Y1 + NB * NY;
+  static constexpr int OFF_VOL = OFF_U1 + NU;
+  static constexpr int TOTAL = ENABLED ? ((OFF_VOL + 1 + 1) & ~1) : 0;
+  __host__ __device__ static constexpr int lap(int j, int i) { return OFF_LAP + j * NY + i; }
+  __host__ __device__ static constexpr int y1(int k, int j) { return OFF_Y1 + k * NY + j; }
+  __host__ __device__ static constexpr int u1(int b) { return OFF_U1 + b; }
   __host__ __device__ static constexpr int yy(int k, int l, int j, int i) { return OFF_YY + ((k * NB + l) * NY + j) * NY + i; }
   __host__ __device__ static constexpr int uy(int l, int j, int i) { return OFF_UY + (l * NY + j) * NU + i; }
   __host__ __device__ static constexpr int yu(int t, int b, int i) { return OFF_YU + (t * NU + b) * NY + i; }
@@ -111,6 +120,8 @@ struct DevModel {
   int64_t nfree_y, nfree_u;
   int32_t ntiles;
   int32_t nparam;
+  int64_t ncells_coef;     // cells of the coefficient arrays (= ncells, except in the create-time self-check on a sample)
+  int32_t notrait;         // 1: ignore the trait-selected shortcuts (self-check: generic per-point evaluation)
 };
 
 // ------------------------------------------------------------------ small device helpers
@@ -219,7 +230,7 @@ __device__ __forceinline__ PointCtx point_ctx(const DevModel& D, const Tables<E>
   pc.source = 0.0;
   if (need && valid) {
     pc.target = __ldg(D.coef + (cell * E::NQ + q));
-    pc.source = __ldg(D.coef + ((D.ncells + cell) * E::NQ + q));
+    pc.source = __ldg(D.coef + ((D.ncells_coef + cell) * E::NQ + q));
   }
   return pc;
 }
@@ -763,7 +774,7 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
     if (KTab<E>::ENABLED && Ks != nullptr && !RA) {
       bool uni = true;
       // integrands that declare FE_DERIVS_POINT_INDEPENDENT are evaluated at the first point only
-      constexpr int NQT = I::FE_DERIVS_POINT_INDEPENDENT ? 1 : E::NQ;
+      const int NQT = (I::FE_DERIVS_POINT_INDEPENDENT && !D.notrait) ? 1 : E::NQ;
 #pragma unroll 1
       for (int q = 0; q < NQT; ++q) {
         Jet1<E::M> s[E::M], R[E::NR];
@@ -1084,7 +1095,7 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
       bool zyy = !RA, zu = !RA, quni = true;
       Jet2<E::M> L, L0;
       double sc = 0.0;  // quadrature-weight-free scale (obj_weight or 1)
-      constexpr int NQT = RA ? 0 : ((KTab<E>::ENABLED && I::FE_DERIVS_POINT_INDEPENDENT) ? 1 : E::NQ);
+      const int NQT = RA ? 0 : ((KTab<E>::ENABLED && I::FE_DERIVS_POINT_INDEPENDENT && !D.notrait) ? 1 : E::NQ);
 #pragma unroll 1
       for (int q = 0; q < NQT; ++q) {
         L = jet_at(q, sc);
@@ -1592,17 +1603,37 @@ k_structure(const DevModel D, int kind, int64_t* __restrict__ rows, int64_t* __r
       }
 }
 
-// Sum of one value per thread over the CTA, added to *dst by ONE atomic (thread 0).  The kappa entries are
-// single addresses: one atomic per warp (~9500 same-address atomics per launch) serialised in L2 and cost
-// 30-40 us per kernel at 10^6 cells.  Must be called by all threads of the CTA.
-__device__ __forceinline__ void cta_sum_atomic(double v, double* dst, double* red /* [kWarpsPerCta] shared */) {
+// The kappa entries of the dof-indexed outputs and the kappa-kappa corners of the Hessian blocks are sums over ALL
+// cells of the slab.  Each CTA writes ONE partial per component (warp shuffles + a fixed-order sum over its warps) and a
+// one-CTA second pass adds the partials in block order: no atomics, so these entries are bitwise reproducible run to
+// run (the grid of a kernel is a function of the model only) and accurate like a pairwise sum.
+struct KappaDst {
+  int64_t pos[16];  // destination index of each component in the output array
+};
+static __global__ void k_add_partials(const double* __restrict__ partials, int nblocks, int ncomp, KappaDst dst, double* __restrict__ out) {
+  __shared__ double sh[256];
+  for (int c = 0; c < ncomp; ++c) {
+    double a = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += 256) a += partials[(int64_t)i * ncomp + c];
+    sh[threadIdx.x] = a;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) {
+      if (threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[dst.pos[c]] += sh[0];
+    __syncthreads();
+  }
+}
+// per-CTA sum of one value per thread -> partials[blockIdx.x * ncomp + comp]   (all threads of the CTA must call)
+__device__ __forceinline__ void cta_partial(double v, double* __restrict__ partials, int ncomp, int comp, double* red /* [kWarpsPerCta] shared */) {
   v = warp_sum(v);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
   if (threadIdx.x == 0) {
     double a = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += red[w];
-    atomicAdd(dst, a);
+    partials[(int64_t)blockIdx.x * ncomp + comp] = a;
   }
   __syncthreads();
 }
@@ -1611,7 +1642,17 @@ __device__ __forceinline__ void cta_sum_atomic(double v, double* dst, double* re
 // (lane = cell; scatter with red.global.add.f64 — north star: "segmented atomics")
 enum VecOp { OP_OBJ = 0, OP_GRAD = 1, OP_CONS = 2, OP_JPROD = 3, OP_JTPROD = 4, OP_HPROD = 5,
              OP_OBJGRAD = 6 /* objgrad!: objective and gradient from one sweep (one gather, one jet evaluation) */,
-             OP_OBJCONS = 7 /* objcons!: objective and residual from one sweep */ };
+             OP_OBJCONS = 7 /* objcons!: objective and residual from one sweep */,
+             OP_JAC_KAPPA = 8 /* dense kappa-block of jac_coord! */, OP_HESS_KAPPA = 9 /* kappa trapezoid of hess_coord! */,
+             OP_HESS_KAPPA_KK = 10 /* objective trapezoid of an `inde` energy: the p x p corner only */ };
+// number of per-CTA partial components (kappa entries) an op produces; they live at partials + gridDim.x * 1 (the first
+// gridDim.x doubles hold the objective partials of OBJ / OBJGRAD / OBJCONS)
+template <class E>
+__host__ __device__ constexpr int kappa_partials(int op) {
+  return E::NP == 0 ? 0
+       : (op == OP_GRAD || op == OP_OBJGRAD || op == OP_JTPROD || op == OP_HPROD) ? E::NP
+       : (op == OP_HESS_KAPPA || op == OP_HESS_KAPPA_KK) ? E::NP * (E::NP + 1) / 2 : 0;
+}
 
 // element vector d/dz_a += sum_k By_a[k] gs[k], d/du_b += Bu_b gs[SU]: accumulated over the quadrature points in
 // registers, scattered once per cell (one red.global.add.f64 per local dof, not per dof and point)
@@ -1845,16 +1886,8 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
     __syncthreads();
   }
   if (E::NP > 0 && (OP == OP_GRAD || OP == OP_OBJGRAD || OP == OP_JTPROD || OP == OP_HPROD)) {
-    if (E::M >= 6 && OP == OP_HPROD) {  // register-bound instance (Jet2<7>): keep the plain per-warp atomics
 #pragma unroll
-      for (int k = 0; k < E::NP; ++k) {
-        const double a = warp_sum(ksum[k]);
-        if (lane == 0) atomicAdd(out + k, a);
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < E::NP; ++k) cta_sum_atomic(ksum[k], out + k, red);
-    }
+    for (int k = 0; k < E::NP; ++k) cta_partial(ksum[k], partials + gridDim.x, E::NP, k, red);
   }
 }
 
@@ -1987,7 +2020,7 @@ __global__ void k_nofe(const __grid_constant__ Tables<E> tab, const double* __re
 template <class E>
 __global__ void __launch_bounds__(kThreads)
 k_hess_kappa_kk(const __grid_constant__ Tables<E> tab, const DevModel D, const double* __restrict__ x, double obj_weight,
-                double* __restrict__ vk) {
+                double* __restrict__ partials) {
   using I = typename E::Integrand;
   constexpr int NPS = E::NP > 0 ? E::NP : 1;
   using JK = Jet2<NPS>;
@@ -2024,17 +2057,19 @@ k_hess_kappa_kk(const __grid_constant__ Tables<E> tab, const DevModel D, const d
     }
   }
   __shared__ double red[kWarpsPerCta];
+  int comp = 0;
 #pragma unroll
   for (int j = 0; j < E::NP; ++j)
 #pragma unroll
-    for (int i = j; i < E::NP; ++i) cta_sum_atomic(kk[i][j], vk + trap_pos(i + 1, j + 1, E::NP), red);
+    for (int i = j; i < E::NP; ++i) { cta_partial(kk[i][j], partials + gridDim.x, E::NP * (E::NP + 1) / 2, comp, red); ++comp; }
 }
 
 // which: 0 = objective (scaled by obj_weight), 1 = constraints (lambda-weighted residual)
 template <class E>
 __global__ void __launch_bounds__(kThreads)
 k_hess_kappa(const __grid_constant__ Tables<E> tab, const DevModel D, const double* __restrict__ x,
-             const double* __restrict__ lambda, double obj_weight, int which, int64_t prows, double* __restrict__ vk) {
+             const double* __restrict__ lambda, double obj_weight, int which, int64_t prows, double* __restrict__ vk,
+             double* __restrict__ partials) {
   using I = typename E::Integrand;
   using J2 = Jet2<E::M>;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -2105,10 +2140,34 @@ k_hess_kappa(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
     }
   }
   __shared__ double red[kWarpsPerCta];
+  int comp = 0;
 #pragma unroll
   for (int j = 0; j < E::NP; ++j)
 #pragma unroll
-    for (int i = j; i < E::NP; ++i) cta_sum_atomic(kk[i][j], vk + trap_pos(i + 1, j + 1, prows), red);
+    for (int i = j; i < E::NP; ++i) { cta_partial(kk[i][j], partials + gridDim.x, E::NP * (E::NP + 1) / 2, comp, red); ++comp; }
+}
+
+// ------------------------------------------------------------------ create-time self-check helpers
+// deterministic pseudo-random fill in [lo, hi) (splitmix64 of the index) and max |a - b|, max |b| of two arrays
+static __global__ void k_fill_random(double* __restrict__ p, int64_t n, uint64_t seed, double lo, double hi) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t z = (uint64_t)i * 0x9E3779B97F4A7C15ull + seed;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    p[i] = lo + (hi - lo) * ((double)(z >> 11) * (1.0 / 9007199254740992.0));
+  }
+}
+static __global__ void k_max_diff(const double* __restrict__ a, const double* __restrict__ b, int64_t n, unsigned long long* __restrict__ res /* [2] */) {
+  double md = 0.0, mb = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double d = fabs(a[i] - b[i]);
+    md = (d > md || d != d) ? d : md;  // a NaN sticks
+    mb = fmax(mb, fabs(b[i]));
+  }
+  // non-negative doubles order like their bit patterns (NaN patterns sort above every finite value)
+  atomicMax(res + 0, (unsigned long long)__double_as_longlong(md));
+  atomicMax(res + 1, (unsigned long long)__double_as_longlong(mb));
 }
 
 }  // namespace pdenlp

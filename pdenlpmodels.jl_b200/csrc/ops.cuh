@@ -4,6 +4,7 @@
 #pragma once
 #include "../../include/pdenlp_cuda.h"
 #include "kernels.cuh"
+#include "kvector.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -33,7 +34,12 @@ inline int fail(int code, const std::string& msg) {
 struct Launch {
   cudaStream_t stream;
   int sms;
+  // true: ignore the integrand traits that select shortcuts (reference-tensor paths, structurally-zero blocks) and run
+  // the generic per-quadrature-point kernels — the create-time self-check compares both (pdenlp_create)
+  bool generic = false;
+  int64_t* launches = nullptr;  // counts the kernel launches issued through this Launch (pdenlp_launch_count)
 };
+inline void count_launch(const Launch& L, int n = 1) { if (L.launches) *L.launches += n; }
 
 // Kernel launch with the programmatic-stream-serialization attribute (see griddep_wait in kernels.cuh): the kernel may
 // be scheduled while its predecessor on the stream drains; it synchronises itself with griddepcontrol.wait.
@@ -62,9 +68,10 @@ struct Ops {
   virtual int structure(const Launch& L, const DevModel& D, int kind, int64_t* r, int64_t* c, int64_t shift) = 0;
   virtual int vec(const Launch& L, const DevModel& D, int op, const double* x, const double* lam, const double* v,
                   double ow, double* out, double* partials, int* nblocks) = 0;
-  virtual int jac_kappa(const Launch& L, const DevModel& D, const double* x, double* vk) = 0;
+  virtual int jac_kappa(const Launch& L, const DevModel& D, const double* x, double* vk, double* partials) = 0;
   virtual int hess_kappa(const Launch& L, const DevModel& D, const double* x, const double* lam, double ow, int which,
-                         int64_t prows, double* vk) = 0;
+                         int64_t prows, double* vk, double* partials) = 0;
+  virtual bool has_shortcuts() const = 0;  // some trait-selected fast path exists (worth a create-time self-check)
   virtual int run_h() const = 0;
   virtual bool needs_coef_deriv() const = 0;  // derivative callbacks read the coefficient fields
   virtual bool res_fe_hessian_zero() const = 0;  // constraint FE Hessian block is structurally zero
@@ -119,10 +126,15 @@ struct OpsImpl : Ops {
   bool res_fe_hessian_zero() const override { return E::Integrand::RES_FE_HESSIAN_ZERO; }
   bool no_fe_obj() const override { return E::Integrand::NO_FE_OBJ; }
   bool is_multi() const override { return E::MULTI; }
+  bool has_shortcuts() const override {
+    using I = typename E::Integrand;
+    return I::RES_FE_HESSIAN_ZERO || (KTab<E>::ENABLED && I::FE_DERIVS_POINT_INDEPENDENT);
+  }
   int nofe(const Launch& L, int mode, const double* x, double ow, const double* v, double* out) override {
     if constexpr (E::Integrand::NO_FE_OBJ) {
       k_nofe<E><<<1, 32, 0, L.stream>>>(tab, x, mode, ow, v, out);
       CU(cudaGetLastError());
+      count_launch(L);
     }
     return PDENLP_OK;
   }
@@ -147,6 +159,7 @@ struct OpsImpl : Ops {
     static const int wj = env_warps("PDENLP_WARPS_J", WJ);
     CU(launch_kernel(jac_kernel(), grid_for(D.ntiles, wj, L.sms * occ_j), wj * 32, SMEM_J, L.stream, pdl_chain() && !E::MULTI,
                      tab, D, x, vy, vu));
+    count_launch(L);
     return PDENLP_OK;
   }
   int hess(const Launch& L, const DevModel& D, const double* x, const double* lam, double ow, double* vo, double* vc) override {
@@ -154,11 +167,43 @@ struct OpsImpl : Ops {
     static const int wh = env_warps("PDENLP_WARPS_H", WH);
     CU(launch_kernel(hess_kernel(), grid_for(D.ntiles, wh, L.sms * occ_h), wh * 32, SMEM_H, L.stream, pdl_chain() && !E::MULTI,
                      tab, D, x, lam, ow, vo, vc));
+    count_launch(L);
     return PDENLP_OK;
   }
   int structure(const Launch& L, const DevModel& D, int kind, int64_t* r, int64_t* c, int64_t shift) override {
     k_structure<E><<<grid_for(D.ntiles, kWarpsPerCta, 1 << 30), kThreads, 0, L.stream>>>(D, kind, r, c, shift);
     CU(cudaGetLastError());
+    count_launch(L);
+    return PDENLP_OK;
+  }
+  // launches the (generic or reference-tensor) kernel of a dof-indexed callback, then the fixed-order second pass that
+  // adds the per-CTA partials of its kappa entries to out[0..p)
+  template <int OP>
+  int vec_op(const Launch& L, const DevModel& D, const double* x, const double* lam, const double* v, double ow,
+             double* out, double* partials, int g) {
+    if constexpr (kvec_enabled<E>() && kvec_op(OP)) {
+      if (!L.generic) {
+        k_vector_K<E, OP><<<g, kThreads, KTab<E>::TOTAL * 8, L.stream>>>(tab, D, x, lam, v, ow, 0, out, partials);
+        CU(cudaGetLastError());
+        count_launch(L);
+        return add_kappa_partials<OP>(L, partials, g, out);
+      }
+    }
+    k_vector<E, OP><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, v, ow, out, partials);
+    CU(cudaGetLastError());
+    count_launch(L);
+    return add_kappa_partials<OP>(L, partials, g, out);
+  }
+  template <int OP>
+  int add_kappa_partials(const Launch& L, double* partials, int g, double* out) {
+    constexpr int NPART = kappa_partials<E>(OP);
+    if constexpr (NPART > 0) {
+      KappaDst dst;
+      for (int k = 0; k < NPART; ++k) dst.pos[k] = k;
+      k_add_partials<<<1, 256, 0, L.stream>>>(partials + g, g, NPART, dst, out);
+      CU(cudaGetLastError());
+      count_launch(L);
+    }
     return PDENLP_OK;
   }
   int vec(const Launch& L, const DevModel& D, int op, const double* x, const double* lam, const double* v, double ow,
@@ -166,37 +211,65 @@ struct OpsImpl : Ops {
     const int g = grid_for(D.ntiles, kWarpsPerCta, L.sms * 8);
     *nblocks = g;
     switch (op) {
-      case OP_OBJ: k_vector<E, OP_OBJ><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, v, ow, out, partials); break;
-      case OP_GRAD: k_vector<E, OP_GRAD><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, v, ow, out, partials); break;
-      case OP_CONS: k_vector<E, OP_CONS><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, v, ow, out, partials); break;
-      case OP_JPROD: k_vector<E, OP_JPROD><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, v, ow, out, partials); break;
-      case OP_JTPROD: k_vector<E, OP_JTPROD><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, v, ow, out, partials); break;
-      case OP_HPROD: k_vector<E, OP_HPROD><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, v, ow, out, partials); break;
-      case OP_OBJGRAD: k_vector<E, OP_OBJGRAD><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, v, ow, out, partials); break;
-      case OP_OBJCONS: k_vector<E, OP_OBJCONS><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, v, ow, out, partials); break;
+      case OP_OBJ: return vec_op<OP_OBJ>(L, D, x, lam, v, ow, out, partials, g);
+      case OP_GRAD: return vec_op<OP_GRAD>(L, D, x, lam, v, ow, out, partials, g);
+      case OP_CONS: return vec_op<OP_CONS>(L, D, x, lam, v, ow, out, partials, g);
+      case OP_JPROD: return vec_op<OP_JPROD>(L, D, x, lam, v, ow, out, partials, g);
+      case OP_JTPROD: return vec_op<OP_JTPROD>(L, D, x, lam, v, ow, out, partials, g);
+      case OP_HPROD: return vec_op<OP_HPROD>(L, D, x, lam, v, ow, out, partials, g);
+      case OP_OBJGRAD: return vec_op<OP_OBJGRAD>(L, D, x, lam, v, ow, out, partials, g);
+      case OP_OBJCONS: return vec_op<OP_OBJCONS>(L, D, x, lam, v, ow, out, partials, g);
       default: return fail(PDENLP_EINVAL, "bad vector op");
     }
-    CU(cudaGetLastError());
-    return PDENLP_OK;
   }
-  int jac_kappa(const Launch& L, const DevModel& D, const double* x, double* vk) override {
-    if constexpr (E::NP > 0)
-    k_jac_kappa<E><<<grid_for(D.ntiles, kWarpsPerCta, L.sms * 8), kThreads, 0, L.stream>>>(tab, D, x, vk);
-    CU(cudaGetLastError());
+  int jac_kappa(const Launch& L, const DevModel& D, const double* x, double* vk, double* partials) override {
+    if constexpr (E::NP > 0) {
+      const int g = grid_for(D.ntiles, kWarpsPerCta, L.sms * 8);
+      if constexpr (kvec_enabled<E>()) {
+        if (!L.generic) {
+          k_vector_K<E, OP_JAC_KAPPA><<<g, kThreads, KTab<E>::TOTAL * 8, L.stream>>>(tab, D, x, nullptr, nullptr, 1.0, 0, vk, partials);
+          CU(cudaGetLastError());
+          count_launch(L);
+          return PDENLP_OK;
+        }
+      }
+      k_jac_kappa<E><<<g, kThreads, 0, L.stream>>>(tab, D, x, vk);
+      CU(cudaGetLastError());
+      count_launch(L);
+    }
     return PDENLP_OK;
   }
   int hess_kappa(const Launch& L, const DevModel& D, const double* x, const double* lam, double ow, int which,
-                 int64_t prows, double* vk) override {
+                 int64_t prows, double* vk, double* partials) override {
     if constexpr (E::NP > 0) {
-      if (which == 0 && prows == E::NP) {  // objective, kappa-kappa triangle only
-        k_hess_kappa_kk<E><<<grid_for(D.ntiles, kWarpsPerCta, L.sms * 8), kThreads, 0, L.stream>>>(tab, D, x, ow, vk);
-        CU(cudaGetLastError());
-        return PDENLP_OK;
+      const int g = grid_for(D.ntiles, kWarpsPerCta, L.sms * 8);
+      constexpr int NKK = E::NP * (E::NP + 1) / 2;
+      KappaDst dst;  // the kappa-kappa corner: column j outer, row i >= j inner
+      {
+        int c = 0;
+        for (int j = 0; j < E::NP; ++j) {
+          int64_t col0 = 0;
+          for (int jj = 0; jj < j; ++jj) col0 += prows - jj;
+          for (int i = j; i < E::NP; ++i) dst.pos[c++] = col0 + (i - j);
+        }
       }
+      bool done = false;
+      if (which == 0 && prows == E::NP) {  // objective of an `inde` energy: kappa-kappa triangle only
+        k_hess_kappa_kk<E><<<g, kThreads, 0, L.stream>>>(tab, D, x, ow, partials);
+        done = true;
+      }
+      if constexpr (kvec_enabled<E>()) {
+        if (!done && which == 1 && !L.generic) {
+          k_vector_K<E, OP_HESS_KAPPA><<<g, kThreads, KTab<E>::TOTAL * 8, L.stream>>>(tab, D, x, lam, nullptr, 1.0, prows, vk, partials);
+          done = true;
+        }
+      }
+      if (!done) k_hess_kappa<E><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, ow, which, prows, vk, partials);
+      CU(cudaGetLastError());
+      k_add_partials<<<1, 256, 0, L.stream>>>(partials + g, g, NKK, dst, vk);
+      CU(cudaGetLastError());
+      count_launch(L, 2);
     }
-    if constexpr (E::NP > 0)
-    k_hess_kappa<E><<<grid_for(D.ntiles, kWarpsPerCta, L.sms * 8), kThreads, 0, L.stream>>>(tab, D, x, lam, ow, which, prows, vk);
-    CU(cudaGetLastError());
     return PDENLP_OK;
   }
 };
@@ -231,6 +304,13 @@ Ops* make_ops(const pdenlp_desc& d) {
           }
       for (int j = 0; j < E::NU; ++j)
         for (int i = 0; i < E::NU; ++i) o->ktab_[KT::uu(j, i)] += w * T.Bu[q][i] * T.Bu[q][j];
+      for (int j = 0; j < E::NY; ++j) {
+        for (int i = 0; i < E::NY; ++i)
+          for (int d = 1; d < E::NB; ++d) o->ktab_[KT::lap(j, i)] += w * T.By[q][i][d] * T.By[q][j][d];
+        for (int k = 0; k < E::NB; ++k) o->ktab_[KT::y1(k, j)] += w * T.By[q][j][k];
+      }
+      for (int b = 0; b < E::NU; ++b) o->ktab_[KT::u1(b)] += w * T.Bu[q][b];
+      o->ktab_[KT::OFF_VOL] += w;
     }
   }
   return o;

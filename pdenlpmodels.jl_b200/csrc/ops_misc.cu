@@ -22,6 +22,9 @@ Ops* select_ops_part3(const pdenlp_desc& d) {
   CASE(PDENLP_DYNAMIC_SIR, 1, 2, 2, 1, 0, DynamicSir)
   CASE(PDENLP_TORE_BRACHISTOCHRONE, 1, 2, 0, 1, 0, ToreBrachistochrone)
   CASE(PDENLP_SIS, 1, 2, 0, 1, 0, Sis)                          // NoFETerm objective
+  // test-only integrand with deliberately wrong shortcut traits: pdenlp_create must fail its self-check
+  CASE(PDENLP_SELFTEST_WRONG_TRAIT, 2, 4, 4, 1, 0, WrongTraitPB<2>)
+  CASE(PDENLP_SELFTEST_WRONG_TRAIT, 2, 4, 4, 4, 0, WrongTraitPB<2>)
   return nullptr;
 }
 

@@ -60,6 +60,7 @@ struct pdenlp_model {
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
+  double selfcheck_err = 0.0;  // worst relative disagreement fast path vs generic path seen by the create-time self-check
 };
 
 namespace {
@@ -170,6 +171,104 @@ int zero_fill(pdenlp_model* m, double* p, int64_t n, bool overlap_previous = fal
     CU(cudaGetLastError());
   }
   m->launches += 1;
+  return PDENLP_OK;
+}
+
+// Create-time self-check of the trait-selected shortcuts (RES_FE_HESSIAN_ZERO: the constraint FE Hessian block is a
+// zero fill; FE_DERIVS_POINT_INDEPENDENT: the coordinate kernels evaluate one quadrature point and use the
+// pre-integrated reference tensors; both: the reference-tensor vector / kappa-block kernels of kvector.cuh).  The traits
+// are hand-set per integrand, so every model that uses one runs BOTH code paths once on a sample of its own cells with
+// pseudo-random x, lambda, v and refuses to be created if they differ: a wrong flag cannot silently change results.
+int self_check(pdenlp_model* m, double* worst_out) {
+  static const bool skip = getenv("PDENLP_NO_SELFCHECK") != nullptr;
+  if (worst_out) *worst_out = 0.0;
+  if (skip || !m->ops->has_shortcuts()) return PDENLP_OK;
+  const pdenlp_info& I = m->info;
+  const int64_t ns = std::min<int64_t>(m->dm.ncells, 2048);
+  DevModel ds = m->dm;
+  ds.ncells = ns;
+  ds.ntiles = (int32_t)((ns + 31) / 32);
+  // sizes of the sample's COO runs = segment offsets of the first tile after the sample
+  int64_t njy = 0, nju = 0, nh = 0;
+  CU(cudaMemcpy(&njy, m->dm.base_jy + ds.ntiles, 8, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(&nju, m->dm.base_ju + ds.ntiles, 8, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(&nh, m->dm.base_h + ds.ntiles, 8, cudaMemcpyDeviceToHost));
+  const int64_t nk = std::max<int64_t>(I.nnzj_k, I.nnzh_k_con);
+  const int64_t nout = std::max<int64_t>({njy + nju, 2 * nh, I.nvar, nk, (int64_t)2});
+  double *x = nullptr, *lam = nullptr, *v = nullptr, *a = nullptr, *b = nullptr;
+  unsigned long long* res = nullptr;
+  std::vector<void*> tmp;
+  auto cleanup = [&]() { for (void* p : tmp) cudaFree(p); };
+  auto alloc = [&](double** p, int64_t n) -> int {
+    CU(cudaMalloc((void**)p, (size_t)std::max<int64_t>(n, 2) * 8));
+    tmp.push_back(*p);
+    return PDENLP_OK;
+  };
+  int rc = PDENLP_OK;
+  if ((rc = alloc(&x, I.nvar)) || (rc = alloc(&lam, I.ncon)) || (rc = alloc(&v, I.nvar)) || (rc = alloc(&a, nout)) ||
+      (rc = alloc(&b, nout)) || (rc = alloc((double**)&res, 2))) { cleanup(); return rc; }
+  cudaStream_t st = m->stream;
+  k_fill_random<<<1024, 256, 0, st>>>(x, I.nvar, 1998, -1.0, 1.0);
+  if (m->d.nparam > 0) k_fill_random<<<1, 32, 0, st>>>(x, m->d.nparam, 7, 0.9, 1.1);
+  k_fill_random<<<1024, 256, 0, st>>>(lam, I.ncon, 1999, -1.0, 1.0);
+  k_fill_random<<<1024, 256, 0, st>>>(v, I.nvar, 2000, -1.0, 1.0);
+  double worst = 0.0;
+  std::string worst_op;
+  // run(generic, out) fills `out` (n entries compared) through one of the two paths
+  auto compare = [&](const char* what, int64_t n, auto&& run) -> int {
+    for (int pass = 0; pass < 2; ++pass) {
+      double* o = pass ? b : a;
+      CU(cudaMemsetAsync(o, 0, (size_t)n * 8, st));
+      Launch L{st, m->sms, pass == 1, nullptr};
+      DevModel d = ds;
+      d.notrait = pass;
+      if (int r = run(L, d, o)) return r;
+    }
+    CU(cudaMemsetAsync(res, 0, 16, st));
+    k_max_diff<<<256, 256, 0, st>>>(a, b, n, res);
+    unsigned long long h[2];
+    CU(cudaMemcpyAsync(h, res, 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    double md, mb;
+    memcpy(&md, &h[0], 8); memcpy(&mb, &h[1], 8);
+    const double err = md != md ? 1.0 : (mb > 0.0 ? md / mb : (md > 0.0 ? 1.0 : 0.0));
+    if (err > worst || worst_op.empty()) { worst = std::max(worst, err); worst_op = what; }
+    return PDENLP_OK;
+  };
+  Ops* ops = m->ops;
+  const bool coef = m->dm.coef != nullptr, need = ops->needs_coef_deriv();
+  if (!rc && (coef || !need) && I.ncon > 0)
+    rc = compare("jac_coord", njy + nju, [&](const Launch& L, const DevModel& d, double* o) { return ops->jac(L, d, x, o, o + njy); });
+  if (!rc && (coef || !need))
+    rc = compare("hess_coord", (m->nofe ? 1 : 2) * nh, [&](const Launch& L, const DevModel& d, double* o) {
+      // generic pass: both FE blocks are computed; shortcut pass: what pdenlp_hess_coord does (zero fill of a
+      // structurally zero constraint block — `o` is already zeroed)
+      double* vo = m->nofe ? nullptr : o;
+      double* vc = o + (m->nofe ? 0 : nh);
+      const bool cons_zero = ops->res_fe_hessian_zero() && !L.generic;
+      if (I.ncon == 0 || cons_zero) vc = nullptr;
+      if (!vo && !vc) return (int)PDENLP_OK;
+      return ops->hess(L, d, x, lam, 0.37, vo, vc);
+    });
+  if (!rc && coef && I.ncon > 0) {
+    int nb = 0;
+    rc = compare("cons", I.ncon, [&](const Launch& L, const DevModel& d, double* o) { return ops->vec(L, d, OP_CONS, x, nullptr, nullptr, 1.0, o, m->partials, &nb); });
+    if (!rc) rc = compare("jprod", I.ncon, [&](const Launch& L, const DevModel& d, double* o) { return ops->vec(L, d, OP_JPROD, x, nullptr, v, 1.0, o, m->partials, &nb); });
+    if (!rc) rc = compare("jtprod", I.nvar, [&](const Launch& L, const DevModel& d, double* o) { return ops->vec(L, d, OP_JTPROD, x, nullptr, lam, 1.0, o, m->partials, &nb); });
+    if (!rc) rc = compare("hprod", I.nvar, [&](const Launch& L, const DevModel& d, double* o) { return ops->vec(L, d, OP_HPROD, x, lam, v, 0.37, o, m->partials, &nb); });
+    if (!rc && I.nnzj_k > 0)
+      rc = compare("jac kappa-block", I.nnzj_k, [&](const Launch& L, const DevModel& d, double* o) { return ops->jac_kappa(L, d, x, o, m->partials); });
+    if (!rc && I.nnzh_k_con > 0)
+      rc = compare("hess kappa-block", I.nnzh_k_con, [&](const Launch& L, const DevModel& d, double* o) { return ops->hess_kappa(L, d, x, lam, 1.0, 1, I.nvar, o, m->partials); });
+  } else if (!rc && !m->nofe) {  // no coefficient fields: the objective part of hprod! is still checkable
+    int nb = 0;
+    if (!need) rc = compare("hprod(obj)", I.nvar, [&](const Launch& L, const DevModel& d, double* o) { return ops->vec(L, d, OP_HPROD, x, nullptr, v, 0.37, o, m->partials, &nb); });
+  }
+  cleanup();
+  if (rc) return rc;
+  if (worst_out) *worst_out = worst;
+  if (worst > 1e-12)
+    return fail(PDENLP_EINVAL, "self-check failed: a trait-selected fast path (" + worst_op + ") disagrees with the generic kernels, relative error " + std::to_string(worst));
   return PDENLP_OK;
 }
 
@@ -290,6 +389,8 @@ int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
     m->dm.coef = nullptr;
   }
   m->dm.ncells = nc;
+  m->dm.ncells_coef = nc;
+  m->dm.notrait = 0;
   m->dm.ldc = ldc;
   m->dm.nfree_y = desc->nfree_y;
   m->dm.nfree_u = desc->nfree_u;
@@ -349,13 +450,14 @@ int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
     I.nnzh_obj = I.nnzh_k_obj + I.nnzh_fe_obj;
     I.nnzh = I.nnzh_obj + I.nnzh_k_con + I.nnzh_fe;
   }
-  m->npartials = m->sms * 8;
+  m->npartials = m->sms * 8 * 17;  // per-CTA partials: 1 objective + up to 16 kappa components, grids of <= 8 CTAs per SM
   if (cudaMalloc((void**)&m->partials, (size_t)m->npartials * 8) != cudaSuccess || cudaMalloc((void**)&m->scalar, 16) != cudaSuccess)
     return bail(fail(PDENLP_ENOMEM, "cudaMalloc failed"));
   m->owned.push_back(m->partials);
   m->owned.push_back(m->scalar);
   if (cudaEventCreate(&m->ev0) != cudaSuccess || cudaEventCreate(&m->ev1) != cudaSuccess)
     return bail(fail(PDENLP_ECUDA, "cudaEventCreate failed"));
+  if ((rc = self_check(m, &m->selfcheck_err))) return bail(rc);
   // the host arrays of the description are not referenced after create
   m->d.cell_dofs_y = m->d.cell_dofs_u = nullptr;
   m->d.dir_y = m->d.dir_u = m->d.phi_y = m->d.grad_y = m->d.phi_u = m->d.wdet = m->d.coef = nullptr;
@@ -415,16 +517,15 @@ int pdenlp_obj(pdenlp_model* m, const double* x, double* f) {
   Scope sc(m);
   const double* dx;
   if (int rc = in_ptr(m, x, m->info.nvar, &m->sx, &dx)) return rc;
-  Launch L{m->stream, m->sms};
+  Launch L{m->stream, m->sms, false, &m->launches};
   if (m->nofe) {  // _obj_integral(::NoFETerm, kappa, x) = f(kappa)
     if (int rc = m->ops->nofe(L, NOFE_OBJ, dx, 1.0, nullptr, m->scalar)) return rc;
-    m->launches += 1;
   } else {
     int nb = 0;
     if (int rc = m->ops->vec(L, m->dm, OP_OBJ, dx, nullptr, nullptr, 1.0, nullptr, m->partials, &nb)) return rc;
     k_sum_partials<<<1, 256, 0, m->stream>>>(m->partials, nb, m->scalar);
     CU(cudaGetLastError());
-    m->launches += 2;
+    m->launches += 1;
   }
   CU(cudaMemcpyAsync(f, m->scalar, 8, cudaMemcpyDeviceToHost, m->stream));
   CU(cudaStreamSynchronize(m->stream));
@@ -443,17 +544,15 @@ static int vec_call(pdenlp_model* m, int op, const double* x, const double* lam,
   if (int rc = in_ptr(m, v, nv, &m->sv, &dv)) return rc;
   if (int rc = out_ptr(m, out, nout, &dout)) return rc;
   CU(cudaMemsetAsync(dout, 0, (size_t)nout * 8, m->stream));  // assemble_vector!/coo_prod! zero-fill first
-  Launch L{m->stream, m->sms};
+  Launch L{m->stream, m->sms, false, &m->launches};
   int nb = 0;
   // NoFETerm objective: the FE part of grad! is zero (additional_obj_terms.jl:82), hprod! keeps its constraint part
   const bool skip_fe = m->nofe && (op == OP_GRAD || (op == OP_HPROD && dl == nullptr));
   if (!skip_fe) {
     if (int rc = m->ops->vec(L, m->dm, op, dx, dl, dv, ow, dout, m->partials, &nb)) return rc;
-    m->launches += 1;
   }
   if (m->nofe && m->d.nparam > 0 && (op == OP_GRAD || op == OP_HPROD)) {
     if (int rc = m->ops->nofe(L, op == OP_GRAD ? NOFE_GRAD : NOFE_HPROD, dx, ow, dv, dout)) return rc;
-    m->launches += 1;
   }
   return out_finish(m, out, nout);
 }
@@ -473,12 +572,12 @@ static int obj_and_vector(pdenlp_model* m, int op, const double* x, double* f, d
   if (int rc = in_ptr(m, x, m->info.nvar, &m->sx, &dx)) return rc;
   if (int rc = out_ptr(m, out, n, &dout)) return rc;
   CU(cudaMemsetAsync(dout, 0, (size_t)n * 8, m->stream));
-  Launch L{m->stream, m->sms};
+  Launch L{m->stream, m->sms, false, &m->launches};
   int nb = 0;
   if (int rc = m->ops->vec(L, m->dm, op, dx, nullptr, nullptr, 1.0, dout, m->partials, &nb)) return rc;
   k_sum_partials<<<1, 256, 0, m->stream>>>(m->partials, nb, m->scalar);
   CU(cudaGetLastError());
-  m->launches += 2;
+  m->launches += 1;
   CU(cudaMemcpyAsync(f, m->scalar, 8, cudaMemcpyDeviceToHost, m->stream));
   if (m->d.memspace == PDENLP_MEM_HOST) return out_finish(m, out, n);
   CU(cudaStreamSynchronize(m->stream));
@@ -518,17 +617,15 @@ int pdenlp_jac_coord(pdenlp_model* m, const double* x, double* vals) {
   if (int rc = in_ptr(m, x, m->info.nvar, &m->sx, &dx)) return rc;
   if (int rc = out_ptr(m, vals, m->info.nnzj, &dv)) return rc;
   if (m->ops->needs_coef_deriv() && !m->dm.coef) return fail(PDENLP_EINVAL, "this integrand's derivatives need the coefficient fields (desc.coef)");
-  Launch L{m->stream, m->sms};
+  Launch L{m->stream, m->sms, false, &m->launches};
   if (m->info.nnzj_k > 0) {
     if (!m->dm.coef) return fail(PDENLP_EINVAL, "the kappa block needs the coefficient fields (desc.coef)");
     CU(cudaMemsetAsync(dv, 0, (size_t)m->info.nnzj_k * 8, m->stream));
-    if (int rc = m->ops->jac_kappa(L, m->dm, dx, dv)) return rc;
-    m->launches += 1;
+    if (int rc = m->ops->jac_kappa(L, m->dm, dx, dv, m->partials)) return rc;
   }
   double* vy = dv + m->info.nnzj_k;
   double* vu = vy + m->info.nnzj_y;
   if (int rc = m->ops->jac(L, m->dm, dx, vy, vu)) return rc;
-  m->launches += 1;
   return out_finish(m, vals, m->info.nnzj);
 }
 
@@ -541,7 +638,7 @@ int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda, do
   if (int rc = in_ptr(m, lambda, m->info.ncon, &m->slam, &dl)) return rc;
   if (int rc = out_ptr(m, vals, m->info.nnzh, &dv)) return rc;
   if (m->ops->needs_coef_deriv() && !m->dm.coef) return fail(PDENLP_EINVAL, "this integrand's derivatives need the coefficient fields (desc.coef)");
-  Launch L{m->stream, m->sms};
+  Launch L{m->stream, m->sms, false, &m->launches};
   const pdenlp_info& I = m->info;
   double* vko = dv;
   double* vfo = vko + I.nnzh_k_obj;
@@ -554,12 +651,10 @@ int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda, do
     if (m->nofe) {
       if (int rc = m->ops->nofe(L, NOFE_HESS, dx, obj_weight, nullptr, vko)) return rc;
     } else {
-      if (int rc = m->ops->hess_kappa(L, m->dm, dx, nullptr, obj_weight, 0, m->inde ? m->d.nparam : I.nvar, vko)) return rc;
+      if (int rc = m->ops->hess_kappa(L, m->dm, dx, nullptr, obj_weight, 0, m->inde ? m->d.nparam : I.nvar, vko, m->partials)) return rc;
     }
-    m->launches += 1;
     if (dl) {
-      if (int rc = m->ops->hess_kappa(L, m->dm, dx, dl, 1.0, 1, I.nvar, vkc)) return rc;
-      m->launches += 1;
+      if (int rc = m->ops->hess_kappa(L, m->dm, dx, dl, 1.0, 1, I.nvar, vkc, m->partials)) return rc;
     }
   }
   // The constraint FE block is a pure zero fill when no multipliers are given (GridapPDENLPModel.jl:295-297)
@@ -584,7 +679,6 @@ int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda, do
   }
   if (vo || vc) {
     if (int rc = m->ops->hess(L, m->dm, dx, dl, obj_weight, vo, vc)) return rc;
-    m->launches += 1;
   }
   if (cons_zero && !host_tail && pdl) {
     if (int rc = zero_fill(m, vfc, I.nnzh_fe, (vo || vc) && !m->ops->is_multi())) return rc;
@@ -604,20 +698,18 @@ int pdenlp_hess_coord_obj(pdenlp_model* m, const double* x, double obj_weight, d
   if (int rc = in_ptr(m, x, I.nvar, &m->sx, &dx)) return rc;
   if (int rc = out_ptr(m, vals, I.nnzh_obj, &dv)) return rc;
   if (m->ops->needs_coef_deriv() && !m->dm.coef) return fail(PDENLP_EINVAL, "this integrand's derivatives need the coefficient fields (desc.coef)");
-  Launch L{m->stream, m->sms};
+  Launch L{m->stream, m->sms, false, &m->launches};
   if (I.nnzh_k_obj > 0) {
     if (!m->dm.coef) return fail(PDENLP_EINVAL, "the kappa blocks need the coefficient fields (desc.coef)");
     CU(cudaMemsetAsync(dv, 0, (size_t)I.nnzh_k_obj * 8, m->stream));
     if (m->nofe) {
       if (int rc = m->ops->nofe(L, NOFE_HESS, dx, obj_weight, nullptr, dv)) return rc;
     } else {
-      if (int rc = m->ops->hess_kappa(L, m->dm, dx, nullptr, obj_weight, 0, m->inde ? m->d.nparam : I.nvar, dv)) return rc;
+      if (int rc = m->ops->hess_kappa(L, m->dm, dx, nullptr, obj_weight, 0, m->inde ? m->d.nparam : I.nvar, dv, m->partials)) return rc;
     }
-    m->launches += 1;
   }
   if (!m->nofe) {
     if (int rc = m->ops->hess(L, m->dm, dx, nullptr, obj_weight, dv + I.nnzh_k_obj, nullptr)) return rc;
-    m->launches += 1;
   }
   return out_finish(m, vals, I.nnzh_obj);
 }
@@ -633,7 +725,7 @@ static int structure_call(pdenlp_model* m, bool hess, int64_t* rows, int64_t* co
     CU(cudaMalloc((void**)&dr, std::max<int64_t>(nnz, 2) * 8));
     CU(cudaMalloc((void**)&dc, std::max<int64_t>(nnz, 2) * 8));
   }
-  Launch L{m->stream, m->sms};
+  Launch L{m->stream, m->sms, false, &m->launches};
   const int64_t p = m->d.nparam, n = I.nvar;
   int rc = PDENLP_OK;
   // dense kappa blocks are tiny index patterns: build on the host and copy
@@ -655,7 +747,6 @@ static int structure_call(pdenlp_model* m, bool hess, int64_t* rows, int64_t* co
     if (!rc) rc = put(0, r, c);
     if (!rc) rc = m->ops->structure(L, m->dm, 0, dr + I.nnzj_k, dc + I.nnzj_k, p);
     if (!rc && m->d.nu > 0) rc = m->ops->structure(L, m->dm, 1, dr + I.nnzj_k + I.nnzj_y, dc + I.nnzj_k + I.nnzj_y, p);
-    m->launches += 1 + (m->d.nu > 0);
   } else {
     std::vector<int64_t> r, c;
     trapezoid(m->inde ? p : n, r, c);
@@ -665,7 +756,6 @@ static int structure_call(pdenlp_model* m, bool hess, int64_t* rows, int64_t* co
     if (!rc) rc = put(I.nnzh_obj, r, c);
     if (!rc && !m->nofe) rc = m->ops->structure(L, m->dm, 2, dr + I.nnzh_k_obj, dc + I.nnzh_k_obj, p);
     if (!rc) rc = m->ops->structure(L, m->dm, 2, dr + I.nnzh_obj + I.nnzh_k_con, dc + I.nnzh_obj + I.nnzh_k_con, p);
-    m->launches += m->nofe ? 1 : 2;
   }
   if (host) {
     if (!rc) {
@@ -682,6 +772,11 @@ static int structure_call(pdenlp_model* m, bool hess, int64_t* rows, int64_t* co
 int pdenlp_jac_structure(pdenlp_model* m, int64_t* rows, int64_t* cols) { return structure_call(m, false, rows, cols); }
 int pdenlp_hess_structure(pdenlp_model* m, int64_t* rows, int64_t* cols) { return structure_call(m, true, rows, cols); }
 
+int pdenlp_selfcheck_error(const pdenlp_model* m, double* max_rel_err) {
+  if (!m || !max_rel_err) return fail(PDENLP_EINVAL, "null argument");
+  *max_rel_err = m->selfcheck_err;
+  return PDENLP_OK;
+}
 int pdenlp_launch_count(const pdenlp_model* m, int64_t* launches) {
   if (!m || !launches) return fail(PDENLP_EINVAL, "null argument");
   *launches = m->launches;

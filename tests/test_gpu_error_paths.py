@@ -76,3 +76,34 @@ def test_callbacks_that_need_coefficients_say_so(fm, cuda_lib):
     torch.cuda.synchronize()
     assert torch.isfinite(v).all()
     h.close()
+
+
+@pytest.mark.parametrize("degree", [1, 2])
+def test_wrong_shortcut_trait_is_refused_by_the_create_time_self_check(pkg, cuda_lib, degree):
+    """The shortcut traits (RES_FE_HESSIAN_ZERO: the constraint FE Hessian block is a zero fill;
+    FE_DERIVS_POINT_INDEPENDENT: one quadrature point + pre-integrated reference tensors) are hand-set per integrand.
+    pdenlp_create runs the shortcut AND the generic kernels on a sample of the model's cells and must refuse a
+    model whose integrand declares them wrongly: the test-only integrand PDENLP_SELFTEST_WRONG_TRAIT is
+    Poisson-Boltzmann (sinh term: neither trait holds) with both traits set."""
+    from pdenlp_b200 import capi, flatten
+    spec = pkg.poissonboltzman2d(12, "H1", degree=degree)
+    good = flatten.flatten(spec)
+    h = capi.Handle(good)          # the honest integrand passes (no shortcut applies: nothing to compare)
+    assert h.selfcheck_error() == 0.0
+    h.close()
+    import copy as _copy
+    bad = _copy.copy(good)
+    bad.spec = _copy.copy(spec); bad.spec.integrand = 1000
+    with pytest.raises(capi.PdenlpError) as ei:
+        capi.Handle(bad)
+    assert ei.value.code == capi.EINVAL and "self-check failed" in str(ei.value), str(ei.value)
+
+
+def test_self_check_passes_and_reports_for_models_with_shortcuts(pkg, cuda_lib):
+    """Models whose integrands really have the traits pass, with a disagreement at round-off level."""
+    from pdenlp_b200 import capi, flatten
+    for spec in (pkg.controlelasticmembrane(10), pkg.controlelasticmembrane(9, degree=2), pkg.poissonmixed(6, 3, True),
+                 pkg.poissonmixed(7), pkg.burger1d(50, degree=2), pkg.poissonparam(8)):
+        h = capi.Handle(flatten.flatten(spec))
+        assert h.selfcheck_error() <= 1e-13, (spec.name, h.selfcheck_error())
+        h.close()
