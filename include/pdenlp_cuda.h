@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define PDENLP_ABI_VERSION 2
+#define PDENLP_ABI_VERSION 3
 
 /* status codes */
 #define PDENLP_OK 0
@@ -147,12 +147,16 @@ typedef struct pdenlp_desc {
   const double* dir_y;        /* [ndir_y] Dirichlet values of the TRIAL space Ypde */
   const double* dir_u;        /* [ndir_u] */
 
-  /* reference-FE tables at the quadrature points, physical gradients for the
-     uniform-Cartesian cell map (grad = diag(1/h) * reference gradient) */
+  /* reference-FE tables at the quadrature points.
+     Uniform geometry (cell_jinvT == NULL: every cell is the same affine image of the reference cell, e.g. a
+     CartesianDiscreteModel without `map`): grad_y holds the PHYSICAL gradients (J^-T * reference gradient, the
+     same for every cell) and wdet = quadrature weight * det(J).
+     Per-cell geometry (cell_jinvT != NULL, any Gridap triangulation): grad_y holds the REFERENCE gradients and
+     wdet the reference quadrature weights; the library applies each cell's J^-T and det(J). */
   const double* phi_y;   /* [nq][ny]      */
   const double* grad_y;  /* [nq][ny][dim] */
   const double* phi_u;   /* [nq][nu]      */
-  const double* wdet;    /* [nq] quadrature weight * det(J) */
+  const double* wdet;    /* [nq] */
 
   int32_t ncoef;         /* number of coefficient fields (<= 2) */
   int32_t nfields_u;     /* fields of a MultiFieldFESpace Ycon; 0 or 1 = single field */
@@ -168,6 +172,16 @@ typedef struct pdenlp_desc {
      (ConsecutiveMultiFieldStyle, src/additional_constructors.jl:236-242). */
   const int64_t* field_nfree;
   const int64_t* field_ndir;
+
+  /* ---- per-cell geometry (ABI v3): "weights and Jacobians" of the cell maps, evaluated by Gridap at the
+     quadrature points (get_cell_map(trian), src/additional_constructors.jl:130-175 accepts any triangulation).
+     geom_nq = 1: affine cells, one Jacobian per cell;  geom_nq = nq: one per cell and quadrature point.
+     cell_jinvT[c][g][d][e] = (J^-1)[e][d], so that  grad_x phi = cell_jinvT * grad_xi phi;  cell_detj[c][g] = |det J|.
+     NULL (both) selects the uniform fast path above. */
+  const double* cell_jinvT; /* [ncells][geom_nq][dim][dim] */
+  const double* cell_detj;  /* [ncells][geom_nq]           */
+  int32_t geom_nq;          /* 0 (no per-cell geometry), 1 or nq */
+  int32_t reserved0;
 } pdenlp_desc;
 
 typedef struct pdenlp_model pdenlp_model; /* opaque */

@@ -34,6 +34,7 @@ class _Problem(C.Structure):
         ("params", C.c_double * 8),
         ("nfy", C.c_int32), ("nfu", C.c_int32), ("field_nfree", C.c_int64 * 8), ("field_ndir", C.c_int64 * 8),
         ("compat_shifted_x", C.c_int32), ("reserved", C.c_int32),
+        ("vertex_coords", C.c_void_p),
     ]
 
 
@@ -135,6 +136,10 @@ class Oracle:
         self._finish_init(P, spec)
 
     def _finish_init(self, P, spec):
+        if getattr(spec.model, "is_mapped", False):  # CartesianDiscreteModel(...; map = f): mapped vertex coordinates
+            vc = np.ascontiguousarray(spec.model.vertex_coords(), dtype=np.float64)
+            self._keep.append(vc)
+            P.vertex_coords = _p(vc)
         self.P = P
         self.nvar = spec.nparam + P.nfree_y + P.nfree_u
         self.ncon = P.nfree_y

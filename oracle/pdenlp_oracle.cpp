@@ -158,6 +158,11 @@ typedef struct oracle_problem {
   // x[1:nfree_y] and the u dofs from x[nfree_y+1:...] although kappa occupies x[1:nparam]
   int32_t compat_shifted_x;
   int32_t reserved;
+  // Mapped mesh — Gridap's CartesianDiscreteModel(domain, partition; map = f): the coordinates of ALL mesh vertices
+  // (x-fastest vertex numbering, [nverts][dim]); NULL = the plain Cartesian mesh.  Every cell is then the Q1
+  // (multi-linear) image of the reference cell spanned by its mapped vertices: x(xi) = sum_v N_v(xi) x_v, with
+  // Jacobian J(xi) = sum_v x_v (x) grad N_v(xi); physical gradients are J^-T grad_xi and the measure w_q |det J(xi_q)|.
+  const double* vertex_coords;
 } oracle_problem;
 }
 
@@ -370,18 +375,93 @@ static S res_density(const oracle_problem& P, const Pt<S>& p, double v, const do
 
 // ------------------------------------------------------------------ cell evaluation
 struct CellGeom {
-  double x0[3];   // lower corner
+  bool mapped;
+  double x0[3];   // lower corner          (plain Cartesian cell)
   double h[3];
   double detJ;
+  // mapped cell: per quadrature point
+  double xq[27][3], detJq[27], JinvT[27][3][3];
 };
-static CellGeom cell_geom(const oracle_problem& P, int64_t c_local) {
-  CellGeom G; int64_t c = P.cell0 + c_local; G.detJ = 1;
+static void invert_transpose(int dim, const double J[3][3], double T[3][3], double* det) {
+  if (dim == 1) { *det = J[0][0]; T[0][0] = 1.0 / J[0][0]; return; }
+  if (dim == 2) {
+    const double d = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    *det = d;
+    // J^-1 = 1/d [[J11, -J01], [-J10, J00]];  T = (J^-1)^T
+    T[0][0] = J[1][1] / d; T[0][1] = -J[1][0] / d; T[1][0] = -J[0][1] / d; T[1][1] = J[0][0] / d;
+    return;
+  }
+  double c[3][3];  // cofactors
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      c[i][j] = J[i1][j1] * J[i2][j2] - J[i1][j2] * J[i2][j1];
+    }
+  const double d = J[0][0] * c[0][0] + J[0][1] * c[0][1] + J[0][2] * c[0][2];
+  *det = d;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) T[i][j] = c[i][j] / d;  // (J^-1)^T = cofactor matrix / det
+}
+static CellGeom cell_geom(const oracle_problem& P, const RefTables& T, int64_t c_local);
+// quadrature weight * |det J| at point q
+static inline double geom_w(const CellGeom& G, const double* w, int q) { return w[q] * (G.mapped ? G.detJq[q] : G.detJ); }
+// physical gradient of a shape function from its reference gradient
+static inline void geom_grad(const oracle_problem& P, const CellGeom& G, int q, const double* ref, double* phys) {
+  for (int d = 0; d < P.dim; ++d) {
+    if (!G.mapped) { phys[d] = ref[d] / G.h[d]; continue; }
+    double a = 0.0;
+    for (int e = 0; e < P.dim; ++e) a += G.JinvT[q][d][e] * ref[e];
+    phys[d] = a;
+  }
+}
+static inline void geom_point(const oracle_problem& P, const CellGeom& G, const double* xi, int q, double* xq) {
+  for (int d = 0; d < 3; ++d) xq[d] = 0.0;
+  for (int d = 0; d < P.dim; ++d) xq[d] = G.mapped ? G.xq[q][d] : G.x0[d] + G.h[d] * xi[q * P.dim + d];
+}
+
+static CellGeom cell_geom(const oracle_problem& P, const RefTables& T, int64_t c_local) {
+  CellGeom G; int64_t c = P.cell0 + c_local; G.detJ = 1; G.mapped = P.vertex_coords != nullptr;
+  int64_t idx[3] = {0, 0, 0};
   for (int d = 0; d < 3; ++d) { G.x0[d] = 0; G.h[d] = 1; }
   for (int d = 0; d < P.dim; ++d) {
     int64_t i = c % P.n[d]; c /= P.n[d];
+    idx[d] = i;
     G.h[d] = (P.hi[d] - P.lo[d]) / P.n[d];
     G.x0[d] = P.lo[d] + G.h[d] * (double)i;
     G.detJ *= G.h[d];
+  }
+  if (!G.mapped) return G;
+  // vertices of the cell (n-cube order, x fastest) in the x-fastest vertex numbering of the mesh
+  const int nv = 1 << P.dim;
+  int64_t stride[3] = {1, 0, 0};
+  for (int d = 1; d < P.dim; ++d) stride[d] = stride[d - 1] * (P.n[d - 1] + 1);
+  double xv[8][3];
+  for (int v = 0; v < nv; ++v) {
+    int64_t id = 0;
+    for (int d = 0; d < P.dim; ++d) id += (idx[d] + ((v >> d) & 1)) * stride[d];
+    for (int d = 0; d < P.dim; ++d) xv[v][d] = P.vertex_coords[id * P.dim + d];
+  }
+  for (int q = 0; q < T.nq; ++q) {
+    double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int d = 0; d < 3; ++d) G.xq[q][d] = 0.0;
+    for (int v = 0; v < nv; ++v) {
+      // Q1 shape function of vertex v and its reference gradient at xi_q
+      double N = 1.0, dN[3] = {1.0, 1.0, 1.0};
+      for (int d = 0; d < P.dim; ++d) {
+        const double xi = T.xi[q * P.dim + d];
+        const bool hi = (v >> d) & 1;
+        const double val = hi ? xi : 1.0 - xi, der = hi ? 1.0 : -1.0;
+        N *= val;
+        for (int e = 0; e < P.dim; ++e) dN[e] *= (e == d) ? der : val;
+      }
+      for (int d = 0; d < P.dim; ++d) {
+        G.xq[q][d] += N * xv[v][d];
+        for (int e = 0; e < P.dim; ++e) J[d][e] += xv[v][d] * dN[e];
+      }
+    }
+    double det;
+    invert_transpose(P.dim, J, G.JinvT[q], &det);
+    G.detJq[q] = std::fabs(det);
   }
   return G;
 }
@@ -406,11 +486,11 @@ static Pt<S> point_data(const oracle_problem& P, const RefTables& T, const CellG
   for (int k = 0; k < NP; ++k) p.k[k] = zz[k];
   for (int a = 0; a < NY; ++a) {
     p.y = p.y + T.phiy[q * NY + a] * zz[NP + a];
-    for (int d = 0; d < P.dim; ++d) p.gy[d] = p.gy[d] + (T.dphiy[(q * NY + a) * P.dim + d] / G.h[d]) * zz[NP + a];
+    double gph[3]; geom_grad(P, G, q, &T.dphiy[(q * NY + a) * P.dim], gph);
+    for (int d = 0; d < P.dim; ++d) p.gy[d] = p.gy[d] + gph[d] * zz[NP + a];
   }
   for (int b = 0; b < NU; ++b) p.u = p.u + T.phiu[q * NU + b] * zz[NP + NY + b];
-  double xq[3] = {0, 0, 0};
-  for (int d = 0; d < P.dim; ++d) xq[d] = G.x0[d] + G.h[d] * T.xi[q * P.dim + d];
+  double xq[3]; geom_point(P, G, T.xi.data(), q, xq);
   p.yd = coef_target(P, xq);
   p.h = coef_source(P, xq);
   return p;
@@ -422,7 +502,7 @@ static S cell_obj(const oracle_problem& P, const RefTables& T, const CellGeom& G
   S acc = cst(0.0, zz[0]);
   for (int q = 0; q < T.nq; ++q) {
     Pt<S> p = point_data<S, NP, NY, NU>(P, T, G, q, zz);
-    acc = acc + (T.w[q] * G.detJ) * f_density(P, p);
+    acc = acc + geom_w(G, T.w.data(), q) * f_density(P, p);
   }
   return acc;
 }
@@ -435,8 +515,8 @@ static void cell_res(const oracle_problem& P, const RefTables& T, const CellGeom
     Pt<S> p = point_data<S, NP, NY, NU>(P, T, G, q, zz);
     for (int i = 0; i < NY; ++i) {
       double gv[3];
-      for (int d = 0; d < P.dim; ++d) gv[d] = T.dphiy[(q * NY + i) * P.dim + d] / G.h[d];
-      out[i] = out[i] + (T.w[q] * G.detJ) * res_density(P, p, T.phiy[q * NY + i], gv, NU > 0);
+      geom_grad(P, G, q, &T.dphiy[(q * NY + i) * P.dim], gv);
+      out[i] = out[i] + geom_w(G, T.w.data(), q) * res_density(P, p, T.phiy[q * NY + i], gv, NU > 0);
     }
   }
 }
@@ -468,7 +548,7 @@ struct Driver {
     CellSums S(1, P.ncells);  // sum(::DomainContribution): pairwise over the cells (see pairwise_sum)
     for (int64_t c = 0; c < P.ncells; ++c) {
       double z[N]; gather_cell<NP, NY, NU>(P, x, c, z);
-      CellGeom G = cell_geom(P, c);
+      CellGeom G = cell_geom(P, T, c);
       S.at(0, c) = cell_obj<double, NP, NY, NU>(P, T, G, z);
     }
     return S.sum(0);
@@ -490,7 +570,7 @@ struct Driver {
     for (int64_t c = 0; c < P.ncells; ++c) {
       double z[N]; gather_cell<NP, NY, NU>(P, x, c, z);
       D1 zz[N]; seed1(z, zz);
-      CellGeom G = cell_geom(P, c);
+      CellGeom G = cell_geom(P, T, c);
       D1 F = cell_obj<D1, NP, NY, NU>(P, T, G, zz);
       for (int k = 0; k < NP; ++k) S.at(k, c) = F.d[k];
       for (int a = 0; a < NY; ++a) { int gid = P.cell_dofs_y[c * NY + a]; if (gid > 0) g[NP + gid - 1] += F.d[NP + a]; }
@@ -504,7 +584,7 @@ struct Driver {
     for (int64_t i = 0; i < P.nfree_y; ++i) cvec[i] = 0.0;
     for (int64_t c = 0; c < P.ncells; ++c) {
       double z[N]; gather_cell<NP, NY, NU>(P, x, c, z);
-      CellGeom G = cell_geom(P, c);
+      CellGeom G = cell_geom(P, T, c);
       double r[NY]; cell_res<double, NP, NY, NU>(P, T, G, z, r);
       for (int i = 0; i < NY; ++i) { int gid = P.cell_dofs_y[c * NY + i]; if (gid > 0) cvec[gid - 1] += r[i]; }
     }
@@ -587,7 +667,7 @@ struct Driver {
     for (int64_t c = 0; c < P.ncells; ++c) {
       double z[N]; gather_cell<NP, NY, NU>(P, x, c, z);
       D1 zz[N]; seed1(z, zz);
-      CellGeom G = cell_geom(P, c);
+      CellGeom G = cell_geom(P, T, c);
       D1 r[NY]; cell_res<D1, NP, NY, NU>(P, T, G, zz, r);
       int64_t n = by[c];
       for (int j = 0; j < NY; ++j) if (P.cell_dofs_y[c * NY + j] > 0)
@@ -655,7 +735,7 @@ struct Driver {
     for (int64_t c = 0; c < P.ncells; ++c) {
       double z[N]; gather_cell<NP, NY, NU>(P, x, c, z);
       D2 zz[N]; seed2(z, zz);
-      CellGeom G = cell_geom(P, c);
+      CellGeom G = cell_geom(P, T, c);
       int64_t gid[NY + NU + 1]; cell_gids(P, c, gid);
       // objective part
       int64_t n = bh[c];
@@ -800,18 +880,18 @@ struct MFDriver {
     for (int f = 0; f < NFY; ++f)
       for (int a = 0; a < NLY; ++a) {
         p.y[f] = p.y[f] + T.phiy[q * NLY + a] * zz[f * NLY + a];
-        for (int d = 0; d < P.dim; ++d) p.gy[f][d] = p.gy[f][d] + (T.dphiy[(q * NLY + a) * P.dim + d] / G.h[d]) * zz[f * NLY + a];
+        { double gph[3]; geom_grad(P, G, q, &T.dphiy[(q * NLY + a) * P.dim], gph);
+          for (int d = 0; d < P.dim; ++d) p.gy[f][d] = p.gy[f][d] + gph[d] * zz[f * NLY + a]; }
       }
     for (int g = 0; g < NFU; ++g)
       for (int b = 0; b < NLU; ++b) p.u[g] = p.u[g] + T.phiu[q * NLU + b] * zz[NYT + g * NLU + b];
-    double xq[3] = {0, 0, 0};
-    for (int d = 0; d < P.dim; ++d) xq[d] = G.x0[d] + G.h[d] * T.xi[q * P.dim + d];
+    double xq[3]; geom_point(P, G, T.xi.data(), q, xq);
     p.yd = coef_target(P, xq); p.h = coef_source(P, xq);
     return p;
   }
   template <class S> static S cell_obj(const oracle_problem& P, const RefTables& T, const CellGeom& G, const S* zz) {
     S acc = cst(0.0, zz[0]);
-    for (int q = 0; q < T.nq; ++q) acc = acc + (T.w[q] * G.detJ) * f_density_mf(P, point<S>(P, T, G, q, zz));
+    for (int q = 0; q < T.nq; ++q) acc = acc + geom_w(G, T.w.data(), q) * f_density_mf(P, point<S>(P, T, G, q, zz));
     return acc;
   }
   // residual vector indexed like the state part of z: (test field ft, local i)
@@ -820,7 +900,7 @@ struct MFDriver {
     for (int q = 0; q < T.nq; ++q) {
       PtMF<S> p = point<S>(P, T, G, q, zz);
       for (int ft = 0; ft < NFY; ++ft)
-        for (int i = 0; i < NLY; ++i) out[ft * NLY + i] = out[ft * NLY + i] + (T.w[q] * G.detJ) * res_density_mf(P, p, ft, T.phiy[q * NLY + i]);
+        for (int i = 0; i < NLY; ++i) out[ft * NLY + i] = out[ft * NLY + i] + geom_w(G, T.w.data(), q) * res_density_mf(P, p, ft, T.phiy[q * NLY + i]);
     }
   }
   static void seed1(const double* z, D1* zz) { for (int i = 0; i < N; ++i) { zz[i].v = z[i]; for (int j = 0; j < N; ++j) zz[i].d[j] = i == j; } }
@@ -850,7 +930,7 @@ struct MFDriver {
 
   static double obj(const oracle_problem& P, const double* x) {
     RefTables T = make_tables(P); CellSums S(1, P.ncells);  // pairwise over the cells (see pairwise_sum)
-    for (int64_t c = 0; c < P.ncells; ++c) { double z[N]; gather(P, x, c, z); S.at(0, c) = cell_obj<double>(P, T, cell_geom(P, c), z); }
+    for (int64_t c = 0; c < P.ncells; ++c) { double z[N]; gather(P, x, c, z); S.at(0, c) = cell_obj<double>(P, T, cell_geom(P, T, c), z); }
     return S.sum(0);
   }
   static void grad(const oracle_problem& P, const double* x, double* g) {
@@ -859,7 +939,7 @@ struct MFDriver {
     for (int64_t i = 0; i < nvar; ++i) g[i] = 0.0;
     for (int64_t c = 0; c < P.ncells; ++c) {
       double z[N]; gather(P, x, c, z); D1 zz[N]; seed1(z, zz);
-      D1 F = cell_obj<D1>(P, T, cell_geom(P, c), zz);
+      D1 F = cell_obj<D1>(P, T, cell_geom(P, T, c), zz);
       int64_t gid[N + 1]; gids(P, c, gid);
       for (int a = 0; a < N; ++a) if (gid[a] > 0) g[gid[a] - 1] += F.d[a];
     }
@@ -869,7 +949,7 @@ struct MFDriver {
     for (int64_t i = 0; i < P.nfree_y; ++i) cv[i] = 0.0;
     for (int64_t c = 0; c < P.ncells; ++c) {
       double z[N]; gather(P, x, c, z); double r[NYT > 0 ? NYT : 1];
-      cell_res<double>(P, T, cell_geom(P, c), z, r);
+      cell_res<double>(P, T, cell_geom(P, T, c), z, r);
       int64_t gid[N + 1]; gids(P, c, gid);
       for (int i = 0; i < NYT; ++i) if (gid[i] > 0) cv[gid[i] - 1] += r[i];
     }
@@ -893,7 +973,7 @@ struct MFDriver {
     int64_t ny = 0, nu = 0;
     for (int64_t c = 0; c < P.ncells; ++c) {
       double z[N]; gather(P, x, c, z); D1 zz[N]; seed1(z, zz);
-      D1 r[NYT > 0 ? NYT : 1]; cell_res<D1>(P, T, cell_geom(P, c), zz, r);
+      D1 r[NYT > 0 ? NYT : 1]; cell_res<D1>(P, T, cell_geom(P, T, c), zz, r);
       visit(P, c, 0, NFY, 0, NFY, false, [&](int li, int lj, int64_t, int64_t) { vy[ny++] = r[li].d[lj]; });
       visit(P, c, 0, NFY, NFY, NF, false, [&](int li, int lj, int64_t, int64_t) { vu[nu++] = r[li].d[lj]; });
     }
@@ -912,7 +992,7 @@ struct MFDriver {
     int64_t no = 0, nc = 0;
     for (int64_t c = 0; c < P.ncells; ++c) {
       double z[N]; gather(P, x, c, z); D2 zz[N]; seed2(z, zz);
-      CellGeom G = cell_geom(P, c);
+      CellGeom G = cell_geom(P, T, c);
       if (!nofe) {
         D2 F = cell_obj<D2>(P, T, G, zz);
         visit(P, c, 0, NF, 0, NF, true, [&](int li, int lj, int64_t, int64_t) { vo[no++] = F.d[li].d[lj]; });

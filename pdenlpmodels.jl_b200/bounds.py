@@ -29,6 +29,8 @@ def _fields(space):
 
 def cell_midpoints(model) -> np.ndarray:
     """midpoint(xs) = sum(xs)/length(xs) of the cell vertices (bounds_function.jl:21-24)."""
+    if getattr(model, "is_mapped", False):
+        return model.vertex_coords()[model.cell_vertices()].mean(axis=1)
     return model.lo + (model.cell_multi_index() + 0.5) * model.h
 
 

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # PDENLP_CUDA_LIB selects an alternative build of the same library (A/B kernel experiments)
 LIB_PATH = os.environ.get("PDENLP_CUDA_LIB") or os.path.join(HERE, "csrc", "libpdenlp_cuda.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = 0, -1, -2, -3, -4
 MEM_DEVICE, MEM_HOST = 0, 1
 
@@ -45,6 +45,7 @@ class Desc(C.Structure):
         ("ncoef", C.c_int32), ("nfields_u", C.c_int32), ("coef", C.c_void_p),
         ("params", C.c_double * 8),
         ("field_nfree", C.c_void_p), ("field_ndir", C.c_void_p),
+        ("cell_jinvT", C.c_void_p), ("cell_detj", C.c_void_p), ("geom_nq", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -163,6 +164,11 @@ class Handle:
         d.nfields_y, d.nfields_u = fm.nfy, fm.nfu
         keep += [np.ascontiguousarray(fm.field_nfree, np.int64), np.ascontiguousarray(fm.field_ndir, np.int64)]
         d.field_nfree, d.field_ndir = _np_ptr(keep[-2]), _np_ptr(keep[-1])
+        if getattr(fm, "cell_jinvT", None) is not None:  # per-cell geometry (ABI v3)
+            keep += [np.ascontiguousarray(fm.cell_jinvT, np.float64), np.ascontiguousarray(fm.cell_detj, np.float64)]
+            d.cell_jinvT, d.cell_detj, d.geom_nq = _np_ptr(keep[-2]), _np_ptr(keep[-1]), int(fm.geom_nq)
+        else:
+            d.cell_jinvT, d.cell_detj, d.geom_nq = None, None, 0
         h = C.c_void_p()
         check(lib.pdenlp_create(C.byref(d), C.byref(h)))
         del keep

@@ -45,13 +45,17 @@ __all__ = [
 # --------------------------------------------------------------------------
 @dataclass
 class CartesianDiscreteModel:
-    """Mirror of Gridap's ``CartesianDiscreteModel(domain, partition)``.
+    """Mirror of Gridap's ``CartesianDiscreteModel(domain, partition; map=identity)``.
 
     domain = (lo_1, hi_1, lo_2, hi_2, ...), partition = (n_1, n_2, ...).
+    ``map``: optional callable X (npts, dim) -> (npts, dim) applied to the VERTEX coordinates (Gridap's ``map``
+    keyword); the cells are then the Q1 (multi-linear) images of the reference cell spanned by their mapped
+    vertices, in general neither identical nor affine: the per-cell "weights and Jacobians" of the north star.
     """
 
     domain: Sequence[float]
     partition: Union[int, Sequence[int]]
+    map: Optional[Callable] = None
 
     def __post_init__(self):
         part = (self.partition,) if np.isscalar(self.partition) else tuple(self.partition)
@@ -98,8 +102,46 @@ class CartesianDiscreteModel:
             v = v // (self.n[d] + 1)
         return out
 
+    @property
+    def is_mapped(self) -> bool:
+        return self.map is not None
+
     def vertex_coords(self) -> np.ndarray:
-        return self.lo + self.vertex_multi_index() * self.h
+        X = self.lo + self.vertex_multi_index() * self.h
+        if self.map is not None:
+            X = np.asarray(self.map(X), dtype=np.float64).reshape(X.shape)
+        return X
+
+    # geometry of the (possibly mapped) cells ---------------------------------------
+    def _cell_vertex_ids(self, cells: np.ndarray) -> np.ndarray:
+        idx = self.cell_multi_index(cells)
+        nv = [k + 1 for k in self.n]
+        stride = np.cumprod([1] + nv[:-1])
+        base = (idx * stride).sum(axis=1)
+        offs = np.array([sum(stride[d] for d in range(self.dim) if (corner >> d) & 1) for corner in range(2 ** self.dim)])
+        return base[:, None] + offs[None, :]
+
+    def physical_points(self, cells: np.ndarray, ref_pts: np.ndarray) -> np.ndarray:
+        """(ncells, npts, dim) images of the reference points under each cell map."""
+        cells = np.asarray(cells, dtype=np.int64)
+        if self.map is None:
+            idx = self.cell_multi_index(cells)
+            return self.lo + (idx[:, None, :] + ref_pts[None, :, :]) * self.h
+        N, _ = lagrange_tables(1, self.dim, ref_pts)          # (npts, 2^dim) Q1 shape functions of the cell map
+        xv = self.vertex_coords()[self._cell_vertex_ids(cells)]  # (nc, 2^dim, dim)
+        return np.einsum("qv,cvd->cqd", N, xv)
+
+    def cell_jacobians(self, cells: np.ndarray, ref_pts: np.ndarray):
+        """J[c, q, d, e] = d x_d / d xi_e of each cell map at the reference points, and |det J|."""
+        cells = np.asarray(cells, dtype=np.int64)
+        nq = ref_pts.shape[0]
+        if self.map is None:
+            J = np.broadcast_to(np.diag(self.h), (cells.size, nq, self.dim, self.dim)).copy()
+        else:
+            _, dN = lagrange_tables(1, self.dim, ref_pts)     # (npts, 2^dim, dim)
+            xv = self.vertex_coords()[self._cell_vertex_ids(cells)]
+            J = np.einsum("cvd,qve->cqde", xv, dN)
+        return J, np.abs(np.linalg.det(J))
 
     # boundary "entity" of a point given per-direction position flags ------------
     def _entity_from_flags(self, at_lo: np.ndarray, at_hi: np.ndarray) -> np.ndarray:

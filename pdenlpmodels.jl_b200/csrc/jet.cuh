@@ -23,6 +23,26 @@
 
 namespace pdenlp {
 
+// Products with a structurally zero factor.  The seeds (and everything affine in them) carry the literal constants
+// 0.0 / 1.0 in their derivative entries after inlining, but IEEE arithmetic forbids folding 0.0 * v (v may be inf or
+// NaN).  That keeps dead multiplications alive — and the values they read, e.g. the gather of x in kernels that only
+// consume second derivatives — and it turns every structural zero of a derivative into a run-time value which the
+// kernels can no longer skip at compile time (the reference-tensor kernels of kvector.cuh branch on them).
+// zmul(h, v) = h * v with "h == 0 => 0": folds at compile time for literal operands; for run-time operands the test
+// runs on the integer pipe (on B200 the FP64 pipe is the scarce one).  -DPDENLP_NO_ZMUL: plain products (A/B switch).
+PDENLP_HD bool jzero(double h) {
+#ifdef PDENLP_NO_ZMUL
+  (void)h;
+  return false;
+#elif defined(__CUDA_ARCH__)
+  return ((unsigned long long)__double_as_longlong(h) << 1) == 0ull;
+#else
+  return h == 0.0;
+#endif
+}
+PDENLP_HD double zmul(double h, double v) { return jzero(h) ? 0.0 : h * v; }
+PDENLP_HD double zmul2(double a, double b) { return (jzero(a) || jzero(b)) ? 0.0 : a * b; }
+
 // ---------------------------------------------------------------- Jet1
 template <int M>
 struct Jet1 {
@@ -40,6 +60,13 @@ template <int M> PDENLP_HD void jet_seed(Jet1<M>& r, double val, int k0) {
   r.v = val;
 #pragma unroll
   for (int k = 0; k < M; ++k) r.g[k] = (k == k0) ? 1.0 : 0.0;
+}
+// seed with a linear combination of n consecutive independent variables starting at k0 (per-cell geometry: a physical
+// gradient component is a combination of the reference gradient slots)
+template <int M> PDENLP_HD void jet_seed_lin(Jet1<M>& r, double val, int k0, int n, const double* row) {
+  r.v = val;
+#pragma unroll
+  for (int k = 0; k < M; ++k) r.g[k] = (k >= k0 && k < k0 + n) ? row[k - k0 < 0 ? 0 : k - k0] : 0.0;
 }
 template <int M> PDENLP_HD Jet1<M> operator+(const Jet1<M>& a, const Jet1<M>& b) {
   Jet1<M> r; r.v = a.v + b.v;
@@ -62,13 +89,13 @@ template <int M> PDENLP_HD Jet1<M> operator-(const Jet1<M>& a) {
 template <int M> PDENLP_HD Jet1<M> operator*(const Jet1<M>& a, const Jet1<M>& b) {
   Jet1<M> r; r.v = a.v * b.v;
 #pragma unroll
-  for (int k = 0; k < M; ++k) r.g[k] = a.g[k] * b.v + a.v * b.g[k];
+  for (int k = 0; k < M; ++k) r.g[k] = zmul(a.g[k], b.v) + zmul(b.g[k], a.v);
   return r;
 }
 template <int M> PDENLP_HD Jet1<M> operator*(double a, const Jet1<M>& b) {
   Jet1<M> r; r.v = a * b.v;
 #pragma unroll
-  for (int k = 0; k < M; ++k) r.g[k] = a * b.g[k];
+  for (int k = 0; k < M; ++k) r.g[k] = zmul(b.g[k], a);
   return r;
 }
 template <int M> PDENLP_HD Jet1<M> operator*(const Jet1<M>& b, double a) { return a * b; }
@@ -79,13 +106,13 @@ template <int M> PDENLP_HD Jet1<M> operator-(double b, const Jet1<M>& a) { retur
 template <int M> PDENLP_HD Jet1<M> jsinh(const Jet1<M>& a) {
   Jet1<M> r; r.v = sinh(a.v); const double c = cosh(a.v);
 #pragma unroll
-  for (int k = 0; k < M; ++k) r.g[k] = c * a.g[k];
+  for (int k = 0; k < M; ++k) r.g[k] = zmul(a.g[k], c);
   return r;
 }
 template <int M> PDENLP_HD Jet1<M> jcos(const Jet1<M>& a) {
   Jet1<M> r; r.v = cos(a.v); const double ms = -sin(a.v);
 #pragma unroll
-  for (int k = 0; k < M; ++k) r.g[k] = ms * a.g[k];
+  for (int k = 0; k < M; ++k) r.g[k] = zmul(a.g[k], ms);
   return r;
 }
 
@@ -115,6 +142,13 @@ template <int M> PDENLP_HD void jet_seed(Jet2<M>& r, double val, int k0) {
 #pragma unroll
   for (int k = 0; k < Jet2<M>::NH; ++k) r.h[k] = 0.0;
 }
+template <int M> PDENLP_HD void jet_seed_lin(Jet2<M>& r, double val, int k0, int n, const double* row) {
+  r.v = val;
+#pragma unroll
+  for (int k = 0; k < M; ++k) r.g[k] = (k >= k0 && k < k0 + n) ? row[k - k0 < 0 ? 0 : k - k0] : 0.0;
+#pragma unroll
+  for (int k = 0; k < Jet2<M>::NH; ++k) r.h[k] = 0.0;
+}
 template <int M> PDENLP_HD Jet2<M> operator+(const Jet2<M>& a, const Jet2<M>& b) {
   Jet2<M> r; r.v = a.v + b.v;
 #pragma unroll
@@ -139,35 +173,24 @@ template <int M> PDENLP_HD Jet2<M> operator-(const Jet2<M>& a) {
   for (int k = 0; k < Jet2<M>::NH; ++k) r.h[k] = -a.h[k];
   return r;
 }
-// h * v with a structurally zero second derivative: the seeds (and everything affine in them) carry the literal
-// constant 0.0 in h after inlining, but IEEE arithmetic forbids folding 0.0 * v, which would keep the VALUE of the
-// other factor alive — and with it the gather of x — in kernels that only consume second derivatives (the Hessian
-// of a quadratic objective or of a bilinear residual does not depend on x at all).  The explicit test folds at
-// compile time for such operands and is a select otherwise.
-#ifdef PDENLP_NO_ZMUL  // A/B switch for measurements
-PDENLP_HD double zmul(double h, double v) { return h * v; }
-#else
-PDENLP_HD double zmul(double h, double v) { return h == 0.0 ? 0.0 : h * v; }
-#endif
-
 template <int M> PDENLP_HD Jet2<M> operator*(const Jet2<M>& a, const Jet2<M>& b) {
   Jet2<M> r; r.v = a.v * b.v;
 #pragma unroll
-  for (int k = 0; k < M; ++k) r.g[k] = a.g[k] * b.v + a.v * b.g[k];
+  for (int k = 0; k < M; ++k) r.g[k] = zmul(a.g[k], b.v) + zmul(b.g[k], a.v);
 #pragma unroll
   for (int k = 0; k < M; ++k)
 #pragma unroll
     for (int l = 0; l <= k; ++l)
       r.h[k * (k + 1) / 2 + l] = zmul(a.h[k * (k + 1) / 2 + l], b.v) + zmul(b.h[k * (k + 1) / 2 + l], a.v) +
-                                 a.g[k] * b.g[l] + a.g[l] * b.g[k];
+                                 zmul2(a.g[k], b.g[l]) + zmul2(a.g[l], b.g[k]);
   return r;
 }
 template <int M> PDENLP_HD Jet2<M> operator*(double a, const Jet2<M>& b) {
   Jet2<M> r; r.v = a * b.v;
 #pragma unroll
-  for (int k = 0; k < M; ++k) r.g[k] = a * b.g[k];
+  for (int k = 0; k < M; ++k) r.g[k] = zmul(b.g[k], a);
 #pragma unroll
-  for (int k = 0; k < Jet2<M>::NH; ++k) r.h[k] = a * b.h[k];
+  for (int k = 0; k < Jet2<M>::NH; ++k) r.h[k] = zmul(b.h[k], a);
   return r;
 }
 template <int M> PDENLP_HD Jet2<M> operator*(const Jet2<M>& b, double a) { return a * b; }
@@ -178,23 +201,23 @@ template <int M> PDENLP_HD Jet2<M> operator-(double b, const Jet2<M>& a) { retur
 template <int M> PDENLP_HD Jet2<M> jsinh(const Jet2<M>& a) {
   Jet2<M> r; const double s = sinh(a.v), c = cosh(a.v); r.v = s;
 #pragma unroll
-  for (int k = 0; k < M; ++k) r.g[k] = c * a.g[k];
+  for (int k = 0; k < M; ++k) r.g[k] = zmul(a.g[k], c);
 #pragma unroll
   for (int k = 0; k < M; ++k)
 #pragma unroll
     for (int l = 0; l <= k; ++l)
-      r.h[k * (k + 1) / 2 + l] = c * a.h[k * (k + 1) / 2 + l] + s * (a.g[k] * a.g[l]);
+      r.h[k * (k + 1) / 2 + l] = zmul(a.h[k * (k + 1) / 2 + l], c) + zmul(zmul2(a.g[k], a.g[l]), s);
   return r;
 }
 template <int M> PDENLP_HD Jet2<M> jcos(const Jet2<M>& a) {
   Jet2<M> r; const double c = cos(a.v), ms = -sin(a.v); r.v = c;
 #pragma unroll
-  for (int k = 0; k < M; ++k) r.g[k] = ms * a.g[k];
+  for (int k = 0; k < M; ++k) r.g[k] = zmul(a.g[k], ms);
 #pragma unroll
   for (int k = 0; k < M; ++k)
 #pragma unroll
     for (int l = 0; l <= k; ++l)
-      r.h[k * (k + 1) / 2 + l] = ms * a.h[k * (k + 1) / 2 + l] - c * (a.g[k] * a.g[l]);
+      r.h[k * (k + 1) / 2 + l] = zmul(a.h[k * (k + 1) / 2 + l], ms) - zmul(zmul2(a.g[k], a.g[l]), c);
   return r;
 }
 
@@ -203,5 +226,6 @@ PDENLP_HD double jet_const(double a, const double&) { return a; }
 PDENLP_HD double jsinh(double a) { return sinh(a); }
 PDENLP_HD double jcos(double a) { return cos(a); }
 PDENLP_HD void jet_seed(double& r, double val, int) { r = val; }
+PDENLP_HD void jet_seed_lin(double& r, double val, int, int, const double*) { r = val; }
 
 }  // namespace pdenlp

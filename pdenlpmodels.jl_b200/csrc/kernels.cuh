@@ -48,9 +48,13 @@ constexpr int kThreads = kWarpsPerCta * 32;
 // NFU control fields, all fields of a kind sharing one reference element) is handled as one element
 // with NY = NFY*NLY state dofs, field-major, whose dof ids were renumbered at create time to the
 // concatenated (ConsecutiveMultiFieldStyle) ids of the whole state / control space.
-template <class Integrand_, int NLY_, int NLU_, int NQ_>
+// GEO_ = true: per-cell geometry (desc.cell_jinvT): the tables hold REFERENCE gradients / weights and every cell applies
+// its own J^-T and det(J) (any Gridap triangulation); false: the uniform fast path with physical gradients folded into
+// the tables (identical affine cells, e.g. a CartesianDiscreteModel without `map`).
+template <class Integrand_, int NLY_, int NLU_, int NQ_, bool GEO_ = false>
 struct Elem {
   using Integrand = Integrand_;
+  static constexpr bool GEO = GEO_;
   static constexpr int DIM = Integrand::DIM, NP = Integrand::NP, M = Integrand::M;
   static constexpr int SY = Integrand::SY, SG = Integrand::SG, SU = Integrand::SU, SK = Integrand::SK;
   static constexpr int NFY = Integrand::NFY, NFU = NLU_ > 0 ? Integrand::NFU : 0;
@@ -84,7 +88,7 @@ struct Tables {
 // sum_{t,k} D[t][k] * K[t][k][.][.]: one pass, no per-quadrature-point read-modify-write in shared memory.
 template <class E>
 struct KTab {
-  static constexpr bool ENABLED = E::NQ > 1 && !E::HAS_CONST && !E::MULTI;
+  static constexpr bool ENABLED = E::NQ > 1 && !E::HAS_CONST && !E::MULTI && !E::GEO;  // (reference tensors need identical cells)
   static constexpr int NB = E::NB, NY = E::NY, NU = E::NU;
   static constexpr int OFF_YY = 0;
   static constexpr int OFF_UY = NB * NB * NY * NY;
@@ -116,6 +120,9 @@ struct DevModel {
   const int64_t* base_ju;
   const int64_t* base_h;
   const double* ktab;      // pre-integrated reference tensors (KTab layout), nq > 1 elements only
+  const double* jinvT;     // per-cell geometry, SoA [geom_nq][dim][dim][ldc]: grad_x = jinvT * grad_xi  (GEO elements only)
+  const double* detj;      // [geom_nq][ldc]
+  int32_t geom_nq;         // 1 (affine cells) or nq
   int64_t ncells, ldc;
   int64_t nfree_y, nfree_u;
   int32_t ntiles;
@@ -200,9 +207,40 @@ __device__ __forceinline__ void gather_free(const double* __restrict__ vec, cons
   }
 }
 
-// pointwise fields at quadrature point q, seeded as jets (or plain doubles)
+// quadrature point q of a cell: coefficient values, quadrature weight * det(J) and (GEO elements) the cell's J^-T
+template <class E>
+struct PointGeo : PointCtx {
+  double w;                                   // quadrature weight * |det J|
+  double T[E::GEO ? E::DIM : 1][E::GEO ? E::DIM : 1];  // J^-T at the point: grad_x = T * grad_xi
+};
+template <class E>
+__device__ __forceinline__ PointGeo<E> point_ctx(const DevModel& D, const Tables<E>& tab, int64_t cell, bool valid, int q, bool need) {
+  PointGeo<E> pc;
+  pc.par = tab.par;
+  pc.target = 0.0;
+  pc.source = 0.0;
+  if (need && valid) {
+    pc.target = __ldg(D.coef + (cell * E::NQ + q));
+    pc.source = __ldg(D.coef + ((D.ncells_coef + cell) * E::NQ + q));
+  }
+  pc.w = tab.wdet[q];
+  if (E::GEO) {
+    const int g = D.geom_nq > 1 ? q : 0;
+    const int64_t c = valid ? cell : 0;
+#pragma unroll
+    for (int d = 0; d < E::DIM; ++d)
+#pragma unroll
+      for (int e = 0; e < E::DIM; ++e) pc.T[E::GEO ? d : 0][E::GEO ? e : 0] = __ldg(D.jinvT + ((int64_t)((g * E::DIM + d) * E::DIM + e) * D.ldc + c));
+    pc.w *= __ldg(D.detj + ((int64_t)g * D.ldc + c));
+  }
+  return pc;
+}
+
+// pointwise fields at quadrature point q, seeded as jets (or plain doubles).  GEO elements: the gradient slots carry
+// the PHYSICAL gradient T * grad_xi y as value and the row of T as seed, so the jets differentiate w.r.t. the
+// reference slots (the chain rule through the cell map is done by the jet arithmetic).
 template <class E, class T>
-__device__ __forceinline__ void point_state(const Tables<E>& tab, const Cell<E>& c, const double* __restrict__ x, int q, T* s) {
+__device__ __forceinline__ void point_state(const Tables<E>& tab, const PointGeo<E>& pc, const Cell<E>& c, const double* __restrict__ x, int q, T* s) {
   double val[E::M];
 #pragma unroll
   for (int k = 0; k < E::M; ++k) val[k] = 0.0;
@@ -218,21 +256,43 @@ __device__ __forceinline__ void point_state(const Tables<E>& tab, const Cell<E>&
     for (int b = 0; b < E::NLU; ++b) val[E::SU + f] = fma(tab.Bu[q][b], c.zu[f * E::NLU + b], val[E::SU + f]);
 #pragma unroll
   for (int k = 0; k < E::NP; ++k) val[E::SK + k] = __ldg(x + k);
+  if (E::GEO) {
 #pragma unroll
-  for (int k = 0; k < E::M; ++k) jet_seed(s[k], val[k], k);
-}
-
-template <class E>
-__device__ __forceinline__ PointCtx point_ctx(const DevModel& D, const Tables<E>& tab, int64_t cell, bool valid, int q, bool need) {
-  PointCtx pc;
-  pc.par = tab.par;
-  pc.target = 0.0;
-  pc.source = 0.0;
-  if (need && valid) {
-    pc.target = __ldg(D.coef + (cell * E::NQ + q));
-    pc.source = __ldg(D.coef + ((D.ncells_coef + cell) * E::NQ + q));
+    for (int k = 0; k < E::M; ++k) {
+      const int f = k / E::NB, d = k % E::NB - 1;  // state field and gradient component of slot k
+      if (k < E::NFY * E::NB && d >= 0) {
+        double row[E::DIM], a = 0.0;
+#pragma unroll
+        for (int e = 0; e < E::DIM; ++e) { row[e] = pc.T[E::GEO ? d : 0][E::GEO ? e : 0]; a = fma(row[e], val[f * E::NB + 1 + e], a); }
+        jet_seed_lin(s[k], a, f * E::NB + 1, E::DIM, row);
+      } else {
+        jet_seed(s[k], val[k], k);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < E::M; ++k) jet_seed(s[k], val[k], k);
   }
-  return pc;
+}
+// the integrand's residual slots; GEO elements: the gradient slots multiply the PHYSICAL test gradient
+// T * grad_xi v, so they are pulled back to the reference slots: R_ref[1+e] = sum_d T[d][e] R[1+d]
+template <class E, class S>
+__device__ __forceinline__ void eval_res(const PointGeo<E>& pc, const S* s, S* R) {
+  E::Integrand::res(pc, s, R);
+  if (E::GEO) {
+#pragma unroll
+    for (int f = 0; f < E::NFY; ++f) {
+      S P[E::DIM];
+#pragma unroll
+      for (int e = 0; e < E::DIM; ++e) {
+        P[e] = pc.T[0][E::GEO ? e : 0] * R[f * E::NB + 1];
+#pragma unroll
+        for (int d = 1; d < E::DIM; ++d) P[e] = P[e] + pc.T[E::GEO ? d : 0][E::GEO ? e : 0] * R[f * E::NB + 1 + d];
+      }
+#pragma unroll
+      for (int e = 0; e < E::DIM; ++e) R[f * E::NB + 1 + e] = P[e];
+    }
+  }
 }
 
 // test-function slot t of local test function i: (phi_i, grad phi_i, [1])  (single-field elements)
@@ -741,9 +801,9 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
 #pragma unroll 1
       for (int q = 0; q < E::NQ; ++q) {
         Jet1<E::M> s[E::M], R[E::NR];
-        point_state<E>(tab, c, x, q, s);
-        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
-        I::res(pc, s, R);
+        const PointGeo<E> pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        point_state<E>(tab, pc, c, x, q, s);
+        eval_res<E>(pc, s, R);
 #pragma unroll
         for (int j = 0; j < E::NY; ++j) {
           double Mj[E::NR];
@@ -752,7 +812,7 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
             double a = 0.0;
 #pragma unroll
             for (int k = 0; k < E::NB; ++k) a = fma(R[t].g[k], tab.By[q][j][k], a);
-            Mj[t] = a * tab.wdet[q];
+            Mj[t] = a * pc.w;
           }
 #pragma unroll
           for (int i = 0; i < E::NY; ++i)
@@ -763,7 +823,7 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
         for (int b = 0; b < E::NU; ++b) {
           double Mb[E::NR];
 #pragma unroll
-          for (int t = 0; t < E::NR; ++t) Mb[t] = R[t].g[E::SU] * tab.Bu[q][b] * tab.wdet[q];
+          for (int t = 0; t < E::NR; ++t) Mb[t] = R[t].g[E::SU] * tab.Bu[q][b] * pc.w;
 #pragma unroll
           for (int i = 0; i < E::NY; ++i)
 #pragma unroll
@@ -778,9 +838,9 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
 #pragma unroll 1
       for (int q = 0; q < NQT; ++q) {
         Jet1<E::M> s[E::M], R[E::NR];
-        point_state<E>(tab, c, x, q, s);
-        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
-        I::res(pc, s, R);
+        const PointGeo<E> pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        point_state<E>(tab, pc, c, x, q, s);
+        eval_res<E>(pc, s, R);
         if (q == 0) {
 #pragma unroll
           for (int t = 0; t < E::NR; ++t) R0[t] = R[t];
@@ -816,9 +876,9 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
 #pragma unroll 1
       for (int q = 0; q < E::NQ; ++q) {
         Jet1<E::M> s[E::M], R[E::NR];
-        point_state<E>(tab, c, x, q, s);
-        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
-        I::res(pc, s, R);
+        const PointGeo<E> pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        point_state<E>(tab, pc, c, x, q, s);
+        eval_res<E>(pc, s, R);
         double* p = p0;
 #pragma unroll
         for (int j = 0; j < E::NY; ++j) {
@@ -828,7 +888,7 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
             double a = 0.0;
 #pragma unroll
             for (int k = 0; k < E::NB; ++k) a = fma(R[t].g[k], tab.By[q][j][k], a);
-            Mj[t] = a * tab.wdet[q];
+            Mj[t] = a * pc.w;
           }
           if (c.gy[j] > 0) {
 #pragma unroll
@@ -865,15 +925,15 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
 #pragma unroll 1
       for (int q = 0; q < E::NQ; ++q) {
         Jet1<E::M> s[E::M], R[E::NR];
-        point_state<E>(tab, c, x, q, s);
-        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
-        I::res(pc, s, R);
+        const PointGeo<E> pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        point_state<E>(tab, pc, c, x, q, s);
+        eval_res<E>(pc, s, R);
         double* p = p0;
 #pragma unroll
         for (int b = 0; b < E::NU; ++b) {
           double Mb[E::NR];
 #pragma unroll
-          for (int t = 0; t < E::NR; ++t) Mb[t] = R[t].g[E::SU] * tab.Bu[q][b] * tab.wdet[q];
+          for (int t = 0; t < E::NR; ++t) Mb[t] = R[t].g[E::SU] * tab.Bu[q][b] * pc.w;
           if (c.gu[b] > 0) {
 #pragma unroll
             for (int i = 0; i < E::NY; ++i) {
@@ -996,10 +1056,9 @@ __device__ __forceinline__ bool fe_hess_block_is_zero(const Jet2<E::M>& L) {
 // lambda-weighted residual  l(s) = sum_t Lam_t R_t(s)  as a Jet2 (its Hessian is the pointwise
 // Lagrangian Hessian; its gradient the pointwise J^T lambda)
 template <class E, class T>
-__device__ __forceinline__ T weighted_res(const PointCtx& pc, const T* s, const double* Lam) {
-  using I = typename E::Integrand;
+__device__ __forceinline__ T weighted_res(const PointGeo<E>& pc, const T* s, const double* Lam) {
   T R[E::NR];
-  I::res(pc, s, R);
+  eval_res<E>(pc, s, R);
   T acc = Lam[0] * R[0];
 #pragma unroll
   for (int t = 1; t < E::NR; ++t) acc = acc + Lam[t] * R[t];
@@ -1086,7 +1145,9 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
     // w.r.t. the FE fields generates the block.  Structural zeros are detected at run time, per
     // sub-block and warp-uniformly (all quadrature points, all lanes): a vanishing (y,y) part and/or
     // a vanishing u row skip their candidates; if both vanish the image is zero-filled.
-    auto segment = [&](double* gdst, auto&& jet_at) {
+    auto segment = [&](double* gdst, auto&& jet_at_w) {
+      double wq = 0.0;  // quadrature weight * det(J) of the point last evaluated
+      auto jet_at = [&](int q, double& scale) { return jet_at_w(q, scale, wq); };
       if (NBUF > 1) { st.wbuf = wbase + slot * STAGE; slot = slot + 1 == NBUF ? 0 : slot + 1; }
       st.template acquire<NBUF>(lane);
       double* const p0 = st.begin(gdst, incl - cnt, lane);
@@ -1139,7 +1200,7 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
 #pragma unroll 1
         for (int q = 0; q < E::NQ; ++q) {
           L = jet_at(q, sc);
-          const double scale = sc * tab.wdet[q];
+          const double scale = sc * wq;
 #pragma unroll
           for (int j = 0; j < E::NY; ++j) {
             double Nj[E::NB];
@@ -1199,7 +1260,7 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
 #pragma unroll 1
         for (int q = 0; q < E::NQ; ++q) {
           if (E::NQ > 1) L = jet_at(q, sc);  // NQ == 1: the jet of the test pass is reused
-          const double scale = sc * tab.wdet[q];
+          const double scale = sc * wq;
           double* p = p0;
           if (!zyy) p = (q == 0) ? emit_hess_yy<E, false>(tab, q, L, scale, c, p) : emit_hess_yy<E, true>(tab, q, L, scale, c, p);
           else { if (q == 0) for (int k = 0; k < n11; ++k) p[k] = 0.0; p += n11; }
@@ -1210,22 +1271,24 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
       st.release(gdst, incl - cnt, incl, lane);
     };
     if (vals_obj != nullptr) {
-      segment(vals_obj + tb, [&](int q, double& scale) {
+      segment(vals_obj + tb, [&](int q, double& scale, double& wq) {
         Jet2<E::M> s[E::M];
-        point_state<E>(tab, c, x, q, s);
-        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        const PointGeo<E> pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        point_state<E>(tab, pc, c, x, q, s);
         scale = obj_weight;
+        wq = pc.w;
         return I::f(pc, s);
       });
     }
     if (vals_con != nullptr) {
-      segment(vals_con + tb, [&](int q, double& scale) {
+      segment(vals_con + tb, [&](int q, double& scale, double& wq) {
         Jet2<E::M> s[E::M];
-        point_state<E>(tab, c, x, q, s);
-        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        const PointGeo<E> pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        point_state<E>(tab, pc, c, x, q, s);
         double Lam[E::NR];
         lambda_slots<E>(tab, q, lam_e, Lam);
         scale = 1.0;
+        wq = pc.w;
         return weighted_res<E>(pc, s, Lam);
       });
     }
@@ -1250,8 +1313,7 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
 // These are the ODE-type problems of the reference (1-D, one quadrature point); they take the plain
 // per-tile loop without the register pipeline and reference-tensor paths of the kernels above.
 template <class E, bool ACC>
-__device__ __forceinline__ double* emit_jac_y_mf(const Tables<E>& tab, int q, const Jet1<E::M> (&R)[E::NR], const Cell<E>& c, double* p) {
-  const double w = tab.wdet[q];
+__device__ __forceinline__ double* emit_jac_y_mf(const Tables<E>& tab, int q, double w, const Jet1<E::M> (&R)[E::NR], const Cell<E>& c, double* p) {
 #pragma unroll
   for (int cf = 0; cf < E::NFY; ++cf)
 #pragma unroll
@@ -1279,8 +1341,7 @@ __device__ __forceinline__ double* emit_jac_y_mf(const Tables<E>& tab, int q, co
   return p;
 }
 template <class E, bool ACC>
-__device__ __forceinline__ double* emit_jac_u_mf(const Tables<E>& tab, int q, const Jet1<E::M> (&R)[E::NR], const Cell<E>& c, double* p) {
-  const double w = tab.wdet[q];
+__device__ __forceinline__ double* emit_jac_u_mf(const Tables<E>& tab, int q, double w, const Jet1<E::M> (&R)[E::NR], const Cell<E>& c, double* p) {
 #pragma unroll
   for (int cf = 0; cf < E::NFU; ++cf)
 #pragma unroll
@@ -1361,10 +1422,10 @@ k_jac_coord_mf(const __grid_constant__ Tables<E> tab, const DevModel D, const do
 #pragma unroll 1
       for (int q = 0; q < E::NQ; ++q) {
         Jet1<E::M> s[E::M], R[E::NR];
-        point_state<E>(tab, c, x, q, s);
-        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
-        I::res(pc, s, R);
-        if (q == 0) emit_jac_y_mf<E, false>(tab, q, R, c, p0); else emit_jac_y_mf<E, true>(tab, q, R, c, p0);
+        const PointGeo<E> pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        point_state<E>(tab, pc, c, x, q, s);
+        eval_res<E>(pc, s, R);
+        if (q == 0) emit_jac_y_mf<E, false>(tab, q, pc.w, R, c, p0); else emit_jac_y_mf<E, true>(tab, q, pc.w, R, c, p0);
       }
       sty.release(gdst, incl - cnt, incl, lane);
     }
@@ -1378,10 +1439,10 @@ k_jac_coord_mf(const __grid_constant__ Tables<E> tab, const DevModel D, const do
 #pragma unroll 1
       for (int q = 0; q < E::NQ; ++q) {
         Jet1<E::M> s[E::M], R[E::NR];
-        point_state<E>(tab, c, x, q, s);
-        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
-        I::res(pc, s, R);
-        if (q == 0) emit_jac_u_mf<E, false>(tab, q, R, c, p0); else emit_jac_u_mf<E, true>(tab, q, R, c, p0);
+        const PointGeo<E> pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        point_state<E>(tab, pc, c, x, q, s);
+        eval_res<E>(pc, s, R);
+        if (q == 0) emit_jac_u_mf<E, false>(tab, q, pc.w, R, c, p0); else emit_jac_u_mf<E, true>(tab, q, pc.w, R, c, p0);
       }
       stu.release(gdst, incl - cnt, incl, lane);
     }
@@ -1520,10 +1581,10 @@ k_hess_coord_mf(const __grid_constant__ Tables<E> tab, const DevModel D, const d
 #pragma unroll 1
       for (int q = 0; q < E::NQ; ++q) {
         Jet2<E::M> s[E::M];
-        point_state<E>(tab, c, x, q, s);
-        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        const PointGeo<E> pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        point_state<E>(tab, pc, c, x, q, s);
         const Jet2<E::M> L = I::f(pc, s);
-        const double scale = obj_weight * tab.wdet[q];
+        const double scale = obj_weight * pc.w;
         if (q == 0) emit_hess_mf<E, false>(tab, q, L, scale, c, p0); else emit_hess_mf<E, true>(tab, q, L, scale, c, p0);
       }
       st.release(gdst, incl - cnt, incl, lane);
@@ -1538,12 +1599,12 @@ k_hess_coord_mf(const __grid_constant__ Tables<E> tab, const DevModel D, const d
 #pragma unroll 1
       for (int q = 0; q < E::NQ; ++q) {
         Jet2<E::M> s[E::M];
-        point_state<E>(tab, c, x, q, s);
-        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        const PointGeo<E> pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        point_state<E>(tab, pc, c, x, q, s);
         double Lam[E::NR];
         lambda_slots<E>(tab, q, lam_e, Lam);
         const Jet2<E::M> L = weighted_res<E>(pc, s, Lam);
-        if (q == 0) emit_hess_mf<E, false>(tab, q, L, tab.wdet[q], c, p0); else emit_hess_mf<E, true>(tab, q, L, tab.wdet[q], c, p0);
+        if (q == 0) emit_hess_mf<E, false>(tab, q, L, pc.w, c, p0); else emit_hess_mf<E, true>(tab, q, L, pc.w, c, p0);
       }
       st.release(gdst, incl - cnt, incl, lane);
     }
@@ -1767,16 +1828,17 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
     for (int b = 0; b < E::NUS; ++b) eu[b] = 0.0;
 #pragma unroll 1
     for (int q = 0; q < E::NQ; ++q) {
-      const double w = tab.wdet[q];
+      // (the objective and the residual read the coefficient fields; their derivatives only for some integrands)
+      constexpr bool VAL = OP == OP_OBJ || OP == OP_GRAD || OP == OP_OBJGRAD || OP == OP_CONS || OP == OP_OBJCONS;
+      const PointGeo<E> pc = point_ctx<E>(D, tab, cell, valid, q, VAL || I::NEEDS_COEF_DERIV);
+      const double w = pc.w;
       if (OP == OP_OBJ) {
         double s[E::M];
-        point_state<E>(tab, c, x, q, s);
-        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, true);
+        point_state<E>(tab, pc, c, x, q, s);
         fsum += w * I::f(pc, s);
       } else if (OP == OP_GRAD || OP == OP_OBJGRAD) {
         Jet1<E::M> s[E::M];
-        point_state<E>(tab, c, x, q, s);
-        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, true);
+        point_state<E>(tab, pc, c, x, q, s);
         const Jet1<E::M> F = I::f(pc, s);
         if (OP == OP_OBJGRAD) fsum += w * F.v;
         double gs[E::M];
@@ -1787,19 +1849,17 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
         for (int k = 0; k < E::NP; ++k) ksum[k] += gs[E::SK + k];
       } else if (OP == OP_CONS || OP == OP_OBJCONS) {
         double s[E::M], R[E::NR];
-        point_state<E>(tab, c, x, q, s);
-        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, true);
+        point_state<E>(tab, pc, c, x, q, s);
         if (OP == OP_OBJCONS) fsum += w * I::f(pc, s);
-        I::res(pc, s, R);
+        eval_res<E>(pc, s, R);
 #pragma unroll
         for (int f = 0; f < E::NFY; ++f)
 #pragma unroll
           for (int i = 0; i < E::NLY; ++i) ey[f * E::NLY + i] = fma(w, test_contract<E>(tab, q, f, i, R), ey[f * E::NLY + i]);
       } else if (OP == OP_JPROD) {
         Jet1<E::M> s[E::M], R[E::NR];
-        point_state<E>(tab, c, x, q, s);
-        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
-        I::res(pc, s, R);
+        point_state<E>(tab, pc, c, x, q, s);
+        eval_res<E>(pc, s, R);
         double ds[E::M];
         field_direction<E>(tab, q, D, c, v, ds);
         double dR[E::NR];
@@ -1816,8 +1876,7 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
           for (int i = 0; i < E::NLY; ++i) ey[f * E::NLY + i] += test_contract<E>(tab, q, f, i, dR);
       } else if (OP == OP_JTPROD) {
         Jet1<E::M> s[E::M];
-        point_state<E>(tab, c, x, q, s);
-        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        point_state<E>(tab, pc, c, x, q, s);
         double w_e[E::NY], Lam[E::NR];
         gather_free<E::NY>(v, c.gy, w_e);
         lambda_slots<E>(tab, q, w_e, Lam);
@@ -1830,8 +1889,7 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
         for (int k = 0; k < E::NP; ++k) ksum[k] += gs[E::SK + k];
       } else if (OP == OP_HPROD) {
         Jet2<E::M> s[E::M];
-        point_state<E>(tab, c, x, q, s);
-        const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
+        point_state<E>(tab, pc, c, x, q, s);
         double ds[E::M];
         field_direction<E>(tab, q, D, c, v, ds);
         double gs[E::M];
@@ -1958,9 +2016,9 @@ k_jac_kappa(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
 #pragma unroll 1
     for (int q = 0; q < E::NQ; ++q) {
       Jet1<E::M> s[E::M], R[E::NR];
-      point_state<E>(tab, c, x, q, s);
-      const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, true);
-      I::res(pc, s, R);
+      const PointGeo<E> pc = point_ctx<E>(D, tab, cell, valid, q, true);
+      point_state<E>(tab, pc, c, x, q, s);
+      eval_res<E>(pc, s, R);
 #pragma unroll
       for (int k = 0; k < E::NP; ++k)
 #pragma unroll
@@ -1968,7 +2026,7 @@ k_jac_kappa(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
           double a = 0.0;
 #pragma unroll
           for (int t = 0; t < E::NR; ++t) a = fma(test_slot<E>(tab, q, i, t), R[t].g[E::SK + k], a);
-          acc[k][i] = fma(tab.wdet[q], a, acc[k][i]);
+          acc[k][i] = fma(pc.w, a, acc[k][i]);
         }
     }
 #pragma unroll
@@ -2039,17 +2097,17 @@ k_hess_kappa_kk(const __grid_constant__ Tables<E> tab, const DevModel D, const d
     gather_state<E>(D, x, valid, c);
 #pragma unroll 1
     for (int q = 0; q < E::NQ; ++q) {
+      const PointGeo<E> pc = point_ctx<E>(D, tab, cell, valid, q, true);
       double val[E::M];
-      point_state<E>(tab, c, x, q, val);
+      point_state<E>(tab, pc, c, x, q, val);
       JK s[E::M];
 #pragma unroll
       for (int k = 0; k < E::M; ++k) {
         if (k >= E::SK && k < E::SK + E::NP) jet_seed(s[k], val[k], k - E::SK);
         else s[k] = jet_const(val[k], s[k]);
       }
-      const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, true);
       const JK F = I::f(pc, s);
-      const double scale = tab.wdet[q] * obj_weight;
+      const double scale = pc.w * obj_weight;
 #pragma unroll
       for (int j = 0; j < E::NP; ++j)
 #pragma unroll
@@ -2100,10 +2158,10 @@ k_hess_kappa(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
 #pragma unroll 1
     for (int q = 0; q < E::NQ; ++q) {
       Jet2<E::M> s[E::M];
-      point_state<E>(tab, c, x, q, s);
-      const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, true);
+      const PointGeo<E> pc = point_ctx<E>(D, tab, cell, valid, q, true);
+      point_state<E>(tab, pc, c, x, q, s);
       J2 L;
-      double scale = tab.wdet[q];
+      double scale = pc.w;
       if (which == 0) { L = I::f(pc, s); scale *= obj_weight; }
       else {
         double Lam[E::NR];

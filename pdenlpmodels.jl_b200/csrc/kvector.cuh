@@ -84,7 +84,7 @@ __device__ __forceinline__ bool gg_iso(const double (&C)[E::NB][E::NB + 1]) {
 #pragma unroll
   for (int t = 1; t < E::NB; ++t)
 #pragma unroll
-    for (int k = 1; k < E::NB; ++k) iso = iso && (t == k ? C[t][k] == C[1][1] : C[t][k] == 0.0);
+    for (int k = 1; k < E::NB; ++k) iso = iso && (t == k ? (t == 1 || C[t][k] == C[1][1]) : jzero(C[t][k]));
   return iso;
 }
 
@@ -94,7 +94,7 @@ __device__ __forceinline__ void apply_yy(const double* __restrict__ Ks, const do
                                          const double (&C1)[E::NB][E::NB + 1], const double* v1, double* out) {
   using KT = KTab<E>;
   const bool iso = gg_iso<E>(C0) && (!TWO || gg_iso<E>(C1));
-  if (iso && (C0[1][1] != 0.0 || (TWO && C1[1][1] != 0.0))) {
+  if (iso && (!jzero(C0[1][1]) || (TWO && !jzero(C1[1][1])))) {
 #pragma unroll
     for (int j = 0; j < E::NY; ++j) {
       const double w = TWO ? fma(C1[1][1], v1[j], C0[1][1] * v0[j]) : C0[1][1] * v0[j];
@@ -107,7 +107,7 @@ __device__ __forceinline__ void apply_yy(const double* __restrict__ Ks, const do
 #pragma unroll
     for (int k = 0; k < E::NB; ++k) {
       const bool gg = t >= 1 && k >= 1;
-      if ((!gg || !iso) && (C0[t][k] != 0.0 || (TWO && C1[t][k] != 0.0))) {
+      if ((!gg || !iso) && (!jzero(C0[t][k]) || (TWO && !jzero(C1[t][k])))) {
 #pragma unroll
         for (int j = 0; j < E::NY; ++j) {
           const double w = TWO ? fma(C1[t][k], v1[j], C0[t][k] * v0[j]) : C0[t][k] * v0[j];
@@ -125,7 +125,7 @@ __device__ __forceinline__ void apply_yu(const double* __restrict__ Ks, const do
   if (E::NU > 0) {
 #pragma unroll
     for (int t = 0; t < E::NB; ++t)
-      if (C0[t][E::NB] != 0.0 || (TWO && C1[t][E::NB] != 0.0)) {
+      if (!jzero(C0[t][E::NB]) || (TWO && !jzero(C1[t][E::NB]))) {
 #pragma unroll
         for (int b = 0; b < E::NU; ++b) {
           const double w = TWO ? fma(C1[t][E::NB], u1[b], C0[t][E::NB] * u0[b]) : C0[t][E::NB] * u0[b];
@@ -147,7 +147,7 @@ __device__ __forceinline__ void apply_T(const double* __restrict__ Ks, const dou
   using KT = KTab<E>;
   constexpr int NPS = AffineRes<E>::NPS;
   auto use_y = [&](const double* p, double c0, const double* c1) {
-    if (WITH_OUT && c0 != 0.0) {
+    if (WITH_OUT && !jzero(c0)) {
 #pragma unroll
       for (int j = 0; j < E::NY; ++j) oy[j] = fma(c0, p[j], oy[j]);
     }
@@ -156,7 +156,8 @@ __device__ __forceinline__ void apply_T(const double* __restrict__ Ks, const dou
 #pragma unroll
       for (int j = 0; j < E::NY; ++j) dot = fma(p[j], zy[j], dot);
 #pragma unroll
-      for (int m = 0; m < E::NP; ++m) kacc[m] = fma(c1[m], dot, kacc[m]);
+      for (int m = 0; m < E::NP; ++m)
+        if (!jzero(c1[m])) kacc[m] = fma(c1[m], dot, kacc[m]);
     }
   };
   bool iso = gg_iso<E>(C0);
@@ -168,12 +169,12 @@ __device__ __forceinline__ void apply_T(const double* __restrict__ Ks, const dou
 #pragma unroll
       for (int t = 1; t < E::NB; ++t)
 #pragma unroll
-        for (int k = 1; k < E::NB; ++k) im = im && (t == k ? C1[t][k][m] == C1[1][1][m] : C1[t][k][m] == 0.0);
+        for (int k = 1; k < E::NB; ++k) im = im && (t == k ? (t == 1 || C1[t][k][m] == C1[1][1][m]) : jzero(C1[t][k][m]));
       iso = iso && im;
-      any1 = any1 || C1[1][1][m] != 0.0;
+      any1 = any1 || !jzero(C1[1][1][m]);
     }
   }
-  if (iso && ((WITH_OUT && C0[1][1] != 0.0) || any1)) {
+  if (iso && ((WITH_OUT && !jzero(C0[1][1])) || any1)) {
     double p[E::NY];
 #pragma unroll
     for (int j = 0; j < E::NY; ++j) {
@@ -189,10 +190,10 @@ __device__ __forceinline__ void apply_T(const double* __restrict__ Ks, const dou
 #pragma unroll
     for (int k = 0; k < E::NB; ++k) {
       const bool gg = t >= 1 && k >= 1;
-      bool act = WITH_OUT && C0[t][k] != 0.0;
+      bool act = WITH_OUT && !jzero(C0[t][k]);
       if (WITH_K) {
 #pragma unroll
-        for (int m = 0; m < E::NP; ++m) act = act || C1[t][k][m] != 0.0;
+        for (int m = 0; m < E::NP; ++m) act = act || !jzero(C1[t][k][m]);
       }
       if ((!gg || !iso) && act) {
         double p[E::NY];
@@ -209,10 +210,10 @@ __device__ __forceinline__ void apply_T(const double* __restrict__ Ks, const dou
   if (E::NU > 0) {
 #pragma unroll
     for (int t = 0; t < E::NB; ++t) {
-      bool act = WITH_OUT && C0[t][E::NB] != 0.0;
+      bool act = WITH_OUT && !jzero(C0[t][E::NB]);
       if (WITH_K) {
 #pragma unroll
-        for (int m = 0; m < E::NP; ++m) act = act || C1[t][E::NB][m] != 0.0;
+        for (int m = 0; m < E::NP; ++m) act = act || !jzero(C1[t][E::NB][m]);
       }
       if (act) {
         double dot = 0.0;
@@ -221,12 +222,13 @@ __device__ __forceinline__ void apply_T(const double* __restrict__ Ks, const dou
           double a = 0.0;
 #pragma unroll
           for (int i = 0; i < E::NY; ++i) a = fma(Ks[KT::yu(t, b, i)], w[i], a);
-          if (WITH_OUT) ou[b] = fma(C0[t][E::NB], a, ou[b]);
+          if (WITH_OUT && !jzero(C0[t][E::NB])) ou[b] = fma(C0[t][E::NB], a, ou[b]);
           if (WITH_K && E::NP > 0) dot = fma(a, zu[b], dot);
         }
         if (WITH_K) {
 #pragma unroll
-          for (int m = 0; m < NPS; ++m) kacc[m] = fma(C1[t][E::NB][m], dot, kacc[m]);
+          for (int m = 0; m < NPS; ++m)
+            if (!jzero(C1[t][E::NB][m])) kacc[m] = fma(C1[t][E::NB][m], dot, kacc[m]);
         }
       }
     }
@@ -245,33 +247,47 @@ template <class E, int ORDER>
 __device__ __forceinline__ void accum_A(const Tables<E>& tab, const DevModel& D, const double* __restrict__ x, int64_t cell, bool valid,
                                         double (&acc)[AOrder<E, ORDER>::NC][E::NY]) {
   using I = typename E::Integrand;
+  constexpr int NC = AOrder<E, ORDER>::NC;
   if (ORDER > 0 && E::NP == 0) return;
-#pragma unroll 1
+  // coefficient values of all points up front: independent loads (one memory latency, not NQ dependent ones)
+  double tgt[E::NQ], src[E::NQ];
+#pragma unroll
   for (int q = 0; q < E::NQ; ++q) {
-    const PointCtx pc = point_ctx<E>(D, tab, cell, valid, q, true);
+    tgt[q] = valid ? __ldg(D.coef + (cell * E::NQ + q)) : 0.0;
+    src[q] = valid ? __ldg(D.coef + ((D.ncells_coef + cell) * E::NQ + q)) : 0.0;
+  }
+  double kap[E::NP > 0 ? E::NP : 1];
+#pragma unroll
+  for (int m = 0; m < E::NP; ++m) kap[m] = __ldg(x + m);
+  // (fully unrolled: the table entries By[q][i][t] are immediate operands, and components that are structurally zero
+  //  — literal zeros after the jets' compile-time folding — disappear from the code)
+#pragma unroll
+  for (int q = 0; q < E::NQ; ++q) {
+    PointCtx pc;
+    pc.par = tab.par; pc.target = tgt[q]; pc.source = src[q];
     const double w = valid ? tab.wdet[q] : 0.0;
-    double X[E::NB][AOrder<E, ORDER>::NC];
+    double X[E::NB][NC];
     if (ORDER == 0) {
       double s[E::M], R[E::NR];
 #pragma unroll
-      for (int k = 0; k < E::M; ++k) s[k] = (k >= E::SK && k < E::SK + E::NP) ? __ldg(x + (k - E::SK)) : 0.0;
+      for (int k = 0; k < E::M; ++k) s[k] = (k >= E::SK && k < E::SK + E::NP) ? kap[k - E::SK] : 0.0;
       I::res(pc, s, R);
 #pragma unroll
-      for (int t = 0; t < E::NB; ++t) X[t][0] = R[t] * w;
+      for (int t = 0; t < E::NB; ++t) X[t][0] = zmul(R[t], w);
     } else if (ORDER == 1) {
       Jet1<E::M> s[E::M], R[E::NR];
 #pragma unroll
-      for (int k = 0; k < E::M; ++k) jet_seed(s[k], (k >= E::SK && k < E::SK + E::NP) ? __ldg(x + (k - E::SK)) : 0.0, k);
+      for (int k = 0; k < E::M; ++k) jet_seed(s[k], (k >= E::SK && k < E::SK + E::NP) ? kap[k - E::SK] : 0.0, k);
       I::res(pc, s, R);
 #pragma unroll
       for (int t = 0; t < E::NB; ++t)
 #pragma unroll
-        for (int m = 0; m < E::NP; ++m) X[t][m] = R[t].g[E::SK + m] * w;
+        for (int m = 0; m < E::NP; ++m) X[t][m] = zmul(R[t].g[E::SK + m], w);
     } else {
       using J2 = Jet2<E::M>;
       J2 s[E::M], R[E::NR];
 #pragma unroll
-      for (int k = 0; k < E::M; ++k) jet_seed(s[k], (k >= E::SK && k < E::SK + E::NP) ? __ldg(x + (k - E::SK)) : 0.0, k);
+      for (int k = 0; k < E::M; ++k) jet_seed(s[k], (k >= E::SK && k < E::SK + E::NP) ? kap[k - E::SK] : 0.0, k);
       I::res(pc, s, R);
 #pragma unroll
       for (int t = 0; t < E::NB; ++t) {
@@ -279,22 +295,32 @@ __device__ __forceinline__ void accum_A(const Tables<E>& tab, const DevModel& D,
 #pragma unroll
         for (int n = 0; n < E::NP; ++n)
 #pragma unroll
-          for (int m = n; m < E::NP; ++m) { X[t][c] = R[t].h[J2::idx(E::SK + m, E::SK + n)] * w; ++c; }
+          for (int m = n; m < E::NP; ++m) { X[t][c] = zmul(R[t].h[J2::idx(E::SK + m, E::SK + n)], w); ++c; }
       }
     }
+    unsigned bits = 0;  // (t, c) terms that are non-zero on some lane of the warp
 #pragma unroll
     for (int t = 0; t < E::NB; ++t)
 #pragma unroll
-      for (int c = 0; c < AOrder<E, ORDER>::NC; ++c)
-        if (__any_sync(0xffffffffu, X[t][c] != 0.0)) {
+      for (int c = 0; c < NC; ++c)
+        if (!jzero(X[t][c])) bits |= 1u << (t * NC + c);
+    bits = __reduce_or_sync(0xffffffffu, bits);
+#pragma unroll
+    for (int t = 0; t < E::NB; ++t)
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        if ((bits >> (t * NC + c)) & 1u) {
 #pragma unroll
           for (int i = 0; i < E::NY; ++i) acc[c][i] = fma(tab.By[q][i][t], X[t][c], acc[c][i]);
         }
   }
 }
 
+#ifndef PDENLP_KVEC_MINB
+#define PDENLP_KVEC_MINB 2
+#endif
 template <class E, int OP>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, PDENLP_KVEC_MINB)
 k_vector_K(const __grid_constant__ Tables<E> tab, const DevModel D, const double* __restrict__ x,
            const double* __restrict__ lambda, const double* __restrict__ v, double obj_weight, int64_t prows,
            double* __restrict__ out, double* __restrict__ partials) {
@@ -337,7 +363,7 @@ k_vector_K(const __grid_constant__ Tables<E> tab, const DevModel D, const double
     if (NEED_Z) gather_state<E>(D, x, valid, c);
     AR A;
     {
-      const PointCtx pc0 = point_ctx<E>(D, tab, cell, valid, 0, I::NEEDS_COEF_DERIV);
+      const PointGeo<E> pc0 = point_ctx<E>(D, tab, cell, valid, 0, I::NEEDS_COEF_DERIV);
       eval_affine<E, NEED_D1>(pc0, x, A);
     }
     double ey[E::NY], eu[E::NUS];
@@ -374,7 +400,7 @@ k_vector_K(const __grid_constant__ Tables<E> tab, const DevModel D, const double
           for (int k = 0; k < NK; ++k) {
             double a = 0.0;
 #pragma unroll
-            for (int m = 0; m < NP; ++m) a = fma(vk[m], A.D1[t][k][m], a);
+            for (int m = 0; m < NP; ++m) a += zmul(A.D1[t][k][m], vk[m]);
             C1[t][k] = a;
           }
         if (NP > 0) {
@@ -461,7 +487,7 @@ k_vector_K(const __grid_constant__ Tables<E> tab, const DevModel D, const double
             for (int k = 0; k < NK; ++k) {
               double a = 0.0;
 #pragma unroll
-              for (int m = 0; m < NP; ++m) a = fma(vk[m], A.D1[t][k][m], a);
+              for (int m = 0; m < NP; ++m) a += zmul(A.D1[t][k][m], vk[m]);
               Cv[t][k] = a;
             }
 #pragma unroll
@@ -507,18 +533,18 @@ k_vector_K(const __grid_constant__ Tables<E> tab, const DevModel D, const double
         }
       }
       // ---- objective part of hprod!: the Hessian C of f w.r.t. the pointwise fields is point- and state-independent
-      if (OP == OP_HPROD && obj_weight != 0.0) {
+      if (OP == OP_HPROD && !jzero(obj_weight)) {
         using J2 = Jet2<E::M>;
         J2 s[E::M];
 #pragma unroll
         for (int k = 0; k < E::M; ++k) jet_seed(s[k], (k >= E::SK && k < E::SK + NP) ? __ldg(x + (k - E::SK)) : 0.0, k);
-        const PointCtx pc0 = point_ctx<E>(D, tab, cell, valid, 0, I::NEEDS_COEF_DERIV);
+        const PointGeo<E> pc0 = point_ctx<E>(D, tab, cell, valid, 0, I::NEEDS_COEF_DERIV);
         const J2 F = I::f(pc0, s);
         double C[NB][NK];
 #pragma unroll
         for (int t = 0; t < NB; ++t)
 #pragma unroll
-          for (int k = 0; k < NK; ++k) C[t][k] = (k < NB ? F.h[J2::idx(t, k)] : 0.0) * obj_weight;
+          for (int k = 0; k < NK; ++k) C[t][k] = zmul(k < NB ? F.h[J2::idx(t, k)] : 0.0, obj_weight);
         double hy[E::NY], hu[E::NUS];
 #pragma unroll
         for (int a = 0; a < E::NY; ++a) hy[a] = 0.0;
@@ -529,8 +555,8 @@ k_vector_K(const __grid_constant__ Tables<E> tab, const DevModel D, const double
           using KT = KTab<E>;
 #pragma unroll
           for (int l = 0; l < NB; ++l) {
-            const double cul = F.h[J2::idx(E::SU, l)] * obj_weight;
-            if (cul != 0.0) {
+            const double cul = zmul(F.h[J2::idx(E::SU, l)], obj_weight);
+            if (!jzero(cul)) {
 #pragma unroll
               for (int j = 0; j < E::NY; ++j) {
                 double a = 0.0;
@@ -543,8 +569,8 @@ k_vector_K(const __grid_constant__ Tables<E> tab, const DevModel D, const double
               }
             }
           }
-          const double cuu = F.h[J2::idx(E::SU, E::SU)] * obj_weight;
-          if (cuu != 0.0) {
+          const double cuu = zmul(F.h[J2::idx(E::SU, E::SU)], obj_weight);
+          if (!jzero(cuu)) {
 #pragma unroll
             for (int j = 0; j < E::NU; ++j) {
               const double wv = cuu * vu[j];
@@ -559,11 +585,11 @@ k_vector_K(const __grid_constant__ Tables<E> tab, const DevModel D, const double
           for (int m = 0; m < NP; ++m) {
             double a = 0.0;
 #pragma unroll
-            for (int n = 0; n < NP; ++n) a = fma(F.h[J2::idx(E::SK + m, E::SK + n)] * Ks[KT::OFF_VOL], vk[n], a);
+            for (int n = 0; n < NP; ++n) a += zmul(F.h[J2::idx(E::SK + m, E::SK + n)], Ks[KT::OFF_VOL] * vk[n]);
 #pragma unroll
             for (int k = 0; k < NB; ++k) {
               const double ck = F.h[J2::idx(E::SK + m, k)];
-              if (ck != 0.0) {
+              if (!jzero(ck)) {
 #pragma unroll
                 for (int j = 0; j < E::NY; ++j) {
                   a = fma(ck * Ks[KT::y1(k, j)], vy[j], a);
@@ -573,7 +599,7 @@ k_vector_K(const __grid_constant__ Tables<E> tab, const DevModel D, const double
             }
             if (E::NU > 0) {
               const double cu = F.h[J2::idx(E::SK + m, E::SU)];
-              if (cu != 0.0) {
+              if (!jzero(cu)) {
 #pragma unroll
                 for (int b = 0; b < E::NU; ++b) {
                   a = fma(cu * Ks[KT::u1(b)], vu[b], a);

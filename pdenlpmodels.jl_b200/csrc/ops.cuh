@@ -182,7 +182,7 @@ struct OpsImpl : Ops {
   int vec_op(const Launch& L, const DevModel& D, const double* x, const double* lam, const double* v, double ow,
              double* out, double* partials, int g) {
     if constexpr (kvec_enabled<E>() && kvec_op(OP)) {
-      if (!L.generic) {
+      if (!L.generic && D.ktab != nullptr) {
         k_vector_K<E, OP><<<g, kThreads, KTab<E>::TOTAL * 8, L.stream>>>(tab, D, x, lam, v, ow, 0, out, partials);
         CU(cudaGetLastError());
         count_launch(L);
@@ -226,7 +226,7 @@ struct OpsImpl : Ops {
     if constexpr (E::NP > 0) {
       const int g = grid_for(D.ntiles, kWarpsPerCta, L.sms * 8);
       if constexpr (kvec_enabled<E>()) {
-        if (!L.generic) {
+        if (!L.generic && D.ktab != nullptr) {
           k_vector_K<E, OP_JAC_KAPPA><<<g, kThreads, KTab<E>::TOTAL * 8, L.stream>>>(tab, D, x, nullptr, nullptr, 1.0, 0, vk, partials);
           CU(cudaGetLastError());
           count_launch(L);
@@ -259,7 +259,7 @@ struct OpsImpl : Ops {
         done = true;
       }
       if constexpr (kvec_enabled<E>()) {
-        if (!done && which == 1 && !L.generic) {
+        if (!done && which == 1 && !L.generic && D.ktab != nullptr) {
           k_vector_K<E, OP_HESS_KAPPA><<<g, kThreads, KTab<E>::TOTAL * 8, L.stream>>>(tab, D, x, lam, nullptr, 1.0, prows, vk, partials);
           done = true;
         }
@@ -326,10 +326,15 @@ inline int desc_nfu(const pdenlp_desc& d) { return d.nu == 0 ? 0 : (d.nfields_u 
   const int I = (d).integrand, dim = (d).dim, ny = (d).ny, nu = (d).nu, nq = (d).nq, np = (d).nparam;  \
   const int nfy = desc_nfy(d), nfu = desc_nfu(d);                                                       \
   (void)I; (void)dim; (void)ny; (void)nu; (void)nq; (void)np; (void)nfy; (void)nfu
+// (each case exists twice: the uniform fast path, and the per-cell-geometry variant chosen when desc.cell_jinvT is given)
 #define CASE(INT, DIMV, NYV, NUV, NQV, NPV, TYPE)                                                       \
   if (I == INT && dim == DIMV && ny == NYV && nu == NUV && nq == NQV && np == NPV) {                   \
-    using EL = Elem<TYPE, NYV, NUV, NQV>;                                                               \
-    if (nfy == EL::NFY && nfu == EL::NFU) return make_ops<EL>(d);                                       \
+    using EL = Elem<TYPE, NYV, NUV, NQV, false>;                                                        \
+    using ELG = Elem<TYPE, NYV, NUV, NQV, true>;                                                        \
+    if (nfy == EL::NFY && nfu == EL::NFU) {                                                             \
+      if ((d).cell_jinvT != nullptr) return make_ops<ELG>(d);                                           \
+      return make_ops<EL>(d);                                                                           \
+    }                                                                                                   \
   }
 
 // the translation units of the closed set (each returns nullptr when the case is not one of its own)

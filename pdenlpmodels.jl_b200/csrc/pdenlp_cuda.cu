@@ -221,7 +221,7 @@ int self_check(pdenlp_model* m, double* worst_out) {
       CU(cudaMemsetAsync(o, 0, (size_t)n * 8, st));
       Launch L{st, m->sms, pass == 1, nullptr};
       DevModel d = ds;
-      d.notrait = pass;
+      d.notrait = pass | ds.notrait;
       if (int r = run(L, d, o)) return r;
     }
     CU(cudaMemsetAsync(res, 0, 16, st));
@@ -310,6 +310,8 @@ int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
   if (!desc->cell_dofs_y || !desc->phi_y || !desc->grad_y || !desc->wdet) return fail(PDENLP_EINVAL, "missing arrays");
   if (desc->nu > 0 && (!desc->cell_dofs_u || !desc->phi_u)) return fail(PDENLP_EINVAL, "missing control arrays");
   if (desc->ncells + 31 >= ((int64_t)1 << 36)) return fail(PDENLP_EINVAL, "too many cells");
+  if ((desc->cell_jinvT != nullptr) != (desc->cell_detj != nullptr)) return fail(PDENLP_EINVAL, "cell_jinvT and cell_detj must be given together");
+  if (desc->cell_jinvT && desc->geom_nq != 1 && desc->geom_nq != desc->nq) return fail(PDENLP_EINVAL, "geom_nq must be 1 (affine cells) or nq");
   int ndev = 0;
   CU(cudaGetDeviceCount(&ndev));
   if (ndev == 0) return fail(PDENLP_ECUDA, "no CUDA device (libpdenlp_cuda has no CPU fallback)");
@@ -398,6 +400,27 @@ int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
   m->dm.nparam = desc->nparam;
   m->dm.base_jy = m->dm.base_ju = m->dm.base_h = nullptr;
   m->dm.ktab = nullptr;
+  m->dm.jinvT = m->dm.detj = nullptr;
+  m->dm.geom_nq = 0;
+  if (desc->cell_jinvT) {
+    // per-cell geometry, transposed to SoA [g][d][e][ldc] so that a warp (lane = cell) reads whole lines
+    const int gq = desc->geom_nq, dd = desc->dim * desc->dim;
+    std::vector<double> soa((size_t)gq * dd * ldc, 0.0), sdet((size_t)gq * ldc, 0.0);
+    for (int64_t c = 0; c < nc; ++c)
+      for (int g = 0; g < gq; ++g) {
+        const double dj = desc->cell_detj[c * gq + g];
+        if (!(dj > 0.0)) return bail(fail(PDENLP_EINVAL, "cell_detj must be positive (|det J| of the cell map)"));
+        sdet[(size_t)g * ldc + c] = dj;
+        for (int k = 0; k < dd; ++k) soa[((size_t)g * dd + k) * ldc + c] = desc->cell_jinvT[(c * gq + g) * dd + k];
+      }
+    if ((rc = dev_upload(m, soa.data(), soa.size(), &dp))) return bail(rc);
+    m->dm.jinvT = dp;
+    if ((rc = dev_upload(m, sdet.data(), sdet.size(), &dp))) return bail(rc);
+    m->dm.detj = dp;
+    m->dm.geom_nq = gq;
+    // Jacobians that vary inside a cell make every derivative point-dependent: no single-point shortcuts
+    if (gq > 1) m->dm.notrait = 1;
+  }
   if (!ops->ktab().empty()) {
     if ((rc = dev_upload(m, ops->ktab().data(), ops->ktab().size(), &dp))) return bail(rc);
     m->dm.ktab = dp;
@@ -461,6 +484,7 @@ int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
   // the host arrays of the description are not referenced after create
   m->d.cell_dofs_y = m->d.cell_dofs_u = nullptr;
   m->d.dir_y = m->d.dir_u = m->d.phi_y = m->d.grad_y = m->d.phi_u = m->d.wdet = m->d.coef = nullptr;
+  m->d.cell_jinvT = m->d.cell_detj = nullptr;
   m->d.field_nfree = m->d.field_ndir = nullptr;
   cudaSetDevice(prev);
   *out = m;

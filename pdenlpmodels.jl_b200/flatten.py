@@ -50,6 +50,12 @@ class FlatModel:
     nfu: int = 1
     field_nfree: np.ndarray = None
     field_ndir: np.ndarray = None
+    # per-cell geometry (pdenlp_desc ABI v3): None = uniform fast path (grad_y physical, wdet = w * detJ); otherwise
+    # grad_y / wdet are the REFERENCE gradients / weights and cell_jinvT (ncells, geom_nq, dim, dim), cell_detj
+    # (ncells, geom_nq) hold J^-T and |det J| of every cell map (geom_nq = 1: affine cells, = nq: per point)
+    cell_jinvT: Optional[np.ndarray] = None
+    cell_detj: Optional[np.ndarray] = None
+    geom_nq: int = 0
 
     @property
     def nvar(self) -> int:
@@ -60,7 +66,28 @@ class FlatModel:
         return self.nfree_y
 
 
-def _flatten_mf(spec, cell_range, with_coef):
+def _geometry(m, cells, pts, wts, dphi_ref, geometry):
+    """Tables and per-cell geometry of a slab.  geometry: None (automatic: per-cell arrays only for a mapped mesh),
+    "uniform" (the fast path; error for a mapped mesh), "per_point" (J^-T and det J at every quadrature point of every
+    cell, the general case) or "affine" (one per cell, evaluated at the cell centre: exact for parallelotope cells).
+    Returns (grad_y, wdet, cell_jinvT, cell_detj, geom_nq)."""
+    if geometry is None:
+        geometry = "per_point" if m.is_mapped else "uniform"
+    if geometry == "uniform":
+        if m.is_mapped:
+            raise ValueError("a mapped mesh has no uniform geometry")
+        return dphi_ref / m.h, wts * float(np.prod(m.h)), None, None, 0
+    if geometry == "per_point":
+        J, det = m.cell_jacobians(cells, pts)
+    elif geometry == "affine":
+        J, det = m.cell_jacobians(cells, np.full((1, m.dim), 0.5))
+    else:
+        raise ValueError("geometry must be None, 'uniform', 'per_point' or 'affine'")
+    jinvT = np.ascontiguousarray(np.swapaxes(np.linalg.inv(J), -1, -2))  # (J^-1)^T: grad_x = jinvT @ grad_xi
+    return dphi_ref, wts, jinvT, np.ascontiguousarray(det), J.shape[1]
+
+
+def _flatten_mf(spec, cell_range, with_coef, geometry=None):
     m = spec.model
     c0, c1 = (0, m.ncells) if cell_range is None else cell_range
     Ys, Us = list(spec.Yfields), list(spec.Ufields)
@@ -70,11 +97,13 @@ def _flatten_mf(spec, cell_range, with_coef):
     phi_y, dphi_y = lagrange_tables(Ys[0].order, m.dim, pts)
     phi_u = lagrange_tables(Us[0].order, m.dim, pts)[0] if Us else np.zeros((nq, 0))
     ncells = c1 - c0
+    cells = np.arange(c0, c1, dtype=np.int64)
+    grad_y, wdet, jinvT, detj, geom_nq = _geometry(m, cells, pts, wts, dphi_y, geometry)
     if with_coef:
-        idx = m.cell_multi_index(np.arange(c0, c1, dtype=np.int64))
+        XQ = m.physical_points(cells, pts)
         coef = np.zeros((2, ncells, nq))
         for q in range(nq):
-            X = m.lo + (idx + pts[q]) * m.h
+            X = XQ[:, q, :]
             if spec.target is not None:
                 coef[0, :, q] = spec.target(X)
             if spec.source is not None:
@@ -91,17 +120,21 @@ def _flatten_mf(spec, cell_range, with_coef):
         spec=spec, cell0=c0, ncells=ncells, dim=m.dim, ny=Ys[0].nloc, nu=(Us[0].nloc if Us else 0), nq=nq, nparam=0,
         nfree_y=sum(f.nfree for f in Ys), nfree_u=sum(f.nfree for f in Us),
         cell_dofs_y=cat(Ys), cell_dofs_u=cat(Us), dir_y=catd(Ys), dir_u=catd(Us),
-        phi_y=np.ascontiguousarray(phi_y), grad_y=np.ascontiguousarray(dphi_y / m.h), phi_u=np.ascontiguousarray(phi_u),
-        wdet=np.ascontiguousarray(wts * float(np.prod(m.h))), coef=np.ascontiguousarray(coef), params=params,
+        phi_y=np.ascontiguousarray(phi_y), grad_y=np.ascontiguousarray(grad_y), phi_u=np.ascontiguousarray(phi_u),
+        wdet=np.ascontiguousarray(wdet), coef=np.ascontiguousarray(coef), params=params,
         nfy=len(Ys), nfu=len(Us),
         field_nfree=np.array([f.nfree for f in Ys + Us], dtype=np.int64),
         field_ndir=np.array([f.ndirichlet for f in Ys + Us], dtype=np.int64),
+        cell_jinvT=jinvT, cell_detj=detj, geom_nq=geom_nq,
     )
 
 
-def flatten(spec: ProblemSpec, cell_range: Optional[Tuple[int, int]] = None, with_coef: bool = True) -> FlatModel:
+def flatten(spec: ProblemSpec, cell_range: Optional[Tuple[int, int]] = None, with_coef: bool = True,
+            geometry: Optional[str] = None) -> FlatModel:
+    """``geometry``: see _geometry (default: the uniform fast path for a plain Cartesian mesh, per-point cell
+    Jacobians for a mapped one)."""
     if getattr(spec, "is_multifield", False):
-        return _flatten_mf(spec, cell_range, with_coef)
+        return _flatten_mf(spec, cell_range, with_coef, geometry)
     m = spec.model
     c0, c1 = (0, m.ncells) if cell_range is None else cell_range
     Y, U = spec.Ypde, spec.Ycon
@@ -110,19 +143,20 @@ def flatten(spec: ProblemSpec, cell_range: Optional[Tuple[int, int]] = None, wit
     pts, wts = gauss_legendre_01(spec.degree, m.dim)
     nq = pts.shape[0]
     phi_y, dphi_y = lagrange_tables(Y.order, m.dim, pts)
-    grad_y = dphi_y / m.h  # physical gradient for the Cartesian map x = lo + h*(idx + xi)
     if U is not None:
         phi_u, _ = lagrange_tables(U.order, m.dim, pts)
     else:
         phi_u = np.zeros((nq, 0))
-    wdet = wts * float(np.prod(m.h))
-
     ncells = c1 - c0
+    cells = np.arange(c0, c1, dtype=np.int64)
+    # uniform mesh: physical gradients for the Cartesian map x = lo + h*(idx + xi) folded into the tables
+    grad_y, wdet, jinvT, detj, geom_nq = _geometry(m, cells, pts, wts, dphi_y, geometry)
+
     if with_coef:
-        idx = m.cell_multi_index(np.arange(c0, c1, dtype=np.int64))
+        XQ = m.physical_points(cells, pts)
         coef = np.empty((2, ncells, nq))
         for q in range(nq):
-            X = m.lo + (idx + pts[q]) * m.h
+            X = XQ[:, q, :]
             coef[0, :, q] = spec.target(X) if spec.target is not None else 0.0
             coef[1, :, q] = spec.source(X) if spec.source is not None else 0.0
     else:
@@ -142,6 +176,7 @@ def flatten(spec: ProblemSpec, cell_range: Optional[Tuple[int, int]] = None, wit
         nfy=1, nfu=(1 if U is not None else 0),
         field_nfree=np.array([Y.nfree] + ([U.nfree] if U is not None else []), dtype=np.int64),
         field_ndir=np.array([Y.ndirichlet] + ([U.ndirichlet] if U is not None else []), dtype=np.int64),
+        cell_jinvT=jinvT, cell_detj=detj, geom_nq=geom_nq,
     )
 
 

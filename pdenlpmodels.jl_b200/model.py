@@ -101,14 +101,15 @@ class GridapPDENLPModel:
     """
 
     def __init__(self, spec: ProblemSpec, device: str = "cuda:0", cell_range=None, memspace: str = "device",
-                 with_coef: bool = True, flat: Optional[FlatModel] = None, x0=None, lvar=None, uvar=None,
+                 with_coef: bool = True, flat: Optional[FlatModel] = None, geometry: Optional[str] = None,
+                 x0=None, lvar=None, uvar=None,
                  lvary=None, uvary=None, lvaru=None, uvaru=None, lvark=None, uvark=None):
         self.spec = spec
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise ValueError("GridapPDENLPModel needs a CUDA device: the hot path has no CPU implementation")
         self.memspace = memspace
-        fm = flat if flat is not None else flatten(spec, cell_range, with_coef=with_coef)
+        fm = flat if flat is not None else flatten(spec, cell_range, with_coef=with_coef, geometry=geometry)
         self.flat = fm
         ms = capi.MEM_DEVICE if memspace == "device" else capi.MEM_HOST
         self.handle = capi.Handle(fm, device=self.device.index if self.device.index is not None else 0,

@@ -119,7 +119,8 @@ def _h_membrane(X):
     return -np.sin(_OMEGA * X[:, 0]) * np.sin(_OMEGA * X[:, 1])
 
 
-def controlelasticmembrane(n: int = 100, affine: bool = False, degree: int = 1, state_order: int = 2, dim: int = 2) -> ProblemSpec:
+def controlelasticmembrane(n: int = 100, affine: bool = False, degree: int = 1, state_order: int = 2, dim: int = 2,
+                           mesh_map: Optional[Callable] = None) -> ProblemSpec:
     """README 'Control elastic membrane' (README.md:58-98; docstring
     src/GridapPDENLPModel.jl:164-204): Q2 state with Dirichlet boundary, Q1
     control, degree 1, res-function (FEOperatorFromWeakForm) variant.
@@ -127,8 +128,9 @@ def controlelasticmembrane(n: int = 100, affine: bool = False, degree: int = 1, 
     (test/problems/controlelasticmembrane.jl:48-53): same PDE, linear API.
     ``degree`` is the user's `Measure(trian, degree)` (1 in the README; 2 or 3 give 2x2 Gauss points),
     ``state_order`` the order of the state element (2 in the README); ``dim = 3`` is the same problem on (-1,1)^3
-    (yd and h keep depending on x1, x2 only)."""
-    model = CartesianDiscreteModel((-1, 1) * dim, (n,) * dim)
+    (yd and h keep depending on x1, x2 only).  ``mesh_map``: Gridap's ``CartesianDiscreteModel(...; map = f)`` —
+    the vertices are mapped, the cells become general Q1 images (per-cell geometry path)."""
+    model = CartesianDiscreteModel((-1, 1) * dim, (n,) * dim, map=mesh_map)
     Ypde = LagrangianFESpace(model, state_order, "H1", "boundary", 0.0)
     Ycon = LagrangianFESpace(model, 1, "H1")
     return ProblemSpec(
@@ -142,10 +144,10 @@ def controlelasticmembrane(n: int = 100, affine: bool = False, degree: int = 1, 
 
 
 def poissonboltzman2d(n: int = 100, control_conformity: str = "L2", degree: int = 1, dim: int = 2,
-                      state_order: int = 1) -> ProblemSpec:
+                      state_order: int = 1, mesh_map: Optional[Callable] = None) -> ProblemSpec:
     """docs/src/poisson-boltzman.md:30-67: Q1 state, Q1 control (L2 in the
     doc), degree 1, sinh reaction term (``dim = 3``: the same on (-1,1)^3)."""
-    model = CartesianDiscreteModel((-1, 1) * dim, (n,) * dim)
+    model = CartesianDiscreteModel((-1, 1) * dim, (n,) * dim, map=mesh_map)
     Ypde = LagrangianFESpace(model, state_order, "H1", "boundary", 0.0)
     Ycon = LagrangianFESpace(model, 1, control_conformity)
 
@@ -160,18 +162,18 @@ def poissonboltzman2d(n: int = 100, control_conformity: str = "L2", degree: int 
     )
 
 
-def _burger_spaces(n):
-    model = CartesianDiscreteModel((0, 1), n)
+def _burger_spaces(n, mesh_map=None):
+    model = CartesianDiscreteModel((0, 1), n, map=mesh_map)
     # dirichlet_tags = ["diri0", "diri1"] = entities [1], [2]; values 0 and -1
     Ypde = LagrangianFESpace(model, 1, "H1", [1, 2], {1: 0.0, 2: -1.0})
     Ycon = LagrangianFESpace(model, 1, "H1")
     return model, Ypde, Ycon
 
 
-def burger1d(n: int = 512, degree: int = 1) -> ProblemSpec:
+def burger1d(n: int = 512, degree: int = 1, mesh_map: Optional[Callable] = None) -> ProblemSpec:
     """test/problems/burger1d.jl:1-52 (the test-suite variant: dt(y,v) = y' v
     is linear, src/util_functions.jl:109-110)."""
-    model, Ypde, Ycon = _burger_spaces(n)
+    model, Ypde, Ycon = _burger_spaces(n, mesh_map)
     nu = 0.08
     return ProblemSpec(
         name="burger1d",
@@ -182,10 +184,10 @@ def burger1d(n: int = 512, degree: int = 1) -> ProblemSpec:
     )
 
 
-def burger1d_param(n: int = 512, degree: int = 1) -> ProblemSpec:
+def burger1d_param(n: int = 512, degree: int = 1, mesh_map: Optional[Callable] = None) -> ProblemSpec:
     """test/problems/burger1d_param.jl:1-54: nonlinear convection v*y*y',
     one algebraic unknown."""
-    model, Ypde, Ycon = _burger_spaces(n)
+    model, Ypde, Ycon = _burger_spaces(n, mesh_map)
     nu = 0.08
     return ProblemSpec(
         name="burger1d_param",
@@ -196,12 +198,12 @@ def burger1d_param(n: int = 512, degree: int = 1) -> ProblemSpec:
     )
 
 
-def poissonmixed(n: int = 3, dim: int = 2, control: bool = False) -> ProblemSpec:
+def poissonmixed(n: int = 3, dim: int = 2, control: bool = False, mesh_map: Optional[Callable] = None) -> ProblemSpec:
     """test/problems/poissonmixed.jl:14-48 (2 algebraic unknowns, degree 2);
     ``dim=3, control=True`` is BASELINE config 5 (inverse Poisson with kappa +
     3-D Q1 Poisson control)."""
     dom = (0, 1) * dim
-    model = CartesianDiscreteModel(dom, (n,) * dim)
+    model = CartesianDiscreteModel(dom, (n,) * dim, map=mesh_map)
     Ypde = LagrangianFESpace(model, 1, "H1", "boundary", 0.0)
     Ycon = LagrangianFESpace(model, 1, "H1") if control else None
 
