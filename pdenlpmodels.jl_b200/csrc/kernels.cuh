@@ -674,10 +674,14 @@ __device__ __forceinline__ double* emit_hess_u_K(const double* __restrict__ Ks, 
 // the warp's CTA stages the tensors in shared memory once (after the staging buffers)
 template <class E>
 __device__ __forceinline__ const double* load_ktab(const DevModel& D, double* dst) {
-  if (!KTab<E>::ENABLED || D.ktab == nullptr) return nullptr;
-  for (int i = threadIdx.x; i < KTab<E>::TOTAL; i += blockDim.x) dst[i] = __ldg(D.ktab + i);
-  __syncthreads();
-  return dst;
+  if constexpr (KTab<E>::ENABLED) {
+    if (D.ktab == nullptr) return nullptr;
+    for (int i = threadIdx.x; i < KTab<E>::TOTAL; i += blockDim.x) dst[i] = __ldg(D.ktab + i);
+    __syncthreads();
+    return dst;
+  } else {
+    return nullptr;
+  }
 }
 
 template <class E>

@@ -97,7 +97,7 @@ __device__ __forceinline__ void apply_yy(const double* __restrict__ Ks, const do
   if (iso && (!jzero(C0[1][1]) || (TWO && !jzero(C1[1][1])))) {
 #pragma unroll
     for (int j = 0; j < E::NY; ++j) {
-      const double w = TWO ? fma(C1[1][1], v1[j], C0[1][1] * v0[j]) : C0[1][1] * v0[j];
+      const double w = TWO ? zmul(C0[1][1], v0[j]) + zmul(C1[1][1], v1[j]) : C0[1][1] * v0[j];
 #pragma unroll
       for (int i = 0; i < E::NY; ++i) out[i] = fma(Ks[KT::lap(j, i)], w, out[i]);
     }
@@ -110,7 +110,7 @@ __device__ __forceinline__ void apply_yy(const double* __restrict__ Ks, const do
       if ((!gg || !iso) && (!jzero(C0[t][k]) || (TWO && !jzero(C1[t][k])))) {
 #pragma unroll
         for (int j = 0; j < E::NY; ++j) {
-          const double w = TWO ? fma(C1[t][k], v1[j], C0[t][k] * v0[j]) : C0[t][k] * v0[j];
+          const double w = TWO ? zmul(C0[t][k], v0[j]) + zmul(C1[t][k], v1[j]) : C0[t][k] * v0[j];
 #pragma unroll
           for (int i = 0; i < E::NY; ++i) out[i] = fma(Ks[KT::yy(t, k, j, i)], w, out[i]);
         }
@@ -128,7 +128,7 @@ __device__ __forceinline__ void apply_yu(const double* __restrict__ Ks, const do
       if (!jzero(C0[t][E::NB]) || (TWO && !jzero(C1[t][E::NB]))) {
 #pragma unroll
         for (int b = 0; b < E::NU; ++b) {
-          const double w = TWO ? fma(C1[t][E::NB], u1[b], C0[t][E::NB] * u0[b]) : C0[t][E::NB] * u0[b];
+          const double w = TWO ? zmul(C0[t][E::NB], u0[b]) + zmul(C1[t][E::NB], u1[b]) : C0[t][E::NB] * u0[b];
 #pragma unroll
           for (int i = 0; i < E::NY; ++i) out[i] = fma(Ks[KT::yu(t, b, i)], w, out[i]);
         }
@@ -238,7 +238,7 @@ __device__ __forceinline__ void apply_T(const double* __restrict__ Ks, const dou
 // a-type element vectors:  acc[c][i] += sum_q w_q sum_t T_i[t](q) X_t^c(q),  X^c = the c-th requested component of
 // res(s = 0; q): ORDER 0: the value (1 component); ORDER 1: d/dkappa_m (NP components); ORDER 2: d2/dkappa_m dkappa_n,
 // m >= n (NP(NP+1)/2 components).  A (q, t, c) term that vanishes on every lane of the warp is skipped.
-// Must be called by all 32 lanes (warp votes); `valid` masks lanes without a cell.
+// `valid` masks lanes without a cell.
 template <class E, int ORDER>
 struct AOrder {
   static constexpr int NC = ORDER == 0 ? 1 : (ORDER == 1 ? (E::NP > 0 ? E::NP : 1) : (E::NP > 0 ? E::NP * (E::NP + 1) / 2 : 1));
@@ -298,18 +298,12 @@ __device__ __forceinline__ void accum_A(const Tables<E>& tab, const DevModel& D,
           for (int m = n; m < E::NP; ++m) { X[t][c] = zmul(R[t].h[J2::idx(E::SK + m, E::SK + n)], w); ++c; }
       }
     }
-    unsigned bits = 0;  // (t, c) terms that are non-zero on some lane of the warp
+    // (structural zeros are literal zeros after the jets' compile-time folding: their terms vanish from the code)
 #pragma unroll
     for (int t = 0; t < E::NB; ++t)
 #pragma unroll
       for (int c = 0; c < NC; ++c)
-        if (!jzero(X[t][c])) bits |= 1u << (t * NC + c);
-    bits = __reduce_or_sync(0xffffffffu, bits);
-#pragma unroll
-    for (int t = 0; t < E::NB; ++t)
-#pragma unroll
-      for (int c = 0; c < NC; ++c)
-        if ((bits >> (t * NC + c)) & 1u) {
+        if (!jzero(X[t][c])) {
 #pragma unroll
           for (int i = 0; i < E::NY; ++i) acc[c][i] = fma(tab.By[q][i][t], X[t][c], acc[c][i]);
         }
@@ -340,15 +334,16 @@ k_vector_K(const __grid_constant__ Tables<E> tab, const DevModel D, const double
 #pragma unroll
   for (int m = 0; m < NPS; ++m) vk[m] = (NP > 0 && (OP == OP_JPROD || OP == OP_HPROD)) ? __ldg(v + m) : 0.0;
 
-  const int64_t vstride = (int64_t)gridDim.x * kWarpsPerCta;
+  const int nwarps = blockDim.x >> 5;
+  const int64_t vstride = (int64_t)gridDim.x * nwarps;
   Cell<E> c, nx;
   {
-    const int64_t t0 = (int64_t)blockIdx.x * kWarpsPerCta + warp;
+    const int64_t t0 = (int64_t)blockIdx.x * nwarps + warp;
     const int64_t c0 = t0 * 32 + lane;
     const bool v0 = t0 < D.ntiles && c0 < D.ncells;
     load_ids<E>(D, v0 ? c0 : 0, v0, nx);
   }
-  for (int64_t tile = (int64_t)blockIdx.x * kWarpsPerCta + warp; tile < D.ntiles; tile += vstride) {
+  for (int64_t tile = (int64_t)blockIdx.x * nwarps + warp; tile < D.ntiles; tile += vstride) {
     const int64_t cell = tile * 32 + lane;
     const bool valid = cell < D.ncells;
 #pragma unroll
@@ -409,7 +404,7 @@ k_vector_K(const __grid_constant__ Tables<E> tab, const DevModel D, const double
 #pragma unroll
           for (int m = 0; m < NP; ++m)
 #pragma unroll
-            for (int i = 0; i < E::NY; ++i) ey[i] = fma(vk[m], a1[m][i], ey[i]);
+            for (int i = 0; i < E::NY; ++i) ey[i] += zmul(a1[m][i], vk[m]);
         } else {
           apply_yy<E, false>(Ks, A.D, vy, A.D, vy, ey);
           apply_yu<E, false>(Ks, A.D, vu, A.D, vu, ey);
@@ -451,7 +446,7 @@ k_vector_K(const __grid_constant__ Tables<E> tab, const DevModel D, const double
         for (int m = 0; m < NP; ++m) {
           double a = kacc[m];
 #pragma unroll
-          for (int i = 0; i < E::NY; ++i) a = fma(w_e[i], a1[m][i], a);
+          for (int i = 0; i < E::NY; ++i) a += zmul(a1[m][i], w_e[i]);
           if (valid) ksum[m] += a;
         }
       }
@@ -476,7 +471,7 @@ k_vector_K(const __grid_constant__ Tables<E> tab, const DevModel D, const double
         for (int cc = 0; cc < AOrder<E, 2>::NC; ++cc) {
           double a = 0.0;
 #pragma unroll
-          for (int i = 0; i < E::NY; ++i) a = fma(lam_e[i], a2[cc][i], a);
+          for (int i = 0; i < E::NY; ++i) a += zmul(a2[cc][i], lam_e[i]);
           la2[cc] = valid ? a : 0.0;
         }
         if (OP == OP_HPROD) {
@@ -498,8 +493,8 @@ k_vector_K(const __grid_constant__ Tables<E> tab, const DevModel D, const double
           for (int n = 0; n < NP; ++n)
 #pragma unroll
             for (int m = n; m < NP; ++m) {
-              kacc[m] = fma(la2[cc], vk[n], kacc[m]);
-              if (m != n) kacc[n] = fma(la2[cc], vk[m], kacc[n]);
+              kacc[m] += zmul(la2[cc], vk[n]);
+              if (m != n) kacc[n] += zmul(la2[cc], vk[m]);
               ++cc;
             }
 #pragma unroll

@@ -178,12 +178,19 @@ struct OpsImpl : Ops {
   }
   // launches the (generic or reference-tensor) kernel of a dof-indexed callback, then the fixed-order second pass that
   // adds the per-CTA partials of its kappa entries to out[0..p)
+  // threads per CTA of the reference-tensor kernels (tuning knob: PDENLP_KVEC_THREADS = 128 | 256)
+  static int kvec_threads() {
+    static const int t = [] { const char* e = getenv("PDENLP_KVEC_THREADS"); int v = e ? atoi(e) : kThreads; return (v == 64 || v == 128 || v == 256) ? v : kThreads; }();
+    return t;
+  }
+  static int kvec_grid(const DevModel& D, const Launch& L) { return grid_for(D.ntiles, kvec_threads() / 32, L.sms * 8); }
   template <int OP>
   int vec_op(const Launch& L, const DevModel& D, const double* x, const double* lam, const double* v, double ow,
              double* out, double* partials, int g) {
     if constexpr (kvec_enabled<E>() && kvec_op(OP)) {
       if (!L.generic && D.ktab != nullptr) {
-        k_vector_K<E, OP><<<g, kThreads, KTab<E>::TOTAL * 8, L.stream>>>(tab, D, x, lam, v, ow, 0, out, partials);
+        g = kvec_grid(D, L);
+        k_vector_K<E, OP><<<g, kvec_threads(), KTab<E>::TOTAL * 8, L.stream>>>(tab, D, x, lam, v, ow, 0, out, partials);
         CU(cudaGetLastError());
         count_launch(L);
         return add_kappa_partials<OP>(L, partials, g, out);
@@ -227,7 +234,7 @@ struct OpsImpl : Ops {
       const int g = grid_for(D.ntiles, kWarpsPerCta, L.sms * 8);
       if constexpr (kvec_enabled<E>()) {
         if (!L.generic && D.ktab != nullptr) {
-          k_vector_K<E, OP_JAC_KAPPA><<<g, kThreads, KTab<E>::TOTAL * 8, L.stream>>>(tab, D, x, nullptr, nullptr, 1.0, 0, vk, partials);
+          k_vector_K<E, OP_JAC_KAPPA><<<kvec_grid(D, L), kvec_threads(), KTab<E>::TOTAL * 8, L.stream>>>(tab, D, x, nullptr, nullptr, 1.0, 0, vk, partials);
           CU(cudaGetLastError());
           count_launch(L);
           return PDENLP_OK;
@@ -242,7 +249,7 @@ struct OpsImpl : Ops {
   int hess_kappa(const Launch& L, const DevModel& D, const double* x, const double* lam, double ow, int which,
                  int64_t prows, double* vk, double* partials) override {
     if constexpr (E::NP > 0) {
-      const int g = grid_for(D.ntiles, kWarpsPerCta, L.sms * 8);
+      int g = grid_for(D.ntiles, kWarpsPerCta, L.sms * 8);
       constexpr int NKK = E::NP * (E::NP + 1) / 2;
       KappaDst dst;  // the kappa-kappa corner: column j outer, row i >= j inner
       {
@@ -260,7 +267,8 @@ struct OpsImpl : Ops {
       }
       if constexpr (kvec_enabled<E>()) {
         if (!done && which == 1 && !L.generic && D.ktab != nullptr) {
-          k_vector_K<E, OP_HESS_KAPPA><<<g, kThreads, KTab<E>::TOTAL * 8, L.stream>>>(tab, D, x, lam, nullptr, 1.0, prows, vk, partials);
+          g = kvec_grid(D, L);
+          k_vector_K<E, OP_HESS_KAPPA><<<g, kvec_threads(), KTab<E>::TOTAL * 8, L.stream>>>(tab, D, x, lam, nullptr, 1.0, prows, vk, partials);
           done = true;
         }
       }
