@@ -67,6 +67,31 @@ def _ncu_traffic(n, world, kernel="k_jac_coord"):
         return None
 
 
+def bind_to_gpu_numa_node(torch, local: int, world: int):
+    """N > 1 ranks share one host: pin this rank (and the library's host threads, which inherit the mask) to the CPUs
+    of the NUMA node its GPU hangs off, BEFORE the pinned host buffers are allocated (first touch puts them on that
+    node) — otherwise every rank's PCIe traffic crosses the socket interconnect to node 0.  Returns a description."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return {"numa_node": None, "why": "numa_node = -1 (single node or not reported)"}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return {"numa_node": node, "why": "no allowed CPU on that node"}
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus), "pci": bdf}
+    except Exception as e:  # topology files missing: keep the default placement
+        return {"numa_node": None, "why": str(e)[:120]}
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -403,7 +428,11 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU implementation")
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
+    numa = None
     if world > 1:
+        numa = bind_to_gpu_numa_node(torch, local, world)
+        # host threads of the library (zero fill of structurally zero blocks in host buffers): share the cores
+        os.environ.setdefault("PDENLP_HOST_THREADS", str(max(1, min(8, _host_cores() * (2 if numa.get("cpus") else 1) // world))))
         dist.init_process_group("nccl", device_id=torch.device(dev))
 
     t_setup = time.perf_counter()
@@ -478,6 +507,8 @@ def main():
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(args, spec, fm, dev, world, rank, ncell, torch, dist)
+        if e2e is not None and numa is not None:
+            e2e["host_placement"] = numa
     del jvals, hvals
 
     cpu = None
@@ -568,7 +599,8 @@ def run_e2e(args, spec, fm, dev, world, rank, ncell, torch, dist):
     dt = float(t.cpu()[0])
     out = {
         "value": ncell / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
-        "h2d_bytes_per_step": int(8 * (2 * info.nvar + info.ncon)),
+        # (the library stages only the dof ranges this rank's cells touch: pdenlp_cuda.cu in_ptr)
+        "h2d_bytes_per_step": int(nlp.staged_input_bytes(("x", "x", "lambda"))),
         # the constraint FE Hessian block of this problem is structurally zero (affine residual): the library
         # fills it in the host buffer with host threads while the DMA copies the computed blocks
         "d2h_bytes_per_step": int(8 * (info.nnzj + info.nnzh - info.nnzh_fe)),

@@ -320,6 +320,12 @@ int pdenlp_compaction_structure(pdenlp_compaction* p, int64_t* rows, int64_t* co
 /* out_vals[e] = sum of the COO values mapped to compressed entry e (device pointers) */
 int pdenlp_compaction_apply(pdenlp_compaction* p, const double* coo_vals, double* out_vals, void* cuda_stream);
 
+/* Free-dof ranges this handle's cells touch, 0-based half-open, in the concatenated numbering of each space:
+   ranges = {y_lo, y_hi, u_lo, u_hi}.  A PDENLP_MEM_HOST model stages only x[0:p], x[p+y_lo : p+y_hi],
+   x[p+nfree_y+u_lo : p+nfree_y+u_hi] (and lambda[y_lo : y_hi]) of the caller's vectors — a cell slab of a sharded model
+   uploads its own rows of the mesh instead of the whole vector (x and lambda are replicated). */
+int pdenlp_input_ranges(const pdenlp_model* m, int64_t ranges[4]);
+
 /* bench support: number of kernel launches issued by this handle so far, and
    the CUDA-event time (ms) of the most recent callback on the handle's stream */
 int pdenlp_launch_count(const pdenlp_model* m, int64_t* launches);

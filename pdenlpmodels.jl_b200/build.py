@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(CSRC, "libpdenlp_cuda.so")
 # pdenlp_cuda.cu holds the C ABI; the ops_*.cu units instantiate disjoint subsets of the (integrand, element)
 # kernels and are compiled in parallel
 SOURCES = ["pdenlp_cuda.cu", "ops_membrane.cu", "ops_membrane4.cu", "ops_kappa.cu", "ops_misc.cu", "ops_3d.cu", "compaction.cu"]
-HEADERS = ["ops.cuh", "kernels.cuh", "integrands.cuh", "jet.cuh", os.path.join("..", "..", "include", "pdenlp_cuda.h")]
+HEADERS = ["ops.cuh", "kernels.cuh", "kvector.cuh", "kmma.cuh", "integrands.cuh", "jet.cuh", os.path.join("..", "..", "include", "pdenlp_cuda.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",

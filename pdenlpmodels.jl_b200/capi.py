@@ -26,7 +26,7 @@ SYMBOLS = [
     "pdenlp_set_stream", "pdenlp_sync", "pdenlp_malloc", "pdenlp_free", "pdenlp_memcpy_h2d", "pdenlp_memcpy_d2h",
     "pdenlp_host_alloc", "pdenlp_host_free",
     "pdenlp_obj", "pdenlp_objgrad", "pdenlp_objcons", "pdenlp_grad", "pdenlp_cons", "pdenlp_jac_coord", "pdenlp_hess_coord", "pdenlp_hess_coord_obj",
-    "pdenlp_jprod", "pdenlp_jtprod", "pdenlp_hprod", "pdenlp_jac_structure", "pdenlp_hess_structure",
+    "pdenlp_jprod", "pdenlp_jtprod", "pdenlp_hprod", "pdenlp_jac_structure", "pdenlp_hess_structure", "pdenlp_input_ranges",
     "pdenlp_selfcheck_error", "pdenlp_launch_count", "pdenlp_last_kernel_ms", "pdenlp_set_timing",
     "pdenlp_compaction_create", "pdenlp_compaction_destroy", "pdenlp_compaction_nnz",
     "pdenlp_compaction_structure", "pdenlp_compaction_apply",
@@ -112,6 +112,7 @@ def load():
     lib.pdenlp_jac_structure.argtypes = [vp, vp, vp]
     lib.pdenlp_hess_structure.argtypes = [vp, vp, vp]
     lib.pdenlp_selfcheck_error.argtypes = [vp, C.POINTER(dbl)]
+    lib.pdenlp_input_ranges.argtypes = [vp, C.POINTER(i64)]
     lib.pdenlp_launch_count.argtypes = [vp, C.POINTER(i64)]
     lib.pdenlp_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.pdenlp_set_timing.argtypes = [vp, C.c_int32]
@@ -240,6 +241,12 @@ class Handle:
 
     def hess_structure(self, rows, cols):
         check(load().pdenlp_hess_structure(self._h, rows, cols))
+
+    def input_ranges(self):
+        """(y_lo, y_hi, u_lo, u_hi): the free-dof ranges the handle's cells touch (what a host-memspace model stages)."""
+        r = (C.c_int64 * 4)()
+        check(load().pdenlp_input_ranges(self._h, r))
+        return tuple(int(v) for v in r)
 
     def launch_count(self) -> int:
         n = C.c_int64()

@@ -26,6 +26,11 @@ struct FieldIdx {
   static constexpr int DIM = DIM_, NP = NP_;
   static constexpr int NFY = 1, NFU = 1;  // one state field, (at most) one control field
   static constexpr bool NO_FE_OBJ = false;  // true: NoFETerm objective fk(kappa), no integral (see PoissonParam)
+  // true: d res/d(y, grad y, u) and the FE-field Hessian of f are the same in EVERY cell of a uniform mesh — they depend
+  // neither on the state nor on the coefficient fields (an affine residual with constant coefficients, a quadratic
+  // objective); kappa may enter.  Selects the template-tile path of the coordinate kernels (kernels.cuh); like the
+  // other shortcut traits it is verified by the create-time self-check.
+  static constexpr bool FE_DERIVS_CELL_INDEPENDENT = false;
   static constexpr int SY = 0, SG = 1, SU = 1 + DIM_, SK = 2 + DIM_;
   static constexpr int M = 2 + DIM_ + NP_;
 };
@@ -44,6 +49,7 @@ struct Membrane : FieldIdx<DIM_, 0> {
   static constexpr bool NEEDS_COEF_DERIV = false;  // derivatives do not read coefficient fields
   static constexpr bool FE_DERIVS_POINT_INDEPENDENT = true;  // d res/d(y,grad y,u) and the FE-field Hessians are the same at every point of a cell
   static constexpr bool RES_FE_HESSIAN_ZERO = true;  // res is affine in (y, grad y, u): the constraint FE Hessian block is identically zero
+  static constexpr bool FE_DERIVS_CELL_INDEPENDENT = true;
   template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) { return tracking_f<T, I>(c, s); }
   // grad(v).grad(y) - v*u - v*h
   template <class T> PDENLP_HD static void res(const PointCtx& c, const T* s, T* R) {
@@ -76,6 +82,7 @@ template <int DIM_>
 struct WrongTraitPB : PoissonBoltzmann<DIM_> {
   static constexpr bool FE_DERIVS_POINT_INDEPENDENT = true;
   static constexpr bool RES_FE_HESSIAN_ZERO = true;
+  static constexpr bool FE_DERIVS_CELL_INDEPENDENT = true;
 };
 
 struct BurgerLin : FieldIdx<1, 0> {
@@ -84,6 +91,7 @@ struct BurgerLin : FieldIdx<1, 0> {
   static constexpr bool NEEDS_COEF_DERIV = false;
   static constexpr bool FE_DERIVS_POINT_INDEPENDENT = true;  // d res/d(y,grad y,u) and the FE-field Hessians are the same at every point of a cell
   static constexpr bool RES_FE_HESSIAN_ZERO = true;  // res is affine in (y, grad y, u): the constraint FE Hessian block is identically zero
+  static constexpr bool FE_DERIVS_CELL_INDEPENDENT = true;
   template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) { return tracking_f<T, I>(c, s); }
   // -nu*grad(v).grad(y) + (grad(y).1)*v - v*u - v*h
   template <class T> PDENLP_HD static void res(const PointCtx& c, const T* s, T* R) {
@@ -117,6 +125,7 @@ struct KappaPoisson : FieldIdx<DIM_, 2> {
   static constexpr bool NEEDS_COEF_DERIV = true;  // d res / d k2 = -v*f
   static constexpr bool FE_DERIVS_POINT_INDEPENDENT = true;  // d res/d(y,grad y,u) and the FE-field Hessians are the same at every point of a cell
   static constexpr bool RES_FE_HESSIAN_ZERO = true;  // res is affine in (y, grad y, u): the constraint FE Hessian block is identically zero
+  static constexpr bool FE_DERIVS_CELL_INDEPENDENT = true;
   template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) {
     T d = c.target - s[I::SY];
     T a = s[I::SK] - 1.0, b = s[I::SK + 1] - 1.0;
@@ -142,6 +151,7 @@ struct PoissonParam : FieldIdx<DIM_, 1> {
   static constexpr bool NEEDS_COEF_DERIV = false;
   static constexpr bool FE_DERIVS_POINT_INDEPENDENT = true;
   static constexpr bool RES_FE_HESSIAN_ZERO = true;
+  static constexpr bool FE_DERIVS_CELL_INDEPENDENT = true;
   static constexpr bool NO_FE_OBJ = true;
   template <class T> PDENLP_HD static T f(const PointCtx&, const T* s) { return jet_const(0.0, s[0]); }
   template <class T> PDENLP_HD static T fk(const double*, const T* k) {
@@ -184,6 +194,7 @@ struct PenalizedPoisson : FieldIdx<DIM_, 0> {
   static constexpr bool NEEDS_COEF_DERIV = false;
   static constexpr bool FE_DERIVS_POINT_INDEPENDENT = true;  // d res/d(y,grad y,u) and the FE-field Hessians are the same at every point of a cell
   static constexpr bool RES_FE_HESSIAN_ZERO = true;  // res is affine in (y, grad y, u): the constraint FE Hessian block is identically zero
+  static constexpr bool FE_DERIVS_CELL_INDEPENDENT = true;
   // 0.5 * grad(y).grad(y) - w * y
   template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) {
     T a = s[I::SG] * s[I::SG];
@@ -204,6 +215,7 @@ struct BasicUnconstrained : FieldIdx<DIM_, 0> {
   static constexpr bool NEEDS_COEF_DERIV = false;
   static constexpr bool FE_DERIVS_POINT_INDEPENDENT = true;  // d res/d(y,grad y,u) and the FE-field Hessians are the same at every point of a cell
   static constexpr bool RES_FE_HESSIAN_ZERO = true;  // res is affine in (y, grad y, u): the constraint FE Hessian block is identically zero
+  static constexpr bool FE_DERIVS_CELL_INDEPENDENT = true;
   // 0.5 * (ubis - u) * (ubis - u) + 0.5 * y * y
   template <class T> PDENLP_HD static T f(const PointCtx& c, const T* s) {
     T d = c.target - s[I::SU];
@@ -227,6 +239,7 @@ struct MFIdx {
   static constexpr int M = SK;
   static constexpr bool HAS_CONST = false;
   static constexpr bool FE_DERIVS_POINT_INDEPENDENT = false;
+  static constexpr bool FE_DERIVS_CELL_INDEPENDENT = false;
   static constexpr bool NO_FE_OBJ = false;
   PDENLP_HD static constexpr int Y(int f) { return f * NB; }
   PDENLP_HD static constexpr int G(int f, int d = 0) { return f * NB + 1 + d; }

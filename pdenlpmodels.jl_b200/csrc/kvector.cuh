@@ -35,6 +35,24 @@ __host__ __device__ constexpr bool kvec_op(int op) {
   return op == OP_CONS || op == OP_JPROD || op == OP_JTPROD || op == OP_HPROD || op == OP_JAC_KAPPA || op == OP_HESS_KAPPA;
 }
 
+// The reference tensors of the K-path vector kernels travel BY VALUE as a __grid_constant__ kernel parameter (up to
+// 13.6 KB for the 3-D Q1 element; parameters may be 32 KB since CUDA 12.1): like the shape tables they then live in the
+// constant bank and every entry the (fully unrolled, compile-time indexed) mat-vecs use is an immediate c[0x0][..]
+// operand of a DFMA — no LDS, no address arithmetic (a shared-memory copy costs one LDS per FMA: 160 of the
+// 1500 instructions per tile of config 5's jprod!, on top of the staging and the barrier).
+template <class E>
+struct KConst {
+  double v[KTab<E>::TOTAL > 0 ? KTab<E>::TOTAL : 1];
+};
+
+__host__ __device__ constexpr bool kvec_tensors_in_smem(int op) {
+#ifdef PDENLP_KVEC_SMEM
+  return true;
+#else
+  return op == OP_HPROD || op == OP_HESS_KAPPA;
+#endif
+}
+
 template <class E>
 struct AffineRes {
   static constexpr int NB = E::NB, NK = E::NB + 1, NPS = E::NP > 0 ? E::NP : 1;
@@ -315,14 +333,17 @@ __device__ __forceinline__ void accum_A(const Tables<E>& tab, const DevModel& D,
 #endif
 template <class E, int OP>
 __global__ void __launch_bounds__(kThreads, PDENLP_KVEC_MINB)
-k_vector_K(const __grid_constant__ Tables<E> tab, const DevModel D, const double* __restrict__ x,
+k_vector_K(const __grid_constant__ Tables<E> tab, const __grid_constant__ KConst<E> kc, const DevModel D, const double* __restrict__ x,
            const double* __restrict__ lambda, const double* __restrict__ v, double obj_weight, int64_t prows,
            double* __restrict__ out, double* __restrict__ partials) {
   using I = typename E::Integrand;
   using AR = AffineRes<E>;
   constexpr int NB = E::NB, NK = NB + 1, NPS = AR::NPS, NP = E::NP;
+  // Operand source of the reference tensors, per op by measurement (config 5, ms): constant bank (LDCU + DFMA with a
+  // uniform-register operand) jprod! 0.139 / jtprod! 0.156 / hprod! 0.238; shared memory (LDS per FMA) 0.180 / 0.174 / 0.122
   extern __shared__ __align__(16) double smem[];
-  const double* const Ks = load_ktab<E>(D, smem);
+  const double* Ks = kc.v;
+  if constexpr (kvec_tensors_in_smem(OP)) Ks = load_ktab<E>(D, smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NKK = NP > 0 ? NP * (NP + 1) / 2 : 1;
   double ksum[NKK];  // kappa entries (JTPROD/HPROD: NP; HESS_KAPPA: the kappa-kappa corner)

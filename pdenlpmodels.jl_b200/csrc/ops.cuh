@@ -5,6 +5,7 @@
 #include "../../include/pdenlp_cuda.h"
 #include "kernels.cuh"
 #include "kvector.cuh"
+#include "kmma.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -73,6 +74,12 @@ struct Ops {
                          int64_t prows, double* vk, double* partials) = 0;
   virtual bool has_shortcuts() const = 0;  // some trait-selected fast path exists (worth a create-time self-check)
   virtual int run_h() const = 0;
+  virtual int run_jy() const = 0;
+  virtual int run_ju() const = 0;
+  // template tiles (kernels.cuh): which coordinate kernels have the path; per-tile classification against a signature
+  virtual bool tpl_jac_ok() const = 0;
+  virtual bool tpl_hess_ok() const = 0;
+  virtual int tile_class(const DevModel& D, unsigned long long sig_y, unsigned long long sig_u, uint8_t* cls, cudaStream_t s) = 0;
   virtual bool needs_coef_deriv() const = 0;  // derivative callbacks read the coefficient fields
   virtual bool res_fe_hessian_zero() const = 0;  // constraint FE Hessian block is structurally zero
   virtual bool no_fe_obj() const = 0;            // NoFETerm objective fk(kappa)
@@ -91,6 +98,7 @@ struct OpsImpl : Ops {
   Tables<E> tab;
   bool attr_done = false;
   std::vector<double> ktab_;
+  KConst<E> kc;  // the same tensors as a by-value kernel parameter (K-path vector kernels)
   const std::vector<double>& ktab() const override { return ktab_; }
   // per-warp staging = (buffer size) x (number of rotating buffers, > 1 only for small elements)
   static constexpr int STJ = jac_stage_doubles<E>() * coord_nbuf(jac_stage_doubles<E>());
@@ -122,13 +130,22 @@ struct OpsImpl : Ops {
     return PDENLP_OK;
   }
   int run_h() const override { return E::RUN_H; }
+  int run_jy() const override { return E::RUN_JY; }
+  int run_ju() const override { return E::RUN_JU; }
+  bool tpl_jac_ok() const override { return tpl_ok<E, false>(); }
+  bool tpl_hess_ok() const override { return tpl_ok<E, true>(); }
+  int tile_class(const DevModel& D, unsigned long long sig_y, unsigned long long sig_u, uint8_t* cls, cudaStream_t s) override {
+    k_tile_class<E><<<grid_for(D.ntiles, kWarpsPerCta, 1 << 30), kThreads, 0, s>>>(D, sig_y, sig_u, cls);
+    CU(cudaGetLastError());
+    return PDENLP_OK;
+  }
   bool needs_coef_deriv() const override { return E::Integrand::NEEDS_COEF_DERIV; }
   bool res_fe_hessian_zero() const override { return E::Integrand::RES_FE_HESSIAN_ZERO; }
   bool no_fe_obj() const override { return E::Integrand::NO_FE_OBJ; }
   bool is_multi() const override { return E::MULTI; }
   bool has_shortcuts() const override {
     using I = typename E::Integrand;
-    return I::RES_FE_HESSIAN_ZERO || (KTab<E>::ENABLED && I::FE_DERIVS_POINT_INDEPENDENT);
+    return I::RES_FE_HESSIAN_ZERO || (KTab<E>::ENABLED && I::FE_DERIVS_POINT_INDEPENDENT) || tpl_ok<E, false>() || tpl_ok<E, true>();
   }
   int nofe(const Launch& L, int mode, const double* x, double ow, const double* v, double* out) override {
     if constexpr (E::Integrand::NO_FE_OBJ) {
@@ -183,14 +200,31 @@ struct OpsImpl : Ops {
     static const int t = [] { const char* e = getenv("PDENLP_KVEC_THREADS"); int v = e ? atoi(e) : kThreads; return (v == 64 || v == 128 || v == 256) ? v : kThreads; }();
     return t;
   }
-  static int kvec_grid(const DevModel& D, const Launch& L) { return grid_for(D.ntiles, kvec_threads() / 32, L.sms * 8); }
+  static constexpr size_t kvec_smem(int op) { return kvec_tensors_in_smem(op) ? KTab<E>::TOTAL * 8 : 0; }
+  // which ops run on the FP64 tensor cores (kmma.cuh) rather than lane = cell (kvector.cuh): by measurement on config 5
+  // (ms, tensor-core / lane = cell): cons! 0.12 / 0.15, hess_coord! kappa trapezoid 0.87 / 0.94 (whole callback),
+  // jprod! 0.17 / 0.14, jtprod! 0.17 / 0.16, hprod! 0.20 / 0.12, jac_coord! kappa block 0.61 / 0.57 (whole callback)
+  static constexpr bool use_mma(int op) {
+#ifdef PDENLP_KMMA_ALL
+    return kmma_enabled<E>();
+#else
+    return kmma_enabled<E>() && (op == OP_CONS || op == OP_HESS_KAPPA);
+#endif
+  }
+  static int kvec_grid(const DevModel& D, const Launch& L, int op) {
+    // tensor-core kernels: one wave of resident CTAs (their per-CTA prologue builds the B fragments)
+    return grid_for(D.ntiles, kvec_threads() / 32, L.sms * (use_mma(op) ? PDENLP_KMMA_MINB : 8));
+  }
   template <int OP>
   int vec_op(const Launch& L, const DevModel& D, const double* x, const double* lam, const double* v, double ow,
              double* out, double* partials, int g) {
     if constexpr (kvec_enabled<E>() && kvec_op(OP)) {
       if (!L.generic && D.ktab != nullptr) {
-        g = kvec_grid(D, L);
-        k_vector_K<E, OP><<<g, kvec_threads(), KTab<E>::TOTAL * 8, L.stream>>>(tab, D, x, lam, v, ow, 0, out, partials);
+        g = kvec_grid(D, L, OP);
+        if constexpr (use_mma(OP))  // FP64 tensor-core version (kmma.cuh)
+          k_vector_M<E, OP><<<g, kvec_threads(), 0, L.stream>>>(tab, kc, D, x, lam, v, ow, 0, out, partials);
+        else
+          k_vector_K<E, OP><<<g, kvec_threads(), kvec_smem(OP), L.stream>>>(tab, kc, D, x, lam, v, ow, 0, out, partials);
         CU(cudaGetLastError());
         count_launch(L);
         return add_kappa_partials<OP>(L, partials, g, out);
@@ -234,7 +268,10 @@ struct OpsImpl : Ops {
       const int g = grid_for(D.ntiles, kWarpsPerCta, L.sms * 8);
       if constexpr (kvec_enabled<E>()) {
         if (!L.generic && D.ktab != nullptr) {
-          k_vector_K<E, OP_JAC_KAPPA><<<kvec_grid(D, L), kvec_threads(), KTab<E>::TOTAL * 8, L.stream>>>(tab, D, x, nullptr, nullptr, 1.0, 0, vk, partials);
+          if constexpr (use_mma(OP_JAC_KAPPA))
+            k_vector_M<E, OP_JAC_KAPPA><<<kvec_grid(D, L, OP_JAC_KAPPA), kvec_threads(), 0, L.stream>>>(tab, kc, D, x, nullptr, nullptr, 1.0, 0, vk, partials);
+          else
+            k_vector_K<E, OP_JAC_KAPPA><<<kvec_grid(D, L, OP_JAC_KAPPA), kvec_threads(), kvec_smem(OP_JAC_KAPPA), L.stream>>>(tab, kc, D, x, nullptr, nullptr, 1.0, 0, vk, partials);
           CU(cudaGetLastError());
           count_launch(L);
           return PDENLP_OK;
@@ -267,8 +304,11 @@ struct OpsImpl : Ops {
       }
       if constexpr (kvec_enabled<E>()) {
         if (!done && which == 1 && !L.generic && D.ktab != nullptr) {
-          g = kvec_grid(D, L);
-          k_vector_K<E, OP_HESS_KAPPA><<<g, kvec_threads(), KTab<E>::TOTAL * 8, L.stream>>>(tab, D, x, lam, nullptr, 1.0, prows, vk, partials);
+          g = kvec_grid(D, L, OP_HESS_KAPPA);
+          if constexpr (use_mma(OP_HESS_KAPPA))
+            k_vector_M<E, OP_HESS_KAPPA><<<g, kvec_threads(), 0, L.stream>>>(tab, kc, D, x, lam, nullptr, 1.0, prows, vk, partials);
+          else
+            k_vector_K<E, OP_HESS_KAPPA><<<g, kvec_threads(), kvec_smem(OP_HESS_KAPPA), L.stream>>>(tab, kc, D, x, lam, nullptr, 1.0, prows, vk, partials);
           done = true;
         }
       }
@@ -319,7 +359,10 @@ Ops* make_ops(const pdenlp_desc& d) {
       }
       for (int b = 0; b < E::NU; ++b) o->ktab_[KT::u1(b)] += w * T.Bu[q][b];
       o->ktab_[KT::OFF_VOL] += w;
+      for (int t = 0; t < E::NB; ++t)
+        for (int i = 0; i < E::NY; ++i) o->ktab_[KT::bt(t, q, i)] = w * T.By[q][i][t];
     }
+    for (int i = 0; i < KT::TOTAL; ++i) o->kc.v[i] = o->ktab_[i];
   }
   return o;
 }

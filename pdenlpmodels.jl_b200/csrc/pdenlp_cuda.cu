@@ -61,6 +61,18 @@ struct pdenlp_model {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
   double selfcheck_err = 0.0;  // worst relative disagreement fast path vs generic path seen by the create-time self-check
+  // free-dof ranges [lo, hi) (0-based, concatenated numbering) the cells of this handle touch: a PDENLP_MEM_HOST model
+  // stages only these parts of x / lambda / v (a slab of a sharded model needs its own rows of the mesh, not the whole vector)
+  int64_t yr[2] = {0, 0}, ur[2] = {0, 0};
+  // template tiles (kernels.cuh): classification lists (host copies for the self-check's sample), image scratch
+  bool tpl_active = false;
+  int32_t tpl_tile = -1;
+  std::vector<int32_t> tpl_list_h, gen_list_h;
+  double *tpl_jy = nullptr, *tpl_ju = nullptr, *tpl_h = nullptr;
+  int64_t* zero_base = nullptr;
+  bool tpl_j_valid = false, tpl_h_valid = false;  // cached images (integrands without kappa: independent of x)
+  double tpl_h_ow = 0.0;
+  int64_t tpl_builds = 0;
 };
 
 namespace {
@@ -100,12 +112,30 @@ int ensure_out(pdenlp_model* m, int64_t n) {
   return PDENLP_OK;
 }
 
-// resolve an input vector to a device pointer (staging it for PDENLP_MEM_HOST)
-int in_ptr(pdenlp_model* m, const double* user, int64_t n, pdenlp_model::Stage* stage, const double** dev) {
+// resolve an input vector to a device pointer (staging it for PDENLP_MEM_HOST).  layout: 0 = x-layout [kappa | y | u]
+// (nvar entries), 1 = constraint layout (ncon entries, the free dofs of the test space = state ids).  Only the
+// entries the handle's cells can read are copied (see yr / ur).
+enum { LAYOUT_X = 0, LAYOUT_C = 1 };
+int in_ptr(pdenlp_model* m, const double* user, int64_t n, pdenlp_model::Stage* stage, const double** dev, int layout = LAYOUT_X) {
   if (user == nullptr) { *dev = nullptr; return PDENLP_OK; }
   if (m->d.memspace == PDENLP_MEM_DEVICE) { *dev = user; return PDENLP_OK; }
   if (int rc = ensure_stage(m, stage, n)) return rc;
-  CU(cudaMemcpyAsync(stage->p, user, n * 8, cudaMemcpyHostToDevice, m->stream));
+  auto part = [&](int64_t lo, int64_t hi) -> int {
+    lo = std::max<int64_t>(lo, 0); hi = std::min<int64_t>(hi, n);
+    if (hi > lo) CU(cudaMemcpyAsync(stage->p + lo, user + lo, (size_t)(hi - lo) * 8, cudaMemcpyHostToDevice, m->stream));
+    return PDENLP_OK;
+  };
+  static const bool whole = getenv("PDENLP_STAGE_WHOLE") != nullptr;  // A/B switch
+  if (whole) {
+    if (int rc = part(0, n)) return rc;
+  } else if (layout == LAYOUT_C) {
+    if (int rc = part(m->yr[0], m->yr[1])) return rc;
+  } else {
+    const int64_t p = m->d.nparam, ny = m->d.nfree_y;
+    if (int rc = part(0, p)) return rc;
+    if (int rc = part(p + m->yr[0], p + m->yr[1])) return rc;
+    if (int rc = part(p + ny + m->ur[0], p + ny + m->ur[1])) return rc;
+  }
   *dev = stage->p;
   return PDENLP_OK;
 }
@@ -174,6 +204,100 @@ int zero_fill(pdenlp_model* m, double* p, int64_t n, bool overlap_previous = fal
   return PDENLP_OK;
 }
 
+// Image of one template tile (kernels.cuh, "template tiles"): the ordinary coordinate kernel on a one-tile sub-model
+// (the model's own arrays, offset to the template tile) writes the tile's run into model-owned scratch.  Integrands
+// without algebraic unknowns have x-independent images, which are cached (the Hessian image per obj_weight).
+int build_template(pdenlp_model* m, bool hess, const double* dx, double ow) {
+  if (!m->tpl_active) return PDENLP_OK;
+  if (hess ? !m->ops->tpl_hess_ok() : !m->ops->tpl_jac_ok()) return PDENLP_OK;
+  const bool cacheable = m->d.nparam == 0;
+  if (cacheable && (hess ? (m->tpl_h_valid && m->tpl_h_ow == ow) : m->tpl_j_valid)) return PDENLP_OK;
+  DevModel dt = m->dm;
+  const int64_t off = (int64_t)m->tpl_tile * 32;
+  dt.dofs_y += off;
+  dt.dofs_u += off;
+  if (dt.coef) dt.coef += off * m->d.nq;  // [field][cell][q]; ncells_coef keeps the field stride
+  dt.ncells = 32;
+  dt.ntiles = 1;
+  dt.base_jy = dt.base_ju = dt.base_h = m->zero_base;
+  dt.tpl_list = dt.gen_list = nullptr;
+  dt.ntpl = 0; dt.ngen = 1;
+  Launch L{m->stream, m->sms, false, &m->launches};
+  if (hess) {
+    if (int rc = m->ops->hess(L, dt, dx, nullptr, ow, m->tpl_h, nullptr)) return rc;
+    m->tpl_h_valid = cacheable; m->tpl_h_ow = ow;
+  } else {
+    if (int rc = m->ops->jac(L, dt, dx, m->tpl_jy, m->tpl_ju)) return rc;
+    m->tpl_j_valid = cacheable;
+  }
+  m->tpl_builds += 1;
+  return PDENLP_OK;
+}
+
+// Classify the tiles once at create time: the template pattern is the id-order signature of an all-free cell near the
+// middle of the slab; a tile is a template tile iff all its 32 cells carry it.  Used only when it pays (>= 25 % of the tiles).
+int classify_tiles(pdenlp_model* m, const pdenlp_desc& desc) {
+  static const bool off = getenv("PDENLP_NO_TEMPLATE") != nullptr;  // experiments / A-B runs
+  if (off || !(m->ops->tpl_jac_ok() || m->ops->tpl_hess_ok())) return PDENLP_OK;
+  const int64_t nc = desc.ncells;
+  const int ny = desc.ny, nu = desc.nu;
+  auto signature = [&](int64_t c, unsigned long long& sy, unsigned long long& su) -> bool {
+    sy = su = 0ull;
+    for (int a = 0; a < ny; ++a) {
+      const int32_t ga = desc.cell_dofs_y[c * ny + a];
+      if (ga <= 0) return false;
+      unsigned r = 0;
+      for (int b = 0; b < ny; ++b) r += desc.cell_dofs_y[c * ny + b] < ga;
+      sy |= (unsigned long long)(r & 15u) << (4 * (a & 15));
+    }
+    for (int a = 0; a < nu; ++a) {
+      const int32_t ga = desc.cell_dofs_u[c * nu + a];
+      if (ga <= 0) return false;
+      unsigned r = 0;
+      for (int b = 0; b < nu; ++b) r += desc.cell_dofs_u[c * nu + b] < ga;
+      su |= (unsigned long long)(r & 15u) << (4 * (a & 15));
+    }
+    return true;
+  };
+  unsigned long long sy = 0, su = 0;
+  bool found = false;
+  for (int64_t c = nc / 2; c < nc && c < nc / 2 + 65536 && !found; ++c) found = signature(c, sy, su);
+  if (!found) return PDENLP_OK;
+  const int64_t nt = m->dm.ntiles;
+  uint8_t* dcls = nullptr;
+  CU(cudaMalloc((void**)&dcls, (size_t)nt));
+  int rc = m->ops->tile_class(m->dm, sy, su, dcls, nullptr);
+  std::vector<uint8_t> cls((size_t)nt);
+  cudaError_t e = cudaMemcpy(cls.data(), dcls, (size_t)nt, cudaMemcpyDeviceToHost);
+  cudaFree(dcls);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(PDENLP_ECUDA, std::string("tile classification: ") + cudaGetErrorString(e));
+  for (int64_t t = 0; t < nt; ++t) (cls[t] ? m->tpl_list_h : m->gen_list_h).push_back((int32_t)t);
+  // (small slabs: the per-CTA image load would cost more than it saves)
+  if ((int64_t)m->tpl_list_h.size() * 4 < nt || nt < 4096) { m->tpl_list_h.clear(); m->gen_list_h.clear(); return PDENLP_OK; }
+  m->tpl_tile = m->tpl_list_h[0];
+  int32_t* ip;
+  if (int r = dev_upload(m, m->tpl_list_h.data(), m->tpl_list_h.size(), &ip)) return r;
+  m->dm.tpl_list = ip;
+  if (int r = dev_upload(m, m->gen_list_h.data(), m->gen_list_h.size(), &ip)) return r;
+  m->dm.gen_list = ip;
+  m->dm.ntpl = (int32_t)m->tpl_list_h.size();
+  m->dm.ngen = (int32_t)m->gen_list_h.size();
+  auto scratch = [&](double** p, int run) -> int {
+    CU(cudaMalloc((void**)p, (size_t)std::max(32 * run, 2) * 8));
+    m->owned.push_back(*p);
+    return PDENLP_OK;
+  };
+  if (int r = scratch(&m->tpl_jy, m->ops->run_jy())) return r;
+  if (int r = scratch(&m->tpl_ju, m->ops->run_ju())) return r;
+  if (int r = scratch(&m->tpl_h, m->ops->run_h())) return r;
+  m->dm.tpl_jy = m->tpl_jy; m->dm.tpl_ju = m->tpl_ju; m->dm.tpl_h = m->tpl_h;
+  const int64_t z[2] = {0, 0};
+  if (int r = dev_upload(m, z, 2, &m->zero_base)) return r;
+  m->tpl_active = true;
+  return PDENLP_OK;
+}
+
 // Create-time self-check of the trait-selected shortcuts (RES_FE_HESSIAN_ZERO: the constraint FE Hessian block is a
 // zero fill; FE_DERIVS_POINT_INDEPENDENT: the coordinate kernels evaluate one quadrature point and use the
 // pre-integrated reference tensors; both: the reference-tensor vector / kappa-block kernels of kvector.cuh).  The traits
@@ -184,10 +308,16 @@ int self_check(pdenlp_model* m, double* worst_out) {
   if (worst_out) *worst_out = 0.0;
   if (skip || !m->ops->has_shortcuts()) return PDENLP_OK;
   const pdenlp_info& I = m->info;
-  const int64_t ns = std::min<int64_t>(m->dm.ncells, 2048);
+  // (the sample is a prefix of the slab; it is extended to contain the first template tiles when there are any)
+  int64_t ns = std::min<int64_t>(m->dm.ncells, 2048);
+  if (m->tpl_active) ns = std::min<int64_t>(m->dm.ncells, std::max<int64_t>(ns, ((int64_t)m->tpl_tile + 24) * 32));
   DevModel ds = m->dm;
   ds.ncells = ns;
   ds.ntiles = (int32_t)((ns + 31) / 32);
+  if (m->tpl_active) {
+    ds.ntpl = (int32_t)(std::lower_bound(m->tpl_list_h.begin(), m->tpl_list_h.end(), ds.ntiles) - m->tpl_list_h.begin());
+    ds.ngen = (int32_t)(std::lower_bound(m->gen_list_h.begin(), m->gen_list_h.end(), ds.ntiles) - m->gen_list_h.begin());
+  }
   // sizes of the sample's COO runs = segment offsets of the first tile after the sample
   int64_t njy = 0, nju = 0, nh = 0;
   CU(cudaMemcpy(&njy, m->dm.base_jy + ds.ntiles, 8, cudaMemcpyDeviceToHost));
@@ -237,8 +367,11 @@ int self_check(pdenlp_model* m, double* worst_out) {
   };
   Ops* ops = m->ops;
   const bool coef = m->dm.coef != nullptr, need = ops->needs_coef_deriv();
-  if (!rc && (coef || !need) && I.ncon > 0)
-    rc = compare("jac_coord", njy + nju, [&](const Launch& L, const DevModel& d, double* o) { return ops->jac(L, d, x, o, o + njy); });
+  if (!rc && (coef || !need) && I.ncon > 0) {
+    rc = build_template(m, false, x, 1.0);
+    if (!rc) rc = compare("jac_coord", njy + nju, [&](const Launch& L, const DevModel& d, double* o) { return ops->jac(L, d, x, o, o + njy); });
+  }
+  if (!rc && (coef || !need) && !m->nofe) rc = build_template(m, true, x, 0.37);
   if (!rc && (coef || !need))
     rc = compare("hess_coord", (m->nofe ? 1 : 2) * nh, [&](const Launch& L, const DevModel& d, double* o) {
       // generic pass: both FE blocks are computed; shortcut pass: what pdenlp_hess_coord does (zero fill of a
@@ -361,23 +494,26 @@ int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
   }
   // SoA transpose of the cell->dof maps, validating the per-field ids against the declared sizes and
   // renumbering them to the concatenated ids of the space
-  auto upload_ids = [&](const int32_t* ids, int nloc_total, int nloc_field, int f0, const char* what, const int32_t** out_ptr) -> int {
+  auto upload_ids = [&](const int32_t* ids, int nloc_total, int nloc_field, int f0, const char* what, const int32_t** out_ptr, int64_t* range) -> int {
     std::vector<int32_t> soa((size_t)ldc * std::max(nloc_total, 1), -1);
+    int64_t lo = INT64_MAX, hi = 0;
     for (int64_t c = 0; c < nc; ++c)
       for (int a = 0; a < nloc_total; ++a) {
         const int f = f0 + a / nloc_field;
         const int64_t g = ids[c * nloc_total + a];
         if (g == 0 || g > fnf[f] || -g > fnd[f]) return fail(PDENLP_EINVAL, std::string(what) + " dof id out of range");
         soa[(size_t)a * ldc + c] = (int32_t)(g > 0 ? g + offf[f] : g - offd[f]);
+        if (g > 0) { lo = std::min(lo, g + offf[f] - 1); hi = std::max(hi, g + offf[f]); }
       }
+    range[0] = hi > 0 ? lo : 0; range[1] = hi;
     int32_t* p;
     if (int r = dev_upload(m, soa.data(), soa.size(), &p)) return r;
     *out_ptr = p;
     return PDENLP_OK;
   };
   if (desc->nfree_y >= ((int64_t)1 << 31) || desc->nfree_u >= ((int64_t)1 << 31)) return bail(fail(PDENLP_EINVAL, "too many dofs for int32 ids"));
-  if ((rc = upload_ids(desc->cell_dofs_y, ny, desc->ny, 0, "state", &m->dm.dofs_y))) return bail(rc);
-  if ((rc = upload_ids(desc->cell_dofs_u, nu, std::max(desc->nu, 1), nfy, "control", &m->dm.dofs_u))) return bail(rc);
+  if ((rc = upload_ids(desc->cell_dofs_y, ny, desc->ny, 0, "state", &m->dm.dofs_y, m->yr))) return bail(rc);
+  if ((rc = upload_ids(desc->cell_dofs_u, nu, std::max(desc->nu, 1), nfy, "control", &m->dm.dofs_u, m->ur))) return bail(rc);
   double* dp;
   if ((rc = dev_upload(m, desc->dir_y, (size_t)desc->ndir_y, &dp))) return bail(rc);
   m->dm.dir_y = dp;
@@ -400,6 +536,9 @@ int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
   m->dm.nparam = desc->nparam;
   m->dm.base_jy = m->dm.base_ju = m->dm.base_h = nullptr;
   m->dm.ktab = nullptr;
+  m->dm.tpl_list = m->dm.gen_list = nullptr;
+  m->dm.ntpl = 0; m->dm.ngen = 0;
+  m->dm.tpl_jy = m->dm.tpl_ju = m->dm.tpl_h = nullptr;
   m->dm.jinvT = m->dm.detj = nullptr;
   m->dm.geom_nq = 0;
   if (desc->cell_jinvT) {
@@ -480,6 +619,7 @@ int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
   m->owned.push_back(m->scalar);
   if (cudaEventCreate(&m->ev0) != cudaSuccess || cudaEventCreate(&m->ev1) != cudaSuccess)
     return bail(fail(PDENLP_ECUDA, "cudaEventCreate failed"));
+  if ((rc = classify_tiles(m, *desc))) return bail(rc);
   if ((rc = self_check(m, &m->selfcheck_err))) return bail(rc);
   // the host arrays of the description are not referenced after create
   m->d.cell_dofs_y = m->d.cell_dofs_u = nullptr;
@@ -564,8 +704,8 @@ static int vec_call(pdenlp_model* m, int op, const double* x, const double* lam,
   const double *dx, *dl, *dv;
   double* dout;
   if (int rc = in_ptr(m, x, m->info.nvar, &m->sx, &dx)) return rc;
-  if (int rc = in_ptr(m, lam, m->info.ncon, &m->slam, &dl)) return rc;
-  if (int rc = in_ptr(m, v, nv, &m->sv, &dv)) return rc;
+  if (int rc = in_ptr(m, lam, m->info.ncon, &m->slam, &dl, LAYOUT_C)) return rc;
+  if (int rc = in_ptr(m, v, nv, &m->sv, &dv, op == OP_JTPROD ? LAYOUT_C : LAYOUT_X)) return rc;
   if (int rc = out_ptr(m, out, nout, &dout)) return rc;
   CU(cudaMemsetAsync(dout, 0, (size_t)nout * 8, m->stream));  // assemble_vector!/coo_prod! zero-fill first
   Launch L{m->stream, m->sms, false, &m->launches};
@@ -649,6 +789,7 @@ int pdenlp_jac_coord(pdenlp_model* m, const double* x, double* vals) {
   }
   double* vy = dv + m->info.nnzj_k;
   double* vu = vy + m->info.nnzj_y;
+  if (int rc = build_template(m, false, dx, 1.0)) return rc;
   if (int rc = m->ops->jac(L, m->dm, dx, vy, vu)) return rc;
   return out_finish(m, vals, m->info.nnzj);
 }
@@ -659,7 +800,7 @@ int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda, do
   const double *dx, *dl;
   double* dv;
   if (int rc = in_ptr(m, x, m->info.nvar, &m->sx, &dx)) return rc;
-  if (int rc = in_ptr(m, lambda, m->info.ncon, &m->slam, &dl)) return rc;
+  if (int rc = in_ptr(m, lambda, m->info.ncon, &m->slam, &dl, LAYOUT_C)) return rc;
   if (int rc = out_ptr(m, vals, m->info.nnzh, &dv)) return rc;
   if (m->ops->needs_coef_deriv() && !m->dm.coef) return fail(PDENLP_EINVAL, "this integrand's derivatives need the coefficient fields (desc.coef)");
   Launch L{m->stream, m->sms, false, &m->launches};
@@ -702,6 +843,7 @@ int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda, do
     vo = nullptr;
   }
   if (vo || vc) {
+    if (vo && !vc) { if (int rc = build_template(m, true, dx, obj_weight)) return rc; }
     if (int rc = m->ops->hess(L, m->dm, dx, dl, obj_weight, vo, vc)) return rc;
   }
   if (cons_zero && !host_tail && pdl) {
@@ -733,6 +875,7 @@ int pdenlp_hess_coord_obj(pdenlp_model* m, const double* x, double obj_weight, d
     }
   }
   if (!m->nofe) {
+    if (int rc = build_template(m, true, dx, obj_weight)) return rc;
     if (int rc = m->ops->hess(L, m->dm, dx, nullptr, obj_weight, dv + I.nnzh_k_obj, nullptr)) return rc;
   }
   return out_finish(m, vals, I.nnzh_obj);
@@ -799,6 +942,11 @@ int pdenlp_hess_structure(pdenlp_model* m, int64_t* rows, int64_t* cols) { retur
 int pdenlp_selfcheck_error(const pdenlp_model* m, double* max_rel_err) {
   if (!m || !max_rel_err) return fail(PDENLP_EINVAL, "null argument");
   *max_rel_err = m->selfcheck_err;
+  return PDENLP_OK;
+}
+int pdenlp_input_ranges(const pdenlp_model* m, int64_t ranges[4]) {
+  if (!m || !ranges) return fail(PDENLP_EINVAL, "null argument");
+  ranges[0] = m->yr[0]; ranges[1] = m->yr[1]; ranges[2] = m->ur[0]; ranges[3] = m->ur[1];
   return PDENLP_OK;
 }
 int pdenlp_launch_count(const pdenlp_model* m, int64_t* launches) {

@@ -198,6 +198,14 @@ class GridapPDENLPModel:
     def launch_count(self) -> int:
         return self.handle.launch_count()
 
+    def staged_input_bytes(self, vectors=("x",)) -> int:
+        """Bytes a host-memspace model copies to the device for the given input vectors ("x" / "v": x-layout,
+        "lambda": constraint layout): only the dof ranges its cells touch are staged."""
+        ylo, yhi, ulo, uhi = self.handle.input_ranges()
+        p = int(self.spec.nparam)
+        per = {"x": p + (yhi - ylo) + (uhi - ulo), "v": p + (yhi - ylo) + (uhi - ulo), "lambda": yhi - ylo}
+        return 8 * sum(per[v] for v in vectors)
+
     def _new(self, n, like=None, dtype=torch.float64):
         if self.memspace == "device":
             return torch.empty(n, dtype=dtype, device=self.device)

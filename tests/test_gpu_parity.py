@@ -169,6 +169,41 @@ def test_host_memspace_matches_device(case, pkg):
     nlp_h.close()
 
 
+def test_host_memspace_slab_stages_only_its_dof_ranges(pkg):
+    """A cell slab in PDENLP_MEM_HOST stages only the dof ranges its cells touch (pdenlp_input_ranges); every callback
+    must equal the device-memspace slab model — with NaNs in the entries of x / lambda / v the slab never reads, so a
+    read outside the staged ranges (or a wrong range) shows up as a NaN."""
+    from pdenlp_b200.model import GridapPDENLPModel
+    for spec in (pkg.controlelasticmembrane(12), pkg.poissonmixed(12, 2, True)):
+        nc = spec.model.ncells
+        rng = (32 * ((nc // 3) // 32), 32 * ((2 * nc // 3) // 32))
+        nd = GridapPDENLPModel(spec, device="cuda:0", cell_range=rng)
+        nh = GridapPDENLPModel(spec, device="cuda:0", cell_range=rng, memspace="host")
+        ylo, yhi, ulo, uhi = nh.handle.input_ranges()
+        n, m, p = nh.meta.nvar, nh.meta.ncon, spec.nparam
+        assert 0 <= ylo < yhi <= m and (yhi - ylo) < m, "the slab must touch a strict sub-range of the state dofs"
+        assert nh.staged_input_bytes(("x",)) == 8 * (p + (yhi - ylo) + (uhi - ulo)) < 8 * n
+        g = np.random.default_rng(5)
+        x, lam, v = g.uniform(-1, 1, n), g.uniform(-1, 1, m), g.uniform(-1, 1, n)
+        if p:
+            x[:p] = 1 + 0.1 * g.uniform(-1, 1, p)
+        xh, lh, vh = x.copy(), lam.copy(), v.copy()
+        keep = np.zeros(n, bool); keep[:p] = True; keep[p + ylo: p + yhi] = True; keep[p + m + ulo: p + m + uhi] = True
+        xh[~keep] = np.nan; vh[~keep] = np.nan
+        kc = np.zeros(m, bool); kc[ylo:yhi] = True
+        lh[~kc] = np.nan
+        tol = dict(rtol=1e-12, atol=1e-13)
+        assert np.array_equal(nh.jac_coord(xh), nd.jac_coord(_d(x)).cpu().numpy())
+        assert np.array_equal(nh.hess_coord(xh, lh, obj_weight=0.5), nd.hess_coord(_d(x), _d(lam), obj_weight=0.5).cpu().numpy())
+        assert np.allclose(nh.grad(xh), nd.grad(_d(x)).cpu().numpy(), **tol)
+        assert np.allclose(nh.cons(xh), nd.cons(_d(x)).cpu().numpy(), **tol)
+        assert np.allclose(nh.jprod(xh, vh), nd.jprod(_d(x), _d(v)).cpu().numpy(), **tol)
+        assert np.allclose(nh.jtprod(xh, lh), nd.jtprod(_d(x), _d(lam)).cpu().numpy(), **tol)
+        assert np.allclose(nh.hprod(xh, lh, vh, obj_weight=0.37), nd.hprod(_d(x), _d(lam), _d(v), obj_weight=0.37).cpu().numpy(), **tol)
+        assert abs(nh.obj(xh) - nd.obj(_d(x))) <= 1e-12 * max(1.0, abs(nd.obj(_d(x))))
+        nh.close(); nd.close()
+
+
 def test_unaligned_guarded_outputs(case):
     """Outputs that are only 8 B aligned (a view starting at an odd element) with sentinel guards on
     both sides: exercises the head/tail handling of the 16 B-aligned bulk stores and catches any
