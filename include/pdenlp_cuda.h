@@ -326,6 +326,37 @@ int pdenlp_compaction_apply(pdenlp_compaction* p, const double* coo_vals, double
    uploads its own rows of the mesh instead of the whole vector (x and lambda are replicated). */
 int pdenlp_input_ranges(const pdenlp_model* m, int64_t ranges[4]);
 
+/* ---- several GPUs behind one handle (cells are independent units; one contiguous, 32-cell aligned cell
+   slab per device).  One process, one host thread; every device gets its own pdenlp_model over its slab, its own
+   stream and its own device copies of the dof ranges of x / lambda / v its cells touch.  All vector arguments are
+   HOST pointers (replicated x, global outputs — what a Julia solver holds); page-locked memory (pdenlp_host_alloc)
+   lets the devices' copies overlap.
+     jac_coord / hess_coord: no reduction — device r writes its slice of every FE segment straight to its place in the
+       global COO stream (the slabs' slices concatenate in device order); the dense kappa blocks are slab partials, summed
+       on the host in device order over the rows each slab touches.
+     obj / grad / cons / jprod / jtprod / hprod: slab partials; only interface dofs (rows touched by two slabs) and the
+       kappa entries are summed, on the host, in device order — deterministic, and no device-to-device collective is
+       needed because the result goes to host memory anyway.
+   Same status codes and error string as the single-device entry points. */
+typedef struct pdenlp_sharded pdenlp_sharded; /* opaque */
+/* devices == NULL: CUDA devices 0 .. ndev-1.  desc->device and desc->memspace are ignored. */
+int pdenlp_sharded_create(const pdenlp_desc* desc, int32_t ndev, const int32_t* devices, pdenlp_sharded** out);
+int pdenlp_sharded_destroy(pdenlp_sharded* s);
+/* sizes of the GLOBAL problem (nnzj / nnzh are the lengths of the global COO streams) */
+int pdenlp_sharded_get_info(const pdenlp_sharded* s, pdenlp_info* info);
+/* cells [c0, c1) owned by device slot k */
+int pdenlp_sharded_slab(const pdenlp_sharded* s, int32_t k, int64_t* c0, int64_t* c1);
+int pdenlp_sharded_obj(pdenlp_sharded* s, const double* x, double* f);
+int pdenlp_sharded_grad(pdenlp_sharded* s, const double* x, double* g);
+int pdenlp_sharded_cons(pdenlp_sharded* s, const double* x, double* c);
+int pdenlp_sharded_jac_coord(pdenlp_sharded* s, const double* x, double* vals);
+int pdenlp_sharded_hess_coord(pdenlp_sharded* s, const double* x, const double* lambda, double obj_weight, double* vals);
+int pdenlp_sharded_jprod(pdenlp_sharded* s, const double* x, const double* v, double* Jv);
+int pdenlp_sharded_jtprod(pdenlp_sharded* s, const double* x, const double* v, double* Jtv);
+int pdenlp_sharded_hprod(pdenlp_sharded* s, const double* x, const double* lambda, double obj_weight, const double* v, double* Hv);
+int pdenlp_sharded_jac_structure(pdenlp_sharded* s, int64_t* rows, int64_t* cols);
+int pdenlp_sharded_hess_structure(pdenlp_sharded* s, int64_t* rows, int64_t* cols);
+
 /* bench support: number of kernel launches issued by this handle so far, and
    the CUDA-event time (ms) of the most recent callback on the handle's stream */
 int pdenlp_launch_count(const pdenlp_model* m, int64_t* launches);

@@ -27,6 +27,7 @@ SYMBOLS = [
     "pdenlp_host_alloc", "pdenlp_host_free",
     "pdenlp_obj", "pdenlp_objgrad", "pdenlp_objcons", "pdenlp_grad", "pdenlp_cons", "pdenlp_jac_coord", "pdenlp_hess_coord", "pdenlp_hess_coord_obj",
     "pdenlp_jprod", "pdenlp_jtprod", "pdenlp_hprod", "pdenlp_jac_structure", "pdenlp_hess_structure", "pdenlp_input_ranges",
+    "pdenlp_sharded_create", "pdenlp_sharded_destroy", "pdenlp_sharded_get_info", "pdenlp_sharded_slab", "pdenlp_sharded_obj", "pdenlp_sharded_grad", "pdenlp_sharded_cons", "pdenlp_sharded_jac_coord", "pdenlp_sharded_hess_coord", "pdenlp_sharded_jprod", "pdenlp_sharded_jtprod", "pdenlp_sharded_hprod", "pdenlp_sharded_jac_structure", "pdenlp_sharded_hess_structure",
     "pdenlp_selfcheck_error", "pdenlp_launch_count", "pdenlp_last_kernel_ms", "pdenlp_set_timing",
     "pdenlp_compaction_create", "pdenlp_compaction_destroy", "pdenlp_compaction_nnz",
     "pdenlp_compaction_structure", "pdenlp_compaction_apply",
@@ -113,6 +114,20 @@ def load():
     lib.pdenlp_hess_structure.argtypes = [vp, vp, vp]
     lib.pdenlp_selfcheck_error.argtypes = [vp, C.POINTER(dbl)]
     lib.pdenlp_input_ranges.argtypes = [vp, C.POINTER(i64)]
+    lib.pdenlp_sharded_create.argtypes = [C.POINTER(Desc), C.c_int32, C.POINTER(C.c_int32), C.POINTER(vp)]
+    lib.pdenlp_sharded_destroy.argtypes = [vp]
+    lib.pdenlp_sharded_get_info.argtypes = [vp, C.POINTER(Info)]
+    lib.pdenlp_sharded_slab.argtypes = [vp, C.c_int32, C.POINTER(i64), C.POINTER(i64)]
+    lib.pdenlp_sharded_obj.argtypes = [vp, vp, C.POINTER(dbl)]
+    lib.pdenlp_sharded_grad.argtypes = [vp, vp, vp]
+    lib.pdenlp_sharded_cons.argtypes = [vp, vp, vp]
+    lib.pdenlp_sharded_jac_coord.argtypes = [vp, vp, vp]
+    lib.pdenlp_sharded_hess_coord.argtypes = [vp, vp, vp, dbl, vp]
+    lib.pdenlp_sharded_jprod.argtypes = [vp, vp, vp, vp]
+    lib.pdenlp_sharded_jtprod.argtypes = [vp, vp, vp, vp]
+    lib.pdenlp_sharded_hprod.argtypes = [vp, vp, vp, dbl, vp, vp]
+    lib.pdenlp_sharded_jac_structure.argtypes = [vp, vp, vp]
+    lib.pdenlp_sharded_hess_structure.argtypes = [vp, vp, vp]
     lib.pdenlp_launch_count.argtypes = [vp, C.POINTER(i64)]
     lib.pdenlp_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.pdenlp_set_timing.argtypes = [vp, C.c_int32]
@@ -138,38 +153,138 @@ def _np_ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
 
 
+def build_desc(fm, device: int = -1, memspace: int = MEM_DEVICE, with_coef: bool = True):
+    """pdenlp_desc of a FlatModel plus the arrays it points at (keep them alive until pdenlp_create returns)."""
+    d = Desc()
+    d.abi_version = ABI_VERSION
+    d.integrand = fm.spec.integrand
+    d.dim, d.ny, d.nu, d.nq, d.nparam = fm.dim, fm.ny, fm.nu, fm.nq, fm.nparam
+    d.memspace = memspace
+    d.device = device
+    d.ncells, d.nfree_y, d.nfree_u = fm.ncells, fm.nfree_y, fm.nfree_u
+    d.ndir_y, d.ndir_u = fm.dir_y.size, fm.dir_u.size
+    keep = [np.ascontiguousarray(fm.cell_dofs_y, np.int32), np.ascontiguousarray(fm.cell_dofs_u, np.int32),
+            fm.dir_y, fm.dir_u, fm.phi_y, fm.grad_y, fm.phi_u, fm.wdet, fm.coef]
+    d.cell_dofs_y, d.cell_dofs_u = _np_ptr(keep[0]), _np_ptr(keep[1])
+    d.dir_y, d.dir_u = _np_ptr(fm.dir_y), _np_ptr(fm.dir_u)
+    d.phi_y, d.grad_y, d.phi_u, d.wdet = _np_ptr(fm.phi_y), _np_ptr(fm.grad_y), _np_ptr(fm.phi_u), _np_ptr(fm.wdet)
+    if with_coef and fm.coef.shape[1] == fm.ncells:
+        d.ncoef, d.coef = 2, _np_ptr(fm.coef)
+    else:
+        d.ncoef, d.coef = 0, None
+    for i in range(8):
+        d.params[i] = fm.params[i]
+    d.nfields_y, d.nfields_u = fm.nfy, fm.nfu
+    keep += [np.ascontiguousarray(fm.field_nfree, np.int64), np.ascontiguousarray(fm.field_ndir, np.int64)]
+    d.field_nfree, d.field_ndir = _np_ptr(keep[-2]), _np_ptr(keep[-1])
+    if getattr(fm, "cell_jinvT", None) is not None:  # per-cell geometry (ABI v3)
+        keep += [np.ascontiguousarray(fm.cell_jinvT, np.float64), np.ascontiguousarray(fm.cell_detj, np.float64)]
+        d.cell_jinvT, d.cell_detj, d.geom_nq = _np_ptr(keep[-2]), _np_ptr(keep[-1]), int(fm.geom_nq)
+    else:
+        d.cell_jinvT, d.cell_detj, d.geom_nq = None, None, 0
+    return d, keep
+
+
+def dump_desc(fm, path: str, with_coef: bool = True):
+    """Write a FlatModel as the flat binary file tests/c/test_sharded.c reads (a C program has no Gridap/Python host
+    layer to flatten a model): magic, 10 int32, 5 int64, params[8], then every array of pdenlp_desc in declaration
+    order (lengths follow from the scalars)."""
+    d, keep = build_desc(fm, -1, MEM_HOST, with_coef)
+    nfy, nfu = max(int(d.nfields_y), 1), (max(int(d.nfields_u), 1) if d.nu else 0)
+    with open(path, "wb") as fh:
+        fh.write(b"PDENLPD3")
+        np.array([d.integrand, d.dim, d.ny, d.nu, d.nq, d.nparam, d.nfields_y, d.nfields_u, d.ncoef, d.geom_nq], np.int32).tofile(fh)
+        np.array([d.ncells, d.nfree_y, d.nfree_u, d.ndir_y, d.ndir_u], np.int64).tofile(fh)
+        np.array([d.params[i] for i in range(8)], np.float64).tofile(fh)
+        arrays = [(keep[0], np.int32, d.ncells * nfy * d.ny), (keep[1], np.int32, d.ncells * nfu * d.nu),
+                  (fm.dir_y, np.float64, d.ndir_y), (fm.dir_u, np.float64, d.ndir_u),
+                  (fm.phi_y, np.float64, d.nq * d.ny), (fm.grad_y, np.float64, d.nq * d.ny * d.dim),
+                  (fm.phi_u, np.float64, d.nq * d.nu), (fm.wdet, np.float64, d.nq),
+                  (fm.coef if d.ncoef else np.zeros(0), np.float64, d.ncoef * d.ncells * d.nq),
+                  (keep[9], np.int64, nfy + nfu), (keep[10], np.int64, nfy + nfu)]
+        if d.geom_nq:
+            arrays += [(keep[11], np.float64, d.ncells * d.geom_nq * d.dim * d.dim), (keep[12], np.float64, d.ncells * d.geom_nq)]
+        for a, dt, n in arrays:
+            a = np.ascontiguousarray(a, dt).reshape(-1)
+            assert a.size == n, (a.size, n)
+            a.tofile(fh)
+
+
+class ShardedHandle:
+    """Owns one ``pdenlp_sharded*``: the in-library multi-GPU handle (one process, host vectors in and out)."""
+
+    def __init__(self, fm, ndev: int, devices=None, with_coef: bool = True):
+        lib = load()
+        d, keep = build_desc(fm, -1, MEM_HOST, with_coef)
+        devs = (C.c_int32 * ndev)(*devices) if devices is not None else None
+        h = C.c_void_p()
+        check(lib.pdenlp_sharded_create(C.byref(d), ndev, devs, C.byref(h)))
+        del keep
+        self._h, self.ndev = h, ndev
+        self.info = Info()
+        check(lib.pdenlp_sharded_get_info(h, C.byref(self.info)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().pdenlp_sharded_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def slab(self, k):
+        a, b = C.c_int64(), C.c_int64()
+        check(load().pdenlp_sharded_slab(self._h, k, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def obj(self, x) -> float:
+        f = C.c_double()
+        check(load().pdenlp_sharded_obj(self._h, _np_ptr(x), C.byref(f)))
+        return f.value
+
+    def _vec(self, fn, n, *args):
+        out = np.empty(n)
+        check(fn(self._h, *args, _np_ptr(out)))
+        return out
+
+    def grad(self, x):
+        return self._vec(load().pdenlp_sharded_grad, self.info.nvar, _np_ptr(x))
+
+    def cons(self, x):
+        return self._vec(load().pdenlp_sharded_cons, self.info.ncon, _np_ptr(x))
+
+    def jac_coord(self, x):
+        return self._vec(load().pdenlp_sharded_jac_coord, self.info.nnzj, _np_ptr(x))
+
+    def hess_coord(self, x, lam=None, obj_weight=1.0):
+        return self._vec(load().pdenlp_sharded_hess_coord, self.info.nnzh, _np_ptr(x), _np_ptr(lam) if lam is not None else None, float(obj_weight))
+
+    def jprod(self, x, v):
+        return self._vec(load().pdenlp_sharded_jprod, self.info.ncon, _np_ptr(x), _np_ptr(v))
+
+    def jtprod(self, x, v):
+        return self._vec(load().pdenlp_sharded_jtprod, self.info.nvar, _np_ptr(x), _np_ptr(v))
+
+    def hprod(self, x, lam, v, obj_weight=1.0):
+        return self._vec(load().pdenlp_sharded_hprod, self.info.nvar, _np_ptr(x), _np_ptr(lam) if lam is not None else None, float(obj_weight), _np_ptr(v))
+
+    def structure(self, hess: bool):
+        n = self.info.nnzh if hess else self.info.nnzj
+        r, c = np.empty(n, np.int64), np.empty(n, np.int64)
+        fn = load().pdenlp_sharded_hess_structure if hess else load().pdenlp_sharded_jac_structure
+        check(fn(self._h, _np_ptr(r), _np_ptr(c)))
+        return r, c
+
+
 class Handle:
     """Owns one ``pdenlp_model*`` created from a FlatModel (one cell slab on one GPU)."""
 
     def __init__(self, fm, device: int = -1, memspace: int = MEM_DEVICE, with_coef: bool = True):
         lib = load()
-        d = Desc()
-        d.abi_version = ABI_VERSION
-        d.integrand = fm.spec.integrand
-        d.dim, d.ny, d.nu, d.nq, d.nparam = fm.dim, fm.ny, fm.nu, fm.nq, fm.nparam
-        d.memspace = memspace
-        d.device = device
-        d.ncells, d.nfree_y, d.nfree_u = fm.ncells, fm.nfree_y, fm.nfree_u
-        d.ndir_y, d.ndir_u = fm.dir_y.size, fm.dir_u.size
-        keep = [np.ascontiguousarray(fm.cell_dofs_y, np.int32), np.ascontiguousarray(fm.cell_dofs_u, np.int32),
-                fm.dir_y, fm.dir_u, fm.phi_y, fm.grad_y, fm.phi_u, fm.wdet, fm.coef]
-        d.cell_dofs_y, d.cell_dofs_u = _np_ptr(keep[0]), _np_ptr(keep[1])
-        d.dir_y, d.dir_u = _np_ptr(fm.dir_y), _np_ptr(fm.dir_u)
-        d.phi_y, d.grad_y, d.phi_u, d.wdet = _np_ptr(fm.phi_y), _np_ptr(fm.grad_y), _np_ptr(fm.phi_u), _np_ptr(fm.wdet)
-        if with_coef and fm.coef.shape[1] == fm.ncells:
-            d.ncoef, d.coef = 2, _np_ptr(fm.coef)
-        else:
-            d.ncoef, d.coef = 0, None
-        for i in range(8):
-            d.params[i] = fm.params[i]
-        d.nfields_y, d.nfields_u = fm.nfy, fm.nfu
-        keep += [np.ascontiguousarray(fm.field_nfree, np.int64), np.ascontiguousarray(fm.field_ndir, np.int64)]
-        d.field_nfree, d.field_ndir = _np_ptr(keep[-2]), _np_ptr(keep[-1])
-        if getattr(fm, "cell_jinvT", None) is not None:  # per-cell geometry (ABI v3)
-            keep += [np.ascontiguousarray(fm.cell_jinvT, np.float64), np.ascontiguousarray(fm.cell_detj, np.float64)]
-            d.cell_jinvT, d.cell_detj, d.geom_nq = _np_ptr(keep[-2]), _np_ptr(keep[-1]), int(fm.geom_nq)
-        else:
-            d.cell_jinvT, d.cell_detj, d.geom_nq = None, None, 0
+        d, keep = build_desc(fm, device, memspace, with_coef)
         h = C.c_void_p()
         check(lib.pdenlp_create(C.byref(d), C.byref(h)))
         del keep

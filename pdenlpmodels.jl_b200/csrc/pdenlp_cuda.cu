@@ -968,4 +968,438 @@ int pdenlp_last_kernel_ms(pdenlp_model* m, float* ms) {
   return PDENLP_OK;
 }
 
+
+// =====================================================================================================================
+// Several GPUs behind one handle (include/pdenlp_cuda.h, "pdenlp_sharded").  One host thread drives every device:
+// stage the dof ranges the slab reads, launch the slab's callback on the device's own stream, copy the slab's slices
+// to their place in the caller's host arrays; rows shared by two slabs and the kappa entries are summed on the host in
+// device order.
+// =====================================================================================================================
+}  // extern "C"
+
+struct pdenlp_sharded {
+  int ndev = 0;
+  std::vector<int> dev;
+  std::vector<pdenlp_model*> m;
+  std::vector<cudaStream_t> st;
+  std::vector<int64_t> c0, c1;
+  std::vector<int64_t> off_jy, off_ju, off_h, off_ho;  // [ndev+1] prefix sums of the local FE segment sizes
+  std::vector<double*> dx, dlam, dv, dout, dcoo;       // device buffers of every device
+  std::vector<double*> hstage;                         // page-locked staging (shared rows, kappa entries / blocks)
+  std::vector<int64_t> hstage_len;
+  pdenlp_info gi;
+  int64_t p = 0, ny = 0, nu = 0;
+  bool ordered = true;  // the slabs' dof ranges start in ascending order (contiguous slabs of a mesh numbered row by row)
+};
+
+namespace {
+
+struct Piece { int64_t dst, len; };  // a run of staged values and where it is added in the caller's array
+
+struct DevGuard {
+  int prev = 0;
+  explicit DevGuard(int d) { cudaGetDevice(&prev); cudaSetDevice(d); }
+  ~DevGuard() { cudaSetDevice(prev); }
+};
+
+int sh_stage_buf(pdenlp_sharded* s, int k, int64_t n) {
+  if (s->hstage_len[k] >= n) return PDENLP_OK;
+  if (s->hstage[k]) cudaFreeHost(s->hstage[k]);
+  s->hstage[k] = nullptr; s->hstage_len[k] = 0;
+  CU(cudaHostAlloc((void**)&s->hstage[k], (size_t)std::max<int64_t>(n, 16) * 8, cudaHostAllocDefault));
+  s->hstage_len[k] = n;
+  return PDENLP_OK;
+}
+// host -> device copy of the parts of an input vector slab k reads (see in_ptr)
+int sh_stage_in(pdenlp_sharded* s, int k, const double* user, double* dbuf, int layout) {
+  const pdenlp_model* m = s->m[k];
+  auto part = [&](int64_t lo, int64_t hi) -> int {
+    if (hi > lo) CU(cudaMemcpyAsync(dbuf + lo, user + lo, (size_t)(hi - lo) * 8, cudaMemcpyHostToDevice, s->st[k]));
+    return PDENLP_OK;
+  };
+  if (layout == LAYOUT_C) return part(m->yr[0], m->yr[1]);
+  if (int rc = part(0, s->p)) return rc;
+  if (int rc = part(s->p + m->yr[0], s->p + m->yr[1])) return rc;
+  return part(s->p + s->ny + m->ur[0], s->p + s->ny + m->ur[1]);
+}
+int sh_sync_all(pdenlp_sharded* s) {
+  for (int k = 0; k < s->ndev; ++k) {
+    DevGuard g(s->dev[k]);
+    CU(cudaStreamSynchronize(s->st[k]));
+  }
+  return PDENLP_OK;
+}
+
+// Assemble a dof-indexed output (x-layout: kappa | y | u, or constraint layout: y only) from the slabs' partial vectors
+// dout[k].  Rows only one slab touches are copied straight to the caller's array; rows an earlier slab already covers
+// are staged and added on the host after the copies (device order => deterministic); gaps are zero-filled.
+int sh_gather_vector(pdenlp_sharded* s, double* out, bool xlayout) {
+  const int nd = s->ndev;
+  const int64_t p = xlayout ? s->p : 0;
+  const int64_t n = xlayout ? s->gi.nvar : s->gi.ncon;
+  std::vector<std::vector<Piece>> adds(nd);
+  std::vector<int64_t> used(nd, 0);
+  if (!s->ordered) memset(out, 0, (size_t)n * 8);
+  for (int k = 0; k < nd; ++k) {
+    const int64_t need = p + (s->m[k]->yr[1] - s->m[k]->yr[0]) + (xlayout ? s->m[k]->ur[1] - s->m[k]->ur[0] : 0);
+    if (int rc = sh_stage_buf(s, k, need)) return rc;
+  }
+  auto staged = [&](int k, int64_t lo, int64_t hi) -> int {  // [lo, hi) of dout[k] -> staging, to be added at out[lo..hi)
+    if (hi <= lo) return PDENLP_OK;
+    DevGuard g(s->dev[k]);
+    CU(cudaMemcpyAsync(s->hstage[k] + used[k], s->dout[k] + lo, (size_t)(hi - lo) * 8, cudaMemcpyDeviceToHost, s->st[k]));
+    adds[k].push_back({lo, hi - lo});
+    used[k] += hi - lo;
+    return PDENLP_OK;
+  };
+  auto direct = [&](int k, int64_t lo, int64_t hi) -> int {
+    if (hi <= lo) return PDENLP_OK;
+    DevGuard g(s->dev[k]);
+    CU(cudaMemcpyAsync(out + lo, s->dout[k] + lo, (size_t)(hi - lo) * 8, cudaMemcpyDeviceToHost, s->st[k]));
+    return PDENLP_OK;
+  };
+  // kappa entries: every slab contributes
+  if (p > 0) {
+    memset(out, 0, (size_t)p * 8);
+    for (int k = 0; k < nd; ++k)
+      if (int rc = staged(k, 0, p)) return rc;
+  }
+  auto space = [&](int64_t base, int64_t nfree, bool is_u) -> int {
+    int64_t cover = 0;  // rows [0, cover) of this space are written (or zero-filled) already
+    for (int k = 0; k < nd; ++k) {
+      const int64_t lo = is_u ? s->m[k]->ur[0] : s->m[k]->yr[0], hi = is_u ? s->m[k]->ur[1] : s->m[k]->yr[1];
+      if (hi <= lo) continue;
+      if (!s->ordered) { if (int rc = staged(k, base + lo, base + hi)) return rc; continue; }
+      if (lo > cover) { memset(out + base + cover, 0, (size_t)(lo - cover) * 8); cover = lo; }
+      if (int rc = staged(k, base + lo, base + std::min(hi, cover))) return rc;
+      if (hi > cover) { if (int rc = direct(k, base + cover, base + hi)) return rc; cover = hi; }
+    }
+    if (s->ordered && cover < nfree) memset(out + base + cover, 0, (size_t)(nfree - cover) * 8);
+    return PDENLP_OK;
+  };
+  if (int rc = space(p, s->ny, false)) return rc;
+  if (xlayout && s->nu > 0) { if (int rc = space(p + s->ny, s->nu, true)) return rc; }
+  if (int rc = sh_sync_all(s)) return rc;
+  for (int k = 0; k < nd; ++k) {
+    const double* src = s->hstage[k];
+    for (const Piece& pc : adds[k]) {
+      for (int64_t i = 0; i < pc.len; ++i) out[pc.dst + i] += src[i];
+      src += pc.len;
+    }
+  }
+  return PDENLP_OK;
+}
+
+// Sum a dense kappa block over the slabs: block = p columns; column j holds the x-layout rows [row0(j), nrows) at
+// col_off(j) + (row - row0(j)).  Slab k contributes the rows it touches (kappa rows, its y rows, its u rows — given in
+// block-row coordinates by `ranges`).  dblock[k] points at slab k's partial block on its device.
+template <class ColOff, class Row0>
+int sh_reduce_block(pdenlp_sharded* s, double* block, int64_t block_len, int ncols, ColOff col_off, Row0 row0,
+                    const std::vector<std::vector<std::pair<int64_t, int64_t>>>& ranges, const std::vector<const double*>& dblock) {
+  const int nd = s->ndev;
+  std::vector<std::vector<Piece>> adds(nd);
+  memset(block, 0, (size_t)block_len * 8);
+  for (int k = 0; k < nd; ++k) {
+    int64_t need = 0;
+    for (int j = 0; j < ncols; ++j)
+      for (auto& r : ranges[k]) need += std::max<int64_t>(0, r.second - std::max(r.first, row0(j)));
+    if (int rc = sh_stage_buf(s, k, need)) return rc;
+    DevGuard g(s->dev[k]);
+    int64_t used = 0;
+    for (int j = 0; j < ncols; ++j)
+      for (auto& r : ranges[k]) {
+        const int64_t a = std::max(r.first, row0(j)), b = r.second;
+        if (b <= a) continue;
+        const int64_t pos = col_off(j) + (a - row0(j));
+        CU(cudaMemcpyAsync(s->hstage[k] + used, dblock[k] + pos, (size_t)(b - a) * 8, cudaMemcpyDeviceToHost, s->st[k]));
+        adds[k].push_back({pos, b - a});
+        used += b - a;
+      }
+  }
+  if (int rc = sh_sync_all(s)) return rc;
+  for (int k = 0; k < nd; ++k) {
+    const double* src = s->hstage[k];
+    for (const Piece& pc : adds[k]) {
+      for (int64_t i = 0; i < pc.len; ++i) block[pc.dst + i] += src[i];
+      src += pc.len;
+    }
+  }
+  return PDENLP_OK;
+}
+// x-layout rows slab k touches: kappa rows, its state rows, its control rows
+std::vector<std::vector<std::pair<int64_t, int64_t>>> sh_x_rows(const pdenlp_sharded* s) {
+  std::vector<std::vector<std::pair<int64_t, int64_t>>> r(s->ndev);
+  for (int k = 0; k < s->ndev; ++k) {
+    r[k].push_back({0, s->p});
+    r[k].push_back({s->p + s->m[k]->yr[0], s->p + s->m[k]->yr[1]});
+    if (s->nu > 0) r[k].push_back({s->p + s->ny + s->m[k]->ur[0], s->p + s->ny + s->m[k]->ur[1]});
+  }
+  return r;
+}
+
+int sh_vector_call(pdenlp_sharded* s, int op, const double* x, const double* lam, const double* v, double ow, double* out) {
+  if (!s || !x || !out) return fail(PDENLP_EINVAL, "null argument");
+  const bool out_x = op == OP_GRAD || op == OP_JTPROD || op == OP_HPROD;
+  for (int k = 0; k < s->ndev; ++k) {
+    DevGuard g(s->dev[k]);
+    if (int rc = sh_stage_in(s, k, x, s->dx[k], LAYOUT_X)) return rc;
+    if (lam) { if (int rc = sh_stage_in(s, k, lam, s->dlam[k], LAYOUT_C)) return rc; }
+    if (v) { if (int rc = sh_stage_in(s, k, v, s->dv[k], op == OP_JTPROD ? LAYOUT_C : LAYOUT_X)) return rc; }
+    int rc = PDENLP_OK;
+    switch (op) {
+      case OP_GRAD: rc = pdenlp_grad(s->m[k], s->dx[k], s->dout[k]); break;
+      case OP_CONS: rc = pdenlp_cons(s->m[k], s->dx[k], s->dout[k]); break;
+      case OP_JPROD: rc = pdenlp_jprod(s->m[k], s->dx[k], s->dv[k], s->dout[k]); break;
+      case OP_JTPROD: rc = pdenlp_jtprod(s->m[k], s->dx[k], s->dv[k], s->dout[k]); break;
+      // (a NoFETerm objective fk(kappa) is not a sum over cells: only the first slab contributes it)
+      case OP_HPROD: rc = pdenlp_hprod(s->m[k], s->dx[k], lam ? s->dlam[k] : nullptr, (s->m[k]->nofe && k > 0) ? 0.0 : ow, s->dv[k], s->dout[k]); break;
+      default: rc = fail(PDENLP_EINVAL, "bad vector op");
+    }
+    if (rc) return rc;
+    if (op == OP_GRAD && s->m[k]->nofe && k > 0 && s->p > 0) CU(cudaMemsetAsync(s->dout[k], 0, (size_t)s->p * 8, s->st[k]));
+  }
+  return sh_gather_vector(s, out, out_x);
+}
+
+}  // namespace
+
+extern "C" {
+
+int pdenlp_sharded_destroy(pdenlp_sharded* s) {
+  if (!s) return PDENLP_OK;
+  for (int k = 0; k < (int)s->m.size(); ++k) {
+    DevGuard g(s->dev[k]);
+    for (double* b : {s->dx[k], s->dlam[k], s->dv[k], s->dout[k], s->dcoo[k]})
+      if (b) cudaFree(b);
+    if (s->hstage[k]) cudaFreeHost(s->hstage[k]);
+    if (s->m[k]) pdenlp_destroy(s->m[k]);
+    if (s->st[k]) cudaStreamDestroy(s->st[k]);
+  }
+  delete s;
+  return PDENLP_OK;
+}
+
+int pdenlp_sharded_create(const pdenlp_desc* desc, int32_t ndev, const int32_t* devices, pdenlp_sharded** out) {
+  if (!desc || !out) return fail(PDENLP_EINVAL, "null argument");
+  *out = nullptr;
+  int have = 0;
+  CU(cudaGetDeviceCount(&have));
+  if (have == 0) return fail(PDENLP_ECUDA, "no CUDA device (libpdenlp_cuda has no CPU fallback)");
+  if (ndev < 1 || ndev > have) return fail(PDENLP_EINVAL, "ndev must be between 1 and the number of CUDA devices");
+  const int64_t nc = desc->ncells, ntiles = (nc + 31) / 32;
+  if (ntiles < ndev) return fail(PDENLP_EINVAL, "fewer 32-cell tiles than devices");
+  auto* s = new pdenlp_sharded();
+  s->ndev = ndev;
+  s->dev.resize(ndev); s->m.assign(ndev, nullptr); s->st.assign(ndev, nullptr);
+  s->c0.resize(ndev); s->c1.resize(ndev);
+  s->dx.assign(ndev, nullptr); s->dlam.assign(ndev, nullptr); s->dv.assign(ndev, nullptr); s->dout.assign(ndev, nullptr); s->dcoo.assign(ndev, nullptr);
+  s->hstage.assign(ndev, nullptr); s->hstage_len.assign(ndev, 0);
+  s->off_jy.assign(ndev + 1, 0); s->off_ju.assign(ndev + 1, 0); s->off_h.assign(ndev + 1, 0); s->off_ho.assign(ndev + 1, 0);
+  s->p = desc->nparam; s->ny = desc->nfree_y; s->nu = desc->nfree_u;
+  const int nfy = desc_nfy(*desc), nfu = desc_nfu(*desc);
+  auto bail = [&](int code) { pdenlp_sharded_destroy(s); return code; };
+  for (int k = 0; k < ndev; ++k) {
+    s->dev[k] = devices ? devices[k] : k;
+    if (s->dev[k] < 0 || s->dev[k] >= have) return bail(fail(PDENLP_EINVAL, "bad device ordinal"));
+    const int64_t t0 = ntiles * k / ndev, t1 = ntiles * (k + 1) / ndev;
+    s->c0[k] = std::min(t0 * 32, nc); s->c1[k] = std::min(t1 * 32, nc);
+    const int64_t a = s->c0[k], ncl = s->c1[k] - a;
+    pdenlp_desc sub = *desc;
+    sub.device = s->dev[k];
+    sub.memspace = PDENLP_MEM_DEVICE;
+    sub.ncells = ncl;
+    sub.cell_dofs_y = desc->cell_dofs_y + a * nfy * desc->ny;
+    sub.cell_dofs_u = desc->cell_dofs_u ? desc->cell_dofs_u + a * nfu * desc->nu : nullptr;
+    std::vector<double> cc;
+    if (desc->coef && desc->ncoef > 0) {  // [field][cell][q]: the slab's rows of every field
+      cc.resize((size_t)desc->ncoef * ncl * desc->nq);
+      for (int f = 0; f < desc->ncoef; ++f)
+        memcpy(cc.data() + (size_t)f * ncl * desc->nq, desc->coef + ((size_t)f * nc + a) * desc->nq, (size_t)ncl * desc->nq * 8);
+      sub.coef = cc.data();
+    }
+    if (desc->cell_jinvT) {
+      const int64_t gq = desc->geom_nq, dd = (int64_t)desc->dim * desc->dim;
+      sub.cell_jinvT = desc->cell_jinvT + a * gq * dd;
+      sub.cell_detj = desc->cell_detj + a * gq;
+    }
+    if (int rc = pdenlp_create(&sub, &s->m[k])) return bail(rc);
+    DevGuard g(s->dev[k]);
+    if (cudaStreamCreateWithFlags(&s->st[k], cudaStreamNonBlocking) != cudaSuccess) return bail(fail(PDENLP_ECUDA, "cudaStreamCreate failed"));
+    pdenlp_set_stream(s->m[k], s->st[k]);
+    const pdenlp_info& I = s->m[k]->info;
+    s->off_jy[k + 1] = s->off_jy[k] + I.nnzj_y;
+    s->off_ju[k + 1] = s->off_ju[k] + I.nnzj_u;
+    s->off_h[k + 1] = s->off_h[k] + I.nnzh_fe;
+    s->off_ho[k + 1] = s->off_ho[k] + I.nnzh_fe_obj;
+    auto alloc = [&](double** b, int64_t n) { return cudaMalloc((void**)b, (size_t)std::max<int64_t>(n, 2) * 8) == cudaSuccess; };
+    if (!alloc(&s->dx[k], I.nvar) || !alloc(&s->dlam[k], I.ncon) || !alloc(&s->dv[k], I.nvar) || !alloc(&s->dout[k], I.nvar) ||
+        !alloc(&s->dcoo[k], std::max(I.nnzj, I.nnzh)))
+      return bail(fail(PDENLP_ENOMEM, "cudaMalloc failed"));
+    // stale entries outside the staged ranges are never read by the slab; keep them finite anyway
+    cudaMemsetAsync(s->dx[k], 0, (size_t)I.nvar * 8, s->st[k]);
+    cudaMemsetAsync(s->dlam[k], 0, (size_t)std::max<int64_t>(I.ncon, 2) * 8, s->st[k]);
+    cudaMemsetAsync(s->dv[k], 0, (size_t)I.nvar * 8, s->st[k]);
+    if (k > 0 && (s->m[k]->yr[0] < s->m[k - 1]->yr[0] || s->m[k]->ur[0] < s->m[k - 1]->ur[0])) s->ordered = false;
+  }
+  const pdenlp_info& I0 = s->m[0]->info;
+  pdenlp_info& G = s->gi;
+  G = I0;
+  G.nnzj_y = s->off_jy[ndev]; G.nnzj_u = s->off_ju[ndev];
+  G.nnzj = G.nnzj_k + G.nnzj_y + G.nnzj_u;
+  G.nnzh_fe = s->off_h[ndev]; G.nnzh_fe_obj = s->off_ho[ndev];
+  G.nnzh_obj = G.nnzh_k_obj + G.nnzh_fe_obj;
+  G.nnzh = G.nnzh_obj + G.nnzh_k_con + G.nnzh_fe;
+  if (int rc = sh_sync_all(s)) return bail(rc);
+  *out = s;
+  return PDENLP_OK;
+}
+
+int pdenlp_sharded_get_info(const pdenlp_sharded* s, pdenlp_info* info) {
+  if (!s || !info) return fail(PDENLP_EINVAL, "null argument");
+  *info = s->gi;
+  return PDENLP_OK;
+}
+int pdenlp_sharded_slab(const pdenlp_sharded* s, int32_t k, int64_t* c0, int64_t* c1) {
+  if (!s || !c0 || !c1 || k < 0 || k >= s->ndev) return fail(PDENLP_EINVAL, "bad argument");
+  *c0 = s->c0[k]; *c1 = s->c1[k];
+  return PDENLP_OK;
+}
+
+int pdenlp_sharded_obj(pdenlp_sharded* s, const double* x, double* f) {
+  if (!s || !x || !f) return fail(PDENLP_EINVAL, "null argument");
+  for (int k = 0; k < s->ndev; ++k) {
+    DevGuard g(s->dev[k]);
+    if (int rc = sh_stage_in(s, k, x, s->dx[k], LAYOUT_X)) return rc;
+  }
+  double sum = 0.0;
+  for (int k = 0; k < s->ndev; ++k) {
+    if (s->m[k]->nofe && k > 0) continue;  // a NoFETerm objective fk(kappa) is not a sum over cells
+    double fk = 0.0;
+    if (int rc = pdenlp_obj(s->m[k], s->dx[k], &fk)) return rc;
+    sum += fk;
+  }
+  *f = sum;
+  return PDENLP_OK;
+}
+int pdenlp_sharded_grad(pdenlp_sharded* s, const double* x, double* g) {
+  return sh_vector_call(s, OP_GRAD, x, nullptr, nullptr, 1.0, g);
+}
+int pdenlp_sharded_cons(pdenlp_sharded* s, const double* x, double* c) { return sh_vector_call(s, OP_CONS, x, nullptr, nullptr, 1.0, c); }
+int pdenlp_sharded_jprod(pdenlp_sharded* s, const double* x, const double* v, double* Jv) {
+  if (!v) return fail(PDENLP_EINVAL, "null argument");
+  return sh_vector_call(s, OP_JPROD, x, nullptr, v, 1.0, Jv);
+}
+int pdenlp_sharded_jtprod(pdenlp_sharded* s, const double* x, const double* v, double* Jtv) {
+  if (!v) return fail(PDENLP_EINVAL, "null argument");
+  return sh_vector_call(s, OP_JTPROD, x, nullptr, v, 1.0, Jtv);
+}
+int pdenlp_sharded_hprod(pdenlp_sharded* s, const double* x, const double* lambda, double obj_weight, const double* v, double* Hv) {
+  if (!v) return fail(PDENLP_EINVAL, "null argument");
+  return sh_vector_call(s, OP_HPROD, x, lambda, v, obj_weight, Hv);
+}
+
+int pdenlp_sharded_jac_coord(pdenlp_sharded* s, const double* x, double* vals) {
+  if (!s || !x || !vals) return fail(PDENLP_EINVAL, "null argument");
+  const pdenlp_info& G = s->gi;
+  for (int k = 0; k < s->ndev; ++k) {
+    DevGuard g(s->dev[k]);
+    const pdenlp_info& I = s->m[k]->info;
+    if (int rc = sh_stage_in(s, k, x, s->dx[k], LAYOUT_X)) return rc;
+    if (int rc = pdenlp_jac_coord(s->m[k], s->dx[k], s->dcoo[k])) return rc;
+    CU(cudaMemcpyAsync(vals + G.nnzj_k + s->off_jy[k], s->dcoo[k] + I.nnzj_k, (size_t)I.nnzj_y * 8, cudaMemcpyDeviceToHost, s->st[k]));
+    if (I.nnzj_u > 0)
+      CU(cudaMemcpyAsync(vals + G.nnzj_k + G.nnzj_y + s->off_ju[k], s->dcoo[k] + I.nnzj_k + I.nnzj_y, (size_t)I.nnzj_u * 8, cudaMemcpyDeviceToHost, s->st[k]));
+  }
+  if (G.nnzj_k > 0) {  // dense ncon x p block, column-major: slab k contributes its state rows
+    std::vector<std::vector<std::pair<int64_t, int64_t>>> rows(s->ndev);
+    std::vector<const double*> blk(s->ndev);
+    for (int k = 0; k < s->ndev; ++k) { rows[k].push_back({s->m[k]->yr[0], s->m[k]->yr[1]}); blk[k] = s->dcoo[k]; }
+    const int64_t ncon = G.ncon;
+    return sh_reduce_block(s, vals, G.nnzj_k, (int)s->p, [&](int j) { return (int64_t)j * ncon; }, [](int) { return (int64_t)0; }, rows, blk);
+  }
+  return sh_sync_all(s);
+}
+
+int pdenlp_sharded_hess_coord(pdenlp_sharded* s, const double* x, const double* lambda, double obj_weight, double* vals) {
+  if (!s || !x || !vals) return fail(PDENLP_EINVAL, "null argument");
+  const pdenlp_info& G = s->gi;
+  double* const gko = vals;
+  double* const gfo = gko + G.nnzh_k_obj;
+  double* const gkc = gfo + G.nnzh_fe_obj;
+  double* const gfc = gkc + G.nnzh_k_con;
+  const bool cons_zero = !lambda || s->m[0]->ops->res_fe_hessian_zero();
+  for (int k = 0; k < s->ndev; ++k) {
+    DevGuard g(s->dev[k]);
+    const pdenlp_info& I = s->m[k]->info;
+    if (int rc = sh_stage_in(s, k, x, s->dx[k], LAYOUT_X)) return rc;
+    if (lambda) { if (int rc = sh_stage_in(s, k, lambda, s->dlam[k], LAYOUT_C)) return rc; }
+    if (int rc = pdenlp_hess_coord(s->m[k], s->dx[k], lambda ? s->dlam[k] : nullptr, obj_weight, s->dcoo[k])) return rc;
+    if (I.nnzh_fe_obj > 0)
+      CU(cudaMemcpyAsync(gfo + s->off_ho[k], s->dcoo[k] + I.nnzh_k_obj, (size_t)I.nnzh_fe_obj * 8, cudaMemcpyDeviceToHost, s->st[k]));
+    if (!cons_zero)
+      CU(cudaMemcpyAsync(gfc + s->off_h[k], s->dcoo[k] + I.nnzh_obj + I.nnzh_k_con, (size_t)I.nnzh_fe * 8, cudaMemcpyDeviceToHost, s->st[k]));
+  }
+  if (cons_zero) host_zero_parallel(gfc, G.nnzh_fe);  // structurally zero block: filled on the host while the copies run
+  if (s->p > 0) {
+    const int64_t n = G.nvar, p = s->p;
+    const auto xrows = sh_x_rows(s);
+    std::vector<std::vector<std::pair<int64_t, int64_t>>> krows(s->ndev);
+    for (int k = 0; k < s->ndev; ++k) krows[k].push_back({0, p});
+    std::vector<const double*> blk(s->ndev);
+    // objective block: p x p corner (inde energies, NoFETerm) or the full trapezoid
+    const bool corner = s->m[0]->inde;
+    const int64_t prows_o = corner ? p : n;
+    for (int k = 0; k < s->ndev; ++k) blk[k] = s->dcoo[k];
+    if (s->m[0]->nofe) {  // fk(kappa) is not a sum over cells: the block of one slab is the block
+      DevGuard g(s->dev[0]);
+      CU(cudaMemcpyAsync(gko, s->dcoo[0], (size_t)G.nnzh_k_obj * 8, cudaMemcpyDeviceToHost, s->st[0]));
+    } else if (int rc = sh_reduce_block(s, gko, G.nnzh_k_obj, (int)p, [&](int j) { return (int64_t)j * prows_o - (int64_t)j * (j - 1) / 2; },
+                                        [](int j) { return (int64_t)j; }, corner ? krows : xrows, blk)) return rc;
+    for (int k = 0; k < s->ndev; ++k) blk[k] = s->dcoo[k] + s->m[k]->info.nnzh_obj;
+    if (lambda) {
+      if (int rc = sh_reduce_block(s, gkc, G.nnzh_k_con, (int)p, [&](int j) { return (int64_t)j * n - (int64_t)j * (j - 1) / 2; },
+                                   [](int j) { return (int64_t)j; }, xrows, blk)) return rc;
+    } else {
+      memset(gkc, 0, (size_t)G.nnzh_k_con * 8);
+    }
+  }
+  return sh_sync_all(s);
+}
+
+static int sh_structure(pdenlp_sharded* s, bool hess, int64_t* rows, int64_t* cols) {
+  if (!s || !rows || !cols) return fail(PDENLP_EINVAL, "null argument");
+  const pdenlp_info& G = s->gi;
+  for (int k = 0; k < s->ndev; ++k) {
+    DevGuard g(s->dev[k]);
+    const pdenlp_info& I = s->m[k]->info;
+    const int64_t nl = hess ? I.nnzh : I.nnzj;
+    int64_t *dr = nullptr, *dc = nullptr;
+    CU(cudaMalloc((void**)&dr, (size_t)std::max<int64_t>(nl, 2) * 8));
+    if (cudaMalloc((void**)&dc, (size_t)std::max<int64_t>(nl, 2) * 8) != cudaSuccess) { cudaFree(dr); return fail(PDENLP_ENOMEM, "cudaMalloc failed"); }
+    int rc = hess ? pdenlp_hess_structure(s->m[k], dr, dc) : pdenlp_jac_structure(s->m[k], dr, dc);
+    auto get = [&](int64_t dst, int64_t src, int64_t n) {
+      if (rc || n <= 0) return;
+      cudaError_t e = cudaMemcpyAsync(rows + dst, dr + src, (size_t)n * 8, cudaMemcpyDeviceToHost, s->st[k]);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(cols + dst, dc + src, (size_t)n * 8, cudaMemcpyDeviceToHost, s->st[k]);
+      if (e != cudaSuccess) rc = fail(PDENLP_ECUDA, cudaGetErrorString(e));
+    };
+    if (!hess) {
+      if (k == 0) get(0, 0, G.nnzj_k);  // the dense kappa block has the same pattern on every slab
+      get(G.nnzj_k + s->off_jy[k], I.nnzj_k, I.nnzj_y);
+      get(G.nnzj_k + G.nnzj_y + s->off_ju[k], I.nnzj_k + I.nnzj_y, I.nnzj_u);
+    } else {
+      if (k == 0) { get(0, 0, G.nnzh_k_obj); get(G.nnzh_obj, I.nnzh_obj, G.nnzh_k_con); }
+      get(G.nnzh_k_obj + s->off_ho[k], I.nnzh_k_obj, I.nnzh_fe_obj);
+      get(G.nnzh_obj + G.nnzh_k_con + s->off_h[k], I.nnzh_obj + I.nnzh_k_con, I.nnzh_fe);
+    }
+    cudaError_t e = cudaStreamSynchronize(s->st[k]);
+    cudaFree(dr); cudaFree(dc);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(PDENLP_ECUDA, cudaGetErrorString(e));
+  }
+  return PDENLP_OK;
+}
+int pdenlp_sharded_jac_structure(pdenlp_sharded* s, int64_t* rows, int64_t* cols) { return sh_structure(s, false, rows, cols); }
+int pdenlp_sharded_hess_structure(pdenlp_sharded* s, int64_t* rows, int64_t* cols) { return sh_structure(s, true, rows, cols); }
+
 }  // extern "C"
