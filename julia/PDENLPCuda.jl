@@ -25,6 +25,8 @@ struct Desc   # mirrors struct pdenlp_desc field by field
   ncoef::Int32; nfields_u::Int32; coef::Ptr{Float64}
   params::NTuple{8, Float64}
   field_nfree::Ptr{Int64}; field_ndir::Ptr{Int64}   # multi-field spaces only, else C_NULL
+  cell_jinvT::Ptr{Float64}; cell_detj::Ptr{Float64}  # per-cell geometry (ABI v3), C_NULL = identical affine cells
+  geom_nq::Int32; reserved0::Int32
 end
 
 struct Info
@@ -34,17 +36,87 @@ end
 
 check(rc) = rc == 0 || error("libpdenlp_cuda ($rc): " * unsafe_string(ccall((:pdenlp_last_error, LIB), Cstring, ())))
 
-const HANDLES = IdDict{Any, Ptr{Cvoid}}()   # nlp => pdenlp_model*
+# nlp => handle.  Weak keys: the table must not keep the model alive, or its finalizer (which frees the device model,
+# its dof maps and staging buffers) would never run.
+mutable struct Handle
+  ptr::Ptr{Cvoid}
+  sharded::Bool      # pdenlp_sharded* (several GPUs, host vectors) instead of pdenlp_model*
+  memspace::Int32
+end
+const HANDLES = WeakKeyDict{Any, Handle}()
+
+function release!(h::Handle)
+  h.ptr == C_NULL && return
+  h.sharded ? ccall((:pdenlp_sharded_destroy, LIB), Cint, (Ptr{Cvoid},), h.ptr) : ccall((:pdenlp_destroy, LIB), Cint, (Ptr{Cvoid},), h.ptr)
+  h.ptr = C_NULL
+end
+"""    detach_cuda!(nlp): free the device model now (otherwise it is freed when `nlp` is collected)."""
+function detach_cuda!(nlp)
+  haskey(HANDLES, nlp) && (release!(HANDLES[nlp]); delete!(HANDLES, nlp))
+  return nlp
+end
+
+# ---- device-resident vectors: the `S` parameter of the model (src/GridapPDENLPModel.jl:65-73, 219-220) --------------
+# A model attached with `memspace = 0` takes its vectors in device memory: x, λ, v, vals stay on the GPU between the
+# callbacks of a solver iteration, so a step runs at the kernels' rate (1.6 ms at config 2) instead of the PCIe rate of
+# the host-vector path (130-155 ms).  DeviceVector needs no CUDA.jl: it wraps pdenlp_malloc / pdenlp_memcpy_*.
+mutable struct DeviceVector <: AbstractVector{Float64}
+  ptr::Ptr{Float64}
+  len::Int
+  function DeviceVector(n::Integer)
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:pdenlp_malloc, LIB), Cint, (Ref{Ptr{Cvoid}}, Int64), p, 8 * n))
+    v = new(convert(Ptr{Float64}, p[]), n)
+    finalizer(w -> (w.ptr != C_NULL && ccall((:pdenlp_free, LIB), Cint, (Ptr{Cvoid},), w.ptr); w.ptr = C_NULL), v)
+    return v
+  end
+end
+DeviceVector(h::AbstractVector{<:Real}) = copyto!(DeviceVector(length(h)), h)
+Base.size(v::DeviceVector) = (v.len,)
+Base.IndexStyle(::Type{DeviceVector}) = IndexLinear()
+Base.similar(v::DeviceVector) = DeviceVector(v.len)
+Base.similar(v::DeviceVector, ::Type{Float64}, dims::Dims{1}) = DeviceVector(dims[1])
+Base.unsafe_convert(::Type{Ptr{Float64}}, v::DeviceVector) = v.ptr
+function Base.copyto!(d::DeviceVector, h::AbstractVector{<:Real})
+  length(h) == d.len || throw(DimensionMismatch("DeviceVector of length $(d.len), source of length $(length(h))"))
+  hh = h isa Vector{Float64} ? h : collect(Float64, h)
+  GC.@preserve hh check(ccall((:pdenlp_memcpy_h2d, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), d.ptr, pointer(hh), 8 * d.len))
+  return d
+end
+function Base.copyto!(h::Vector{Float64}, d::DeviceVector)
+  length(h) == d.len || throw(DimensionMismatch("DeviceVector of length $(d.len), destination of length $(length(h))"))
+  GC.@preserve h check(ccall((:pdenlp_memcpy_d2h, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), pointer(h), d.ptr, 8 * d.len))
+  return h
+end
+Base.Array(d::DeviceVector) = copyto!(Vector{Float64}(undef, d.len), d)
+Base.collect(d::DeviceVector) = Array(d)
+# scalar indexing is a device round trip: for inspection only (solvers use broadcasting-free vector kernels or Array(v))
+function Base.getindex(d::DeviceVector, i::Int)
+  @boundscheck checkbounds(d, i)
+  r = Ref{Float64}()
+  check(ccall((:pdenlp_memcpy_d2h, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), r, d.ptr + 8 * (i - 1), 8))
+  return r[]
+end
+function Base.setindex!(d::DeviceVector, x, i::Int)
+  @boundscheck checkbounds(d, i)
+  r = Ref{Float64}(x)
+  check(ccall((:pdenlp_memcpy_h2d, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), d.ptr + 8 * (i - 1), r, 8))
+  return d
+end
+Base.fill!(d::DeviceVector, x) = copyto!(d, fill(Float64(x), d.len))
 
 """
-    attach_cuda!(nlp, integrand; params, target, source, memspace = 1)
+    attach_cuda!(nlp, integrand; params, target, source, memspace = 1, device = -1, devices = nothing)
 
 Flatten the Gridap side of `nlp` (cell→dof maps, Dirichlet values, reference-FE tables at the
-quadrature points, weights·detJ, coefficient fields sampled at the quadrature points) and create the
-device model.  `memspace = 1` (PDENLP_MEM_HOST): the callbacks take ordinary `Vector{Float64}`.
+quadrature points, weights·detJ or per-cell Jacobians, coefficient fields sampled at the quadrature points) and create
+the device model.  `memspace = 1` (PDENLP_MEM_HOST): the callbacks take ordinary `Vector{Float64}`; `memspace = 0`:
+they take `DeviceVector`s.  `devices = [0, 1, ...]`: one cell slab per GPU behind one handle (pdenlp_sharded_create;
+host vectors).
 """
 function attach_cuda!(nlp::GridapPDENLPModel, integrand::Integrand; params = Float64[], target = x -> 0.0,
-                      source = x -> 0.0, degree::Int = 1, memspace::Integer = 1, device::Integer = -1)
+                      source = x -> 0.0, degree::Int = 1, memspace::Integer = 1, device::Integer = -1,
+                      devices::Union{Nothing, AbstractVector{<:Integer}} = nothing)
   Ypde, Ycon = nlp.pdemeta.Ypde, nlp.pdemeta.Ycon
   trian = get_triangulation(Ypde)
   dΩ = Measure(trian, degree)
@@ -68,44 +140,90 @@ function attach_cuda!(nlp::GridapPDENLPModel, integrand::Integrand; params = Flo
   uf = has_u ? fields(Ycon) : []
   cellu, diru, nfree_uf, ndir_uf, nu = has_u ? flat(uf) : (Matrix{Int32}(undef, 0, nc), Float64[], Int64[], Int64[], 0)
   field_nfree = vcat(nfree_yf, nfree_uf); field_ndir = vcat(ndir_yf, ndir_uf)
-  # tables on cell 1 (uniform Cartesian map: identical for every cell; all fields of a space share the element)
+  # tables from cell 1 (all fields of a space share the reference element)
   sfy = get_cell_shapefuns(yf[1])
   φ = evaluate(sfy, qpts)[1]                    # nq × ny
-  ∇φ = evaluate(∇(sfy), qpts)[1]                # nq × ny of VectorValue (physical gradients)
+  ∇φ = evaluate(∇(sfy), qpts)[1]                # nq × ny of VectorValue (PHYSICAL gradients on cell 1)
   nq, D = size(φ, 1), length(∇φ[1, 1])
   phi_y = permutedims(Float64.(φ))              # ny × nq column-major == [nq][ny]
-  grad_y = [∇φ[q, a][d] for d in 1:D, a in 1:ny, q in 1:nq]   # [nq][ny][dim]
   phi_u = has_u ? permutedims(Float64.(evaluate(get_cell_shapefuns(uf[1]), qpts)[1])) : zeros(0, nq)
   w = get_cell_weights(quad)[1]; cmap = get_cell_map(trian)
-  detJ = [abs(det(∇(cmap)[1](p))) for p in get_cell_coordinates(quad)[1]]
-  wdet = Float64.(w .* detJ)
+  # Geometry.  Gridap's gradient of the cell map is G[i,j] = ∂x_j/∂ξ_i (the TRANSPOSE of the usual Jacobian), so
+  # ∇ₓφ = inv(G)·∇_ξφ and ∇_ξφ = G·∇ₓφ.  G is evaluated at every quadrature point of every cell; the uniform fast path
+  # (physical gradients folded into the tables) is taken only when ALL cells carry the same constant G — anything else
+  # (a CartesianDiscreteModel with `map`, an unstructured / simplicial mesh) goes through cell_jinvT / cell_detj.
+  Gs = evaluate(∇(cmap), get_cell_coordinates(quad))     # per cell: nq TensorValues
+  G1 = Gs[1][1]
+  tolG = 1e-13 * maximum(abs, Tuple(G1))
+  affine = all(all(maximum(abs, Tuple(Gc[q] - Gc[1])) <= tolG for q in 1:nq) for Gc in Gs)
+  uniform = affine && all(maximum(abs, Tuple(Gc[1] - G1)) <= tolG for Gc in Gs)
+  if uniform
+    grad_y = [∇φ[q, a][d] for d in 1:D, a in 1:ny, q in 1:nq]   # [nq][ny][dim], physical
+    wdet = Float64.(w .* [abs(det(Gs[1][q])) for q in 1:nq])
+    jinvT = Float64[]; detj = Float64[]; geom_nq = 0
+  else
+    # reference gradients from cell 1's physical ones: ∇_ξφ = G·∇ₓφ
+    grad_y = [(Gs[1][q] ⋅ ∇φ[q, a])[d] for d in 1:D, a in 1:ny, q in 1:nq]
+    wdet = Float64.(w)
+    geom_nq = affine ? 1 : nq
+    # cell_jinvT[c][g][d][e] = inv(G)[d,e]  (C row-major [nc][geom_nq][dim][dim] == Julia (e, d, g, c))
+    jinvT = Array{Float64}(undef, D, D, geom_nq, nc); detj = Array{Float64}(undef, geom_nq, nc)
+    for c in 1:nc, g in 1:geom_nq
+      Gi = inv(Gs[c][g])
+      for d in 1:D, e in 1:D; jinvT[e, d, g, c] = Gi[d, e]; end
+      detj[g, c] = abs(det(Gs[c][g]))
+    end
+  end
   xq = evaluate(cmap, get_cell_coordinates(quad))   # physical quadrature points per cell
   coef = Array{Float64}(undef, nq, nc, 2)           # [2][nc][nq]
   for c in 1:nc, q in 1:nq; coef[q, c, 1] = target(xq[c][q]); coef[q, c, 2] = source(xq[c][q]); end
   par = ntuple(i -> i <= length(params) ? Float64(params[i]) : 0.0, 8)
-  GC.@preserve celly cellu diry diru phi_y grad_y phi_u wdet coef field_nfree field_ndir begin
-    d = Desc(2, Int32(integrand), D, ny, nu, nq, nlp.pdemeta.nparam, memspace, device, length(yf),
+  sharded = devices !== nothing
+  devs = sharded ? Int32.(devices) : Int32[]
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  GC.@preserve celly cellu diry diru phi_y grad_y phi_u wdet coef field_nfree field_ndir jinvT detj devs begin
+    d = Desc(3, Int32(integrand), D, ny, nu, nq, nlp.pdemeta.nparam, sharded ? 1 : memspace, device, length(yf),
              nc, num_free_dofs(Ypde), has_u ? num_free_dofs(Ycon) : 0, length(diry), length(diru),
              pointer(celly), pointer(cellu), pointer(diry), pointer(diru),
              pointer(phi_y), pointer(grad_y), pointer(phi_u), pointer(wdet), 2, length(uf), pointer(coef), par,
-             pointer(field_nfree), pointer(field_ndir))
-    h = Ref{Ptr{Cvoid}}(C_NULL)
-    check(ccall((:pdenlp_create, LIB), Cint, (Ref{Desc}, Ref{Ptr{Cvoid}}), d, h))
+             pointer(field_nfree), pointer(field_ndir),
+             geom_nq == 0 ? Ptr{Float64}(C_NULL) : pointer(jinvT), geom_nq == 0 ? Ptr{Float64}(C_NULL) : pointer(detj), geom_nq, 0)
+    if sharded
+      check(ccall((:pdenlp_sharded_create, LIB), Cint, (Ref{Desc}, Int32, Ptr{Int32}, Ref{Ptr{Cvoid}}), d, length(devs), devs, h))
+    else
+      check(ccall((:pdenlp_create, LIB), Cint, (Ref{Desc}, Ref{Ptr{Cvoid}}), d, h))
+    end
   end
   info = Ref{Info}()
-  check(ccall((:pdenlp_get_info, LIB), Cint, (Ptr{Cvoid}, Ref{Info}), h[], info))
+  check(sharded ? ccall((:pdenlp_sharded_get_info, LIB), Cint, (Ptr{Cvoid}, Ref{Info}), h[], info) :
+                  ccall((:pdenlp_get_info, LIB), Cint, (Ptr{Cvoid}, Ref{Info}), h[], info))
   # Gridap's structure stays authoritative; the device structure only cross-checks it
   @assert info[].nnzj == nlp.meta.nnzj && info[].nnzh == nlp.meta.nnzh && info[].nnzh_obj == nlp.pdemeta.nnzh_obj
-  rows = Vector{Int64}(undef, nlp.meta.nnzh); cols = similar(rows)
-  check(ccall((:pdenlp_hess_structure, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), h[], rows, cols))
-  @assert rows == nlp.pdemeta.Hrows && cols == nlp.pdemeta.Hcols "COO order differs from hess_structure!"
-  HANDLES[nlp] = h[]
-  finalizer(n -> (haskey(HANDLES, n) && ccall((:pdenlp_destroy, LIB), Cint, (Ptr{Cvoid},), pop!(HANDLES, n))), nlp)
+  if sharded || memspace == 1   # (a device-memspace model returns its structure in device memory)
+    rows = Vector{Int64}(undef, nlp.meta.nnzh); cols = similar(rows)
+    check(sharded ? ccall((:pdenlp_sharded_hess_structure, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), h[], rows, cols) :
+                    ccall((:pdenlp_hess_structure, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), h[], rows, cols))
+    @assert rows == nlp.pdemeta.Hrows && cols == nlp.pdemeta.Hcols "COO order differs from hess_structure!"
+  end
+  hd = Handle(h[], sharded, sharded ? 1 : memspace)
+  finalizer(release!, hd)        # the handle frees the device model when it is collected — with the model, see HANDLES
+  HANDLES[nlp] = hd
   return nlp
 end
 
-handle(nlp) = HANDLES[nlp]
-# callbacks arrive with contiguous whole-vector views (SURVEY §8b); anything else is staged
+handle(nlp) = HANDLES[nlp].ptr
+# Entry point of a callback: `pdenlp_<name>` for one device, `pdenlp_sharded_<name>` for the multi-GPU handle (same
+# argument lists).  ccall needs the symbol as a constant, hence the macro.
+macro pcall(name, argtypes, nlp, args...)
+  one = QuoteNode(Symbol("pdenlp_", name)); many = QuoteNode(Symbol("pdenlp_sharded_", name))
+  quote
+    local hd = HANDLES[$(esc(nlp))]
+    check(hd.sharded ? ccall(($many, LIB), Cint, $(esc(argtypes)), hd.ptr, $(map(esc, args)...)) :
+                       ccall(($one, LIB), Cint, $(esc(argtypes)), hd.ptr, $(map(esc, args)...)))
+  end
+end
+# callbacks arrive with contiguous whole-vector views (SURVEY §8b); anything else is staged.  DeviceVectors pass through.
+dense(v::DeviceVector) = v
 dense(v::StridedVector{Float64}) = stride(v, 1) == 1 ? v : collect(v)
 dense(v) = collect(Float64, v)
 
@@ -114,7 +232,7 @@ function obj(nlp::GridapPDENLPModel, x::AbstractVector)                       # 
   @lencheck nlp.meta.nvar x
   increment!(nlp, :neval_obj)
   f = Ref{Float64}()
-  check(ccall((:pdenlp_obj, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}), handle(nlp), dense(x), f))
+  @pcall(obj, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}), nlp, dense(x), f)
   return f[]
 end
 
@@ -122,7 +240,7 @@ function grad!(nlp::GridapPDENLPModel, x::AbstractVector, g::AbstractVector)   #
   @lencheck nlp.meta.nvar x g
   increment!(nlp, :neval_grad)
   out = dense(g)
-  check(ccall((:pdenlp_grad, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), handle(nlp), dense(x), out))
+  @pcall(grad, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), nlp, dense(x), out)
   out === g || copyto!(g, out)
   return g
 end
@@ -130,9 +248,10 @@ end
 # optional override of the NLPModels default (obj then grad!): one sweep over the cells for both
 function objgrad!(nlp::GridapPDENLPModel, x::AbstractVector, g::AbstractVector)
   @lencheck nlp.meta.nvar x g
+  HANDLES[nlp].sharded && return obj(nlp, x), grad!(nlp, x, g)   # (no fused entry point on the multi-GPU handle)
   increment!(nlp, :neval_obj); increment!(nlp, :neval_grad)
   out = dense(g); f = Ref{Float64}(0.0)
-  check(ccall((:pdenlp_objgrad, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}), handle(nlp), dense(x), f, out))
+  @pcall(objgrad, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}), nlp, dense(x), f, out)
   out === g || copyto!(g, out)
   return f[], g
 end
@@ -142,7 +261,7 @@ function cons_nln!(nlp::GridapPDENLPModel, x::AbstractVector, c::AbstractVector)
   @lencheck nlp.meta.nnln c
   increment!(nlp, :neval_cons_nln)
   out = dense(c)
-  check(ccall((:pdenlp_cons, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), handle(nlp), dense(x), out))
+  @pcall(cons, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), nlp, dense(x), out)
   out === c || copyto!(c, out)
   return c
 end
@@ -152,7 +271,7 @@ function jac_nln_coord!(nlp::GridapPDENLPModel, x::AbstractVector, vals::Abstrac
   @lencheck nlp.meta.nln_nnzj vals
   increment!(nlp, :neval_jac_nln)
   out = dense(vals)
-  check(ccall((:pdenlp_jac_coord, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), handle(nlp), dense(x), out))
+  @pcall(jac_coord, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), nlp, dense(x), out)
   out === vals || copyto!(vals, out)
   return vals
 end
@@ -162,8 +281,7 @@ function hess_coord!(nlp::GridapPDENLPModel, x::AbstractVector{T}, vals::Abstrac
   @lencheck nlp.meta.nnzh vals
   increment!(nlp, :neval_hess)
   out = dense(vals)
-  check(ccall((:pdenlp_hess_coord, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cdouble, Ptr{Float64}),
-              handle(nlp), dense(x), C_NULL, obj_weight, out))
+  @pcall(hess_coord, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cdouble, Ptr{Float64}), nlp, dense(x), C_NULL, obj_weight, out)
   out === vals || copyto!(vals, out)
   return vals
 end
@@ -175,8 +293,7 @@ function hess_coord!(nlp::GridapPDENLPModel, x::AbstractVector{T}, λ::AbstractV
   @lencheck nlp.meta.nnzh vals
   increment!(nlp, :neval_hess)
   out = dense(vals)
-  check(ccall((:pdenlp_hess_coord, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cdouble, Ptr{Float64}),
-              handle(nlp), dense(x), dense(λ), obj_weight, out))
+  @pcall(hess_coord, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cdouble, Ptr{Float64}), nlp, dense(x), dense(λ), obj_weight, out)
   out === vals || copyto!(vals, out)
   return vals
 end
@@ -186,7 +303,7 @@ function jprod_nln!(nlp::GridapPDENLPModel, x::AbstractVector, v::AbstractVector
   @lencheck nlp.meta.nnln Jv
   increment!(nlp, :neval_jprod_nln)      # net effect of the reference's increment/decrement pair (:483-484)
   out = dense(Jv)
-  check(ccall((:pdenlp_jprod, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), handle(nlp), dense(x), dense(v), out))
+  @pcall(jprod, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), nlp, dense(x), dense(v), out)
   out === Jv || copyto!(Jv, out)
   return Jv
 end
@@ -196,7 +313,7 @@ function jtprod_nln!(nlp::GridapPDENLPModel, x::AbstractVector, v::AbstractVecto
   @lencheck nlp.meta.nnln v
   increment!(nlp, :neval_jtprod_nln)
   out = dense(Jtv)
-  check(ccall((:pdenlp_jtprod, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), handle(nlp), dense(x), dense(v), out))
+  @pcall(jtprod, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), nlp, dense(x), dense(v), out)
   out === Jtv || copyto!(Jtv, out)
   return Jtv
 end
@@ -205,8 +322,7 @@ function hprod!(nlp::GridapPDENLPModel, x::AbstractVector{T}, v::AbstractVector,
   @lencheck nlp.meta.nvar x v Hv
   increment!(nlp, :neval_hprod)
   out = dense(Hv)
-  check(ccall((:pdenlp_hprod, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cdouble, Ptr{Float64}, Ptr{Float64}),
-              handle(nlp), dense(x), C_NULL, obj_weight, dense(v), out))
+  @pcall(hprod, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cdouble, Ptr{Float64}, Ptr{Float64}), nlp, dense(x), C_NULL, obj_weight, dense(v), out)
   out === Hv || copyto!(Hv, out)
   return Hv
 end
@@ -217,8 +333,7 @@ function hprod!(nlp::GridapPDENLPModel, x::AbstractVector{T}, λ::AbstractVector
   @lencheck nlp.meta.ncon λ
   increment!(nlp, :neval_hprod)
   out = dense(Hv)
-  check(ccall((:pdenlp_hprod, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cdouble, Ptr{Float64}, Ptr{Float64}),
-              handle(nlp), dense(x), dense(λ), obj_weight, dense(v), out))
+  @pcall(hprod, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cdouble, Ptr{Float64}, Ptr{Float64}), nlp, dense(x), dense(λ), obj_weight, dense(v), out)
   out === Hv || copyto!(Hv, out)
   return Hv
 end

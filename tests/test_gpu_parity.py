@@ -193,8 +193,10 @@ def test_host_memspace_slab_stages_only_its_dof_ranges(pkg):
         kc = np.zeros(m, bool); kc[ylo:yhi] = True
         lh[~kc] = np.nan
         tol = dict(rtol=1e-12, atol=1e-13)
-        assert np.array_equal(nh.jac_coord(xh), nd.jac_coord(_d(x)).cpu().numpy())
-        assert np.array_equal(nh.hess_coord(xh, lh, obj_weight=0.5), nd.hess_coord(_d(x), _d(lam), obj_weight=0.5).cpu().numpy())
+        # (FE segments are bitwise reproducible; the dense kappa blocks are sums over cells through atomics: round-off)
+        same = np.array_equal if p == 0 else (lambda a, b: np.allclose(a, b, **tol))
+        assert same(nh.jac_coord(xh), nd.jac_coord(_d(x)).cpu().numpy())
+        assert same(nh.hess_coord(xh, lh, obj_weight=0.5), nd.hess_coord(_d(x), _d(lam), obj_weight=0.5).cpu().numpy())
         assert np.allclose(nh.grad(xh), nd.grad(_d(x)).cpu().numpy(), **tol)
         assert np.allclose(nh.cons(xh), nd.cons(_d(x)).cpu().numpy(), **tol)
         assert np.allclose(nh.jprod(xh, vh), nd.jprod(_d(x), _d(v)).cpu().numpy(), **tol)
