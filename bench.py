@@ -440,7 +440,10 @@ def main():
     ncell = spec.model.ncells
     c0, c1 = slab(ncell, rank, world)
     fm = flatten(spec, (c0, c1), with_coef=False)
+    t_create = time.perf_counter()
     nlp = GridapPDENLPModel(spec, device=dev, flat=fm, with_coef=False)
+    torch.cuda.synchronize()
+    t_create = time.perf_counter() - t_create  # pdenlp_create: upload, tile offsets, tile classification, self-check
     info = nlp.handle.info
     t_setup = time.perf_counter() - t_setup
 
@@ -531,6 +534,7 @@ def main():
                 "parallelism": f"cell slabs x{world}, no data-path collective",
                 "l2": "streams > L2 every step (10.0 GB of outputs, 0.5 GB of inputs per step at N=1)",
                 "x": "U(-1,1) seed 1998, lambda U(-1,1) seed 1999", "setup_s": round(t_setup, 2),
+                "create_s": round(t_create, 3),
             },
             "jac_ms": jac_ms_max, "hess_ms": hess_ms_max,
             "roofline": {

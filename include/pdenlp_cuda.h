@@ -181,8 +181,16 @@ typedef struct pdenlp_desc {
   const double* cell_jinvT; /* [ncells][geom_nq][dim][dim] */
   const double* cell_detj;  /* [ncells][geom_nq]           */
   int32_t geom_nq;          /* 0 (no per-cell geometry), 1 or nq */
-  int32_t reserved0;
+  int32_t flags;            /* PDENLP_FLAG_* (0 = defaults; the former reserved word) */
 } pdenlp_desc;
+
+/* Deterministic accumulation.  By default the dof-indexed outputs (grad!, cons!, jprod!, jtprod!, hprod!, the dense
+   kappa blocks) are summed with floating-point atomics: equal to the reference's cell-ordered sums up to round-off, not
+   bitwise reproducible from run to run.  With this flag the cells are coloured once at create time (greedy: no two
+   cells of a colour share a free dof) and those callbacks run one launch per colour with plain read-modify-write
+   stores, so every entry is summed in a fixed order — bitwise identical results on every run, at 1.5-3x the time of
+   the atomic kernels.  jac_coord!/hess_coord! FE segments and obj are deterministic either way. */
+#define PDENLP_FLAG_DETERMINISTIC 1
 
 typedef struct pdenlp_model pdenlp_model; /* opaque */
 

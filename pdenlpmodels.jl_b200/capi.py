@@ -19,6 +19,7 @@ LIB_PATH = os.environ.get("PDENLP_CUDA_LIB") or os.path.join(HERE, "csrc", "libp
 ABI_VERSION = 3
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = 0, -1, -2, -3, -4
 MEM_DEVICE, MEM_HOST = 0, 1
+FLAG_DETERMINISTIC = 1
 
 # every symbol include/pdenlp_cuda.h declares
 SYMBOLS = [
@@ -46,7 +47,7 @@ class Desc(C.Structure):
         ("ncoef", C.c_int32), ("nfields_u", C.c_int32), ("coef", C.c_void_p),
         ("params", C.c_double * 8),
         ("field_nfree", C.c_void_p), ("field_ndir", C.c_void_p),
-        ("cell_jinvT", C.c_void_p), ("cell_detj", C.c_void_p), ("geom_nq", C.c_int32), ("reserved0", C.c_int32),
+        ("cell_jinvT", C.c_void_p), ("cell_detj", C.c_void_p), ("geom_nq", C.c_int32), ("flags", C.c_int32),
     ]
 
 
@@ -153,7 +154,7 @@ def _np_ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
 
 
-def build_desc(fm, device: int = -1, memspace: int = MEM_DEVICE, with_coef: bool = True):
+def build_desc(fm, device: int = -1, memspace: int = MEM_DEVICE, with_coef: bool = True, flags: int = 0):
     """pdenlp_desc of a FlatModel plus the arrays it points at (keep them alive until pdenlp_create returns)."""
     d = Desc()
     d.abi_version = ABI_VERSION
@@ -161,6 +162,7 @@ def build_desc(fm, device: int = -1, memspace: int = MEM_DEVICE, with_coef: bool
     d.dim, d.ny, d.nu, d.nq, d.nparam = fm.dim, fm.ny, fm.nu, fm.nq, fm.nparam
     d.memspace = memspace
     d.device = device
+    d.flags = flags
     d.ncells, d.nfree_y, d.nfree_u = fm.ncells, fm.nfree_y, fm.nfree_u
     d.ndir_y, d.ndir_u = fm.dir_y.size, fm.dir_u.size
     keep = [np.ascontiguousarray(fm.cell_dofs_y, np.int32), np.ascontiguousarray(fm.cell_dofs_u, np.int32),
@@ -282,9 +284,9 @@ class ShardedHandle:
 class Handle:
     """Owns one ``pdenlp_model*`` created from a FlatModel (one cell slab on one GPU)."""
 
-    def __init__(self, fm, device: int = -1, memspace: int = MEM_DEVICE, with_coef: bool = True):
+    def __init__(self, fm, device: int = -1, memspace: int = MEM_DEVICE, with_coef: bool = True, flags: int = 0):
         lib = load()
-        d, keep = build_desc(fm, device, memspace, with_coef)
+        d, keep = build_desc(fm, device, memspace, with_coef, flags)
         h = C.c_void_p()
         check(lib.pdenlp_create(C.byref(d), C.byref(h)))
         del keep

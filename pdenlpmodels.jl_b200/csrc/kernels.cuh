@@ -132,6 +132,11 @@ struct DevModel {
   int32_t ntiles;
   int32_t nparam;
   int32_t notrait;         // 1: ignore the trait-selected shortcuts (self-check: generic per-point evaluation)
+  // ---- deterministic mode (PDENLP_FLAG_DETERMINISTIC): the dof-indexed kernels run once per COLOUR of a greedy cell
+  // colouring (cells of one colour share no free dof), over the colour's cell list and with plain read-modify-write
+  // instead of atomics: every dof receives its contributions in colour order — bitwise reproducible run to run
+  const int32_t* cell_list;  // cells of the colour being processed (nullptr: all cells, lane = cell, atomics)
+  int64_t nlist;
   // ---- template tiles (see "template tiles" below); tpl_list == nullptr: every tile takes the generic path
   const int32_t* tpl_list; // [ntpl] tiles whose image equals the template's, ascending
   const int32_t* gen_list; // [ngen] all other tiles, ascending
@@ -172,6 +177,20 @@ __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("grid
 template <int N>  // at most N of this thread's most recent bulk groups may still be reading shared memory
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// cell processed by lane `lane` of tile `tile`: tile*32 + lane, or the entry of the colour's cell list (deterministic mode)
+__device__ __forceinline__ int64_t lane_cell(const DevModel& D, int64_t tile, int lane, bool& valid) {
+  const int64_t idx = tile * 32 + lane;
+  if (D.cell_list == nullptr) { valid = tile < D.ntiles && idx < D.ncells; return valid ? idx : 0; }
+  valid = tile < D.ntiles && idx < D.nlist;
+  return valid ? (int64_t)__ldg(D.cell_list + idx) : 0;
+}
+// out[i] += v: atomically, or as a plain read-modify-write when the launch covers one colour (no two cells of the
+// launch touch the same dof)
+__device__ __forceinline__ void accumulate(const DevModel& D, double* p, double v) {
+  if (D.cell_list == nullptr) atomicAdd(p, v);
+  else *p += v;
+}
 
 // ------------------------------------------------------------------ per-lane cell data
 template <class E>
@@ -1898,11 +1917,11 @@ __device__ __forceinline__ void scatter_element(const DevModel& D, const Cell<E>
   double* ou = oy + D.nfree_y;
 #pragma unroll
   for (int a = 0; a < E::NY; ++a)
-    if (c.gy[a] > 0) atomicAdd(oy + (c.gy[a] - 1), ey[a]);
+    if (c.gy[a] > 0) accumulate(D, oy + (c.gy[a] - 1), ey[a]);
   if (E::NU > 0) {
 #pragma unroll
     for (int b = 0; b < E::NU; ++b)
-      if (c.gu[b] > 0) atomicAdd(ou + (c.gu[b] - 1), eu[b]);
+      if (c.gu[b] > 0) accumulate(D, ou + (c.gu[b] - 1), eu[b]);
   }
 }
 
@@ -1958,24 +1977,18 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
 
   const int64_t vstride = (int64_t)gridDim.x * kWarpsPerCta;
   Cell<E> c, nx;  // the dof ids of the next tile are loaded one iteration ahead
-  {
-    const int64_t t0 = (int64_t)blockIdx.x * kWarpsPerCta + warp;
-    const int64_t c0 = t0 * 32 + lane;
-    const bool v0 = t0 < D.ntiles && c0 < D.ncells;
-    load_ids<E>(D, v0 ? c0 : 0, v0, nx);
-  }
+  bool nvalid;
+  int64_t ncell = lane_cell(D, (int64_t)blockIdx.x * kWarpsPerCta + warp, lane, nvalid);
+  load_ids<E>(D, ncell, nvalid, nx);
   for (int64_t tile = (int64_t)blockIdx.x * kWarpsPerCta + warp; tile < D.ntiles; tile += vstride) {
-    const int64_t cell = tile * 32 + lane;
-    const bool valid = cell < D.ncells;
+    const int64_t cell = ncell;
+    const bool valid = nvalid;
 #pragma unroll
     for (int a = 0; a < E::NY; ++a) c.gy[a] = nx.gy[a];
 #pragma unroll
     for (int b = 0; b < E::NUS; ++b) c.gu[b] = nx.gu[b];
-    {
-      const int64_t c1 = (tile + vstride) * 32 + lane;
-      const bool v1 = (tile + vstride) < D.ntiles && c1 < D.ncells;
-      load_ids<E>(D, v1 ? c1 : 0, v1, nx);
-    }
+    ncell = lane_cell(D, tile + vstride, lane, nvalid);
+    load_ids<E>(D, ncell, nvalid, nx);
     gather_state<E>(D, x, valid, c);
     if (!valid) continue;
     double ey[E::NY], eu[E::NUS];  // element vector, summed over the quadrature points
@@ -2084,7 +2097,7 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
     if (OP == OP_CONS || OP == OP_OBJCONS || OP == OP_JPROD) {  // rows = free dofs of the test space
 #pragma unroll
       for (int i = 0; i < E::NY; ++i)
-        if (c.gy[i] > 0) atomicAdd(out + (c.gy[i] - 1), ey[i]);
+        if (c.gy[i] > 0) accumulate(D, out + (c.gy[i] - 1), ey[i]);
     }
   }
   // block-level reductions: objective partial sums (deterministic two-pass) and kappa entries
@@ -2158,8 +2171,8 @@ k_jac_kappa(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
   using I = typename E::Integrand;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int64_t tile = (int64_t)blockIdx.x * kWarpsPerCta + warp; tile < D.ntiles; tile += (int64_t)gridDim.x * kWarpsPerCta) {
-    const int64_t cell = tile * 32 + lane;
-    const bool valid = cell < D.ncells;
+    bool valid;
+    const int64_t cell = lane_cell(D, tile, lane, valid);
     if (!valid) continue;
     Cell<E> c;
     load_ids<E>(D, cell, valid, c);
@@ -2190,7 +2203,7 @@ k_jac_kappa(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
     for (int k = 0; k < E::NP; ++k)
 #pragma unroll
       for (int i = 0; i < E::NY; ++i)
-        if (c.gy[i] > 0) atomicAdd(vk + ((int64_t)k * D.nfree_y + (c.gy[i] - 1)), acc[k][i]);
+        if (c.gy[i] > 0) accumulate(D, vk + ((int64_t)k * D.nfree_y + (c.gy[i] - 1)), acc[k][i]);
   }
 }
 
@@ -2246,8 +2259,8 @@ k_hess_kappa_kk(const __grid_constant__ Tables<E> tab, const DevModel D, const d
 #pragma unroll
     for (int b = 0; b < NPS; ++b) kk[a][b] = 0.0;
   for (int64_t tile = (int64_t)blockIdx.x * kWarpsPerCta + warp; tile < D.ntiles; tile += (int64_t)gridDim.x * kWarpsPerCta) {
-    const int64_t cell = tile * 32 + lane;
-    const bool valid = cell < D.ncells;
+    bool valid;
+    const int64_t cell = lane_cell(D, tile, lane, valid);
     if (!valid) continue;
     Cell<E> c;
     load_ids<E>(D, cell, valid, c);
@@ -2296,8 +2309,8 @@ k_hess_kappa(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
     for (int b = 0; b < NPS; ++b) kk[a][b] = 0.0;
   const bool cross = prows > E::NP;
   for (int64_t tile = (int64_t)blockIdx.x * kWarpsPerCta + warp; tile < D.ntiles; tile += (int64_t)gridDim.x * kWarpsPerCta) {
-    const int64_t cell = tile * 32 + lane;
-    const bool valid = cell < D.ncells;
+    bool valid;
+    const int64_t cell = lane_cell(D, tile, lane, valid);
     if (!valid) continue;
     Cell<E> c;
     load_ids<E>(D, cell, valid, c);
@@ -2347,10 +2360,10 @@ k_hess_kappa(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
       for (int j = 0; j < E::NP; ++j) {
 #pragma unroll
         for (int a = 0; a < E::NY; ++a)
-          if (c.gy[a] > 0) atomicAdd(vk + trap_pos((int64_t)E::NP + c.gy[a], j + 1, prows), accy[j][a]);
+          if (c.gy[a] > 0) accumulate(D, vk + trap_pos((int64_t)E::NP + c.gy[a], j + 1, prows), accy[j][a]);
 #pragma unroll
         for (int b = 0; b < E::NU; ++b)
-          if (c.gu[b] > 0) atomicAdd(vk + trap_pos((int64_t)E::NP + D.nfree_y + c.gu[b], j + 1, prows), accu[j][b]);
+          if (c.gu[b] > 0) accumulate(D, vk + trap_pos((int64_t)E::NP + D.nfree_y + c.gu[b], j + 1, prows), accu[j][b]);
       }
     }
   }

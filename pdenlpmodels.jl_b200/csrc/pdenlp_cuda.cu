@@ -64,6 +64,10 @@ struct pdenlp_model {
   // free-dof ranges [lo, hi) (0-based, concatenated numbering) the cells of this handle touch: a PDENLP_MEM_HOST model
   // stages only these parts of x / lambda / v (a slab of a sharded model needs its own rows of the mesh, not the whole vector)
   int64_t yr[2] = {0, 0}, ur[2] = {0, 0};
+  // deterministic mode (PDENLP_FLAG_DETERMINISTIC): greedy cell colouring, the cells of every colour as one list
+  bool deterministic = false;
+  int32_t* col_cells = nullptr;      // device: cells grouped by colour
+  std::vector<int64_t> col_off;      // [ncolours + 1]
   // template tiles (kernels.cuh): classification lists (host copies for the self-check's sample), image scratch
   bool tpl_active = false;
   int32_t tpl_tile = -1;
@@ -295,6 +299,65 @@ int classify_tiles(pdenlp_model* m, const pdenlp_desc& desc) {
   const int64_t z[2] = {0, 0};
   if (int r = dev_upload(m, z, 2, &m->zero_base)) return r;
   m->tpl_active = true;
+  return PDENLP_OK;
+}
+
+// Greedy colouring of the cells for the deterministic mode: a cell takes the lowest colour none of its free dofs has
+// seen yet (one 64-bit mask per dof), so two cells of a colour never share a free dof and a launch over one colour can
+// accumulate with plain stores.  Structured meshes need 2^dim colours.
+int colour_cells(pdenlp_model* m, const pdenlp_desc& desc, const std::vector<int64_t>& offf, int nfy, int nfu) {
+  const int64_t nc = desc.ncells;
+  const int ny = nfy * desc.ny, nu = nfu * desc.nu;
+  std::vector<uint64_t> masky((size_t)desc.nfree_y, 0), masku((size_t)std::max<int64_t>(desc.nfree_u, 1), 0);
+  std::vector<uint8_t> colour((size_t)nc);
+  std::vector<int64_t> count(64, 0);
+  int ncol = 0;
+  for (int64_t c = 0; c < nc; ++c) {
+    uint64_t used = 0;
+    for (int a = 0; a < ny; ++a) {
+      const int64_t g = desc.cell_dofs_y[c * ny + a];
+      if (g > 0) used |= masky[(size_t)(g + offf[a / desc.ny] - 1)];
+    }
+    for (int b = 0; b < nu; ++b) {
+      const int64_t g = desc.cell_dofs_u[c * nu + b];
+      if (g > 0) used |= masku[(size_t)(g + offf[nfy + b / desc.nu] - 1)];
+    }
+    if (used == ~0ull) return fail(PDENLP_EUNSUPPORTED, "deterministic mode: more than 64 colours needed");
+    const int k = __builtin_ctzll(~used);
+    colour[(size_t)c] = (uint8_t)k;
+    ncol = std::max(ncol, k + 1);
+    ++count[k];
+    const uint64_t bit = 1ull << k;
+    for (int a = 0; a < ny; ++a) {
+      const int64_t g = desc.cell_dofs_y[c * ny + a];
+      if (g > 0) masky[(size_t)(g + offf[a / desc.ny] - 1)] |= bit;
+    }
+    for (int b = 0; b < nu; ++b) {
+      const int64_t g = desc.cell_dofs_u[c * nu + b];
+      if (g > 0) masku[(size_t)(g + offf[nfy + b / desc.nu] - 1)] |= bit;
+    }
+  }
+  m->col_off.assign(ncol + 1, 0);
+  for (int k = 0; k < ncol; ++k) m->col_off[k + 1] = m->col_off[k] + count[k];
+  std::vector<int64_t> pos(m->col_off.begin(), m->col_off.end() - 1);
+  std::vector<int32_t> cells((size_t)nc);
+  for (int64_t c = 0; c < nc; ++c) cells[(size_t)pos[colour[(size_t)c]]++] = (int32_t)c;  // ascending inside a colour
+  if (int rc = dev_upload(m, cells.data(), cells.size(), &m->col_cells)) return rc;
+  m->deterministic = true;
+  return PDENLP_OK;
+}
+// run `launch(DevModel of one colour)` for every colour (deterministic mode) or once on the whole model
+template <class F>
+int for_each_colour(pdenlp_model* m, F&& launch) {
+  if (!m->deterministic) return launch(m->dm, false);
+  for (size_t k = 0; k + 1 < m->col_off.size(); ++k) {
+    DevModel d = m->dm;
+    d.cell_list = m->col_cells + m->col_off[k];
+    d.nlist = m->col_off[k + 1] - m->col_off[k];
+    d.ntiles = (int32_t)((d.nlist + 31) / 32);
+    if (d.nlist == 0) continue;
+    if (int rc = launch(d, true)) return rc;
+  }
   return PDENLP_OK;
 }
 
@@ -536,6 +599,7 @@ int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
   m->dm.nparam = desc->nparam;
   m->dm.base_jy = m->dm.base_ju = m->dm.base_h = nullptr;
   m->dm.ktab = nullptr;
+  m->dm.cell_list = nullptr; m->dm.nlist = 0;
   m->dm.tpl_list = m->dm.gen_list = nullptr;
   m->dm.ntpl = 0; m->dm.ngen = 0;
   m->dm.tpl_jy = m->dm.tpl_ju = m->dm.tpl_h = nullptr;
@@ -620,6 +684,7 @@ int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
   if (cudaEventCreate(&m->ev0) != cudaSuccess || cudaEventCreate(&m->ev1) != cudaSuccess)
     return bail(fail(PDENLP_ECUDA, "cudaEventCreate failed"));
   if ((rc = classify_tiles(m, *desc))) return bail(rc);
+  if (desc->flags & PDENLP_FLAG_DETERMINISTIC) { if ((rc = colour_cells(m, *desc, offf, nfy, nfu))) return bail(rc); }
   if ((rc = self_check(m, &m->selfcheck_err))) return bail(rc);
   // the host arrays of the description are not referenced after create
   m->d.cell_dofs_y = m->d.cell_dofs_u = nullptr;
@@ -713,7 +778,12 @@ static int vec_call(pdenlp_model* m, int op, const double* x, const double* lam,
   // NoFETerm objective: the FE part of grad! is zero (additional_obj_terms.jl:82), hprod! keeps its constraint part
   const bool skip_fe = m->nofe && (op == OP_GRAD || (op == OP_HPROD && dl == nullptr));
   if (!skip_fe) {
-    if (int rc = m->ops->vec(L, m->dm, op, dx, dl, dv, ow, dout, m->partials, &nb)) return rc;
+    // (deterministic mode: one launch of the generic kernel per colour, plain read-modify-write accumulation)
+    if (int rc = for_each_colour(m, [&](const DevModel& d, bool coloured) {
+          Launch Lc = L;
+          Lc.generic = coloured;
+          return m->ops->vec(Lc, d, op, dx, dl, dv, ow, dout, m->partials, &nb);
+        })) return rc;
   }
   if (m->nofe && m->d.nparam > 0 && (op == OP_GRAD || op == OP_HPROD)) {
     if (int rc = m->ops->nofe(L, op == OP_GRAD ? NOFE_GRAD : NOFE_HPROD, dx, ow, dv, dout)) return rc;
@@ -725,7 +795,7 @@ static int vec_call(pdenlp_model* m, int op, const double* x, const double* lam,
 static int obj_and_vector(pdenlp_model* m, int op, const double* x, double* f, double* out, int64_t n,
                           int (*vector_only)(pdenlp_model*, const double*, double*)) {
   if (!m || !x || !f || !out) return fail(PDENLP_EINVAL, "null argument");
-  if (m->nofe) {  // NoFETerm: the objective comes from the one-thread kernel
+  if (m->nofe || m->deterministic) {  // NoFETerm: the objective comes from the one-thread kernel; deterministic: per colour
     if (int rc = pdenlp_obj(m, x, f)) return rc;
     return vector_only(m, x, out);
   }
@@ -785,7 +855,11 @@ int pdenlp_jac_coord(pdenlp_model* m, const double* x, double* vals) {
   if (m->info.nnzj_k > 0) {
     if (!m->dm.coef) return fail(PDENLP_EINVAL, "the kappa block needs the coefficient fields (desc.coef)");
     CU(cudaMemsetAsync(dv, 0, (size_t)m->info.nnzj_k * 8, m->stream));
-    if (int rc = m->ops->jac_kappa(L, m->dm, dx, dv, m->partials)) return rc;
+    if (int rc = for_each_colour(m, [&](const DevModel& d, bool coloured) {
+          Launch Lc = L;
+          Lc.generic = coloured;
+          return m->ops->jac_kappa(Lc, d, dx, dv, m->partials);
+        })) return rc;
   }
   double* vy = dv + m->info.nnzj_k;
   double* vu = vy + m->info.nnzj_y;
@@ -816,10 +890,18 @@ int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda, do
     if (m->nofe) {
       if (int rc = m->ops->nofe(L, NOFE_HESS, dx, obj_weight, nullptr, vko)) return rc;
     } else {
-      if (int rc = m->ops->hess_kappa(L, m->dm, dx, nullptr, obj_weight, 0, m->inde ? m->d.nparam : I.nvar, vko, m->partials)) return rc;
+      if (int rc = for_each_colour(m, [&](const DevModel& d, bool coloured) {
+            Launch Lc = L;
+            Lc.generic = coloured;
+            return m->ops->hess_kappa(Lc, d, dx, nullptr, obj_weight, 0, m->inde ? m->d.nparam : I.nvar, vko, m->partials);
+          })) return rc;
     }
     if (dl) {
-      if (int rc = m->ops->hess_kappa(L, m->dm, dx, dl, 1.0, 1, I.nvar, vkc, m->partials)) return rc;
+      if (int rc = for_each_colour(m, [&](const DevModel& d, bool coloured) {
+            Launch Lc = L;
+            Lc.generic = coloured;
+            return m->ops->hess_kappa(Lc, d, dx, dl, 1.0, 1, I.nvar, vkc, m->partials);
+          })) return rc;
     }
   }
   // The constraint FE block is a pure zero fill when no multipliers are given (GridapPDENLPModel.jl:295-297)
@@ -871,7 +953,11 @@ int pdenlp_hess_coord_obj(pdenlp_model* m, const double* x, double obj_weight, d
     if (m->nofe) {
       if (int rc = m->ops->nofe(L, NOFE_HESS, dx, obj_weight, nullptr, dv)) return rc;
     } else {
-      if (int rc = m->ops->hess_kappa(L, m->dm, dx, nullptr, obj_weight, 0, m->inde ? m->d.nparam : I.nvar, dv, m->partials)) return rc;
+      if (int rc = for_each_colour(m, [&](const DevModel& d, bool coloured) {
+            Launch Lc = L;
+            Lc.generic = coloured;
+            return m->ops->hess_kappa(Lc, d, dx, nullptr, obj_weight, 0, m->inde ? m->d.nparam : I.nvar, dv, m->partials);
+          })) return rc;
     }
   }
   if (!m->nofe) {

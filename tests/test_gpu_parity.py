@@ -206,6 +206,39 @@ def test_host_memspace_slab_stages_only_its_dof_ranges(pkg):
         nh.close(); nd.close()
 
 
+def test_deterministic_mode_is_bitwise_reproducible_and_equal_to_the_atomic_path(pkg):
+    """PDENLP_FLAG_DETERMINISTIC: coloured launches with plain read-modify-write accumulation.  Every dof-indexed output
+    and the dense kappa blocks must (a) agree with the default (atomic) kernels to round-off and (b) be bitwise identical
+    over repeated evaluations — also against a second model of the same problem (fresh colouring, fresh buffers)."""
+    from pdenlp_b200.model import GridapPDENLPModel
+    for spec in (pkg.controlelasticmembrane(40), pkg.poissonmixed(24, 2, True), pkg.burger1d_param(3000), pkg.poissonboltzman2d(48)):
+        nd = GridapPDENLPModel(spec, device="cuda:0")
+        n1 = GridapPDENLPModel(spec, device="cuda:0", deterministic=True)
+        n2 = GridapPDENLPModel(spec, device="cuda:0", deterministic=True)
+        n, m, p = nd.meta.nvar, nd.meta.ncon, spec.nparam
+        g = np.random.default_rng(7)
+        x, lam, v = g.uniform(-1, 1, n), g.uniform(-1, 1, m), g.uniform(-1, 1, n)
+        if p:
+            x[:p] = 1 + 0.1 * g.uniform(-1, 1, p)
+        x, lam, v = _d(x), _d(lam), _d(v)
+        calls = {
+            "grad": lambda q: q.grad(x), "cons": lambda q: q.cons(x), "jprod": lambda q: q.jprod(x, v),
+            "jtprod": lambda q: q.jtprod(x, lam), "hprod": lambda q: q.hprod(x, lam, v, obj_weight=0.37),
+            "jac_coord": lambda q: q.jac_coord(x), "hess_coord": lambda q: q.hess_coord(x, lam, obj_weight=0.37),
+            "objgrad": lambda q: q.objgrad(x)[1],
+        }
+        for name, fn in calls.items():
+            ref = fn(nd).cpu().numpy()
+            a = fn(n1).cpu().numpy()
+            _close(a, ref, f"{spec.name} {name} deterministic vs atomic")
+            for _ in range(3):
+                assert np.array_equal(fn(n1).cpu().numpy(), a), f"{spec.name} {name}: not reproducible"
+            assert np.array_equal(fn(n2).cpu().numpy(), a), f"{spec.name} {name}: differs between two models"
+        assert abs(n1.obj(x) - nd.obj(x)) <= 1e-12 * max(1.0, abs(nd.obj(x)))
+        for q in (nd, n1, n2):
+            q.close()
+
+
 def test_unaligned_guarded_outputs(case):
     """Outputs that are only 8 B aligned (a view starting at an odd element) with sentinel guards on
     both sides: exercises the head/tail handling of the 16 B-aligned bulk stores and catches any
