@@ -14,7 +14,7 @@ class _Info:
 
 
 class FakeHandle:
-    def __init__(self, fm, device=-1, memspace=0, with_coef=True):
+    def __init__(self, fm, device=-1, memspace=0, with_coef=True, flags=0):
         self.info = _Info(); self.calls = []; self.memspace = memspace
 
     def set_stream(self, s): pass
