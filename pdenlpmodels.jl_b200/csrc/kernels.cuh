@@ -144,6 +144,18 @@ struct DevModel {
   const double* tpl_jy;    // [32*RUN_JY] image of one template tile of the Jacobian y-block (model-owned scratch)
   const double* tpl_ju;    // [32*RUN_JU]
   const double* tpl_h;     // [32*RUN_H]  objective FE Hessian block
+  // ---- cell-granular templates (see "cell-granular templates" below); ch_n == nullptr: not in use.  The slab's cells
+  // are either members of a CHUNK (<= 32 consecutive template cells = one contiguous run of every COO segment, stored
+  // from the shared-memory image with one bulk copy) or GENERIC cells (evaluated one per lane, stored directly).
+  const int64_t* ch_jy;    // [nchunk] first entry of the chunk in the Jacobian y-block
+  const int64_t* ch_ju;    // [nchunk]   ... u-block
+  const int64_t* ch_h;     // [nchunk]   ... FE Hessian block
+  const uint8_t* ch_n;     // [nchunk] cells of the chunk (1..32)
+  const int32_t* gc_cell;  // [ngc] generic cells, ascending
+  const int64_t* gc_jy;    // [ngc] first entry of the cell in each segment
+  const int64_t* gc_ju;
+  const int64_t* gc_h;
+  int32_t nchunk, ngc;
 };
 
 // ------------------------------------------------------------------ small device helpers
@@ -778,6 +790,22 @@ __global__ void __launch_bounds__(kThreads) k_tile_class(DevModel D, unsigned lo
   const bool ok = __all_sync(0xffffffffu, af && sy == sig_y && su == sig_u);
   if (lane == 0) cls[tile] = ok ? 1 : 0;
 }
+// mask[tile] bit l = 1 iff cell 32*tile + l is a template cell (valid, all dofs free, template id order)
+template <class E>
+__global__ void __launch_bounds__(kThreads) k_cell_class(DevModel D, unsigned long long sig_y, unsigned long long sig_u, uint32_t* __restrict__ mask) {
+  const int lane = threadIdx.x & 31;
+  const int64_t tile = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (tile >= D.ntiles) return;
+  const int64_t cell = tile * 32 + lane;
+  const bool valid = cell < D.ncells;
+  Cell<E> c;
+  load_ids<E>(D, valid ? cell : 0, valid, c);
+  bool af;
+  unsigned long long sy, su;
+  cell_signature<E>(c, valid, af, sy, su);
+  const unsigned b = __ballot_sync(0xffffffffu, af && sy == sig_y && su == sig_u);
+  if (lane == 0) mask[tile] = b;
+}
 // one contiguous run of n doubles from a shared-memory image to global memory; img0 / img1 are the two copies of the
 // image whose FIRST element sits at an even / odd double offset (bulk copies need 16 B alignment on both sides)
 __device__ __forceinline__ void store_template(double* g, const double* img0, const double* img1, int n) {
@@ -799,6 +827,52 @@ __device__ __forceinline__ void load_template(const double* __restrict__ g, doub
     const double v = __ldg(g + i);
     t0[i] = v;
     t1[i + 1] = v;
+  }
+}
+
+// ---- per-point emitters of the Jacobian blocks (single-field elements): quadrature point q adds its contribution to
+// the cell's kept entries at p[0..) (q == 0 stores, q > 0 accumulates); column dof outer, row dof inner
+//   y-block:  A_e[i][j] = sum_q w sum_t T_i[t] sum_k dR_t/ds_k By_j[k]
+template <class E>
+__device__ __forceinline__ void emit_jac_y_pt(const Tables<E>& tab, int q, double w, const Jet1<E::M> (&R)[E::NR], const Cell<E>& c, double* p) {
+#pragma unroll
+  for (int j = 0; j < E::NY; ++j) {
+    double Mj[E::NR];
+#pragma unroll
+    for (int t = 0; t < E::NR; ++t) {
+      double a = 0.0;
+#pragma unroll
+      for (int k = 0; k < E::NB; ++k) a = fma(R[t].g[k], tab.By[q][j][k], a);
+      Mj[t] = a * w;
+    }
+    if (c.gy[j] > 0) {
+#pragma unroll
+      for (int i = 0; i < E::NY; ++i) {
+        double v = 0.0;
+#pragma unroll
+        for (int t = 0; t < E::NR; ++t) v = fma(test_slot<E>(tab, q, i, t), Mj[t], v);
+        if (c.gy[i] > 0) { if (q == 0) *p = v; else *p += v; ++p; }
+      }
+    }
+  }
+}
+//   u-block:  B_e[i][b] = sum_q w sum_t T_i[t] dR_t/du psi_b
+template <class E>
+__device__ __forceinline__ void emit_jac_u_pt(const Tables<E>& tab, int q, double w, const Jet1<E::M> (&R)[E::NR], const Cell<E>& c, double* p) {
+#pragma unroll
+  for (int b = 0; b < E::NU; ++b) {
+    double Mb[E::NR];
+#pragma unroll
+    for (int t = 0; t < E::NR; ++t) Mb[t] = R[t].g[E::SU] * tab.Bu[q][b] * w;
+    if (c.gu[b] > 0) {
+#pragma unroll
+      for (int i = 0; i < E::NY; ++i) {
+        double v = 0.0;
+#pragma unroll
+        for (int t = 0; t < E::NR; ++t) v = fma(test_slot<E>(tab, q, i, t), Mb[t], v);
+        if (c.gy[i] > 0) { if (q == 0) *p = v; else *p += v; ++p; }
+      }
+    }
   }
 }
 
@@ -1024,27 +1098,7 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
         const PointGeo<E> pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
         point_state<E>(tab, pc, c, x, q, s);
         eval_res<E>(pc, s, R);
-        double* p = p0;
-#pragma unroll
-        for (int j = 0; j < E::NY; ++j) {
-          double Mj[E::NR];
-#pragma unroll
-          for (int t = 0; t < E::NR; ++t) {
-            double a = 0.0;
-#pragma unroll
-            for (int k = 0; k < E::NB; ++k) a = fma(R[t].g[k], tab.By[q][j][k], a);
-            Mj[t] = a * pc.w;
-          }
-          if (c.gy[j] > 0) {
-#pragma unroll
-            for (int i = 0; i < E::NY; ++i) {
-              double v = 0.0;
-#pragma unroll
-              for (int t = 0; t < E::NR; ++t) v = fma(test_slot<E>(tab, q, i, t), Mj[t], v);
-              if (c.gy[i] > 0) { if (q == 0) *p = v; else *p += v; ++p; }
-            }
-          }
-        }
+        emit_jac_y_pt<E>(tab, q, pc.w, R, c, p0);
       }
       sty.release(gdst, incl - cnt, incl, lane);
     }
@@ -1073,22 +1127,7 @@ k_jac_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doubl
         const PointGeo<E> pc = point_ctx<E>(D, tab, cell, valid, q, I::NEEDS_COEF_DERIV);
         point_state<E>(tab, pc, c, x, q, s);
         eval_res<E>(pc, s, R);
-        double* p = p0;
-#pragma unroll
-        for (int b = 0; b < E::NU; ++b) {
-          double Mb[E::NR];
-#pragma unroll
-          for (int t = 0; t < E::NR; ++t) Mb[t] = R[t].g[E::SU] * tab.Bu[q][b] * pc.w;
-          if (c.gu[b] > 0) {
-#pragma unroll
-            for (int i = 0; i < E::NY; ++i) {
-              double v = 0.0;
-#pragma unroll
-              for (int t = 0; t < E::NR; ++t) v = fma(test_slot<E>(tab, q, i, t), Mb[t], v);
-              if (c.gy[i] > 0) { if (q == 0) *p = v; else *p += v; ++p; }
-            }
-          }
-        }
+        emit_jac_u_pt<E>(tab, q, pc.w, R, c, p0);
       }
       stu.release(gdst, incl - cnt, incl, lane);
     }
@@ -1478,6 +1517,292 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
     kt += stride;
   }
   st.drain(lane);
+}
+
+
+// ------------------------------------------------------------------ cell-granular templates
+// The template-tile idea at the granularity of cells.  The image of a template TILE is 32 copies of the image of a
+// template CELL (same values, same kept entries, cell after cell), so any run of n <= 32 consecutive template cells is
+// the first n*RUN doubles of the tile image: pdenlp_create cuts the slab into CHUNKS (maximal runs of template cells,
+// split every 32 cells, each with the offset of its first entry in every segment) and a compact list of the remaining
+// GENERIC cells (boundary layers: 0.2 % of config 2, 4.6 % of config 5) with their offsets.
+// Two launches, one CTA per unit of work, like the zero fill (the fastest write stream measured on this part is a
+// non-persistent grid of plain 16 B stores — 7.4 TB/s against 6.4 TB/s for TMA bulk stores):
+//   * k_copy_chunks: one chunk per CTA — it copies the first n*RUN doubles of the image (global scratch, L1 hits
+//     after the first touch) to the chunk's run with 16 B stores; no dof ids, no x, no arithmetic, ~30 registers.
+//   * k_jac_cells_cg / k_hess_cells_cg: 256 generic cells per CTA.  They are scattered, so a staged image would not
+//     be one run.  Elements on the reference-tensor path evaluate lane = cell and then emit lane = ENTRY, cell after
+//     cell (the cell's derivative data is broadcast by shuffles, the kept entries are ranked by popcounts /
+//     ballots): the stores of a cell are contiguous across the lanes.  (Lane = cell stores cost one 32 B sector
+//     request per 8 B entry: 55 us for the 97 k boundary cells of config 5.)  One-point elements emit lane = cell
+//     straight to global memory (config 2: 0.2 % of the cells).  The host runs this launch, together with the
+//     latency-bound kappa-block kernels, on the model's auxiliary stream, concurrently with the chunk copy.
+// Same arithmetic as the tile kernels, entry by entry (same fma chains; terms the tile kernels skip are exact zeros).
+__device__ __forceinline__ void copy_image(double* __restrict__ g, const double* __restrict__ img, int n) {
+  const int head = (int)((reinterpret_cast<uintptr_t>(g) >> 3) & 1);  // 8 B-aligned start
+  const int n2 = (n - head) >> 1;
+  double2* const q = reinterpret_cast<double2*>(g + head);
+  const double* const src = img + head;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < n2; i += kThreads) q[i] = make_double2(__ldg(src + 2 * i), __ldg(src + 2 * i + 1));
+  if (threadIdx.x == 0) {
+    if (head) g[0] = img[0];
+    if ((n - head) & 1) g[n - 1] = img[n - 1];
+  }
+}
+__device__ __forceinline__ double* shfl_ptr(double* p, int src) {
+  return reinterpret_cast<double*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(p), src));
+}
+template <int N>
+__device__ __forceinline__ unsigned free_mask(const int* g) {
+  unsigned m = 0;
+#pragma unroll
+  for (int a = 0; a < N; ++a) m |= (g[a] > 0 ? 1u : 0u) << a;
+  return m;
+}
+// lane = entry emission of the Jacobian blocks of the warp's 32 cells (lane = cell data in R, c, py, pu)
+template <class E>
+__device__ __forceinline__ void cg_emit_jac_K(const double* __restrict__ Ks, const Jet1<E::M> (&R)[E::NR], const Cell<E>& c, bool valid,
+                                              double* py, double* pu, int lane) {
+  using KT = KTab<E>;
+  constexpr int NB = E::NB, NY = E::NY, NU = E::NU;
+  unsigned nzy = 0, nzu = 0;
+#pragma unroll
+  for (int t = 0; t < NB; ++t) {
+#pragma unroll
+    for (int k = 0; k < NB; ++k)
+      if (__any_sync(0xffffffffu, valid && R[t].g[k] != 0.0)) nzy |= 1u << (t * NB + k);
+    if (NU > 0 && __any_sync(0xffffffffu, valid && R[t].g[E::SU] != 0.0)) nzu |= 1u << t;
+  }
+  const unsigned fmy = free_mask<NY>(c.gy), fmu = NU > 0 ? free_mask<E::NUS>(c.gu) : 0u;
+  const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+#pragma unroll 1
+  for (int r = 0; r < 32; ++r) {
+    if (!((vmask >> r) & 1u)) continue;
+    const unsigned my = __shfl_sync(0xffffffffu, fmy, r), mu = __shfl_sync(0xffffffffu, fmu, r);
+    const int fy = __popc(my);
+    double* const gy = shfl_ptr(py, r);
+    double* const gu = shfl_ptr(pu, r);
+    double dy[NB * NB], du[NB];
+#pragma unroll
+    for (int t = 0; t < NB; ++t) {
+#pragma unroll
+      for (int k = 0; k < NB; ++k) dy[t * NB + k] = ((nzy >> (t * NB + k)) & 1u) ? __shfl_sync(0xffffffffu, R[t].g[k], r) : 0.0;
+      du[t] = (NU > 0 && ((nzu >> t) & 1u)) ? __shfl_sync(0xffffffffu, R[t].g[E::SU], r) : 0.0;
+    }
+#pragma unroll
+    for (int e0 = 0; e0 < NY * NY; e0 += 32) {  // y-block: column j outer, row i inner
+      const int e = e0 + lane;
+      const bool in = e < NY * NY;
+      const int j = in ? e / NY : 0, i = in ? e - j * NY : 0;
+      double acc = 0.0;
+#pragma unroll
+      for (int t = 0; t < NB; ++t)
+#pragma unroll
+        for (int k = 0; k < NB; ++k)
+          if ((nzy >> (t * NB + k)) & 1u) acc = fma(dy[t * NB + k], Ks[KT::yy(t, k, 0, 0) + (in ? e : 0)], acc);
+      if (in && ((my >> j) & 1u) && ((my >> i) & 1u))
+        gy[__popc(my & ((1u << j) - 1u)) * fy + __popc(my & ((1u << i) - 1u))] = acc;
+    }
+    if (NU > 0) {
+#pragma unroll
+      for (int e0 = 0; e0 < NU * NY; e0 += 32) {  // u-block: column b outer, row i inner
+        const int e = e0 + lane;
+        const bool in = e < NU * NY;
+        const int b = in ? e / NY : 0, i = in ? e - b * NY : 0;
+        double acc = 0.0;
+#pragma unroll
+        for (int t = 0; t < NB; ++t)
+          if ((nzu >> t) & 1u) acc = fma(du[t], Ks[KT::yu(t, 0, 0) + (in ? e : 0)], acc);
+        if (in && ((mu >> b) & 1u) && ((my >> i) & 1u))
+          gu[__popc(mu & ((1u << b) - 1u)) * fy + __popc(my & ((1u << i) - 1u))] = acc;
+      }
+    }
+  }
+}
+// lane = entry emission of the FE Hessian blocks (1,1), (2,1), (2,2) of the warp's 32 cells; ids = this warp's
+// shared-memory copy of the cells' dof ids, [32][IDS] (the lower-triangle filter compares global ids)
+template <class E>
+__host__ __device__ constexpr int cg_ids_stride() { return (E::NY + E::NU) | 1; }
+template <class E>
+__device__ __forceinline__ void cg_emit_hess_K(const double* __restrict__ Ks, const Jet2<E::M>& L, double sc, bool zyy, bool zu,
+                                               const int* ids, bool valid, double* p0, int lane) {
+  using KT = KTab<E>;
+  using J2 = Jet2<E::M>;
+  constexpr int NB = E::NB, NY = E::NY, NU = E::NU, IDS = cg_ids_stride<E>();
+  unsigned nzy = 0, nzu = 0;
+#pragma unroll
+  for (int k = 0; k < NB; ++k)
+#pragma unroll
+    for (int l = 0; l < NB; ++l)
+      if (__any_sync(0xffffffffu, valid && L.h[J2::idx(k, l)] != 0.0)) nzy |= 1u << (k * NB + l);
+  if (NU > 0) {
+#pragma unroll
+    for (int l = 0; l < NB; ++l)
+      if (__any_sync(0xffffffffu, valid && L.h[J2::idx(E::SU, l)] != 0.0)) nzu |= 1u << l;
+  }
+  const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll 1
+  for (int r = 0; r < 32; ++r) {
+    if (!((vmask >> r) & 1u)) continue;
+    double* const gp = shfl_ptr(p0, r);
+    const int* const id = ids + r * IDS;
+    int base = 0;
+    {  // block (1,1): column j outer, row i inner, keep gid_col > 0 and gid_col <= gid_row
+      double d[NB * NB];
+#pragma unroll
+      for (int k = 0; k < NB; ++k)
+#pragma unroll
+        for (int l = 0; l < NB; ++l)
+          d[k * NB + l] = ((nzy >> (k * NB + l)) & 1u) ? __shfl_sync(0xffffffffu, L.h[J2::idx(k, l)] * sc, r) : 0.0;
+#pragma unroll
+      for (int e0 = 0; e0 < NY * NY; e0 += 32) {
+        const int e = e0 + lane;
+        const bool in = e < NY * NY;
+        const int j = in ? e / NY : 0, i = in ? e - j * NY : 0;
+        const int gj = id[j], gi = id[i];
+        const bool kept = in && gj > 0 && gj <= gi;
+        double acc = 0.0;
+        if (!zyy) {
+#pragma unroll
+          for (int k = 0; k < NB; ++k)
+#pragma unroll
+            for (int l = 0; l < NB; ++l)
+              if ((nzy >> (k * NB + l)) & 1u) acc = fma(d[k * NB + l], Ks[KT::yy(k, l, 0, 0) + (in ? e : 0)], acc);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, kept);
+        if (kept) gp[base + __popc(bal & lt)] = acc;
+        base += __popc(bal);
+      }
+    }
+    if (NU > 0) {
+      double dl[NB];
+#pragma unroll
+      for (int l = 0; l < NB; ++l) dl[l] = ((nzu >> l) & 1u) ? __shfl_sync(0xffffffffu, L.h[J2::idx(E::SU, l)] * sc, r) : 0.0;
+      const double duu = __shfl_sync(0xffffffffu, L.h[J2::idx(E::SU, E::SU)] * sc, r);
+#pragma unroll
+      for (int e0 = 0; e0 < NY * NU; e0 += 32) {  // block (2,1): state column j outer, control row i inner
+        const int e = e0 + lane;
+        const bool in = e < NY * NU;
+        const int j = in ? e / NU : 0, i = in ? e - j * NU : 0;
+        const bool kept = in && id[j] > 0 && id[NY + i] > 0;
+        double acc = 0.0;
+        if (!zu) {
+#pragma unroll
+          for (int l = 0; l < NB; ++l)
+            if ((nzu >> l) & 1u) acc = fma(dl[l], Ks[KT::uy(l, 0, 0) + (in ? e : 0)], acc);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, kept);
+        if (kept) gp[base + __popc(bal & lt)] = acc;
+        base += __popc(bal);
+      }
+#pragma unroll
+      for (int e0 = 0; e0 < NU * NU; e0 += 32) {  // block (2,2)
+        const int e = e0 + lane;
+        const bool in = e < NU * NU;
+        const int j = in ? e / NU : 0, i = in ? e - j * NU : 0;
+        const int gj = id[NY + j], gi = id[NY + i];
+        const bool kept = in && gj > 0 && gj <= gi;
+        const double v = zu ? 0.0 : duu * Ks[KT::uu(0, 0) + (in ? e : 0)];
+        const unsigned bal = __ballot_sync(0xffffffffu, kept);
+        if (kept) gp[base + __popc(bal & lt)] = v;
+        base += __popc(bal);
+      }
+    }
+  }
+}
+
+// one CTA per chunk: copies the first n*RUN doubles of the image(s) to the chunk's run(s) (element-independent)
+struct ChunkSeg {
+  double* vals;         // segment of the output (nullptr: unused)
+  const int64_t* off;   // [nchunk] first entry of the chunk in the segment
+  const double* img;    // image of a template tile
+  int run;              // entries per template cell
+};
+static __global__ void __launch_bounds__(kThreads) k_copy_chunks(ChunkSeg a, ChunkSeg b, const uint8_t* __restrict__ ch_n) {
+  griddep_wait();  // (the image is written by the preceding one-tile launch on the stream)
+  griddep_launch_dependents();
+  const int64_t k = blockIdx.x;
+  const int n = ch_n[k];
+  copy_image(a.vals + a.off[k], a.img, n * a.run);
+  if (b.vals != nullptr) copy_image(b.vals + b.off[k], b.img, n * b.run);
+}
+
+// generic cells of the Jacobian blocks: one warp per 32 cells of the list
+template <class E>
+__global__ void __launch_bounds__(kThreads)
+k_jac_cells_cg(const __grid_constant__ Tables<E> tab, const DevModel D, const double* __restrict__ x,
+               double* __restrict__ vals_y, double* __restrict__ vals_u) {
+  using I = typename E::Integrand;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  griddep_wait();
+  griddep_launch_dependents();
+  const int64_t i = ((int64_t)blockIdx.x * kWarpsPerCta + warp) * 32 + lane;
+  const bool valid = i < D.ngc;
+  const int64_t cell = valid ? (int64_t)__ldg(D.gc_cell + i) : 0;
+  double* const py = vals_y + (valid ? __ldg(D.gc_jy + i) : 0);
+  double* const pu = vals_u + ((valid && E::NU > 0) ? __ldg(D.gc_ju + i) : 0);
+  Cell<E> c;
+  load_ids<E>(D, cell, valid, c);
+  gather_state<E>(D, x, valid, c);
+  Jet1<E::M> s[E::M], R[E::NR];
+  const PointGeo<E> pc = point_ctx<E>(D, tab, cell, valid, 0, I::NEEDS_COEF_DERIV);
+  point_state<E>(tab, pc, c, x, 0, s);
+  eval_res<E>(pc, s, R);
+  if constexpr (E::NQ > 1) {  // point-independent derivatives: pre-integrated reference tensors
+    cg_emit_jac_K<E>(D.ktab, R, c, valid, py, pu, lane);
+  } else {
+    emit_jac_y_pt<E>(tab, 0, pc.w, R, c, py);
+    if (E::NU > 0) emit_jac_u_pt<E>(tab, 0, pc.w, R, c, pu);
+  }
+}
+
+// generic cells of the objective FE Hessian block (the one computed block: tpl_ok<E, true> integrands have a
+// structurally zero constraint block)
+template <class E>
+__global__ void __launch_bounds__(kThreads)
+k_hess_cells_cg(const __grid_constant__ Tables<E> tab, const DevModel D, const double* __restrict__ x, double obj_weight,
+                double* __restrict__ vals_obj) {
+  using I = typename E::Integrand;
+  __shared__ int sids[E::NQ > 1 ? kWarpsPerCta * 32 * cg_ids_stride<E>() : 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  griddep_wait();
+  griddep_launch_dependents();
+  const int64_t i = ((int64_t)blockIdx.x * kWarpsPerCta + warp) * 32 + lane;
+  const bool valid = i < D.ngc;
+  const int64_t cell = valid ? (int64_t)__ldg(D.gc_cell + i) : 0;
+  double* const p0 = vals_obj + (valid ? __ldg(D.gc_h + i) : 0);
+  Cell<E> c;
+  load_ids<E>(D, cell, valid, c);
+  gather_state<E>(D, x, valid, c);
+  int fy, fu, cnt;
+  closed_counts<E>(c, fy, fu, cnt);
+  const int n11 = fy * (fy + 1) / 2;
+  Jet2<E::M> s[E::M];
+  const PointGeo<E> pc = point_ctx<E>(D, tab, cell, valid, 0, I::NEEDS_COEF_DERIV);
+  point_state<E>(tab, pc, c, x, 0, s);
+  const Jet2<E::M> L = I::f(pc, s);
+  const double sc = obj_weight;
+  // structural zeros, as in the tile kernel (warp-uniform; a vanishing part is written as zeros)
+  const bool zyy = __all_sync(0xffffffffu, sc == 0.0 || fe_hess_block_is_zero<E, false>(L) || !valid);
+  const bool zu = __all_sync(0xffffffffu, sc == 0.0 || fe_hess_block_is_zero<E, true>(L) || !valid);
+  if constexpr (E::NQ > 1) {
+    int* const ids = sids + warp * 32 * cg_ids_stride<E>();
+#pragma unroll
+    for (int a = 0; a < E::NY; ++a) ids[lane * cg_ids_stride<E>() + a] = c.gy[a];
+#pragma unroll
+    for (int b = 0; b < E::NU; ++b) ids[lane * cg_ids_stride<E>() + E::NY + b] = c.gu[b];
+    __syncwarp();
+    cg_emit_hess_K<E>(D.ktab, L, sc, zyy, zu, ids, valid, p0, lane);
+  } else {
+    double* p = p0;
+    const double scale = sc * pc.w;
+    if (!zyy) p = emit_hess_yy<E, false>(tab, 0, L, scale, c, p);
+    else { for (int k = 0; k < n11; ++k) p[k] = 0.0; p += n11; }
+    if (!zu) emit_hess_u<E, false>(tab, 0, L, scale, c, p);
+    else for (int k = 0; k < cnt - n11; ++k) p[k] = 0.0;
+  }
 }
 
 

@@ -39,6 +39,9 @@ struct Launch {
   // the generic per-quadrature-point kernels — the create-time self-check compares both (pdenlp_create)
   bool generic = false;
   int64_t* launches = nullptr;  // counts the kernel launches issued through this Launch (pdenlp_launch_count)
+  // auxiliary stream (already forked from `stream` by the caller, who also joins it): the cell-granular template path
+  // runs its generic-cell kernel there, concurrently with the chunk copy; nullptr: everything on `stream`
+  cudaStream_t aux = nullptr;
 };
 inline void count_launch(const Launch& L, int n = 1) { if (L.launches) *L.launches += n; }
 
@@ -80,6 +83,7 @@ struct Ops {
   virtual bool tpl_jac_ok() const = 0;
   virtual bool tpl_hess_ok() const = 0;
   virtual int tile_class(const DevModel& D, unsigned long long sig_y, unsigned long long sig_u, uint8_t* cls, cudaStream_t s) = 0;
+  virtual int cell_class(const DevModel& D, unsigned long long sig_y, unsigned long long sig_u, uint32_t* mask, cudaStream_t s) = 0;
   virtual bool needs_coef_deriv() const = 0;  // derivative callbacks read the coefficient fields
   virtual bool res_fe_hessian_zero() const = 0;  // constraint FE Hessian block is structurally zero
   virtual bool no_fe_obj() const = 0;            // NoFETerm objective fk(kappa)
@@ -139,6 +143,11 @@ struct OpsImpl : Ops {
     CU(cudaGetLastError());
     return PDENLP_OK;
   }
+  int cell_class(const DevModel& D, unsigned long long sig_y, unsigned long long sig_u, uint32_t* mask, cudaStream_t s) override {
+    k_cell_class<E><<<grid_for(D.ntiles, kWarpsPerCta, 1 << 30), kThreads, 0, s>>>(D, sig_y, sig_u, mask);
+    CU(cudaGetLastError());
+    return PDENLP_OK;
+  }
   bool needs_coef_deriv() const override { return E::Integrand::NEEDS_COEF_DERIV; }
   bool res_fe_hessian_zero() const override { return E::Integrand::RES_FE_HESSIAN_ZERO; }
   bool no_fe_obj() const override { return E::Integrand::NO_FE_OBJ; }
@@ -171,7 +180,24 @@ struct OpsImpl : Ops {
     int w = atoi(e);
     return w >= 1 && w <= maxw ? w : maxw;
   }
+  // cell-granular templates (kernels.cuh): generic cells (256 per CTA) on the auxiliary stream, chunk copy (one per CTA)
+  static int cg_cells_grid(const DevModel& D) { return (D.ngc + kThreads - 1) / kThreads; }
   int jac(const Launch& L, const DevModel& D, const double* x, double* vy, double* vu) override {
+    if constexpr (tpl_ok<E, false>()) {
+      if (D.ch_n != nullptr && !D.notrait && !L.generic) {
+        if (D.ngc > 0) {
+          CU(launch_kernel(k_jac_cells_cg<E>, cg_cells_grid(D), kThreads, 0, L.aux ? L.aux : L.stream, false, tab, D, x, vy, vu));
+          count_launch(L);
+        }
+        if (D.nchunk > 0) {
+          const ChunkSeg a{vy, D.ch_jy, D.tpl_jy, E::RUN_JY};
+          const ChunkSeg b{E::NU > 0 ? vu : nullptr, D.ch_ju, D.tpl_ju, E::RUN_JU};
+          CU(launch_kernel(k_copy_chunks, D.nchunk, kThreads, 0, L.stream, pdl_chain(), a, b, D.ch_n));
+          count_launch(L);
+        }
+        return PDENLP_OK;
+      }
+    }
     if (int rc = set_attrs()) return rc;
     static const int wj = env_warps("PDENLP_WARPS_J", WJ);
     CU(launch_kernel(jac_kernel(), grid_for(D.ntiles, wj, L.sms * occ_j), wj * 32, SMEM_J, L.stream, pdl_chain() && !E::MULTI,
@@ -180,6 +206,21 @@ struct OpsImpl : Ops {
     return PDENLP_OK;
   }
   int hess(const Launch& L, const DevModel& D, const double* x, const double* lam, double ow, double* vo, double* vc) override {
+    if constexpr (tpl_ok<E, true>()) {
+      if (D.ch_n != nullptr && !D.notrait && !L.generic && vo != nullptr && vc == nullptr) {
+        if (D.ngc > 0) {
+          CU(launch_kernel(k_hess_cells_cg<E>, cg_cells_grid(D), kThreads, 0, L.aux ? L.aux : L.stream, false, tab, D, x, ow, vo));
+          count_launch(L);
+        }
+        if (D.nchunk > 0) {
+          const ChunkSeg a{vo, D.ch_h, D.tpl_h, E::RUN_H};
+          const ChunkSeg b{nullptr, nullptr, nullptr, 0};
+          CU(launch_kernel(k_copy_chunks, D.nchunk, kThreads, 0, L.stream, pdl_chain(), a, b, D.ch_n));
+          count_launch(L);
+        }
+        return PDENLP_OK;
+      }
+    }
     if (int rc = set_attrs()) return rc;
     static const int wh = env_warps("PDENLP_WARPS_H", WH);
     CU(launch_kernel(hess_kernel(), grid_for(D.ntiles, wh, L.sms * occ_h), wh * 32, SMEM_H, L.stream, pdl_chain() && !E::MULTI,

@@ -77,6 +77,15 @@ struct pdenlp_model {
   bool tpl_j_valid = false, tpl_h_valid = false;  // cached images (integrands without kappa: independent of x)
   double tpl_h_ow = 0.0;
   int64_t tpl_builds = 0;
+  // cell-granular templates: host copies of the chunk table (the self-check cuts its sample at a chunk start)
+  bool cg_active = false;
+  // auxiliary stream of the cell-granular template path: the generic-cell kernel and the latency-bound kappa-block
+  // kernels of jac_coord! / hess_coord! run there, concurrently with the chunk copy on the caller's stream
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  std::vector<int64_t> ch_cell0_h, ch_jy_h, ch_ju_h, ch_h_h;
+  std::vector<int32_t> gc_cell_h;
+  std::vector<int64_t> hb_jy, hb_ju, hb_h;  // host copies of the per-tile segment offsets (create time only)
 };
 
 namespace {
@@ -226,6 +235,7 @@ int build_template(pdenlp_model* m, bool hess, const double* dx, double ow) {
   dt.base_jy = dt.base_ju = dt.base_h = m->zero_base;
   dt.tpl_list = dt.gen_list = nullptr;
   dt.ntpl = 0; dt.ngen = 1;
+  dt.ch_n = nullptr; dt.nchunk = 0; dt.ngc = 0;
   Launch L{m->stream, m->sms, false, &m->launches};
   if (hess) {
     if (int rc = m->ops->hess(L, dt, dx, nullptr, ow, m->tpl_h, nullptr)) return rc;
@@ -235,6 +245,107 @@ int build_template(pdenlp_model* m, bool hess, const double* dx, double ow) {
     m->tpl_j_valid = cacheable;
   }
   m->tpl_builds += 1;
+  return PDENLP_OK;
+}
+
+// Cell-granular templates (kernels.cuh): the device marks the template cells (one ballot mask per tile); the host cuts
+// the slab into chunks of <= 32 consecutive template cells and a list of the remaining (generic) cells, each with the
+// offset of its first entry in every COO segment.  The offsets are carried along from the per-tile exclusive scans
+// (a template cell has RUN entries per segment, a generic cell its counted ones) and re-checked at every tile end.
+int classify_cells(pdenlp_model* m, const pdenlp_desc& desc, unsigned long long sy, unsigned long long su) {
+  const int64_t nt = m->dm.ntiles, nc = desc.ncells;
+  if (nt < 4096) return PDENLP_OK;  // (small slabs: the per-CTA image load would cost more than it saves)
+  if (desc.nq > 1 && m->dm.ktab == nullptr) return PDENLP_OK;
+  uint32_t* dmask = nullptr;
+  CU(cudaMalloc((void**)&dmask, (size_t)nt * 4));
+  int rc = m->ops->cell_class(m->dm, sy, su, dmask, nullptr);
+  std::vector<uint32_t> mask((size_t)nt);
+  cudaError_t e = cudaMemcpy(mask.data(), dmask, (size_t)nt * 4, cudaMemcpyDeviceToHost);
+  cudaFree(dmask);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(PDENLP_ECUDA, std::string("cell classification: ") + cudaGetErrorString(e));
+  int64_t ntplc = 0, first_full = -1;
+  for (int64_t t = 0; t < nt; ++t) {
+    ntplc += __builtin_popcount(mask[t]);
+    if (first_full < 0 && mask[t] == 0xffffffffu) first_full = t;
+  }
+  if (first_full < 0 || ntplc * 4 < nc) return PDENLP_OK;
+  const int ny = desc.ny, nu = desc.nu;
+  const int64_t rjy = m->ops->run_jy(), rju = m->ops->run_ju(), rh = m->ops->run_h();
+  std::vector<int64_t> gjy, gju, gh;
+  std::vector<uint8_t> chn;
+  int64_t run0 = -1, runn = 0, r_jy = 0, r_ju = 0, r_h = 0;  // the open run of template cells
+  auto flush = [&]() {
+    if (runn > 0) {
+      m->ch_cell0_h.push_back(run0); m->ch_jy_h.push_back(r_jy); m->ch_ju_h.push_back(r_ju); m->ch_h_h.push_back(r_h);
+      chn.push_back((uint8_t)runn);
+    }
+    runn = 0;
+  };
+  for (int64_t t = 0; t < nt; ++t) {
+    int64_t ojy = m->hb_jy[t], oju = m->hb_ju[t], oh = m->hb_h[t];
+    const uint32_t mk = mask[t];
+    if (mk == 0xffffffffu && runn == 0) {  // (fast path: a whole tile of template cells starting a chunk)
+      m->ch_cell0_h.push_back(t * 32); m->ch_jy_h.push_back(ojy); m->ch_ju_h.push_back(oju); m->ch_h_h.push_back(oh);
+      chn.push_back(32);
+      continue;
+    }
+    for (int l = 0; l < 32; ++l) {
+      const int64_t c = t * 32 + l;
+      if (c >= nc) break;
+      if ((mk >> l) & 1u) {
+        if (runn == 0) { run0 = c; r_jy = ojy; r_ju = oju; r_h = oh; }
+        ++runn;
+        ojy += rjy; oju += rju; oh += rh;
+        if (runn == 32) flush();
+      } else {
+        flush();
+        int fy = 0, fu = 0;
+        for (int a = 0; a < ny; ++a) fy += desc.cell_dofs_y[c * ny + a] > 0;
+        for (int b = 0; b < nu; ++b) fu += desc.cell_dofs_u[c * nu + b] > 0;
+        m->gc_cell_h.push_back((int32_t)c); gjy.push_back(ojy); gju.push_back(oju); gh.push_back(oh);
+        ojy += (int64_t)fy * fy; oju += (int64_t)fy * fu;
+        oh += (int64_t)fy * (fy + 1) / 2 + (int64_t)fu * fy + (int64_t)fu * (fu + 1) / 2;  // (distinct ids: checked by k_count)
+      }
+    }
+    if (ojy != m->hb_jy[t + 1] || oju != m->hb_ju[t + 1] || oh != m->hb_h[t + 1])
+      return fail(PDENLP_EINVAL, "internal: per-cell segment offsets disagree with the per-tile scans");
+  }
+  flush();
+  if (m->ch_cell0_h.size() >= ((size_t)1 << 31) || m->gc_cell_h.size() >= ((size_t)1 << 31)) return PDENLP_OK;
+  int64_t* lp; uint8_t* bp; int32_t* ip;
+  if (int r = dev_upload(m, m->ch_jy_h.data(), m->ch_jy_h.size(), &lp)) return r;
+  m->dm.ch_jy = lp;
+  if (int r = dev_upload(m, m->ch_ju_h.data(), m->ch_ju_h.size(), &lp)) return r;
+  m->dm.ch_ju = lp;
+  if (int r = dev_upload(m, m->ch_h_h.data(), m->ch_h_h.size(), &lp)) return r;
+  m->dm.ch_h = lp;
+  if (int r = dev_upload(m, chn.data(), chn.size(), &bp)) return r;
+  m->dm.ch_n = bp;
+  if (int r = dev_upload(m, m->gc_cell_h.data(), m->gc_cell_h.size(), &ip)) return r;
+  m->dm.gc_cell = ip;
+  if (int r = dev_upload(m, gjy.data(), gjy.size(), &lp)) return r;
+  m->dm.gc_jy = lp;
+  if (int r = dev_upload(m, gju.data(), gju.size(), &lp)) return r;
+  m->dm.gc_ju = lp;
+  if (int r = dev_upload(m, gh.data(), gh.size(), &lp)) return r;
+  m->dm.gc_h = lp;
+  m->dm.nchunk = (int32_t)m->ch_cell0_h.size();
+  m->dm.ngc = (int32_t)m->gc_cell_h.size();
+  m->tpl_tile = (int32_t)first_full;
+  auto scratch = [&](double** p, int run) -> int {
+    CU(cudaMalloc((void**)p, (size_t)std::max(32 * run, 2) * 8));
+    m->owned.push_back(*p);
+    return PDENLP_OK;
+  };
+  if (int r = scratch(&m->tpl_jy, (int)rjy)) return r;
+  if (int r = scratch(&m->tpl_ju, (int)rju)) return r;
+  if (int r = scratch(&m->tpl_h, (int)rh)) return r;
+  m->dm.tpl_jy = m->tpl_jy; m->dm.tpl_ju = m->tpl_ju; m->dm.tpl_h = m->tpl_h;
+  const int64_t z[2] = {0, 0};
+  if (int r = dev_upload(m, z, 2, &m->zero_base)) return r;
+  m->tpl_active = true;
+  m->cg_active = true;
   return PDENLP_OK;
 }
 
@@ -268,6 +379,8 @@ int classify_tiles(pdenlp_model* m, const pdenlp_desc& desc) {
   for (int64_t c = nc / 2; c < nc && c < nc / 2 + 65536 && !found; ++c) found = signature(c, sy, su);
   if (!found) return PDENLP_OK;
   const int64_t nt = m->dm.ntiles;
+  static const bool tile_mode = [] { const char* e = getenv("PDENLP_TPL_MODE"); return e && std::string(e) == "tile"; }();
+  if (!tile_mode) return classify_cells(m, desc, sy, su);
   uint8_t* dcls = nullptr;
   CU(cudaMalloc((void**)&dcls, (size_t)nt));
   int rc = m->ops->tile_class(m->dm, sy, su, dcls, nullptr);
@@ -375,17 +488,31 @@ int self_check(pdenlp_model* m, double* worst_out) {
   int64_t ns = std::min<int64_t>(m->dm.ncells, 2048);
   if (m->tpl_active) ns = std::min<int64_t>(m->dm.ncells, std::max<int64_t>(ns, ((int64_t)m->tpl_tile + 24) * 32));
   DevModel ds = m->dm;
+  int64_t njy = 0, nju = 0, nh = 0;  // sizes of the sample's COO runs
+  bool sizes_known = false;
+  if (m->cg_active) {  // the sample ends where a chunk starts (chunks are not aligned to tiles)
+    const size_t k = std::lower_bound(m->ch_cell0_h.begin(), m->ch_cell0_h.end(), ns) - m->ch_cell0_h.begin();
+    if (k < m->ch_cell0_h.size()) {
+      ns = m->ch_cell0_h[k];
+      njy = m->ch_jy_h[k]; nju = m->ch_ju_h[k]; nh = m->ch_h_h[k];
+      sizes_known = true;
+    } else {
+      ns = m->dm.ncells;
+    }
+    ds.nchunk = (int32_t)k;
+    ds.ngc = (int32_t)(std::lower_bound(m->gc_cell_h.begin(), m->gc_cell_h.end(), (int32_t)std::min<int64_t>(ns, INT32_MAX)) - m->gc_cell_h.begin());
+  }
   ds.ncells = ns;
   ds.ntiles = (int32_t)((ns + 31) / 32);
-  if (m->tpl_active) {
+  if (m->tpl_active && !m->cg_active) {
     ds.ntpl = (int32_t)(std::lower_bound(m->tpl_list_h.begin(), m->tpl_list_h.end(), ds.ntiles) - m->tpl_list_h.begin());
     ds.ngen = (int32_t)(std::lower_bound(m->gen_list_h.begin(), m->gen_list_h.end(), ds.ntiles) - m->gen_list_h.begin());
   }
-  // sizes of the sample's COO runs = segment offsets of the first tile after the sample
-  int64_t njy = 0, nju = 0, nh = 0;
-  CU(cudaMemcpy(&njy, m->dm.base_jy + ds.ntiles, 8, cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(&nju, m->dm.base_ju + ds.ntiles, 8, cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(&nh, m->dm.base_h + ds.ntiles, 8, cudaMemcpyDeviceToHost));
+  if (!sizes_known) {  // = segment offsets of the first tile after the sample
+    CU(cudaMemcpy(&njy, m->dm.base_jy + ds.ntiles, 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&nju, m->dm.base_ju + ds.ntiles, 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&nh, m->dm.base_h + ds.ntiles, 8, cudaMemcpyDeviceToHost));
+  }
   const int64_t nk = std::max<int64_t>(I.nnzj_k, I.nnzh_k_con);
   const int64_t nout = std::max<int64_t>({njy + nju, 2 * nh, I.nvar, nk, (int64_t)2});
   double *x = nullptr, *lam = nullptr, *v = nullptr, *a = nullptr, *b = nullptr;
@@ -467,6 +594,24 @@ int self_check(pdenlp_model* m, double* worst_out) {
     return fail(PDENLP_EINVAL, "self-check failed: a trait-selected fast path (" + worst_op + ") disagrees with the generic kernels, relative error " + std::to_string(worst));
   return PDENLP_OK;
 }
+
+struct Fork {  // part of a callback on the model's auxiliary stream: forked from / joined back into the caller's stream
+  pdenlp_model* m;
+  bool on = false;
+  Fork(pdenlp_model* mm, bool want) : m(mm) {
+    static const bool off = getenv("PDENLP_NO_AUX_STREAM") != nullptr;  // experiments / A-B runs
+    if (want && !off && m->aux &&
+        cudaEventRecord(m->ev_fork, m->stream) == cudaSuccess && cudaStreamWaitEvent(m->aux, m->ev_fork, 0) == cudaSuccess)
+      on = true;
+  }
+  cudaStream_t side() const { return on ? m->aux : m->stream; }
+  cudaStream_t aux() const { return on ? m->aux : nullptr; }
+  void join() {
+    if (on) { cudaEventRecord(m->ev_join, m->aux); cudaStreamWaitEvent(m->stream, m->ev_join, 0); }
+    on = false;
+  }
+  ~Fork() { join(); }
+};
 
 struct Scope {  // device + timing bracket of one callback
   pdenlp_model* m;
@@ -603,6 +748,11 @@ int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
   m->dm.tpl_list = m->dm.gen_list = nullptr;
   m->dm.ntpl = 0; m->dm.ngen = 0;
   m->dm.tpl_jy = m->dm.tpl_ju = m->dm.tpl_h = nullptr;
+  m->dm.ch_jy = m->dm.ch_ju = m->dm.ch_h = nullptr;
+  m->dm.ch_n = nullptr;
+  m->dm.gc_cell = nullptr;
+  m->dm.gc_jy = m->dm.gc_ju = m->dm.gc_h = nullptr;
+  m->dm.nchunk = 0; m->dm.ngc = 0;
   m->dm.jinvT = m->dm.detj = nullptr;
   m->dm.geom_nq = 0;
   if (desc->cell_jinvT) {
@@ -654,6 +804,7 @@ int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
       b1[t + 1] = b1[t] + hc[t * 3 + 1];
       b2[t + 1] = b2[t] + hc[t * 3 + 2];
     }
+    m->hb_jy = b0; m->hb_ju = b1; m->hb_h = b2;
     int64_t* ip;
     if ((rc = dev_upload(m, b0.data(), b0.size(), &ip))) return bail(rc);
     m->dm.base_jy = ip;
@@ -684,8 +835,16 @@ int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
   if (cudaEventCreate(&m->ev0) != cudaSuccess || cudaEventCreate(&m->ev1) != cudaSuccess)
     return bail(fail(PDENLP_ECUDA, "cudaEventCreate failed"));
   if ((rc = classify_tiles(m, *desc))) return bail(rc);
+  if (m->cg_active) {
+    if (cudaStreamCreateWithFlags(&m->aux, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess)
+      return bail(fail(PDENLP_ECUDA, "auxiliary stream / events: creation failed"));
+  }
   if (desc->flags & PDENLP_FLAG_DETERMINISTIC) { if ((rc = colour_cells(m, *desc, offf, nfy, nfu))) return bail(rc); }
   if ((rc = self_check(m, &m->selfcheck_err))) return bail(rc);
+  for (auto* v : {&m->hb_jy, &m->hb_ju, &m->hb_h, &m->ch_cell0_h, &m->ch_jy_h, &m->ch_ju_h, &m->ch_h_h}) std::vector<int64_t>().swap(*v);
+  std::vector<int32_t>().swap(m->gc_cell_h);
   // the host arrays of the description are not referenced after create
   m->d.cell_dofs_y = m->d.cell_dofs_u = nullptr;
   m->d.dir_y = m->d.dir_u = m->d.phi_y = m->d.grad_y = m->d.phi_u = m->d.wdet = m->d.coef = nullptr;
@@ -704,6 +863,9 @@ int pdenlp_destroy(pdenlp_model* m) {
   for (void* p : m->owned) cudaFree(p);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  if (m->ev_join) cudaEventDestroy(m->ev_join);
+  if (m->aux) { cudaStreamSynchronize(m->aux); cudaStreamDestroy(m->aux); }
   delete m->ops;
   delete m;
   cudaSetDevice(prev);
@@ -852,11 +1014,13 @@ int pdenlp_jac_coord(pdenlp_model* m, const double* x, double* vals) {
   if (int rc = out_ptr(m, vals, m->info.nnzj, &dv)) return rc;
   if (m->ops->needs_coef_deriv() && !m->dm.coef) return fail(PDENLP_EINVAL, "this integrand's derivatives need the coefficient fields (desc.coef)");
   Launch L{m->stream, m->sms, false, &m->launches};
+  Fork fk(m, m->cg_active);  // kappa block + generic cells beside the chunk copy
   if (m->info.nnzj_k > 0) {
     if (!m->dm.coef) return fail(PDENLP_EINVAL, "the kappa block needs the coefficient fields (desc.coef)");
-    CU(cudaMemsetAsync(dv, 0, (size_t)m->info.nnzj_k * 8, m->stream));
+    CU(cudaMemsetAsync(dv, 0, (size_t)m->info.nnzj_k * 8, fk.side()));
     if (int rc = for_each_colour(m, [&](const DevModel& d, bool coloured) {
           Launch Lc = L;
+          Lc.stream = fk.side();
           Lc.generic = coloured;
           return m->ops->jac_kappa(Lc, d, dx, dv, m->partials);
         })) return rc;
@@ -864,7 +1028,9 @@ int pdenlp_jac_coord(pdenlp_model* m, const double* x, double* vals) {
   double* vy = dv + m->info.nnzj_k;
   double* vu = vy + m->info.nnzj_y;
   if (int rc = build_template(m, false, dx, 1.0)) return rc;
+  L.aux = fk.aux();
   if (int rc = m->ops->jac(L, m->dm, dx, vy, vu)) return rc;
+  fk.join();
   return out_finish(m, vals, m->info.nnzj);
 }
 
@@ -883,22 +1049,25 @@ int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda, do
   double* vfo = vko + I.nnzh_k_obj;
   double* vkc = vfo + I.nnzh_fe_obj;
   double* vfc = vkc + I.nnzh_k_con;
+  Fork fk(m, m->cg_active);  // kappa blocks + generic cells beside the chunk copy and the zero fill
   if (I.nnzh_k_obj + I.nnzh_k_con > 0) {
     if (!m->dm.coef) return fail(PDENLP_EINVAL, "the kappa blocks need the coefficient fields (desc.coef)");
-    CU(cudaMemsetAsync(vko, 0, (size_t)I.nnzh_k_obj * 8, m->stream));
-    CU(cudaMemsetAsync(vkc, 0, (size_t)I.nnzh_k_con * 8, m->stream));
+    CU(cudaMemsetAsync(vko, 0, (size_t)I.nnzh_k_obj * 8, fk.side()));
+    CU(cudaMemsetAsync(vkc, 0, (size_t)I.nnzh_k_con * 8, fk.side()));
+    Launch Lk = L;
+    Lk.stream = fk.side();
     if (m->nofe) {
-      if (int rc = m->ops->nofe(L, NOFE_HESS, dx, obj_weight, nullptr, vko)) return rc;
+      if (int rc = m->ops->nofe(Lk, NOFE_HESS, dx, obj_weight, nullptr, vko)) return rc;
     } else {
       if (int rc = for_each_colour(m, [&](const DevModel& d, bool coloured) {
-            Launch Lc = L;
+            Launch Lc = Lk;
             Lc.generic = coloured;
             return m->ops->hess_kappa(Lc, d, dx, nullptr, obj_weight, 0, m->inde ? m->d.nparam : I.nvar, vko, m->partials);
           })) return rc;
     }
     if (dl) {
       if (int rc = for_each_colour(m, [&](const DevModel& d, bool coloured) {
-            Launch Lc = L;
+            Launch Lc = Lk;
             Lc.generic = coloured;
             return m->ops->hess_kappa(Lc, d, dx, dl, 1.0, 1, I.nvar, vkc, m->partials);
           })) return rc;
@@ -926,11 +1095,13 @@ int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda, do
   }
   if (vo || vc) {
     if (vo && !vc) { if (int rc = build_template(m, true, dx, obj_weight)) return rc; }
+    L.aux = fk.aux();
     if (int rc = m->ops->hess(L, m->dm, dx, dl, obj_weight, vo, vc)) return rc;
   }
   if (cons_zero && !host_tail && pdl) {
     if (int rc = zero_fill(m, vfc, I.nnzh_fe, (vo || vc) && !m->ops->is_multi())) return rc;
   }
+  fk.join();
   if (host_tail) return out_finish_zero_tail(m, vals, I.nnzh - I.nnzh_fe, I.nnzh_fe);
   return out_finish(m, vals, I.nnzh);
 }
@@ -947,14 +1118,17 @@ int pdenlp_hess_coord_obj(pdenlp_model* m, const double* x, double obj_weight, d
   if (int rc = out_ptr(m, vals, I.nnzh_obj, &dv)) return rc;
   if (m->ops->needs_coef_deriv() && !m->dm.coef) return fail(PDENLP_EINVAL, "this integrand's derivatives need the coefficient fields (desc.coef)");
   Launch L{m->stream, m->sms, false, &m->launches};
+  Fork fk(m, m->cg_active);
   if (I.nnzh_k_obj > 0) {
     if (!m->dm.coef) return fail(PDENLP_EINVAL, "the kappa blocks need the coefficient fields (desc.coef)");
-    CU(cudaMemsetAsync(dv, 0, (size_t)I.nnzh_k_obj * 8, m->stream));
+    CU(cudaMemsetAsync(dv, 0, (size_t)I.nnzh_k_obj * 8, fk.side()));
+    Launch Lk = L;
+    Lk.stream = fk.side();
     if (m->nofe) {
-      if (int rc = m->ops->nofe(L, NOFE_HESS, dx, obj_weight, nullptr, dv)) return rc;
+      if (int rc = m->ops->nofe(Lk, NOFE_HESS, dx, obj_weight, nullptr, dv)) return rc;
     } else {
       if (int rc = for_each_colour(m, [&](const DevModel& d, bool coloured) {
-            Launch Lc = L;
+            Launch Lc = Lk;
             Lc.generic = coloured;
             return m->ops->hess_kappa(Lc, d, dx, nullptr, obj_weight, 0, m->inde ? m->d.nparam : I.nvar, dv, m->partials);
           })) return rc;
@@ -962,8 +1136,10 @@ int pdenlp_hess_coord_obj(pdenlp_model* m, const double* x, double obj_weight, d
   }
   if (!m->nofe) {
     if (int rc = build_template(m, true, dx, obj_weight)) return rc;
+    L.aux = fk.aux();
     if (int rc = m->ops->hess(L, m->dm, dx, nullptr, obj_weight, dv + I.nnzh_k_obj, nullptr)) return rc;
   }
+  fk.join();
   return out_finish(m, vals, I.nnzh_obj);
 }
 
