@@ -42,6 +42,7 @@ struct Launch {
   // auxiliary stream (already forked from `stream` by the caller, who also joins it): the cell-granular template path
   // runs its generic-cell kernel there, concurrently with the chunk copy; nullptr: everything on `stream`
   cudaStream_t aux = nullptr;
+  int bg_ctas = 0;  // > 0: CTAs per SM of the kappa-block kernels when they run in the background of a streaming kernel
 };
 inline void count_launch(const Launch& L, int n = 1) { if (L.launches) *L.launches += n; }
 
@@ -254,7 +255,8 @@ struct OpsImpl : Ops {
   }
   static int kvec_grid(const DevModel& D, const Launch& L, int op) {
     // tensor-core kernels: one wave of resident CTAs (their per-CTA prologue builds the B fragments)
-    return grid_for(D.ntiles, kvec_threads() / 32, L.sms * (use_mma(op) ? PDENLP_KMMA_MINB : 8));
+    const int per_sm = use_mma(op) ? PDENLP_KMMA_MINB : 8;
+    return grid_for(D.ntiles, kvec_threads() / 32, L.sms * (L.bg_ctas > 0 ? std::min(L.bg_ctas, per_sm) : per_sm));
   }
   template <int OP>
   int vec_op(const Launch& L, const DevModel& D, const double* x, const double* lam, const double* v, double ow,

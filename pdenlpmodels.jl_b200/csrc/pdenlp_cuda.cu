@@ -606,6 +606,14 @@ struct Fork {  // part of a callback on the model's auxiliary stream: forked fro
   }
   cudaStream_t side() const { return on ? m->aux : m->stream; }
   cudaStream_t aux() const { return on ? m->aux : nullptr; }
+  // CTAs per SM of the Jacobian kappa-block kernel while it shares the SMs with the chunk copy (0: its default grid).
+  // Measured on config 5 (jac_coord! ms, auxiliary stream at high priority): default grid 0.454, 2 per SM 0.438, 1 per SM
+  // 0.429 — a small resident footprint leaves the registers to the copy CTAs; the Hessian kappa kernels keep theirs
+  // (hess_coord! 0.759 against 0.767 / 0.778).
+  int bg_ctas() const {
+    static const int v = [] { const char* e = getenv("PDENLP_KAPPA_BG_CTAS"); return e ? atoi(e) : 1; }();
+    return on ? v : 0;
+  }
   void join() {
     if (on) { cudaEventRecord(m->ev_join, m->aux); cudaStreamWaitEvent(m->stream, m->ev_join, 0); }
     on = false;
@@ -836,7 +844,13 @@ int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
     return bail(fail(PDENLP_ECUDA, "cudaEventCreate failed"));
   if ((rc = classify_tiles(m, *desc))) return bail(rc);
   if (m->cg_active) {
-    if (cudaStreamCreateWithFlags(&m->aux, cudaStreamNonBlocking) != cudaSuccess ||
+    // high priority: the CTAs of the latency-bound side kernels are placed ahead of the pending chunk-copy CTAs
+    // (config 5: jac_coord! 0.475 -> 0.454 ms, hess_coord! 0.794 -> 0.759); PDENLP_AUX_PRIO=0|lo: experiments
+    int plo = 0, phi = 0;
+    cudaDeviceGetStreamPriorityRange(&plo, &phi);  // (lowest, highest)
+    const char* pe = getenv("PDENLP_AUX_PRIO");
+    const int prio = !pe ? phi : (std::string(pe) == "lo" ? plo : 0);
+    if (cudaStreamCreateWithPriority(&m->aux, cudaStreamNonBlocking, prio) != cudaSuccess ||
         cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess)
       return bail(fail(PDENLP_ECUDA, "auxiliary stream / events: creation failed"));
@@ -1021,6 +1035,7 @@ int pdenlp_jac_coord(pdenlp_model* m, const double* x, double* vals) {
     if (int rc = for_each_colour(m, [&](const DevModel& d, bool coloured) {
           Launch Lc = L;
           Lc.stream = fk.side();
+          Lc.bg_ctas = fk.bg_ctas();
           Lc.generic = coloured;
           return m->ops->jac_kappa(Lc, d, dx, dv, m->partials);
         })) return rc;

@@ -3,7 +3,9 @@
 Usage (in the container, after bringing the .ncu-rep back in gpurun_out/):
     ncu -i gpurun_out/x.ncu-rep --page raw --csv > /tmp/raw.csv
     python tools/ncu_summary.py /tmp/raw.csv profiles/rNN_vK_ncu_summary.json
-One entry per distinct kernel name (first captured launch), values with their ncu units.
+One entry per distinct kernel name (first captured launch), values with their ncu units; with --all one entry
+per captured launch ("launch_index" = position in the capture): kernels such as k_copy_chunks run once per callback
+with different sizes.
 """
 import csv
 import json
@@ -23,7 +25,7 @@ KEEP = [
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
-def main(src, dst):
+def main(src, dst, keep_all=False):
     rows = list(csv.reader(open(src)))
     hdr = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
     names, units = rows[hdr], rows[hdr + 1]
@@ -31,10 +33,10 @@ def main(src, dst):
     for r in rows[hdr + 2:]:
         rec = dict(zip(names, r))
         k = rec["Kernel Name"]
-        if k in seen:
+        if k in seen and not keep_all:
             continue
         seen.add(k)
-        e = {"Kernel Name": k}
+        e = {"Kernel Name": k, "launch_index": len(out)}
         tot = 0.0
         for m in KEEP:
             if m in rec:
@@ -50,4 +52,5 @@ def main(src, dst):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    args = [a for a in sys.argv[1:] if a != "--all"]
+    main(args[0], args[1], keep_all="--all" in sys.argv)
