@@ -156,6 +156,11 @@ struct DevModel {
   const int64_t* gc_ju;
   const int64_t* gc_h;
   int32_t nchunk, ngc;
+  // ---- last-CTA reductions (see finish_partials): arrival counter of the running kernel (reset by the last CTA),
+  // device scalar of the objective and its pinned host mirror (written by the kernel: no copy after the launch)
+  unsigned* ticket;
+  double* fsum;
+  double* fsum_host;
 };
 
 // ------------------------------------------------------------------ small device helpers
@@ -1538,16 +1543,21 @@ k_hess_coord(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
 //     straight to global memory (config 2: 0.2 % of the cells).  The host runs this launch, together with the
 //     latency-bound kappa-block kernels, on the model's auxiliary stream, concurrently with the chunk copy.
 // Same arithmetic as the tile kernels, entry by entry (same fma chains; terms the tile kernels skip are exact zeros).
-__device__ __forceinline__ void copy_image(double* __restrict__ g, const double* __restrict__ img, int n) {
+// n <= 2*len doubles of the periodic image img[0..len) (len = 32 cells) to g[0..n)
+__device__ __forceinline__ void copy_image(double* __restrict__ g, const double* __restrict__ img, int n, int len) {
   const int head = (int)((reinterpret_cast<uintptr_t>(g) >> 3) & 1);  // 8 B-aligned start
   const int n2 = (n - head) >> 1;
   double2* const q = reinterpret_cast<double2*>(g + head);
-  const double* const src = img + head;
 #pragma unroll 4
-  for (int i = threadIdx.x; i < n2; i += kThreads) q[i] = make_double2(__ldg(src + 2 * i), __ldg(src + 2 * i + 1));
+  for (int i = threadIdx.x; i < n2; i += kThreads) {
+    int j0 = 2 * i + head, j1 = j0 + 1;
+    j0 -= j0 >= len ? len : 0;
+    j1 -= j1 >= len ? len : 0;
+    q[i] = make_double2(__ldg(img + j0), __ldg(img + j1));
+  }
   if (threadIdx.x == 0) {
     if (head) g[0] = img[0];
-    if ((n - head) & 1) g[n - 1] = img[n - 1];
+    if ((n - head) & 1) { int j = n - 1; j -= j >= len ? len : 0; g[n - 1] = img[j]; }
   }
 }
 __device__ __forceinline__ double* shfl_ptr(double* p, int src) {
@@ -1725,8 +1735,8 @@ static __global__ void __launch_bounds__(kThreads) k_copy_chunks(ChunkSeg a, Chu
   griddep_launch_dependents();
   const int64_t k = blockIdx.x;
   const int n = ch_n[k];
-  copy_image(a.vals + a.off[k], a.img, n * a.run);
-  if (b.vals != nullptr) copy_image(b.vals + b.off[k], b.img, n * b.run);
+  copy_image(a.vals + a.off[k], a.img, n * a.run, 32 * a.run);
+  if (b.vals != nullptr) copy_image(b.vals + b.off[k], b.img, n * b.run, 32 * b.run);
 }
 
 // generic cells of the Jacobian blocks: one warp per 32 cells of the list
@@ -2200,6 +2210,65 @@ __device__ __forceinline__ void cta_partial(double v, double* __restrict__ parti
   __syncthreads();
 }
 
+// Second pass without a second launch: every CTA publishes its partials, takes a ticket, and the CTA that arrives last
+// adds all partials in BLOCK ORDER (the same fixed-order strided + tree sum whichever CTA it is), so the result stays
+// bitwise reproducible run to run.  Saves one launch (~5 us + its ramp) per callback: visible for the 20-50 us callbacks
+// of the small problems.  All threads of every CTA must call last_cta() exactly once, after their cta_partial() calls.
+__device__ __forceinline__ bool last_cta(unsigned* ticket) {
+  __shared__ unsigned s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();  // this CTA's partials are visible before its ticket
+    const unsigned t = atomicAdd(ticket, 1u);
+    s_last = (t == gridDim.x - 1) ? 1u : 0u;
+    if (s_last) { *ticket = 0u; __threadfence(); }  // (every CTA has arrived: reset for the next launch on the stream)
+  }
+  __syncthreads();
+  return s_last != 0u;
+}
+// sum of p[0], p[stride], ..., n terms, by the whole CTA (blockDim.x a power of two <= 256), result on every thread
+__device__ __forceinline__ double cta_sum_strided(const double* p, int n, int stride) {
+  __shared__ double sh[256];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) a += __ldcg(p + (int64_t)i * stride);
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int d = blockDim.x >> 1; d > 0; d >>= 1) {
+    if ((int)threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+    __syncthreads();
+  }
+  const double r = sh[0];
+  __syncthreads();
+  return r;
+}
+// position of component `comp` of the kappa-kappa corner (column j outer, row i >= j inner) in a trapezoid with
+// `prows` rows; prows < 0: identity (the kappa entries of a dof-indexed vector)
+__device__ __forceinline__ int64_t kk_pos(int comp, int np, int64_t prows) {
+  if (prows < 0) return comp;
+  int c = 0;
+  int64_t col0 = 0;
+  for (int j = 0; j < np; ++j) {
+    for (int i = j; i < np; ++i, ++c)
+      if (c == comp) return col0 + (i - j);
+    col0 += prows - j;
+  }
+  return 0;
+}
+// called by the last CTA: out[pos(c)] += sum over the CTAs of partial component c
+__device__ __forceinline__ void finish_partials(const double* kpart /* [gridDim.x][ncomp] */, int ncomp, int np, int64_t prows, double* out) {
+  for (int c = 0; c < ncomp; ++c) {
+    const double a = cta_sum_strided(kpart + c, (int)gridDim.x, ncomp);
+    if (threadIdx.x == 0) out[kk_pos(c, np, prows)] += a;
+  }
+}
+__device__ __forceinline__ void finish_objective(const DevModel& D, const double* fpart /* [gridDim.x] */) {
+  const double a = cta_sum_strided(fpart, (int)gridDim.x, 1);
+  if (threadIdx.x == 0) {
+    *D.fsum = a;
+    if (D.fsum_host != nullptr) *D.fsum_host = a;
+  }
+}
+
 // ------------------------------------------------------------------ vector-valued callbacks
 // (lane = cell; scatter with red.global.add.f64 — north star: "segmented atomics")
 enum VecOp { OP_OBJ = 0, OP_GRAD = 1, OP_CONS = 2, OP_JPROD = 3, OP_JTPROD = 4, OP_HPROD = 5,
@@ -2438,9 +2507,16 @@ k_vector(const __grid_constant__ Tables<E> tab, const DevModel D, const double* 
     }
     __syncthreads();
   }
-  if (E::NP > 0 && (OP == OP_GRAD || OP == OP_OBJGRAD || OP == OP_JTPROD || OP == OP_HPROD)) {
+  constexpr bool KP = E::NP > 0 && (OP == OP_GRAD || OP == OP_OBJGRAD || OP == OP_JTPROD || OP == OP_HPROD);
+  if (KP) {
 #pragma unroll
     for (int k = 0; k < E::NP; ++k) cta_partial(ksum[k], partials + gridDim.x, E::NP, k, red);
+  }
+  // OP_OBJ: the last CTA sums the partials (no second launch).  The ops that scatter with atomics keep the second
+  // launch (k_sum_partials / k_add_partials): the __threadfence of the ticket protocol waits for the SM's outstanding
+  // red.global.add traffic (measured on config 5: jtprod! 0.173 -> 0.195 ms with the in-kernel second pass).
+  if (OP == OP_OBJ) {
+    if (last_cta(D.ticket)) finish_objective(D, partials);
   }
 }
 
@@ -2573,7 +2649,7 @@ __global__ void k_nofe(const __grid_constant__ Tables<E> tab, const double* __re
 template <class E>
 __global__ void __launch_bounds__(kThreads)
 k_hess_kappa_kk(const __grid_constant__ Tables<E> tab, const DevModel D, const double* __restrict__ x, double obj_weight,
-                double* __restrict__ partials) {
+                int64_t prows, double* __restrict__ vk, double* __restrict__ partials) {
   using I = typename E::Integrand;
   constexpr int NPS = E::NP > 0 ? E::NP : 1;
   using JK = Jet2<NPS>;
@@ -2615,24 +2691,29 @@ k_hess_kappa_kk(const __grid_constant__ Tables<E> tab, const DevModel D, const d
   for (int j = 0; j < E::NP; ++j)
 #pragma unroll
     for (int i = j; i < E::NP; ++i) { cta_partial(kk[i][j], partials + gridDim.x, E::NP * (E::NP + 1) / 2, comp, red); ++comp; }
+  if (last_cta(D.ticket)) finish_partials(partials + gridDim.x, E::NP * (E::NP + 1) / 2, E::NP, prows, vk);
 }
 
-// which: 0 = objective (scaled by obj_weight), 1 = constraints (lambda-weighted residual)
+// which: 0 = objective (scaled by obj_weight), 1 = constraints (lambda-weighted residual), 2 = both from one sweep
+// (objective into vk / prows, constraints into vk2 / prows2; the cell's ids and state are gathered once and the
+// callback saves two launches — hess_coord! of the 1-D problems is a chain of 20-30 us launches)
 template <class E>
 __global__ void __launch_bounds__(kThreads)
 k_hess_kappa(const __grid_constant__ Tables<E> tab, const DevModel D, const double* __restrict__ x,
              const double* __restrict__ lambda, double obj_weight, int which, int64_t prows, double* __restrict__ vk,
-             double* __restrict__ partials) {
+             double* __restrict__ partials, int64_t prows2, double* __restrict__ vk2) {
   using I = typename E::Integrand;
   using J2 = Jet2<E::M>;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NPS = E::NP > 0 ? E::NP : 1;
-  double kk[NPS][NPS];
+  const int w0 = which == 2 ? 0 : which, w1 = which == 2 ? 1 : which;
+  double kk[2][NPS][NPS];
 #pragma unroll
-  for (int a = 0; a < NPS; ++a)
+  for (int w = 0; w < 2; ++w)
 #pragma unroll
-    for (int b = 0; b < NPS; ++b) kk[a][b] = 0.0;
-  const bool cross = prows > E::NP;
+    for (int a = 0; a < NPS; ++a)
+#pragma unroll
+      for (int b = 0; b < NPS; ++b) kk[w][a][b] = 0.0;
   for (int64_t tile = (int64_t)blockIdx.x * kWarpsPerCta + warp; tile < D.ntiles; tile += (int64_t)gridDim.x * kWarpsPerCta) {
     bool valid;
     const int64_t cell = lane_cell(D, tile, lane, valid);
@@ -2641,63 +2722,77 @@ k_hess_kappa(const __grid_constant__ Tables<E> tab, const DevModel D, const doub
     load_ids<E>(D, cell, valid, c);
     gather_state<E>(D, x, valid, c);
     double lam_e[E::NY];
-    if (which != 0) gather_free<E::NY>(lambda, c.gy, lam_e);
-    double accy[NPS][E::NY], accu[NPS][E::NUS];  // cross terms summed over quadrature points
+    if (w1 != 0) gather_free<E::NY>(lambda, c.gy, lam_e);
 #pragma unroll
-    for (int j = 0; j < NPS; ++j) {
+    for (int w = 0; w < 2; ++w) {  // (unrolled: kk[w] stays in registers)
+      if (w < w0 || w > w1) continue;
+      const bool second = which == 2 && w == 1;
+      const int64_t pr = second ? prows2 : prows;
+      double* const out = second ? vk2 : vk;
+      const bool cross = pr > E::NP;
+      double accy[NPS][E::NY], accu[NPS][E::NUS];  // cross terms summed over quadrature points
 #pragma unroll
-      for (int a = 0; a < E::NY; ++a) accy[j][a] = 0.0;
+      for (int j = 0; j < NPS; ++j) {
 #pragma unroll
-      for (int b = 0; b < E::NUS; ++b) accu[j][b] = 0.0;
-    }
-#pragma unroll 1
-    for (int q = 0; q < E::NQ; ++q) {
-      Jet2<E::M> s[E::M];
-      const PointGeo<E> pc = point_ctx<E>(D, tab, cell, valid, q, true);
-      point_state<E>(tab, pc, c, x, q, s);
-      J2 L;
-      double scale = pc.w;
-      if (which == 0) { L = I::f(pc, s); scale *= obj_weight; }
-      else {
-        double Lam[E::NR];
-        lambda_slots<E>(tab, q, lam_e, Lam);
-        L = weighted_res<E>(pc, s, Lam);
+        for (int a = 0; a < E::NY; ++a) accy[j][a] = 0.0;
+#pragma unroll
+        for (int b = 0; b < E::NUS; ++b) accu[j][b] = 0.0;
       }
+#pragma unroll 1
+      for (int q = 0; q < E::NQ; ++q) {
+        Jet2<E::M> s[E::M];
+        const PointGeo<E> pc = point_ctx<E>(D, tab, cell, valid, q, true);
+        point_state<E>(tab, pc, c, x, q, s);
+        J2 L;
+        double scale = pc.w;
+        if (w == 0) { L = I::f(pc, s); scale *= obj_weight; }
+        else {
+          double Lam[E::NR];
+          lambda_slots<E>(tab, q, lam_e, Lam);
+          L = weighted_res<E>(pc, s, Lam);
+        }
 #pragma unroll
-      for (int j = 0; j < E::NP; ++j) {
+        for (int j = 0; j < E::NP; ++j) {
 #pragma unroll
-        for (int i = j; i < E::NP; ++i) kk[i][j] += scale * L.h[J2::idx(E::SK + i, E::SK + j)];
-        if (cross) {
+          for (int i = j; i < E::NP; ++i) kk[w][i][j] += scale * L.h[J2::idx(E::SK + i, E::SK + j)];
+          if (cross) {
 #pragma unroll
-          for (int a = 0; a < E::NY; ++a) {
-            double v = 0.0;
+            for (int a = 0; a < E::NY; ++a) {
+              double v = 0.0;
 #pragma unroll
-            for (int k = 0; k < E::NB; ++k) v = fma(tab.By[q][a][k], L.h[J2::idx(k, E::SK + j)], v);
-            accy[j][a] = fma(scale, v, accy[j][a]);
+              for (int k = 0; k < E::NB; ++k) v = fma(tab.By[q][a][k], L.h[J2::idx(k, E::SK + j)], v);
+              accy[j][a] = fma(scale, v, accy[j][a]);
+            }
+#pragma unroll
+            for (int b = 0; b < E::NU; ++b) accu[j][b] = fma(scale, tab.Bu[q][b] * L.h[J2::idx(E::SU, E::SK + j)], accu[j][b]);
           }
-#pragma unroll
-          for (int b = 0; b < E::NU; ++b) accu[j][b] = fma(scale, tab.Bu[q][b] * L.h[J2::idx(E::SU, E::SK + j)], accu[j][b]);
         }
       }
-    }
-    if (cross) {
+      if (cross) {
 #pragma unroll
-      for (int j = 0; j < E::NP; ++j) {
+        for (int j = 0; j < E::NP; ++j) {
 #pragma unroll
-        for (int a = 0; a < E::NY; ++a)
-          if (c.gy[a] > 0) accumulate(D, vk + trap_pos((int64_t)E::NP + c.gy[a], j + 1, prows), accy[j][a]);
+          for (int a = 0; a < E::NY; ++a)
+            if (c.gy[a] > 0) accumulate(D, out + trap_pos((int64_t)E::NP + c.gy[a], j + 1, pr), accy[j][a]);
 #pragma unroll
-        for (int b = 0; b < E::NU; ++b)
-          if (c.gu[b] > 0) accumulate(D, vk + trap_pos((int64_t)E::NP + D.nfree_y + c.gu[b], j + 1, prows), accu[j][b]);
+          for (int b = 0; b < E::NU; ++b)
+            if (c.gu[b] > 0) accumulate(D, out + trap_pos((int64_t)E::NP + D.nfree_y + c.gu[b], j + 1, pr), accu[j][b]);
+        }
       }
     }
   }
   __shared__ double red[kWarpsPerCta];
-  int comp = 0;
+  constexpr int NKK = E::NP * (E::NP + 1) / 2;
+  const int ncomp = NKK * (w1 - w0 + 1);
 #pragma unroll
-  for (int j = 0; j < E::NP; ++j)
+  for (int w = 0; w < 2; ++w) {
+    if (w < w0 || w > w1) continue;  // (block-uniform)
+    int comp = 0;
 #pragma unroll
-    for (int i = j; i < E::NP; ++i) { cta_partial(kk[i][j], partials + gridDim.x, E::NP * (E::NP + 1) / 2, comp, red); ++comp; }
+    for (int j = 0; j < E::NP; ++j)
+#pragma unroll
+      for (int i = j; i < E::NP; ++i) { cta_partial(kk[w][i][j], partials + gridDim.x, ncomp, (w - w0) * NKK + comp, red); ++comp; }
+  }
 }
 
 // ------------------------------------------------------------------ create-time self-check helpers

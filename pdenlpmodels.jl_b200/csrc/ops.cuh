@@ -74,8 +74,9 @@ struct Ops {
   virtual int vec(const Launch& L, const DevModel& D, int op, const double* x, const double* lam, const double* v,
                   double ow, double* out, double* partials, int* nblocks) = 0;
   virtual int jac_kappa(const Launch& L, const DevModel& D, const double* x, double* vk, double* partials) = 0;
+  // which: 0 = objective trapezoid, 1 = constraint trapezoid, 2 = both (objective: prows / vk, constraints: prows2 / vk2)
   virtual int hess_kappa(const Launch& L, const DevModel& D, const double* x, const double* lam, double ow, int which,
-                         int64_t prows, double* vk, double* partials) = 0;
+                         int64_t prows, double* vk, double* partials, int64_t prows2 = 0, double* vk2 = nullptr) = 0;
   virtual bool has_shortcuts() const = 0;  // some trait-selected fast path exists (worth a create-time self-check)
   virtual int run_h() const = 0;
   virtual int run_jy() const = 0;
@@ -327,9 +328,35 @@ struct OpsImpl : Ops {
     return PDENLP_OK;
   }
   int hess_kappa(const Launch& L, const DevModel& D, const double* x, const double* lam, double ow, int which,
-                 int64_t prows, double* vk, double* partials) override {
+                 int64_t prows, double* vk, double* partials, int64_t prows2 = 0, double* vk2 = nullptr) override {
     if constexpr (E::NP > 0) {
       int g = grid_for(D.ntiles, kWarpsPerCta, L.sms * 8);
+      if (which == 2) {
+        // one sweep for both trapezoids where both take the generic kernel; otherwise two calls
+        bool fast_con = false;
+        if constexpr (kvec_enabled<E>()) fast_con = !L.generic && D.ktab != nullptr;
+        constexpr int NKK2 = E::NP * (E::NP + 1) / 2;
+        if (fast_con || prows == E::NP || 2 * NKK2 > 16) {
+          if (int rc = hess_kappa(L, D, x, nullptr, ow, 0, prows, vk, partials)) return rc;
+          return hess_kappa(L, D, x, lam, 1.0, 1, prows2, vk2, partials);
+        }
+        KappaDst dst2;
+        int c = 0;
+        for (int w = 0; w < 2; ++w) {
+          const int64_t pr = w ? prows2 : prows, base = w ? (vk2 - vk) : 0;
+          for (int j = 0; j < E::NP; ++j) {
+            int64_t col0 = 0;
+            for (int jj = 0; jj < j; ++jj) col0 += pr - jj;
+            for (int i = j; i < E::NP; ++i) dst2.pos[c++] = base + col0 + (i - j);
+          }
+        }
+        k_hess_kappa<E><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, ow, 2, prows, vk, partials, prows2, vk2);
+        CU(cudaGetLastError());
+        k_add_partials<<<1, 256, 0, L.stream>>>(partials + g, g, 2 * NKK2, dst2, vk);
+        CU(cudaGetLastError());
+        count_launch(L, 2);
+        return PDENLP_OK;
+      }
       constexpr int NKK = E::NP * (E::NP + 1) / 2;
       KappaDst dst;  // the kappa-kappa corner: column j outer, row i >= j inner
       {
@@ -340,11 +367,14 @@ struct OpsImpl : Ops {
           for (int i = j; i < E::NP; ++i) dst.pos[c++] = col0 + (i - j);
         }
       }
-      bool done = false;
       if (which == 0 && prows == E::NP) {  // objective of an `inde` energy: kappa-kappa triangle only
-        k_hess_kappa_kk<E><<<g, kThreads, 0, L.stream>>>(tab, D, x, ow, partials);
-        done = true;
+        // (no scatter in this kernel: its last CTA adds the partials itself, see last_cta)
+        k_hess_kappa_kk<E><<<g, kThreads, 0, L.stream>>>(tab, D, x, ow, prows, vk, partials);
+        CU(cudaGetLastError());
+        count_launch(L);
+        return PDENLP_OK;
       }
+      bool done = false;
       if constexpr (kvec_enabled<E>()) {
         if (!done && which == 1 && !L.generic && D.ktab != nullptr) {
           g = kvec_grid(D, L, OP_HESS_KAPPA);
@@ -355,7 +385,7 @@ struct OpsImpl : Ops {
           done = true;
         }
       }
-      if (!done) k_hess_kappa<E><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, ow, which, prows, vk, partials);
+      if (!done) k_hess_kappa<E><<<g, kThreads, 0, L.stream>>>(tab, D, x, lam, ow, which, prows, vk, partials, (int64_t)0, (double*)nullptr);
       CU(cudaGetLastError());
       k_add_partials<<<1, 256, 0, L.stream>>>(partials + g, g, NKK, dst, vk);
       CU(cudaGetLastError());

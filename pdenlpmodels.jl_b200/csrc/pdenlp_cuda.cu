@@ -49,6 +49,8 @@ struct pdenlp_model {
   // scratch
   double* partials = nullptr;
   double* scalar = nullptr;
+  double* scalar_host = nullptr;  // pinned + mapped mirror of `scalar`, written by the objective kernel itself
+  unsigned* ticket = nullptr;     // arrival counter of the last-CTA reductions
   int32_t npartials = 0;
   // host-memspace staging
   // (each staging buffer remembers its capacity: sv serves directions of length nvar (jprod!, hprod!) and ncon (jtprod!))
@@ -274,6 +276,8 @@ int classify_cells(pdenlp_model* m, const pdenlp_desc& desc, unsigned long long 
   const int64_t rjy = m->ops->run_jy(), rju = m->ops->run_ju(), rh = m->ops->run_h();
   std::vector<int64_t> gjy, gju, gh;
   std::vector<uint8_t> chn;
+  // cells per chunk: 32 = one image length; up to 64 through the periodicity of the image (tuning knob)
+  static const int chunk_cells = [] { const char* e = getenv("PDENLP_CHUNK_CELLS"); int v = e ? atoi(e) : 32; return v >= 1 && v <= 64 ? v : 32; }();
   int64_t run0 = -1, runn = 0, r_jy = 0, r_ju = 0, r_h = 0;  // the open run of template cells
   auto flush = [&]() {
     if (runn > 0) {
@@ -285,7 +289,7 @@ int classify_cells(pdenlp_model* m, const pdenlp_desc& desc, unsigned long long 
   for (int64_t t = 0; t < nt; ++t) {
     int64_t ojy = m->hb_jy[t], oju = m->hb_ju[t], oh = m->hb_h[t];
     const uint32_t mk = mask[t];
-    if (mk == 0xffffffffu && runn == 0) {  // (fast path: a whole tile of template cells starting a chunk)
+    if (mk == 0xffffffffu && runn == 0 && chunk_cells == 32) {  // (fast path: a whole tile of template cells starting a chunk)
       m->ch_cell0_h.push_back(t * 32); m->ch_jy_h.push_back(ojy); m->ch_ju_h.push_back(oju); m->ch_h_h.push_back(oh);
       chn.push_back(32);
       continue;
@@ -297,7 +301,7 @@ int classify_cells(pdenlp_model* m, const pdenlp_desc& desc, unsigned long long 
         if (runn == 0) { run0 = c; r_jy = ojy; r_ju = oju; r_h = oh; }
         ++runn;
         ojy += rjy; oju += rju; oh += rh;
-        if (runn == 32) flush();
+        if (runn == chunk_cells) flush();
       } else {
         flush();
         int fy = 0, fu = 0;
@@ -612,7 +616,7 @@ struct Fork {  // part of a callback on the model's auxiliary stream: forked fro
   // (hess_coord! 0.759 against 0.767 / 0.778).
   int bg_ctas() const {
     static const int v = [] { const char* e = getenv("PDENLP_KAPPA_BG_CTAS"); return e ? atoi(e) : 1; }();
-    return on ? v : 0;
+    return (on && m->cg_active) ? v : 0;
   }
   void join() {
     if (on) { cudaEventRecord(m->ev_join, m->aux); cudaStreamWaitEvent(m->stream, m->ev_join, 0); }
@@ -840,10 +844,19 @@ int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
     return bail(fail(PDENLP_ENOMEM, "cudaMalloc failed"));
   m->owned.push_back(m->partials);
   m->owned.push_back(m->scalar);
+  if (cudaMalloc((void**)&m->ticket, 16) != cudaSuccess || cudaMemset(m->ticket, 0, 16) != cudaSuccess)
+    return bail(fail(PDENLP_ENOMEM, "cudaMalloc failed"));
+  m->owned.push_back(m->ticket);
+  if (cudaHostAlloc((void**)&m->scalar_host, 16, cudaHostAllocMapped) != cudaSuccess)
+    return bail(fail(PDENLP_ENOMEM, "cudaHostAlloc failed"));
+  m->dm.ticket = m->ticket;
+  m->dm.fsum = m->scalar;
+  m->dm.fsum_host = nullptr;
+  { double* hd = nullptr; if (cudaHostGetDevicePointer((void**)&hd, m->scalar_host, 0) == cudaSuccess) m->dm.fsum_host = hd; }
   if (cudaEventCreate(&m->ev0) != cudaSuccess || cudaEventCreate(&m->ev1) != cudaSuccess)
     return bail(fail(PDENLP_ECUDA, "cudaEventCreate failed"));
   if ((rc = classify_tiles(m, *desc))) return bail(rc);
-  if (m->cg_active) {
+  if (m->cg_active || (desc->nparam > 0 && !m->nofe)) {  // (models with kappa-block kernels, see Fork)
     // high priority: the CTAs of the latency-bound side kernels are placed ahead of the pending chunk-copy CTAs
     // (config 5: jac_coord! 0.475 -> 0.454 ms, hess_coord! 0.794 -> 0.759); PDENLP_AUX_PRIO=0|lo: experiments
     int plo = 0, phi = 0;
@@ -877,6 +890,7 @@ int pdenlp_destroy(pdenlp_model* m) {
   for (void* p : m->owned) cudaFree(p);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
+  if (m->scalar_host) cudaFreeHost(m->scalar_host);
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
   if (m->ev_join) cudaEventDestroy(m->ev_join);
   if (m->aux) { cudaStreamSynchronize(m->aux); cudaStreamDestroy(m->aux); }
@@ -927,10 +941,13 @@ int pdenlp_obj(pdenlp_model* m, const double* x, double* f) {
     if (int rc = m->ops->nofe(L, NOFE_OBJ, dx, 1.0, nullptr, m->scalar)) return rc;
   } else {
     int nb = 0;
+    // (the last CTA of the kernel sums the per-CTA partials in block order and writes the pinned host mirror)
     if (int rc = m->ops->vec(L, m->dm, OP_OBJ, dx, nullptr, nullptr, 1.0, nullptr, m->partials, &nb)) return rc;
-    k_sum_partials<<<1, 256, 0, m->stream>>>(m->partials, nb, m->scalar);
-    CU(cudaGetLastError());
-    m->launches += 1;
+    if (m->dm.fsum_host != nullptr) {
+      CU(cudaStreamSynchronize(m->stream));
+      *f = *(volatile double*)m->scalar_host;
+      return PDENLP_OK;
+    }
   }
   CU(cudaMemcpyAsync(f, m->scalar, 8, cudaMemcpyDeviceToHost, m->stream));
   CU(cudaStreamSynchronize(m->stream));
@@ -1028,7 +1045,7 @@ int pdenlp_jac_coord(pdenlp_model* m, const double* x, double* vals) {
   if (int rc = out_ptr(m, vals, m->info.nnzj, &dv)) return rc;
   if (m->ops->needs_coef_deriv() && !m->dm.coef) return fail(PDENLP_EINVAL, "this integrand's derivatives need the coefficient fields (desc.coef)");
   Launch L{m->stream, m->sms, false, &m->launches};
-  Fork fk(m, m->cg_active);  // kappa block + generic cells beside the chunk copy
+  Fork fk(m, m->cg_active || m->info.nnzj_k > 0);  // kappa block (+ generic cells) beside the FE stream
   if (m->info.nnzj_k > 0) {
     if (!m->dm.coef) return fail(PDENLP_EINVAL, "the kappa block needs the coefficient fields (desc.coef)");
     CU(cudaMemsetAsync(dv, 0, (size_t)m->info.nnzj_k * 8, fk.side()));
@@ -1064,15 +1081,23 @@ int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda, do
   double* vfo = vko + I.nnzh_k_obj;
   double* vkc = vfo + I.nnzh_fe_obj;
   double* vfc = vkc + I.nnzh_k_con;
-  Fork fk(m, m->cg_active);  // kappa blocks + generic cells beside the chunk copy and the zero fill
+  Fork fk(m, m->cg_active || (I.nnzh_k_obj + I.nnzh_k_con > 0 && !m->nofe));  // kappa blocks (+ generic cells) beside the FE stream and the zero fill
   if (I.nnzh_k_obj + I.nnzh_k_con > 0) {
     if (!m->dm.coef) return fail(PDENLP_EINVAL, "the kappa blocks need the coefficient fields (desc.coef)");
     CU(cudaMemsetAsync(vko, 0, (size_t)I.nnzh_k_obj * 8, fk.side()));
     CU(cudaMemsetAsync(vkc, 0, (size_t)I.nnzh_k_con * 8, fk.side()));
     Launch Lk = L;
     Lk.stream = fk.side();
+    bool both = false;
     if (m->nofe) {
       if (int rc = m->ops->nofe(Lk, NOFE_HESS, dx, obj_weight, nullptr, vko)) return rc;
+    } else if (dl) {  // objective and constraint trapezoids from one sweep (which = 2)
+      both = true;
+      if (int rc = for_each_colour(m, [&](const DevModel& d, bool coloured) {
+            Launch Lc = Lk;
+            Lc.generic = coloured;
+            return m->ops->hess_kappa(Lc, d, dx, dl, obj_weight, 2, m->inde ? m->d.nparam : I.nvar, vko, m->partials, I.nvar, vkc);
+          })) return rc;
     } else {
       if (int rc = for_each_colour(m, [&](const DevModel& d, bool coloured) {
             Launch Lc = Lk;
@@ -1080,7 +1105,7 @@ int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda, do
             return m->ops->hess_kappa(Lc, d, dx, nullptr, obj_weight, 0, m->inde ? m->d.nparam : I.nvar, vko, m->partials);
           })) return rc;
     }
-    if (dl) {
+    if (dl && !both) {
       if (int rc = for_each_colour(m, [&](const DevModel& d, bool coloured) {
             Launch Lc = Lk;
             Lc.generic = coloured;
@@ -1133,7 +1158,7 @@ int pdenlp_hess_coord_obj(pdenlp_model* m, const double* x, double obj_weight, d
   if (int rc = out_ptr(m, vals, I.nnzh_obj, &dv)) return rc;
   if (m->ops->needs_coef_deriv() && !m->dm.coef) return fail(PDENLP_EINVAL, "this integrand's derivatives need the coefficient fields (desc.coef)");
   Launch L{m->stream, m->sms, false, &m->launches};
-  Fork fk(m, m->cg_active);
+  Fork fk(m, m->cg_active || (I.nnzh_k_obj > 0 && !m->nofe));
   if (I.nnzh_k_obj > 0) {
     if (!m->dm.coef) return fail(PDENLP_EINVAL, "the kappa blocks need the coefficient fields (desc.coef)");
     CU(cudaMemsetAsync(dv, 0, (size_t)I.nnzh_k_obj * 8, fk.side()));
