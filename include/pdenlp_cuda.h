@@ -191,6 +191,11 @@ typedef struct pdenlp_desc {
    stores, so every entry is summed in a fixed order — bitwise identical results on every run, at 1.5-3x the time of
    the atomic kernels.  jac_coord!/hess_coord! FE segments and obj are deterministic either way. */
 #define PDENLP_FLAG_DETERMINISTIC 1
+/* Templates off.  For affine problems on identical cells jac_coord! / hess_coord! copy the COO image of one template
+   cell to every cell with the same free-dof pattern instead of evaluating it.  With this flag every cell
+   is evaluated by the generic kernels: same values, entry by entry; used by the tests that compare both paths over whole
+   full-size outputs, and available to callers who want the reference's cell-by-cell evaluation literally. */
+#define PDENLP_FLAG_NO_TEMPLATES 2
 
 typedef struct pdenlp_model pdenlp_model; /* opaque */
 

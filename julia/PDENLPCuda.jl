@@ -26,7 +26,7 @@ struct Desc   # mirrors struct pdenlp_desc field by field
   params::NTuple{8, Float64}
   field_nfree::Ptr{Int64}; field_ndir::Ptr{Int64}   # multi-field spaces only, else C_NULL
   cell_jinvT::Ptr{Float64}; cell_detj::Ptr{Float64}  # per-cell geometry (ABI v3), C_NULL = identical affine cells
-  geom_nq::Int32; flags::Int32   # flags: 1 = deterministic accumulation (coloured, no atomics)
+  geom_nq::Int32; flags::Int32   # flags: 1 = deterministic accumulation (coloured, no atomics), 2 = no templates (every cell evaluated)
 end
 
 struct Info

@@ -20,6 +20,7 @@ ABI_VERSION = 3
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = 0, -1, -2, -3, -4
 MEM_DEVICE, MEM_HOST = 0, 1
 FLAG_DETERMINISTIC = 1
+FLAG_NO_TEMPLATES = 2
 
 # every symbol include/pdenlp_cuda.h declares
 SYMBOLS = [

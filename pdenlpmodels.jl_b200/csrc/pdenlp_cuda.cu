@@ -357,7 +357,7 @@ int classify_cells(pdenlp_model* m, const pdenlp_desc& desc, unsigned long long 
 // middle of the slab; a tile is a template tile iff all its 32 cells carry it.  Used only when it pays (>= 25 % of the tiles).
 int classify_tiles(pdenlp_model* m, const pdenlp_desc& desc) {
   static const bool off = getenv("PDENLP_NO_TEMPLATE") != nullptr;  // experiments / A-B runs
-  if (off || !(m->ops->tpl_jac_ok() || m->ops->tpl_hess_ok())) return PDENLP_OK;
+  if (off || (desc.flags & PDENLP_FLAG_NO_TEMPLATES) || !(m->ops->tpl_jac_ok() || m->ops->tpl_hess_ok())) return PDENLP_OK;
   const int64_t nc = desc.ncells;
   const int ny = desc.ny, nu = desc.nu;
   auto signature = [&](int64_t c, unsigned long long& sy, unsigned long long& su) -> bool {

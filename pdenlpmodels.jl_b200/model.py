@@ -99,11 +99,13 @@ class GridapPDENLPModel:
     cell_range : (c0, c1) slab of cells owned by this handle (default: all).
     memspace : "device" (vectors are CUDA tensors, used in place) or "host".
     deterministic : sum the dof-indexed outputs in a fixed order (coloured launches, no atomics): bitwise reproducible.
+    templates : False evaluates every cell with the generic kernels (PDENLP_FLAG_NO_TEMPLATES) instead of copying the
+        image of a template cell (affine problems on identical cells): same values, used to compare both paths.
     """
 
     def __init__(self, spec: ProblemSpec, device: str = "cuda:0", cell_range=None, memspace: str = "device",
                  with_coef: bool = True, flat: Optional[FlatModel] = None, geometry: Optional[str] = None,
-                 deterministic: bool = False, x0=None, lvar=None, uvar=None,
+                 deterministic: bool = False, templates: bool = True, x0=None, lvar=None, uvar=None,
                  lvary=None, uvary=None, lvaru=None, uvaru=None, lvark=None, uvark=None):
         self.spec = spec
         self.device = torch.device(device)
@@ -114,7 +116,8 @@ class GridapPDENLPModel:
         self.flat = fm
         ms = capi.MEM_DEVICE if memspace == "device" else capi.MEM_HOST
         self.handle = capi.Handle(fm, device=self.device.index if self.device.index is not None else 0,
-                                  memspace=ms, with_coef=with_coef, flags=capi.FLAG_DETERMINISTIC if deterministic else 0)
+                                  memspace=ms, with_coef=with_coef,
+                                  flags=(capi.FLAG_DETERMINISTIC if deterministic else 0) | (0 if templates else capi.FLAG_NO_TEMPLATES))
         I = self.handle.info
         self.affine = bool(getattr(spec, "affine", False))
         self._jac_plan = self._hess_plan = None

@@ -247,3 +247,42 @@ def test_burger1d_1M_coord_slabs_vs_oracle(pkg, cuda_lib, oracle_mod):
     b = pm.nnzh_obj
     assert _rel(hv[b: b + pm.nnzh_k_con].cpu().numpy(), hf[of.nnzh_obj: of.nnzh_obj + of.nnzh_k_con]) <= 1e-11
     nlp.close()
+
+
+@pytest.mark.parametrize("case", ["membrane2048", "kappa_poisson3d_128"])
+def test_template_path_equals_cell_by_cell_evaluation_over_whole_outputs(pkg, cuda_lib, case):
+    """Full-size property (BASELINE configs[1] and configs[4]): the template path (chunks copied from the image of one
+    template cell + lane = entry emission of the boundary cells) against the generic kernels that evaluate every
+    cell (PDENLP_FLAG_NO_TEMPLATES), over the WHOLE jac_coord! / hess_coord! value streams — every chunk offset, every
+    boundary cell, head to tail.  Same fma chains on both sides: the FE segments must agree bit for bit; the dense
+    kappa blocks are atomic sums (round-off)."""
+    from pdenlp_b200.model import GridapPDENLPModel
+    spec = pkg.controlelasticmembrane(2048) if case == "membrane2048" else pkg.poissonmixed(128, dim=3, control=True)
+    a = GridapPDENLPModel(spec, device="cuda:0", with_coef=(spec.nparam > 0))
+    b = GridapPDENLPModel(spec, device="cuda:0", with_coef=(spec.nparam > 0), flat=a.flat, templates=False)
+    try:
+        I, pm = a.handle.info, a.pdemeta
+        rng = np.random.default_rng(77)
+        xh = rng.uniform(-1, 1, I.nvar)
+        if spec.nparam:
+            xh[: spec.nparam] = 1 + 0.1 * rng.uniform(-1, 1, spec.nparam)
+        x = torch.from_numpy(xh).cuda()
+        lam = torch.from_numpy(rng.uniform(-1, 1, I.ncon)).cuda()
+        nk = int(I.nnzj_k)
+        ja, jb = a.jac_coord(x), b.jac_coord(x)
+        assert torch.equal(ja[nk:], jb[nk:])
+        if nk:
+            assert float((ja[:nk] - jb[:nk]).abs().max()) <= 1e-12 * float(jb[:nk].abs().max())
+        del ja, jb
+        for ow in (1.0, 0.37):
+            ha, hb = a.hess_coord(x, lam, obj_weight=ow), b.hess_coord(x, lam, obj_weight=ow)
+            ko, kc = int(I.nnzh_k_obj), int(I.nnzh_k_con)
+            fo0, fo1 = ko, ko + int(I.nnzh_fe_obj)
+            assert torch.equal(ha[fo0:fo1], hb[fo0:fo1])            # objective FE block
+            assert torch.equal(ha[fo1 + kc:], hb[fo1 + kc:])        # constraint FE block
+            for lo, hi in ((0, ko), (fo1, fo1 + kc)):
+                if hi > lo:
+                    assert float((ha[lo:hi] - hb[lo:hi]).abs().max()) <= 1e-12 * max(float(hb[lo:hi].abs().max()), 1e-300)
+            del ha, hb
+    finally:
+        a.close(); b.close()
