@@ -599,6 +599,71 @@ int self_check(pdenlp_model* m, double* worst_out) {
   return PDENLP_OK;
 }
 
+// ---- create-time device helpers: SoA transpose of the cell -> dof maps and the segment-offset scans
+struct FieldTab { long long nf[16], nd[16], of[16], od[16]; };  // per field: free / Dirichlet sizes and their offsets in the space
+// soa[a][cell] = concatenated id of local dof a (validated against the field sizes); res[0] = min free id - 1,
+// res[1] = max free id (0-based range [lo, hi) of the free dofs the cells touch), res[2] = 1 on a bad id
+__global__ void __launch_bounds__(256) k_transpose_ids(const int32_t* __restrict__ aos, int64_t nc, int64_t ldc, int nloc, int nloc_field,
+                                                        int f0, FieldTab ft, int32_t* __restrict__ soa, unsigned long long* __restrict__ res) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ldc) return;
+  unsigned long long lo = ~0ull, hi = 0ull;
+  bool bad = false;
+  for (int a = 0; a < nloc; ++a) {
+    int32_t o = -1;
+    if (c < nc) {
+      const int f = f0 + a / nloc_field;
+      const long long g = aos[c * nloc + a];
+      if (g == 0 || g > ft.nf[f] || -g > ft.nd[f]) bad = true;
+      o = (int32_t)(g > 0 ? g + ft.of[f] : g - ft.od[f]);
+      if (g > 0) { lo = min(lo, (unsigned long long)(g + ft.of[f] - 1)); hi = max(hi, (unsigned long long)(g + ft.of[f])); }
+    }
+    soa[(int64_t)a * ldc + c] = o;
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+    const int ob = __shfl_xor_sync(0xffffffffu, (int)bad, d);  // (unconditional: no short-circuit around a shuffle)
+    bad = bad || ob != 0;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (hi > 0) { atomicMin(res + 0, lo); atomicMax(res + 1, hi); }
+    if (bad) atomicExch(res + 2, 1ull);
+  }
+}
+// exclusive scans of the three per-tile counts (AoS [ntiles][3], int32) -> base[k][0..ntiles] (int64); one CTA per
+// segment kind, decoupled in chunks of 1024 tiles carried serially (ntiles <= 2^31 / 32: a few thousand chunks)
+__global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict__ counts, int64_t nt, int64_t* __restrict__ b0,
+                                                       int64_t* __restrict__ b1, int64_t* __restrict__ b2) {
+  __shared__ long long wsum[32];
+  __shared__ long long carry_s;
+  int64_t* const base = blockIdx.x == 0 ? b0 : (blockIdx.x == 1 ? b1 : b2);
+  const int k = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int64_t t0 = 0; t0 < nt; t0 += 1024) {
+    const int64_t t = t0 + threadIdx.x;
+    const long long v = t < nt ? (long long)counts[t * 3 + k] : 0ll;
+    long long incl = v;
+    for (int d = 1; d < 32; d <<= 1) { const long long u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      long long w = wsum[lane];
+      for (int d = 1; d < 32; d <<= 1) { const long long u = __shfl_up_sync(0xffffffffu, w, d); if (lane >= d) w += u; }
+      wsum[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const long long carry = carry_s;
+    const long long excl = carry + (warp > 0 ? wsum[warp - 1] : 0ll) + incl - v;
+    if (t < nt) base[t] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + wsum[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) base[nt] = carry_s;
+}
+
 struct Fork {  // part of a callback on the model's auxiliary stream: forked from / joined back into the caller's stream
   pdenlp_model* m;
   bool on = false;
@@ -712,23 +777,39 @@ int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
     for (int f = nfy; f < nfy + nfu; ++f) { offf[f] = sf; offd[f] = sd; sf += fnf[f]; sd += fnd[f]; }
     if (nfu && (sf != desc->nfree_u || sd != desc->ndir_u)) return bail(fail(PDENLP_EINVAL, "control field sizes do not add up to nfree_u/ndir_u"));
   }
-  // SoA transpose of the cell->dof maps, validating the per-field ids against the declared sizes and
-  // renumbering them to the concatenated ids of the space
+  // SoA transpose of the cell->dof maps on the device (the raw maps are uploaded as they are), validating the per-field
+  // ids against the declared sizes and renumbering them to the concatenated ids of the space
+  if (nfy + nfu > 16) return bail(fail(PDENLP_EUNSUPPORTED, "more than 16 fields"));
+  FieldTab ft;
+  for (int f = 0; f < 16; ++f) { ft.nf[f] = ft.nd[f] = ft.of[f] = ft.od[f] = 0; }
+  for (int f = 0; f < nfy + nfu; ++f) { ft.nf[f] = fnf[f]; ft.nd[f] = fnd[f]; ft.of[f] = offf[f]; ft.od[f] = offd[f]; }
   auto upload_ids = [&](const int32_t* ids, int nloc_total, int nloc_field, int f0, const char* what, const int32_t** out_ptr, int64_t* range) -> int {
-    std::vector<int32_t> soa((size_t)ldc * std::max(nloc_total, 1), -1);
-    int64_t lo = INT64_MAX, hi = 0;
-    for (int64_t c = 0; c < nc; ++c)
-      for (int a = 0; a < nloc_total; ++a) {
-        const int f = f0 + a / nloc_field;
-        const int64_t g = ids[c * nloc_total + a];
-        if (g == 0 || g > fnf[f] || -g > fnd[f]) return fail(PDENLP_EINVAL, std::string(what) + " dof id out of range");
-        soa[(size_t)a * ldc + c] = (int32_t)(g > 0 ? g + offf[f] : g - offd[f]);
-        if (g > 0) { lo = std::min(lo, g + offf[f] - 1); hi = std::max(hi, g + offf[f]); }
-      }
-    range[0] = hi > 0 ? lo : 0; range[1] = hi;
-    int32_t* p;
-    if (int r = dev_upload(m, soa.data(), soa.size(), &p)) return r;
-    *out_ptr = p;
+    int32_t* soa = nullptr;
+    CU(cudaMalloc((void**)&soa, (size_t)ldc * std::max(nloc_total, 1) * 4));
+    m->owned.push_back(soa);
+    *out_ptr = soa;
+    range[0] = range[1] = 0;
+    if (nloc_total == 0) { CU(cudaMemset(soa, 0xff, (size_t)ldc * 4)); return PDENLP_OK; }
+    int32_t* raw = nullptr;
+    unsigned long long* res = nullptr;
+    if (cudaMalloc((void**)&raw, (size_t)nc * nloc_total * 4) != cudaSuccess || cudaMalloc((void**)&res, 24) != cudaSuccess) {
+      cudaFree(raw);
+      return fail(PDENLP_ENOMEM, "cudaMalloc failed");
+    }
+    const unsigned long long init[3] = {~0ull, 0ull, 0ull};
+    unsigned long long h[3] = {0, 0, 0};
+    cudaError_t e = cudaMemcpy(raw, ids, (size_t)nc * nloc_total * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(res, init, 24, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+      k_transpose_ids<<<(unsigned)((ldc + 255) / 256), 256>>>(raw, nc, ldc, nloc_total, nloc_field, f0, ft, soa, res);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(h, res, 24, cudaMemcpyDeviceToHost);
+    cudaFree(raw);
+    cudaFree(res);
+    if (e != cudaSuccess) return fail(PDENLP_ECUDA, std::string("dof map transpose: ") + cudaGetErrorString(e));
+    if (h[2]) return fail(PDENLP_EINVAL, std::string(what) + " dof id out of range");
+    if (h[1] > 0) { range[0] = (int64_t)h[0]; range[1] = (int64_t)h[1]; }
     return PDENLP_OK;
   };
   if (desc->nfree_y >= ((int64_t)1 << 31) || desc->nfree_u >= ((int64_t)1 << 31)) return bail(fail(PDENLP_EINVAL, "too many dofs for int32 ids"));
@@ -799,31 +880,30 @@ int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
       return bail(fail(PDENLP_ENOMEM, "cudaMalloc failed"));
     cudaMemset(dflag, 0, 4);
     rc = ops->count(m->dm, dcounts, dflag, nullptr);
-    std::vector<int32_t> hc((size_t)nt * 3);
     int32_t hflag = 0;
-    cudaError_t e1 = cudaMemcpy(hc.data(), dcounts, nt * 3 * 4, cudaMemcpyDeviceToHost);
+    int64_t* base3 = nullptr;  // [3][nt + 1]
+    if (!rc && cudaMalloc((void**)&base3, (size_t)(nt + 1) * 3 * 8) != cudaSuccess) { cudaFree(dcounts); cudaFree(dflag); return bail(fail(PDENLP_ENOMEM, "cudaMalloc failed")); }
+    if (base3) m->owned.push_back(base3);
+    if (!rc) k_scan_counts<<<3, 1024>>>(dcounts, nt, base3, base3 + (nt + 1), base3 + 2 * (nt + 1));
+    cudaError_t e1 = cudaGetLastError();
     cudaError_t e2 = cudaMemcpy(&hflag, dflag, 4, cudaMemcpyDeviceToHost);
+    // (host copies of the offsets: totals for the info block, per-tile values for the template classification)
+    std::vector<int64_t> b0(nt + 1), b1(nt + 1), b2(nt + 1);
+    if (!rc && e1 == cudaSuccess && e2 == cudaSuccess) {
+      e1 = cudaMemcpy(b0.data(), base3, (size_t)(nt + 1) * 8, cudaMemcpyDeviceToHost);
+      if (e1 == cudaSuccess) e1 = cudaMemcpy(b1.data(), base3 + (nt + 1), (size_t)(nt + 1) * 8, cudaMemcpyDeviceToHost);
+      if (e1 == cudaSuccess) e1 = cudaMemcpy(b2.data(), base3 + 2 * (nt + 1), (size_t)(nt + 1) * 8, cudaMemcpyDeviceToHost);
+    }
     cudaFree(dcounts);
     cudaFree(dflag);
     if (rc) return bail(rc);
     if (e1 != cudaSuccess || e2 != cudaSuccess)
       return bail(fail(PDENLP_ECUDA, std::string("count kernel: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)));
     if (hflag) return bail(fail(PDENLP_EINVAL, "a cell repeats a dof id; not supported"));
-    std::vector<int64_t> b0(nt + 1), b1(nt + 1), b2(nt + 1);
-    b0[0] = b1[0] = b2[0] = 0;
-    for (int64_t t = 0; t < nt; ++t) {
-      b0[t + 1] = b0[t] + hc[t * 3 + 0];
-      b1[t + 1] = b1[t] + hc[t * 3 + 1];
-      b2[t + 1] = b2[t] + hc[t * 3 + 2];
-    }
     m->hb_jy = b0; m->hb_ju = b1; m->hb_h = b2;
-    int64_t* ip;
-    if ((rc = dev_upload(m, b0.data(), b0.size(), &ip))) return bail(rc);
-    m->dm.base_jy = ip;
-    if ((rc = dev_upload(m, b1.data(), b1.size(), &ip))) return bail(rc);
-    m->dm.base_ju = ip;
-    if ((rc = dev_upload(m, b2.data(), b2.size(), &ip))) return bail(rc);
-    m->dm.base_h = ip;
+    m->dm.base_jy = base3;
+    m->dm.base_ju = base3 + (nt + 1);
+    m->dm.base_h = base3 + 2 * (nt + 1);
     const int64_t p = desc->nparam, n = p + desc->nfree_y + desc->nfree_u;
     pdenlp_info& I = m->info;
     I.nvar = n;
