@@ -189,9 +189,13 @@ class ShardedModel:
         if self.world == 1:
             return vals
         t = vals if isinstance(vals, torch.Tensor) else torch.from_numpy(vals)
-        ck = (key, t.device, base)
+        # (several blocks in one exchange: base / idx_fn are tuples, the index sets are concatenated)
+        bases = base if isinstance(base, tuple) else (base,)
+        fns = idx_fn if isinstance(idx_fn, tuple) else (idx_fn,)
+        ck = (key, t.device, bases)
         if ck not in self._idx_cache:
-            self._idx_cache[ck] = torch.from_numpy(np.asarray(idx_fn(), dtype=np.int64) + base).to(t.device)
+            parts = [np.asarray(f(), dtype=np.int64) + b for f, b in zip(fns, bases)]
+            self._idx_cache[ck] = torch.from_numpy(np.concatenate(parts) if parts else np.zeros(0, np.int64)).to(t.device)
         ix = self._idx_cache[ck]
         if ix.numel() == 0:
             return vals
@@ -221,8 +225,9 @@ class ShardedModel:
         if L.p == 0:
             return vals
         nvar = L.p + L.ny + L.nu
-        vals = self._reduce_packed(vals, 0, lambda: L.trap_index(self._prows_obj(), L.iface_var), "hko")
-        return self._reduce_packed(vals, pm.nnzh_obj, lambda: L.trap_index(nvar, L.iface_var), "hkc")
+        # one packed all-reduce for both trapezoids (two exchanges cost 0.1 ms of launch + NCCL latency at 8 GPUs)
+        return self._reduce_packed(vals, (0, int(pm.nnzh_obj)),
+                                   (lambda: L.trap_index(self._prows_obj(), L.iface_var), lambda: L.trap_index(nvar, L.iface_var)), "hk")
 
     def assemble_global_coo(self, vals, which: str):
         """The GLOBAL COO value stream (replicated on every rank) from the per-rank streams: every dense kappa-block

@@ -310,14 +310,25 @@ def test_callbacks_follow_the_current_torch_stream(pkg, cuda_lib):
     nlp.close()
 
 
-def test_callbacks_can_be_captured_in_a_cuda_graph(pkg, cuda_lib):
+@pytest.mark.parametrize("case", ["membrane48", "membrane512_templates", "kappa3d64_templates_aux_stream", "burger_param_aux_stream"])
+def test_callbacks_can_be_captured_in_a_cuda_graph(pkg, cuda_lib, case):
     """Device-memspace coordinate / vector callbacks enqueue kernels only (no host synchronisation, no host
-    copies), so a solver can capture an iteration in a CUDA graph and replay it with new x / lambda contents."""
+    copies), so a solver can capture an iteration in a CUDA graph and replay it with new x / lambda contents.
+    The larger cases run the cell-granular template path and fork / join the model's auxiliary stream inside the
+    capture (event record + wait: the auxiliary stream joins the capture and is joined back before the callback returns)."""
     from pdenlp_b200.model import GridapPDENLPModel
-    spec = pkg.controlelasticmembrane(48)
+    spec = {"membrane48": lambda: pkg.controlelasticmembrane(48),
+            "membrane512_templates": lambda: pkg.controlelasticmembrane(512),
+            "kappa3d64_templates_aux_stream": lambda: pkg.poissonmixed(64, 3, True),
+            "burger_param_aux_stream": lambda: pkg.burger1d_param(100000)}[case]()
     nlp = GridapPDENLPModel(spec, device="cuda:0")
     rng = np.random.default_rng(4)
-    x = _d(rng.uniform(-1, 1, nlp.meta.nvar)); lam = _d(rng.uniform(-1, 1, nlp.meta.ncon))
+    def _x():
+        v = rng.uniform(-1, 1, nlp.meta.nvar)
+        if spec.nparam:
+            v[: spec.nparam] = 1 + 0.1 * rng.uniform(-1, 1, spec.nparam)
+        return v
+    x = _d(_x()); lam = _d(rng.uniform(-1, 1, nlp.meta.ncon))
     jv = torch.empty(nlp.meta.nnzj, dtype=torch.float64, device="cuda")
     hv = torch.empty(nlp.meta.nnzh, dtype=torch.float64, device="cuda")
     g = torch.empty(nlp.meta.nvar, dtype=torch.float64, device="cuda")
@@ -331,11 +342,19 @@ def test_callbacks_can_be_captured_in_a_cuda_graph(pkg, cuda_lib):
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
         nlp.jac_coord_(x, jv); nlp.hess_coord_(x, lam, hv, obj_weight=0.5); nlp.grad_(x, g); nlp.cons_(x, c)
-    x2 = _d(rng.uniform(-1, 1, nlp.meta.nvar)); lam2 = _d(rng.uniform(-1, 1, nlp.meta.ncon))
+    x2 = _d(_x()); lam2 = _d(rng.uniform(-1, 1, nlp.meta.ncon))
     x.copy_(x2); lam.copy_(lam2)
     jv.fill_(float("nan")); hv.fill_(float("nan"))
     graph.replay()
     torch.cuda.synchronize()
-    assert torch.equal(jv, nlp.jac_coord(x2)) and torch.equal(hv, nlp.hess_coord(x2, lam2, obj_weight=0.5))
+    jr, hr = nlp.jac_coord(x2), nlp.hess_coord(x2, lam2, obj_weight=0.5)
+    if spec.nparam == 0:
+        assert torch.equal(jv, jr) and torch.equal(hv, hr)
+    else:  # (the dense kappa blocks are atomic sums: equal up to round-off; the FE segments bit for bit)
+        I = nlp.handle.info
+        assert torch.equal(jv[int(I.nnzj_k):], jr[int(I.nnzj_k):])
+        assert torch.allclose(jv, jr, rtol=1e-12, atol=1e-14 * float(jr.abs().max()))
+        assert torch.allclose(hv, hr, rtol=1e-12, atol=1e-14 * float(hr.abs().max()))
+        assert not torch.isnan(hv).any() and not torch.isnan(jv).any()
     assert torch.allclose(g, nlp.grad(x2), rtol=1e-13, atol=1e-15) and torch.allclose(c, nlp.cons(x2), rtol=1e-13, atol=1e-15)
     nlp.close()
