@@ -113,6 +113,9 @@ struct KTab {
   __host__ __device__ static constexpr int uu(int j, int i) { return OFF_UU + j * NU + i; }
 };
 
+// chunk of the cell-granular template path: first entry in the Jacobian y- / u-block and the FE Hessian block, cells (1..32)
+struct __align__(32) ChunkRec { long long jy, ju, h, n; };
+
 struct DevModel {
   const int32_t* dofs_y;
   const int32_t* dofs_u;
@@ -144,13 +147,10 @@ struct DevModel {
   const double* tpl_jy;    // [32*RUN_JY] image of one template tile of the Jacobian y-block (model-owned scratch)
   const double* tpl_ju;    // [32*RUN_JU]
   const double* tpl_h;     // [32*RUN_H]  objective FE Hessian block
-  // ---- cell-granular templates (see "cell-granular templates" below); ch_n == nullptr: not in use.  The slab's cells
+  // ---- cell-granular templates (see "cell-granular templates" below); ch == nullptr: not in use.  The slab's cells
   // are either members of a CHUNK (<= 32 consecutive template cells = one contiguous run of every COO segment, stored
   // from the shared-memory image with one bulk copy) or GENERIC cells (evaluated one per lane, stored directly).
-  const int64_t* ch_jy;    // [nchunk] first entry of the chunk in the Jacobian y-block
-  const int64_t* ch_ju;    // [nchunk]   ... u-block
-  const int64_t* ch_h;     // [nchunk]   ... FE Hessian block
-  const uint8_t* ch_n;     // [nchunk] cells of the chunk (1..32)
+  const ChunkRec* ch;      // [nchunk] one 32 B record per chunk: a copy CTA reads ONE sector before its first store
   const int32_t* gc_cell;  // [ngc] generic cells, ascending
   const int64_t* gc_jy;    // [ngc] first entry of the cell in each segment
   const int64_t* gc_ju;
@@ -1723,20 +1723,22 @@ __device__ __forceinline__ void cg_emit_hess_K(const double* __restrict__ Ks, co
   }
 }
 
-// one CTA per chunk: copies the first n*RUN doubles of the image(s) to the chunk's run(s) (element-independent)
+// one CTA per chunk: copies the first n*RUN doubles of the image(s) to the chunk's run(s) (element-independent).
+// which = 0: Jacobian (segment a = y-block, b = u-block when b.vals != nullptr); 1: FE Hessian block (segment a)
 struct ChunkSeg {
   double* vals;         // segment of the output (nullptr: unused)
-  const int64_t* off;   // [nchunk] first entry of the chunk in the segment
   const double* img;    // image of a template tile
   int run;              // entries per template cell
 };
-static __global__ void __launch_bounds__(kThreads) k_copy_chunks(ChunkSeg a, ChunkSeg b, const uint8_t* __restrict__ ch_n) {
+static __global__ void __launch_bounds__(kThreads) k_copy_chunks(ChunkSeg a, ChunkSeg b, const ChunkRec* __restrict__ ch, int which) {
   griddep_wait();  // (the image is written by the preceding one-tile launch on the stream)
   griddep_launch_dependents();
-  const int64_t k = blockIdx.x;
-  const int n = ch_n[k];
-  copy_image(a.vals + a.off[k], a.img, n * a.run, 32 * a.run);
-  if (b.vals != nullptr) copy_image(b.vals + b.off[k], b.img, n * b.run, 32 * b.run);
+  // the record is two 16 B loads of one sector: both segment offsets are known before the first store
+  const longlong2 r0 = __ldg(reinterpret_cast<const longlong2*>(ch + blockIdx.x));
+  const longlong2 r1 = __ldg(reinterpret_cast<const longlong2*>(ch + blockIdx.x) + 1);
+  const int n = (int)r1.y;
+  copy_image(a.vals + (which ? r1.x : r0.x), a.img, n * a.run, 32 * a.run);
+  if (b.vals != nullptr) copy_image(b.vals + r0.y, b.img, n * b.run, 32 * b.run);
 }
 
 // generic cells of the Jacobian blocks: one warp per 32 cells of the list

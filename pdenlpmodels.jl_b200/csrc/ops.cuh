@@ -186,15 +186,15 @@ struct OpsImpl : Ops {
   static int cg_cells_grid(const DevModel& D) { return (D.ngc + kThreads - 1) / kThreads; }
   int jac(const Launch& L, const DevModel& D, const double* x, double* vy, double* vu) override {
     if constexpr (tpl_ok<E, false>()) {
-      if (D.ch_n != nullptr && !D.notrait && !L.generic) {
+      if (D.ch != nullptr && !D.notrait && !L.generic) {
         if (D.ngc > 0) {
           CU(launch_kernel(k_jac_cells_cg<E>, cg_cells_grid(D), kThreads, 0, L.aux ? L.aux : L.stream, false, tab, D, x, vy, vu));
           count_launch(L);
         }
         if (D.nchunk > 0) {
-          const ChunkSeg a{vy, D.ch_jy, D.tpl_jy, E::RUN_JY};
-          const ChunkSeg b{E::NU > 0 ? vu : nullptr, D.ch_ju, D.tpl_ju, E::RUN_JU};
-          CU(launch_kernel(k_copy_chunks, D.nchunk, kThreads, 0, L.stream, pdl_chain(), a, b, D.ch_n));
+          const ChunkSeg a{vy, D.tpl_jy, E::RUN_JY};
+          const ChunkSeg b{E::NU > 0 ? vu : nullptr, D.tpl_ju, E::RUN_JU};
+          CU(launch_kernel(k_copy_chunks, D.nchunk, kThreads, 0, L.stream, pdl_chain(), a, b, D.ch, 0));
           count_launch(L);
         }
         return PDENLP_OK;
@@ -209,15 +209,15 @@ struct OpsImpl : Ops {
   }
   int hess(const Launch& L, const DevModel& D, const double* x, const double* lam, double ow, double* vo, double* vc) override {
     if constexpr (tpl_ok<E, true>()) {
-      if (D.ch_n != nullptr && !D.notrait && !L.generic && vo != nullptr && vc == nullptr) {
+      if (D.ch != nullptr && !D.notrait && !L.generic && vo != nullptr && vc == nullptr) {
         if (D.ngc > 0) {
           CU(launch_kernel(k_hess_cells_cg<E>, cg_cells_grid(D), kThreads, 0, L.aux ? L.aux : L.stream, false, tab, D, x, ow, vo));
           count_launch(L);
         }
         if (D.nchunk > 0) {
-          const ChunkSeg a{vo, D.ch_h, D.tpl_h, E::RUN_H};
-          const ChunkSeg b{nullptr, nullptr, nullptr, 0};
-          CU(launch_kernel(k_copy_chunks, D.nchunk, kThreads, 0, L.stream, pdl_chain(), a, b, D.ch_n));
+          const ChunkSeg a{vo, D.tpl_h, E::RUN_H};
+          const ChunkSeg b{nullptr, nullptr, 0};
+          CU(launch_kernel(k_copy_chunks, D.nchunk, kThreads, 0, L.stream, pdl_chain(), a, b, D.ch, 1));
           count_launch(L);
         }
         return PDENLP_OK;

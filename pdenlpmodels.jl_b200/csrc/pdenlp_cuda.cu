@@ -237,7 +237,7 @@ int build_template(pdenlp_model* m, bool hess, const double* dx, double ow) {
   dt.base_jy = dt.base_ju = dt.base_h = m->zero_base;
   dt.tpl_list = dt.gen_list = nullptr;
   dt.ntpl = 0; dt.ngen = 1;
-  dt.ch_n = nullptr; dt.nchunk = 0; dt.ngc = 0;
+  dt.ch = nullptr; dt.nchunk = 0; dt.ngc = 0;
   Launch L{m->stream, m->sms, false, &m->launches};
   if (hess) {
     if (int rc = m->ops->hess(L, dt, dx, nullptr, ow, m->tpl_h, nullptr)) return rc;
@@ -317,15 +317,14 @@ int classify_cells(pdenlp_model* m, const pdenlp_desc& desc, unsigned long long 
   }
   flush();
   if (m->ch_cell0_h.size() >= ((size_t)1 << 31) || m->gc_cell_h.size() >= ((size_t)1 << 31)) return PDENLP_OK;
-  int64_t* lp; uint8_t* bp; int32_t* ip;
-  if (int r = dev_upload(m, m->ch_jy_h.data(), m->ch_jy_h.size(), &lp)) return r;
-  m->dm.ch_jy = lp;
-  if (int r = dev_upload(m, m->ch_ju_h.data(), m->ch_ju_h.size(), &lp)) return r;
-  m->dm.ch_ju = lp;
-  if (int r = dev_upload(m, m->ch_h_h.data(), m->ch_h_h.size(), &lp)) return r;
-  m->dm.ch_h = lp;
-  if (int r = dev_upload(m, chn.data(), chn.size(), &bp)) return r;
-  m->dm.ch_n = bp;
+  int64_t* lp; int32_t* ip;
+  {
+    std::vector<ChunkRec> recs(m->ch_cell0_h.size());
+    for (size_t k = 0; k < recs.size(); ++k) recs[k] = ChunkRec{m->ch_jy_h[k], m->ch_ju_h[k], m->ch_h_h[k], (long long)chn[k]};
+    ChunkRec* rp = nullptr;
+    if (int r = dev_upload(m, recs.data(), recs.size(), &rp)) return r;
+    m->dm.ch = rp;
+  }
   if (int r = dev_upload(m, m->gc_cell_h.data(), m->gc_cell_h.size(), &ip)) return r;
   m->dm.gc_cell = ip;
   if (int r = dev_upload(m, gjy.data(), gjy.size(), &lp)) return r;
@@ -841,8 +840,7 @@ int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
   m->dm.tpl_list = m->dm.gen_list = nullptr;
   m->dm.ntpl = 0; m->dm.ngen = 0;
   m->dm.tpl_jy = m->dm.tpl_ju = m->dm.tpl_h = nullptr;
-  m->dm.ch_jy = m->dm.ch_ju = m->dm.ch_h = nullptr;
-  m->dm.ch_n = nullptr;
+  m->dm.ch = nullptr;
   m->dm.gc_cell = nullptr;
   m->dm.gc_jy = m->dm.gc_ju = m->dm.gc_h = nullptr;
   m->dm.nchunk = 0; m->dm.ngc = 0;

@@ -7,7 +7,7 @@ cfgs=${@:-3 4 5}
 mkdir -p gpurun_out
 for k in $cfgs; do
   python tools/profile_configs.py --config $k > gpurun_out/${tag}_cfg${k}_plain.log 2>&1 || { echo "plain run failed for $k"; tail -5 gpurun_out/${tag}_cfg${k}_plain.log; continue; }
-  ncu --set full --clock-control none -k regex:'k_(vector|jac|hess|zero|add|sum)' -c ${NCU_COUNT:-40} -f \
+  ncu --set full --clock-control none -k regex:'k_(vector|jac|hess|zero|add|sum|copy)' -c ${NCU_COUNT:-40} -f \
       -o gpurun_out/${tag}_cfg${k} python tools/profile_configs.py --config $k > gpurun_out/${tag}_cfg${k}_ncu.log 2>&1
   ncu -i gpurun_out/${tag}_cfg${k}.ncu-rep --page raw --csv > gpurun_out/${tag}_cfg${k}_raw.csv 2>/dev/null
   [ -n "$KEEP_REP" ] || rm -f gpurun_out/${tag}_cfg${k}.ncu-rep
