@@ -451,6 +451,7 @@ def main():
     t_create = time.perf_counter() - t_create  # pdenlp_create: upload, tile offsets, tile classification, self-check
     info = nlp.handle.info
     t_setup = time.perf_counter() - t_setup
+    tpl_stats = nlp.handle.template_stats()
 
     x = torch.from_numpy(np.random.default_rng(1998).uniform(-1, 1, info.nvar)).to(dev)
     lam = torch.from_numpy(np.random.default_rng(1999).uniform(-1, 1, info.ncon)).to(dev)
@@ -556,6 +557,8 @@ def main():
                 "l2": "streams > L2 every step (10.0 GB of outputs, 0.5 GB of inputs per step at N=1)",
                 "x": "U(-1,1) seed 1998, lambda U(-1,1) seed 1999", "setup_s": round(t_setup, 2),
                 "create_s": round(t_create, 3),
+                # cells whose COO image is copied from the template image / cells evaluated one by one
+                "templates": tpl_stats,
             },
             "jac_ms": jac_ms_max, "hess_ms": hess_ms_max,
             "roofline": {

@@ -374,6 +374,10 @@ int pdenlp_sharded_hess_structure(pdenlp_sharded* s, int64_t* rows, int64_t* col
    the CUDA-event time (ms) of the most recent callback on the handle's stream */
 int pdenlp_launch_count(const pdenlp_model* m, int64_t* launches);
 int pdenlp_last_kernel_ms(pdenlp_model* m, float* ms);
+/* template path of jac_coord! / hess_coord!: stats[0] = chunks of consecutive template cells,
+   stats[1] = template cells (copied from the image), stats[2] = generic cells (evaluated one by one), stats[3] = images
+   built so far; all 0 when the model evaluates every cell (no template path, small slab, PDENLP_FLAG_NO_TEMPLATES) */
+int pdenlp_template_stats(const pdenlp_model* m, int64_t stats[4]);
 int pdenlp_set_timing(pdenlp_model* m, int32_t enabled);
 
 #ifdef __cplusplus

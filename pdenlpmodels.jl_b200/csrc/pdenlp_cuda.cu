@@ -81,6 +81,7 @@ struct pdenlp_model {
   int64_t tpl_builds = 0;
   // cell-granular templates: host copies of the chunk table (the self-check cuts its sample at a chunk start)
   bool cg_active = false;
+  int64_t ntpl_cells = 0;
   // auxiliary stream of the cell-granular template path: the generic-cell kernel and the latency-bound kappa-block
   // kernels of jac_coord! / hess_coord! run there, concurrently with the chunk copy on the caller's stream
   cudaStream_t aux = nullptr;
@@ -272,6 +273,7 @@ int classify_cells(pdenlp_model* m, const pdenlp_desc& desc, unsigned long long 
     if (first_full < 0 && mask[t] == 0xffffffffu) first_full = t;
   }
   if (first_full < 0 || ntplc * 4 < nc) return PDENLP_OK;
+  m->ntpl_cells = ntplc;
   const int ny = desc.ny, nu = desc.nu;
   const int64_t rjy = m->ops->run_jy(), rju = m->ops->run_ju(), rh = m->ops->run_h();
   std::vector<int64_t> gjy, gju, gh;
@@ -1332,6 +1334,14 @@ int pdenlp_input_ranges(const pdenlp_model* m, int64_t ranges[4]) {
 int pdenlp_launch_count(const pdenlp_model* m, int64_t* launches) {
   if (!m || !launches) return fail(PDENLP_EINVAL, "null argument");
   *launches = m->launches;
+  return PDENLP_OK;
+}
+int pdenlp_template_stats(const pdenlp_model* m, int64_t stats[4]) {
+  if (!m || !stats) return fail(PDENLP_EINVAL, "null argument");
+  stats[0] = m->cg_active ? m->dm.nchunk : 0;
+  stats[1] = m->cg_active ? m->ntpl_cells : 0;
+  stats[2] = m->cg_active ? m->dm.ngc : 0;
+  stats[3] = m->tpl_builds;
   return PDENLP_OK;
 }
 int pdenlp_set_timing(pdenlp_model* m, int32_t enabled) {

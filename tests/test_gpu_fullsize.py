@@ -286,3 +286,63 @@ def test_template_path_equals_cell_by_cell_evaluation_over_whole_outputs(pkg, cu
             del ha, hb
     finally:
         a.close(); b.close()
+
+
+TEMPLATE_FAMILIES = {
+    # every instantiated element with a template path, at a size where it is active (>= 4096 tiles of 32 cells)
+    "membrane_q1q1_nq1": lambda pkg: pkg.controlelasticmembrane(384, state_order=1),
+    "membrane_q1q1_nq4": lambda pkg: pkg.controlelasticmembrane(384, state_order=1, degree=2),
+    "membrane_q2q1_nq1": lambda pkg: pkg.controlelasticmembrane(384),
+    "membrane_q2q1_nq4": lambda pkg: pkg.controlelasticmembrane(384, degree=2),
+    "membrane3d_q1q1_nq1": lambda pkg: pkg.controlelasticmembrane(56, state_order=1, dim=3),
+    "membrane3d_q1q1_nq8": lambda pkg: pkg.controlelasticmembrane(56, state_order=1, degree=2, dim=3),
+    "kappa_poisson2d": lambda pkg: pkg.poissonmixed(384, 2, False),
+    "kappa_poisson2d_control": lambda pkg: pkg.poissonmixed(384, 2, True),
+    "kappa_poisson3d_control": lambda pkg: pkg.poissonmixed(56, 3, True),
+    "poissonparam": lambda pkg: pkg.poissonparam(384),
+    "penalizedpoisson": lambda pkg: pkg.penalizedpoisson(384),
+    "basicunconstrained": lambda pkg: pkg.basicunconstrained(384),
+}
+
+
+@pytest.mark.parametrize("family", sorted(TEMPLATE_FAMILIES))
+def test_template_path_equals_cell_by_cell_evaluation_for_every_element_family(pkg, cuda_lib, family):
+    """The cell-granular template path against the generic kernels (PDENLP_FLAG_NO_TEMPLATES) over whole outputs, for
+    every (integrand, element, quadrature) instance that has one: FE segments bit for bit (same fma chains), dense
+    kappa blocks to round-off.  The small parity cases of test_gpu_parity.py stay below the 4096-tile threshold and
+    never take this path."""
+    from pdenlp_b200.model import GridapPDENLPModel
+    spec = TEMPLATE_FAMILIES[family](pkg)
+    a = GridapPDENLPModel(spec, device="cuda:0")
+    b = GridapPDENLPModel(spec, device="cuda:0", flat=a.flat, templates=False)
+    try:
+        I = a.handle.info
+        assert a.flat.ncells >= 4096 * 32
+        sa, sb = a.handle.template_stats(), b.handle.template_stats()
+        assert sa["chunks"] > 0 and sa["template_cells"] + sa["generic_cells"] == a.flat.ncells, sa  # the path is taken
+        assert sa["template_cells"] > 0.85 * a.flat.ncells and sb["chunks"] == 0, (sa, sb)  # (3-D n = 56: 54^3 / 56^3 = 0.897)
+        rng = np.random.default_rng(5)
+        xh = rng.uniform(-1, 1, I.nvar)
+        if spec.nparam:
+            xh[: spec.nparam] = 1 + 0.1 * rng.uniform(-1, 1, spec.nparam)
+        x = torch.from_numpy(xh).cuda()
+        ncon = a.meta.ncon  # (0 for the unconstrained problems)
+        lam = torch.from_numpy(rng.uniform(-1, 1, ncon)).cuda()
+
+        def same(u, v, dense):  # dense = [(lo, hi)] ranges of atomic sums inside the stream
+            mask = torch.ones(u.numel(), dtype=torch.bool, device=u.device)
+            for lo, hi in dense:
+                mask[lo:hi] = False
+                if hi > lo:
+                    assert float((u[lo:hi] - v[lo:hi]).abs().max()) <= 1e-12 * max(float(v[lo:hi].abs().max()), 1e-300)
+            assert torch.equal(u[mask], v[mask])
+
+        if ncon > 0:
+            same(a.jac_coord(x), b.jac_coord(x), [(0, int(I.nnzj_k))])
+        ko, kc, fo = int(I.nnzh_k_obj), int(I.nnzh_k_con), int(I.nnzh_fe_obj)
+        for ow in (1.0, 0.37, 0.0):
+            if ncon > 0:
+                same(a.hess_coord(x, lam, obj_weight=ow), b.hess_coord(x, lam, obj_weight=ow), [(0, ko), (ko + fo, ko + fo + kc)])
+            same(a.hess_coord(x, obj_weight=ow), b.hess_coord(x, obj_weight=ow), [(0, ko)])
+    finally:
+        a.close(); b.close()
