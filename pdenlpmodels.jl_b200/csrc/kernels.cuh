@@ -1730,8 +1730,12 @@ struct ChunkSeg {
   const double* img;    // image of a template tile
   int run;              // entries per template cell
 };
-static __global__ void __launch_bounds__(kThreads) k_copy_chunks(ChunkSeg a, ChunkSeg b, const ChunkRec* __restrict__ ch, int which) {
-  griddep_wait();  // (the image is written by the preceding one-tile launch on the stream)
+// chained = 1: launched with programmatic stream serialization right behind the generic-cell kernel of the same callback
+// (same stream, disjoint outputs).  That kernel started only after the image was complete, so this one need not wait
+// for it before copying; ONE thread waits at the end, so that the completion of this grid implies the completion of
+// its predecessor (the k_zero_fill protocol).  Both run concurrently without an event fork / join.
+static __global__ void __launch_bounds__(kThreads) k_copy_chunks(ChunkSeg a, ChunkSeg b, const ChunkRec* __restrict__ ch, int which, int chained) {
+  if (!chained) griddep_wait();  // (the image is written by the preceding one-tile launch on the stream)
   griddep_launch_dependents();
   // the record is two 16 B loads of one sector: both segment offsets are known before the first store
   const longlong2 r0 = __ldg(reinterpret_cast<const longlong2*>(ch + blockIdx.x));
@@ -1739,6 +1743,7 @@ static __global__ void __launch_bounds__(kThreads) k_copy_chunks(ChunkSeg a, Chu
   const int n = (int)r1.y;
   copy_image(a.vals + (which ? r1.x : r0.x), a.img, n * a.run, 32 * a.run);
   if (b.vals != nullptr) copy_image(b.vals + r0.y, b.img, n * b.run, 32 * b.run);
+  if (chained && blockIdx.x == 0 && threadIdx.x == 0) griddep_wait();
 }
 
 // generic cells of the Jacobian blocks: one warp per 32 cells of the list

@@ -42,6 +42,9 @@ struct Launch {
   // auxiliary stream (already forked from `stream` by the caller, who also joins it): the cell-granular template path
   // runs its generic-cell kernel there, concurrently with the chunk copy; nullptr: everything on `stream`
   cudaStream_t aux = nullptr;
+  // true (and aux == nullptr): the template path chains its chunk copy behind its generic-cell kernel on `stream` with
+  // programmatic stream serialization instead of forking the auxiliary stream (models without kappa-block kernels)
+  bool chain = false;
   int bg_ctas = 0;  // > 0: CTAs per SM of the kappa-block kernels when they run in the background of a streaming kernel
 };
 inline void count_launch(const Launch& L, int n = 1) { if (L.launches) *L.launches += n; }
@@ -194,7 +197,8 @@ struct OpsImpl : Ops {
         if (D.nchunk > 0) {
           const ChunkSeg a{vy, D.tpl_jy, E::RUN_JY};
           const ChunkSeg b{E::NU > 0 ? vu : nullptr, D.tpl_ju, E::RUN_JU};
-          CU(launch_kernel(k_copy_chunks, D.nchunk, kThreads, 0, L.stream, pdl_chain(), a, b, D.ch, 0));
+          const bool chained = L.chain && !L.aux && D.ngc > 0;
+          CU(launch_kernel(k_copy_chunks, D.nchunk, kThreads, 0, L.stream, chained || pdl_chain(), a, b, D.ch, 0, chained ? 1 : 0));
           count_launch(L);
         }
         return PDENLP_OK;
@@ -217,7 +221,8 @@ struct OpsImpl : Ops {
         if (D.nchunk > 0) {
           const ChunkSeg a{vo, D.tpl_h, E::RUN_H};
           const ChunkSeg b{nullptr, nullptr, 0};
-          CU(launch_kernel(k_copy_chunks, D.nchunk, kThreads, 0, L.stream, pdl_chain(), a, b, D.ch, 1));
+          const bool chained = L.chain && !L.aux && D.ngc > 0;
+          CU(launch_kernel(k_copy_chunks, D.nchunk, kThreads, 0, L.stream, chained || pdl_chain(), a, b, D.ch, 1, chained ? 1 : 0));
           count_launch(L);
         }
         return PDENLP_OK;

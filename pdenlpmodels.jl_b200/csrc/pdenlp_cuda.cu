@@ -1125,7 +1125,10 @@ int pdenlp_jac_coord(pdenlp_model* m, const double* x, double* vals) {
   if (int rc = out_ptr(m, vals, m->info.nnzj, &dv)) return rc;
   if (m->ops->needs_coef_deriv() && !m->dm.coef) return fail(PDENLP_EINVAL, "this integrand's derivatives need the coefficient fields (desc.coef)");
   Launch L{m->stream, m->sms, false, &m->launches};
-  Fork fk(m, m->cg_active || m->info.nnzj_k > 0);  // kappa block (+ generic cells) beside the FE stream
+  // kappa block (+ generic cells) beside the FE stream on the auxiliary stream; template models WITHOUT a kappa block
+  // need no second stream: their chunk copy is chained behind the generic-cell kernel (Launch::chain)
+  static const bool no_chain = getenv("PDENLP_NO_CHAIN") != nullptr;  // experiments / A-B runs
+  Fork fk(m, m->info.nnzj_k > 0 || (m->cg_active && no_chain));
   if (m->info.nnzj_k > 0) {
     if (!m->dm.coef) return fail(PDENLP_EINVAL, "the kappa block needs the coefficient fields (desc.coef)");
     CU(cudaMemsetAsync(dv, 0, (size_t)m->info.nnzj_k * 8, fk.side()));
@@ -1141,6 +1144,7 @@ int pdenlp_jac_coord(pdenlp_model* m, const double* x, double* vals) {
   double* vu = vy + m->info.nnzj_y;
   if (int rc = build_template(m, false, dx, 1.0)) return rc;
   L.aux = fk.aux();
+  L.chain = !fk.on && !no_chain;
   if (int rc = m->ops->jac(L, m->dm, dx, vy, vu)) return rc;
   fk.join();
   return out_finish(m, vals, m->info.nnzj);
@@ -1161,7 +1165,9 @@ int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda, do
   double* vfo = vko + I.nnzh_k_obj;
   double* vkc = vfo + I.nnzh_fe_obj;
   double* vfc = vkc + I.nnzh_k_con;
-  Fork fk(m, m->cg_active || (I.nnzh_k_obj + I.nnzh_k_con > 0 && !m->nofe));  // kappa blocks (+ generic cells) beside the FE stream and the zero fill
+  // kappa blocks (+ generic cells) beside the FE stream and the zero fill (see pdenlp_jac_coord)
+  static const bool no_chain = getenv("PDENLP_NO_CHAIN") != nullptr;
+  Fork fk(m, (I.nnzh_k_obj + I.nnzh_k_con > 0 && !m->nofe) || (m->cg_active && no_chain));
   if (I.nnzh_k_obj + I.nnzh_k_con > 0) {
     if (!m->dm.coef) return fail(PDENLP_EINVAL, "the kappa blocks need the coefficient fields (desc.coef)");
     CU(cudaMemsetAsync(vko, 0, (size_t)I.nnzh_k_obj * 8, fk.side()));
@@ -1216,6 +1222,7 @@ int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda, do
   if (vo || vc) {
     if (vo && !vc) { if (int rc = build_template(m, true, dx, obj_weight)) return rc; }
     L.aux = fk.aux();
+    L.chain = !fk.on && !no_chain;
     if (int rc = m->ops->hess(L, m->dm, dx, dl, obj_weight, vo, vc)) return rc;
   }
   if (cons_zero && !host_tail && pdl) {
@@ -1238,7 +1245,8 @@ int pdenlp_hess_coord_obj(pdenlp_model* m, const double* x, double obj_weight, d
   if (int rc = out_ptr(m, vals, I.nnzh_obj, &dv)) return rc;
   if (m->ops->needs_coef_deriv() && !m->dm.coef) return fail(PDENLP_EINVAL, "this integrand's derivatives need the coefficient fields (desc.coef)");
   Launch L{m->stream, m->sms, false, &m->launches};
-  Fork fk(m, m->cg_active || (I.nnzh_k_obj > 0 && !m->nofe));
+  static const bool no_chain = getenv("PDENLP_NO_CHAIN") != nullptr;
+  Fork fk(m, (I.nnzh_k_obj > 0 && !m->nofe) || (m->cg_active && no_chain));
   if (I.nnzh_k_obj > 0) {
     if (!m->dm.coef) return fail(PDENLP_EINVAL, "the kappa blocks need the coefficient fields (desc.coef)");
     CU(cudaMemsetAsync(dv, 0, (size_t)I.nnzh_k_obj * 8, fk.side()));
@@ -1257,6 +1265,7 @@ int pdenlp_hess_coord_obj(pdenlp_model* m, const double* x, double obj_weight, d
   if (!m->nofe) {
     if (int rc = build_template(m, true, dx, obj_weight)) return rc;
     L.aux = fk.aux();
+    L.chain = !fk.on && !no_chain;
     if (int rc = m->ops->hess(L, m->dm, dx, nullptr, obj_weight, dv + I.nnzh_k_obj, nullptr)) return rc;
   }
   fk.join();
