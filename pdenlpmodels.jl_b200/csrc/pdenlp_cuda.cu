@@ -257,7 +257,8 @@ int build_template(pdenlp_model* m, bool hess, const double* dx, double ow) {
 // (a template cell has RUN entries per segment, a generic cell its counted ones) and re-checked at every tile end.
 int classify_cells(pdenlp_model* m, const pdenlp_desc& desc, unsigned long long sy, unsigned long long su) {
   const int64_t nt = m->dm.ntiles, nc = desc.ncells;
-  if (nt < 4096) return PDENLP_OK;  // (small slabs: the per-CTA image load would cost more than it saves)
+  if (nt < 4096) return PDENLP_OK;  // (small slabs: launch-bound either way; the tile kernels need no image)
+  if (nc >= ((int64_t)1 << 31)) return PDENLP_OK;  // (the generic-cell list holds int32 cell numbers)
   if (desc.nq > 1 && m->dm.ktab == nullptr) return PDENLP_OK;
   uint32_t* dmask = nullptr;
   CU(cudaMalloc((void**)&dmask, (size_t)nt * 4));
