@@ -116,7 +116,8 @@ host vectors).
 """
 function attach_cuda!(nlp::GridapPDENLPModel, integrand::Integrand; params = Float64[], target = x -> 0.0,
                       source = x -> 0.0, degree::Int = 1, memspace::Integer = 1, device::Integer = -1,
-                      devices::Union{Nothing, AbstractVector{<:Integer}} = nothing)
+                      devices::Union{Nothing, AbstractVector{<:Integer}} = nothing,
+                      deterministic::Bool = false, templates::Bool = true)
   Ypde, Ycon = nlp.pdemeta.Ypde, nlp.pdemeta.Ycon
   trian = get_triangulation(Ypde)
   dΩ = Measure(trian, degree)
@@ -187,7 +188,8 @@ function attach_cuda!(nlp::GridapPDENLPModel, integrand::Integrand; params = Flo
              pointer(celly), pointer(cellu), pointer(diry), pointer(diru),
              pointer(phi_y), pointer(grad_y), pointer(phi_u), pointer(wdet), 2, length(uf), pointer(coef), par,
              pointer(field_nfree), pointer(field_ndir),
-             geom_nq == 0 ? Ptr{Float64}(C_NULL) : pointer(jinvT), geom_nq == 0 ? Ptr{Float64}(C_NULL) : pointer(detj), geom_nq, 0)
+             geom_nq == 0 ? Ptr{Float64}(C_NULL) : pointer(jinvT), geom_nq == 0 ? Ptr{Float64}(C_NULL) : pointer(detj), geom_nq,
+             Int32((deterministic ? 1 : 0) | (templates ? 0 : 2)))   # PDENLP_FLAG_DETERMINISTIC | PDENLP_FLAG_NO_TEMPLATES
     if sharded
       check(ccall((:pdenlp_sharded_create, LIB), Cint, (Ref{Desc}, Int32, Ptr{Int32}, Ref{Ptr{Cvoid}}), d, length(devs), devs, h))
     else
