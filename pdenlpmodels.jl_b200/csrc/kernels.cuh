@@ -28,10 +28,14 @@
 //   k_jac_coord, k_hess_coord                  the two streaming writers (register pipeline over tiles; nq > 1 elements
 //                                              take the reference-tensor path, the register-accumulate path for small
 //                                              nonlinear elements, or per-point accumulation in shared memory)
+//   k_copy_chunks, k_jac_cells_cg, k_hess_cells_cg   cell-granular templates: affine problems on identical cells copy the
+//                                              image of a template cell (pure 16 B-store stream) and evaluate only
+//                                              the boundary cells (lane = entry emission)
 //   k_jac_coord_mf, k_hess_coord_mf            the same writers for multi-field spaces (block-ordered emission)
 //   k_structure, k_count                       setup: rows / cols and per-tile entry counts
 //   k_vector<OP>                               obj, grad!, cons!, jprod!, jtprod!, hprod! (matrix-free, atomics)
 //   k_zero_fill, k_sum_partials, k_nofe        zero fill of structurally zero blocks, objective reduction, NoFETerm
+//   last_cta, finish_objective / finish_partials   second pass of a reduction by the last CTA to arrive (no extra launch)
 //   k_jac_kappa, k_hess_kappa(_kk)             dense kappa blocks
 #pragma once
 #include <cstdint>
