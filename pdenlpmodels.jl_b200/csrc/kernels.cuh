@@ -1553,7 +1553,7 @@ __device__ __forceinline__ void copy_image(double* __restrict__ g, const double*
   const int n2 = (n - head) >> 1;
   double2* const q = reinterpret_cast<double2*>(g + head);
 #pragma unroll 4
-  for (int i = threadIdx.x; i < n2; i += kThreads) {
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
     int j0 = 2 * i + head, j1 = j0 + 1;
     j0 -= j0 >= len ? len : 0;
     j1 -= j1 >= len ? len : 0;

@@ -187,6 +187,12 @@ struct OpsImpl : Ops {
   }
   // cell-granular templates (kernels.cuh): generic cells (256 per CTA) on the auxiliary stream, chunk copy (one per CTA)
   static int cg_cells_grid(const DevModel& D) { return (D.ngc + kThreads - 1) / kThreads; }
+  // threads per CTA of the chunk copy (tuning knob PDENLP_COPY_THREADS = 64 | 128 | 256).  Measured (tools/ab_copy_threads.sh,
+  // config 2 jac_coord! ms): 64: 0.628, 128: 0.570, 256: 0.546, 384: 0.618, 512: 0.738 — a sharp optimum at 256
+  static int copy_threads() {
+    static const int t = [] { const char* e = getenv("PDENLP_COPY_THREADS"); int v = e ? atoi(e) : kThreads; return (v == 64 || v == 128 || v == 256) ? v : kThreads; }();
+    return t;
+  }
   int jac(const Launch& L, const DevModel& D, const double* x, double* vy, double* vu) override {
     if constexpr (tpl_ok<E, false>()) {
       if (D.ch != nullptr && !D.notrait && !L.generic) {
@@ -198,7 +204,7 @@ struct OpsImpl : Ops {
           const ChunkSeg a{vy, D.tpl_jy, E::RUN_JY};
           const ChunkSeg b{E::NU > 0 ? vu : nullptr, D.tpl_ju, E::RUN_JU};
           const bool chained = L.chain && !L.aux && D.ngc > 0;
-          CU(launch_kernel(k_copy_chunks, D.nchunk, kThreads, 0, L.stream, chained || pdl_chain(), a, b, D.ch, 0, chained ? 1 : 0));
+          CU(launch_kernel(k_copy_chunks, D.nchunk, copy_threads(), 0, L.stream, chained || pdl_chain(), a, b, D.ch, 0, chained ? 1 : 0));
           count_launch(L);
         }
         return PDENLP_OK;
@@ -222,7 +228,7 @@ struct OpsImpl : Ops {
           const ChunkSeg a{vo, D.tpl_h, E::RUN_H};
           const ChunkSeg b{nullptr, nullptr, 0};
           const bool chained = L.chain && !L.aux && D.ngc > 0;
-          CU(launch_kernel(k_copy_chunks, D.nchunk, kThreads, 0, L.stream, chained || pdl_chain(), a, b, D.ch, 1, chained ? 1 : 0));
+          CU(launch_kernel(k_copy_chunks, D.nchunk, copy_threads(), 0, L.stream, chained || pdl_chain(), a, b, D.ch, 1, chained ? 1 : 0));
           count_launch(L);
         }
         return PDENLP_OK;
