@@ -86,6 +86,7 @@ struct pdenlp_model {
   // kernels of jac_coord! / hess_coord! run there, concurrently with the chunk copy on the caller's stream
   cudaStream_t aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_switch = nullptr;  // orders a new caller stream behind the previous one (pdenlp_set_stream)
   std::vector<int64_t> ch_cell0_h, ch_jy_h, ch_ju_h, ch_h_h;
   std::vector<int32_t> gc_cell_h;
   std::vector<int64_t> hb_jy, hb_ju, hb_h;  // host copies of the per-tile segment offsets (create time only)
@@ -934,6 +935,8 @@ int pdenlp_create(const pdenlp_desc* desc, pdenlp_model** out) {
   m->dm.fsum = m->scalar;
   m->dm.fsum_host = nullptr;
   { double* hd = nullptr; if (cudaHostGetDevicePointer((void**)&hd, m->scalar_host, 0) == cudaSuccess) m->dm.fsum_host = hd; }
+  if (cudaEventCreateWithFlags(&m->ev_switch, cudaEventDisableTiming) != cudaSuccess)
+    return bail(fail(PDENLP_ECUDA, "cudaEventCreate failed"));
   if (cudaEventCreate(&m->ev0) != cudaSuccess || cudaEventCreate(&m->ev1) != cudaSuccess)
     return bail(fail(PDENLP_ECUDA, "cudaEventCreate failed"));
   if ((rc = classify_tiles(m, *desc))) return bail(rc);
@@ -972,6 +975,7 @@ int pdenlp_destroy(pdenlp_model* m) {
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
   if (m->scalar_host) cudaFreeHost(m->scalar_host);
+  if (m->ev_switch) cudaEventDestroy(m->ev_switch);
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
   if (m->ev_join) cudaEventDestroy(m->ev_join);
   if (m->aux) { cudaStreamSynchronize(m->aux); cudaStreamDestroy(m->aux); }
@@ -988,7 +992,24 @@ int pdenlp_get_info(const pdenlp_model* m, pdenlp_info* info) {
 }
 int pdenlp_set_stream(pdenlp_model* m, void* s) {
   if (!m) return fail(PDENLP_EINVAL, "null model");
-  m->stream = (cudaStream_t)s;
+  cudaStream_t ns = (cudaStream_t)s;
+  if (ns != m->stream) {
+    // Model-owned scratch (cached template images, partials, staging buffers) may still be in use by work enqueued on
+    // the previous stream: the new stream waits for it (an event, no host synchronisation).  Skipped while either
+    // stream is being captured: a capture starts from quiescent streams, and an event wait across a capture boundary
+    // is not legal.
+    cudaStreamCaptureStatus so = cudaStreamCaptureStatusNone, sn = cudaStreamCaptureStatusNone;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != m->device) cudaSetDevice(m->device);
+    if (cudaStreamIsCapturing(m->stream, &so) != cudaSuccess) { cudaGetLastError(); so = cudaStreamCaptureStatusNone; }
+    if (cudaStreamIsCapturing(ns, &sn) != cudaSuccess) { cudaGetLastError(); sn = cudaStreamCaptureStatusNone; }
+    if (so == cudaStreamCaptureStatusNone && sn == cudaStreamCaptureStatusNone && m->ev_switch &&
+        cudaEventRecord(m->ev_switch, m->stream) == cudaSuccess)
+      cudaStreamWaitEvent(ns, m->ev_switch, 0);
+    if (prev != m->device && prev >= 0) cudaSetDevice(prev);
+  }
+  m->stream = ns;
   return PDENLP_OK;
 }
 int pdenlp_sync(pdenlp_model* m) {
