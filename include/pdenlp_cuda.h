@@ -378,6 +378,10 @@ int pdenlp_last_kernel_ms(pdenlp_model* m, float* ms);
    stats[1] = template cells (copied from the image), stats[2] = generic cells (evaluated one by one), stats[3] = images
    built so far; all 0 when the model evaluates every cell (no template path, small slab, PDENLP_FLAG_NO_TEMPLATES) */
 int pdenlp_template_stats(const pdenlp_model* m, int64_t stats[4]);
+/* jac_coord! / hess_coord! of small models with kappa blocks are chains of short launches; from the second call with
+   the same (x, lambda, vals, obj_weight, stream) on they are replayed as one CUDA graph (device memory space only; the
+   contents of x / lambda are read at replay time; PDENLP_NO_GRAPHS=1 disables).  Number of replays so far: */
+int pdenlp_graph_replays(const pdenlp_model* m, int64_t* replays);
 int pdenlp_set_timing(pdenlp_model* m, int32_t enabled);
 
 #ifdef __cplusplus

@@ -30,7 +30,7 @@ SYMBOLS = [
     "pdenlp_obj", "pdenlp_objgrad", "pdenlp_objcons", "pdenlp_grad", "pdenlp_cons", "pdenlp_jac_coord", "pdenlp_hess_coord", "pdenlp_hess_coord_obj",
     "pdenlp_jprod", "pdenlp_jtprod", "pdenlp_hprod", "pdenlp_jac_structure", "pdenlp_hess_structure", "pdenlp_input_ranges",
     "pdenlp_sharded_create", "pdenlp_sharded_destroy", "pdenlp_sharded_get_info", "pdenlp_sharded_slab", "pdenlp_sharded_obj", "pdenlp_sharded_grad", "pdenlp_sharded_cons", "pdenlp_sharded_jac_coord", "pdenlp_sharded_hess_coord", "pdenlp_sharded_jprod", "pdenlp_sharded_jtprod", "pdenlp_sharded_hprod", "pdenlp_sharded_jac_structure", "pdenlp_sharded_hess_structure",
-    "pdenlp_selfcheck_error", "pdenlp_launch_count", "pdenlp_template_stats", "pdenlp_last_kernel_ms", "pdenlp_set_timing",
+    "pdenlp_selfcheck_error", "pdenlp_launch_count", "pdenlp_template_stats", "pdenlp_graph_replays", "pdenlp_last_kernel_ms", "pdenlp_set_timing",
     "pdenlp_compaction_create", "pdenlp_compaction_destroy", "pdenlp_compaction_nnz",
     "pdenlp_compaction_structure", "pdenlp_compaction_apply",
 ]
@@ -132,6 +132,7 @@ def load():
     lib.pdenlp_sharded_hess_structure.argtypes = [vp, vp, vp]
     lib.pdenlp_launch_count.argtypes = [vp, C.POINTER(i64)]
     lib.pdenlp_template_stats.argtypes = [vp, C.POINTER(i64)]
+    lib.pdenlp_graph_replays.argtypes = [vp, C.POINTER(i64)]
     lib.pdenlp_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.pdenlp_set_timing.argtypes = [vp, C.c_int32]
     lib.pdenlp_compaction_create.argtypes = [i64, vp, vp, i64, i64, C.c_int32, C.c_int32, C.POINTER(vp)]
@@ -376,6 +377,11 @@ class Handle:
         st = (C.c_int64 * 4)()
         check(load().pdenlp_template_stats(self._h, st))
         return {"chunks": st[0], "template_cells": st[1], "generic_cells": st[2], "image_builds": st[3]}
+
+    def graph_replays(self) -> int:
+        n = C.c_int64()
+        check(load().pdenlp_graph_replays(self._h, C.byref(n)))
+        return n.value
 
     def selfcheck_error(self) -> float:
         e = C.c_double()

@@ -86,6 +86,15 @@ struct pdenlp_model {
   // kernels of jac_coord! / hess_coord! run there, concurrently with the chunk copy on the caller's stream
   cudaStream_t aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // replay cache of the multi-launch coordinate callbacks of SMALL models (see graph_call)
+  struct GraphEntry {
+    int cb = 0; const void *x = nullptr, *lam = nullptr, *vals = nullptr; double ow = 0.0; cudaStream_t stream = nullptr;
+    cudaGraphExec_t exec = nullptr; int64_t launches = 0; bool failed = false; uint64_t used = 0;
+  };
+  std::vector<GraphEntry> graphs;
+  uint64_t graph_clock = 0;
+  cudaStream_t cap = nullptr;  // private capture stream
+  int64_t graph_replays = 0;
   cudaEvent_t ev_switch = nullptr;  // orders a new caller stream behind the previous one (pdenlp_set_stream)
   std::vector<int64_t> ch_cell0_h, ch_jy_h, ch_ju_h, ch_h_h;
   std::vector<int32_t> gc_cell_h;
@@ -975,6 +984,8 @@ int pdenlp_destroy(pdenlp_model* m) {
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
   if (m->scalar_host) cudaFreeHost(m->scalar_host);
+  for (auto& g : m->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (m->cap) cudaStreamDestroy(m->cap);
   if (m->ev_switch) cudaEventDestroy(m->ev_switch);
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
   if (m->ev_join) cudaEventDestroy(m->ev_join);
@@ -1138,8 +1149,7 @@ int pdenlp_hprod(pdenlp_model* m, const double* x, const double* lambda, double 
   return vec_call(m, OP_HPROD, x, lambda, v, m ? m->info.nvar : 0, obj_weight, Hv, m ? m->info.nvar : 0, m && m->ops->needs_coef_deriv());
 }
 
-int pdenlp_jac_coord(pdenlp_model* m, const double* x, double* vals) {
-  if (!m || !x || !vals) return fail(PDENLP_EINVAL, "null argument");
+static int jac_coord_body(pdenlp_model* m, const double* x, double* vals) {
   Scope sc(m);
   const double* dx;
   double* dv;
@@ -1172,8 +1182,7 @@ int pdenlp_jac_coord(pdenlp_model* m, const double* x, double* vals) {
   return out_finish(m, vals, m->info.nnzj);
 }
 
-int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda, double obj_weight, double* vals) {
-  if (!m || !x || !vals) return fail(PDENLP_EINVAL, "null argument");
+static int hess_coord_body(pdenlp_model* m, const double* x, const double* lambda, double obj_weight, double* vals) {
   Scope sc(m);
   const double *dx, *dl;
   double* dv;
@@ -1253,6 +1262,99 @@ int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda, do
   fk.join();
   if (host_tail) return out_finish_zero_tail(m, vals, I.nnzh - I.nnzh_fe, I.nnzh_fe);
   return out_finish(m, vals, I.nnzh);
+}
+
+// Replay cache.  jac_coord! / hess_coord! of a SMALL model with kappa blocks are chains of 4-9 stream operations (memsets,
+// kappa kernels and their second passes on the auxiliary stream, the FE kernel, event fork / join) of 5-35 us each: the
+// callback takes as long as the CPU needs to submit them (config 4 hess_coord!: 68 us for 45 us of kernels).  The second
+// call with the same (callback, x, lambda, vals, obj_weight, stream) captures the chain into a CUDA graph; later calls
+// replay it with one launch.  Pointers and obj_weight are baked into the nodes, the CONTENTS of x / lambda are read at
+// replay time.  Only device-memspace models without templates (whose image cache is host state) and without timing
+// brackets; never while the caller's stream is itself being captured.  PDENLP_NO_GRAPHS=1 turns it off.
+}  // extern "C"  (graph_call is a template: no C linkage)
+
+static bool graph_eligible(pdenlp_model* m) {
+  static const bool off = getenv("PDENLP_NO_GRAPHS") != nullptr;
+  if (off || m->d.memspace != PDENLP_MEM_DEVICE || m->timing || m->tpl_active || m->aux == nullptr || m->nofe) return false;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(m->stream, &st) != cudaSuccess) { cudaGetLastError(); return false; }
+  return st == cudaStreamCaptureStatusNone;
+}
+template <class Body>
+static int graph_call(pdenlp_model* m, int cb, const void* x, const void* lam, const void* vals, double ow, Body&& body) {
+  using GE = pdenlp_model::GraphEntry;
+  GE* e = nullptr;
+  for (auto& g : m->graphs)
+    if (g.cb == cb && g.x == x && g.lam == lam && g.vals == vals && g.ow == ow && g.stream == m->stream) { e = &g; break; }
+  m->graph_clock += 1;
+  if (e == nullptr) {  // first sight of this argument set: run it plainly (one-time attribute / occupancy queries happen here)
+    if (m->graphs.size() >= 8) {
+      size_t old = 0;
+      for (size_t k = 1; k < m->graphs.size(); ++k) if (m->graphs[k].used < m->graphs[old].used) old = k;
+      if (m->graphs[old].exec) cudaGraphExecDestroy(m->graphs[old].exec);
+      m->graphs.erase(m->graphs.begin() + old);
+    }
+    GE g;
+    g.cb = cb; g.x = x; g.lam = lam; g.vals = vals; g.ow = ow; g.stream = m->stream; g.used = m->graph_clock;
+    m->graphs.push_back(g);
+    return body();
+  }
+  e->used = m->graph_clock;
+  if (e->failed) return body();
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (prev != m->device) cudaSetDevice(m->device);
+  int rc = PDENLP_OK;
+  if (e->exec == nullptr) {  // second call: capture
+    const int64_t l0 = m->launches;
+    // captured on a private stream (the caller's may be the legacy default stream, which cannot be captured); the
+    // graph is then launched into the caller's stream
+    cudaStream_t user = m->stream;
+    if (m->cap == nullptr && cudaStreamCreateWithFlags(&m->cap, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); m->cap = nullptr; }
+    if (m->cap == nullptr || cudaStreamBeginCapture(m->cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      e->failed = true;
+      rc = body();
+    } else {
+      m->stream = m->cap;
+      rc = body();
+      m->stream = user;
+      cudaGraph_t g = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(m->cap, &g);
+      if (rc == PDENLP_OK && ce == cudaSuccess && g != nullptr && cudaGraphInstantiate(&e->exec, g, 0) == cudaSuccess) {
+        e->launches = m->launches - l0;
+      } else {  // not capturable here: remember, and do the work the plain way
+        cudaGetLastError();
+        e->exec = nullptr;
+        e->failed = true;
+        m->launches = l0;
+        if (rc == PDENLP_OK) rc = body();
+      }
+      if (g) cudaGraphDestroy(g);
+      if (e->exec) m->launches = l0;  // (counted below, per replay)
+    }
+  }
+  if (rc == PDENLP_OK && e->exec != nullptr) {
+    if (cudaGraphLaunch(e->exec, m->stream) != cudaSuccess) rc = fail(PDENLP_ECUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(cudaGetLastError()));
+    else { m->launches += e->launches; m->graph_replays += 1; }
+  }
+  if (prev != m->device && prev >= 0) cudaSetDevice(prev);
+  return rc;
+}
+
+extern "C" {
+
+int pdenlp_jac_coord(pdenlp_model* m, const double* x, double* vals) {
+  if (!m || !x || !vals) return fail(PDENLP_EINVAL, "null argument");
+  if (m->info.nnzj_k > 0 && graph_eligible(m))
+    return graph_call(m, 1, x, nullptr, vals, 0.0, [&] { return jac_coord_body(m, x, vals); });
+  return jac_coord_body(m, x, vals);
+}
+int pdenlp_hess_coord(pdenlp_model* m, const double* x, const double* lambda, double obj_weight, double* vals) {
+  if (!m || !x || !vals) return fail(PDENLP_EINVAL, "null argument");
+  if (m->info.nnzh_k_obj + m->info.nnzh_k_con > 0 && graph_eligible(m))
+    return graph_call(m, 2, x, lambda, vals, obj_weight, [&] { return hess_coord_body(m, x, lambda, obj_weight, vals); });
+  return hess_coord_body(m, x, lambda, obj_weight, vals);
 }
 
 // objective part only, vals[nnzh_obj]: the whole Hessian of a model whose operator is affine
@@ -1373,6 +1475,11 @@ int pdenlp_template_stats(const pdenlp_model* m, int64_t stats[4]) {
   stats[1] = m->cg_active ? m->ntpl_cells : 0;
   stats[2] = m->cg_active ? m->dm.ngc : 0;
   stats[3] = m->tpl_builds;
+  return PDENLP_OK;
+}
+int pdenlp_graph_replays(const pdenlp_model* m, int64_t* replays) {
+  if (!m || !replays) return fail(PDENLP_EINVAL, "null argument");
+  *replays = m->graph_replays;
   return PDENLP_OK;
 }
 int pdenlp_set_timing(pdenlp_model* m, int32_t enabled) {

@@ -358,3 +358,39 @@ def test_callbacks_can_be_captured_in_a_cuda_graph(pkg, cuda_lib, case):
         assert not torch.isnan(hv).any() and not torch.isnan(jv).any()
     assert torch.allclose(g, nlp.grad(x2), rtol=1e-13, atol=1e-15) and torch.allclose(c, nlp.cons(x2), rtol=1e-13, atol=1e-15)
     nlp.close()
+
+
+@pytest.mark.parametrize("case", ["burger1d_param", "poissonmixed2d", "poissonmixed2"])
+def test_graph_replay_of_small_kappa_models_matches_plain_calls(pkg, cuda_lib, case):
+    """Small models with kappa blocks replay jac_coord! / hess_coord! as one CUDA graph from the second call with the
+    same buffers on (include/pdenlp_cuda.h: pdenlp_graph_replays).  The replays must read the CURRENT contents of x and
+    lambda and equal a model that never replays (fresh buffers every call): FE segments bit for bit, kappa blocks
+    (atomic sums) to round-off; a different obj_weight or buffer is a different graph."""
+    from pdenlp_b200.model import GridapPDENLPModel
+    spec = {"burger1d_param": lambda: pkg.burger1d_param(20000), "poissonmixed2d": lambda: pkg.poissonmixed(40, 2, True),
+            "poissonmixed2": lambda: pkg.poissonmixed2(40)}[case]()
+    a = GridapPDENLPModel(spec, device="cuda:0")
+    b = GridapPDENLPModel(spec, device="cuda:0")
+    I = a.handle.info
+    rng = np.random.default_rng(11)
+    x = torch.empty(a.meta.nvar, dtype=torch.float64, device="cuda")
+    lam = torch.empty(a.meta.ncon, dtype=torch.float64, device="cuda")
+    jv = torch.empty(a.meta.nnzj, dtype=torch.float64, device="cuda")
+    hv = torch.empty(a.meta.nnzh, dtype=torch.float64, device="cuda")
+    nk = int(I.nnzj_k)
+    for it in range(5):
+        xh = rng.uniform(-1, 1, a.meta.nvar); xh[: spec.nparam] = 1 + 0.1 * rng.uniform(-1, 1, spec.nparam)
+        lh = rng.uniform(-1, 1, a.meta.ncon)
+        x.copy_(torch.from_numpy(xh)); lam.copy_(torch.from_numpy(lh))
+        ow = 0.37 if it % 2 else 1.0
+        jv.fill_(float("nan")); hv.fill_(float("nan"))
+        a.jac_coord_(x, jv); a.hess_coord_(x, lam, hv, obj_weight=ow)
+        jr = b.jac_coord(x.clone()); hr = b.hess_coord(x.clone(), lam.clone(), obj_weight=ow)   # fresh buffers: never replayed
+        torch.cuda.synchronize()
+        assert torch.equal(jv[nk:], jr[nk:])
+        assert torch.allclose(jv, jr, rtol=1e-12, atol=1e-14 * float(jr.abs().max()))
+        assert torch.allclose(hv, hr, rtol=1e-12, atol=1e-14 * float(hr.abs().max()))
+        assert not torch.isnan(jv).any() and not torch.isnan(hv).any()
+    # (b may replay too when the caching allocator hands a freed buffer back at the same address: equally valid)
+    assert a.handle.graph_replays() >= 5, a.handle.graph_replays()
+    a.close(); b.close()
