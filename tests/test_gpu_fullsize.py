@@ -346,3 +346,32 @@ def test_template_path_equals_cell_by_cell_evaluation_for_every_element_family(p
             same(a.hess_coord(x, obj_weight=ow), b.hess_coord(x, obj_weight=ow), [(0, ko)])
     finally:
         a.close(); b.close()
+
+
+@pytest.mark.parametrize("family", ["membrane_q2q1_nq1", "kappa_poisson2d_control"])
+def test_template_path_through_the_host_memory_space(pkg, cuda_lib, family):
+    """PDENLP_MEM_HOST handles (the Julia stub's default: host vectors staged by the library) at a template-active size:
+    same numbers as the device-memspace model, including the structurally zero tail that host threads fill."""
+    from pdenlp_b200.model import GridapPDENLPModel
+    spec = TEMPLATE_FAMILIES[family](pkg)
+    d = GridapPDENLPModel(spec, device="cuda:0")
+    h = GridapPDENLPModel(spec, device="cuda:0", flat=d.flat, memspace="host")
+    try:
+        assert h.handle.template_stats()["chunks"] > 0
+        rng = np.random.default_rng(9)
+        x = rng.uniform(-1, 1, d.meta.nvar)
+        if spec.nparam:
+            x[: spec.nparam] = 1 + 0.1 * rng.uniform(-1, 1, spec.nparam)
+        lam = rng.uniform(-1, 1, d.meta.ncon)
+        xd, ld = torch.from_numpy(x).cuda(), torch.from_numpy(lam).cuda()
+        I = d.handle.info
+        nk = int(I.nnzj_k)
+        for rep in range(2):  # (second pass: cached images)
+            jh, jd = h.jac_coord(x), d.jac_coord(xd).cpu().numpy()
+            assert np.array_equal(jh[nk:], jd[nk:]) and np.allclose(jh[:nk], jd[:nk], rtol=1e-12, atol=1e-14)
+            hh, hd = h.hess_coord(x, lam, obj_weight=0.37), d.hess_coord(xd, ld, obj_weight=0.37).cpu().numpy()
+            ko, kc, fo = int(I.nnzh_k_obj), int(I.nnzh_k_con), int(I.nnzh_fe_obj)
+            assert np.array_equal(hh[ko: ko + fo], hd[ko: ko + fo]) and np.array_equal(hh[ko + fo + kc:], hd[ko + fo + kc:])
+            assert np.allclose(hh, hd, rtol=1e-12, atol=1e-14 * np.abs(hd).max())
+    finally:
+        d.close(); h.close()
