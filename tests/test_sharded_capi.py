@@ -74,3 +74,34 @@ def test_sharded_handle_matches_the_oracle(pkg):
         ro, co = orc.hess_structure() if hess else orc.jac_structure()
         assert np.array_equal(r, ro) and np.array_equal(c, co)
     h.close()
+
+
+@pytest.mark.gpu
+def test_sharded_handle_at_a_template_active_size_equals_the_single_device_model(pkg, cuda_lib):
+    """pdenlp_sharded_* (one process, one slab per device, host vectors) on slabs large enough for the cell-granular
+    template path (>= 4096 tiles per slab): global jac_coord! / hess_coord! streams equal the single-device model's —
+    FE segments bit for bit, the dense kappa blocks (host-side sums of slab partials) to round-off."""
+    import torch
+    from pdenlp_b200.capi import ShardedHandle
+    from pdenlp_b200.flatten import flatten
+    from pdenlp_b200.model import GridapPDENLPModel
+    ndev = min(2, torch.cuda.device_count())
+    spec = pkg.poissonmixed(64 if ndev == 1 else 80, 3, True)   # 262 144 / 512 000 cells
+    fm = flatten(spec)
+    h = ShardedHandle(fm, ndev)
+    d = GridapPDENLPModel(spec, device="cuda:0", flat=fm)
+    try:
+        I = d.handle.info
+        g = np.random.default_rng(13)
+        x = g.uniform(-1, 1, d.meta.nvar); x[: spec.nparam] = 1 + 0.1 * g.uniform(-1, 1, spec.nparam)
+        lam = g.uniform(-1, 1, d.meta.ncon)
+        xd, ld = torch.from_numpy(x).cuda(), torch.from_numpy(lam).cuda()
+        nk = int(I.nnzj_k)
+        jh, jd = h.jac_coord(x), d.jac_coord(xd).cpu().numpy()
+        assert np.array_equal(jh[nk:], jd[nk:]) and np.allclose(jh[:nk], jd[:nk], rtol=1e-11, atol=1e-13 * np.abs(jd[:nk]).max())
+        hh, hd = h.hess_coord(x, lam, 0.37), d.hess_coord(xd, ld, obj_weight=0.37).cpu().numpy()
+        ko, kc, fo = int(I.nnzh_k_obj), int(I.nnzh_k_con), int(I.nnzh_fe_obj)
+        assert np.array_equal(hh[ko: ko + fo], hd[ko: ko + fo]) and np.array_equal(hh[ko + fo + kc:], hd[ko + fo + kc:])
+        assert np.allclose(hh, hd, rtol=1e-11, atol=1e-13 * np.abs(hd).max())
+    finally:
+        h.close(); d.close()
