@@ -492,6 +492,7 @@ def main():
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     launches = nlp.launch_count() - launches0
+    tpl_stats["image_builds_after_timed_region"] = nlp.handle.template_stats()["image_builds"]
     total_ms = ev[0].elapsed_time(ev[2 * args.steps])
     jac_ms = float(np.mean([ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps)]))
     hess_ms = float(np.mean([ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(args.steps)]))
