@@ -533,6 +533,33 @@ def main():
     # spot-check the result against size-independent properties before reporting
     assert torch.isfinite(jvals[:: max(1, info.nnzj // 100003)]).all()
 
+    # the same step with every cell evaluated by the generic kernels (PDENLP_FLAG_NO_TEMPLATES): what the template path
+    # is worth, and the rate of the evaluate-every-cell path, in the same run (N = 1 only; 20 steps)
+    generic = None
+    if world == 1:
+        try:
+            g = GridapPDENLPModel(spec, device=dev, flat=fm, with_coef=False, templates=False)
+            for _ in range(3):
+                g.jac_coord_(x, jvals); g.hess_coord_(x, lam, hvals, obj_weight=1.0)
+            ge = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ge[0].record(stream)
+            for _ in range(20):
+                g.jac_coord_(x, jvals)
+            ge[1].record(stream)
+            for _ in range(20):
+                g.hess_coord_(x, lam, hvals, obj_weight=1.0)
+            ge[2].record(stream)
+            torch.cuda.synchronize()
+            gj, gh = ge[0].elapsed_time(ge[1]) / 20, ge[1].elapsed_time(ge[2]) / 20
+            generic = {"jac_ms": gj, "hess_ms": gh, "ms_per_step": gj + gh, "value": ncell / ((gj + gh) * 1e-3), "unit": UNIT,
+                       "what": "PDENLP_FLAG_NO_TEMPLATES: k_jac_coord / k_hess_coord evaluate every cell (staged TMA stores)",
+                       "frac_of_copy_peak": (b_jac + b_hess) / ((gj + gh) * 1e-3) / 1e9 / peak}
+            g.close()
+            nlp.jac_coord_(x, jvals)  # (restore the template path's values for the checks below)
+            torch.cuda.synchronize()
+        except Exception as exc:  # noqa: BLE001
+            generic = {"error": str(exc)[:200]}
+
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(args, spec, fm, dev, world, rank, ncell, torch, dist)
@@ -597,6 +624,8 @@ def main():
             line["e2e"] = e2e
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if generic is not None:
+            line["every_cell_evaluated"] = generic
         if others:
             line["other_configs"] = others
         from pdenlp_b200 import capi
