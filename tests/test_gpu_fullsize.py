@@ -375,3 +375,42 @@ def test_template_path_through_the_host_memory_space(pkg, cuda_lib, family):
             assert np.allclose(hh, hd, rtol=1e-12, atol=1e-14 * np.abs(hd).max())
     finally:
         d.close(); h.close()
+
+
+@pytest.mark.parametrize("family", ["membrane_q2q1_nq1", "kappa_poisson3d_control"])
+@pytest.mark.parametrize("shift", [0, 1, 3])
+def test_template_path_writes_exactly_its_output_range(pkg, cuda_lib, family, shift):
+    """Guard bands: the value arrays are views into larger NaN-filled buffers, starting `shift` doubles into them (an odd
+    shift makes every 16 B-aligned store of the chunk copy start one element late: head / tail paths).  Nothing outside
+    [0, nnz) may be written, nothing inside may stay unwritten, and the values do not depend on the alignment."""
+    from pdenlp_b200.model import GridapPDENLPModel
+    spec = TEMPLATE_FAMILIES[family](pkg)
+    nlp = GridapPDENLPModel(spec, device="cuda:0")
+    try:
+        assert nlp.handle.template_stats()["chunks"] > 0
+        rng = np.random.default_rng(21)
+        xh = rng.uniform(-1, 1, nlp.meta.nvar)
+        if spec.nparam:
+            xh[: spec.nparam] = 1 + 0.1 * rng.uniform(-1, 1, spec.nparam)
+        x = torch.from_numpy(xh).cuda()
+        lam = torch.from_numpy(rng.uniform(-1, 1, nlp.meta.ncon)).cuda()
+        pad = 4096
+        ref_j, ref_h = nlp.jac_coord(x), nlp.hess_coord(x, lam, obj_weight=0.37)
+        I = nlp.handle.info
+        for nnz, call, ref, dense in ((nlp.meta.nnzj, lambda v: nlp.jac_coord_(x, v), ref_j, [(0, int(I.nnzj_k))]),
+                                      (nlp.meta.nnzh, lambda v: nlp.hess_coord_(x, lam, v, obj_weight=0.37), ref_h,
+                                       [(0, int(I.nnzh_k_obj)), (int(I.nnzh_obj), int(I.nnzh_obj) + int(I.nnzh_k_con))])):
+            buf = torch.full((nnz + 2 * pad + 8,), float("nan"), dtype=torch.float64, device="cuda")
+            view = buf[pad + shift: pad + shift + nnz]
+            call(view)
+            torch.cuda.synchronize()
+            assert torch.isnan(buf[: pad + shift]).all() and torch.isnan(buf[pad + shift + nnz:]).all(), "wrote outside its range"
+            assert not torch.isnan(view).any(), "left entries unwritten"
+            mask = torch.ones(nnz, dtype=torch.bool, device="cuda")
+            for lo, hi in dense:
+                mask[lo:hi] = False
+            assert torch.equal(view[mask], ref[mask])
+            assert torch.allclose(view, ref, rtol=1e-12, atol=1e-14 * float(ref.abs().max()))
+            del buf
+    finally:
+        nlp.close()
