@@ -52,22 +52,19 @@ def _host_cores() -> int:
 NCU_SUMMARY = os.path.join("profiles", "r02_final_ncu_summary.json")
 
 
-def _ncu_traffic(n, world, kernel="k_copy_chunks", nth_largest=0):
+def _ncu_traffic(n, world, kernel="k_copy_chunks", expect_bytes=None):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed `ncu --set full`
     capture of this workload (NCU_SUMMARY, one entry per launch); only valid for the captured workload.  A kernel
-    that runs several times per step with different sizes (k_copy_chunks: jac_coord! writes more than hess_coord!)
-    is picked by size: nth_largest = 0 is the launch with the most traffic."""
+    that runs several times per step with different sizes (k_copy_chunks: once per coordinate callback) is picked by
+    size: the launch whose traffic is closest to `expect_bytes` (default: the largest)."""
     if n != 2048 or world != 1:
         return None
     try:
         with open(os.path.join(ROOT, NCU_SUMMARY)) as fh:
             d = sorted({int(e["traffic_bytes_per_launch"]) for e in json.load(fh) if kernel in e.get("Kernel Name", "")}, reverse=True)
-        # (launches of the same callback repeat with the same size up to DRAM-counter noise: keep sizes > 5 % apart)
-        distinct = []
-        for t in d:
-            if not distinct or t < 0.95 * distinct[-1]:
-                distinct.append(t)
-        return distinct[nth_largest]
+        if not d:
+            return None
+        return d[0] if expect_bytes is None else min(d, key=lambda t: abs(t - expect_bytes))
     except Exception:
         return None
 
@@ -505,8 +502,8 @@ def main():
 
     # Roofline on THIS rank's slab.  jac_coord! = k_copy_chunks over the y- and u-block chunks (the dominant kernel of
     # the step: 41 % of its bytes; pure 16 B stores from the template image) beside k_jac_cells_cg (the 0.2 % boundary
-    # cells, auxiliary stream); hess_coord! = k_hess_cells_cg + k_copy_chunks on the objective FE block + k_zero_fill of
-    # the constraint FE block (the membrane residual is affine, so that block is structurally zero).
+    # cells); hess_coord! = k_hess_cells_cg + k_copy_chunks on the objective FE block, whose last CTAs zero-fill the
+    # constraint FE block (the membrane residual is affine, so that block is structurally zero).
     peak, peak_src = _peaks()
     b_jac, b_hess = algorithmic_bytes(info, fm)
     # (rank 0's slab bytes over the slowest rank's launch time: conservative for N > 1)
@@ -596,15 +593,14 @@ def main():
                 "jac_ms": jac_ms_max, "hess_ms": hess_ms_max,
                 "bound": "hbm", "kernel": "k_copy_chunks (jac_coord!: chunks of the y- and u-block; k_jac_cells_cg runs beside it)",
                 "achieved": ach_jac, "peak": peak, "unit": "GB/s",
-                "frac": ach_jac / peak, "traffic": _ncu_traffic(args.n, world, "k_copy_chunks", 0), "peak_source": peak_src,
+                "frac": ach_jac / peak, "traffic": _ncu_traffic(args.n, world, "k_copy_chunks", 8 * int(info.nnzj)), "peak_source": peak_src,
                 "traffic_source": NCU_SUMMARY,
                 "algorithmic_bytes_per_launch": int(b_jac), "launch_ms": jac_ms,
                 "launch_ms_note": "duration of the jac_coord! callback (CUDA events around it): the copy kernel and the concurrent boundary-cell kernel",
                 "hess_callback": {
-                    "launches": "k_hess_cells_cg (boundary cells, auxiliary stream) + k_copy_chunks (objective FE block) + k_zero_fill (constraint FE block, structurally zero)",
+                    "launches": "k_hess_cells_cg (boundary cells) + k_copy_chunks (objective FE block; the last CTAs of the same launch zero-fill the structurally zero constraint FE block)",
                     "achieved": ach_hess, "frac": ach_hess / peak, "algorithmic_bytes_per_callback": int(b_hess),
-                    "callback_ms": hess_ms, "k_copy_chunks_traffic": _ncu_traffic(args.n, world, "k_copy_chunks", 1),
-                    "k_zero_fill_traffic": _ncu_traffic(args.n, world, "k_zero_fill", 0),
+                    "callback_ms": hess_ms, "k_copy_chunks_traffic": _ncu_traffic(args.n, world, "k_copy_chunks", 8 * int(info.nnzh)),
                 },
                 "step": {"achieved": ach_step, "frac": ach_step / peak},
                 "write_stream": {

@@ -1738,9 +1738,25 @@ struct ChunkSeg {
 // (same stream, disjoint outputs).  That kernel started only after the image was complete, so this one need not wait
 // for it before copying; ONE thread waits at the end, so that the completion of this grid implies the completion of
 // its predecessor (the k_zero_fill protocol).  Both run concurrently without an event fork / join.
-static __global__ void __launch_bounds__(kThreads) k_copy_chunks(ChunkSeg a, ChunkSeg b, const ChunkRec* __restrict__ ch, int which, int chained) {
+// CTAs [nchunk, gridDim.x) zero-fill fillp[0, filln) — the structurally zero constraint FE block of hess_coord! — one
+// 16 KB page each, like k_zero_fill: one launch for both streams of the callback.
+static __global__ void __launch_bounds__(kThreads) k_copy_chunks(ChunkSeg a, ChunkSeg b, const ChunkRec* __restrict__ ch, int which, int chained,
+                                                                 int nchunk, double* __restrict__ fillp, int64_t filln) {
   if (!chained) griddep_wait();  // (the image is written by the preceding one-tile launch on the stream)
   griddep_launch_dependents();
+  if ((int)blockIdx.x >= nchunk) {
+    const int64_t head = (filln > 0 && ((reinterpret_cast<uintptr_t>(fillp) >> 3) & 1)) ? 1 : 0;
+    const int64_t n2 = (filln - head) >> 1;
+    double2* q = reinterpret_cast<double2*>(fillp + head);
+    const double2 z = make_double2(0.0, 0.0);
+    const int64_t c = (int64_t)blockIdx.x - nchunk;
+    for (int64_t i = (c << 10) + threadIdx.x; i < min(n2, (c + 1) << 10); i += blockDim.x) q[i] = z;
+    if (c == 0 && threadIdx.x == 0) {
+      if (head) fillp[0] = 0.0;
+      if ((filln - head) & 1) fillp[filln - 1] = 0.0;
+    }
+    return;
+  }
   // the record is two 16 B loads of one sector: both segment offsets are known before the first store
   const longlong2 r0 = __ldg(reinterpret_cast<const longlong2*>(ch + blockIdx.x));
   const longlong2 r1 = __ldg(reinterpret_cast<const longlong2*>(ch + blockIdx.x) + 1);

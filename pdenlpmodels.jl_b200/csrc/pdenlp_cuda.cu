@@ -1244,6 +1244,7 @@ static int hess_coord_body(pdenlp_model* m, const double* x, const double* lambd
   if (cons_zero && !host_tail && !pdl) {
     if (int rc = zero_fill(m, vfc, I.nnzh_fe)) return rc;
   }
+  bool fill_done = false;  // the template path's copy launch also filled the zero block
   double* vo = m->nofe ? nullptr : vfo;  // NoFETerm: the objective has no FE block
   double* vc = cons_zero ? nullptr : vfc;
   if (vo && obj_weight == 0.0) {  // vals .*= obj_weight (GridapPDENLPModel.jl:299): the objective block is a zero fill too
@@ -1254,9 +1255,10 @@ static int hess_coord_body(pdenlp_model* m, const double* x, const double* lambd
     if (vo && !vc) { if (int rc = build_template(m, true, dx, obj_weight)) return rc; }
     L.aux = fk.aux();
     L.chain = !fk.on && !no_chain;
+    if (cons_zero && !host_tail && pdl && vo && !vc) { L.fill_ptr = vfc; L.fill_n = I.nnzh_fe; L.fill_done = &fill_done; }
     if (int rc = m->ops->hess(L, m->dm, dx, dl, obj_weight, vo, vc)) return rc;
   }
-  if (cons_zero && !host_tail && pdl) {
+  if (cons_zero && !host_tail && pdl && !fill_done) {
     if (int rc = zero_fill(m, vfc, I.nnzh_fe, (vo || vc) && !m->ops->is_multi())) return rc;
   }
   fk.join();
